@@ -1,0 +1,199 @@
+/* knpemi_b200.h -- C ABI of the B200-native KNP-EMI timestep library (libknpemi_b200.so).
+ *
+ * The reference (hherlyng/knp-emi-cgx, "CGx") has no FFI boundary of its own: its hot path is a
+ * chain of Python calls into DOLFINx / multiphenicsx / PETSc.  Each entry point below states the
+ * reference call site(s) it replaces (paths relative to /root/reference/src/CGx).  The Python
+ * mirror of the reference classes (knp-emi-cgx_b200/{problem,solver,ionic_models}.py) binds these
+ * with ctypes; INTEGRATION.md shows the stub a CGx maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative KNP_E_* code on error; knp_last_error()
+ *     returns a thread-local message.
+ *   - "host" pointers are plain CPU memory; "dev" pointers are CUDA device memory on the
+ *     context's device.  Nothing here takes or returns a torch type.
+ *   - one context per GPU; a context is not thread-safe; `stream` is a cudaStream_t passed as
+ *     void* (NULL = the context's own stream).
+ *   - unknown ordering is the reference's: field-major blocks
+ *       [Na_i K_i Cl_i phi_i | Na_e K_e Cl_e phi_e], block (s,f) restricted to the vertices of
+ *     subdomain s in ascending vertex order (multiphenicsx DofMapRestriction, owned first).
+ *     Vectors in "column layout" have n_cols = n_rows + n_ghost_cols entries (ghost tail filled by
+ *     the halo exchange); on a single GPU n_cols == n_rows.
+ */
+#ifndef KNPEMI_B200_H
+#define KNPEMI_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KNP_OK 0
+#define KNP_E_INVALID (-1)   /* bad argument / inconsistent mesh */
+#define KNP_E_CUDA (-2)      /* CUDA runtime error */
+#define KNP_E_NOCONV (-3)    /* Krylov solver did not converge / produced non-finite values */
+#define KNP_E_UNSUPPORTED (-4)
+#define KNP_E_NCCL (-5)
+
+typedef struct knp_ctx knp_ctx;
+
+/* ---- membrane model flags (IonicModel subclasses, KNPEMI/KNPEMIx_ionic_model.py) ---- */
+#define KNP_MODEL_PASSIVE     1u   /* PassiveModel            :77-91   */
+#define KNP_MODEL_KIRNA       2u   /* KirNaKPumpModel         :93-222  */
+#define KNP_MODEL_GLIAL_CT    4u   /* GlialCotransporters     :224-298 */
+#define KNP_MODEL_NEURONAL_CT 8u   /* NeuronalCotransporters  :300-369 */
+#define KNP_MODEL_ATP        16u   /* ATPPump                 :371-424 */
+#define KNP_MODEL_HH         32u   /* HodgkinHuxley           :426-515 */
+
+/* Local mesh of one rank (the whole mesh on a single GPU).  Vertices [0,n_owned_vertices) are owned
+ * by this rank, the rest are ghosts; cells = every cell touching an owned vertex.  Replaces the
+ * XDMF read + dS entity ordering of utils/mixed_dim_problem.py:634-733 as *input* to the path. */
+typedef struct {
+  int32_t gdim;                 /* 2 (triangles) or 3 (tetrahedra); P1 elements */
+  int64_t n_vertices;
+  int64_t n_owned_vertices;
+  const double* coords;         /* host, n_vertices x gdim, already scaled (mesh_conversion_factor) */
+  int64_t n_cells;
+  const int32_t* cell_verts;    /* host, n_cells x (gdim+1) */
+  const int32_t* cell_tags;     /* host, n_cells */
+  int32_t n_intra_tags;
+  const int32_t* intra_tags;    /* host */
+  int32_t extra_tag;
+  int64_t n_mfacets;
+  const int32_t* mfacet_verts;  /* host, n_mfacets x gdim : membrane facets (intra/extra interfaces) */
+  const int32_t* mfacet_tags;   /* host, n_mfacets */
+  const uint8_t* cell_owned;    /* host, n_cells or NULL (=all): this rank integrates functionals over the cell */
+  const uint8_t* mfacet_owned;  /* host, n_mfacets or NULL (=all) */
+  int32_t n_quad;               /* facet quadrature rule (degree 10 in the reference, :732-733) */
+  const double* quad_bary;      /* host, n_quad x gdim barycentric points on the facet */
+  const double* quad_w;         /* host, n_quad weights summing to 1 */
+} knp_mesh_desc;
+
+typedef struct {
+  int64_t n_rows, n_cols, nnz, nnz_P;
+  int64_t n_own[2], n_loc[2];   /* restricted dofs per subdomain: owned, owned+ghost */
+  int64_t n_mverts, n_mfacets;
+  int64_t n_cells[2];
+  int32_t max_deg, max_gdeg;
+} knp_sizes;
+
+/* ProblemKNPEMI.setup_constants (KNPEMI/KNPEMIx_problem.py:909-981) + the config keys of
+ * utils/mixed_dim_problem.py:187-356 that enter the forms. */
+typedef struct {
+  double dt, F, R, T, C_M, phi_rest;
+  double z[3], D[3];
+  double g_Na_bar, g_K_bar, g_leak[3], g_leak_g[3];
+  double g_syn_bar, a_syn, T_stim;
+  int32_t scale_stimulus;
+  int32_t stim_dir;             /* -1: no stimulus_region; else axis */
+  double stim_lo, stim_hi;
+  double K_e_init, K_i_g_init;  /* KirNaKPumpModel.E_K_init (:117) */
+  int32_t ode_substeps;         /* HodgkinHuxley time_steps_ODE (:431) */
+  int32_t rush_larsen;          /* use_Rush_Larsen (:430) */
+  double stim_area;             /* global integral of mask over stimulus facets; <=0: computed locally */
+} knp_params;
+
+typedef struct {
+  int32_t tag;
+  uint32_t models;              /* OR of KNP_MODEL_* active on this membrane tag */
+  int32_t stimulated;           /* tag in stimulus_tags (HH adds the synaptic Na current) */
+} knp_tag_models;
+
+/* KSP options of SolverKNPEMI.setup_solver (KNPEMI/KNPEMIx_solver.py:152-295). */
+typedef struct {
+  double rtol;                  /* ksp_rtol, preconditioned residual norm relative to ||B b|| */
+  int32_t max_it;               /* ksp_max_it (5000) */
+  int32_t restart;              /* GMRES restart (PETSc default 30) */
+  int32_t pc;                   /* 0 none, 1 Jacobi(P), 2 smoothed-aggregation AMG V-cycle on P */
+  int32_t project_nullspace;    /* remove the phi-constant nullspace after each PC apply (:324-333) */
+  int32_t zero_mean_solution;   /* direct-solver convention: return the solution with ns^T x = 0 */
+  int32_t refine;               /* extra iterative-refinement restarts for the "direct" mode */
+} knp_solve_opts;
+
+typedef struct {
+  int32_t iterations;
+  int32_t converged;
+  double rnorm0, rnorm;         /* preconditioned ||B b|| and final ||B r|| */
+} knp_solve_info;
+
+const char* knp_last_error(void);
+int knp_version(void);
+
+/* Build the restricted dof maps, CSR pattern (A and block-diagonal P) and all device-side gather maps.
+ * Replaces: DofMapRestriction (KNPEMI/KNPEMIx_problem.py:85-94), create_matrix_block/create_vector_block
+ * (KNPEMI/KNPEMIx_solver.py:157-161) and compute_integration_domains (utils/mixed_dim_problem.py:708-729). */
+int knp_create(knp_ctx** out, const knp_mesh_desc* mesh, int device);
+int knp_destroy(knp_ctx* ctx);
+int knp_get_sizes(const knp_ctx* ctx, knp_sizes* out);
+/* CSR structure of A (device views, borrowed) and host copies for parity checks. */
+int knp_csr_dev(const knp_ctx* ctx, const int32_t** indptr, const int32_t** indices);
+int knp_csr_host(const knp_ctx* ctx, int32_t* indptr, int32_t* indices);
+int knp_csr_P_host(const knp_ctx* ctx, int32_t* indptr, int32_t* indices);
+/* restricted dof -> local vertex id, per subdomain (length n_loc[s]) */
+int knp_dofmap_host(const knp_ctx* ctx, int32_t* verts_intra, int32_t* verts_extra);
+/* membrane vertex table (length n_mverts): local vertex id */
+int knp_mverts_host(const knp_ctx* ctx, int32_t* verts);
+
+int knp_set_params(knp_ctx* ctx, const knp_params* p, int32_t n_tags, const knp_tag_models* tags);
+/* local integral of the stimulus mask over stimulated membrane facets owned by this rank
+ * (HodgkinHuxley._add_stimulus, KNPEMI/KNPEMIx_ionic_model.py:591-598; the caller all-reduces). */
+int knp_stimulus_area_local(knp_ctx* ctx, double* out);
+
+/* State: u = previous solution in column layout (wh[*][*] restricted, KNPEMI/KNPEMIx_problem.py:51),
+ * gates = n,m,h on membrane vertices (3 x n_mverts, KNPEMI/KNPEMIx_ionic_model.py:473-480). */
+int knp_set_state(knp_ctx* ctx, const double* u_host, const double* gates_host);
+int knp_get_state(knp_ctx* ctx, double* u_host, double* gates_host);
+int knp_state_dev(knp_ctx* ctx, double** u_dev, double** gates_dev);
+int knp_phi_m_host(knp_ctx* ctx, double* phi_m_host);     /* phi_i - phi_e on membrane vertices (:462-468) */
+
+/* HodgkinHuxley.update_gating_variables (KNPEMI/KNPEMIx_ionic_model.py:605-671). */
+int knp_gate_step(knp_ctx* ctx, void* stream);
+/* SolverKNPEMI.assemble (KNPEMI/KNPEMIx_solver.py:104-116): A values (nnz) and b (n_rows) from the
+ * current state at time t.  A_vals/b = NULL -> the context's own buffers. */
+int knp_assemble(knp_ctx* ctx, double t, double* A_vals_dev, double* b_dev, void* stream);
+/* assemble_preconditioner (KNPEMI/KNPEMIx_solver.py:118-135) for the block-Jacobi form
+ * (KNPEMI/KNPEMIx_problem.py:717-738). */
+int knp_assemble_P(knp_ctx* ctx, double* P_vals_dev, void* stream);
+int knp_values_dev(knp_ctx* ctx, double** A_vals, double** b, double** P_vals, double** x);
+/* y = A x with the context's CSR pattern (PETSc MatMult inside ksp.solve, :435). x in column layout. */
+int knp_spmv(knp_ctx* ctx, const double* A_vals_dev, const double* x_dev, double* y_dev, void* stream);
+/* KSP/PC setup (ksp.setOperators + ksp.setUp, :386-389): builds the AMG hierarchy from P. */
+int knp_pc_setup(knp_ctx* ctx, const knp_solve_opts* opts);
+/* z = B r : one preconditioner application (hypre V-cycle in the reference). */
+int knp_pc_apply(knp_ctx* ctx, const double* r_dev, double* z_dev, void* stream);
+/* ksp.solve(b, x) (:435) incl. nullspace handling (:297-335). x_dev in/out (column layout). */
+int knp_solve(knp_ctx* ctx, const double* A_vals_dev, const double* b_dev, double* x_dev,
+              const knp_solve_opts* opts, knp_solve_info* info, void* stream);
+/* One pass of the time loop body (:365-468): t += dt, gate update (if any HH tag), assemble,
+ * [nullspace.remove(b) on the first step], solve, u <- x.  Fully device resident. */
+int knp_step(knp_ctx* ctx, const knp_solve_opts* opts, knp_solve_info* info, void* stream);
+/* Same, through host buffers: H2D of (u, gates), step, D2H of (u, gates). Used for the e2e number. */
+int knp_step_host(knp_ctx* ctx, double* u_host, double* gates_host, const knp_solve_opts* opts,
+                  knp_solve_info* info);
+int knp_set_time(knp_ctx* ctx, double t, int32_t step_index);
+int knp_get_time(const knp_ctx* ctx, double* t, int32_t* step_index);
+/* int u^2 dx over the owned share of cells of subdomain s with tag in tags (tests :45-51). */
+int knp_l2_norm_sq(knp_ctx* ctx, int32_t subdomain, int32_t field, int32_t n_tags, const int32_t* tags,
+                   double* out);
+/* per-phase device timers of the last knp_step (ms): gate, facet, rows, solve, total */
+int knp_last_timings(const knp_ctx* ctx, double* ms5);
+
+/* AMG hierarchy inspection for level-by-level parity tests */
+int knp_amg_num_levels(const knp_ctx* ctx);
+int knp_amg_level_sizes(const knp_ctx* ctx, int32_t level, int64_t* n, int64_t* nnz);
+int knp_amg_level_host(const knp_ctx* ctx, int32_t level, int32_t* indptr, int32_t* indices, double* vals);
+
+/* ---- multi-GPU: halo exchange of ghost columns + all-reduce over NCCL (one rank per GPU) ----
+ * Replaces PETSc VecScatter/ghostUpdate and MPI_Allreduce inside KSP (KNPEMI/KNPEMIx_solver.py:435,439,458-468). */
+int knp_nccl_unique_id(char* out128);
+int knp_dist_init(knp_ctx* ctx, int32_t rank, int32_t nranks, const char* unique_id128,
+                  int64_t n_phi_global,                               /* global count of phi_i + phi_e dofs */
+                  int32_t n_peers, const int32_t* peers,
+                  const int64_t* send_ptr, const int32_t* send_cols,   /* owned columns packed per peer */
+                  const int64_t* recv_ptr, const int32_t* recv_cols);  /* ghost columns filled per peer */
+int knp_halo_exchange(knp_ctx* ctx, double* x_dev, void* stream);
+int knp_allreduce_sum(knp_ctx* ctx, double* buf_dev, int32_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

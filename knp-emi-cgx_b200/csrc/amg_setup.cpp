@@ -1,0 +1,354 @@
+// Smoothed-aggregation AMG hierarchy construction (setup time, host, OpenMP).
+//
+// The reference preconditions GMRES with one hypre BoomerAMG V-cycle on the block-diagonal matrix P,
+// which is assembled ONCE (reassemble_P = False; KNPEMIx_solver.py:33-34,118-135,269-273,358-362,386).
+// hypre is a third-party library that is not vendored in the reference; this is our own algorithm:
+// MIS(2) aggregation with deterministic hashed priorities, constant tentative prolongator smoothed by one
+// damped-Jacobi step, Galerkin coarse operators, dense inverse on the coarsest level.  The V-cycle itself
+// (all per-iteration work) runs on the GPU (solver.cu).  oracle/amg.py restates the same algorithm in
+// numpy/scipy and tests compare the two hierarchies level by level.
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+#include "common.cuh"
+
+namespace knp {
+
+static inline int64_t hash32(int64_t i) {
+  uint64_t x = ((uint64_t)i + 0x9E3779B9ull) & 0xFFFFFFFFull;
+  x = ((x ^ (x >> 16)) * 0x85EBCA6Bull) & 0xFFFFFFFFull;
+  x = ((x ^ (x >> 13)) * 0xC2B2AE35ull) & 0xFFFFFFFFull;
+  x = x ^ (x >> 16);
+  return (int64_t)x;
+}
+
+struct Graph {
+  int n = 0;
+  std::vector<int32_t> ptr, idx;
+};
+
+// symmetric strength graph |a_ij| >= theta sqrt(|a_ii a_jj|), i != j, a_ij != 0; symmetrised (S + S^T)
+static void strength_graph(const CsrHost& A, double theta, Graph& S) {
+  const int n = A.n_rows;
+  std::vector<double> d(n, 0.0);
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n; ++i) {
+    double v = 0.0;
+    for (int j = A.indptr[i]; j < A.indptr[i + 1]; ++j)
+      if (A.indices[j] == i) v += A.vals[j];
+    d[i] = std::fabs(v);
+  }
+  // directed strong edges
+  std::vector<int32_t> cnt(n + 1, 0);
+  std::vector<uint8_t> strong(A.indices.size(), 0);
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n; ++i)
+    for (int j = A.indptr[i]; j < A.indptr[i + 1]; ++j) {
+      const int c = A.indices[j];
+      const double v = A.vals[j];
+      if (c != i && v != 0.0 && std::fabs(v) >= theta * std::sqrt(d[i] * d[c])) strong[j] = 1;
+    }
+  // symmetrise: collect (i,c) and (c,i)
+  for (int i = 0; i < n; ++i)
+    for (int j = A.indptr[i]; j < A.indptr[i + 1]; ++j)
+      if (strong[j]) {
+        ++cnt[i + 1];
+        ++cnt[A.indices[j] + 1];
+      }
+  std::vector<int64_t> ptr(n + 1, 0);
+  for (int i = 0; i < n; ++i) ptr[i + 1] = ptr[i] + cnt[i + 1];
+  std::vector<int32_t> tmp(ptr[n]);
+  {
+    std::vector<int64_t> fill(ptr.begin(), ptr.end() - 1);
+    for (int i = 0; i < n; ++i)
+      for (int j = A.indptr[i]; j < A.indptr[i + 1]; ++j)
+        if (strong[j]) {
+          const int c = A.indices[j];
+          tmp[fill[i]++] = c;
+          tmp[fill[c]++] = i;
+        }
+  }
+  S.n = n;
+  S.ptr.assign(n + 1, 0);
+  std::vector<int32_t> ucnt(n);
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n; ++i) {
+    std::sort(tmp.begin() + ptr[i], tmp.begin() + ptr[i + 1]);
+    ucnt[i] = (int32_t)(std::unique(tmp.begin() + ptr[i], tmp.begin() + ptr[i + 1]) - (tmp.begin() + ptr[i]));
+  }
+  for (int i = 0; i < n; ++i) S.ptr[i + 1] = S.ptr[i] + ucnt[i];
+  S.idx.resize(S.ptr[n]);
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n; ++i) std::copy(tmp.begin() + ptr[i], tmp.begin() + ptr[i] + ucnt[i], S.idx.begin() + S.ptr[i]);
+}
+
+static void nbr_max(const Graph& S, const std::vector<int64_t>& key, std::vector<int64_t>& out) {
+  const int n = S.n;
+  out.resize(n);
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n; ++i) {
+    int64_t m = key[i];
+    for (int j = S.ptr[i]; j < S.ptr[i + 1]; ++j) m = std::max(m, key[S.idx[j]]);
+    out[i] = m;
+  }
+}
+
+// MIS(2) aggregation; identical decisions to oracle/amg.py::mis2_aggregate
+static int mis2_aggregate(const Graph& S, std::vector<int32_t>& agg) {
+  const int n = S.n;
+  std::vector<int64_t> pr(n), key(n), k1, k2;
+  std::vector<int8_t> state(n, 0);
+  const int64_t BIG = (int64_t)1 << 62;
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n; ++i) pr[i] = ((hash32(i) & 0x3FFFFFFFll) << 31) | (int64_t)i;
+  while (true) {
+    bool any = false;
+#pragma omp parallel for schedule(static) reduction(|| : any)
+    for (int i = 0; i < n; ++i) {
+      any = any || state[i] == 0;
+      key[i] = state[i] == 1 ? BIG + pr[i] : (state[i] == 0 ? pr[i] : -1);
+    }
+    if (!any) break;
+    nbr_max(S, key, k1);
+    nbr_max(S, k1, k2);
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; ++i)
+      if (state[i] == 0 && k2[i] == key[i]) state[i] = 1;
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; ++i) key[i] = state[i] == 1 ? BIG + pr[i] : -1;
+    nbr_max(S, key, k1);
+    nbr_max(S, k1, k2);
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; ++i)
+      if (state[i] == 0 && k2[i] >= BIG) state[i] = -1;
+  }
+  agg.assign(n, -1);
+  int nroots = 0;
+  for (int i = 0; i < n; ++i)
+    if (state[i] == 1) agg[i] = nroots++;
+  // root priority per node (for joined nodes: priority of their aggregate's root)
+  std::vector<int64_t> rootpr(n, -1);
+  for (int i = 0; i < n; ++i)
+    if (state[i] == 1) rootpr[i] = pr[i];
+  for (int round = 0; round < 2; ++round) {
+    nbr_max(S, rootpr, k1);
+    std::vector<int32_t> newagg(agg);
+    std::vector<int64_t> newpr(rootpr);
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; ++i)
+      if (agg[i] < 0 && k1[i] >= 0) {
+        const int root = (int)(k1[i] & (((int64_t)1 << 31) - 1));
+        newagg[i] = agg[root];
+        newpr[i] = k1[i];
+      }
+    agg.swap(newagg);
+    rootpr.swap(newpr);
+  }
+  int nagg = nroots;
+  for (int i = 0; i < n; ++i)
+    if (agg[i] < 0) agg[i] = nagg++;
+  return nagg;
+}
+
+// C = A * B (CSR, sorted columns out), row-parallel with a dense accumulator per thread
+static void spgemm(const CsrHost& A, const CsrHost& B, CsrHost& C) {
+  const int n = A.n_rows, mcols = B.n_cols;
+  C.n_rows = n;
+  C.n_cols = mcols;
+  C.indptr.assign(n + 1, 0);
+  std::vector<std::vector<int32_t>> rcols(n);
+  std::vector<std::vector<double>> rvals(n);
+#pragma omp parallel
+  {
+    std::vector<double> acc(mcols, 0.0);
+    std::vector<int32_t> mark(mcols, -1), list;
+#pragma omp for schedule(dynamic, 1024)
+    for (int i = 0; i < n; ++i) {
+      list.clear();
+      for (int j = A.indptr[i]; j < A.indptr[i + 1]; ++j) {
+        const int k = A.indices[j];
+        const double a = A.vals[j];
+        for (int l = B.indptr[k]; l < B.indptr[k + 1]; ++l) {
+          const int c = B.indices[l];
+          if (mark[c] != i) {
+            mark[c] = i;
+            acc[c] = 0.0;
+            list.push_back(c);
+          }
+          acc[c] += a * B.vals[l];
+        }
+      }
+      std::sort(list.begin(), list.end());
+      rcols[i] = list;
+      rvals[i].resize(list.size());
+      for (size_t t = 0; t < list.size(); ++t) rvals[i][t] = acc[list[t]];
+    }
+  }
+  for (int i = 0; i < n; ++i) C.indptr[i + 1] = C.indptr[i] + (int32_t)rcols[i].size();
+  C.indices.resize(C.indptr[n]);
+  C.vals.resize(C.indptr[n]);
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n; ++i) {
+    std::copy(rcols[i].begin(), rcols[i].end(), C.indices.begin() + C.indptr[i]);
+    std::copy(rvals[i].begin(), rvals[i].end(), C.vals.begin() + C.indptr[i]);
+  }
+}
+
+static void transpose(const CsrHost& A, CsrHost& At) {
+  const int n = A.n_rows, m = A.n_cols;
+  At.n_rows = m;
+  At.n_cols = n;
+  At.indptr.assign(m + 1, 0);
+  for (size_t j = 0; j < A.indices.size(); ++j) ++At.indptr[A.indices[j] + 1];
+  for (int i = 0; i < m; ++i) At.indptr[i + 1] += At.indptr[i];
+  At.indices.resize(A.indices.size());
+  At.vals.resize(A.indices.size());
+  std::vector<int32_t> fill(At.indptr.begin(), At.indptr.end() - 1);
+  for (int i = 0; i < n; ++i)
+    for (int j = A.indptr[i]; j < A.indptr[i + 1]; ++j) {
+      const int c = A.indices[j];
+      At.indices[fill[c]] = i;
+      At.vals[fill[c]] = A.vals[j];
+      ++fill[c];
+    }
+}
+
+// dense inverse by LU with partial pivoting (coarsest level only; n <= a few thousand)
+static int dense_inverse(int n, std::vector<double>& M, std::vector<double>& inv) {
+  inv.assign((size_t)n * n, 0.0);
+  for (int i = 0; i < n; ++i) inv[(size_t)i * n + i] = 1.0;
+  for (int k = 0; k < n; ++k) {
+    int piv = k;
+    double best = std::fabs(M[(size_t)k * n + k]);
+    for (int i = k + 1; i < n; ++i)
+      if (std::fabs(M[(size_t)i * n + k]) > best) {
+        best = std::fabs(M[(size_t)i * n + k]);
+        piv = i;
+      }
+    if (best == 0.0) {
+      set_error("AMG coarsest-level matrix is singular (column %d)", k);
+      return KNP_E_INVALID;
+    }
+    if (piv != k)
+      for (int j = 0; j < n; ++j) {
+        std::swap(M[(size_t)k * n + j], M[(size_t)piv * n + j]);
+        std::swap(inv[(size_t)k * n + j], inv[(size_t)piv * n + j]);
+      }
+    const double d = 1.0 / M[(size_t)k * n + k];
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; ++i) {
+      if (i == k) continue;
+      const double f = M[(size_t)i * n + k] * d;
+      if (f == 0.0) continue;
+      for (int j = k; j < n; ++j) M[(size_t)i * n + j] -= f * M[(size_t)k * n + j];
+      for (int j = 0; j < n; ++j) inv[(size_t)i * n + j] -= f * inv[(size_t)k * n + j];
+    }
+    for (int j = k; j < n; ++j) M[(size_t)k * n + j] *= d;
+    for (int j = 0; j < n; ++j) inv[(size_t)k * n + j] *= d;
+  }
+  return KNP_OK;
+}
+
+int amg_setup_host(const CsrHost& A0, double theta, int coarse_size, int max_levels, std::vector<CsrHost>& As,
+                   std::vector<CsrHost>& Ps, std::vector<CsrHost>& Rs, std::vector<double>& rhos,
+                   std::vector<double>& coarse_inv) {
+  As.clear();
+  Ps.clear();
+  Rs.clear();
+  rhos.clear();
+  As.push_back(A0);
+  const double omega = 4.0 / 3.0;
+  while (As.back().n_rows > coarse_size && (int)As.size() < max_levels) {
+    const CsrHost& A = As.back();
+    const int n = A.n_rows;
+    Graph S;
+    strength_graph(A, theta, S);
+    std::vector<int32_t> agg;
+    const int nagg = mis2_aggregate(S, agg);
+    if (nagg >= 0.8 * n) break;
+    // Gershgorin bound on rho(D^-1 A) and D^-1
+    std::vector<double> dinv(n);
+    double rho = 0.0;
+#pragma omp parallel for schedule(static) reduction(max : rho)
+    for (int i = 0; i < n; ++i) {
+      double d = 0.0, s = 0.0;
+      for (int j = A.indptr[i]; j < A.indptr[i + 1]; ++j) {
+        if (A.indices[j] == i) d += A.vals[j];
+        s += std::fabs(A.vals[j]);
+      }
+      dinv[i] = 1.0 / d;
+      rho = std::max(rho, std::fabs(dinv[i]) * s);
+    }
+    // P = T - (omega/rho) D^-1 A T, T(i, agg[i]) = 1
+    CsrHost T;
+    T.n_rows = n;
+    T.n_cols = nagg;
+    T.indptr.resize(n + 1);
+    T.indices.resize(n);
+    T.vals.assign(n, 1.0);
+    for (int i = 0; i <= n; ++i) T.indptr[i] = i;
+    for (int i = 0; i < n; ++i) T.indices[i] = agg[i];
+    CsrHost AT;
+    spgemm(A, T, AT);
+    CsrHost P;
+    P.n_rows = n;
+    P.n_cols = nagg;
+    P.indptr.assign(n + 1, 0);
+    std::vector<int32_t> plen(n);
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; ++i) {
+      bool has = false;
+      for (int j = AT.indptr[i]; j < AT.indptr[i + 1]; ++j) has |= (AT.indices[j] == agg[i]);
+      plen[i] = AT.indptr[i + 1] - AT.indptr[i] + (has ? 0 : 1);
+    }
+    for (int i = 0; i < n; ++i) P.indptr[i + 1] = P.indptr[i] + plen[i];
+    P.indices.resize(P.indptr[n]);
+    P.vals.resize(P.indptr[n]);
+    const double sc = omega / rho;
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; ++i) {
+      int pos = P.indptr[i];
+      bool placed = false;
+      for (int j = AT.indptr[i]; j < AT.indptr[i + 1]; ++j) {
+        const int c = AT.indices[j];
+        if (!placed && c > agg[i]) {
+          P.indices[pos] = agg[i];
+          P.vals[pos++] = 1.0;
+          placed = true;
+        }
+        double v = -(sc * dinv[i]) * AT.vals[j];
+        if (c == agg[i]) {
+          v = 1.0 + v;
+          placed = true;
+        }
+        P.indices[pos] = c;
+        P.vals[pos++] = v;
+      }
+      if (!placed) {
+        P.indices[pos] = agg[i];
+        P.vals[pos++] = 1.0;
+      }
+    }
+    CsrHost R, AP, Ac;
+    transpose(P, R);
+    spgemm(A, P, AP);
+    spgemm(R, AP, Ac);
+    rhos.push_back(rho);
+    Ps.push_back(std::move(P));
+    Rs.push_back(std::move(R));
+    As.push_back(std::move(Ac));
+  }
+  // dense inverse of the coarsest operator
+  const CsrHost& Ac = As.back();
+  const int nc = Ac.n_rows;
+  if ((int64_t)nc * nc > (int64_t)64 * 1000 * 1000) {
+    set_error("AMG coarsening stalled at %d unknowns; coarsest level too large for a dense solve", nc);
+    return KNP_E_UNSUPPORTED;
+  }
+  std::vector<double> M((size_t)nc * nc, 0.0);
+  for (int i = 0; i < nc; ++i)
+    for (int j = Ac.indptr[i]; j < Ac.indptr[i + 1]; ++j) M[(size_t)i * nc + Ac.indices[j]] += Ac.vals[j];
+  return dense_inverse(nc, M, coarse_inv);
+}
+
+}  // namespace knp

@@ -1,0 +1,502 @@
+// extern "C" entry points of libknpemi_b200.so (see include/knpemi_b200.h for the reference call sites).
+#include <cmath>
+#include <dlfcn.h>
+#include "context.cuh"
+
+using namespace knp;
+
+namespace knp {
+int nullspace_remove(knp_ctx* c, double* x, cudaStream_t st);
+}
+
+static cudaStream_t pick(knp_ctx* c, void* stream) { return stream ? (cudaStream_t)stream : c->stream; }
+
+#define CTX_GUARD(c)                              \
+  do {                                            \
+    if (!(c)) {                                   \
+      set_error("context is NULL");               \
+      return KNP_E_INVALID;                       \
+    }                                             \
+    cudaError_t e_ = cudaSetDevice((c)->device);  \
+    if (e_ != cudaSuccess) {                      \
+      set_error("cudaSetDevice(%d): %s", (c)->device, cudaGetErrorString(e_)); \
+      return KNP_E_CUDA;                          \
+    }                                             \
+  } while (0)
+
+extern "C" {
+
+const char* knp_last_error(void) { return knp::last_error(); }
+int knp_version(void) { return 100; }
+
+int knp_create(knp_ctx** out, const knp_mesh_desc* mesh, int device) {
+  if (!out) {
+    set_error("out is NULL");
+    return KNP_E_INVALID;
+  }
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    set_error("no CUDA device available (%s); libknpemi_b200 has no CPU fallback", cudaGetErrorString(e));
+    return KNP_E_CUDA;
+  }
+  KNP_CHECK(device >= 0 && device < ndev, "device %d out of range (%d devices)", device, ndev);
+  KNP_CUDA(cudaSetDevice(device));
+  std::unique_ptr<knp_ctx> c(new knp_ctx());
+  c->device = device;
+  KNP_TRY(build_topology(mesh, c->H));
+  HostTopo& H = c->H;
+  KNP_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  for (auto& ev : c->ev) KNP_CUDA(cudaEventCreate(&ev));
+  // upload
+  KNP_TRY(c->d_node_x.upload(H.node_x));
+  KNP_TRY(c->d_adj_ptr.upload(H.adj_ptr));
+  KNP_TRY(c->d_adj_idx.upload(H.adj_idx));
+  KNP_TRY(c->d_inc_ptr.upload(H.inc_ptr));
+  KNP_TRY(c->d_inc_slots.upload(H.inc_slots));
+  KNP_TRY(c->d_self_slot.upload(H.self_slot));
+  KNP_TRY(c->d_mv_of_node.upload(H.mv_of_node));
+  KNP_TRY(c->d_mv_node0.upload(H.mv_node[0]));
+  KNP_TRY(c->d_mv_node1.upload(H.mv_node[1]));
+  KNP_TRY(c->d_mf_mv.upload(H.mf_mv));
+  KNP_TRY(c->d_mf_tagidx.upload(H.mf_tagidx));
+  KNP_TRY(c->d_mf_area.upload(H.mf_area));
+  KNP_TRY(c->d_gam_ptr.upload(H.gam_ptr));
+  KNP_TRY(c->d_gam_mv.upload(H.gam_mv));
+  KNP_TRY(c->d_minc_ptr.upload(H.minc_ptr));
+  KNP_TRY(c->d_minc.upload(H.minc));
+  KNP_TRY(c->d_indptr.upload(H.indptr));
+  KNP_TRY(c->d_indptr_P.upload(H.indptr_P));
+  {
+    std::vector<double> qb(mesh->quad_bary, mesh->quad_bary + (size_t)mesh->n_quad * mesh->gdim);
+    std::vector<double> qw(mesh->quad_w, mesh->quad_w + mesh->n_quad);
+    KNP_TRY(c->d_qb.upload(qb));
+    KNP_TRY(c->d_qw.upload(qw));
+  }
+  for (int s = 0; s < 2; ++s) {
+    KNP_TRY(c->d_cell_nodes[s].upload(H.cell_nodes[s]));
+    KNP_TRY(c->d_cell_tag[s].upload(H.cell_tag[s]));
+    KNP_TRY(c->d_cell_owned[s].upload(H.cell_owned[s]));
+  }
+  DevTopo& T = c->T;
+  T.gdim = H.gdim;
+  T.L = H.L;
+  T.n_work = H.n_work;
+  T.n_mv = H.n_mv;
+  T.n_mf = H.n_mf;
+  T.nq = mesh->n_quad;
+  T.node_x = c->d_node_x.p;
+  T.adj_ptr = c->d_adj_ptr.p;
+  T.adj_idx = c->d_adj_idx.p;
+  T.inc_ptr = c->d_inc_ptr.p;
+  T.inc_slots = c->d_inc_slots.p;
+  T.self_slot = c->d_self_slot.p;
+  T.mv_of_node = c->d_mv_of_node.p;
+  T.mv_node0 = c->d_mv_node0.p;
+  T.mv_node1 = c->d_mv_node1.p;
+  T.mf_mv = c->d_mf_mv.p;
+  T.mf_tagidx = c->d_mf_tagidx.p;
+  T.mf_area = c->d_mf_area.p;
+  T.gam_ptr = c->d_gam_ptr.p;
+  T.gam_mv = c->d_gam_mv.p;
+  T.minc_ptr = c->d_minc_ptr.p;
+  T.minc = c->d_minc.p;
+  T.indptr = c->d_indptr.p;
+  T.indptr_P = c->d_indptr_P.p;
+  T.qb = c->d_qb.p;
+  T.qw = c->d_qw.p;
+  // CSR column indices on the device
+  KNP_TRY(c->d_indices.alloc(H.nnz));
+  KNP_TRY(c->d_indices_P.alloc(H.nnz_P));
+  KNP_TRY(launch_csr_indices(T, 0, c->d_indices.p, c->stream));
+  KNP_TRY(launch_csr_indices(T, 1, c->d_indices_P.p, c->stream));
+  // state and system storage
+  KNP_TRY(c->u.alloc(T.L.n_cols));
+  KNP_TRY(c->gates.alloc((size_t)3 * T.n_mv));
+  KNP_TRY(c->A_vals.alloc(H.nnz));
+  KNP_TRY(c->P_vals.alloc(H.nnz_P));
+  KNP_TRY(c->b.alloc(T.L.n_rows));
+  KNP_TRY(c->fe.alloc((size_t)facet_ncomp(H.gdim) * (T.n_mf > 0 ? T.n_mf : 1)));
+  KNP_CUDA(cudaMemsetAsync(c->u.p, 0, (size_t)T.L.n_cols * sizeof(double), c->stream));
+  c->rows_stride = rows_smem_stride(H.max_deg, H.max_gdeg);
+  KNP_TRY(c->fpartial.alloc(1024));
+  KNP_TRY(c->fout.alloc(8));
+  KNP_TRY(c->ftags.alloc(4096));
+  c->n_phi_global = T.L.n_own[0] + T.L.n_own[1];
+  KNP_CUDA(cudaStreamSynchronize(c->stream));
+  // the big host-side tables are only needed on the device from here on
+  std::vector<uint32_t>().swap(H.inc_slots);
+  std::vector<uint32_t>().swap(H.minc);
+  std::vector<int32_t>().swap(H.adj_idx);
+  *out = c.release();
+  return KNP_OK;
+}
+
+int knp_destroy(knp_ctx* c) {
+  if (!c) return KNP_OK;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  if (c->comm) {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (h) {
+      auto fn = (int (*)(ncclComm*))dlsym(h, "ncclCommDestroy");
+      if (fn) fn(c->comm);
+    }
+  }
+  if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  for (auto& ev : c->ev)
+    if (ev) cudaEventDestroy(ev);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return KNP_OK;
+}
+
+int knp_get_sizes(const knp_ctx* c, knp_sizes* o) {
+  KNP_CHECK(c && o, "NULL argument");
+  const Layout& L = c->T.L;
+  o->n_rows = L.n_rows;
+  o->n_cols = L.n_cols;
+  o->nnz = c->H.nnz;
+  o->nnz_P = c->H.nnz_P;
+  for (int s = 0; s < 2; ++s) {
+    o->n_own[s] = L.n_own[s];
+    o->n_loc[s] = L.n_loc[s];
+    o->n_cells[s] = (int64_t)c->H.cell_tag[s].size();
+  }
+  o->n_mverts = c->T.n_mv;
+  o->n_mfacets = c->T.n_mf;
+  o->max_deg = c->H.max_deg;
+  o->max_gdeg = c->H.max_gdeg;
+  return KNP_OK;
+}
+
+int knp_csr_dev(const knp_ctx* c, const int32_t** indptr, const int32_t** indices) {
+  KNP_CHECK(c, "context is NULL");
+  if (indptr) *indptr = c->d_indptr.p;
+  if (indices) *indices = c->d_indices.p;
+  return KNP_OK;
+}
+
+int knp_csr_host(const knp_ctx* c, int32_t* indptr, int32_t* indices) {
+  KNP_CHECK(c, "context is NULL");
+  KNP_CUDA(cudaSetDevice(c->device));
+  if (indptr) memcpy(indptr, c->H.indptr.data(), c->H.indptr.size() * sizeof(int32_t));
+  if (indices) KNP_CUDA(cudaMemcpy(indices, c->d_indices.p, c->H.nnz * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  return KNP_OK;
+}
+
+int knp_csr_P_host(const knp_ctx* c, int32_t* indptr, int32_t* indices) {
+  KNP_CHECK(c, "context is NULL");
+  KNP_CUDA(cudaSetDevice(c->device));
+  if (indptr) memcpy(indptr, c->H.indptr_P.data(), c->H.indptr_P.size() * sizeof(int32_t));
+  if (indices) KNP_CUDA(cudaMemcpy(indices, c->d_indices_P.p, c->H.nnz_P * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  return KNP_OK;
+}
+
+int knp_dofmap_host(const knp_ctx* c, int32_t* vi, int32_t* ve) {
+  KNP_CHECK(c, "context is NULL");
+  if (vi) memcpy(vi, c->H.node_vert[0].data(), c->H.node_vert[0].size() * sizeof(int32_t));
+  if (ve) memcpy(ve, c->H.node_vert[1].data(), c->H.node_vert[1].size() * sizeof(int32_t));
+  return KNP_OK;
+}
+
+int knp_mverts_host(const knp_ctx* c, int32_t* verts) {
+  KNP_CHECK(c && verts, "NULL argument");
+  memcpy(verts, c->H.mv_vert.data(), c->H.mv_vert.size() * sizeof(int32_t));
+  return KNP_OK;
+}
+
+int knp_stimulus_area_local(knp_ctx* c, double* out) {
+  KNP_CHECK(c && out, "NULL argument");
+  KNP_CHECK(c->params_set, "knp_set_params must be called first");
+  // setup-time integral of the stimulus mask over owned stimulated facets (host, fixed order)
+  const HostTopo& H = c->H;
+  const int d = H.gdim;
+  std::vector<double> qb(c->d_qb.n), qw(c->d_qw.n);
+  KNP_CUDA(cudaSetDevice(c->device));
+  KNP_CUDA(cudaMemcpy(qb.data(), c->d_qb.p, qb.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  KNP_CUDA(cudaMemcpy(qw.data(), c->d_qw.p, qw.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  const knp_params& p = c->params.p;
+  double acc = 0.0;
+  for (int f = 0; f < H.n_mf; ++f) {
+    if (!H.mf_owned[f] || !c->params.tag_stim[H.mf_tagidx[f]]) continue;
+    for (size_t q = 0; q < qw.size(); ++q) {
+      double mask = 1.0;
+      if (p.stim_dir >= 0) {
+        double xq = 0.0;
+        for (int a = 0; a < d; ++a) {
+          const int node = H.mv_node[0][H.mf_mv[(size_t)f * d + a]];
+          xq += qb[q * d + a] * H.node_x[(size_t)node * d + p.stim_dir];
+        }
+        mask = (xq > p.stim_lo && xq < p.stim_hi) ? 1.0 : 0.0;
+      }
+      acc += H.mf_area[f] * qw[q] * mask;
+    }
+  }
+  *out = acc;
+  return KNP_OK;
+}
+
+int knp_set_params(knp_ctx* c, const knp_params* p, int32_t n_tags, const knp_tag_models* tags) {
+  CTX_GUARD(c);
+  KNP_CHECK(p, "params is NULL");
+  KNP_CHECK(p->dt > 0 && p->F > 0 && p->R > 0 && p->T > 0, "dt, F, R, T must be positive");
+  KNP_CHECK(p->ode_substeps >= 1, "ode_substeps must be >= 1");
+  Params& P = c->params;
+  P.p = *p;
+  P.psi = p->R * p->T / p->F;
+  P.n_tags = (int)c->H.mtags.size();
+  P.any_hh = false;
+  std::vector<uint32_t> tm(P.n_tags > 0 ? P.n_tags : 1, 0u);
+  std::vector<int32_t> ts(P.n_tags > 0 ? P.n_tags : 1, 0);
+  for (int i = 0; i < P.n_tags; ++i) {
+    bool found = false;
+    for (int j = 0; j < n_tags; ++j)
+      if (tags[j].tag == c->H.mtags[i]) {
+        tm[i] = tags[j].models;
+        ts[i] = tags[j].stimulated ? 1 : 0;
+        found = true;
+      }
+    KNP_CHECK(found, "membrane tag %d present in the mesh has no ionic model (Mismatch between membrane tags and ionic models tags)",
+              c->H.mtags[i]);
+    P.tag_models[i] = tm[i];
+    P.tag_stim[i] = ts[i];
+    if (tm[i] & KNP_MODEL_HH) P.any_hh = true;
+  }
+  for (int j = 0; j < n_tags; ++j)
+    if (tags[j].models & KNP_MODEL_HH) P.any_hh = true;
+  KNP_TRY(c->d_tag_models.upload(tm));
+  KNP_TRY(c->d_tag_stim.upload(ts));
+  KParams& K = c->kp;
+  K.dt = p->dt;
+  K.F = p->F;
+  K.C_M = p->C_M;
+  K.psi = P.psi;
+  K.phi_rest = p->phi_rest;
+  for (int k = 0; k < 3; ++k) {
+    K.z[k] = p->z[k];
+    K.D[k] = p->D[k];
+    K.g_leak[k] = p->g_leak[k];
+    K.g_leak_g[k] = p->g_leak_g[k];
+  }
+  K.g_Na_bar = p->g_Na_bar;
+  K.g_K_bar = p->g_K_bar;
+  K.stim_lo = p->stim_lo;
+  K.stim_hi = p->stim_hi;
+  K.K_e_init = p->K_e_init;
+  K.K_i_g_init = p->K_i_g_init;
+  K.stim_dir = p->stim_dir;
+  K.ode_substeps = p->ode_substeps;
+  K.rush_larsen = p->rush_larsen;
+  c->params_set = true;
+  if (p->stim_area > 0.0) {
+    P.stim_area = p->stim_area;
+  } else {
+    double a = 0.0;
+    KNP_TRY(knp_stimulus_area_local(c, &a));
+    P.stim_area = a;
+  }
+  return KNP_OK;
+}
+
+int knp_set_state(knp_ctx* c, const double* u_host, const double* gates_host) {
+  CTX_GUARD(c);
+  if (u_host)
+    KNP_CUDA(cudaMemcpyAsync(c->u.p, u_host, (size_t)c->T.L.n_cols * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (gates_host && c->T.n_mv)
+    KNP_CUDA(cudaMemcpyAsync(c->gates.p, gates_host, (size_t)3 * c->T.n_mv * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  KNP_CUDA(cudaStreamSynchronize(c->stream));
+  return KNP_OK;
+}
+
+int knp_get_state(knp_ctx* c, double* u_host, double* gates_host) {
+  CTX_GUARD(c);
+  if (u_host)
+    KNP_CUDA(cudaMemcpyAsync(u_host, c->u.p, (size_t)c->T.L.n_cols * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (gates_host && c->T.n_mv)
+    KNP_CUDA(cudaMemcpyAsync(gates_host, c->gates.p, (size_t)3 * c->T.n_mv * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  KNP_CUDA(cudaStreamSynchronize(c->stream));
+  return KNP_OK;
+}
+
+int knp_state_dev(knp_ctx* c, double** u_dev, double** gates_dev) {
+  KNP_CHECK(c, "context is NULL");
+  if (u_dev) *u_dev = c->u.p;
+  if (gates_dev) *gates_dev = c->gates.p;
+  return KNP_OK;
+}
+
+int knp_phi_m_host(knp_ctx* c, double* out) {
+  CTX_GUARD(c);
+  KNP_CHECK(out, "NULL argument");
+  std::vector<double> u(c->T.L.n_cols);
+  KNP_CUDA(cudaStreamSynchronize(c->stream));
+  KNP_CUDA(cudaMemcpy(u.data(), c->u.p, u.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  for (int g = 0; g < c->T.n_mv; ++g)
+    out[g] = u[c->T.L.col(0, 3, c->H.mv_node[0][g])] - u[c->T.L.col(1, 3, c->H.mv_node[1][g])];
+  return KNP_OK;
+}
+
+int knp_gate_step(knp_ctx* c, void* stream) {
+  CTX_GUARD(c);
+  KNP_CHECK(c->params_set, "knp_set_params must be called first");
+  return launch_gate(c->T, c->kp, c->u.p, c->gates.p, pick(c, stream));
+}
+
+int knp_assemble(knp_ctx* c, double t, double* A_vals, double* b, void* stream) {
+  CTX_GUARD(c);
+  KNP_CHECK(c->params_set, "knp_set_params must be called first");
+  cudaStream_t st = pick(c, stream);
+  const knp_params& p = c->params.p;
+  // HodgkinHuxley.update_t_mod (KNPEMIx_ionic_model.py:673-674) and the stimulus prefactor (:552,589,600)
+  const double t_mod = std::fmod(t + 1e-12, p.T_stim);
+  double stim_fac = p.g_syn_bar * std::exp(-t_mod / p.a_syn);
+  if (p.scale_stimulus) stim_fac *= 1.0 / c->params.stim_area;
+  KNP_TRY(launch_facets(c->T, c->kp, c->d_tag_models.p, c->d_tag_stim.p, c->u.p, c->gates.p, stim_fac, c->fe.p, st));
+  KNP_CUDA(cudaEventRecord(c->ev[2], st));
+  KNP_TRY(launch_rows(c->T, c->kp, 0, c->u.p, c->fe.p, A_vals ? A_vals : c->A_vals.p, b ? b : c->b.p, c->rows_stride, st));
+  return KNP_OK;
+}
+
+int knp_assemble_P(knp_ctx* c, double* P_vals, void* stream) {
+  CTX_GUARD(c);
+  KNP_CHECK(c->params_set, "knp_set_params must be called first");
+  KNP_TRY(launch_rows(c->T, c->kp, 1, c->u.p, c->fe.p, P_vals ? P_vals : c->P_vals.p, nullptr, c->rows_stride, pick(c, stream)));
+  if (!P_vals) c->P_assembled = true;
+  return KNP_OK;
+}
+
+int knp_values_dev(knp_ctx* c, double** A_vals, double** b, double** P_vals, double** x) {
+  KNP_CHECK(c, "context is NULL");
+  if (A_vals) *A_vals = c->A_vals.p;
+  if (b) *b = c->b.p;
+  if (P_vals) *P_vals = c->P_vals.p;
+  if (x) *x = c->u.p;
+  return KNP_OK;
+}
+
+int knp_spmv(knp_ctx* c, const double* A_vals, const double* x, double* y, void* stream) {
+  CTX_GUARD(c);
+  return launch_spmv(c->T.L.n_rows, c->H.nnz, c->d_indptr.p, c->d_indices.p, A_vals ? A_vals : c->A_vals.p, x, y,
+                     EPI_SET, nullptr, nullptr, 0.0, pick(c, stream));
+}
+
+int knp_pc_setup(knp_ctx* c, const knp_solve_opts* o) {
+  CTX_GUARD(c);
+  KNP_CHECK(o, "options are NULL");
+  return pc_setup(c, o);
+}
+
+int knp_pc_apply(knp_ctx* c, const double* r, double* z, void* stream) {
+  CTX_GUARD(c);
+  KNP_CHECK(c->pc_kind >= 0, "knp_pc_setup must be called first");
+  return pc_apply(c, r, z, pick(c, stream));
+}
+
+int knp_solve(knp_ctx* c, const double* A_vals, const double* b, double* x, const knp_solve_opts* o,
+              knp_solve_info* info, void* stream) {
+  CTX_GUARD(c);
+  KNP_CHECK(o && info, "NULL argument");
+  KNP_CHECK(c->pc_kind == o->pc, "knp_pc_setup must be called with the same preconditioner kind before knp_solve");
+  return gmres_solve(c, A_vals ? A_vals : c->A_vals.p, b ? b : c->b.p, x ? x : c->u.p, o, info, pick(c, stream));
+}
+
+int knp_set_time(knp_ctx* c, double t, int32_t step_index) {
+  KNP_CHECK(c, "context is NULL");
+  c->t = t;
+  c->step_index = step_index;
+  return KNP_OK;
+}
+int knp_get_time(const knp_ctx* c, double* t, int32_t* step_index) {
+  KNP_CHECK(c, "context is NULL");
+  if (t) *t = c->t;
+  if (step_index) *step_index = c->step_index;
+  return KNP_OK;
+}
+
+int knp_step(knp_ctx* c, const knp_solve_opts* o, knp_solve_info* info, void* stream) {
+  CTX_GUARD(c);
+  KNP_CHECK(o && info, "NULL argument");
+  KNP_CHECK(c->params_set, "knp_set_params must be called first");
+  KNP_CHECK(c->pc_kind == o->pc, "knp_pc_setup must be called with the same preconditioner kind before knp_step");
+  cudaStream_t st = pick(c, stream);
+  KNP_TRY(ensure_workspace(c, o->restart > 0 ? o->restart : 30));
+  c->t += c->params.p.dt;                      // KNPEMIx_solver.py:368
+  c->step_index += 1;
+  KNP_CUDA(cudaEventRecord(c->ev[0], st));
+  if (c->params.any_hh) KNP_TRY(launch_gate(c->T, c->kp, c->u.p, c->gates.p, st));   // :395-399
+  KNP_CUDA(cudaEventRecord(c->ev[1], st));
+  KNP_TRY(knp_assemble(c, c->t, nullptr, nullptr, st));                              // :402-403 (records ev[2])
+  KNP_CUDA(cudaEventRecord(c->ev[3], st));
+  if (c->step_index == 1 && o->project_nullspace) KNP_TRY(nullspace_remove(c, c->b.p, st));   // :415-419,333
+  int rc = gmres_solve(c, c->A_vals.p, c->b.p, c->u.p, o, info, st);                 // :435 ; u <- x (:451-468)
+  KNP_CUDA(cudaEventRecord(c->ev[4], st));
+  KNP_CUDA(cudaEventSynchronize(c->ev[4]));
+  float ms;
+  cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); c->last_ms[0] = ms;
+  cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); c->last_ms[1] = ms;
+  cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); c->last_ms[2] = ms;
+  cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]); c->last_ms[3] = ms;
+  cudaEventElapsedTime(&ms, c->ev[0], c->ev[4]); c->last_ms[4] = ms;
+  return rc;
+}
+
+int knp_step_host(knp_ctx* c, double* u_host, double* gates_host, const knp_solve_opts* o, knp_solve_info* info) {
+  CTX_GUARD(c);
+  KNP_CHECK(u_host, "u_host is NULL");
+  cudaStream_t st = c->stream;
+  KNP_CUDA(cudaMemcpyAsync(c->u.p, u_host, (size_t)c->T.L.n_cols * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (gates_host && c->T.n_mv)
+    KNP_CUDA(cudaMemcpyAsync(c->gates.p, gates_host, (size_t)3 * c->T.n_mv * sizeof(double), cudaMemcpyHostToDevice, st));
+  int rc = knp_step(c, o, info, st);
+  if (rc != KNP_OK) return rc;
+  KNP_CUDA(cudaMemcpyAsync(u_host, c->u.p, (size_t)c->T.L.n_cols * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (gates_host && c->T.n_mv)
+    KNP_CUDA(cudaMemcpyAsync(gates_host, c->gates.p, (size_t)3 * c->T.n_mv * sizeof(double), cudaMemcpyDeviceToHost, st));
+  KNP_CUDA(cudaStreamSynchronize(st));
+  return KNP_OK;
+}
+
+int knp_last_timings(const knp_ctx* c, double* ms5) {
+  KNP_CHECK(c && ms5, "NULL argument");
+  for (int i = 0; i < 5; ++i) ms5[i] = c->last_ms[i];
+  return KNP_OK;
+}
+
+int knp_l2_norm_sq(knp_ctx* c, int32_t s, int32_t field, int32_t n_tags, const int32_t* tags, double* out) {
+  CTX_GUARD(c);
+  KNP_CHECK(out && tags && n_tags > 0 && n_tags <= 4096, "bad tag list");
+  KNP_CHECK((s == 0 || s == 1) && field >= 0 && field < 4, "bad subdomain/field");
+  const int nc = (int)c->H.cell_tag[s].size();
+  cudaStream_t st = c->stream;
+  KNP_CUDA(cudaMemcpyAsync(c->ftags.p, tags, n_tags * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  const int nb = 592;
+  KNP_TRY(launch_l2_cells(c->T.gdim, c->T.L, s, field, nc, c->d_cell_nodes[s].p, c->d_cell_tag[s].p,
+                          c->d_cell_owned[s].p, c->d_node_x.p, s ? c->T.L.n_loc[0] : 0, c->ftags.p, n_tags, c->u.p,
+                          c->fpartial.p, nb, st));
+  KNP_TRY(launch_reduce_partials(c->fpartial.p, nb, c->fout.p, st));
+  KNP_CUDA(cudaMemcpyAsync(out, c->fout.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+  KNP_CUDA(cudaStreamSynchronize(st));
+  return KNP_OK;
+}
+
+int knp_amg_num_levels(const knp_ctx* c) { return (c && c->amg) ? (int)c->amg->hostA.size() : 0; }
+
+int knp_amg_level_sizes(const knp_ctx* c, int32_t level, int64_t* n, int64_t* nnz) {
+  KNP_CHECK(c && c->amg && level >= 0 && level < (int)c->amg->hostA.size(), "no such AMG level");
+  if (n) *n = c->amg->hostA[level].n_rows;
+  if (nnz) *nnz = c->amg->hostA[level].nnz();
+  return KNP_OK;
+}
+
+int knp_amg_level_host(const knp_ctx* c, int32_t level, int32_t* indptr, int32_t* indices, double* vals) {
+  KNP_CHECK(c && c->amg && level >= 0 && level < (int)c->amg->hostA.size(), "no such AMG level");
+  const CsrHost& A = c->amg->hostA[level];
+  if (indptr) memcpy(indptr, A.indptr.data(), A.indptr.size() * sizeof(int32_t));
+  if (indices) memcpy(indices, A.indices.data(), A.indices.size() * sizeof(int32_t));
+  if (vals) memcpy(vals, A.vals.data(), A.vals.size() * sizeof(double));
+  return KNP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,180 @@
+// Internal definitions shared by the translation units of libknpemi_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "knpemi_b200.h"
+
+namespace knp {
+
+void set_error(const char* fmt, ...);
+
+#define KNP_CUDA(call)                                                              \
+  do {                                                                              \
+    cudaError_t e_ = (call);                                                        \
+    if (e_ != cudaSuccess) {                                                        \
+      knp::set_error("%s:%d CUDA error %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \
+      return KNP_E_CUDA;                                                            \
+    }                                                                               \
+  } while (0)
+
+#define KNP_CHECK(cond, ...)             \
+  do {                                   \
+    if (!(cond)) {                       \
+      knp::set_error(__VA_ARGS__);       \
+      return KNP_E_INVALID;              \
+    }                                    \
+  } while (0)
+
+#define KNP_TRY(call)           \
+  do {                          \
+    int rc_ = (call);           \
+    if (rc_ != KNP_OK) return rc_; \
+  } while (0)
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  int alloc(size_t count) {
+    free();
+    n = count;
+    if (count == 0) return KNP_OK;
+    KNP_CUDA(cudaMalloc(&p, count * sizeof(T)));
+    return KNP_OK;
+  }
+  int upload(const std::vector<T>& h) {
+    KNP_TRY(alloc(h.size()));
+    if (!h.empty()) KNP_CUDA(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return KNP_OK;
+  }
+  void free() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  ~DevBuf() { free(); }
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+};
+
+// Column layout: owned (s,f,p) -> rowbase[s] + f*n_own[s] + p ; ghost (s,f,q>=n_own[s]) ->
+// n_rows + gbase[s] + f*n_gh[s] + (q - n_own[s]).
+struct Layout {
+  int n_own[2], n_loc[2], n_gh[2];
+  int rowbase[2];
+  int gbase[2];
+  int n_rows, n_cols;
+  __host__ __device__ __forceinline__ int col(int s, int f, int q) const {
+    return q < n_own[s] ? rowbase[s] + f * n_own[s] + q
+                        : n_rows + gbase[s] + f * n_gh[s] + (q - n_own[s]);
+  }
+  __host__ __device__ __forceinline__ int row(int s, int f, int p) const {
+    return rowbase[s] + f * n_own[s] + p;
+  }
+};
+
+// Host-built topology (topology.cpp)
+struct HostTopo {
+  int gdim = 0;
+  Layout L{};
+  int n_work = 0;                         // owned nodes (intra then extra)
+  std::vector<double> node_x;             // [n_loc0+n_loc1][gdim], intra local nodes first
+  std::vector<int32_t> node_vert[2];      // restricted dof -> local vertex
+  std::vector<int32_t> adj_ptr, adj_idx;  // per owned node (unified index w), neighbours as subdomain-local node ids
+  std::vector<int32_t> inc_ptr;           // per owned node
+  std::vector<uint32_t> inc_slots;        // per (node, cell): adjacency slots of the cell's vertices (8 bit each)
+  std::vector<int32_t> self_slot;         // per owned node: slot of itself in its adjacency
+  std::vector<int32_t> mv_of_node;        // per owned node: membrane vertex id or -1
+  // membrane
+  int n_mv = 0, n_mf = 0;
+  std::vector<int32_t> mv_vert, mv_node[2];   // per membrane vertex
+  std::vector<int32_t> mf_mv;                 // [n_mf][gdim-...]: d membrane-vertex ids per facet (d = gdim)
+  std::vector<int32_t> mf_tagidx;             // index into the sorted unique membrane tag list
+  std::vector<int32_t> mf_owned;              // this rank integrates functionals over the facet
+  std::vector<double> mf_area;                // facet measure |F|
+  std::vector<int32_t> mtags;                 // sorted unique membrane tags
+  std::vector<int32_t> gam_ptr, gam_mv;       // per membrane vertex: sorted neighbouring membrane vertices (incl. self)
+  std::vector<int32_t> minc_ptr;              // per membrane vertex: incident facets
+  std::vector<uint32_t> minc;                 // 4 words per incidence: facet, a|slots_i<<8, slots_e, slots_gam
+  // cells per subdomain (for functionals)
+  std::vector<int32_t> cell_nodes[2];         // [(gdim+1) per cell] subdomain-local node ids
+  std::vector<int32_t> cell_tag[2];
+  std::vector<int32_t> cell_owned[2];         // 1 if the cell's lowest-id vertex is owned (integrate once)
+  int max_deg = 0, max_gdeg = 0;
+  // CSR sizes
+  int64_t nnz = 0, nnz_P = 0;
+  std::vector<int32_t> indptr, indptr_P;      // computed on host (n_rows+1)
+  std::vector<int32_t> gpre;                  // per owned node: prefix of gamma degree (own subdomain)
+};
+
+int build_topology(const knp_mesh_desc* m, HostTopo& T);
+
+// Device-side views handed to kernels (all pointers device)
+struct DevTopo {
+  int gdim;
+  Layout L;
+  int n_work;
+  int n_mv, n_mf;
+  int nq;
+  const double* node_x;
+  const int32_t *adj_ptr, *adj_idx, *inc_ptr, *self_slot, *mv_of_node;
+  const uint32_t* inc_slots;
+  const int32_t *mv_node0, *mv_node1, *mf_mv, *mf_tagidx, *gam_ptr, *gam_mv, *minc_ptr;
+  const double* mf_area;
+  const uint32_t* minc;
+  const int32_t *indptr, *indptr_P;
+  const double *qb, *qw;
+};
+
+struct Params {
+  knp_params p;
+  double psi;
+  double stim_area;
+  int n_tags;
+  uint32_t tag_models[256];
+  int tag_stim[256];
+  bool any_hh;
+};
+
+// ---- generic CSR level (AMG) ----
+struct CsrDev {
+  int n_rows = 0, n_cols = 0;
+  int64_t nnz = 0;
+  DevBuf<int32_t> indptr, indices;
+  DevBuf<double> vals;
+};
+
+struct CsrHost {
+  int n_rows = 0, n_cols = 0;
+  std::vector<int32_t> indptr, indices;
+  std::vector<double> vals;
+  int64_t nnz() const { return (int64_t)indices.size(); }
+};
+
+struct AmgLevelDev {
+  CsrDev A, P, R;
+  DevBuf<double> dinv, x, b, r;
+  double rho = 2.0;
+};
+
+struct Amg {
+  std::vector<AmgLevelDev*> levels;   // levels[0].A is not owned (views the context's P) when external
+  DevBuf<double> coarse_inv;          // dense n_c x n_c (row-major)
+  DevBuf<double> cb, cx;
+  int n_coarse = 0;
+  std::vector<CsrHost> hostA;         // kept for inspection
+  ~Amg() {
+    for (auto* l : levels) delete l;
+  }
+};
+
+int amg_setup_host(const CsrHost& A0, double theta, int coarse_size, int max_levels,
+                   std::vector<CsrHost>& As, std::vector<CsrHost>& Ps, std::vector<CsrHost>& Rs,
+                   std::vector<double>& rhos, std::vector<double>& coarse_inv);
+
+}  // namespace knp

@@ -1,0 +1,66 @@
+// The per-GPU context behind the opaque knp_ctx handle.
+#pragma once
+#include <memory>
+#include "common.cuh"
+#include "kernels.cuh"
+
+struct ncclComm;
+
+struct knp_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  knp::HostTopo H;
+  knp::DevTopo T{};
+  // device copies of the topology
+  knp::DevBuf<double> d_node_x, d_mf_area, d_qb, d_qw;
+  knp::DevBuf<int32_t> d_adj_ptr, d_adj_idx, d_inc_ptr, d_self_slot, d_mv_of_node;
+  knp::DevBuf<uint32_t> d_inc_slots, d_minc;
+  knp::DevBuf<int32_t> d_mv_node0, d_mv_node1, d_mf_mv, d_mf_tagidx, d_gam_ptr, d_gam_mv, d_minc_ptr;
+  knp::DevBuf<int32_t> d_indptr, d_indices, d_indptr_P, d_indices_P;
+  knp::DevBuf<int32_t> d_cell_nodes[2], d_cell_tag[2], d_cell_owned[2];
+  knp::DevBuf<uint32_t> d_tag_models;
+  knp::DevBuf<int32_t> d_tag_stim;
+  // parameters
+  knp::Params params{};
+  knp::KParams kp{};
+  bool params_set = false;
+  // state and system
+  knp::DevBuf<double> u, gates, A_vals, P_vals, b, fe;
+  bool P_assembled = false;
+  int rows_stride = 0;
+  double t = 0.0;
+  int step_index = 0;
+  // Krylov workspace
+  int ws_restart = 0;
+  size_t ldv = 0;
+  knp::DevBuf<double> V, w, tmp, partial, hdev, ydev, pc_dinv;
+  double* h_pinned = nullptr;
+  // preconditioner
+  int pc_kind = -1;
+  std::unique_ptr<knp::Amg> amg;
+  // distributed
+  ncclComm* comm = nullptr;
+  int rank = 0, nranks = 1;
+  std::vector<int32_t> peers;
+  std::vector<int64_t> send_ptr, recv_ptr;
+  knp::DevBuf<int32_t> d_send_cols;
+  knp::DevBuf<double> d_send_buf;
+  int64_t n_phi_global = 0;   // global number of potential dofs (nullspace normalisation)
+  // timers
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  double last_ms[5] = {0, 0, 0, 0, 0};
+  // scratch for functionals
+  knp::DevBuf<double> fpartial, fout;
+  knp::DevBuf<int32_t> ftags;
+};
+
+namespace knp {
+int ensure_workspace(knp_ctx* c, int restart);
+int pc_setup(knp_ctx* c, const knp_solve_opts* o);
+int pc_apply(knp_ctx* c, const double* r, double* z, cudaStream_t st);
+int gmres_solve(knp_ctx* c, const double* A_vals, const double* b, double* x, const knp_solve_opts* o,
+                knp_solve_info* info, cudaStream_t st);
+int halo_exchange(knp_ctx* c, double* x, cudaStream_t st);
+int allreduce_sum(knp_ctx* c, double* buf, int n, cudaStream_t st);
+const char* last_error();
+}  // namespace knp

@@ -1,0 +1,166 @@
+// Multi-GPU plumbing: ghost-column halo exchange (grouped ncclSend/ncclRecv over NVLink) and all-reduce of
+// the fused Gram-Schmidt blocks.  Replaces PETSc's VecScatter / ghostUpdate and MPI_Allreduce inside KSP
+// (KNPEMIx_solver.py:435,439,458-468).  NCCL is bound lazily with dlopen so that the single-GPU library has
+// no link-time dependency on it; the Python host passes a ncclUniqueId broadcast through torch.distributed.
+#include <dlfcn.h>
+#include <nccl.h>
+#include "context.cuh"
+
+namespace knp {
+
+struct NcclApi {
+  void* h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static NcclApi* nccl_api() {
+  static NcclApi api;
+  if (api.h) return &api;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) {
+    set_error("cannot load libnccl.so.2: %s", dlerror());
+    return nullptr;
+  }
+#define BIND(name)                                                        \
+  api.name = (decltype(api.name))dlsym(h, "nccl" #name);                  \
+  if (!api.name) {                                                        \
+    set_error("libnccl.so.2 lacks nccl" #name);                           \
+    return nullptr;                                                       \
+  }
+  BIND(GetUniqueId) BIND(CommInitRank) BIND(AllReduce) BIND(Send) BIND(Recv) BIND(GroupStart) BIND(GroupEnd)
+  BIND(GetErrorString)
+#undef BIND
+  api.h = h;
+  return &api;
+}
+
+#define KNP_NCCL(call)                                                                 \
+  do {                                                                                 \
+    ncclResult_t r_ = (call);                                                          \
+    if (r_ != ncclSuccess) {                                                           \
+      set_error("%s:%d NCCL error %s", __FILE__, __LINE__, api->GetErrorString(r_));   \
+      return KNP_E_NCCL;                                                               \
+    }                                                                                  \
+  } while (0)
+
+__global__ void pack_kernel(int64_t n, const int32_t* __restrict__ cols, const double* __restrict__ x,
+                            double* __restrict__ buf) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    buf[i] = x[cols[i]];
+}
+__global__ void unpack_kernel(int64_t n, const int32_t* __restrict__ cols, const double* __restrict__ buf,
+                              double* __restrict__ x) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    x[cols[i]] = buf[i];
+}
+
+int halo_exchange(knp_ctx* c, double* x, cudaStream_t st) {
+  if (c->nranks <= 1 || c->peers.empty()) return KNP_OK;
+  NcclApi* api = nccl_api();
+  if (!api) return KNP_E_NCCL;
+  const int np = (int)c->peers.size();
+  const int64_t ns = c->send_ptr[np], nr = c->recv_ptr[np];
+  double* sbuf = c->d_send_buf.p;
+  double* rbuf = c->d_send_buf.p + ns;
+  if (ns > 0) {
+    int grid = (int)((ns + 255) / 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    pack_kernel<<<grid, 256, 0, st>>>(ns, c->d_send_cols.p, x, sbuf);
+    KNP_CUDA(cudaGetLastError());
+  }
+  KNP_NCCL(api->GroupStart());
+  for (int i = 0; i < np; ++i) {
+    const int64_t cs = c->send_ptr[i + 1] - c->send_ptr[i], cr = c->recv_ptr[i + 1] - c->recv_ptr[i];
+    if (cs > 0) KNP_NCCL(api->Send(sbuf + c->send_ptr[i], (size_t)cs, ncclFloat64, c->peers[i], c->comm, st));
+    if (cr > 0) KNP_NCCL(api->Recv(rbuf + c->recv_ptr[i], (size_t)cr, ncclFloat64, c->peers[i], c->comm, st));
+  }
+  KNP_NCCL(api->GroupEnd());
+  if (nr > 0) {
+    int grid = (int)((nr + 255) / 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    unpack_kernel<<<grid, 256, 0, st>>>(nr, c->d_send_cols.p + ns, rbuf, x);
+    KNP_CUDA(cudaGetLastError());
+  }
+  return KNP_OK;
+}
+
+int allreduce_sum(knp_ctx* c, double* buf, int n, cudaStream_t st) {
+  if (c->nranks <= 1) return KNP_OK;
+  NcclApi* api = nccl_api();
+  if (!api) return KNP_E_NCCL;
+  KNP_NCCL(api->AllReduce(buf, buf, (size_t)n, ncclFloat64, ncclSum, c->comm, st));
+  return KNP_OK;
+}
+
+}  // namespace knp
+
+using namespace knp;
+
+extern "C" {
+
+int knp_nccl_unique_id(char* out128) {
+  KNP_CHECK(out128, "NULL argument");
+  NcclApi* api = nccl_api();
+  if (!api) return KNP_E_NCCL;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  ncclUniqueId id;
+  KNP_NCCL(api->GetUniqueId(&id));
+  memcpy(out128, &id, 128);
+  return KNP_OK;
+}
+
+int knp_dist_init(knp_ctx* c, int32_t rank, int32_t nranks, const char* unique_id128, int64_t n_phi_global,
+                  int32_t n_peers, const int32_t* peers, const int64_t* send_ptr, const int32_t* send_cols,
+                  const int64_t* recv_ptr, const int32_t* recv_cols) {
+  KNP_CHECK(c, "context is NULL");
+  KNP_CUDA(cudaSetDevice(c->device));
+  KNP_CHECK(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank/nranks");
+  c->rank = rank;
+  c->nranks = nranks;
+  c->n_phi_global = n_phi_global;
+  if (nranks == 1) return KNP_OK;
+  KNP_CHECK(unique_id128 && (n_peers == 0 || (peers && send_ptr && recv_ptr)), "NULL argument");
+  NcclApi* api = nccl_api();
+  if (!api) return KNP_E_NCCL;
+  ncclUniqueId id;
+  memcpy(&id, unique_id128, 128);
+  KNP_NCCL(api->CommInitRank(&c->comm, nranks, id, rank));
+  c->peers.assign(peers, peers + n_peers);
+  c->send_ptr.assign(send_ptr, send_ptr + n_peers + 1);
+  c->recv_ptr.assign(recv_ptr, recv_ptr + n_peers + 1);
+  const int64_t ns = c->send_ptr[n_peers], nr = c->recv_ptr[n_peers];
+  const int ncols = c->T.L.n_cols, nrows = c->T.L.n_rows;
+  std::vector<int32_t> cols((size_t)(ns + nr));
+  for (int64_t i = 0; i < ns; ++i) {
+    KNP_CHECK(send_cols[i] >= 0 && send_cols[i] < nrows, "send column %d is not an owned column", send_cols[i]);
+    cols[i] = send_cols[i];
+  }
+  for (int64_t i = 0; i < nr; ++i) {
+    KNP_CHECK(recv_cols[i] >= nrows && recv_cols[i] < ncols, "recv column %d is not a ghost column", recv_cols[i]);
+    cols[ns + i] = recv_cols[i];
+  }
+  KNP_TRY(c->d_send_cols.upload(cols));
+  KNP_TRY(c->d_send_buf.alloc((size_t)(ns + nr) + 1));
+  return KNP_OK;
+}
+
+int knp_halo_exchange(knp_ctx* c, double* x_dev, void* stream) {
+  KNP_CHECK(c, "context is NULL");
+  KNP_CUDA(cudaSetDevice(c->device));
+  return halo_exchange(c, x_dev ? x_dev : c->u.p, stream ? (cudaStream_t)stream : c->stream);
+}
+
+int knp_allreduce_sum(knp_ctx* c, double* buf_dev, int32_t n, void* stream) {
+  KNP_CHECK(c && buf_dev, "NULL argument");
+  KNP_CUDA(cudaSetDevice(c->device));
+  return allreduce_sum(c, buf_dev, n, stream ? (cudaStream_t)stream : c->stream);
+}
+
+}  // extern "C"

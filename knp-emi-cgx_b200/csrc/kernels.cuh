@@ -1,0 +1,59 @@
+// Kernel-side parameter block and launcher declarations.
+#pragma once
+#include "common.cuh"
+
+namespace knp {
+
+constexpr int ROWS_BLOCK = 128;
+
+// Plain-old-data copy of the constants that enter the forms (passed by value to kernels).
+struct KParams {
+  double dt, F, C_M, psi, phi_rest;
+  double z[3], D[3];
+  double g_Na_bar, g_K_bar, g_leak[3], g_leak_g[3];
+  double stim_lo, stim_hi;
+  double K_e_init, K_i_g_init;
+  int stim_dir;
+  int ode_substeps, rush_larsen;
+};
+
+int launch_gate(const DevTopo& T, const KParams& P, const double* u, double* gates, cudaStream_t st);
+int facet_ncomp(int gdim);
+int launch_facets(const DevTopo& T, const KParams& P, const uint32_t* tag_models, const int32_t* tag_stim,
+                  const double* u, const double* gates, double stim_fac, double* fe, cudaStream_t st);
+int rows_smem_stride(int max_deg, int max_gdeg);
+int launch_rows(const DevTopo& T, const KParams& P, int mode, const double* u, const double* fe, double* vals,
+                double* b, int stride, cudaStream_t st);
+int launch_csr_indices(const DevTopo& T, int mode, int32_t* indices, cudaStream_t st);
+int launch_l2_cells(int gdim, const Layout& L, int s, int field, int n_cells, const int32_t* cell_nodes,
+                    const int32_t* cell_tag, const int32_t* cell_owned, const double* node_x, int nodeoff,
+                    const int32_t* tags, int n_tags, const double* u, double* partial, int n_partial,
+                    cudaStream_t st);
+
+// ---- linalg.cu ----
+enum SpmvEpi { EPI_SET = 0, EPI_RESID = 1, EPI_JACOBI = 2, EPI_ADD = 3 };
+// out = epilogue(A x): SET: A x | RESID: b - A x | JACOBI: x + w*dinv*(b - A x) | ADD: out + A x
+int launch_spmv(int n_rows, int64_t nnz, const int32_t* indptr, const int32_t* indices, const double* vals,
+                const double* x, double* out, int epi, const double* b, const double* dinv, double w,
+                cudaStream_t st);
+int launch_scale_dinv(int n, double w, const double* dinv, const double* b, double* x, cudaStream_t st);   // x = w*dinv*b
+int launch_extract_dinv(int n_rows, const int32_t* indptr, const int32_t* indices, const double* vals, double* dinv,
+                        cudaStream_t st);
+int launch_dense_gemv(int n, const double* Minv, const double* b, double* x, cudaStream_t st);
+// Gram-Schmidt building blocks (deterministic two-stage reductions; no atomics)
+constexpr int RED_BLOCKS = 296;   // 2 x 148 SMs
+// out[j] = sum_i V[j*ldv + i] * w[i], j < m ; out[m] = sum_i w[i]^2 ; partial is (m+1) x RED_BLOCKS scratch
+int launch_multi_dot(int n, int m, const double* V, size_t ldv, const double* w, double* partial, double* out,
+                     cudaStream_t st);
+// w -= sum_j h[j] V_j   (h on device)
+int launch_multi_axpy(int n, int m, const double* V, size_t ldv, const double* h, double* w, cudaStream_t st);
+int launch_axpby(int n, double a, const double* x, double b, double* y, cudaStream_t st);              // y = a x + b y
+int launch_scale_copy(int n, const double* alpha_dev, int invert, const double* x, double* y, cudaStream_t st);   // y = x*alpha or x/alpha
+int launch_update_x(int n, int m, const double* V, size_t ldv, const double* y_dev, double* x, cudaStream_t st);   // x += sum_j y[j] V_j
+// sum over [lo0,hi0) U [lo1,hi1) of x -> out[0] (deterministic), and x[range] -= shift
+int launch_range_sum(const double* x, int lo0, int hi0, int lo1, int hi1, double* partial, double* out, cudaStream_t st);
+int launch_range_shift(double* x, int lo0, int hi0, int lo1, int hi1, const double* sum_dev, double inv_count,
+                       cudaStream_t st);
+int launch_reduce_partials(const double* partial, int n_partial, double* out, cudaStream_t st);
+
+}  // namespace knp

@@ -1,0 +1,309 @@
+// Sparse / dense linear-algebra kernels of the Krylov solver (sm_100a).
+//
+//   spmv_kernel<LANES,EPI>  K5   CSR y = A x, LANES lanes per row, fused epilogues (residual, Jacobi sweep,
+//                                prolongation add) -- replaces PETSc MatMult / hypre relax inside ksp.solve
+//                                (KNPEMIx_solver.py:435)
+//   multi_dot / multi_axpy  K6   classical Gram-Schmidt building blocks: all (j+1) inner products and ||w||^2
+//                                in ONE pass over w and V, reduced in a fixed order (two-stage, no atomics)
+//   range_sum / range_shift K8   nullspace projection x -= (ns.x) ns (KNPEMIx_solver.py:324-333)
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace knp {
+
+__device__ __forceinline__ double ld_stream(const double* p) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int ld_stream(const int* p) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+template <int LANES, int EPI>
+__global__ void __launch_bounds__(256) spmv_kernel(int n_rows, const int32_t* __restrict__ indptr,
+                                                   const int32_t* __restrict__ indices,
+                                                   const double* __restrict__ vals, const double* __restrict__ x,
+                                                   double* __restrict__ out, const double* __restrict__ b,
+                                                   const double* __restrict__ dinv, double w) {
+  const int lane = threadIdx.x & (LANES - 1);
+  constexpr int RPB = 256 / LANES;
+  // block-uniform trip count so that the sub-warp shuffles are always convergent
+  for (int base = blockIdx.x * RPB; base < n_rows; base += gridDim.x * RPB) {
+    const int row = base + threadIdx.x / LANES;
+    const bool valid = row < n_rows;
+    double sum = 0.0;
+    if (valid) {
+      const int r0 = indptr[row], r1 = indptr[row + 1];
+      for (int j = r0 + lane; j < r1; j += LANES) sum += ld_stream(vals + j) * __ldg(x + ld_stream(indices + j));
+    }
+#pragma unroll
+    for (int off = LANES / 2; off > 0; off >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, off, LANES);
+    if (valid && lane == 0) {
+      double r;
+      if (EPI == EPI_SET) r = sum;
+      else if (EPI == EPI_RESID) r = b[row] - sum;
+      else if (EPI == EPI_JACOBI) r = x[row] + w * dinv[row] * (b[row] - sum);
+      else r = out[row] + sum;
+      out[row] = r;
+    }
+  }
+}
+
+template <int LANES>
+static int launch_spmv_l(int grid, int n_rows, const int32_t* indptr, const int32_t* indices, const double* vals,
+                         const double* x, double* out, int epi, const double* b, const double* dinv, double w,
+                         cudaStream_t st) {
+  switch (epi) {
+    case EPI_SET: spmv_kernel<LANES, EPI_SET><<<grid, 256, 0, st>>>(n_rows, indptr, indices, vals, x, out, b, dinv, w); break;
+    case EPI_RESID: spmv_kernel<LANES, EPI_RESID><<<grid, 256, 0, st>>>(n_rows, indptr, indices, vals, x, out, b, dinv, w); break;
+    case EPI_JACOBI: spmv_kernel<LANES, EPI_JACOBI><<<grid, 256, 0, st>>>(n_rows, indptr, indices, vals, x, out, b, dinv, w); break;
+    default: spmv_kernel<LANES, EPI_ADD><<<grid, 256, 0, st>>>(n_rows, indptr, indices, vals, x, out, b, dinv, w); break;
+  }
+  KNP_CUDA(cudaGetLastError());
+  return KNP_OK;
+}
+
+int launch_spmv(int n_rows, int64_t nnz, const int32_t* indptr, const int32_t* indices, const double* vals,
+                const double* x, double* out, int epi, const double* b, const double* dinv, double w,
+                cudaStream_t st) {
+  if (n_rows == 0) return KNP_OK;
+  const double avg = (double)nnz / n_rows;
+  int lanes = avg <= 3 ? 2 : avg <= 6 ? 4 : avg <= 12 ? 8 : avg <= 40 ? 16 : 32;
+  const int rows_per_block = 256 / lanes;
+  const int64_t want = ((int64_t)n_rows + rows_per_block - 1) / rows_per_block;
+  const int grid = (int)(want < (int64_t)148 * 64 ? want : (int64_t)148 * 64);
+  switch (lanes) {
+    case 2: return launch_spmv_l<2>(grid, n_rows, indptr, indices, vals, x, out, epi, b, dinv, w, st);
+    case 4: return launch_spmv_l<4>(grid, n_rows, indptr, indices, vals, x, out, epi, b, dinv, w, st);
+    case 8: return launch_spmv_l<8>(grid, n_rows, indptr, indices, vals, x, out, epi, b, dinv, w, st);
+    case 16: return launch_spmv_l<16>(grid, n_rows, indptr, indices, vals, x, out, epi, b, dinv, w, st);
+    default: return launch_spmv_l<32>(grid, n_rows, indptr, indices, vals, x, out, epi, b, dinv, w, st);
+  }
+}
+
+__global__ void scale_dinv_kernel(int n, double w, const double* __restrict__ dinv, const double* __restrict__ b,
+                                  double* __restrict__ x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) x[i] = w * dinv[i] * b[i];
+}
+int launch_scale_dinv(int n, double w, const double* dinv, const double* b, double* x, cudaStream_t st) {
+  if (n == 0) return KNP_OK;
+  int grid = (n + 255) / 256;
+  if (grid > 148 * 16) grid = 148 * 16;
+  scale_dinv_kernel<<<grid, 256, 0, st>>>(n, w, dinv, b, x);
+  KNP_CUDA(cudaGetLastError());
+  return KNP_OK;
+}
+
+__global__ void extract_dinv_kernel(int n_rows, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                    const double* __restrict__ vals, double* __restrict__ dinv) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n_rows) return;
+  double d = 0.0;
+  for (int j = indptr[row]; j < indptr[row + 1]; ++j)
+    if (indices[j] == row) d += vals[j];
+  dinv[row] = 1.0 / d;
+}
+int launch_extract_dinv(int n_rows, const int32_t* indptr, const int32_t* indices, const double* vals, double* dinv,
+                        cudaStream_t st) {
+  if (n_rows == 0) return KNP_OK;
+  extract_dinv_kernel<<<(n_rows + 255) / 256, 256, 0, st>>>(n_rows, indptr, indices, vals, dinv);
+  KNP_CUDA(cudaGetLastError());
+  return KNP_OK;
+}
+
+// x = Minv b, Minv dense row-major n x n; one warp per row
+__global__ void dense_gemv_kernel(int n, const double* __restrict__ M, const double* __restrict__ b,
+                                  double* __restrict__ x) {
+  const int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  double s = 0.0;
+  for (int j = lane; j < n; j += 32) s += M[(size_t)row * n + j] * b[j];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+  if (lane == 0) x[row] = s;
+}
+int launch_dense_gemv(int n, const double* Minv, const double* b, double* x, cudaStream_t st) {
+  if (n == 0) return KNP_OK;
+  dense_gemv_kernel<<<(n + 7) / 8, 256, 0, st>>>(n, Minv, b, x);
+  KNP_CUDA(cudaGetLastError());
+  return KNP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ reductions
+__device__ __forceinline__ double block_reduce_256(double v, double* red) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r += red[i];
+  }
+  __syncthreads();
+  return r;
+}
+
+constexpr int MD_CHUNK = 8;   // basis vectors handled per pass over w
+
+// partial[(j)*RED_BLOCKS + blk] ; j in [j0, j0+cnt) for V rows, and slot m for ||w||^2 when with_norm
+__global__ void __launch_bounds__(256) multi_dot_kernel(int n, int j0, int cnt, int m, int with_norm,
+                                                        const double* __restrict__ V, size_t ldv,
+                                                        const double* __restrict__ w, double* __restrict__ partial) {
+  __shared__ double red[8];
+  double acc[MD_CHUNK + 1];
+#pragma unroll
+  for (int j = 0; j <= MD_CHUNK; ++j) acc[j] = 0.0;
+  // contiguous slab per block => fixed summation order independent of the launch schedule
+  const int per = (n + gridDim.x - 1) / gridDim.x;
+  const int lo = blockIdx.x * per;
+  const int hi = min(n, lo + per);
+  for (int i = lo + threadIdx.x; i < hi; i += 256) {
+    const double wi = w[i];
+#pragma unroll
+    for (int j = 0; j < MD_CHUNK; ++j)
+      if (j < cnt) acc[j] += V[(size_t)(j0 + j) * ldv + i] * wi;
+    acc[MD_CHUNK] += wi * wi;
+  }
+#pragma unroll
+  for (int j = 0; j < MD_CHUNK; ++j) {
+    if (j < cnt) {
+      const double r = block_reduce_256(acc[j], red);
+      if (threadIdx.x == 0) partial[(size_t)(j0 + j) * RED_BLOCKS + blockIdx.x] = r;
+    }
+  }
+  if (with_norm) {
+    const double r = block_reduce_256(acc[MD_CHUNK], red);
+    if (threadIdx.x == 0) partial[(size_t)m * RED_BLOCKS + blockIdx.x] = r;
+  }
+}
+
+// out[j] = sum_blk partial[j*RED_BLOCKS + blk], fixed order; one warp per j
+__global__ void reduce_rows_kernel(int rows, int n_partial, const double* __restrict__ partial,
+                                   double* __restrict__ out) {
+  const int j = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  const int lane = threadIdx.x & 31;
+  if (j >= rows) return;
+  double s = 0.0;
+  for (int i = lane; i < n_partial; i += 32) s += partial[(size_t)j * n_partial + i];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+  if (lane == 0) out[j] = s;
+}
+
+int launch_multi_dot(int n, int m, const double* V, size_t ldv, const double* w, double* partial, double* out,
+                     cudaStream_t st) {
+  if (m == 0) {
+    multi_dot_kernel<<<RED_BLOCKS, 256, 0, st>>>(n, 0, 0, 0, 1, V, ldv, w, partial);
+    KNP_CUDA(cudaGetLastError());
+  }
+  for (int j0 = 0; j0 < m; j0 += MD_CHUNK) {
+    const int cnt = m - j0 < MD_CHUNK ? m - j0 : MD_CHUNK;
+    multi_dot_kernel<<<RED_BLOCKS, 256, 0, st>>>(n, j0, cnt, m, j0 == 0 ? 1 : 0, V, ldv, w, partial);
+    KNP_CUDA(cudaGetLastError());
+  }
+  reduce_rows_kernel<<<(m + 1 + 7) / 8, 256, 0, st>>>(m + 1, RED_BLOCKS, partial, out);
+  KNP_CUDA(cudaGetLastError());
+  return KNP_OK;
+}
+
+__global__ void __launch_bounds__(256) multi_axpy_kernel(int n, int m, const double* __restrict__ V, size_t ldv,
+                                                         const double* __restrict__ h, double sign,
+                                                         double* __restrict__ w) {
+  __shared__ double hs[64];
+  if (threadIdx.x < m) hs[threadIdx.x] = h[threadIdx.x];
+  __syncthreads();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    for (int j = 0; j < m; ++j) acc += hs[j] * V[(size_t)j * ldv + i];
+    w[i] += sign * acc;
+  }
+}
+static int grid_for(int n) {
+  int grid = (n + 255) / 256;
+  if (grid > 148 * 16) grid = 148 * 16;
+  return grid < 1 ? 1 : grid;
+}
+int launch_multi_axpy(int n, int m, const double* V, size_t ldv, const double* h, double* w, cudaStream_t st) {
+  if (n == 0 || m == 0) return KNP_OK;
+  multi_axpy_kernel<<<grid_for(n), 256, 0, st>>>(n, m, V, ldv, h, -1.0, w);
+  KNP_CUDA(cudaGetLastError());
+  return KNP_OK;
+}
+int launch_update_x(int n, int m, const double* V, size_t ldv, const double* y_dev, double* x, cudaStream_t st) {
+  if (n == 0 || m == 0) return KNP_OK;
+  multi_axpy_kernel<<<grid_for(n), 256, 0, st>>>(n, m, V, ldv, y_dev, 1.0, x);
+  KNP_CUDA(cudaGetLastError());
+  return KNP_OK;
+}
+
+__global__ void axpby_kernel(int n, double a, const double* __restrict__ x, double b, double* __restrict__ y) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    y[i] = a * x[i] + (b == 0.0 ? 0.0 : b * y[i]);
+}
+int launch_axpby(int n, double a, const double* x, double b, double* y, cudaStream_t st) {
+  if (n == 0) return KNP_OK;
+  axpby_kernel<<<grid_for(n), 256, 0, st>>>(n, a, x, b, y);
+  KNP_CUDA(cudaGetLastError());
+  return KNP_OK;
+}
+
+__global__ void scale_copy_kernel(int n, const double* __restrict__ alpha, int invert, const double* __restrict__ x,
+                                  double* __restrict__ y) {
+  const double a = invert ? 1.0 / sqrt(alpha[0]) : alpha[0];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) y[i] = a * x[i];
+}
+// invert=1: y = x / sqrt(alpha[0])  (normalise by a squared norm held on the device)
+int launch_scale_copy(int n, const double* alpha_dev, int invert, const double* x, double* y, cudaStream_t st) {
+  if (n == 0) return KNP_OK;
+  scale_copy_kernel<<<grid_for(n), 256, 0, st>>>(n, alpha_dev, invert, x, y);
+  KNP_CUDA(cudaGetLastError());
+  return KNP_OK;
+}
+
+__global__ void __launch_bounds__(256) range_sum_kernel(const double* __restrict__ x, int lo0, int hi0, int lo1,
+                                                        int hi1, double* __restrict__ partial) {
+  __shared__ double red[8];
+  const int n0 = hi0 - lo0, n = n0 + (hi1 - lo1);
+  const int per = (n + gridDim.x - 1) / gridDim.x;
+  const int lo = blockIdx.x * per, hi = min(n, lo + per);
+  double acc = 0.0;
+  for (int i = lo + threadIdx.x; i < hi; i += 256) acc += x[i < n0 ? lo0 + i : lo1 + (i - n0)];
+  const double r = block_reduce_256(acc, red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = r;
+}
+int launch_range_sum(const double* x, int lo0, int hi0, int lo1, int hi1, double* partial, double* out,
+                     cudaStream_t st) {
+  range_sum_kernel<<<RED_BLOCKS, 256, 0, st>>>(x, lo0, hi0, lo1, hi1, partial);
+  KNP_CUDA(cudaGetLastError());
+  reduce_rows_kernel<<<1, 32, 0, st>>>(1, RED_BLOCKS, partial, out);
+  KNP_CUDA(cudaGetLastError());
+  return KNP_OK;
+}
+__global__ void range_shift_kernel(double* __restrict__ x, int lo0, int hi0, int lo1, int hi1,
+                                   const double* __restrict__ sum, double inv_count) {
+  const int n0 = hi0 - lo0, n = n0 + (hi1 - lo1);
+  const double sh = sum[0] * inv_count;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    x[i < n0 ? lo0 + i : lo1 + (i - n0)] -= sh;
+}
+int launch_range_shift(double* x, int lo0, int hi0, int lo1, int hi1, const double* sum_dev, double inv_count,
+                       cudaStream_t st) {
+  const int n = (hi0 - lo0) + (hi1 - lo1);
+  if (n == 0) return KNP_OK;
+  range_shift_kernel<<<grid_for(n), 256, 0, st>>>(x, lo0, hi0, lo1, hi1, sum_dev, inv_count);
+  KNP_CUDA(cudaGetLastError());
+  return KNP_OK;
+}
+int launch_reduce_partials(const double* partial, int n_partial, double* out, cudaStream_t st) {
+  reduce_rows_kernel<<<1, 32, 0, st>>>(1, n_partial, partial, out);
+  KNP_CUDA(cudaGetLastError());
+  return KNP_OK;
+}
+
+}  // namespace knp

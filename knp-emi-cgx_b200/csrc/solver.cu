@@ -1,0 +1,323 @@
+// GPU Krylov solver: left-preconditioned restarted GMRES with classical Gram-Schmidt (two passes),
+// preconditioned-norm convergence test relative to ||B b||, nullspace removal after every preconditioner
+// application -- the semantics of the reference's PETSc KSP configuration
+// (KNPEMIx_solver.py:212-214,276-280,324-333,386-389,435; PETSc defaults restated in SURVEY.md Appendix F).
+// The preconditioner B is one V(1,1) cycle of our smoothed-aggregation hierarchy on P (amg_setup.cpp),
+// Jacobi on P, or the identity.
+#include <cmath>
+#include "context.cuh"
+
+namespace knp {
+
+int ensure_workspace(knp_ctx* c, int restart) {
+  const size_t ncols = (size_t)c->T.L.n_cols;
+  if (c->ws_restart >= restart && c->V.p) return KNP_OK;
+  c->ldv = (ncols + 31) / 32 * 32;
+  KNP_TRY(c->V.alloc(c->ldv * (restart + 1)));
+  KNP_CUDA(cudaMemset(c->V.p, 0, c->ldv * (restart + 1) * sizeof(double)));
+  KNP_TRY(c->w.alloc(c->ldv));
+  KNP_TRY(c->tmp.alloc(c->ldv));
+  KNP_CUDA(cudaMemset(c->w.p, 0, c->ldv * sizeof(double)));
+  KNP_CUDA(cudaMemset(c->tmp.p, 0, c->ldv * sizeof(double)));
+  KNP_TRY(c->partial.alloc((size_t)(restart + 2) * RED_BLOCKS));
+  KNP_TRY(c->hdev.alloc(restart + 2));
+  KNP_TRY(c->ydev.alloc(restart + 2));
+  if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  KNP_CUDA(cudaMallocHost(&c->h_pinned, (restart + 2) * sizeof(double)));
+  c->ws_restart = restart;
+  return KNP_OK;
+}
+
+static int upload_csr(const CsrHost& h, CsrDev& d) {
+  d.n_rows = h.n_rows;
+  d.n_cols = h.n_cols;
+  d.nnz = h.nnz();
+  KNP_TRY(d.indptr.upload(h.indptr));
+  KNP_TRY(d.indices.upload(h.indices));
+  KNP_TRY(d.vals.upload(h.vals));
+  return KNP_OK;
+}
+
+int pc_setup(knp_ctx* c, const knp_solve_opts* o) {
+  const int n = c->T.L.n_rows;
+  c->amg.reset();
+  c->pc_kind = o->pc;
+  if (o->pc == 0) return KNP_OK;
+  if (!c->P_assembled) {
+    set_error("knp_pc_setup: assemble P first (knp_assemble_P)");
+    return KNP_E_INVALID;
+  }
+  if (o->pc == 1) {
+    KNP_TRY(c->pc_dinv.alloc(n));
+    KNP_TRY(launch_extract_dinv(n, c->d_indptr_P.p, c->d_indices_P.p, c->P_vals.p, c->pc_dinv.p, c->stream));
+    KNP_CUDA(cudaStreamSynchronize(c->stream));
+    return KNP_OK;
+  }
+  if (o->pc != 2) {
+    set_error("unknown preconditioner kind %d", o->pc);
+    return KNP_E_INVALID;
+  }
+  // host copy of the owned-column part of P (processor-local block on multi-GPU runs)
+  CsrHost P0;
+  {
+    std::vector<int32_t> idx(c->H.nnz_P);
+    std::vector<double> val(c->H.nnz_P);
+    KNP_CUDA(cudaStreamSynchronize(c->stream));
+    KNP_CUDA(cudaMemcpy(idx.data(), c->d_indices_P.p, idx.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    KNP_CUDA(cudaMemcpy(val.data(), c->P_vals.p, val.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    P0.n_rows = n;
+    P0.n_cols = n;
+    P0.indptr.assign(n + 1, 0);
+    P0.indices.reserve(idx.size());
+    P0.vals.reserve(idx.size());
+    for (int i = 0; i < n; ++i) {
+      for (int j = c->H.indptr_P[i]; j < c->H.indptr_P[i + 1]; ++j)
+        if (idx[j] < n) {
+          P0.indices.push_back(idx[j]);
+          P0.vals.push_back(val[j]);
+        }
+      P0.indptr[i + 1] = (int32_t)P0.indices.size();
+    }
+  }
+  std::vector<CsrHost> As, Ps, Rs;
+  std::vector<double> rhos, cinv;
+  KNP_TRY(amg_setup_host(P0, 0.08, 600, 16, As, Ps, Rs, rhos, cinv));
+  auto amg = std::make_unique<Amg>();
+  const int nl = (int)Ps.size();
+  for (int l = 0; l < nl; ++l) {
+    auto* lv = new AmgLevelDev();
+    amg->levels.push_back(lv);
+    KNP_TRY(upload_csr(As[l], lv->A));
+    KNP_TRY(upload_csr(Ps[l], lv->P));
+    KNP_TRY(upload_csr(Rs[l], lv->R));
+    lv->rho = rhos[l];
+    const int nr = As[l].n_rows;
+    KNP_TRY(lv->dinv.alloc(nr));
+    KNP_TRY(lv->x.alloc(nr));
+    KNP_TRY(lv->b.alloc(nr));
+    KNP_TRY(lv->r.alloc(nr));
+    KNP_TRY(launch_extract_dinv(nr, lv->A.indptr.p, lv->A.indices.p, lv->A.vals.p, lv->dinv.p, c->stream));
+  }
+  amg->n_coarse = As.back().n_rows;
+  KNP_TRY(amg->coarse_inv.upload(cinv));
+  KNP_TRY(amg->cb.alloc(amg->n_coarse));
+  KNP_TRY(amg->cx.alloc(amg->n_coarse));
+  amg->hostA = std::move(As);
+  KNP_CUDA(cudaStreamSynchronize(c->stream));
+  c->amg = std::move(amg);
+  return KNP_OK;
+}
+
+// z = V-cycle(r); level-l right-hand side in bl, result written to xout (distinct from bl)
+static int vcycle(knp_ctx* c, int l, const double* bl, double* xout, cudaStream_t st) {
+  Amg& M = *c->amg;
+  const int nl = (int)M.levels.size();
+  if (l == nl) return launch_dense_gemv(M.n_coarse, M.coarse_inv.p, bl, xout, st);
+  AmgLevelDev& L = *M.levels[l];
+  const int n = L.A.n_rows;
+  const double w = (4.0 / 3.0) / L.rho;
+  // pre-smooth from a zero initial guess
+  KNP_TRY(launch_scale_dinv(n, w, L.dinv.p, bl, L.x.p, st));
+  // r = b - A x ; b_{l+1} = R r
+  KNP_TRY(launch_spmv(n, L.A.nnz, L.A.indptr.p, L.A.indices.p, L.A.vals.p, L.x.p, L.r.p, EPI_RESID, bl, nullptr, 0.0, st));
+  // child right-hand side; the child's result goes into this level's r, which is free after the restriction
+  double* bc = (l + 1 == nl) ? M.cb.p : M.levels[l + 1]->b.p;
+  double* xc = L.r.p;
+  KNP_TRY(launch_spmv(L.R.n_rows, L.R.nnz, L.R.indptr.p, L.R.indices.p, L.R.vals.p, L.r.p, bc, EPI_SET, nullptr, nullptr, 0.0, st));
+  KNP_TRY(vcycle(c, l + 1, bc, xc, st));
+  // x += P x_c
+  KNP_TRY(launch_spmv(n, L.P.nnz, L.P.indptr.p, L.P.indices.p, L.P.vals.p, xc, L.x.p, EPI_ADD, nullptr, nullptr, 0.0, st));
+  // post-smooth, out of place into xout
+  KNP_TRY(launch_spmv(n, L.A.nnz, L.A.indptr.p, L.A.indices.p, L.A.vals.p, L.x.p, xout, EPI_JACOBI, bl, L.dinv.p, w, st));
+  return KNP_OK;
+}
+
+__global__ void dinv_mul_kernel(int n, const double* __restrict__ dinv, const double* __restrict__ r, double* __restrict__ z) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) z[i] = dinv[i] * r[i];
+}
+
+int pc_apply(knp_ctx* c, const double* r, double* z, cudaStream_t st) {
+  const int n = c->T.L.n_rows;
+  if (c->pc_kind == 2 && c->amg) return vcycle(c, 0, r, z, st);
+  if (c->pc_kind == 1) {
+    int grid = (n + 255) / 256;
+    if (grid > 148 * 16) grid = 148 * 16;
+    dinv_mul_kernel<<<grid, 256, 0, st>>>(n, c->pc_dinv.p, r, z);
+    KNP_CUDA(cudaGetLastError());
+    return KNP_OK;
+  }
+  KNP_CUDA(cudaMemcpyAsync(z, r, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  return KNP_OK;
+}
+
+// x -= ns (ns . x): ns = normalised indicator of all phi_i and phi_e rows (KNPEMIx_solver.py:297-335)
+static int project_nullspace(knp_ctx* c, double* x, cudaStream_t st) {
+  const Layout& L = c->T.L;
+  const int lo0 = L.row(0, 3, 0), hi0 = lo0 + L.n_own[0];
+  const int lo1 = L.row(1, 3, 0), hi1 = lo1 + L.n_own[1];
+  KNP_TRY(launch_range_sum(x, lo0, hi0, lo1, hi1, c->partial.p, c->hdev.p, st));
+  KNP_TRY(allreduce_sum(c, c->hdev.p, 1, st));
+  const double cnt = c->nranks > 1 ? (double)c->n_phi_global : (double)(L.n_own[0] + L.n_own[1]);
+  return launch_range_shift(x, lo0, hi0, lo1, hi1, c->hdev.p, 1.0 / cnt, st);
+}
+
+int nullspace_remove(knp_ctx* c, double* x, cudaStream_t st) { return project_nullspace(c, x, st); }
+
+// z = B v  (+ nullspace removal)
+static int apply_B(knp_ctx* c, const knp_solve_opts* o, const double* v, double* z, cudaStream_t st) {
+  KNP_TRY(pc_apply(c, v, z, st));
+  if (o->project_nullspace) KNP_TRY(project_nullspace(c, z, st));
+  return KNP_OK;
+}
+
+static int spmv_A(knp_ctx* c, const double* A_vals, double* x, double* y, int epi, const double* b, cudaStream_t st) {
+  KNP_TRY(halo_exchange(c, x, st));
+  return launch_spmv(c->T.L.n_rows, c->H.nnz, c->d_indptr.p, c->d_indices.p, A_vals, x, y, epi, b, nullptr, 0.0, st);
+}
+
+// dots of w against V[0..m) plus ||w||^2 -> host (m+1 values)
+static int dots_to_host(knp_ctx* c, int m, const double* w, double* host, cudaStream_t st) {
+  const int n = c->T.L.n_rows;
+  KNP_TRY(launch_multi_dot(n, m, c->V.p, c->ldv, w, c->partial.p, c->hdev.p, st));
+  KNP_TRY(allreduce_sum(c, c->hdev.p, m + 1, st));
+  KNP_CUDA(cudaMemcpyAsync(host, c->hdev.p, (m + 1) * sizeof(double), cudaMemcpyDeviceToHost, st));
+  KNP_CUDA(cudaStreamSynchronize(st));
+  return KNP_OK;
+}
+
+int gmres_solve(knp_ctx* c, const double* A_vals, const double* b, double* x, const knp_solve_opts* o,
+                knp_solve_info* info, cudaStream_t st) {
+  const int n = c->T.L.n_rows;
+  const int m = o->restart > 0 ? o->restart : 30;
+  if (m > 62) {
+    set_error("GMRES restart %d > 62 not supported", m);
+    return KNP_E_INVALID;
+  }
+  KNP_TRY(ensure_workspace(c, m));
+  double* hp = c->h_pinned;
+  double* w = c->w.p;
+  double* tmp = c->tmp.p;
+  std::vector<double> H((size_t)(m + 1) * m, 0.0), g(m + 1, 0.0), cs(m, 0.0), sn(m, 0.0), y(m, 0.0);
+  auto Hat = [&](int i, int j) -> double& { return H[(size_t)i * m + j]; };
+
+  // ||B b||
+  KNP_TRY(apply_B(c, o, b, w, st));
+  KNP_TRY(dots_to_host(c, 0, w, hp, st));
+  const double bnorm = std::sqrt(hp[0]);
+  info->rnorm0 = bnorm;
+  info->iterations = 0;
+  info->converged = 0;
+  info->rnorm = bnorm;
+  if (!(bnorm == bnorm) || std::isinf(bnorm)) {
+    set_error("GMRES: right-hand side is not finite");
+    return KNP_E_NOCONV;
+  }
+  const double tol = o->rtol * bnorm;
+  int its = 0;
+  double prev_beta = -1.0;
+  int stagn = 0;
+  while (true) {
+    // r = B (b - A x)
+    KNP_TRY(spmv_A(c, A_vals, x, tmp, EPI_RESID, b, st));
+    KNP_TRY(apply_B(c, o, tmp, w, st));
+    KNP_TRY(dots_to_host(c, 0, w, hp, st));
+    const double beta = std::sqrt(hp[0]);
+    info->rnorm = beta;
+    if (!(beta == beta) || std::isinf(beta)) {
+      set_error("GMRES: residual is not finite after %d iterations", its);
+      info->iterations = its;
+      return KNP_E_NOCONV;
+    }
+    if (beta <= tol || bnorm == 0.0) {
+      info->converged = 1;
+      break;
+    }
+    if (its >= o->max_it) break;
+    if (o->refine > 0 && prev_beta > 0.0 && beta > 0.5 * prev_beta) {
+      // "direct" mode: the true preconditioned residual stopped improving -> at the fp64 floor
+      if (++stagn >= o->refine) {
+        info->converged = 2;
+        break;
+      }
+    }
+    prev_beta = beta;
+    // V0 = r / beta
+    KNP_TRY(launch_axpby(n, 1.0 / beta, w, 0.0, c->V.p, st));
+    std::fill(g.begin(), g.end(), 0.0);
+    g[0] = beta;
+    int jdone = 0;
+    bool done = false;
+    for (int j = 0; j < m; ++j) {
+      double* vj = c->V.p + (size_t)j * c->ldv;
+      KNP_TRY(spmv_A(c, A_vals, vj, tmp, EPI_SET, nullptr, st));
+      KNP_TRY(apply_B(c, o, tmp, w, st));
+      // classical Gram-Schmidt, two passes; every pass is one fused multi-dot and one fused multi-axpy
+      KNP_TRY(dots_to_host(c, j + 1, w, hp, st));
+      for (int i = 0; i <= j; ++i) Hat(i, j) = hp[i];
+      KNP_TRY(launch_multi_axpy(n, j + 1, c->V.p, c->ldv, c->hdev.p, w, st));
+      KNP_TRY(dots_to_host(c, j + 1, w, hp, st));
+      double h2sq = 0.0;
+      for (int i = 0; i <= j; ++i) {
+        Hat(i, j) += hp[i];
+        h2sq += hp[i] * hp[i];
+      }
+      KNP_TRY(launch_multi_axpy(n, j + 1, c->V.p, c->ldv, c->hdev.p, w, st));
+      double nrm2 = hp[j + 1] - h2sq;
+      if (nrm2 < 0.0) nrm2 = 0.0;
+      const double hn = std::sqrt(nrm2);
+      Hat(j + 1, j) = hn;
+      if (hn > 0.0) KNP_TRY(launch_axpby(n, 1.0 / hn, w, 0.0, c->V.p + (size_t)(j + 1) * c->ldv, st));
+      for (int i = 0; i < j; ++i) {
+        const double t = cs[i] * Hat(i, j) + sn[i] * Hat(i + 1, j);
+        Hat(i + 1, j) = -sn[i] * Hat(i, j) + cs[i] * Hat(i + 1, j);
+        Hat(i, j) = t;
+      }
+      const double den = std::hypot(Hat(j, j), Hat(j + 1, j));
+      cs[j] = Hat(j, j) / den;
+      sn[j] = Hat(j + 1, j) / den;
+      Hat(j, j) = den;
+      Hat(j + 1, j) = 0.0;
+      g[j + 1] = -sn[j] * g[j];
+      g[j] = cs[j] * g[j];
+      ++its;
+      jdone = j + 1;
+      info->rnorm = std::fabs(g[j + 1]);
+      if (!(den == den)) {
+        set_error("GMRES: breakdown (non-finite Hessenberg entry) at iteration %d", its);
+        info->iterations = its;
+        return KNP_E_NOCONV;
+      }
+      if (std::fabs(g[j + 1]) <= tol || its >= o->max_it || hn == 0.0) {
+        done = std::fabs(g[j + 1]) <= tol;
+        break;
+      }
+    }
+    // y = H^-1 g ; x += V y
+    for (int i = jdone - 1; i >= 0; --i) {
+      double s = g[i];
+      for (int k = i + 1; k < jdone; ++k) s -= Hat(i, k) * y[k];
+      y[i] = s / Hat(i, i);
+    }
+    for (int i = 0; i < jdone; ++i) hp[i] = y[i];
+    KNP_CUDA(cudaMemcpyAsync(c->ydev.p, hp, jdone * sizeof(double), cudaMemcpyHostToDevice, st));
+    KNP_TRY(launch_update_x(n, jdone, c->V.p, c->ldv, c->ydev.p, x, st));
+    KNP_CUDA(cudaStreamSynchronize(st));   // hp is reused by the next dots_to_host
+    if (done && o->refine == 0) {
+      info->converged = 1;
+      break;
+    }
+    if (its >= o->max_it && !done) {
+      // fall through to recompute the true residual once and exit
+    }
+  }
+  info->iterations = its;
+  if (o->zero_mean_solution) KNP_TRY(project_nullspace(c, x, st));
+  KNP_TRY(halo_exchange(c, x, st));
+  if (!info->converged) {
+    set_error("GMRES did not converge: %d iterations, ||B r|| = %.3e, tol = %.3e", its, info->rnorm, tol);
+    return KNP_E_NOCONV;
+  }
+  return KNP_OK;
+}
+
+}  // namespace knp

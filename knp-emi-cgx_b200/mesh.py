@@ -1,0 +1,192 @@
+"""Synthetic mesh fixtures and mesh-side tables for the KNP-EMI path (host side, setup time).
+
+Replaces, as input providers: src/CGx/utils/generate_square_mesh.py:28-42 with the tagging rules of
+src/CGx/utils/misc.py:99-195 (square) and :256-398 (cube), the XDMF read of
+src/CGx/utils/mixed_dim_problem.py:634-681 (no HDF5 reader exists in this image: meshes are generated in
+memory from the file name or from a ``synthetic_mesh`` block in the YAML file), and the '+' = intracellular
+orientation of membrane facets (:708-729).  For continuous P1 fields the orientation only matters through
+which cell supplies which trace, so a membrane facet is stored as its vertex list plus its tag.
+"""
+from dataclasses import dataclass, field
+import numpy as np
+
+
+@dataclass
+class Mesh:
+    gdim: int
+    x: np.ndarray           # (Nv, gdim) float64, scaled
+    cells: np.ndarray       # (Nc, gdim+1) int32
+    cell_tags: np.ndarray   # (Nc,) int32
+    intra_tags: tuple
+    extra_tag: int
+    mf_verts: np.ndarray    # (Nf, gdim) int32
+    mf_tags: np.ndarray     # (Nf,) int32
+    grid: tuple = None      # (N, ...) for structured fixtures (used by the block partitioner)
+    # distributed extras (None on a single GPU)
+    n_owned: int = None
+    cell_owned: np.ndarray = None
+    mf_owned: np.ndarray = None
+    vert_global: np.ndarray = None
+
+
+# ------------------------------------------------------------------------------------------ quadrature
+def _gauss_jacobi_10(n):
+    """Gauss-Jacobi nodes/weights for the weight (1 - t) on [-1, 1] (Golub-Welsch)."""
+    al, be = 1.0, 0.0
+    k = np.arange(n, dtype=float)
+    a = (be ** 2 - al ** 2) / ((2 * k + al + be) * (2 * k + al + be + 2))
+    kk = np.arange(1, n, dtype=float)
+    b = 2.0 / (2 * kk + al + be) * np.sqrt(kk * (kk + al) * (kk + be) * (kk + al + be)
+                                           / ((2 * kk + al + be - 1) * (2 * kk + al + be + 1)))
+    J = np.diag(a) + np.diag(b, 1) + np.diag(b, -1)
+    t, V = np.linalg.eigh(J)
+    w = 2.0 * V[0] ** 2
+    return t, w
+
+
+def facet_quadrature(gdim, npts=6):
+    """Degree >= 10 rule on the membrane facet (quadrature_degree 10, mixed_dim_problem.py:732-733):
+    6-point Gauss-Legendre on edges (what basix uses); collapsed Gauss-Legendre x Gauss-Jacobi(1,0) with
+    6 x 6 points on triangles (basix's 25-point Xiao-Gimbutas table is not available offline).
+    Returns barycentric points (nq, gdim) and weights summing to 1."""
+    tu, wu = np.polynomial.legendre.leggauss(npts)
+    u, wu = 0.5 * (tu + 1.0), 0.5 * wu
+    if gdim == 2:
+        return np.stack([1.0 - u, u], 1), wu
+    tv, wv = _gauss_jacobi_10(npts)
+    v, wv = 0.5 * (tv + 1.0), 0.25 * wv
+    U, V = np.meshgrid(u, v, indexing="ij")
+    l1 = V.ravel()
+    l2 = (U * (1.0 - V)).ravel()
+    return np.stack([1.0 - l1 - l2, l1, l2], 1), (np.outer(wu, wv).ravel() * 2.0)
+
+
+# ------------------------------------------------------------------------------------------ grids
+def _square_cells(n):
+    ix, iy = np.meshgrid(np.arange(n, dtype=np.int64), np.arange(n, dtype=np.int64), indexing="xy")
+    v0 = (iy * (n + 1) + ix).ravel()
+    v1, v2, v3 = v0 + 1, v0 + n + 1, v0 + n + 2
+    c = np.empty((v0.size, 2, 3), np.int32)
+    c[:, 0, 0], c[:, 0, 1], c[:, 0, 2] = v0, v1, v3
+    c[:, 1, 0], c[:, 1, 1], c[:, 1, 2] = v0, v2, v3
+    return c.reshape(-1, 3)
+
+
+def _cube_cells(n):
+    iz, iy, ix = np.meshgrid(np.arange(n, dtype=np.int64), np.arange(n, dtype=np.int64),
+                             np.arange(n, dtype=np.int64), indexing="ij")
+    m = n + 1
+    v0 = (iz * m * m + iy * m + ix).ravel()
+    v1, v2, v3 = v0 + 1, v0 + m, v0 + m + 1
+    v4, v5, v6, v7 = v0 + m * m, v1 + m * m, v2 + m * m, v3 + m * m
+    tets = [(v0, v1, v3, v7), (v0, v1, v7, v5), (v0, v5, v7, v4), (v0, v3, v2, v7), (v0, v6, v4, v7), (v0, v2, v6, v7)]
+    c = np.empty((v0.size, 6, 4), np.int32)
+    for j, t in enumerate(tets):
+        for a in range(4):
+            c[:, j, a] = t[a]
+    return c.reshape(-1, 4)
+
+
+def _grid_coords(n, gdim):
+    g = np.arange(n + 1) / n
+    if gdim == 2:
+        X, Y = np.meshgrid(g, g, indexing="xy")
+        return np.stack([X.ravel(), Y.ravel()], 1)
+    Z, Y, X = np.meshgrid(g, g, g, indexing="ij")
+    return np.stack([X.ravel(), Y.ravel(), Z.ravel()], 1)
+
+
+def membrane_facets(cells, cell_tags, intra_tags, extra_tag, membrane_tag=None):
+    """Facets shared by an intracellular and an extracellular cell.  membrane_tag=None -> the facet
+    carries the tag of its intracellular cell (production convention, configs/5m/100c.yaml:27-30)."""
+    cells = np.asarray(cells)
+    nc, nv = cells.shape
+    d = nv - 1
+    is_in = np.isin(cell_tags, np.asarray(intra_tags))
+    is_ex = cell_tags == extra_tag
+    nvert = int(cells.max()) + 1
+    vi = np.zeros(nvert, bool)
+    ve = np.zeros(nvert, bool)
+    vi[cells[is_in].ravel()] = True
+    ve[cells[is_ex].ravel()] = True
+    mv = vi & ve
+    cand = np.flatnonzero((mv[cells].sum(1) >= d) & (is_in | is_ex))
+    cc = cells[cand]
+    loc = [tuple(j for j in range(nv) if j != i) for i in range(nv)]
+    fac = np.concatenate([cc[:, l] for l in loc], 0)
+    owner = np.tile(cand, nv)
+    onm = np.all(mv[fac], axis=1)
+    fac, owner = fac[onm], owner[onm]
+    key = np.sort(fac, 1)
+    order = np.lexsort(tuple(key[:, j] for j in range(d - 1, -1, -1)))
+    ks, ow = key[order], owner[order]
+    same = np.all(ks[1:] == ks[:-1], axis=1)
+    c0, c1 = ow[:-1][same], ow[1:][same]
+    mixed = is_in[c0] != is_in[c1]
+    c0, c1, fv = c0[mixed], c1[mixed], ks[:-1][same][mixed]
+    ci = np.where(is_in[c0], c0, c1)
+    tags = cell_tags[ci] if membrane_tag is None else np.full(ci.shape, membrane_tag)
+    return fv.astype(np.int32), tags.astype(np.int32)
+
+
+def unit_square_fixture(n=32, scale=1e-6):
+    """The reference CI fixture: intra 1 = cells with all vertices in [0.25,0.75]^2, extra 2, membrane 4."""
+    x = _grid_coords(n, 2)
+    cells = _square_cells(n)
+    inside = (x[:, 0] <= 0.75) & (x[:, 0] >= 0.25) & (x[:, 1] <= 0.75) & (x[:, 1] >= 0.25)
+    tags = np.where(np.all(inside[cells], axis=1), 1, 2).astype(np.int32)
+    fv, ft = membrane_facets(cells, tags, (1,), 2, membrane_tag=4)
+    return Mesh(2, x * scale, cells, tags, (1,), 2, fv, ft, grid=(n, n))
+
+
+def unit_cube_fixture(n=8, scale=1e-6):
+    x = _grid_coords(n, 3)
+    cells = _cube_cells(n)
+    inside = np.all((x <= 0.75) & (x >= 0.25), axis=1)
+    tags = np.where(np.all(inside[cells], axis=1), 1, 2).astype(np.int32)
+    fv, ft = membrane_facets(cells, tags, (1,), 2, membrane_tag=4)
+    return Mesh(3, x * scale, cells, tags, (1,), 2, fv, ft, grid=(n, n, n))
+
+
+def cell_array_mesh(gdim, n, m, scale=1e-6, fill=0.5, first_tag=2, extra_tag=1):
+    """Synthetic tissue block (BASELINE configs C3/C4): an m^gdim array of square/cubic biological cells.
+    Cell (p,q[,r]) occupies the middle `fill` fraction of its n/m-wide block; intracellular tags
+    first_tag..first_tag+m^gdim-1, extracellular tag `extra_tag`, membrane tag = intracellular tag."""
+    assert n % m == 0
+    bs = n // m
+    lo = int(round(bs * (1 - fill) / 2))
+    hi = bs - lo
+    idx = np.arange(n)
+    blk, off = idx // bs, idx % bs
+    ins = (off >= lo) & (off < hi)
+    if gdim == 2:
+        IN = ins[None, :] & ins[:, None]                       # [iy, ix]
+        tag = first_tag + blk[:, None] * m + blk[None, :]      # q*m + p
+        gt = np.where(IN, tag, extra_tag).ravel()
+        cells = _square_cells(n)
+        tags = np.repeat(gt, 2).astype(np.int32)
+    else:
+        IN = ins[:, None, None] & ins[None, :, None] & ins[None, None, :]   # [iz, iy, ix]
+        tag = first_tag + (blk[:, None, None] * m + blk[None, :, None]) * m + blk[None, None, :]
+        gt = np.where(IN, tag, extra_tag).ravel()
+        cells = _cube_cells(n)
+        tags = np.repeat(gt, 6).astype(np.int32)
+    x = _grid_coords(n, gdim)
+    intra = tuple(range(first_tag, first_tag + m ** gdim))
+    fv, ft = membrane_facets(cells, tags, intra, extra_tag)
+    return Mesh(gdim, x * scale, cells, tags, intra, extra_tag, fv, ft, grid=(n,) * gdim)
+
+
+def from_descriptor(desc, scale):
+    """``synthetic_mesh`` YAML block -> Mesh.  kinds: square, cube (reference fixtures), cell_array."""
+    kind = desc.get("kind", "square")
+    n = int(desc.get("N", 32))
+    if kind == "square":
+        return unit_square_fixture(n, scale)
+    if kind == "cube":
+        return unit_cube_fixture(n, scale)
+    if kind == "cell_array":
+        return cell_array_mesh(int(desc.get("dim", 2)), n, int(desc.get("cells_per_dim", 8)), scale,
+                               float(desc.get("fill", 0.5)), int(desc.get("first_tag", 2)),
+                               int(desc.get("extra_tag", 1)))
+    raise ValueError(f"unknown synthetic_mesh kind {kind!r}")

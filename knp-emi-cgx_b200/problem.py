@@ -1,0 +1,626 @@
+"""ProblemKNPEMI: host-side mirror of the reference's problem classes.
+
+Mirrors src/CGx/utils/mixed_dim_problem.py (MixedDimensionalProblem: YAML schema :86-374, tag parsing
+:376-433, init_ionic_models :435-465) and src/CGx/KNPEMI/KNPEMIx_problem.py (ProblemKNPEMI: spaces and
+restrictions :28-94, initial conditions :220-452, constants :909-981, class defaults :983-997) with the same
+public names, argument meaning and error behaviour.  What differs is *where the forms live*: instead of
+building UFL forms that FFCx JIT-compiles, ``setup_variational_form`` creates a device context in
+libknpemi_b200.so whose CUDA kernels evaluate exactly those forms (csrc/assembly.cu).
+"""
+import os
+import re
+import time
+import collections.abc
+import numpy as np
+import yaml
+
+from . import lib as _lib
+from . import mesh as _mesh
+from .comm import Comm, MPI
+
+
+def range_constructor(loader, node):
+    """!range [a, b] -> list(range(a, b))   (src/CGx/utils/misc.py:33-37)."""
+    return list(range(*loader.construct_sequence(node)))
+
+
+def flatten_list(input_list):
+    return [item for sub in input_list for item in (sub if isinstance(sub, tuple) else [sub])]
+
+
+class Constant:
+    """Stand-in for dolfinx.fem.Constant: a mutable scalar with a ``.value``."""
+
+    def __init__(self, value):
+        self.value = value
+
+    def __float__(self):
+        return float(self.value)
+
+    def __repr__(self):
+        return f"Constant({self.value})"
+
+
+class _Vector:
+    def __init__(self, fn):
+        self._fn = fn
+
+    @property
+    def array(self):
+        self._fn._problem._sync_host()
+        return self._fn._data
+
+    def scatter_forward(self):
+        pass
+
+
+class Function:
+    """Stand-in for dolfinx.fem.Function on the whole (local) mesh: ``.x.array`` is a numpy view that is
+    refreshed from the device state on access."""
+
+    def __init__(self, problem, n, name=""):
+        self._problem = problem
+        self._data = np.zeros(n)
+        self.name = name
+        self.x = _Vector(self)
+
+
+class _IndexMap:
+    def __init__(self, size_local, num_ghosts=0):
+        self.size_local = size_local
+        self.num_ghosts = num_ghosts
+
+
+class _Restriction:
+    """Stand-in for multiphenicsx.fem.DofMapRestriction (KNPEMIx_problem.py:88-89)."""
+
+    def __init__(self, dofs, n_owned):
+        self.dofs = dofs
+        self.index_map = _IndexMap(int(n_owned), int(dofs.size - n_owned))
+
+
+class Measure:
+    """problem.dx(tag): only used to take norms in the reference drivers (tests/KNPEMI/*.py:45-51)."""
+
+    def __init__(self, problem, tags=None):
+        self.problem = problem
+        self.tags = tags
+
+    def __call__(self, tags):
+        return Measure(self.problem, tuple(np.atleast_1d(tags).tolist()))
+
+
+class ProblemKNPEMI:
+    # Class settings (KNPEMIx_problem.py:983-997)
+    mesh_conversion_factor = 1.0
+    fem_order = 1
+    MMS_test = False
+    dirichlet_bcs = False
+    pin_ecs_potential = False
+    # physical defaults used when the config gives no physical_constants (mixed_dim_problem.py:193-195)
+    T_value = R_value = F_value = psi_value = 1.0
+
+    def __init__(self, config_file: str, comm: Comm = None, device: int = None, verbose: bool = True):
+        tic = time.perf_counter()
+        self.comm = comm if comm is not None else Comm()
+        self.verbose = verbose
+        self.device = device
+        self._print("Reading input data from " + str(config_file))
+        self.read_config_file(config_file=str(config_file))
+        self.setup_domain()
+        self.t = Constant(0.0)
+        self.dt = Constant(float(self.dt))
+        self.setup_constants()
+        self.setup_spaces()
+        self.init()
+        self.setup_boundary_conditions()
+        if self.source_terms == "ion_injection":
+            self.setup_source_terms()
+        self.ionic_models = []
+        self.gating_variables = False
+        self.ode_substeps, self.rush_larsen = 25, True
+        self._ctx = None
+        self._host_stale = False
+        self._print(f"Problem setup in {time.perf_counter() - tic:0.4f} seconds.\n")
+
+    # ------------------------------------------------------------------ helpers
+    def _print(self, *a):
+        if self.verbose and self.comm.rank == 0:
+            print(*a, flush=True)
+
+    # ------------------------------------------------------------------ config
+    def read_config_file(self, config_file):
+        """utils/mixed_dim_problem.py:86-374 (same keys, same RuntimeErrors)."""
+        yaml.add_constructor("!range", range_constructor, Loader=yaml.FullLoader)
+        with open(config_file, "r") as fh:
+            config = yaml.load(fh, Loader=yaml.FullLoader)
+        self.config = config
+        if "solver" in config:
+            self.solver_config = config["solver"]
+        else:
+            raise RuntimeError("Provide solver configuration in input file.")
+        input_dir = config.get("input_dir", "./")
+        self.output_dir = config.get("output_dir", "./output/")
+        if "cell_tag_file" in config and "facet_tag_file" in config:
+            mesh_file = input_dir + config["cell_tag_file"]
+            facet_file = input_dir + config["facet_tag_file"]
+            self.input_files = {"mesh_file": mesh_file, "facet_file": facet_file}
+            if "square" in mesh_file or mesh_file == facet_file:
+                self.ct_name, self.ft_name = "ct", "ft"
+            else:
+                self.ct_name = self.ft_name = "mesh"
+        elif "synthetic_mesh" in config:
+            self.input_files = {"mesh_file": "<synthetic>", "facet_file": "<synthetic>"}
+        else:
+            raise RuntimeError("Provide cell_tag_file and facet_tag_file fields in input file.")
+        self.synthetic_mesh = config.get("synthetic_mesh")
+        if "dt" in config:
+            self.dt = float(config["dt"])
+        else:
+            raise RuntimeError("Provide dt (timestep size) field in input file.")
+        if "time_steps" in config:
+            self.time_steps = int(config["time_steps"])
+        elif "T" in config:
+            self.time_steps = int(float(config["T"]) / float(config["dt"]))
+        else:
+            raise RuntimeError("Provide final time T or time_steps field in input file.")
+        tags = {}
+        if "ics_tags" in config:
+            tags["intra"] = config["ics_tags"]
+        else:
+            raise RuntimeError("Provide ics_tags (intracellular space tags) field in input file.")
+        if "ecs_tags" in config: tags["extra"] = config["ecs_tags"]
+        if "boundary_tags" in config: tags["boundary"] = config["boundary_tags"]
+        if "membrane_tags" in config: tags["membrane"] = config["membrane_tags"]
+        if "stimulus_tags" in config:
+            self.stimulus_tags = config["stimulus_tags"]
+        else:
+            self.stimulus_tags = tags.get("membrane", tags["intra"])
+        if "glia_tags" in config:
+            tags["glia"] = config["glia_tags"]
+            tags["neuron"] = [t for t in tags["intra"] if t not in tags["glia"]]
+        else:
+            tags["neuron"] = tags["intra"]
+        self.parse_tags(tags)
+        if "physical_constants" in config:
+            consts = config["physical_constants"]
+            if "T" in consts: self.T_value = consts["T"]
+            if "R" in consts: self.R_value = consts["R"]
+            if "F" in consts: self.F_value = consts["F"]
+            self.psi_value = self.R_value * self.T_value / self.F_value
+        else:
+            self.T_value = self.R_value = self.F_value = self.psi_value = 1.0
+        self.C_M_value = config.get("C_M", 1.0)
+        if "mesh_conversion_factor" in config:
+            self.mesh_conversion_factor = float(config["mesh_conversion_factor"])
+        if "fem_order" in config:
+            self.fem_order = config["fem_order"]
+        if "dirichlet_bcs" in config:
+            self.dirichlet_bcs = config["dirichlet_bcs"]
+        if "MMS_test" in config:
+            raise NotImplementedError("MMS_test is verification tooling outside the per-timestep path (SURVEY.md section 2, #8)")
+        if "ion_species" in config:
+            raise NotImplementedError("custom ion_species tables are not supported by the B200 path yet (Na/K/Cl only)")
+        self.source_terms = config.get("source_terms")
+        self.point_evaluation = "point_evaluation" in config
+        self.gamma_points = None
+        if "stimulus" in config:
+            try:
+                g_dict = config["stimulus"]["conductance"]
+                self.g_syn_bar_val = g_dict["g_syn_bar"]
+                self.a_syn_val = config["stimulus"]["a_syn"]
+                self.T_stim_val = config["stimulus"]["T_stim"]
+            except Exception:
+                raise RuntimeError("For stimulus, provide g_syn_bar, a_syn and T_stim in input file.")
+            if "tau_syn_rise" in config["stimulus"] or "tau_syn_decay" in config["stimulus"]:
+                try:
+                    self.tau_syn_rise = config["stimulus"]["tau_syn_rise"]
+                    self.tau_syn_decay = config["stimulus"]["tau_syn_decay"]
+                except Exception:
+                    raise RuntimeError("For rise and decay stimulus, provide tau_syn_rise and tau_syn_decay in input file.")
+            if "scale" in config["stimulus"]:
+                self.scale_stimulus = config["stimulus"]["scale"]
+            else:
+                raise RuntimeError("Provide whether to scale stimulus strength by surface area in stimulus configuration in input file.")
+            self.g_Na_bar_val = g_dict.get("g_Na_bar", 1200.0)
+            self.g_K_bar_val = g_dict.get("g_K_bar", 360.0)
+            self.g_Na_leak_val = g_dict.get("g_Na_leak", 0.3)
+            self.g_Na_leak_g_val = g_dict.get("g_Na_leak_g", 1.0)
+            self.g_K_leak_val = g_dict.get("g_K_leak", 0.1)
+            self.g_K_leak_g_val = g_dict.get("g_K_leak_g", 16.96)
+            self.g_Cl_leak_val = g_dict.get("g_Cl_leak", 0.25)
+            self.g_Cl_leak_g_val = g_dict.get("g_Cl_leak_g", 2.0)
+        else:
+            self.g_syn_bar_val, self.a_syn_val, self.T_stim_val, self.scale_stimulus = 40.0, 5e-4, 1.0, False
+            self.g_Na_bar_val, self.g_K_bar_val = 1200, 360
+            self.g_Na_leak_val, self.g_Na_leak_g_val = 1.0, 1.0
+            self.g_K_leak_val, self.g_K_leak_g_val = 4.0, 16.96
+            self.g_Cl_leak_val, self.g_Cl_leak_g_val = 0.25, 0.50
+        if "stimulus_region" in config:
+            self.stimulus_region = True
+            self.stimulus_region_range = np.array(config["stimulus_region"]["range"]) * self.mesh_conversion_factor
+            axes = {"x": 0, "y": 1, "z": 2}
+            if config["stimulus_region"].get("multiple", False):
+                raise NotImplementedError("stimulus_region with multiple directions is not supported by the B200 path yet")
+            self.multiple_stimulus_directions = False
+            self.stimulus_region_direction = axes[str(config["stimulus_region"]["direction"])]
+        else:
+            self.stimulus_region = False
+        if "initial_conditions" in config:
+            self.initial_conditions = config["initial_conditions"]
+            self.find_initial_conditions = False
+        else:
+            self.find_initial_conditions = True
+        if "membrane_data_tag" in config:
+            self.membrane_data_tag = int(config["membrane_data_tag"])
+        else:
+            self.membrane_data_tag = self.stimulus_tags[0] if len(self.stimulus_tags) > 0 else self.gamma_tags[0]
+
+    def parse_tags(self, tags: dict):
+        """utils/mixed_dim_problem.py:376-433."""
+        allowed = {"intra", "extra", "membrane", "boundary", "glia", "neuron"}
+        if not set(tags).issubset(allowed):
+            raise ValueError(f"Mismatch in tags.\nAllowed tags: {allowed}\nInput tags: {set(tags)}")
+        if isinstance(tags["intra"], collections.abc.Sequence):
+            self._print(f"# Cell tags = {len(tags['intra'])}.")
+        self.intra_tags = tags["intra"]
+        self.extra_tag = tags.get("extra", 1)
+        self.gamma_tags = tags.get("membrane", self.intra_tags)
+        if "glia" in tags:
+            self.glia_tags = tags["glia"]
+            self.glia_flag = len(self.glia_tags) > 0
+        else:
+            self.glia_tags, self.glia_flag = None, False
+        self.neuron_tags = tags["neuron"]
+        self.boundary_tags = tags.get("boundary", ())
+        as_tuple = lambda v: tuple(int(t) for t in (v if isinstance(v, collections.abc.Sequence) else (v,)))
+        self.intra_tags = as_tuple(self.intra_tags)
+        self.extra_tag = as_tuple(self.extra_tag)
+        self.boundary_tags = as_tuple(self.boundary_tags)
+        self.gamma_tags = as_tuple(self.gamma_tags)
+        self.neuron_tags = as_tuple(self.neuron_tags)
+        self.stimulus_tags = as_tuple(self.stimulus_tags)
+        if self.glia_flag:
+            self.glia_tags = as_tuple(self.glia_tags)
+        if len(self.extra_tag) != 1:
+            raise NotImplementedError("exactly one extracellular tag is supported (as in every reference config)")
+
+    # ------------------------------------------------------------------ domain
+    def setup_domain(self):
+        """Mesh ingest (utils/mixed_dim_problem.py:634-733).  There is no HDF5/XDMF reader in this image:
+        the fixture is generated in memory from ``synthetic_mesh`` or from the file name
+        (``square{N}.xdmf`` / ``cube{N}.xdmf``, as written by utils/generate_square_mesh.py)."""
+        if self.synthetic_mesh is not None:
+            m = _mesh.from_descriptor(self.synthetic_mesh, self.mesh_conversion_factor)
+        else:
+            base = os.path.basename(self.input_files["mesh_file"])
+            mt = re.match(r"(square|cube)(\d+)\.xdmf$", base)
+            if not mt:
+                raise RuntimeError(f"Cannot read {self.input_files['mesh_file']}: no XDMF/HDF5 reader is available; "
+                                   "use a square{N}.xdmf / cube{N}.xdmf fixture name or a synthetic_mesh block.")
+            n = int(mt.group(2))
+            m = (_mesh.unit_square_fixture if mt.group(1) == "square" else _mesh.unit_cube_fixture)(
+                n, self.mesh_conversion_factor)
+        if not (all(t < self.extra_tag[0] for t in self.intra_tags) or all(t > self.extra_tag[0] for t in self.intra_tags)):
+            raise RuntimeError("Intracellular tags must be all smaller or all larger than extracellular tag.")
+        # keep only membrane facets whose tag is listed, check the listed tags exist
+        keep = np.isin(m.mf_tags, np.asarray(self.gamma_tags))
+        m.mf_verts, m.mf_tags = m.mf_verts[keep], m.mf_tags[keep]
+        m.intra_tags, m.extra_tag = self.intra_tags, self.extra_tag[0]
+        self.global_mesh_info = dict(n_vertices=m.x.shape[0], n_cells=m.cells.shape[0])
+        if self.comm.size > 1:
+            from .partition import partition_mesh
+            m, self.halo = partition_mesh(m, self.comm.rank, self.comm.size)
+        else:
+            self.halo = None
+        self.mesh = m
+        self.dx = Measure(self)
+        self.dS = Measure(self)
+
+    # ------------------------------------------------------------------ constants / spaces
+    def setup_constants(self):
+        """KNPEMIx_problem.py:909-981."""
+        C = Constant
+        self.C_M, self.T, self.F, self.R, self.psi = C(self.C_M_value), C(self.T_value), C(self.F_value), C(self.R_value), C(self.psi_value)
+        self.g_Na_bar, self.g_K_bar = C(self.g_Na_bar_val), C(self.g_K_bar_val)
+        self.g_Na_leak, self.g_Na_leak_g = C(self.g_Na_leak_val), C(self.g_Na_leak_g_val)
+        self.g_K_leak, self.g_K_leak_g = C(self.g_K_leak_val), C(self.g_K_leak_g_val)
+        self.g_Cl_leak, self.g_Cl_leak_g = C(self.g_Cl_leak_val), C(self.g_Cl_leak_g_val)
+        self.g_syn_bar, self.a_syn, self.T_stim = C(self.g_syn_bar_val), C(self.a_syn_val), C(self.T_stim_val)
+        self.D_Na, self.D_K, self.D_Cl = C(1.33e-9), C(1.96e-9), C(2.03e-9)
+        self.phi_rest = C(-0.065)
+        self.phi_m_init = C(-0.070)
+        self.Na_i_init, self.Na_e_init = C(10.0), C(145.0)
+        self.K_i_init, self.K_e_init = C(130.0), C(3.0)
+        self.Cl_i_init, self.Cl_e_init = C(5.0), C(134.0)
+        self.phi_m_n_init, self.phi_m_g_init = C(self.phi_m_init.value), C(-0.085)
+        self.Na_i_n_init, self.K_i_n_init, self.Cl_i_n_init = C(self.Na_i_init.value), C(self.K_i_init.value), C(self.Cl_i_init.value)
+        self.Na_i_g_init, self.K_i_g_init, self.Cl_i_g_init = C(15.0), C(100.0), C(5.0)
+        self.n_init, self.m_init, self.h_init = C(0.24458654944007155), C(0.028905534475191896), C(0.7540796658225248)
+        mk = lambda name, gl, glg, D, ki, ke, kin, kig, z: {"name": name, "g_leak": gl, "g_leak_g": glg, "Di": D, "De": D,
+                                                              "ki_init": ki, "ke_init": ke, "ki_init_n": kin, "ki_init_g": kig,
+                                                              "z": C(z), "f_e": C(0.0), "f_i": C(0.0)}
+        self.Na = mk("Na", self.g_Na_leak, self.g_Na_leak_g, self.D_Na, self.Na_i_init, self.Na_e_init, self.Na_i_n_init, self.Na_i_g_init, 1.0)
+        self.K = mk("K", self.g_K_leak, self.g_K_leak_g, self.D_K, self.K_i_init, self.K_e_init, self.K_i_n_init, self.K_i_g_init, 1.0)
+        self.Cl = mk("Cl", self.g_Cl_leak, self.g_Cl_leak_g, self.D_Cl, self.Cl_i_init, self.Cl_e_init, self.Cl_i_n_init, self.Cl_i_g_init, -1.0)
+        self.ion_list = [self.Na, self.K, self.Cl]
+        self.N_ions = len(self.ion_list)
+
+    def setup_spaces(self):
+        """KNPEMIx_problem.py:28-94: P1 space on the whole mesh, 8 fields, restrictions to the vertices of the
+        intracellular / extracellular cells (membrane vertices belong to both)."""
+        if self.fem_order != 1:
+            raise NotImplementedError("fem_order = 2 is not implemented on the B200 path yet (no shipped config uses it)")
+        self._print("Setting up function spaces ...")
+        m = self.mesh
+        self.num_variables = self.N_ions + 1
+        self.num_variables_total = 2 * self.num_variables
+        nv = m.x.shape[0]
+        names_i = [f"{ion['name']}_i" for ion in self.ion_list] + ["phi_i"]
+        names_e = [f"{ion['name']}_e" for ion in self.ion_list] + ["phi_e"]
+        self.wh = [[Function(self, nv, nm) for nm in names_i], [Function(self, nv, nm) for nm in names_e]]
+        self.u_out_i, self.u_out_e = list(self.wh[0]), list(self.wh[1])
+        self._print("Creating mesh restrictions ...")
+        is_in = np.isin(m.cell_tags, np.asarray(self.intra_tags))
+        is_ex = m.cell_tags == self.extra_tag[0]
+        self.dofs_intra = np.unique(m.cells[is_in].ravel()).astype(np.int32)
+        self.dofs_extra = np.unique(m.cells[is_ex].ravel()).astype(np.int32)
+        n_owned = nv if m.n_owned is None else m.n_owned
+        self.interior = _Restriction(self.dofs_intra, int((self.dofs_intra < n_owned).sum()))
+        self.exterior = _Restriction(self.dofs_extra, int((self.dofs_extra < n_owned).sum()))
+        self.restriction = [self.interior] * self.num_variables + [self.exterior] * self.num_variables
+        self.neuron_cells = np.flatnonzero(np.isin(m.cell_tags, np.asarray(self.neuron_tags)))
+        if self.glia_flag:
+            self.glia_cells = np.flatnonzero(np.isin(m.cell_tags, np.asarray(self.glia_tags)))
+
+    def init(self):
+        pass
+
+    def setup_boundary_conditions(self):
+        """KNPEMIx_problem.py:96-198: every shipped config uses pure Neumann conditions (bcs = [])."""
+        if self.dirichlet_bcs or self.pin_ecs_potential:
+            raise NotImplementedError("Dirichlet conditions / ECS pinning are outside the B200 hot path (SURVEY.md 8f-3)")
+        self.bcs = []
+
+    def setup_source_terms(self):
+        raise NotImplementedError("ion_injection source terms are outside the B200 hot path (SURVEY.md 8f-3)")
+
+    # ------------------------------------------------------------------ initial conditions
+    def set_initial_conditions(self):
+        """KNPEMIx_problem.py:220-452 (config-provided initial conditions, :326-353 and :386-447)."""
+        if self.find_initial_conditions:
+            raise NotImplementedError("steady-state initial-condition ODE solve is outside the B200 hot path "
+                                      "(SURVEY.md 8f-4); provide initial_conditions in the config")
+        self._print("Setting initial conditions from input file ...")
+        ic = self.initial_conditions
+        pick = lambda a, b: ic[a] if a in ic else ic[b]
+        if not self.glia_flag:
+            self.phi_m_init.value = pick("phi_m", "phi_m_n")
+            self.Na_i_init.value = pick("Na_i", "Na_i_n")
+            self.K_i_init.value = pick("K_i", "K_i_n")
+            self.Cl_i_init.value = pick("Cl_i", "Cl_i_n")
+        else:
+            self.phi_m_n_init.value, self.phi_m_g_init.value = ic["phi_m_n"], ic["phi_m_g"]
+            self.Na_i_n_init.value, self.Na_i_g_init.value = ic["Na_i_n"], ic["Na_i_g"]
+            self.K_i_n_init.value, self.K_i_g_init.value = ic["K_i_n"], ic["K_i_g"]
+            self.Cl_i_n_init.value, self.Cl_i_g_init.value = ic["Cl_i_n"], ic["Cl_i_g"]
+        self.Na_e_init.value, self.K_e_init.value, self.Cl_e_init.value = ic["Na_e"], ic["K_e"], ic["Cl_e"]
+        self.n_init.value, self.m_init.value, self.h_init.value = ic["n"], ic["m"], ic["h"]
+        nv = self.mesh.x.shape[0]
+        self.phi_m_prev = Function(self, nv, "phi_m")
+        self._fill_initial_fields()
+        self._print("Initial conditions set.")
+
+    def _fill_initial_fields(self):
+        """Write the initial conditions into wh / phi_m_prev (also used by the iterative solver's
+        initial-guess reset, KNPEMIx_solver.py:179-199)."""
+        ui, ue = self.wh[0], self.wh[1]
+        N = self.N_ions
+        if not self.glia_flag:
+            self.phi_m_prev._data[:] = self.phi_m_init.value
+            ui[N]._data[:] = self.phi_m_init.value
+            ue[N]._data[:] = 0.0
+            for idx, ion in enumerate(self.ion_list):
+                ui[idx]._data[:] = ion["ki_init"].value
+                ue[idx]._data[:] = ion["ke_init"].value
+        else:
+            m = self.mesh
+            self.neuron_dofs = np.unique(m.cells[self.neuron_cells].ravel())
+            self.glia_dofs = np.unique(m.cells[self.glia_cells].ravel())
+            self.phi_m_prev._data[self.neuron_dofs] = self.phi_m_n_init.value
+            self.phi_m_prev._data[self.glia_dofs] = self.phi_m_g_init.value
+            ui[N]._data[self.neuron_dofs] = self.phi_m_n_init.value
+            ui[N]._data[self.glia_dofs] = self.phi_m_g_init.value
+            ue[N]._data[:] = 0.0
+            for idx, ion in enumerate(self.ion_list):
+                ui[idx]._data[self.neuron_dofs] = ion["ki_init_n"].value
+                ui[idx]._data[self.glia_dofs] = ion["ki_init_g"].value
+                ue[idx]._data[:] = ion["ke_init"].value
+        self._host_stale = False
+        if self._ctx is not None:
+            self._push_state()
+
+    def init_ionic_models(self, ionic_models):
+        """utils/mixed_dim_problem.py:435-465."""
+        if not isinstance(ionic_models, (list, tuple)):
+            ionic_models = [ionic_models]
+        self.ionic_models = list(ionic_models)
+        self.gating_variables = False
+        ionic_tags = set()
+        from .ionic_models import HodgkinHuxley
+        nv = self.mesh.x.shape[0]
+        for model in self.ionic_models:
+            model._init()
+            ionic_tags.update(model.tags)
+            self._print("Added tags for ionic model: ", str(model))
+            if isinstance(model, HodgkinHuxley):
+                self.gating_variables = True
+                self.n, self.m, self.h = Function(self, nv, "n"), Function(self, nv, "m"), Function(self, nv, "h")
+                self.n._data[:], self.m._data[:], self.h._data[:] = self.n_init.value, self.m_init.value, self.h_init.value
+                self._print("Gating variables flag set to True.")
+        ionic_tags = sorted(ionic_tags)
+        gamma_tags = sorted(flatten_list([self.gamma_tags]))
+        if ionic_tags != gamma_tags and not self.MMS_test and len(ionic_tags) != 0:
+            raise RuntimeError("Mismatch between membrane tags and ionic models tags."
+                               + f"\nIonic models tags: {ionic_tags}\nMembrane tags: {gamma_tags}")
+        self._print("# Membrane tags = ", len(gamma_tags))
+        self._print("# Ionic models  = ", len(self.ionic_models), "\n")
+
+    # ------------------------------------------------------------------ device context
+    def _require_context(self):
+        if self._ctx is None:
+            raise RuntimeError("call setup_variational_form() first (it creates the CUDA context)")
+        return self._ctx
+
+    def setup_variational_form(self):
+        """KNPEMIx_problem.py:454-655.  The reference builds the UFL forms a, L and JIT-compiles them; here
+        the same forms are hard-wired in the CUDA kernels, so this step creates the device context (dof maps,
+        CSR pattern, gather maps), uploads constants / model table and the initial state."""
+        self._print("Setting up variational form ...")
+        m = self.mesh
+        qb, qw = _mesh.facet_quadrature(m.gdim)
+        if self.device is None:
+            self.device = int(os.environ.get("LOCAL_RANK", "0"))
+        self._ctx = _lib.Context(m.gdim, m.x, m.cells, m.cell_tags, self.intra_tags, self.extra_tag[0], m.mf_verts,
+                                 m.mf_tags, qb, qw, n_owned_vertices=m.n_owned, cell_owned=m.cell_owned,
+                                 mfacet_owned=m.mf_owned, device=self.device)
+        ctx = self._ctx
+        self._node_vert = ctx.dofmaps()
+        self._mverts = ctx.mverts()
+        if self.comm.size > 1:
+            from .partition import init_halo
+            init_halo(self, ctx)
+        self._upload_params()
+        self._push_state()
+        self.a = self.L = "device-resident forms (csrc/assembly.cu)"
+
+    def _tag_table(self):
+        from .ionic_models import HodgkinHuxley
+        table = {int(t): 0 for t in self.gamma_tags}
+        for model in self.ionic_models:
+            for t in model.tags:
+                table[int(t)] = table.get(int(t), 0) | model.flag
+        return [(t, fl, (t in self.stimulus_tags)) for t, fl in sorted(table.items())]
+
+    def _upload_params(self, stim_area=0.0):
+        P = _lib.Params()
+        P.dt, P.F, P.R, P.T, P.C_M = self.dt.value, self.F.value, self.R.value, self.T.value, self.C_M.value
+        P.phi_rest = self.phi_rest.value
+        for k, ion in enumerate(self.ion_list):
+            P.z[k], P.D[k] = ion["z"].value, ion["Di"].value
+            P.g_leak[k], P.g_leak_g[k] = ion["g_leak"].value, ion["g_leak_g"].value
+        P.g_Na_bar, P.g_K_bar = self.g_Na_bar.value, self.g_K_bar.value
+        P.g_syn_bar, P.a_syn, P.T_stim = self.g_syn_bar.value, self.a_syn.value, self.T_stim.value
+        P.scale_stimulus = int(bool(self.scale_stimulus))
+        if self.stimulus_region:
+            P.stim_dir = int(self.stimulus_region_direction)
+            P.stim_lo, P.stim_hi = float(self.stimulus_region_range[0]), float(self.stimulus_region_range[1])
+        else:
+            P.stim_dir, P.stim_lo, P.stim_hi = -1, 0.0, 0.0
+        P.K_e_init, P.K_i_g_init = self.K_e_init.value, self.K_i_g_init.value
+        P.ode_substeps, P.rush_larsen = int(self.ode_substeps), int(self.rush_larsen)
+        P.stim_area = stim_area
+        table = self._tag_table()
+        self._ctx.set_params(P, table)
+        if self.scale_stimulus and stim_area == 0.0:
+            # p.stimulus_area = allreduce(assemble_scalar(mask * dS(stimulus_tags)))  (KNPEMIx_ionic_model.py:591-601)
+            area = self.comm.allreduce(self._ctx.stimulus_area_local(), op=MPI.SUM)
+            self.stimulus_area = area
+            if any(st for _, _, st in table) and self.gating_variables:
+                self._print(f"Stimulus area on tag {self.stimulus_tags[0]}: {area:0.6e} m^2")
+            if area > 0.0:
+                P.stim_area = area
+                self._ctx.set_params(P, table)
+
+    def setup_preconditioner(self, use_block_jacobi: bool = True):
+        """KNPEMIx_problem.py:657-744: block-diagonal preconditioner matrix P from the current fields."""
+        self._print("Setting up preconditioner ...")
+        if not use_block_jacobi:
+            raise NotImplementedError("only the block-Jacobi preconditioner form (the reference default) is implemented")
+        ctx = self._require_context()
+        if not self._host_stale:
+            self._push_state()
+        ctx.assemble_P()
+        self.P = "device-resident preconditioner matrix (block-Jacobi form)"
+
+    # ------------------------------------------------------------------ host <-> device state
+    def _pack_u(self):
+        ctx = self._ctx
+        u = np.zeros(ctx.n_cols)
+        off_row = [0, 4 * ctx.n_own[0]]
+        gh = [ctx.n_loc[0] - ctx.n_own[0], ctx.n_loc[1] - ctx.n_own[1]]
+        off_gh = [ctx.n_rows, ctx.n_rows + 4 * gh[0]]
+        for s in range(2):
+            verts = self._node_vert[s]
+            no = ctx.n_own[s]
+            for f in range(4):
+                vals = self.wh[s][f]._data[verts]
+                u[off_row[s] + f * no: off_row[s] + (f + 1) * no] = vals[:no]
+                u[off_gh[s] + f * gh[s]: off_gh[s] + (f + 1) * gh[s]] = vals[no:]
+        return u
+
+    def _unpack_u(self, u):
+        ctx = self._ctx
+        off_row = [0, 4 * ctx.n_own[0]]
+        gh = [ctx.n_loc[0] - ctx.n_own[0], ctx.n_loc[1] - ctx.n_own[1]]
+        off_gh = [ctx.n_rows, ctx.n_rows + 4 * gh[0]]
+        for s in range(2):
+            verts = self._node_vert[s]
+            no = ctx.n_own[s]
+            for f in range(4):
+                d = self.wh[s][f]._data
+                d[verts[:no]] = u[off_row[s] + f * no: off_row[s] + (f + 1) * no]
+                d[verts[no:]] = u[off_gh[s] + f * gh[s]: off_gh[s] + (f + 1) * gh[s]]
+
+    def _push_state(self):
+        ctx = self._ctx
+        gates = None
+        if self.gating_variables:
+            gates = np.stack([self.n._data[self._mverts], self.m._data[self._mverts], self.h._data[self._mverts]])
+        elif ctx.n_mverts:
+            gates = np.zeros((3, ctx.n_mverts))
+        ctx.set_state(self._pack_u(), gates)
+        self._host_stale = False
+
+    def _mark_device_newer(self):
+        self._host_stale = True
+
+    def _sync_host(self):
+        """Refresh wh / phi_m_prev / gates from the device (KNPEMIx_solver.py:451-468 done lazily)."""
+        if not self._host_stale or self._ctx is None:
+            return
+        self._host_stale = False
+        u, g = self._ctx.get_state()
+        self._unpack_u(u)
+        N = self.N_ions
+        self.phi_m_prev._data[:] = self.wh[0][N]._data - self.wh[1][N]._data
+        if self.gating_variables:
+            self.n._data[self._mverts], self.m._data[self._mverts], self.h._data[self._mverts] = g[0], g[1], g[2]
+
+    # ------------------------------------------------------------------ functionals
+    def l2_norm_squared(self, function, tags):
+        """Local (this rank's) integral of function^2 over the cells tagged `tags`; all-reduce with
+        comm.allreduce(..., op=MPI.SUM) like the reference drivers do."""
+        tags = tuple(np.atleast_1d(tags).tolist())
+        ctx = self._require_context()
+        for s in range(2):
+            for f in range(4):
+                if self.wh[s][f] is function:
+                    in_sub = all(t in self.intra_tags for t in tags) if s == 0 else all(t == self.extra_tag[0] for t in tags)
+                    if in_sub:
+                        return ctx.l2_norm_sq(s, f, tags)
+        # generic host path for any other field/tag combination (post-processing, not the hot path)
+        self._sync_host()
+        m = self.mesh
+        sel = np.isin(m.cell_tags, np.asarray(tags))
+        if m.cell_owned is not None:
+            sel &= m.cell_owned.astype(bool)
+        cells = m.cells[sel]
+        xx = m.x[cells]
+        d = m.gdim
+        vol = np.abs(np.linalg.det(xx[:, 1:] - xx[:, :1])) / (2.0 if d == 2 else 6.0)
+        uc = function._data[cells]
+        return float((vol / ((d + 1) * (d + 2)) * ((uc ** 2).sum(1) + uc.sum(1) ** 2)).sum())
+
+    def l2_norm(self, function, tags):
+        return float(np.sqrt(self.comm.allreduce(self.l2_norm_squared(function, tags), op=MPI.SUM)))

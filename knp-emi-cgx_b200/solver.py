@@ -1,0 +1,218 @@
+"""SolverKNPEMI: host-side mirror of src/CGx/KNPEMI/KNPEMIx_solver.py.
+
+Same constructor, class-level tunables (KNPEMIx_solver.py:25-51), ``solve()`` time loop (:337-501) and
+bookkeeping attributes (``iterations``, ``solve_time``, ``assembly_time``, ``tot_its`` ...).  The per-step work
+(gate ODE, assembly, Krylov solve, field update) runs in libknpemi_b200.so on the GPU; nothing in the loop
+falls back to the CPU.
+
+Solver mapping (documented in DESIGN.md):
+  * ``direct: True``  (PREONLY + MUMPS LU, :167-172)  -> GMRES + SA-AMG driven to the fp64 floor
+    (``direct_rtol``) followed by the projection ns^T x = 0 that KSP applies after MUMPS (:324-333).
+  * ``pc_type: hypre`` (one BoomerAMG V-cycle on P, :269-273) -> one V(1,1) cycle of our smoothed-aggregation
+    hierarchy on the same P.  Iteration counts are therefore ours, not hypre's.
+"""
+import time
+import numpy as np
+
+from . import lib as _lib
+from .comm import MPI
+from .ionic_models import HodgkinHuxley
+
+
+class SolverKNPEMI:
+    # Default solver parameters (KNPEMIx_solver.py:25-51)
+    ksp_type = "gmres"
+    pc_type = "hypre"
+    ksp_rtol = 1e-8
+    ksp_max_it = 5000
+    use_P_mat = True
+    reassemble_P = False
+    reassemble_N = 1
+    verbose = False
+    use_block_Jacobi = True
+    nonzero_init_guess = True
+    norm_type = "preconditioned"
+    max_amg_iter = 1
+    strong_threshold = 0.5
+    save_interval = 20
+    tot_its = 0.0
+    tot_assembly_time = 0.0
+    tot_solver_time = 0.0
+    # B200-path extras
+    gmres_restart = 30          # PETSc default
+    direct_rtol = 1e-13         # "direct" = Krylov solve to the fp64 floor
+    direct_refine = 2
+
+    def __init__(self, problem, solver_config: dict):
+        self.problem = problem
+        self.comm = problem.comm
+        self.time_steps = problem.time_steps
+        out = solver_config["output"]
+        self.save_xdmfs = out.get("save_xdmf", False)
+        self.save_pngs = out.get("save_pngs", False)
+        self.save_cpoints = out.get("save_cpoints", False)
+        self.save_dat = out.get("save_dat", False)
+        self.save_mat = out.get("save_mat", False)
+        if "save_interval" in out:
+            self.save_interval = out["save_interval"]
+        self.out_file_prefix = problem.output_dir
+        self.direct_solver = solver_config["direct"]
+        self.view_input = solver_config["view_ksp"]
+        if "ksp_settings" in solver_config:
+            ks = solver_config["ksp_settings"]
+            if "ksp_type" in ks: self.ksp_type = ks["ksp_type"]
+            if "pc_type" in ks: self.pc_type = ks["pc_type"]
+            if "ksp_rtol" in ks: self.ksp_rtol = float(ks["ksp_rtol"])
+            if "norm_type" in ks: self.norm_type = ks["norm_type"]
+            if "strong_threshold" in ks: self.strong_threshold = float(ks["strong_threshold"])
+            if "reassemble_P" in ks: self.reassemble_P = bool(ks["reassemble_P"])
+            if "non_zero_init_guess" in ks: self.nonzero_init_guess = bool(ks["non_zero_init_guess"])
+        if any((self.save_xdmfs, self.save_pngs, self.save_cpoints, self.save_dat)) or problem.point_evaluation:
+            raise NotImplementedError("XDMF / checkpoint / PNG / point-probe output is outside the B200 hot path "
+                                      "(SURVEY.md section 2, #10); switch the output options off")
+        if self.save_mat:
+            self.time_steps = 1
+
+    def _print(self, *a):
+        self.problem._print(*a)
+
+    # ------------------------------------------------------------------ setup
+    def _opts(self):
+        o = _lib.SolveOpts()
+        pure_neumann = not self.problem.dirichlet_bcs and not self.problem.pin_ecs_potential
+        if self.direct_solver:
+            o.rtol, o.max_it, o.restart = self.direct_rtol, self.ksp_max_it, self.gmres_restart
+            o.pc, o.project_nullspace = 2, int(pure_neumann)
+            o.zero_mean_solution, o.refine = int(pure_neumann), self.direct_refine
+        else:
+            if self.ksp_type != "gmres":
+                raise NotImplementedError(f"ksp_type {self.ksp_type!r}: the system is nonsymmetric; only gmres is implemented")
+            if self.norm_type != "preconditioned":
+                raise NotImplementedError("only the preconditioned residual norm (the reference default) is implemented")
+            pcs = {"hypre": 2, "gamg": 2, "amg": 2, "jacobi": 1, "none": 0}
+            if self.pc_type not in pcs:
+                raise NotImplementedError(f"pc_type {self.pc_type!r} is not implemented (hypre|gamg|jacobi|none)")
+            o.rtol, o.max_it, o.restart = self.ksp_rtol, self.ksp_max_it, self.gmres_restart
+            o.pc = pcs[self.pc_type] if self.use_P_mat else 0
+            o.project_nullspace, o.zero_mean_solution, o.refine = int(pure_neumann), 0, 0
+        return o
+
+    def setup_solver(self):
+        """KNPEMIx_solver.py:152-295.  Matrix/vector storage already lives in the device context."""
+        p = self.problem
+        self.ctx = p._require_context()
+        if self.direct_solver:
+            self._print("Using direct solver ...")
+        else:
+            self._print("Setting up iterative solver ...")
+            # initial conditions as initial guess (:179-209): wh <- ICs, x <- wh
+            p._fill_initial_fields()
+            if not self.nonzero_init_guess:
+                raise NotImplementedError("zero initial guess is not supported: the state vector doubles as x")
+            self.iterations = []
+        self.opts = self._opts()
+        self.solve_time = []
+        self.assembly_time = []
+        self.A = _Sized(self.ctx.n_rows)
+        self.ksp = self
+
+    def assemble_preconditioner(self):
+        """KNPEMIx_solver.py:118-135."""
+        self._print("Assembling preconditioner ...")
+        self.ctx.assemble_P()
+
+    def reassemble_preconditioner(self):
+        """KNPEMIx_solver.py:137-150 (+ hierarchy rebuild, which hypre does inside ksp.setUp)."""
+        self._print("Re-assembling preconditioner ...")
+        self.ctx.assemble_P()
+        self.ctx.pc_setup(self.opts)
+
+    def assemble(self):
+        """KNPEMIx_solver.py:104-116."""
+        self._print("Assembling linear system ...")
+        self.ctx.assemble(self.problem.t.value)
+
+    def getIterationNumber(self):
+        return self._last_info.iterations
+
+    # ------------------------------------------------------------------ time loop
+    def solve(self):
+        """KNPEMIx_solver.py:337-501."""
+        p = self.problem
+        setup_timer = 0.0
+        tic = time.perf_counter()
+        self.setup_solver()
+        ctx = self.ctx
+        setup_timer += self.comm.allreduce(time.perf_counter() - tic, op=MPI.MAX)
+        tic = time.perf_counter()
+        if self.opts.pc != 0:
+            p.setup_preconditioner(self.use_block_Jacobi)           # :358-362 (assembled once from the ICs)
+        ctx.pc_setup(self.opts)                                     # ksp.setOperators + ksp.setUp (:386-389)
+        setup_timer += self.comm.allreduce(time.perf_counter() - tic, op=MPI.MAX)
+        ctx.set_time(p.t.value, 0)
+        for model in p.ionic_models:
+            if isinstance(model, HodgkinHuxley):
+                p.ode_substeps, p.rush_larsen = model.time_steps_ODE, model.use_Rush_Larsen
+        for i in range(1, self.time_steps + 1):
+            self._print("\nTime step ", i)
+            if self.save_mat:
+                raise NotImplementedError("save_mat: use Context.csr() / device buffers to export the matrix")
+            if i > 1 and self.reassemble_P and (i % self.reassemble_N == 0) and not self.direct_solver and self.use_P_mat:
+                self.reassemble_preconditioner()
+            info = ctx.step(self.opts)                              # t += dt, gates, assemble, solve, u <- x
+            p.t.value, _ = ctx.get_time()
+            self._print("t (ms) = ", 1000 * float(p.t.value))
+            for model in p.ionic_models:
+                if isinstance(model, HodgkinHuxley):
+                    model.update_t_mod()
+            p._mark_device_newer()
+            tm = ctx.last_timings()
+            asm = self.comm.allreduce((tm["gate"] + tm["facet"] + tm["rows"]) * 1e-3, op=MPI.MAX)
+            sol = self.comm.allreduce(tm["solve"] * 1e-3, op=MPI.MAX)
+            self.tot_assembly_time += asm
+            self.tot_solver_time += sol
+            self.assembly_time.append(asm)
+            self.solve_time.append(sol)
+            self._print(f"Time dependent assembly in {asm:0.4f} seconds")
+            self._print(f"Solved in {sol:0.4f} seconds")
+            self._last_info = info
+            self.tot_its += info.iterations
+            if not self.direct_solver:
+                self.iterations.append(info.iterations)
+            if i == self.time_steps:
+                self._print("\nTotal setup time:", setup_timer)
+                self._print("Total assembly time:", sum(self.assembly_time))
+                self._print("Total solve time:", sum(self.solve_time))
+                self.print_info()
+
+    def print_info(self):
+        """KNPEMIx_solver.py:504-548."""
+        p = self.problem
+        num_dofs = p.interior.index_map.size_local * p.num_variables + p.exterior.index_map.size_local * p.num_variables
+        num_dofs = int(self.comm.allreduce(float(num_dofs), op=MPI.SUM))
+        self._print("\n#------------ PROBLEM -------------#\n")
+        self._print("MPI Size = ", self.comm.size)
+        self._print("Input mesh = ", p.input_files["mesh_file"])
+        self._print("Global # mesh cells = ", p.global_mesh_info["n_cells"])
+        self._print("System size (global # dofs) = ", num_dofs)
+        self._print("FEM order = ", p.fem_order)
+        self._print("# Time steps = ", self.time_steps)
+        self._print("dt = ", float(p.dt.value))
+        self._print("Using Dirichlet BCs." if p.dirichlet_bcs else "Using Neumann BCs.")
+        self._print("\n#------------ SOLVER -------------#\n")
+        if self.direct_solver:
+            self._print(f"Using 'direct' mode: GMRES+SA-AMG to rtol {self.direct_rtol:.1e} (no sparse LU on the GPU).")
+        else:
+            self._print("Solver type: [" + self.ksp_type + "+" + self.pc_type + "]")
+            self._print(f"Tolerance: {self.ksp_rtol:.2e}")
+            self._print(f"Norm type: {self.norm_type}")
+            self._print(f"None-zero initial guess: {self.nonzero_init_guess}")
+            if self.use_P_mat: self._print("Preconditioner matrix P enabled.")
+            if self.use_block_Jacobi: self._print("Using block-Jacobi preconditioner form.")
+            if self.reassemble_P: self._print(f"Re-assembling preconditioner every {self.reassemble_N} timesteps.")
+            self._print("Average iterations: " + str(sum(self.iterations) / len(self.iterations)))
+
+
+class _Sized:
+    def __init__(self, n):
+        self.size = (n, n)
