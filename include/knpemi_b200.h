@@ -177,6 +177,9 @@ int knp_l2_norm_sq(knp_ctx* ctx, int32_t subdomain, int32_t field, int32_t n_tag
 /* per-phase device timers of the last knp_step (ms): gate, facet, rows, solve, total */
 int knp_last_timings(const knp_ctx* ctx, double* ms5);
 
+/* plain copies on the context's stream, synchronous: kind 1 = host->device, 2 = device->host, 3 = device->device */
+int knp_copy(knp_ctx* ctx, void* dst, const void* src, int64_t nbytes, int32_t kind);
+
 /* AMG hierarchy inspection for level-by-level parity tests */
 int knp_amg_num_levels(const knp_ctx* ctx);
 int knp_amg_level_sizes(const knp_ctx* ctx, int32_t level, int64_t* n, int64_t* nnz);

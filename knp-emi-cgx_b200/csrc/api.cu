@@ -481,6 +481,15 @@ int knp_l2_norm_sq(knp_ctx* c, int32_t s, int32_t field, int32_t n_tags, const i
   return KNP_OK;
 }
 
+int knp_copy(knp_ctx* c, void* dst, const void* src, int64_t nbytes, int32_t kind) {
+  CTX_GUARD(c);
+  KNP_CHECK(dst && src && nbytes >= 0 && kind >= 1 && kind <= 3, "bad knp_copy arguments");
+  const cudaMemcpyKind k = kind == 1 ? cudaMemcpyHostToDevice : kind == 2 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  KNP_CUDA(cudaMemcpyAsync(dst, src, (size_t)nbytes, k, c->stream));
+  KNP_CUDA(cudaStreamSynchronize(c->stream));
+  return KNP_OK;
+}
+
 int knp_amg_num_levels(const knp_ctx* c) { return (c && c->amg) ? (int)c->amg->hostA.size() : 0; }
 
 int knp_amg_level_sizes(const knp_ctx* c, int32_t level, int64_t* n, int64_t* nnz) {

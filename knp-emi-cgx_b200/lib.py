@@ -65,7 +65,7 @@ SYMBOLS = [
     "knp_set_state", "knp_get_state", "knp_state_dev", "knp_phi_m_host", "knp_gate_step", "knp_assemble",
     "knp_assemble_P", "knp_values_dev", "knp_spmv", "knp_pc_setup", "knp_pc_apply", "knp_solve", "knp_step",
     "knp_step_host", "knp_set_time", "knp_get_time", "knp_l2_norm_sq", "knp_last_timings", "knp_amg_num_levels",
-    "knp_amg_level_sizes", "knp_amg_level_host", "knp_nccl_unique_id", "knp_dist_init", "knp_halo_exchange",
+    "knp_copy", "knp_amg_level_sizes", "knp_amg_level_host", "knp_nccl_unique_id", "knp_dist_init", "knp_halo_exchange",
     "knp_allreduce_sum",
 ]
 
@@ -116,6 +116,7 @@ def load():
     lib.knp_get_time.argtypes = [vp, c_f64p, c_i32p]
     lib.knp_l2_norm_sq.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, vp, c_f64p]
     lib.knp_last_timings.argtypes = [vp, vp]
+    lib.knp_copy.argtypes = [vp, vp, vp, C.c_int64, C.c_int32]
     lib.knp_amg_num_levels.argtypes = [vp]
     lib.knp_amg_level_sizes.argtypes = [vp, C.c_int32, c_i64p, c_i64p]
     lib.knp_amg_level_host.argtypes = [vp, C.c_int32, vp, vp, vp]
@@ -314,6 +315,20 @@ class Context:
         ms = np.zeros(5)
         check(self._lib.knp_last_timings(self.h, _ptr(ms)))
         return dict(gate=ms[0], facet=ms[1], rows=ms[2], solve=ms[3], total=ms[4])
+
+    def to_host(self, dev_ptr, count, dtype=np.float64):
+        out = np.empty(count, dtype)
+        check(self._lib.knp_copy(self.h, _ptr(out), dev_ptr, out.nbytes, 2))
+        return out
+
+    def to_dev(self, dev_ptr, arr):
+        arr = np.ascontiguousarray(arr)
+        check(self._lib.knp_copy(self.h, dev_ptr, _ptr(arr), arr.nbytes, 1))
+
+    def values_host(self):
+        """(A values, b, P values) copied from the context's own buffers."""
+        d = self.dev_ptrs()
+        return (self.to_host(d["A"], self.nnz), self.to_host(d["b"], self.n_rows), self.to_host(d["P"], self.nnz_P))
 
     def amg_levels(self):
         import scipy.sparse as sp

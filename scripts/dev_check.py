@@ -21,20 +21,10 @@ print("sizes", ctx.n_rows, ctx.nnz, ctx.nnz_P, ctx.n_own, ctx.n_mverts)
 o = KNPEMIOracle(unit_square(32), OracleParams(), [("NeuronalCT", None), ("HH", None), ("ATP", None)])
 ip, ix = ctx.csr()
 # one assembly at t = dt after a gate step (as the solver loop does)
-import torch
 o.t += o.p.dt; o.gate_update(); A, b = o.assemble(o.t)
 print("indptr equal", np.array_equal(ip, A.indptr), "indices equal", np.array_equal(ix, A.indices))
 ctx.gate_step(); ctx.assemble(o.p.dt)
-n, nnz = ctx.n_rows, ctx.nnz
-d = ctx.dev_ptrs()
-def dev_to_np(ptr, count):
-    t = torch.empty(count, dtype=torch.float64, device="cuda")
-    torch.cuda.synchronize()
-    import ctypes
-    cudart = torch.cuda.cudart()
-    cudart.cudaMemcpy(t.data_ptr(), ptr, count * 8, 3)
-    return t.cpu().numpy()
-Av = dev_to_np(d["A"], nnz); bv = dev_to_np(d["b"], n)
+Av, bv, _ = ctx.values_host()
 u, g = ctx.get_state()
 print("gates diff", np.abs(g - o.gates[:, o.mverts]).max())
 scale = np.maximum.reduceat(np.abs(A.data), A.indptr[:-1])
