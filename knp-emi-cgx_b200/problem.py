@@ -436,9 +436,28 @@ class ProblemKNPEMI:
                 ui[idx]._data[self.neuron_dofs] = ion["ki_init_n"].value
                 ui[idx]._data[self.glia_dofs] = ion["ki_init_g"].value
                 ue[idx]._data[:] = ion["ke_init"].value
+        self._apply_initial_perturbation()
         self._host_stale = False
         if self._ctx is not None:
             self._push_state()
+
+    def _apply_initial_perturbation(self):
+        """Extension key ``initial_perturbation`` (synthetic benchmark configs only):
+        concentrations x (1 + r sin 2 pi X sin 2 pi Y), phi_m = phi_m + a cos 2 pi X with X, Y in unit-mesh
+        coordinates, so that the assembled coefficients are not constant."""
+        pert = self.config.get("initial_perturbation")
+        if not pert:
+            return
+        X = self.mesh.x / self.mesh_conversion_factor
+        r, a = float(pert.get("relative", 0.0)), float(pert.get("phi_m_amplitude", 0.0))
+        fac = 1.0 + r * np.sin(2 * np.pi * X[:, 0]) * np.sin(2 * np.pi * X[:, 1])
+        N = self.N_ions
+        for s in range(2):
+            for k in range(N):
+                self.wh[s][k]._data *= fac
+        dphi = a * np.cos(2 * np.pi * X[:, 0])
+        self.phi_m_prev._data += dphi
+        self.wh[0][N]._data += dphi
 
     def init_ionic_models(self, ionic_models):
         """utils/mixed_dim_problem.py:435-465."""

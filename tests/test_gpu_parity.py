@@ -1,0 +1,397 @@
+"""GPU parity tests (run on the B200 box with -m gpu).  Every check calls the CUDA path through the C ABI
+(knp-emi-cgx_b200/lib.py -> libknpemi_b200.so) and compares with the CPU oracle on the same inputs, with the
+committed golden fixtures, and with the reference's own golden norms.
+
+Tolerances: CSR structure / dof maps bit-exact; matrix and vector entries 1e-12 relative to the row's largest
+entry (north star: 1e-12 relative, fp64); norms per timestep 1e-8 relative."""
+import os
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle.fixtures import unit_square, unit_cube, from_arrays
+from oracle.knpemi import KNPEMIOracle, OracleParams
+from oracle.amg import SAAMG
+from conftest import MODELS_TEST, GOLD_DIRECT, GOLD_ITERATIVE
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+FLAGS = {"NeuronalCT": 8, "HH": 32, "ATP": 16, "Passive": 1, "GlialCT": 4, "KirNa": 2}
+
+
+def make_ctx(kb, om, p: OracleParams, models, device=0):
+    """Device context for an oracle mesh + parameter set (direct C-ABI use, no Problem class)."""
+    qb, qw = kb.mesh.facet_quadrature(om.gdim)
+    ctx = kb.lib.Context(om.gdim, om.x, om.cells, om.cell_tags, p.intra_tags, p.extra_tag, om.mf_verts, om.mf_tags,
+                         qb, qw, device=device)
+    P = kb.lib.Params()
+    P.dt, P.F, P.R, P.T, P.C_M, P.phi_rest = p.dt, p.F, p.R, p.T, p.C_M, p.phi_rest
+    for k in range(3):
+        P.z[k], P.D[k], P.g_leak[k], P.g_leak_g[k] = p.z[k], p.D[k], p.g_leak[k], p.g_leak_g[k]
+    P.g_Na_bar, P.g_K_bar, P.g_syn_bar, P.a_syn, P.T_stim = p.g_Na_bar, p.g_K_bar, p.g_syn_bar, p.a_syn, p.T_stim
+    P.scale_stimulus = int(p.scale_stimulus)
+    if p.stimulus_region is None:
+        P.stim_dir = -1
+    else:
+        P.stim_dir, P.stim_lo, P.stim_hi = p.stimulus_region
+    P.K_e_init, P.K_i_g_init = p.c_e_init[1], p.c_i_g_init[1]
+    P.ode_substeps, P.rush_larsen, P.stim_area = p.ode_substeps, int(p.rush_larsen), 0.0
+    table = {}
+    for name, tags in models:
+        for t in (p.membrane_tags if tags is None else tags):
+            table[t] = table.get(t, 0) | FLAGS[name]
+    ctx.set_params(P, [(t, fl, t in p.stimulus_tags) for t, fl in sorted(table.items())])
+    return ctx
+
+
+def push_oracle_state(ctx, o):
+    ctx.set_state(o.pack(), o.gates[:, o.mverts])
+
+
+def rel_rows(A_ref: sp.csr_matrix, vals):
+    scale = np.maximum.reduceat(np.abs(A_ref.data), A_ref.indptr[:-1])
+    return (np.abs(vals - A_ref.data) / np.repeat(scale, np.diff(A_ref.indptr))).max()
+
+
+def perturbed_oracle(om, p, models, seed=0):
+    o = KNPEMIOracle(om, p, models)
+    rng = np.random.default_rng(seed)
+    for s in range(2):
+        o.c[s] *= 1 + 0.05 * rng.random(o.c[s].shape)
+    o.phi[0] += 0.004 * rng.standard_normal(o.phi[0].shape)
+    o.phi[1] += 0.001 * rng.standard_normal(o.phi[1].shape)
+    o.phi_m = o.phi[0] - o.phi[1]
+    o.gates *= 1 + 0.1 * rng.random(o.gates.shape)
+    return o
+
+
+# ---------------------------------------------------------------------------------------------- structure
+@pytest.mark.parametrize("name", ["square32", "square7", "cube6", "cells2d", "cells3d"])
+def test_csr_structure_and_dofmaps_bit_exact(kb, name):
+    om, p = MESHES[name](kb)
+    o = KNPEMIOracle(om, p, MODELS_TEST)
+    ctx = make_ctx(kb, om, p, MODELS_TEST)
+    A, _ = o.assemble(p.dt)
+    ip, ix = ctx.csr()
+    assert ctx.n_rows == o.n and ctx.nnz == A.nnz
+    assert np.array_equal(ip, A.indptr) and np.array_equal(ix, A.indices)
+    vi, ve = ctx.dofmaps()
+    assert np.array_equal(vi, o.S[0]) and np.array_equal(ve, o.S[1])
+    assert np.array_equal(ctx.mverts(), o.mverts)
+    P = o.assemble_P()
+    ipP, ixP = ctx.csr_P()
+    assert np.array_equal(ipP, P.indptr) and np.array_equal(ixP, P.indices)
+    ctx.close()
+
+
+def _sq(n):
+    return lambda kb: (unit_square(n), OracleParams())
+
+
+def _cells(d, n, m):
+    def f(kb):
+        mm = kb.mesh.cell_array_mesh(d, n, m)
+        om = from_arrays(d, mm.x, mm.cells, mm.cell_tags, mm.intra_tags)
+        it = tuple(mm.intra_tags)
+        return om, OracleParams(intra_tags=it, extra_tag=1, membrane_tags=it, stimulus_tags=(2,))
+    return f
+
+
+MESHES = {"square32": _sq(32), "square7": _sq(7), "cube6": lambda kb: (unit_cube(6), OracleParams()),
+          "cells2d": _cells(2, 24, 3), "cells3d": _cells(3, 8, 2)}
+
+
+def test_c1_structure_against_committed_golden(kb):
+    g = np.load(os.path.join(GOLD, "c1_square32.npz"))
+    om, p = MESHES["square32"](kb)
+    ctx = make_ctx(kb, om, p, MODELS_TEST)
+    ip, ix = ctx.csr()
+    assert np.array_equal(ip, g["indptr"]) and np.array_equal(ix, g["indices"])
+    vi, ve = ctx.dofmaps()
+    assert np.array_equal(vi, g["S_i"]) and np.array_equal(ve, g["S_e"])
+    ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------- values
+@pytest.mark.parametrize("name", ["square32", "square7", "cube6", "cells2d", "cells3d"])
+def test_assembled_matrix_and_vector(kb, name):
+    om, p = MESHES[name](kb)
+    o = perturbed_oracle(om, p, MODELS_TEST, seed=1)
+    ctx = make_ctx(kb, om, p, MODELS_TEST)
+    push_oracle_state(ctx, o)
+    t = 3 * p.dt
+    A, b = o.assemble(t)
+    ctx.assemble(t)
+    Av, bv, _ = ctx.values_host()
+    assert rel_rows(A, Av) < 1e-12
+    assert np.abs(bv - b).max() / np.abs(b).max() < 1e-12
+    # per-field check of b (fields differ by orders of magnitude)
+    for s in range(2):
+        for f in range(4):
+            sl = slice(o.base[s] + f * o.ns[s], o.base[s] + (f + 1) * o.ns[s])
+            assert np.abs(bv[sl] - b[sl]).max() <= 1e-12 * np.abs(b[sl]).max()
+    # preconditioner matrix
+    P = o.assemble_P()
+    ctx.assemble_P()
+    _, _, Pv = ctx.values_host()
+    assert rel_rows(P, Pv) < 1e-12
+    ctx.close()
+
+
+def test_c1_values_against_committed_golden(kb):
+    g = np.load(os.path.join(GOLD, "c1_square32.npz"))
+    om, p = MESHES["square32"](kb)
+    o = KNPEMIOracle(om, p, MODELS_TEST)
+    ctx = make_ctx(kb, om, p, MODELS_TEST)
+    push_oracle_state(ctx, o)
+    ctx.gate_step()
+    ctx.assemble(p.dt)
+    Av, bv, _ = ctx.values_host()
+    A = sp.csr_matrix((Av, g["indices"], g["indptr"]), shape=(o.n, o.n))
+    np.testing.assert_allclose(bv, g["b"], rtol=0, atol=1e-12 * np.abs(g["b"]).max())
+    np.testing.assert_allclose(A.diagonal(), g["A_diag"], rtol=1e-12)
+    np.testing.assert_allclose(np.asarray(abs(A).sum(axis=1)).ravel(), g["A_absrowsum"], rtol=1e-12)
+    _, gates = ctx.get_state()
+    np.testing.assert_allclose(gates, g["gates"], rtol=1e-13)
+    ctx.close()
+
+
+def test_cube_values_against_committed_golden(kb):
+    g = np.load(os.path.join(GOLD, "cube6.npz"))
+    om, p = MESHES["cube6"](kb)
+    o = KNPEMIOracle(om, p, MODELS_TEST)
+    ctx = make_ctx(kb, om, p, MODELS_TEST)
+    push_oracle_state(ctx, o)
+    ctx.gate_step()
+    ctx.assemble(p.dt)
+    Av, bv, _ = ctx.values_host()
+    ip, ix = ctx.csr()
+    assert np.array_equal(ip, g["indptr"]) and np.array_equal(ix, g["indices"])
+    A = sp.csr_matrix((g["A_data"], g["indices"], g["indptr"]))
+    assert rel_rows(A, Av) < 1e-12
+    assert np.abs(bv - g["b"]).max() <= 1e-12 * np.abs(g["b"]).max()
+    ctx.close()
+
+
+@pytest.mark.parametrize("models", [
+    [("Passive", None)],
+    [("HH", None)],
+    [("NeuronalCT", None), ("HH", None), ("ATP", None)],
+    [("HH", (2, 3)), ("ATP", (2, 3)), ("NeuronalCT", (2, 3)), ("GlialCT", (4, 5)), ("KirNa", (4, 5))],
+])
+def test_membrane_models(kb, models):
+    """Every IonicModel._eval of the reference (KNPEMIx_ionic_model.py) incl. the glial set used by main.py:32-38."""
+    mm = kb.mesh.cell_array_mesh(2, 16, 2)
+    om = from_arrays(2, mm.x, mm.cells, mm.cell_tags, mm.intra_tags)
+    glia = (4, 5) if any(n == "KirNa" for n, _ in models) else ()
+    p = OracleParams(intra_tags=(2, 3, 4, 5), extra_tag=1, membrane_tags=(2, 3, 4, 5), stimulus_tags=(2,),
+                     glia_tags=glia, stimulus_region=(0, 0.2e-6, 0.45e-6), g_syn_bar=40.0, scale_stimulus=True)
+    o = perturbed_oracle(om, p, models, seed=4)
+    ctx = make_ctx(kb, om, p, models)
+    push_oracle_state(ctx, o)
+    t = 7 * p.dt
+    A, b = o.assemble(t)
+    ctx.assemble(t)
+    Av, bv, _ = ctx.values_host()
+    assert abs(ctx.stimulus_area_local() - o.stimulus_area()) <= 1e-14 * o.stimulus_area()
+    assert rel_rows(A, Av) < 1e-12
+    for s in range(2):
+        for f in range(4):
+            sl = slice(o.base[s] + f * o.ns[s], o.base[s] + (f + 1) * o.ns[s])
+            assert np.abs(bv[sl] - b[sl]).max() <= 1e-12 * np.abs(b[sl]).max()
+    ctx.close()
+
+
+def test_gate_kernel_rush_larsen_and_forward_euler(kb):
+    om, p0 = MESHES["square32"](kb)
+    for rl in (True, False):
+        p = OracleParams(rush_larsen=rl)
+        o = perturbed_oracle(om, p, MODELS_TEST, seed=2)
+        o.phi[0][:] = np.linspace(-0.09, 0.04, o.phi[0].size)          # sweeps the whole HH voltage range
+        o.phi_m = o.phi[0] - o.phi[1]
+        ctx = make_ctx(kb, om, p, MODELS_TEST)
+        push_oracle_state(ctx, o)
+        o.gate_update()
+        ctx.gate_step()
+        _, g = ctx.get_state()
+        np.testing.assert_allclose(g, o.gates[:, o.mverts], rtol=1e-13, atol=1e-16)
+        ctx.close()
+
+
+def test_assembly_is_bitwise_reproducible(kb):
+    om, p = MESHES["cells2d"](kb)
+    o = perturbed_oracle(om, p, MODELS_TEST, seed=5)
+    ctx = make_ctx(kb, om, p, MODELS_TEST)
+    push_oracle_state(ctx, o)
+    ctx.assemble(p.dt)
+    A1, b1, _ = ctx.values_host()
+    for _ in range(3):
+        ctx.assemble(p.dt)
+        A2, b2, _ = ctx.values_host()
+        assert np.array_equal(A1, A2) and np.array_equal(b1, b2)
+    ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------- linear algebra
+def test_spmv_and_nullspace(kb):
+    import torch
+    om, p = MESHES["cells2d"](kb)
+    o = perturbed_oracle(om, p, MODELS_TEST, seed=6)
+    ctx = make_ctx(kb, om, p, MODELS_TEST)
+    push_oracle_state(ctx, o)
+    A, b = o.assemble(p.dt)
+    ctx.assemble(p.dt)
+    x = np.random.default_rng(0).standard_normal(o.n)
+    xd = torch.tensor(x, device="cuda")
+    yd = torch.empty(o.n, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    ctx.spmv(xd.data_ptr(), yd.data_ptr())
+    ctx.to_host(yd.data_ptr(), 1)       # synchronises the context's stream
+    y = yd.cpu().numpy()
+    ref = A @ x
+    assert np.abs(y - ref).max() <= 1e-13 * (abs(A) @ np.abs(x)).max()
+    ns = torch.tensor(o.nullspace(), device="cuda")
+    ctx.spmv(ns.data_ptr(), yd.data_ptr())
+    ctx.to_host(yd.data_ptr(), 1)
+    assert yd.abs().max().item() < 1e-22                                  # nullspace.test(A), KNPEMIx_solver.py:327
+    ctx.close()
+
+
+def test_amg_hierarchy_matches_oracle_level_by_level(kb):
+    om, p = MESHES["square32"](kb)
+    o = KNPEMIOracle(om, p, MODELS_TEST)
+    ctx = make_ctx(kb, om, p, MODELS_TEST)
+    push_oracle_state(ctx, o)
+    ctx.assemble_P()
+    opts = kb.lib.SolveOpts(rtol=1e-9, max_it=100, restart=30, pc=2, project_nullspace=1, zero_mean_solution=0, refine=0)
+    ctx.pc_setup(opts)
+    amg = SAAMG(o.assemble_P())
+    levels = ctx.amg_levels()
+    ref = [lv["A"] for lv in amg.levels] + [amg.Ac]
+    assert [a.shape[0] for a in levels] == [a.shape[0] for a in ref]
+    for a, r in zip(levels, ref):
+        d = (a - r).tocoo()
+        assert np.abs(d.data).max() <= 1e-10 * np.abs(r.data).max()
+    # one V-cycle
+    import torch
+    r = np.random.default_rng(1).standard_normal(o.n)
+    rd = torch.tensor(r, device="cuda"); zd = torch.empty_like(rd)
+    torch.cuda.synchronize()
+    ctx.pc_apply(rd.data_ptr(), zd.data_ptr())
+    ctx.to_host(zd.data_ptr(), 1)
+    z = zd.cpu().numpy()
+    zr = amg(r)
+    assert np.abs(z - zr).max() <= 1e-8 * np.abs(zr).max()
+    ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------- time loop
+def run_problem(kb, cfgdir, cfg):
+    p = kb.ProblemKNPEMI(os.path.join(cfgdir, cfg), verbose=False)
+    HH, ATP, NCT = kb.HodgkinHuxley(p), kb.ATPPump(p), kb.NeuronalCotransporters(p)
+    p.set_initial_conditions()
+    p.init_ionic_models([NCT, HH, ATP])
+    p.setup_variational_form()
+    p.solver_config["view_ksp"] = False
+    s = kb.SolverKNPEMI(p, solver_config=p.solver_config)
+    s.solve()
+    phi_i, phi_e = s.problem.wh[0][s.problem.N_ions], s.problem.wh[1][s.problem.N_ions]
+    li = np.sqrt(s.comm.allreduce(p.l2_norm_squared(phi_i, 1), op=kb.MPI.SUM))
+    le = np.sqrt(s.comm.allreduce(p.l2_norm_squared(phi_e, 2), op=kb.MPI.SUM))
+    return p, s, li, le
+
+
+def test_c1_direct_solver_golden_norms(kb, cfgdir):
+    """BASELINE config C1 = the reference's tests/KNPEMI/electric_potential_norms_direct_solver.py."""
+    p, s, li, le = run_problem(kb, cfgdir, "c1_square32_direct.yaml")
+    assert abs(li - GOLD_DIRECT[0]) / GOLD_DIRECT[0] < 1e-8
+    assert abs(le - GOLD_DIRECT[1]) / GOLD_DIRECT[1] < 1e-8
+    # per-field norms and gates against the oracle's 10-step run (north star: 1e-8 relative per timestep)
+    g = np.load(os.path.join(GOLD, "c1_square32.npz"))
+    got = [li, le] + [p.l2_norm(p.wh[sd][k], 1 if sd == 0 else 2) for sd in range(2) for k in range(3)]
+    np.testing.assert_allclose(got, g["norms"][-1], rtol=1e-8)
+    mv = p._mverts
+    np.testing.assert_allclose(np.stack([p.n.x.array[mv], p.m.x.array[mv], p.h.x.array[mv]]), g["gates_final"], rtol=1e-8)
+    assert abs(p.phi_m_prev.x.array[mv].mean() - g["phim_mean"][-1]) < 1e-8 * abs(g["phim_mean"][-1])
+
+
+def test_c2_iterative_solver_matches_oracle_per_timestep(kb, cfgdir):
+    """BASELINE config C2 = tests/KNPEMI/electric_potential_norms_iterative_solver.py.  Per-timestep norms of all
+    eight fields against the oracle running the same algorithm (GMRES(30) + SA-AMG V-cycle, rtol 1e-9)."""
+    p = kb.ProblemKNPEMI(os.path.join(cfgdir, "c2_square32_iterative.yaml"), verbose=False)
+    HH, ATP, NCT = kb.HodgkinHuxley(p), kb.ATPPump(p), kb.NeuronalCotransporters(p)
+    p.set_initial_conditions(); p.init_ionic_models([NCT, HH, ATP]); p.setup_variational_form()
+    p.solver_config["view_ksp"] = False
+    s = kb.SolverKNPEMI(p, solver_config=p.solver_config)
+    s.time_steps = 1
+    o = KNPEMIOracle(unit_square(32), OracleParams(), MODELS_TEST)
+    amg = SAAMG(o.assemble_P())
+    x = o.pack()
+    s.setup_solver(); p.setup_preconditioner(True); s.ctx.pc_setup(s.opts); s.ctx.set_time(0.0, 0)
+    its_gpu, its_cpu = [], []
+    for i in range(10):
+        info = s.ctx.step(s.opts); p._mark_device_newer()
+        _, _, x, its = o.step("gmres", amg, 1e-9, x, first=(i == 0))
+        its_gpu.append(info.iterations); its_cpu.append(its)
+        for sd in range(2):
+            for f in range(4):
+                ref = o.l2_norm(o.c[sd][f] if f < 3 else o.phi[sd], 1 if sd == 0 else 2)
+                got = p.l2_norm(p.wh[sd][f], 1 if sd == 0 else 2)
+                assert abs(got - ref) <= 1e-8 * ref, (i, sd, f, got, ref)
+    assert its_gpu == its_cpu
+    assert sum(its_gpu) / 10 <= 4.0          # the reference's hypre needs 3.0 (tests/...iterative_solver.py:81)
+
+
+def test_c2_iterative_solver_golden_norms(kb, cfgdir):
+    p, s, li, le = run_problem(kb, cfgdir, "c2_square32_iterative.yaml")
+    # sanity bounds only: the goldens embed the reference's own GMRES truncation error
+    assert abs(li - GOLD_ITERATIVE[0]) / GOLD_ITERATIVE[0] < 1e-6
+    assert abs(le - GOLD_ITERATIVE[1]) / GOLD_ITERATIVE[1] < 1e-3
+    assert len(s.iterations) == 10
+
+
+def test_step_host_roundtrip_equals_device_resident(kb, cfgdir):
+    ps = []
+    for mode in ("device", "host"):
+        p = kb.ProblemKNPEMI(os.path.join(cfgdir, "c2_square32_iterative.yaml"), verbose=False)
+        p.set_initial_conditions()
+        p.init_ionic_models([kb.NeuronalCotransporters(p), kb.HodgkinHuxley(p), kb.ATPPump(p)])
+        p.setup_variational_form()
+        p.solver_config["view_ksp"] = False
+        s = kb.SolverKNPEMI(p, solver_config=p.solver_config)
+        s.setup_solver(); p.setup_preconditioner(True); s.ctx.pc_setup(s.opts); s.ctx.set_time(0.0, 0)
+        u, g = s.ctx.get_state()
+        for _ in range(3):
+            if mode == "device":
+                s.ctx.step(s.opts)
+            else:
+                s.ctx.step_host(u, g, s.opts)
+        if mode == "device":
+            u, g = s.ctx.get_state()
+        ps.append((u.copy(), g.copy()))
+    assert np.array_equal(ps[0][0], ps[1][0]) and np.array_equal(ps[0][1], ps[1][1])
+
+
+def test_3d_passive_time_loop_matches_oracle(kb):
+    """BASELINE config C4 in miniature: 3D tissue block, PassiveModel, GMRES + AMG; full-size property:
+    the assembled system keeps the phi-constant nullspace and the solution matches the oracle's."""
+    om, p = MESHES["cells3d"](kb)
+    models = [("Passive", None)]
+    o = KNPEMIOracle(om, p, models)
+    ctx = make_ctx(kb, om, p, models)
+    push_oracle_state(ctx, o)
+    ctx.assemble_P()
+    opts = kb.lib.SolveOpts(rtol=1e-11, max_it=500, restart=30, pc=2, project_nullspace=1, zero_mean_solution=0, refine=0)
+    ctx.pc_setup(opts)
+    ctx.set_time(0.0, 0)
+    amg = SAAMG(o.assemble_P())
+    x = o.pack()
+    for i in range(3):
+        info = ctx.step(opts)
+        _, _, x, its = o.step("gmres", amg, 1e-11, x, first=(i == 0))
+        u, _ = ctx.get_state()
+        for s in range(2):
+            for f in range(4):
+                sl = slice(o.base[s] + f * o.ns[s], o.base[s] + (f + 1) * o.ns[s])
+                assert np.linalg.norm(u[sl] - x[sl]) <= 1e-8 * np.linalg.norm(x[sl])
+    ctx.close()

@@ -1,0 +1,136 @@
+"""CPU-only checks of the host side: YAML schema / error behaviour of the reference, mesh fixtures against the
+oracle's independent generator, quadrature tables, the membrane-model table, and the C-ABI library itself
+(it must load and export every symbol declared in include/knpemi_b200.h; it must refuse to run without a GPU)."""
+import os
+import re
+import numpy as np
+import pytest
+from oracle.fixtures import unit_square, unit_cube, from_arrays
+from oracle.quadrature import facet_rule
+from conftest import has_gpu
+
+BASE = """
+problem_type: "KNP-EMI"
+dt: 2.5e-5
+time_steps: 2
+physical_constants: {T: 300, F: 96485, R: 8.314}
+C_M: 0.02
+cell_tag_file: "./input/geometries/square8.xdmf"
+facet_tag_file: "./input/geometries/square8_facets.xdmf"
+ics_tags: [1]
+ecs_tags: [2]
+boundary_tags: [3]
+membrane_tags: [4]
+mesh_conversion_factor: 1e-6
+initial_conditions: {phi_m: -0.070, Na_i: 12, Na_e: 140, K_i: 130, K_e: 4, Cl_i: 5, Cl_e: 125, n: 0.276, m: 0.0379, h: 0.688}
+stimulus: {conductance: {g_syn_bar: 1.0e-9}, a_syn: 5.0e-4, T_stim: 1.0, scale: True}
+solver: {direct: True, output: {save_xdmf: False}}
+"""
+
+
+def write(tmp_path, text, name="cfg.yaml"):
+    f = tmp_path / name
+    f.write_text(text)
+    return str(f)
+
+
+def drop(text, key):
+    return "\n".join(l for l in text.splitlines() if not l.startswith(key))
+
+
+def test_config_schema_and_errors(kb, tmp_path):
+    p = kb.ProblemKNPEMI(write(tmp_path, BASE), verbose=False)
+    assert p.time_steps == 2 and p.dt.value == 2.5e-5 and p.N_ions == 3
+    assert p.intra_tags == (1,) and p.extra_tag == (2,) and p.gamma_tags == (4,) and p.stimulus_tags == (4,)
+    assert abs(p.psi.value - 8.314 * 300 / 96485) < 1e-18
+    # conductance defaults when a stimulus dict is present (mixed_dim_problem.py:311-318)
+    assert (p.g_Na_leak.value, p.g_K_leak.value, p.g_Cl_leak.value) == (0.3, 0.1, 0.25)
+    assert p.solver_config["direct"] is True
+    # required keys raise RuntimeError like the reference (mixed_dim_problem.py:98-166)
+    for key, msg in [("solver", "solver configuration"), ("dt", "dt"), ("time_steps", "time_steps"), ("ics_tags", "ics_tags")]:
+        with pytest.raises(RuntimeError, match=msg):
+            kb.ProblemKNPEMI(write(tmp_path, drop(BASE, key)), verbose=False)
+    with pytest.raises(RuntimeError, match="cell_tag_file"):
+        kb.ProblemKNPEMI(write(tmp_path, drop(drop(BASE, "cell_tag_file"), "facet_tag_file")), verbose=False)
+    with pytest.raises(RuntimeError, match="scale"):
+        kb.ProblemKNPEMI(write(tmp_path, BASE.replace(", scale: True", "")), verbose=False)
+    # T instead of time_steps: int(T/dt) (mixed_dim_problem.py:157)
+    p2 = kb.ProblemKNPEMI(write(tmp_path, BASE.replace("time_steps: 2", "T: 1.0e-4")), verbose=False)
+    assert p2.time_steps == int(1.0e-4 / 2.5e-5)
+    # no stimulus block -> other defaults (mixed_dim_problem.py:320-332)
+    p3 = kb.ProblemKNPEMI(write(tmp_path, drop(BASE, "stimulus")), verbose=False)
+    assert (p3.g_Na_leak.value, p3.g_K_leak.value, p3.g_syn_bar.value, p3.scale_stimulus) == (1.0, 4.0, 40.0, False)
+
+
+def test_range_tag_and_tag_order_check(kb, tmp_path):
+    txt = BASE.replace("ics_tags: [1]", "ics_tags: !range [2, 6]").replace("ecs_tags: [2]", "ecs_tags: [1]") \
+              .replace("membrane_tags: [4]", "membrane_tags: !range [2, 6]")
+    txt = drop(drop(txt, "cell_tag_file"), "facet_tag_file") + \
+        "\nsynthetic_mesh: {kind: cell_array, dim: 2, N: 16, cells_per_dim: 2, first_tag: 2, extra_tag: 1}\n"
+    p = kb.ProblemKNPEMI(write(tmp_path, txt), verbose=False)
+    assert p.intra_tags == (2, 3, 4, 5) and p.gamma_tags == (2, 3, 4, 5)
+    assert sorted(np.unique(p.mesh.mf_tags)) == [2, 3, 4, 5]
+    bad = txt.replace("ecs_tags: [1]", "ecs_tags: [3]")
+    with pytest.raises(RuntimeError, match="all smaller or all larger"):
+        kb.ProblemKNPEMI(write(tmp_path, bad), verbose=False)
+
+
+def test_model_table_and_mismatch(kb, tmp_path):
+    p = kb.ProblemKNPEMI(write(tmp_path, BASE), verbose=False)
+    HH, ATP, NCT = kb.HodgkinHuxley(p), kb.ATPPump(p), kb.NeuronalCotransporters(p)
+    assert HH.tags == (4,) and HH.time_steps_ODE == 25 and abs(HH.dt_ode - 1e-6) < 1e-20
+    p.set_initial_conditions()
+    p.init_ionic_models([NCT, HH, ATP])
+    assert p.gating_variables
+    assert p._tag_table() == [(4, kb.lib.MODEL_HH | kb.lib.MODEL_ATP | kb.lib.MODEL_NEURONAL_CT, True)]
+    assert np.all(p.n.x.array == 0.276) and np.all(p.wh[0][3].x.array == -0.070) and np.all(p.wh[1][1].x.array == 4)
+    with pytest.raises(RuntimeError, match="Mismatch between membrane tags"):
+        p.init_ionic_models([kb.PassiveModel(p, tags=(7,))])
+
+
+def test_mesh_fixtures_match_oracle_generator(kb):
+    for n in (4, 32):
+        m, o = kb.mesh.unit_square_fixture(n), unit_square(n)
+        assert np.array_equal(m.cells, o.cells) and np.array_equal(m.x, o.x) and np.array_equal(m.cell_tags, o.cell_tags)
+        assert np.array_equal(m.mf_verts, o.mf_verts) and np.all(m.mf_tags == 4)
+    m, o = kb.mesh.unit_cube_fixture(6), unit_cube(6)
+    assert np.array_equal(m.cells, o.cells) and np.array_equal(m.mf_verts, o.mf_verts)
+    # C1 sizes quoted by the survey
+    m = kb.mesh.unit_square_fixture(32)
+    assert m.x.shape[0] == 1089 and m.cells.shape[0] == 2048 and (m.cell_tags == 1).sum() == 512 and m.mf_verts.shape[0] == 64
+    # tissue block: facets agree with the oracle's generic facet matcher
+    m = kb.mesh.cell_array_mesh(2, 32, 4)
+    o = from_arrays(2, m.x, m.cells, m.cell_tags, m.intra_tags)
+    assert np.array_equal(m.mf_verts, o.mf_verts) and np.array_equal(m.mf_tags, o.mf_tags)
+    m3 = kb.mesh.cell_array_mesh(3, 8, 2)
+    o3 = from_arrays(3, m3.x, m3.cells, m3.cell_tags, m3.intra_tags)
+    assert np.array_equal(m3.mf_verts, o3.mf_verts) and np.array_equal(m3.mf_tags, o3.mf_tags)
+    assert m3.mf_verts.shape[0] == 8 * 6 * 2 * 2 * 2      # 8 cubes x 6 faces x (2x2 squares) x 2 triangles
+
+
+def test_quadrature_tables(kb):
+    for d in (2, 3):
+        b, w = kb.mesh.facet_quadrature(d)
+        ob, ow = facet_rule(d)
+        np.testing.assert_allclose(b, ob, atol=1e-15)
+        np.testing.assert_allclose(w, ow, atol=1e-15)
+        assert abs(w.sum() - 1) < 1e-14 and np.allclose(b.sum(1), 1)
+
+
+def test_library_exports_every_declared_symbol(kb):
+    lib = kb.lib.load()
+    header = open(os.path.join(os.path.dirname(os.path.dirname(kb.__file__)), "include", "knpemi_b200.h")).read()
+    declared = set(re.findall(r"\b(knp_[A-Za-z0-9_]+)\s*\(", header))
+    assert declared == set(kb.lib.SYMBOLS), declared ^ set(kb.lib.SYMBOLS)
+    for s in declared:
+        assert hasattr(lib, s), s
+    assert lib.knp_version() >= 100
+
+
+@pytest.mark.skipif(has_gpu(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback(kb, tmp_path):
+    p = kb.ProblemKNPEMI(write(tmp_path, BASE), verbose=False)
+    p.set_initial_conditions()
+    p.init_ionic_models([kb.PassiveModel(p)])
+    with pytest.raises(kb.lib.KnpError, match="no CPU fallback"):
+        p.setup_variational_form()
