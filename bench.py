@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- ms per KNP-EMI timestep (assembly + solve) on synthetic meshes, with the HBM roofline of the
+dominant kernels and the CPU oracle timed beside it.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3                    # our arm, BASELINE config C3 (2D N=2048, 64 cells)
+    python bench.py --impl reference --gpus 1 --steps 5 --warmup 3   # CPU restatement of the reference path
+    torchrun --nproc-per-node N ... bench.py --gpus N ...            # weak scaling: per-GPU mesh fixed
+
+A "step" is one pass of the reference's time-loop body (KNPEMIx_solver.py:365-468): gate ODE, assembly of A and b,
+GMRES + AMG solve, field update, on one batch of synthetic input.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ms per KNP-EMI timestep (assembly+solve)"
+
+
+def workload_yaml(kb, n, cells_per_dim=8):
+    txt = open(os.path.join(os.path.dirname(kb.__file__), "configs", "c3_square2048_cells64.yaml")).read()
+    txt = txt.replace("N: 2048", f"N: {n}").replace("cells_per_dim: 8", f"cells_per_dim: {cells_per_dim}")
+    hi = 2 + cells_per_dim ** 2
+    txt = txt.replace("!range [2, 66]", f"!range [2, {hi}]")
+    f = tempfile.NamedTemporaryFile("w", suffix=".yaml", delete=False)
+    f.write(txt)
+    f.close()
+    return f.name
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.rows, self.index, self.proc = [], index, None
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm
+def cpu_oracle_run(n_sample, cells_per_dim, warmup, steps, n_full_rows=None):
+    """Times the CPU oracle (numpy/scipy restatement of the reference path + the same SA-AMG/GMRES algorithm) on a
+    bounded sample of the workload: same tissue-block generator at a smaller N, same step indices."""
+    import cgx_b200 as kb
+    from oracle.fixtures import from_arrays
+    from oracle.knpemi import KNPEMIOracle, OracleParams
+    from oracle.amg import SAAMG
+    m = kb.mesh.cell_array_mesh(2, n_sample, cells_per_dim)
+    om = from_arrays(2, m.x, m.cells, m.cell_tags, m.intra_tags)
+    it = tuple(m.intra_tags)
+    p = OracleParams(intra_tags=it, extra_tag=1, membrane_tags=it, stimulus_tags=(2,))
+    o = KNPEMIOracle(om, p, [("NeuronalCT", None), ("HH", None), ("ATP", None)])
+    X = om.x / 1e-6
+    fac = 1 + 0.01 * np.sin(2 * np.pi * X[:, 0]) * np.sin(2 * np.pi * X[:, 1])
+    for s in range(2):
+        o.c[s] *= fac[None, :]
+    dphi = 0.005 * np.cos(2 * np.pi * X[:, 0])
+    o.phi_m += dphi
+    o.phi[0] += dphi
+    amg = SAAMG(o.assemble_P())
+    x = o.pack()
+    t_asm, t_step, its = [], [], []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        o.t += p.dt
+        o.gate_update()
+        A, b = o.assemble(o.t)
+        t1 = time.perf_counter()
+        ns = o.nullspace()
+        if i == 0:
+            b = b - ns * (ns @ b)
+        x, k = o.solve_gmres(A, b, x, ns, amg, 1e-9)
+        o.unpack(x)
+        t2 = time.perf_counter()
+        if i >= warmup:
+            t_asm.append(t1 - t0)
+            t_step.append(t2 - t0)
+            its.append(k)
+    ms = 1e3 * float(np.mean(t_step))
+    scale = (n_full_rows / o.n) if n_full_rows else 1.0
+    return dict(ms_sample=ms, ms_scaled=ms * scale, rows=o.n, nnz=int(A.nnz), iterations=its,
+                assembly_ms_sample=1e3 * float(np.mean(t_asm)), scale=scale)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_s, cpd = args.cpu_sample_n, 8
+    # the full workload's row count, needed to scale the sample to the metric's unit
+    per_dim = args.size
+    full_rows = None
+    t0 = time.time()
+    r = cpu_oracle_run(n_s, cpd, args.warmup, args.steps, None)
+    # rows scale with N^2 for this generator
+    scale = (per_dim / n_s) ** 2 * max(1, args.gpus)
+    val = r["ms_sample"] * scale
+    line = {"metric": METRIC, "value": val, "unit": "ms", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": val, "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": f"C3 tissue block 2D N={per_dim} x{max(1, args.gpus)} GPUs-equivalent, 64 cells, Na/K/Cl + HH+ATP+KCC2, GMRES rtol 1e-9",
+                       "sample_N": n_s, "sample_rows": r["rows"], "iterations": r["iterations"]},
+            "cpu_baseline": {"value": val, "unit": "ms", "cores": 1, "kind": "port",
+                             "sample": f"CPU oracle (numpy/scipy restatement; DOLFINx/PETSc not installable) on the same generator at N={n_s} "
+                                       f"({r['rows']} rows), steps {args.warmup + 1}..{args.warmup + args.steps}, {r['ms_sample']:.0f} ms/step measured, "
+                                       f"scaled x{scale:.0f} by DOFs to the full workload"},
+            "e2e": {"value": val, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": time.time() - t0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import cgx_b200 as kb
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    # weak scaling: cells per GPU fixed -> N grows with sqrt(world)
+    n = args.size if world == 1 else int(round(args.size * math.sqrt(world) / 8)) * 8
+    cfg = workload_yaml(kb, n)
+    t_setup = time.time()
+    p = kb.ProblemKNPEMI(cfg, verbose=False, device=local)
+    p.set_initial_conditions()
+    p.init_ionic_models([kb.NeuronalCotransporters(p), kb.HodgkinHuxley(p), kb.ATPPump(p)])
+    p.setup_variational_form()
+    p.solver_config["view_ksp"] = False
+    s = kb.SolverKNPEMI(p, solver_config=p.solver_config)
+    s.gmres_restart = args.restart
+    s.setup_solver()
+    p.setup_preconditioner(True)
+    ctx = s.ctx
+    ctx.pc_setup(s.opts)
+    ctx.set_time(0.0, 0)
+    t_setup = time.time() - t_setup
+    comm = p.comm
+
+    def barrier():
+        torch.cuda.synchronize()
+        comm.Barrier()
+
+    for _ in range(args.warmup):
+        ctx.step(s.opts)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    l0 = kb.lib.launch_count()
+    tot, asm, sol, its = 0.0, 0.0, 0.0, []
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        info = ctx.step(s.opts)
+        tm = ctx.last_timings()              # CUDA events on the launching stream, recorded inside knp_step
+        tot += tm["total"]
+        asm += tm["gate"] + tm["facet"] + tm["rows"]
+        sol += tm["solve"]
+        its.append(int(info.iterations))
+    barrier()
+    wall = (time.perf_counter() - wall0) * 1e3 / args.steps
+    launches = kb.lib.launch_count() - l0
+    clocks = sampler.stop()
+    ms_dev = comm.allreduce(tot / args.steps, op=kb.MPI.MAX)
+    ms_wall = comm.allreduce(wall, op=kb.MPI.MAX)
+    ms = max(ms_dev, ms_wall) if world > 1 else ms_dev
+
+    # ---- end to end through the host-buffer C-ABI call (H2D of the state + step + D2H of the result every step)
+    nst = ctx.n_cols
+    u_pin = torch.empty(nst, dtype=torch.float64).pin_memory()
+    g_pin = torch.empty(3 * ctx.n_mverts, dtype=torch.float64).pin_memory()
+    u0, g0 = ctx.get_state()
+    u_pin.numpy()[:] = u0
+    g_pin.numpy()[:] = g0.ravel()
+    un, gn = u_pin.numpy(), g_pin.numpy()
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.step_host(un, gn, s.opts)
+    barrier()
+    e2e_ms = comm.allreduce((time.perf_counter() - e0) * 1e3 / args.steps, op=kb.MPI.MAX)
+    io_bytes = (nst + 3 * ctx.n_mverts) * 8
+
+    # ---- roofline of the dominant kernels, measured live with CUDA events on the launching stream
+    st = torch.cuda.Stream()
+    sp = st.cuda_stream
+    x = torch.randn(ctx.n_cols, dtype=torch.float64, device="cuda")
+    y = torch.empty(ctx.n_rows, dtype=torch.float64, device="cuda")
+
+    def timeit(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(st)
+        for _ in range(reps):
+            fn()
+        b.record(st)
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    t_spmv = timeit(lambda: ctx.spmv(x.data_ptr(), y.data_ptr(), stream=sp), 20)
+    t_asm = timeit(lambda: ctx.assemble(1e-4, stream=sp), 10)
+    t_pc = timeit(lambda: ctx.pc_apply(x.data_ptr(), y.data_ptr(), stream=sp), 10)
+    m = p.mesh
+    nvert, ncell = m.x.shape[0], m.cells.shape[0]
+    B_spmv = 12 * ctx.nnz + 20 * ctx.n_rows
+    B_asm = (8 * ctx.nnz + 16 * ctx.n_rows + 8 * m.gdim * nvert + (4 * (m.gdim + 1) + 4) * ncell
+             + 32 * ctx.n_mverts + 16 * ctx.sizes.n_mfacets)
+    peak, peak_src = peaks()
+    mean_its = float(np.mean(its))
+    share_spmv = (mean_its + 1) * t_spmv / (tot / args.steps)
+    roof = {"bound": "hbm", "kernel": "spmv_kernel<16,EPI_SET> (y = A x, plain CSR)", "achieved": B_spmv / t_spmv / 1e6,
+            "peak": peak, "unit": "GB/s", "frac": B_spmv / t_spmv / 1e6 / peak, "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes": B_spmv, "ms_per_launch": t_spmv, "share_of_step": share_spmv}
+    kernels = {
+        "assembly (facet_kernel + rows_kernel)": {"ms": t_asm, "algorithmic_bytes": B_asm, "GB/s": B_asm / t_asm / 1e6,
+                                                  "frac": B_asm / t_asm / 1e6 / peak},
+        "spmv A": {"ms": t_spmv, "algorithmic_bytes": B_spmv, "GB/s": B_spmv / t_spmv / 1e6, "frac": roof["frac"]},
+        "amg_vcycle (pc_apply)": {"ms": t_pc},
+    }
+    dofs_global = int(comm.allreduce(float(ctx.n_rows), op=kb.MPI.SUM))
+    nnz_global = int(comm.allreduce(float(ctx.nnz), op=kb.MPI.SUM))
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_oracle_run(args.cpu_sample_n, 8, args.warmup, min(args.steps, 2))
+        scale = ctx.n_rows / r["rows"]
+        cpu = {"value": r["ms_sample"] * scale, "unit": "ms", "cores": 1, "kind": "port",
+               "sample": f"CPU oracle (numpy/scipy restatement of the DOLFINx/PETSc path, same GMRES+SA-AMG algorithm) on the same "
+                         f"generator at N={args.cpu_sample_n} ({r['rows']} rows, iterations {r['iterations']}), steps {args.warmup + 1}.."
+                         f"{args.warmup + min(args.steps, 2)}: {r['ms_sample']:.0f} ms/step (assembly {r['assembly_ms_sample']:.0f} ms), "
+                         f"scaled x{scale:.1f} by DOFs"}
+    if rank == 0:
+        line = {"metric": METRIC, "value": ms, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms, "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": f"BASELINE C3: synthetic 2D tissue block N={n} ({'x'.join(['8'] * 2)} cells), Na/K/Cl + HH+ATP+KCC2, "
+                                       f"GMRES({args.restart})+SA-AMG rtol 1e-9, ICs perturbed as SURVEY 8(d)",
+                           "dofs": dofs_global, "nnz": nnz_global, "cells": int(p.global_mesh_info["n_cells"]),
+                           "iterations_per_step": its, "timed_step_indices": [args.warmup + 1, args.warmup + args.steps],
+                           "l2_policy": "inputs (A: %.1f GB) larger than L2" % (12 * ctx.nnz / 1e9), "setup_s": t_setup},
+                "phases_ms": {"assembly": asm / args.steps, "solve": sol / args.steps},
+                "clocks": clocks,
+                "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": io_bytes, "d2h_bytes_per_step": io_bytes},
+                "gpu_launches": int(launches),
+                "roofline": roof, "kernels": kernels}
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=2048, help="grid squares per side on one GPU (BASELINE C3: 2048)")
+    ap.add_argument("--restart", type=int, default=30)
+    ap.add_argument("--cpu-sample-n", type=int, default=128)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        print("bench.py: warm-up raised to 3 (timing rules)", file=sys.stderr)
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

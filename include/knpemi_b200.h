@@ -106,7 +106,9 @@ typedef struct {
   int32_t pc;                   /* 0 none, 1 Jacobi(P), 2 smoothed-aggregation AMG V-cycle on P */
   int32_t project_nullspace;    /* remove the phi-constant nullspace after each PC apply (:324-333) */
   int32_t zero_mean_solution;   /* direct-solver convention: return the solution with ns^T x = 0 */
-  int32_t refine;               /* extra iterative-refinement restarts for the "direct" mode */
+  int32_t refine;               /* "direct" mode: keep restarting until the true residual stagnates `refine` times */
+  double field_scale[8];        /* >0: solve in variables scaled per field block (balances c ~ 1e2 against phi ~ 1e-2
+                                   in the residual norm; used by the "direct" mode); all 0 = unscaled (PETSc semantics) */
 } knp_solve_opts;
 
 typedef struct {
@@ -117,6 +119,8 @@ typedef struct {
 
 const char* knp_last_error(void);
 int knp_version(void);
+/* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
+int64_t knp_launch_count(void);
 
 /* Build the restricted dof maps, CSR pattern (A and block-diagonal P) and all device-side gather maps.
  * Replaces: DofMapRestriction (KNPEMI/KNPEMIx_problem.py:85-94), create_matrix_block/create_vector_block

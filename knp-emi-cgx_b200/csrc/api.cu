@@ -28,6 +28,7 @@ extern "C" {
 
 const char* knp_last_error(void) { return knp::last_error(); }
 int knp_version(void) { return 100; }
+int64_t knp_launch_count(void) { return (int64_t)knp::g_kernel_launches; }
 
 int knp_create(knp_ctx** out, const knp_mesh_desc* mesh, int device) {
   if (!out) {

@@ -570,7 +570,7 @@ __global__ void __launch_bounds__(256) l2_cells_kernel(Layout L, int s, int fiel
 int launch_gate(const DevTopo& T, const KParams& P, const double* u, double* gates, cudaStream_t st) {
   if (T.n_mv == 0) return KNP_OK;
   gate_kernel<<<(T.n_mv + 127) / 128, 128, 0, st>>>(T, P, u, gates);
-  KNP_CUDA(cudaGetLastError());
+  KNP_LAUNCHED();
   return KNP_OK;
 }
 
@@ -584,7 +584,7 @@ int launch_facets(const DevTopo& T, const KParams& P, const uint32_t* tag_models
     facet_kernel<2><<<grid, 128, 0, st>>>(T, P, tag_models, tag_stim, u, gates, stim_fac, fe);
   else
     facet_kernel<3><<<grid, 128, 0, st>>>(T, P, tag_models, tag_stim, u, gates, stim_fac, fe);
-  KNP_CUDA(cudaGetLastError());
+  KNP_LAUNCHED();
   return KNP_OK;
 }
 
@@ -605,7 +605,7 @@ static int launch_rows_t(const DevTopo& T, const KParams& P, const double* u, co
   }
   const int grid = (T.n_work + ROWS_BLOCK - 1) / ROWS_BLOCK;
   rows_kernel<D, MODE><<<grid, ROWS_BLOCK, smem, st>>>(T, P, u, fe, vals, b, stride);
-  KNP_CUDA(cudaGetLastError());
+  KNP_LAUNCHED();
   return KNP_OK;
 }
 
@@ -628,7 +628,7 @@ int launch_csr_indices(const DevTopo& T, int mode, int32_t* indices, cudaStream_
   const int grid = (T.n_work + 127) / 128;
   if (mode == 0) csr_indices_kernel<0><<<grid, 128, 0, st>>>(T, indices);
   else csr_indices_kernel<1><<<grid, 128, 0, st>>>(T, indices);
-  KNP_CUDA(cudaGetLastError());
+  KNP_LAUNCHED();
   return KNP_OK;
 }
 
@@ -642,7 +642,7 @@ int launch_l2_cells(int gdim, const Layout& L, int s, int field, int n_cells, co
   else
     l2_cells_kernel<3><<<n_partial, 256, 0, st>>>(L, s, field, n_cells, cell_nodes, cell_tag, cell_owned, node_x,
                                                   nodeoff, tags, n_tags, u, partial);
-  KNP_CUDA(cudaGetLastError());
+  KNP_LAUNCHED();
   return KNP_OK;
 }
 

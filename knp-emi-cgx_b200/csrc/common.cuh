@@ -21,6 +21,14 @@ void set_error(const char* fmt, ...);
     }                                                                               \
   } while (0)
 
+ // counts our own kernel launches (bench.py reports them as gpu_launches)
+extern unsigned long long g_kernel_launches;
+#define KNP_LAUNCHED()                      \
+  do {                                      \
+    KNP_CUDA(cudaGetLastError());           \
+    ++knp::g_kernel_launches;               \
+  } while (0)
+
 #define KNP_CHECK(cond, ...)             \
   do {                                   \
     if (!(cond)) {                       \

@@ -33,7 +33,7 @@ struct knp_ctx {
   // Krylov workspace
   int ws_restart = 0;
   size_t ldv = 0;
-  knp::DevBuf<double> V, w, tmp, partial, hdev, ydev, pc_dinv;
+  knp::DevBuf<double> V, w, tmp, tmp2, colscale, partial, hdev, ydev, pc_dinv;
   double* h_pinned = nullptr;
   // preconditioner
   int pc_kind = -1;

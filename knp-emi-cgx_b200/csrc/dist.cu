@@ -73,7 +73,7 @@ int halo_exchange(knp_ctx* c, double* x, cudaStream_t st) {
     int grid = (int)((ns + 255) / 256);
     if (grid > 148 * 8) grid = 148 * 8;
     pack_kernel<<<grid, 256, 0, st>>>(ns, c->d_send_cols.p, x, sbuf);
-    KNP_CUDA(cudaGetLastError());
+    KNP_LAUNCHED();
   }
   KNP_NCCL(api->GroupStart());
   for (int i = 0; i < np; ++i) {
@@ -86,7 +86,7 @@ int halo_exchange(knp_ctx* c, double* x, cudaStream_t st) {
     int grid = (int)((nr + 255) / 256);
     if (grid > 148 * 8) grid = 148 * 8;
     unpack_kernel<<<grid, 256, 0, st>>>(nr, c->d_send_cols.p + ns, rbuf, x);
-    KNP_CUDA(cudaGetLastError());
+    KNP_LAUNCHED();
   }
   return KNP_OK;
 }

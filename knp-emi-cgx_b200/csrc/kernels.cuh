@@ -49,7 +49,9 @@ int launch_multi_dot(int n, int m, const double* V, size_t ldv, const double* w,
 int launch_multi_axpy(int n, int m, const double* V, size_t ldv, const double* h, double* w, cudaStream_t st);
 int launch_axpby(int n, double a, const double* x, double b, double* y, cudaStream_t st);              // y = a x + b y
 int launch_scale_copy(int n, const double* alpha_dev, int invert, const double* x, double* y, cudaStream_t st);   // y = x*alpha or x/alpha
-int launch_update_x(int n, int m, const double* V, size_t ldv, const double* y_dev, double* x, cudaStream_t st);   // x += sum_j y[j] V_j
+int launch_update_x(int n, int m, const double* V, size_t ldv, const double* y_dev, double* x, const double* scale,
+                    cudaStream_t st);   // x += scale .* sum_j y[j] V_j   (scale may be NULL)
+int launch_pointwise(int n, const double* a, const double* b, int divide, double* out, cudaStream_t st);   // out = a.*b or a./b
 // sum over [lo0,hi0) U [lo1,hi1) of x -> out[0] (deterministic), and x[range] -= shift
 int launch_range_sum(const double* x, int lo0, int hi0, int lo1, int hi1, double* partial, double* out, cudaStream_t st);
 int launch_range_shift(double* x, int lo0, int hi0, int lo1, int hi1, const double* sum_dev, double inv_count,

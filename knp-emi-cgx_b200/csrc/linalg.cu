@@ -22,6 +22,12 @@ __device__ __forceinline__ int ld_stream(const int* p) {
   return v;
 }
 
+static int grid_for(int n) {
+  int grid = (n + 255) / 256;
+  if (grid > 148 * 16) grid = 148 * 16;
+  return grid < 1 ? 1 : grid;
+}
+
 template <int LANES, int EPI>
 __global__ void __launch_bounds__(256) spmv_kernel(int n_rows, const int32_t* __restrict__ indptr,
                                                    const int32_t* __restrict__ indices,
@@ -62,7 +68,7 @@ static int launch_spmv_l(int grid, int n_rows, const int32_t* indptr, const int3
     case EPI_JACOBI: spmv_kernel<LANES, EPI_JACOBI><<<grid, 256, 0, st>>>(n_rows, indptr, indices, vals, x, out, b, dinv, w); break;
     default: spmv_kernel<LANES, EPI_ADD><<<grid, 256, 0, st>>>(n_rows, indptr, indices, vals, x, out, b, dinv, w); break;
   }
-  KNP_CUDA(cudaGetLastError());
+  KNP_LAUNCHED();
   return KNP_OK;
 }
 
@@ -93,7 +99,7 @@ int launch_scale_dinv(int n, double w, const double* dinv, const double* b, doub
   int grid = (n + 255) / 256;
   if (grid > 148 * 16) grid = 148 * 16;
   scale_dinv_kernel<<<grid, 256, 0, st>>>(n, w, dinv, b, x);
-  KNP_CUDA(cudaGetLastError());
+  KNP_LAUNCHED();
   return KNP_OK;
 }
 
@@ -110,7 +116,7 @@ int launch_extract_dinv(int n_rows, const int32_t* indptr, const int32_t* indice
                         cudaStream_t st) {
   if (n_rows == 0) return KNP_OK;
   extract_dinv_kernel<<<(n_rows + 255) / 256, 256, 0, st>>>(n_rows, indptr, indices, vals, dinv);
-  KNP_CUDA(cudaGetLastError());
+  KNP_LAUNCHED();
   return KNP_OK;
 }
 
@@ -129,7 +135,7 @@ __global__ void dense_gemv_kernel(int n, const double* __restrict__ M, const dou
 int launch_dense_gemv(int n, const double* Minv, const double* b, double* x, cudaStream_t st) {
   if (n == 0) return KNP_OK;
   dense_gemv_kernel<<<(n + 7) / 8, 256, 0, st>>>(n, Minv, b, x);
-  KNP_CUDA(cudaGetLastError());
+  KNP_LAUNCHED();
   return KNP_OK;
 }
 
@@ -200,45 +206,53 @@ int launch_multi_dot(int n, int m, const double* V, size_t ldv, const double* w,
                      cudaStream_t st) {
   if (m == 0) {
     multi_dot_kernel<<<RED_BLOCKS, 256, 0, st>>>(n, 0, 0, 0, 1, V, ldv, w, partial);
-    KNP_CUDA(cudaGetLastError());
+    KNP_LAUNCHED();
   }
   for (int j0 = 0; j0 < m; j0 += MD_CHUNK) {
     const int cnt = m - j0 < MD_CHUNK ? m - j0 : MD_CHUNK;
     multi_dot_kernel<<<RED_BLOCKS, 256, 0, st>>>(n, j0, cnt, m, j0 == 0 ? 1 : 0, V, ldv, w, partial);
-    KNP_CUDA(cudaGetLastError());
+    KNP_LAUNCHED();
   }
   reduce_rows_kernel<<<(m + 1 + 7) / 8, 256, 0, st>>>(m + 1, RED_BLOCKS, partial, out);
-  KNP_CUDA(cudaGetLastError());
+  KNP_LAUNCHED();
   return KNP_OK;
 }
 
 __global__ void __launch_bounds__(256) multi_axpy_kernel(int n, int m, const double* __restrict__ V, size_t ldv,
                                                          const double* __restrict__ h, double sign,
-                                                         double* __restrict__ w) {
+                                                         const double* __restrict__ scale, double* __restrict__ w) {
   __shared__ double hs[64];
   if (threadIdx.x < m) hs[threadIdx.x] = h[threadIdx.x];
   __syncthreads();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     double acc = 0.0;
     for (int j = 0; j < m; ++j) acc += hs[j] * V[(size_t)j * ldv + i];
-    w[i] += sign * acc;
+    w[i] += sign * (scale ? scale[i] * acc : acc);
   }
-}
-static int grid_for(int n) {
-  int grid = (n + 255) / 256;
-  if (grid > 148 * 16) grid = 148 * 16;
-  return grid < 1 ? 1 : grid;
 }
 int launch_multi_axpy(int n, int m, const double* V, size_t ldv, const double* h, double* w, cudaStream_t st) {
   if (n == 0 || m == 0) return KNP_OK;
-  multi_axpy_kernel<<<grid_for(n), 256, 0, st>>>(n, m, V, ldv, h, -1.0, w);
-  KNP_CUDA(cudaGetLastError());
+  multi_axpy_kernel<<<grid_for(n), 256, 0, st>>>(n, m, V, ldv, h, -1.0, nullptr, w);
+  KNP_LAUNCHED();
   return KNP_OK;
 }
-int launch_update_x(int n, int m, const double* V, size_t ldv, const double* y_dev, double* x, cudaStream_t st) {
+int launch_update_x(int n, int m, const double* V, size_t ldv, const double* y_dev, double* x, const double* scale,
+                    cudaStream_t st) {
   if (n == 0 || m == 0) return KNP_OK;
-  multi_axpy_kernel<<<grid_for(n), 256, 0, st>>>(n, m, V, ldv, y_dev, 1.0, x);
-  KNP_CUDA(cudaGetLastError());
+  multi_axpy_kernel<<<grid_for(n), 256, 0, st>>>(n, m, V, ldv, y_dev, 1.0, scale, x);
+  KNP_LAUNCHED();
+  return KNP_OK;
+}
+
+__global__ void pointwise_kernel(int n, const double* __restrict__ a, const double* __restrict__ b, int divide,
+                                 double* __restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    out[i] = divide ? a[i] / b[i] : a[i] * b[i];
+}
+int launch_pointwise(int n, const double* a, const double* b, int divide, double* out, cudaStream_t st) {
+  if (n == 0) return KNP_OK;
+  pointwise_kernel<<<grid_for(n), 256, 0, st>>>(n, a, b, divide, out);
+  KNP_LAUNCHED();
   return KNP_OK;
 }
 
@@ -249,7 +263,7 @@ __global__ void axpby_kernel(int n, double a, const double* __restrict__ x, doub
 int launch_axpby(int n, double a, const double* x, double b, double* y, cudaStream_t st) {
   if (n == 0) return KNP_OK;
   axpby_kernel<<<grid_for(n), 256, 0, st>>>(n, a, x, b, y);
-  KNP_CUDA(cudaGetLastError());
+  KNP_LAUNCHED();
   return KNP_OK;
 }
 
@@ -262,7 +276,7 @@ __global__ void scale_copy_kernel(int n, const double* __restrict__ alpha, int i
 int launch_scale_copy(int n, const double* alpha_dev, int invert, const double* x, double* y, cudaStream_t st) {
   if (n == 0) return KNP_OK;
   scale_copy_kernel<<<grid_for(n), 256, 0, st>>>(n, alpha_dev, invert, x, y);
-  KNP_CUDA(cudaGetLastError());
+  KNP_LAUNCHED();
   return KNP_OK;
 }
 
@@ -280,9 +294,9 @@ __global__ void __launch_bounds__(256) range_sum_kernel(const double* __restrict
 int launch_range_sum(const double* x, int lo0, int hi0, int lo1, int hi1, double* partial, double* out,
                      cudaStream_t st) {
   range_sum_kernel<<<RED_BLOCKS, 256, 0, st>>>(x, lo0, hi0, lo1, hi1, partial);
-  KNP_CUDA(cudaGetLastError());
+  KNP_LAUNCHED();
   reduce_rows_kernel<<<1, 32, 0, st>>>(1, RED_BLOCKS, partial, out);
-  KNP_CUDA(cudaGetLastError());
+  KNP_LAUNCHED();
   return KNP_OK;
 }
 __global__ void range_shift_kernel(double* __restrict__ x, int lo0, int hi0, int lo1, int hi1,
@@ -297,12 +311,12 @@ int launch_range_shift(double* x, int lo0, int hi0, int lo1, int hi1, const doub
   const int n = (hi0 - lo0) + (hi1 - lo1);
   if (n == 0) return KNP_OK;
   range_shift_kernel<<<grid_for(n), 256, 0, st>>>(x, lo0, hi0, lo1, hi1, sum_dev, inv_count);
-  KNP_CUDA(cudaGetLastError());
+  KNP_LAUNCHED();
   return KNP_OK;
 }
 int launch_reduce_partials(const double* partial, int n_partial, double* out, cudaStream_t st) {
   reduce_rows_kernel<<<1, 32, 0, st>>>(1, n_partial, partial, out);
-  KNP_CUDA(cudaGetLastError());
+  KNP_LAUNCHED();
   return KNP_OK;
 }
 

@@ -17,6 +17,9 @@ int ensure_workspace(knp_ctx* c, int restart) {
   KNP_CUDA(cudaMemset(c->V.p, 0, c->ldv * (restart + 1) * sizeof(double)));
   KNP_TRY(c->w.alloc(c->ldv));
   KNP_TRY(c->tmp.alloc(c->ldv));
+  KNP_TRY(c->tmp2.alloc(c->ldv));
+  KNP_TRY(c->colscale.alloc(c->ldv));
+  KNP_CUDA(cudaMemset(c->tmp2.p, 0, c->ldv * sizeof(double)));
   KNP_CUDA(cudaMemset(c->w.p, 0, c->ldv * sizeof(double)));
   KNP_CUDA(cudaMemset(c->tmp.p, 0, c->ldv * sizeof(double)));
   KNP_TRY(c->partial.alloc((size_t)(restart + 2) * RED_BLOCKS));
@@ -143,7 +146,7 @@ int pc_apply(knp_ctx* c, const double* r, double* z, cudaStream_t st) {
     int grid = (n + 255) / 256;
     if (grid > 148 * 16) grid = 148 * 16;
     dinv_mul_kernel<<<grid, 256, 0, st>>>(n, c->pc_dinv.p, r, z);
-    KNP_CUDA(cudaGetLastError());
+    KNP_LAUNCHED();
     return KNP_OK;
   }
   KNP_CUDA(cudaMemcpyAsync(z, r, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -200,8 +203,25 @@ int gmres_solve(knp_ctx* c, const double* A_vals, const double* b, double* x, co
   std::vector<double> H((size_t)(m + 1) * m, 0.0), g(m + 1, 0.0), cs(m, 0.0), sn(m, 0.0), y(m, 0.0);
   auto Hat = [&](int i, int j) -> double& { return H[(size_t)i * m + j]; };
 
-  // ||B b||
+  // optional per-field variable scaling x = D y (host fills D on the device once per solve)
+  bool scaled = false;
+  for (int f = 0; f < 8; ++f) scaled = scaled || o->field_scale[f] > 0.0;
+  const double* D = nullptr;
+  if (scaled) {
+    std::vector<double> hs(c->ldv, 1.0);
+    const Layout& L = c->T.L;
+    for (int s = 0; s < 2; ++s)
+      for (int f = 0; f < 4; ++f) {
+        const double sc = o->field_scale[4 * s + f] > 0.0 ? o->field_scale[4 * s + f] : 1.0;
+        for (int q = 0; q < L.n_loc[s]; ++q) hs[L.col(s, f, q)] = sc;
+      }
+    KNP_CUDA(cudaMemcpyAsync(c->colscale.p, hs.data(), c->ldv * sizeof(double), cudaMemcpyHostToDevice, st));
+    KNP_CUDA(cudaStreamSynchronize(st));
+    D = c->colscale.p;
+  }
+  // ||B b||  (in the scaled variables when D is set)
   KNP_TRY(apply_B(c, o, b, w, st));
+  if (D) KNP_TRY(launch_pointwise(n, w, D, 1, w, st));
   KNP_TRY(dots_to_host(c, 0, w, hp, st));
   const double bnorm = std::sqrt(hp[0]);
   info->rnorm0 = bnorm;
@@ -220,6 +240,7 @@ int gmres_solve(knp_ctx* c, const double* A_vals, const double* b, double* x, co
     // r = B (b - A x)
     KNP_TRY(spmv_A(c, A_vals, x, tmp, EPI_RESID, b, st));
     KNP_TRY(apply_B(c, o, tmp, w, st));
+    if (D) KNP_TRY(launch_pointwise(n, w, D, 1, w, st));
     KNP_TRY(dots_to_host(c, 0, w, hp, st));
     const double beta = std::sqrt(hp[0]);
     info->rnorm = beta;
@@ -249,8 +270,14 @@ int gmres_solve(knp_ctx* c, const double* A_vals, const double* b, double* x, co
     bool done = false;
     for (int j = 0; j < m; ++j) {
       double* vj = c->V.p + (size_t)j * c->ldv;
-      KNP_TRY(spmv_A(c, A_vals, vj, tmp, EPI_SET, nullptr, st));
+      if (D) {
+        KNP_TRY(launch_pointwise(n, vj, D, 0, c->tmp2.p, st));
+        KNP_TRY(spmv_A(c, A_vals, c->tmp2.p, tmp, EPI_SET, nullptr, st));
+      } else {
+        KNP_TRY(spmv_A(c, A_vals, vj, tmp, EPI_SET, nullptr, st));
+      }
       KNP_TRY(apply_B(c, o, tmp, w, st));
+      if (D) KNP_TRY(launch_pointwise(n, w, D, 1, w, st));
       // classical Gram-Schmidt, two passes; every pass is one fused multi-dot and one fused multi-axpy
       KNP_TRY(dots_to_host(c, j + 1, w, hp, st));
       for (int i = 0; i <= j; ++i) Hat(i, j) = hp[i];
@@ -300,7 +327,7 @@ int gmres_solve(knp_ctx* c, const double* A_vals, const double* b, double* x, co
     }
     for (int i = 0; i < jdone; ++i) hp[i] = y[i];
     KNP_CUDA(cudaMemcpyAsync(c->ydev.p, hp, jdone * sizeof(double), cudaMemcpyHostToDevice, st));
-    KNP_TRY(launch_update_x(n, jdone, c->V.p, c->ldv, c->ydev.p, x, st));
+    KNP_TRY(launch_update_x(n, jdone, c->V.p, c->ldv, c->ydev.p, x, D, st));
     KNP_CUDA(cudaStreamSynchronize(st));   // hp is reused by the next dots_to_host
     if (done && o->refine == 0) {
       info->converged = 1;

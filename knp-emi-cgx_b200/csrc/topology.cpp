@@ -12,6 +12,7 @@
 
 namespace knp {
 
+unsigned long long g_kernel_launches = 0;
 static thread_local char g_err[1024] = "";
 void set_error(const char* fmt, ...) {
   va_list ap;

@@ -51,7 +51,8 @@ class TagModels(C.Structure):
 
 class SolveOpts(C.Structure):
     _fields_ = [("rtol", C.c_double), ("max_it", C.c_int32), ("restart", C.c_int32), ("pc", C.c_int32),
-                ("project_nullspace", C.c_int32), ("zero_mean_solution", C.c_int32), ("refine", C.c_int32)]
+                ("project_nullspace", C.c_int32), ("zero_mean_solution", C.c_int32), ("refine", C.c_int32),
+                ("field_scale", C.c_double * 8)]
 
 
 class SolveInfo(C.Structure):
@@ -60,7 +61,7 @@ class SolveInfo(C.Structure):
 
 # every symbol declared in include/knpemi_b200.h (tests check that the library exports all of them)
 SYMBOLS = [
-    "knp_last_error", "knp_version", "knp_create", "knp_destroy", "knp_get_sizes", "knp_csr_dev", "knp_csr_host",
+    "knp_last_error", "knp_version", "knp_launch_count", "knp_create", "knp_destroy", "knp_get_sizes", "knp_csr_dev", "knp_csr_host",
     "knp_csr_P_host", "knp_dofmap_host", "knp_mverts_host", "knp_set_params", "knp_stimulus_area_local",
     "knp_set_state", "knp_get_state", "knp_state_dev", "knp_phi_m_host", "knp_gate_step", "knp_assemble",
     "knp_assemble_P", "knp_values_dev", "knp_spmv", "knp_pc_setup", "knp_pc_apply", "knp_solve", "knp_step",
@@ -87,6 +88,7 @@ def load():
                        "or `make -C knp-emi-cgx_b200/csrc`. There is no CPU fallback.")
     lib = C.CDLL(LIB_PATH)
     lib.knp_last_error.restype = C.c_char_p
+    lib.knp_launch_count.restype = C.c_int64
     vp = C.c_void_p
     lib.knp_create.argtypes = [C.POINTER(vp), C.POINTER(MeshDesc), C.c_int]
     lib.knp_destroy.argtypes = [vp]
@@ -355,6 +357,10 @@ class Context:
 
     def halo_exchange(self, x_ptr=None, stream=None):
         check(self._lib.knp_halo_exchange(self.h, x_ptr, stream))
+
+
+def launch_count():
+    return int(load().knp_launch_count())
 
 
 def nccl_unique_id():

@@ -42,6 +42,7 @@ class SolverKNPEMI:
     gmres_restart = 30          # PETSc default
     direct_rtol = 1e-13         # "direct" = Krylov solve to the fp64 floor
     direct_refine = 2
+    direct_restart = 60
 
     def __init__(self, problem, solver_config: dict):
         self.problem = problem
@@ -81,9 +82,16 @@ class SolverKNPEMI:
         o = _lib.SolveOpts()
         pure_neumann = not self.problem.dirichlet_bcs and not self.problem.pin_ecs_potential
         if self.direct_solver:
-            o.rtol, o.max_it, o.restart = self.direct_rtol, self.ksp_max_it, self.gmres_restart
+            o.rtol, o.max_it, o.restart = self.direct_rtol, self.ksp_max_it, self.direct_restart
             o.pc, o.project_nullspace = 2, int(pure_neumann)
             o.zero_mean_solution, o.refine = int(pure_neumann), self.direct_refine
+            # balance concentrations (~1e2) against potentials (~1e-2) in the residual norm
+            p = self.problem
+            for s in range(2):
+                for f in range(3):
+                    o.field_scale[4 * s + f] = max(self.comm.allreduce(float(np.abs(p.wh[s][f]._data).max()), op=MPI.MAX), 1e-300)
+                o.field_scale[4 * s + 3] = max(self.comm.allreduce(float(np.abs(p.wh[0][3]._data).max()), op=MPI.MAX),
+                                               self.comm.allreduce(float(np.abs(p.wh[1][3]._data).max()), op=MPI.MAX), 1e-3)
         else:
             if self.ksp_type != "gmres":
                 raise NotImplementedError(f"ksp_type {self.ksp_type!r}: the system is nonsymmetric; only gmres is implemented")
