@@ -61,6 +61,14 @@ class Comm:
         d.broadcast_object_list(box, src=root)
         return box[0]
 
+    def allgather(self, obj):
+        d = _dist()
+        if d is None or d.get_world_size() == 1:
+            return [obj]
+        out = [None] * d.get_world_size()
+        d.all_gather_object(out, obj)
+        return out
+
     def Barrier(self):
         d = _dist()
         if d is not None and d.get_world_size() > 1:

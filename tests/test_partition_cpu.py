@@ -1,0 +1,120 @@
+"""Multi-GPU host logic on the CPU: vertex partition, ghost layer, halo lists (simulated ranks in one process),
+owner-computes assembly against the global oracle, and a real world_size-2 gloo run of the Comm shim + exchange."""
+import os
+import subprocess
+import sys
+import numpy as np
+import pytest
+import scipy.sparse as sp
+from oracle.fixtures import from_arrays
+from oracle.knpemi import KNPEMIOracle, OracleParams
+from conftest import MODELS_TEST, ROOT
+
+
+def _setup(kb, gdim, n, m, size):
+    part = __import__("importlib").import_module("knp-emi-cgx_b200.partition")
+    mesh = kb.mesh.cell_array_mesh(gdim, n, m)
+    locs = [part.partition_mesh(mesh, r, size) for r in range(size)]
+    lays = [part.Layout(part.local_dofmaps(l), l.n_owned) for l, _ in locs]
+    reqs = []
+    for (l, info), lay in zip(locs, lays):
+        mine = part.ghost_requests(l, info, lay)
+        reqs.append({r: {s: v[0] for s, v in d.items()} for r, d in mine.items()})
+    lists = [part.build_halo_lists(l, info, lay, reqs) for (l, info), lay in zip(locs, lays)]
+    return part, mesh, locs, lays, lists
+
+
+@pytest.mark.parametrize("gdim,n,m,size", [(2, 24, 3, 2), (2, 24, 3, 3), (2, 32, 4, 4), (3, 8, 2, 2), (3, 8, 2, 8)])
+def test_partition_invariants_and_halo_exchange(kb, gdim, n, m, size):
+    part, mesh, locs, lays, lists = _setup(kb, gdim, n, m, size)
+    nv = mesh.x.shape[0]
+    owned = np.concatenate([info["l2g"][:l.n_owned] for l, info in locs])
+    assert np.array_equal(np.sort(owned), np.arange(nv))                         # every vertex owned exactly once
+    # every cell / membrane facet integrated exactly once
+    cnt = np.zeros(mesh.cells.shape[0], int)
+    key = {tuple(c): i for i, c in enumerate(mesh.cells.tolist())}
+    for l, info in locs:
+        gc = info["l2g"][l.cells]
+        for c, o in zip(gc.tolist(), l.cell_owned.tolist()):
+            cnt[key[tuple(c)]] += o
+    assert (cnt == 1).all()
+    assert sum(int(l.mf_owned.sum()) for l, _ in locs) == mesh.mf_verts.shape[0]
+    # rows: union over ranks = global dof count
+    o = KNPEMIOracle(from_arrays(gdim, mesh.x, mesh.cells, mesh.cell_tags, mesh.intra_tags),
+                     OracleParams(intra_tags=tuple(mesh.intra_tags), extra_tag=1, membrane_tags=tuple(mesh.intra_tags),
+                                  stimulus_tags=(2,)), MODELS_TEST)
+    assert sum(lay.n_rows for lay in lays) == o.n
+    # simulated halo exchange of a field that encodes (subdomain, field, global vertex)
+    def field(s, f, gv):
+        return 1000.0 * (4 * s + f) + gv + 0.5
+    xs = []
+    for (l, info), lay in zip(locs, lays):
+        x = np.full(lay.n_cols, np.nan)
+        for s in range(2):
+            gv = info["l2g"][lay.node_vert[s]]
+            for f in range(4):
+                q = np.arange(lay.n_own[s])
+                x[lay.col(s, f, q)] = field(s, f, gv[:lay.n_own[s]])
+        xs.append(x)
+    for r, (peers, sp_, sc, rp, rc) in enumerate(lists):
+        for i, pr in enumerate(peers.tolist()):
+            ppeers, psp, psc, _, _ = lists[pr]
+            j = ppeers.tolist().index(r)
+            buf = xs[pr][psc[psp[j]:psp[j + 1]]]                                  # what the peer packs for me
+            assert buf.size == rp[i + 1] - rp[i]
+            xs[r][rc[rp[i]:rp[i + 1]]] = buf
+    for (l, info), lay, x in zip(locs, lays, xs):
+        assert not np.isnan(x).any()                                             # every ghost column was filled
+        for s in range(2):
+            gv = info["l2g"][lay.node_vert[s]]
+            for f in range(4):
+                assert np.array_equal(x[lay.col(s, f, np.arange(lay.n_loc[s]))], field(s, f, gv))
+
+
+def test_owner_computes_assembly_equals_global_rows(kb):
+    """Assembling on the local mesh (owned vertices + one ghost-cell layer) reproduces the global rows of the owned
+    dofs without any exchange: the claim behind the distributed row kernel."""
+    part, mesh, locs, lays, _ = _setup(kb, 2, 24, 3, 3)
+    it = tuple(mesh.intra_tags)
+    P = OracleParams(intra_tags=it, extra_tag=1, membrane_tags=it, stimulus_tags=(2,), scale_stimulus=False)
+    og = KNPEMIOracle(from_arrays(2, mesh.x, mesh.cells, mesh.cell_tags, it), P, MODELS_TEST)
+    rng = np.random.default_rng(0)
+    for s in range(2):
+        og.c[s] *= 1 + 0.05 * rng.random(og.c[s].shape)
+    og.phi_m += 0.003 * rng.standard_normal(og.phi_m.shape)
+    og.gates *= 1 + 0.1 * rng.random(og.gates.shape)
+    Ag, bg = og.assemble(2 * P.dt)
+    Ag = Ag.tocsr()
+    for (l, info), lay in zip(locs, lays):
+        l2g = info["l2g"]
+        ol = KNPEMIOracle(from_arrays(2, l.x, l.cells, l.cell_tags, it), P, MODELS_TEST)
+        for s in range(2):
+            ol.c[s] = og.c[s][:, l2g].copy()
+        ol.phi_m, ol.gates = og.phi_m[l2g].copy(), og.gates[:, l2g].copy()
+        Al, bl = ol.assemble(2 * P.dt)
+        # local oracle numbering (all local dofs, owned and ghost) -> global rows
+        gmap = np.empty(ol.n, np.int64)
+        for s in range(2):
+            for f in range(4):
+                lo = ol.base[s] + f * ol.ns[s]
+                gmap[lo:lo + ol.ns[s]] = og.row(s, f, l2g[ol.S[s]])
+        owned_rows = np.concatenate([ol.base[s] + f * ol.ns[s] + np.flatnonzero(ol.S[s] < l.n_owned)
+                                     for s in range(2) for f in range(4)])
+        C = Al[owned_rows].tocoo()
+        Aloc = sp.csr_matrix((C.data, (gmap[owned_rows][C.row], gmap[C.col])), shape=Ag.shape)
+        sel = sp.csr_matrix((np.ones(owned_rows.size), (gmap[owned_rows], gmap[owned_rows])), shape=Ag.shape)
+        ref = sel @ Ag
+        diff = abs(Aloc - ref)
+        assert diff.max() <= 1e-13 * abs(Ag).max()
+        assert np.abs(bl[owned_rows] - bg[gmap[owned_rows]]).max() <= 1e-13 * np.abs(bg).max()
+
+
+def test_gloo_world_size_2():
+    """Real two-process run (gloo): Comm shim collectives and a halo exchange through torch.distributed."""
+    worker = os.path.join(os.path.dirname(__file__), "dist_worker.py")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29517", worker],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("WORKER_OK") == 2
