@@ -70,6 +70,12 @@ int knp_create(knp_ctx** out, const knp_mesh_desc* mesh, int device) {
   KNP_TRY(c->d_indptr.upload(H.indptr));
   KNP_TRY(c->d_indptr_P.upload(H.indptr_P));
   {
+    std::vector<int32_t> blk;
+    c->nblk_A = build_rowblocks(H.indptr.data(), H.L.n_rows, blk);
+    if (c->nblk_A > 0) KNP_TRY(c->d_rowblk_A.upload(blk));
+    else c->nblk_A = 0;
+  }
+  {
     std::vector<double> qb(mesh->quad_bary, mesh->quad_bary + (size_t)mesh->n_quad * mesh->gdim);
     std::vector<double> qw(mesh->quad_w, mesh->quad_w + mesh->n_quad);
     KNP_TRY(c->d_qb.upload(qb));
@@ -356,14 +362,14 @@ int knp_assemble(knp_ctx* c, double t, double* A_vals, double* b, void* stream) 
   if (p.scale_stimulus) stim_fac *= 1.0 / c->params.stim_area;
   KNP_TRY(launch_facets(c->T, c->kp, c->d_tag_models.p, c->d_tag_stim.p, c->u.p, c->gates.p, stim_fac, c->fe.p, st));
   KNP_CUDA(cudaEventRecord(c->ev[2], st));
-  KNP_TRY(launch_rows(c->T, c->kp, 0, c->u.p, c->fe.p, A_vals ? A_vals : c->A_vals.p, b ? b : c->b.p, c->rows_stride, st));
+  KNP_TRY(launch_rows(c->T, c->kp, 0, c->u.p, c->fe.p, A_vals ? A_vals : c->A_vals.p, b ? b : c->b.p, c->H.max_deg, c->H.max_gdeg, st));
   return KNP_OK;
 }
 
 int knp_assemble_P(knp_ctx* c, double* P_vals, void* stream) {
   CTX_GUARD(c);
   KNP_CHECK(c->params_set, "knp_set_params must be called first");
-  KNP_TRY(launch_rows(c->T, c->kp, 1, c->u.p, c->fe.p, P_vals ? P_vals : c->P_vals.p, nullptr, c->rows_stride, pick(c, stream)));
+  KNP_TRY(launch_rows(c->T, c->kp, 1, c->u.p, c->fe.p, P_vals ? P_vals : c->P_vals.p, nullptr, c->H.max_deg, c->H.max_gdeg, pick(c, stream)));
   if (!P_vals) c->P_assembled = true;
   return KNP_OK;
 }
@@ -379,8 +385,9 @@ int knp_values_dev(knp_ctx* c, double** A_vals, double** b, double** P_vals, dou
 
 int knp_spmv(knp_ctx* c, const double* A_vals, const double* x, double* y, void* stream) {
   CTX_GUARD(c);
-  return launch_spmv(c->T.L.n_rows, c->H.nnz, c->d_indptr.p, c->d_indices.p, A_vals ? A_vals : c->A_vals.p, x, y,
-                     EPI_SET, nullptr, nullptr, 0.0, pick(c, stream));
+  const CsrView A{c->T.L.n_rows, c->H.nnz, c->d_indptr.p, c->d_indices.p, A_vals ? A_vals : c->A_vals.p,
+                  c->d_rowblk_A.p, c->nblk_A};
+  return spmv(A, x, y, EPI_SET, nullptr, nullptr, 0.0, pick(c, stream));
 }
 
 int knp_pc_setup(knp_ctx* c, const knp_solve_opts* o) {

@@ -15,6 +15,7 @@
 // Design note: all ten (d+1)x(d+1) cell blocks of KNPEMIx_problem.py:598-605,633-634 are linear
 // combinations of M^T, K^T and cbar_k K^T, and each block row shares the node's adjacency list, so the
 // "cell -> nnz map" collapses to one byte per (node, cell, local vertex): the adjacency slot.
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -280,20 +281,23 @@ template <int D, int MODE>
 __global__ void __launch_bounds__(ROWS_BLOCK) rows_kernel(DevTopo T, KParams P, const double* __restrict__ u,
                                                           const double* __restrict__ fe,
                                                           double* __restrict__ vals, double* __restrict__ bvec,
-                                                          int stride) {
+                                                          int stride, int group, int stage_len, int nb0) {
   constexpr int NV = D + 1;
   constexpr int NS = D * (D + 1) / 2;
   extern __shared__ double sm[];
   const int tid = threadIdx.x;
   const int lane = tid & 31;
-  const int w = blockIdx.x * ROWS_BLOCK + tid;
-  const bool active = w < T.n_work;
+  // blocks [0, nb0) serve the intracellular dofs, the rest the extracellular ones, so that the rows a warp
+  // produces for one field are one contiguous CSR span
+  const int s = blockIdx.x >= nb0 ? 1 : 0;
+  const int p = (blockIdx.x - (s ? nb0 : 0)) * blockDim.x + tid;
+  const bool active = p < T.L.n_own[s];
+  const int w = (s ? T.L.n_own[0] : 0) + p;
   double* acc = sm + (size_t)tid * stride;
+  double* stg = sm + (size_t)blockDim.x * stride + (size_t)(tid >> 5) * stage_len;
 
-  int s = 0, p = 0, deg = 0, gdeg = 0, g = -1;
+  int deg = 0, gdeg = 0, g = -1;
   if (active) {
-    s = w >= T.L.n_own[0] ? 1 : 0;
-    p = w - (s ? T.L.n_own[0] : 0);
     const int a0 = T.adj_ptr[w];
     deg = T.adj_ptr[w + 1] - a0;
     g = T.mv_of_node[w];
@@ -427,60 +431,61 @@ __global__ void __launch_bounds__(ROWS_BLOCK) rows_kernel(DevTopo T, KParams P, 
     }
   }
   __syncwarp();
-  // ---- stream the finished rows out: the 32 nodes of this warp, one row at a time, lanes along the row ----
+  // ---- output: each thread writes its finished row into the warp's staging strip at its CSR-relative offset, then
+  //      the warp copies the contiguous span to global memory with fully coalesced stores (one pass per field) ----
   const int* __restrict__ iptr = MODE == 0 ? T.indptr : T.indptr_P;
-  int rs[4] = {0, 0, 0, 0};
-  if (active) {
-#pragma unroll
-    for (int f = 0; f < 4; ++f) rs[f] = iptr[T.L.row(s, f, p)];
-  }
-  const unsigned amask = __ballot_sync(0xffffffffu, active);
-  const int wbase = tid - lane;
-  for (int i = 0; i < 32; ++i) {
-    if (!((amask >> i) & 1u)) break;
-    const int s_i = __shfl_sync(0xffffffffu, s, i);
-    const int deg_i = __shfl_sync(0xffffffffu, deg, i);
-    const int gdeg_i = MODE == 0 ? __shfl_sync(0xffffffffu, gdeg, i) : 0;
-    const double* ac = sm + (size_t)(wbase + i) * stride;
-#pragma unroll
-    for (int f = 0; f < 4; ++f) {
-      const int r0 = __shfl_sync(0xffffffffu, rs[f], i);
-      const int nseg = MODE == 0 ? (f < 3 ? 2 : 4) : 1;
-      const int len = nseg * deg_i + gdeg_i;
-      for (int j = lane; j < len; j += 32) {
-        int jj = j;
-        double v;
-        bool gam = false;
+  const double* a_m = acc;
+  const double* a_kk = acc + deg;
+  const double* a_kphi = acc + 2 * deg;
+  const double* a_pp = acc + 5 * deg;
+  const double* a_ga = acc + 6 * deg;
+  const double* a_g1 = acc + 6 * deg + 3 * gdeg;
+  const int gd = MODE == 0 ? gdeg : 0;
+#pragma unroll 1
+  for (int f = 0; f < 4; ++f) {
+    const int nseg = MODE == 0 ? (f < 3 ? 2 : 4) : 1;
+    const int rs = active ? iptr[T.L.row(s, f, p)] : 0;
+    const int len = active ? nseg * deg + gd : 0;
+#pragma unroll 1
+    for (int g0 = 0; g0 < 32; g0 += group) {
+      const int base = __shfl_sync(0xffffffffu, rs, g0);
+      const bool mine = active && lane >= g0 && lane < g0 + group;
+      if (mine) {
+        double* o = stg + (rs - base);
         if (MODE == 0) {
-          if (s_i == 1) {
-            jj -= gdeg_i;
-            gam = jj < 0;
-            if (gam) jj += gdeg_i;
+          if (f < 3) {
+            if (s == 1)
+              for (int e = 0; e < gd; ++e) *o++ = -a_ga[f * gdeg + e];
+            const double dk = P.dt * P.D[f];
+            for (int e = 0; e < deg; ++e) *o++ = a_m[e] + dk * a_kk[e];
+            for (int e = 0; e < deg; ++e) *o++ = a_kphi[f * deg + e];
+            if (s == 0)
+              for (int e = 0; e < gd; ++e) *o++ = -a_ga[f * gdeg + e];
           } else {
-            gam = jj >= nseg * deg_i;
-            if (gam) jj -= nseg * deg_i;
-          }
-        }
-        if (gam) {
-          v = f < 3 ? -ac[6 * deg_i + f * gdeg_i + jj] : -ac[6 * deg_i + 3 * gdeg_i + jj];
-        } else {
-          int seg = 0;
-          while (jj >= deg_i) {
-            jj -= deg_i;
-            ++seg;
-          }
-          if (MODE == 0) {
-            if (f < 3) {
-              v = seg == 0 ? ac[jj] + (P.dt * P.D[f]) * ac[deg_i + jj] : ac[(2 + f) * deg_i + jj];
-            } else {
-              v = seg < 3 ? (P.dt * P.z[seg] * P.D[seg]) * ac[deg_i + jj] : ac[5 * deg_i + jj];
+            if (s == 1)
+              for (int e = 0; e < gd; ++e) *o++ = -a_g1[e];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              const double ck = P.dt * P.z[k] * P.D[k];
+              for (int e = 0; e < deg; ++e) *o++ = ck * a_kk[e];
             }
+            for (int e = 0; e < deg; ++e) *o++ = a_pp[e];
+            if (s == 0)
+              for (int e = 0; e < gd; ++e) *o++ = -a_g1[e];
+          }
+        } else {
+          if (f < 3) {
+            const double dk = P.dt * P.D[f];
+            for (int e = 0; e < deg; ++e) *o++ = a_m[e] + dk * a_kk[e];
           } else {
-            v = f < 3 ? ac[jj] + (P.dt * P.D[f]) * ac[deg_i + jj] : ac[5 * deg_i + jj];
+            for (int e = 0; e < deg; ++e) *o++ = a_pp[e];
           }
         }
-        vals[(size_t)r0 + j] = v;
       }
+      const int total = __reduce_max_sync(0xffffffffu, mine ? rs + len - base : 0);
+      __syncwarp();
+      for (int q = lane; q < total; q += 32) vals[(size_t)base + q] = stg[q];
+      __syncwarp();
     }
   }
 }
@@ -594,33 +599,51 @@ int rows_smem_stride(int max_deg, int max_gdeg) {
   return st;
 }
 
+// block size / staging group for the row kernel from the mesh's maximum degrees (shared-memory budget)
+void rows_config(int max_deg, int max_gdeg, int mode, int& block, int& group, int& stage_len, size_t& smem) {
+  const int stride = rows_smem_stride(max_deg, max_gdeg);
+  const int maxrow = mode == 0 ? 4 * max_deg + max_gdeg : max_deg;
+  block = 128;
+  while (block > 32 && (size_t)block * stride * 8 > 64 * 1024) block >>= 1;
+  const size_t acc = (size_t)block * stride * 8;
+  const size_t budget = acc <= 60 * 1024 ? 74 * 1024 : (acc <= 100 * 1024 ? 112 * 1024 : 226 * 1024);
+  group = 32;
+  while (group > 1 && acc + (size_t)(block / 32) * group * maxrow * 8 > budget) group >>= 1;
+  if (const char* e = getenv("KNP_ROWS_BLOCK")) block = atoi(e);
+  if (const char* e = getenv("KNP_ROWS_GROUP")) group = atoi(e);
+  stage_len = group * maxrow;
+  smem = (size_t)block * stride * 8 + (size_t)(block / 32) * stage_len * 8;
+}
+
 template <int D, int MODE>
 static int launch_rows_t(const DevTopo& T, const KParams& P, const double* u, const double* fe, double* vals,
-                         double* b, int stride, cudaStream_t st) {
-  const size_t smem = (size_t)ROWS_BLOCK * stride * sizeof(double);
+                         double* b, int stride, int max_deg, int max_gdeg, cudaStream_t st) {
+  int block, group, stage_len;
+  size_t smem;
+  rows_config(max_deg, max_gdeg, MODE, block, group, stage_len, smem);
+  if (smem > 227 * 1024) {
+    set_error("vertex degree too large for the row kernel's shared-memory strip (%zu bytes)", smem);
+    return KNP_E_UNSUPPORTED;
+  }
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     KNP_CUDA(cudaFuncSetAttribute(rows_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  const int grid = (T.n_work + ROWS_BLOCK - 1) / ROWS_BLOCK;
-  rows_kernel<D, MODE><<<grid, ROWS_BLOCK, smem, st>>>(T, P, u, fe, vals, b, stride);
+  const int nb0 = (T.L.n_own[0] + block - 1) / block, nb1 = (T.L.n_own[1] + block - 1) / block;
+  rows_kernel<D, MODE><<<nb0 + nb1, block, smem, st>>>(T, P, u, fe, vals, b, stride, group, stage_len, nb0);
   KNP_LAUNCHED();
   return KNP_OK;
 }
 
 int launch_rows(const DevTopo& T, const KParams& P, int mode, const double* u, const double* fe, double* vals,
-                double* b, int stride, cudaStream_t st) {
+                double* b, int max_deg, int max_gdeg, cudaStream_t st) {
   if (T.n_work == 0) return KNP_OK;
-  const size_t smem = (size_t)ROWS_BLOCK * stride * sizeof(double);
-  if (smem > 227 * 1024) {
-    set_error("vertex degree too large for the row kernel's shared-memory strip (%zu bytes)", smem);
-    return KNP_E_UNSUPPORTED;
-  }
-  if (T.gdim == 2) return mode == 0 ? launch_rows_t<2, 0>(T, P, u, fe, vals, b, stride, st)
-                                    : launch_rows_t<2, 1>(T, P, u, fe, vals, b, stride, st);
-  return mode == 0 ? launch_rows_t<3, 0>(T, P, u, fe, vals, b, stride, st)
-                   : launch_rows_t<3, 1>(T, P, u, fe, vals, b, stride, st);
+  const int stride = rows_smem_stride(max_deg, max_gdeg);
+  if (T.gdim == 2) return mode == 0 ? launch_rows_t<2, 0>(T, P, u, fe, vals, b, stride, max_deg, max_gdeg, st)
+                                    : launch_rows_t<2, 1>(T, P, u, fe, vals, b, stride, max_deg, max_gdeg, st);
+  return mode == 0 ? launch_rows_t<3, 0>(T, P, u, fe, vals, b, stride, max_deg, max_gdeg, st)
+                   : launch_rows_t<3, 1>(T, P, u, fe, vals, b, stride, max_deg, max_gdeg, st);
 }
 
 int launch_csr_indices(const DevTopo& T, int mode, int32_t* indices, cudaStream_t st) {

@@ -153,8 +153,9 @@ struct Params {
 struct CsrDev {
   int n_rows = 0, n_cols = 0;
   int64_t nnz = 0;
-  DevBuf<int32_t> indptr, indices;
+  DevBuf<int32_t> indptr, indices, rowblk;
   DevBuf<double> vals;
+  int nblk = 0;   // row blocks of the streaming SpMV (0: use the CSR-vector kernel)
 };
 
 struct CsrHost {

@@ -23,7 +23,7 @@ int launch_facets(const DevTopo& T, const KParams& P, const uint32_t* tag_models
                   const double* u, const double* gates, double stim_fac, double* fe, cudaStream_t st);
 int rows_smem_stride(int max_deg, int max_gdeg);
 int launch_rows(const DevTopo& T, const KParams& P, int mode, const double* u, const double* fe, double* vals,
-                double* b, int stride, cudaStream_t st);
+                double* b, int max_deg, int max_gdeg, cudaStream_t st);
 int launch_csr_indices(const DevTopo& T, int mode, int32_t* indices, cudaStream_t st);
 int launch_l2_cells(int gdim, const Layout& L, int s, int field, int n_cells, const int32_t* cell_nodes,
                     const int32_t* cell_tag, const int32_t* cell_owned, const double* node_x, int nodeoff,
@@ -36,6 +36,21 @@ enum SpmvEpi { EPI_SET = 0, EPI_RESID = 1, EPI_JACOBI = 2, EPI_ADD = 3 };
 int launch_spmv(int n_rows, int64_t nnz, const int32_t* indptr, const int32_t* indices, const double* vals,
                 const double* x, double* out, int epi, const double* b, const double* dinv, double w,
                 cudaStream_t st);
+// TMA-staged streaming SpMV over precomputed row blocks (falls back to launch_spmv when nblk <= 0)
+int build_rowblocks(const int32_t* indptr_host, int n_rows, std::vector<int32_t>& blk);
+int launch_spmv_stream(int nblk, const int32_t* rowblk, const int32_t* indptr, const int32_t* indices, const double* vals,
+                       const double* x, double* out, int epi, const double* b, const double* dinv, double w, cudaStream_t st);
+struct CsrView {
+  int n_rows;
+  int64_t nnz;
+  const int32_t *indptr, *indices;
+  const double* vals;
+  const int32_t* rowblk;
+  int nblk;
+};
+// out = epilogue(M x): streaming TMA kernel when row blocks exist and the arrays are 16-byte aligned, else CSR-vector
+int spmv(const CsrView& M, const double* x, double* out, int epi, const double* b, const double* dinv, double w,
+         cudaStream_t st);
 int launch_scale_dinv(int n, double w, const double* dinv, const double* b, double* x, cudaStream_t st);   // x = w*dinv*b
 int launch_extract_dinv(int n_rows, const int32_t* indptr, const int32_t* indices, const double* vals, double* dinv,
                         cudaStream_t st);

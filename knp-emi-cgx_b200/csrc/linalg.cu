@@ -58,6 +58,167 @@ __global__ void __launch_bounds__(256) spmv_kernel(int n_rows, const int32_t* __
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Streaming SpMV: persistent CTAs walk over precomputed row blocks (<= SPMV_CAP non-zeros, <= 256 rows).  One elected
+// thread moves the block's values and column indices into shared memory with two TMA 1-D bulk copies
+// (cp.async.bulk ... mbarrier::complete_tx) into a 2-stage ring, so the next block streams in while the current one is
+// processed.  Every thread then owns SPMV_CAP/256 consecutive-stride elements: the x gathers of a thread are independent
+// (memory-level parallelism 8 instead of 1), products are written back in place, and each row is summed by one thread in
+// a fixed order (bitwise reproducible, no atomics).
+constexpr int SPMV_CAP = 2048;
+constexpr int SPMV_THREADS = 256;
+constexpr int SPMV_PAD = 8;
+
+struct SpmvStage {
+  double v[SPMV_CAP + SPMV_PAD];
+  int c[SPMV_CAP + SPMV_PAD];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(SPMV_THREADS) spmv_stream_kernel(int nblk, const int32_t* __restrict__ rowblk,
+                                                                    const int32_t* __restrict__ indptr,
+                                                                    const int32_t* __restrict__ indices,
+                                                                    const double* __restrict__ vals,
+                                                                    const double* __restrict__ x, double* __restrict__ out,
+                                                                    const double* __restrict__ b,
+                                                                    const double* __restrict__ dinv, double w) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  SpmvStage* st = reinterpret_cast<SpmvStage*>(smem_raw);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + 2 * sizeof(SpmvStage));
+  __shared__ int s_a4[2], s_ntma[2];
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto issue = [&](int blk, int s) {
+    // called by thread 0 only
+    const int r0 = rowblk[blk], r1 = rowblk[blk + 1];
+    const int a = indptr[r0], e = indptr[r1];
+    const int a4 = a & ~3;
+    const int ntma = (e - a4) & ~3;          // multiple of 4 elements -> 16-byte multiples for both arrays
+    s_a4[s] = a4;
+    s_ntma[s] = ntma;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(&bar[s], (uint32_t)ntma * 12u);
+    if (ntma > 0) {
+      tma_load_1d(st[s].v, vals + a4, (uint32_t)ntma * 8u, &bar[s]);
+      tma_load_1d(st[s].c, indices + a4, (uint32_t)ntma * 4u, &bar[s]);
+    }
+  };
+
+  int blk = blockIdx.x;
+  if (tid == 0 && blk < nblk) issue(blk, 0);
+  for (int it = 0; blk < nblk; blk += gridDim.x, ++it) {
+    const int s = it & 1;
+    const int nxt = blk + gridDim.x;
+    if (tid == 0 && nxt < nblk) issue(nxt, s ^ 1);
+    const int r0 = rowblk[blk], r1 = rowblk[blk + 1];
+    const int a = indptr[r0], e = indptr[r1];
+    mbar_wait(&bar[s], (uint32_t)((it >> 1) & 1));
+    const int a4 = a & ~3;
+    const int ntma = (e - a4) & ~3;
+    const int n = e - a4;                    // staged elements (the first a - a4 are padding of the previous block)
+    double* sv = st[s].v;
+    int* sc = st[s].c;
+    // the (< 4) trailing elements that do not fill a 16-byte unit
+    if (tid < n - ntma) {
+      sv[ntma + tid] = vals[a4 + ntma + tid];
+      sc[ntma + tid] = indices[a4 + ntma + tid];
+    }
+    __syncthreads();
+    // products, in place; 8 independent gathers per thread
+#pragma unroll
+    for (int i = 0; i < (SPMV_CAP + SPMV_PAD + SPMV_THREADS - 1) / SPMV_THREADS; ++i) {
+      const int j = tid + i * SPMV_THREADS;
+      if (j < n) sv[j] = sv[j] * __ldg(x + sc[j]);
+    }
+    __syncthreads();
+    // one thread per row, fixed summation order
+    for (int r = r0 + tid; r < r1; r += SPMV_THREADS) {
+      const int j0 = indptr[r] - a4, j1 = indptr[r + 1] - a4;
+      double sum = 0.0;
+      for (int j = j0; j < j1; ++j) sum += sv[j];
+      double res;
+      if (EPI == EPI_SET) res = sum;
+      else if (EPI == EPI_RESID) res = b[r] - sum;
+      else if (EPI == EPI_JACOBI) res = x[r] + w * dinv[r] * (b[r] - sum);
+      else res = out[r] + sum;
+      out[r] = res;
+    }
+    __syncthreads();
+  }
+}
+
+// greedy row blocks: <= SPMV_CAP non-zeros (counted from the 4-aligned start) and <= SPMV_THREADS rows
+int build_rowblocks(const int32_t* indptr, int n_rows, std::vector<int32_t>& blk) {
+  blk.clear();
+  blk.push_back(0);
+  int r0 = 0;
+  while (r0 < n_rows) {
+    const int a4 = indptr[r0] & ~3;
+    int r1 = r0;
+    while (r1 < n_rows && r1 - r0 < SPMV_THREADS && indptr[r1 + 1] - a4 <= SPMV_CAP) ++r1;
+    if (r1 == r0) return -1;   // a single row exceeds the stage capacity: caller falls back to the CSR-vector kernel
+    blk.push_back(r1);
+    r0 = r1;
+  }
+  return (int)blk.size() - 1;
+}
+
+int launch_spmv_stream(int nblk, const int32_t* rowblk, const int32_t* indptr, const int32_t* indices, const double* vals,
+                       const double* x, double* out, int epi, const double* b, const double* dinv, double w, cudaStream_t st) {
+  if (nblk == 0) return KNP_OK;
+  const size_t smem = 2 * sizeof(SpmvStage) + 2 * sizeof(uint64_t);
+  static bool configured = false;
+  if (!configured) {
+    KNP_CUDA(cudaFuncSetAttribute(spmv_stream_kernel<EPI_SET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    KNP_CUDA(cudaFuncSetAttribute(spmv_stream_kernel<EPI_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    KNP_CUDA(cudaFuncSetAttribute(spmv_stream_kernel<EPI_JACOBI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    KNP_CUDA(cudaFuncSetAttribute(spmv_stream_kernel<EPI_ADD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const int grid = nblk < 148 * 4 ? nblk : 148 * 4;   // persistent: 4 CTAs per SM
+  switch (epi) {
+    case EPI_SET: spmv_stream_kernel<EPI_SET><<<grid, SPMV_THREADS, smem, st>>>(nblk, rowblk, indptr, indices, vals, x, out, b, dinv, w); break;
+    case EPI_RESID: spmv_stream_kernel<EPI_RESID><<<grid, SPMV_THREADS, smem, st>>>(nblk, rowblk, indptr, indices, vals, x, out, b, dinv, w); break;
+    case EPI_JACOBI: spmv_stream_kernel<EPI_JACOBI><<<grid, SPMV_THREADS, smem, st>>>(nblk, rowblk, indptr, indices, vals, x, out, b, dinv, w); break;
+    default: spmv_stream_kernel<EPI_ADD><<<grid, SPMV_THREADS, smem, st>>>(nblk, rowblk, indptr, indices, vals, x, out, b, dinv, w); break;
+  }
+  KNP_LAUNCHED();
+  return KNP_OK;
+}
+
 template <int LANES>
 static int launch_spmv_l(int grid, int n_rows, const int32_t* indptr, const int32_t* indices, const double* vals,
                          const double* x, double* out, int epi, const double* b, const double* dinv, double w,
@@ -88,6 +249,14 @@ int launch_spmv(int n_rows, int64_t nnz, const int32_t* indptr, const int32_t* i
     case 16: return launch_spmv_l<16>(grid, n_rows, indptr, indices, vals, x, out, epi, b, dinv, w, st);
     default: return launch_spmv_l<32>(grid, n_rows, indptr, indices, vals, x, out, epi, b, dinv, w, st);
   }
+}
+
+int spmv(const CsrView& M, const double* x, double* out, int epi, const double* b, const double* dinv, double w,
+         cudaStream_t st) {
+  const bool aligned = (((uintptr_t)M.vals | (uintptr_t)M.indices) & 15u) == 0;
+  if (M.nblk > 0 && M.rowblk && aligned)
+    return launch_spmv_stream(M.nblk, M.rowblk, M.indptr, M.indices, M.vals, x, out, epi, b, dinv, w, st);
+  return launch_spmv(M.n_rows, M.nnz, M.indptr, M.indices, M.vals, x, out, epi, b, dinv, w, st);
 }
 
 __global__ void scale_dinv_kernel(int n, double w, const double* __restrict__ dinv, const double* __restrict__ b,

@@ -38,6 +38,10 @@ static int upload_csr(const CsrHost& h, CsrDev& d) {
   KNP_TRY(d.indptr.upload(h.indptr));
   KNP_TRY(d.indices.upload(h.indices));
   KNP_TRY(d.vals.upload(h.vals));
+  std::vector<int32_t> blk;
+  d.nblk = build_rowblocks(h.indptr.data(), h.n_rows, blk);
+  if (d.nblk > 0) KNP_TRY(d.rowblk.upload(blk));
+  else d.nblk = 0;
   return KNP_OK;
 }
 
@@ -112,6 +116,10 @@ int pc_setup(knp_ctx* c, const knp_solve_opts* o) {
 }
 
 // z = V-cycle(r); level-l right-hand side in bl, result written to xout (distinct from bl)
+static CsrView view(const CsrDev& M) {
+  return CsrView{M.n_rows, M.nnz, M.indptr.p, M.indices.p, M.vals.p, M.rowblk.p, M.nblk};
+}
+
 static int vcycle(knp_ctx* c, int l, const double* bl, double* xout, cudaStream_t st) {
   Amg& M = *c->amg;
   const int nl = (int)M.levels.size();
@@ -122,16 +130,16 @@ static int vcycle(knp_ctx* c, int l, const double* bl, double* xout, cudaStream_
   // pre-smooth from a zero initial guess
   KNP_TRY(launch_scale_dinv(n, w, L.dinv.p, bl, L.x.p, st));
   // r = b - A x ; b_{l+1} = R r
-  KNP_TRY(launch_spmv(n, L.A.nnz, L.A.indptr.p, L.A.indices.p, L.A.vals.p, L.x.p, L.r.p, EPI_RESID, bl, nullptr, 0.0, st));
+  KNP_TRY(spmv(view(L.A), L.x.p, L.r.p, EPI_RESID, bl, nullptr, 0.0, st));
   // child right-hand side; the child's result goes into this level's r, which is free after the restriction
   double* bc = (l + 1 == nl) ? M.cb.p : M.levels[l + 1]->b.p;
   double* xc = L.r.p;
-  KNP_TRY(launch_spmv(L.R.n_rows, L.R.nnz, L.R.indptr.p, L.R.indices.p, L.R.vals.p, L.r.p, bc, EPI_SET, nullptr, nullptr, 0.0, st));
+  KNP_TRY(spmv(view(L.R), L.r.p, bc, EPI_SET, nullptr, nullptr, 0.0, st));
   KNP_TRY(vcycle(c, l + 1, bc, xc, st));
   // x += P x_c
-  KNP_TRY(launch_spmv(n, L.P.nnz, L.P.indptr.p, L.P.indices.p, L.P.vals.p, xc, L.x.p, EPI_ADD, nullptr, nullptr, 0.0, st));
+  KNP_TRY(spmv(view(L.P), xc, L.x.p, EPI_ADD, nullptr, nullptr, 0.0, st));
   // post-smooth, out of place into xout
-  KNP_TRY(launch_spmv(n, L.A.nnz, L.A.indptr.p, L.A.indices.p, L.A.vals.p, L.x.p, xout, EPI_JACOBI, bl, L.dinv.p, w, st));
+  KNP_TRY(spmv(view(L.A), L.x.p, xout, EPI_JACOBI, bl, L.dinv.p, w, st));
   return KNP_OK;
 }
 
@@ -175,7 +183,8 @@ static int apply_B(knp_ctx* c, const knp_solve_opts* o, const double* v, double*
 
 static int spmv_A(knp_ctx* c, const double* A_vals, double* x, double* y, int epi, const double* b, cudaStream_t st) {
   KNP_TRY(halo_exchange(c, x, st));
-  return launch_spmv(c->T.L.n_rows, c->H.nnz, c->d_indptr.p, c->d_indices.p, A_vals, x, y, epi, b, nullptr, 0.0, st);
+  const CsrView A{c->T.L.n_rows, c->H.nnz, c->d_indptr.p, c->d_indices.p, A_vals, c->d_rowblk_A.p, c->nblk_A};
+  return spmv(A, x, y, epi, b, nullptr, 0.0, st);
 }
 
 // dots of w against V[0..m) plus ||w||^2 -> host (m+1 values)
@@ -278,18 +287,27 @@ int gmres_solve(knp_ctx* c, const double* A_vals, const double* b, double* x, co
       }
       KNP_TRY(apply_B(c, o, tmp, w, st));
       if (D) KNP_TRY(launch_pointwise(n, w, D, 1, w, st));
-      // classical Gram-Schmidt, two passes; every pass is one fused multi-dot and one fused multi-axpy
+      // classical Gram-Schmidt with refinement only if needed (DGKS criterion, PETSc's default
+      // KSP_GMRES_CGS_REFINE_IFNEEDED): every pass is one fused multi-dot (+ ||w||^2) and one fused multi-axpy
       KNP_TRY(dots_to_host(c, j + 1, w, hp, st));
-      for (int i = 0; i <= j; ++i) Hat(i, j) = hp[i];
-      KNP_TRY(launch_multi_axpy(n, j + 1, c->V.p, c->ldv, c->hdev.p, w, st));
-      KNP_TRY(dots_to_host(c, j + 1, w, hp, st));
-      double h2sq = 0.0;
+      double hsq = 0.0;
       for (int i = 0; i <= j; ++i) {
-        Hat(i, j) += hp[i];
-        h2sq += hp[i] * hp[i];
+        Hat(i, j) = hp[i];
+        hsq += hp[i] * hp[i];
       }
+      const double before = hp[j + 1];
       KNP_TRY(launch_multi_axpy(n, j + 1, c->V.p, c->ldv, c->hdev.p, w, st));
-      double nrm2 = hp[j + 1] - h2sq;
+      double nrm2 = before - hsq;
+      if (!(nrm2 > 0.5 * before)) {
+        KNP_TRY(dots_to_host(c, j + 1, w, hp, st));
+        double h2sq = 0.0;
+        for (int i = 0; i <= j; ++i) {
+          Hat(i, j) += hp[i];
+          h2sq += hp[i] * hp[i];
+        }
+        KNP_TRY(launch_multi_axpy(n, j + 1, c->V.p, c->ldv, c->hdev.p, w, st));
+        nrm2 = hp[j + 1] - h2sq;
+      }
       if (nrm2 < 0.0) nrm2 = 0.0;
       const double hn = std::sqrt(nrm2);
       Hat(j + 1, j) = hn;

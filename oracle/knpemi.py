@@ -455,7 +455,7 @@ class KNPEMIOracle:
         return x - ns * (ns @ x)
 
     def solve_gmres(self, A, b, x0, ns, Pinv, rtol, restart=30, maxit=5000):
-        """Left-preconditioned GMRES(restart) with classical Gram-Schmidt (+1 refinement),
+        """Left-preconditioned GMRES(restart) with classical Gram-Schmidt (refinement if needed),
         convergence ||B r|| <= rtol ||B b||, nullspace removed after every PC apply
         (PETSc KSP defaults).  Returns (x, iterations)."""
         def B(v):
@@ -479,12 +479,17 @@ class KNPEMIOracle:
             for j in range(restart):
                 w = B(A @ V[j])
                 h = V[: j + 1] @ w
+                before = w @ w
                 w = w - V[: j + 1].T @ h
-                h2 = V[: j + 1] @ w
-                w = w - V[: j + 1].T @ h2
-                h = h + h2
+                nrm2 = before - h @ h
+                if not (nrm2 > 0.5 * before):          # DGKS refinement only if needed (PETSc default)
+                    h2 = V[: j + 1] @ w
+                    w2 = w @ w
+                    w = w - V[: j + 1].T @ h2
+                    h = h + h2
+                    nrm2 = w2 - h2 @ h2
                 H[: j + 1, j] = h
-                H[j + 1, j] = np.linalg.norm(w)
+                H[j + 1, j] = np.sqrt(max(nrm2, 0.0))
                 if H[j + 1, j] > 0:
                     V[j + 1] = w / H[j + 1, j]
                 for i in range(j):
