@@ -67,8 +67,15 @@ int knp_create(knp_ctx** out, const knp_mesh_desc* mesh, int device) {
   KNP_TRY(c->d_gam_mv.upload(H.gam_mv));
   KNP_TRY(c->d_minc_ptr.upload(H.minc_ptr));
   KNP_TRY(c->d_minc.upload(H.minc));
-  KNP_TRY(c->d_indptr.upload(H.indptr));
-  KNP_TRY(c->d_indptr_P.upload(H.indptr_P));
+  {
+    std::vector<int32_t> ip(H.indptr), ipP(H.indptr_P);
+    for (int k = 0; k < 4; ++k) {   // padding for the 16-byte TMA slices of the streaming SpMV
+      ip.push_back(H.indptr.back());
+      ipP.push_back(H.indptr_P.back());
+    }
+    KNP_TRY(c->d_indptr.upload(ip));
+    KNP_TRY(c->d_indptr_P.upload(ipP));
+  }
   {
     std::vector<int32_t> blk;
     c->nblk_A = build_rowblocks(H.indptr.data(), H.L.n_rows, blk);

@@ -6,6 +6,7 @@
 //   multi_dot / multi_axpy  K6   classical Gram-Schmidt building blocks: all (j+1) inner products and ||w||^2
 //                                in ONE pass over w and V, reduced in a fixed order (two-stage, no atomics)
 //   range_sum / range_shift K8   nullspace projection x -= (ns.x) ns (KNPEMIx_solver.py:324-333)
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -69,10 +70,12 @@ __global__ void __launch_bounds__(256) spmv_kernel(int n_rows, const int32_t* __
 constexpr int SPMV_CAP = 2048;
 constexpr int SPMV_THREADS = 256;
 constexpr int SPMV_PAD = 8;
+constexpr int SPMV_ROWS = 256;          // max rows per block (multiple of 4: the row-pointer slice is TMA-loaded too)
 
 struct SpmvStage {
   double v[SPMV_CAP + SPMV_PAD];
   int c[SPMV_CAP + SPMV_PAD];
+  int rp[SPMV_ROWS + 8];
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -101,8 +104,9 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
                : "memory");
 }
 
+// blkinfo[blk] = {first row r0 (multiple of 4), number of rows, a4 = 4-aligned first non-zero, staged element count}
 template <int EPI>
-__global__ void __launch_bounds__(SPMV_THREADS) spmv_stream_kernel(int nblk, const int32_t* __restrict__ rowblk,
+__global__ void __launch_bounds__(SPMV_THREADS) spmv_stream_kernel(int nblk, const int4* __restrict__ blkinfo,
                                                                     const int32_t* __restrict__ indptr,
                                                                     const int32_t* __restrict__ indices,
                                                                     const double* __restrict__ vals,
@@ -112,7 +116,7 @@ __global__ void __launch_bounds__(SPMV_THREADS) spmv_stream_kernel(int nblk, con
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SpmvStage* st = reinterpret_cast<SpmvStage*>(smem_raw);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + 2 * sizeof(SpmvStage));
-  __shared__ int s_a4[2], s_ntma[2];
+  __shared__ double rsum[SPMV_ROWS];
   const int tid = threadIdx.x;
   if (tid == 0) {
     mbar_init(&bar[0], 1);
@@ -121,82 +125,124 @@ __global__ void __launch_bounds__(SPMV_THREADS) spmv_stream_kernel(int nblk, con
   }
   __syncthreads();
 
-  auto issue = [&](int blk, int s) {
-    // called by thread 0 only
-    const int r0 = rowblk[blk], r1 = rowblk[blk + 1];
-    const int a = indptr[r0], e = indptr[r1];
-    const int a4 = a & ~3;
-    const int ntma = (e - a4) & ~3;          // multiple of 4 elements -> 16-byte multiples for both arrays
-    s_a4[s] = a4;
-    s_ntma[s] = ntma;
+  auto issue = [&](const int4 bi, int s) {   // thread 0 only: three bulk copies completing on one mbarrier
+    const int ntma = bi.w & ~3;
+    const int nrp = (bi.y + 1 + 3) & ~3;     // row pointers r0 .. r0+nrows, rounded up to 16 bytes (arrays are padded)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    mbar_expect_tx(&bar[s], (uint32_t)ntma * 12u);
+    mbar_expect_tx(&bar[s], (uint32_t)ntma * 12u + (uint32_t)nrp * 4u);
+    tma_load_1d(st[s].rp, indptr + bi.x, (uint32_t)nrp * 4u, &bar[s]);
     if (ntma > 0) {
-      tma_load_1d(st[s].v, vals + a4, (uint32_t)ntma * 8u, &bar[s]);
-      tma_load_1d(st[s].c, indices + a4, (uint32_t)ntma * 4u, &bar[s]);
+      tma_load_1d(st[s].v, vals + bi.z, (uint32_t)ntma * 8u, &bar[s]);
+      tma_load_1d(st[s].c, indices + bi.z, (uint32_t)ntma * 4u, &bar[s]);
     }
   };
 
+  const int stride = gridDim.x;
   int blk = blockIdx.x;
-  if (tid == 0 && blk < nblk) issue(blk, 0);
-  for (int it = 0; blk < nblk; blk += gridDim.x, ++it) {
+  const int4 zero = make_int4(0, 0, 0, 0);
+  int4 cur = blk < nblk ? blkinfo[blk] : zero;
+  int4 nx1 = blk + stride < nblk ? blkinfo[blk + stride] : zero;
+  if (tid == 0 && blk < nblk) issue(cur, 0);
+  for (int it = 0; blk < nblk; blk += stride, ++it) {
     const int s = it & 1;
-    const int nxt = blk + gridDim.x;
-    if (tid == 0 && nxt < nblk) issue(nxt, s ^ 1);
-    const int r0 = rowblk[blk], r1 = rowblk[blk + 1];
-    const int a = indptr[r0], e = indptr[r1];
-    mbar_wait(&bar[s], (uint32_t)((it >> 1) & 1));
-    const int a4 = a & ~3;
-    const int ntma = (e - a4) & ~3;
-    const int n = e - a4;                    // staged elements (the first a - a4 are padding of the previous block)
+    // block descriptors are prefetched two iterations ahead so that neither the producer nor the consumers wait on them
+    const int4 nx2 = blk + 2 * stride < nblk ? blkinfo[blk + 2 * stride] : zero;
+    if (tid == 0 && blk + stride < nblk) issue(nx1, s ^ 1);
+    const int r0 = cur.x, nrows = cur.y, a4 = cur.z, n = cur.w;
+    const int ntma = n & ~3;
     double* sv = st[s].v;
     int* sc = st[s].c;
+    const int* rp = st[s].rp;
+    // epilogue operands of "my" row (thread t <-> row r0 + t): coalesced, issued long before they are needed
+    double eb = 0.0, ed = 0.0, ex = 0.0;
+    if (tid < nrows) {
+      const int r = r0 + tid;
+      if (EPI == EPI_RESID || EPI == EPI_JACOBI) eb = b[r];
+      if (EPI == EPI_JACOBI) {
+        ed = dinv[r];
+        ex = x[r];
+      }
+      if (EPI == EPI_ADD) eb = out[r];
+    }
     // the (< 4) trailing elements that do not fill a 16-byte unit
     if (tid < n - ntma) {
       sv[ntma + tid] = vals[a4 + ntma + tid];
       sc[ntma + tid] = indices[a4 + ntma + tid];
     }
+    mbar_wait(&bar[s], (uint32_t)((it >> 1) & 1));
     __syncthreads();
-    // products, in place; 8 independent gathers per thread
+    // products, in place.  All gathers of a thread are issued before the first one is consumed (the in-place
+    // store would otherwise serialise them through possible shared-memory aliasing): memory-level parallelism 8-9.
+    {
+      constexpr int NI = (SPMV_CAP + SPMV_PAD + SPMV_THREADS - 1) / SPMV_THREADS;
+      double xv[NI];
 #pragma unroll
-    for (int i = 0; i < (SPMV_CAP + SPMV_PAD + SPMV_THREADS - 1) / SPMV_THREADS; ++i) {
-      const int j = tid + i * SPMV_THREADS;
-      if (j < n) sv[j] = sv[j] * __ldg(x + sc[j]);
+      for (int i = 0; i < NI; ++i) {
+        const int j = tid + i * SPMV_THREADS;
+        const int col = j < n ? sc[j] : 0;
+        xv[i] = __ldg(x + col);
+      }
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        const int j = tid + i * SPMV_THREADS;
+        if (j < n) sv[j] *= xv[i];
+      }
     }
     __syncthreads();
-    // one thread per row, fixed summation order
-    for (int r = r0 + tid; r < r1; r += SPMV_THREADS) {
-      const int j0 = indptr[r] - a4, j1 = indptr[r + 1] - a4;
+    // 8 lanes per row, fixed summation order (lane-strided partial sums, then a shuffle tree) -> rsum[]
+    const int sub = tid & 7;
+    for (int i0 = 0; i0 < nrows; i0 += SPMV_THREADS / 8) {
+      const int i = i0 + (tid >> 3);
       double sum = 0.0;
-      for (int j = j0; j < j1; ++j) sum += sv[j];
+      if (i < nrows) {
+        const int j1 = rp[i + 1] - a4;
+        for (int j = rp[i] - a4 + sub; j < j1; j += 8) sum += sv[j];
+      }
+      sum += __shfl_down_sync(0xffffffffu, sum, 4, 8);
+      sum += __shfl_down_sync(0xffffffffu, sum, 2, 8);
+      sum += __shfl_down_sync(0xffffffffu, sum, 1, 8);
+      if (sub == 0 && i < nrows) rsum[i] = sum;
+    }
+    __syncthreads();
+    if (tid < nrows) {
+      const double sum = rsum[tid];
       double res;
       if (EPI == EPI_SET) res = sum;
-      else if (EPI == EPI_RESID) res = b[r] - sum;
-      else if (EPI == EPI_JACOBI) res = x[r] + w * dinv[r] * (b[r] - sum);
-      else res = out[r] + sum;
-      out[r] = res;
+      else if (EPI == EPI_RESID) res = eb - sum;
+      else if (EPI == EPI_JACOBI) res = ex + w * ed * (eb - sum);
+      else res = eb + sum;
+      out[r0 + tid] = res;
     }
     __syncthreads();
+    cur = nx1;
+    nx1 = nx2;
   }
 }
 
-// greedy row blocks: <= SPMV_CAP non-zeros (counted from the 4-aligned start) and <= SPMV_THREADS rows
-int build_rowblocks(const int32_t* indptr, int n_rows, std::vector<int32_t>& blk) {
-  blk.clear();
-  blk.push_back(0);
+// greedy row blocks: first row a multiple of 4, <= SPMV_CAP staged non-zeros (counted from the 4-aligned start),
+// <= SPMV_ROWS rows.  Returns the number of blocks or -1 when a group of 4 rows exceeds the stage capacity.
+int build_rowblocks(const int32_t* indptr, int n_rows, std::vector<int32_t>& info) {
+  info.clear();
   int r0 = 0;
   while (r0 < n_rows) {
     const int a4 = indptr[r0] & ~3;
     int r1 = r0;
-    while (r1 < n_rows && r1 - r0 < SPMV_THREADS && indptr[r1 + 1] - a4 <= SPMV_CAP) ++r1;
-    if (r1 == r0) return -1;   // a single row exceeds the stage capacity: caller falls back to the CSR-vector kernel
-    blk.push_back(r1);
+    while (r1 < n_rows) {
+      const int nxt = r1 + 4 < n_rows ? r1 + 4 : n_rows;
+      if (nxt - r0 > SPMV_ROWS || indptr[nxt] - a4 > SPMV_CAP) break;
+      r1 = nxt;
+    }
+    if (r1 == r0) return -1;
+    info.push_back(r0);
+    info.push_back(r1 - r0);
+    info.push_back(a4);
+    info.push_back(indptr[r1] - a4);
     r0 = r1;
   }
-  return (int)blk.size() - 1;
+  return (int)(info.size() / 4);
 }
 
-int launch_spmv_stream(int nblk, const int32_t* rowblk, const int32_t* indptr, const int32_t* indices, const double* vals,
+int launch_spmv_stream(int nblk, const int32_t* blkinfo, const int32_t* indptr, const int32_t* indices, const double* vals,
                        const double* x, double* out, int epi, const double* b, const double* dinv, double w, cudaStream_t st) {
   if (nblk == 0) return KNP_OK;
   const size_t smem = 2 * sizeof(SpmvStage) + 2 * sizeof(uint64_t);
@@ -209,11 +255,12 @@ int launch_spmv_stream(int nblk, const int32_t* rowblk, const int32_t* indptr, c
     configured = true;
   }
   const int grid = nblk < 148 * 4 ? nblk : 148 * 4;   // persistent: 4 CTAs per SM
+  const int4* bi = reinterpret_cast<const int4*>(blkinfo);
   switch (epi) {
-    case EPI_SET: spmv_stream_kernel<EPI_SET><<<grid, SPMV_THREADS, smem, st>>>(nblk, rowblk, indptr, indices, vals, x, out, b, dinv, w); break;
-    case EPI_RESID: spmv_stream_kernel<EPI_RESID><<<grid, SPMV_THREADS, smem, st>>>(nblk, rowblk, indptr, indices, vals, x, out, b, dinv, w); break;
-    case EPI_JACOBI: spmv_stream_kernel<EPI_JACOBI><<<grid, SPMV_THREADS, smem, st>>>(nblk, rowblk, indptr, indices, vals, x, out, b, dinv, w); break;
-    default: spmv_stream_kernel<EPI_ADD><<<grid, SPMV_THREADS, smem, st>>>(nblk, rowblk, indptr, indices, vals, x, out, b, dinv, w); break;
+    case EPI_SET: spmv_stream_kernel<EPI_SET><<<grid, SPMV_THREADS, smem, st>>>(nblk, bi, indptr, indices, vals, x, out, b, dinv, w); break;
+    case EPI_RESID: spmv_stream_kernel<EPI_RESID><<<grid, SPMV_THREADS, smem, st>>>(nblk, bi, indptr, indices, vals, x, out, b, dinv, w); break;
+    case EPI_JACOBI: spmv_stream_kernel<EPI_JACOBI><<<grid, SPMV_THREADS, smem, st>>>(nblk, bi, indptr, indices, vals, x, out, b, dinv, w); break;
+    default: spmv_stream_kernel<EPI_ADD><<<grid, SPMV_THREADS, smem, st>>>(nblk, bi, indptr, indices, vals, x, out, b, dinv, w); break;
   }
   KNP_LAUNCHED();
   return KNP_OK;
@@ -254,7 +301,11 @@ int launch_spmv(int n_rows, int64_t nnz, const int32_t* indptr, const int32_t* i
 int spmv(const CsrView& M, const double* x, double* out, int epi, const double* b, const double* dinv, double w,
          cudaStream_t st) {
   const bool aligned = (((uintptr_t)M.vals | (uintptr_t)M.indices) & 15u) == 0;
-  if (M.nblk > 0 && M.rowblk && aligned)
+  // the TMA-staged kernel pays off on long-enough rows and enough blocks to fill the persistent grid
+  static const double min_avg = getenv("KNP_SPMV_STREAM_MIN_AVG") ? atof(getenv("KNP_SPMV_STREAM_MIN_AVG")) : 0.0;
+  static const int min_blk = getenv("KNP_SPMV_STREAM_MIN_BLK") ? atoi(getenv("KNP_SPMV_STREAM_MIN_BLK")) : 1;
+  const double avg = M.n_rows > 0 ? (double)M.nnz / M.n_rows : 0.0;
+  if (M.nblk >= min_blk && M.rowblk && aligned && avg >= min_avg)
     return launch_spmv_stream(M.nblk, M.rowblk, M.indptr, M.indices, M.vals, x, out, epi, b, dinv, w, st);
   return launch_spmv(M.n_rows, M.nnz, M.indptr, M.indices, M.vals, x, out, epi, b, dinv, w, st);
 }

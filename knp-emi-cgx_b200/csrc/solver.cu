@@ -35,7 +35,11 @@ static int upload_csr(const CsrHost& h, CsrDev& d) {
   d.n_rows = h.n_rows;
   d.n_cols = h.n_cols;
   d.nnz = h.nnz();
-  KNP_TRY(d.indptr.upload(h.indptr));
+  {
+    std::vector<int32_t> ip(h.indptr);
+    for (int k = 0; k < 4; ++k) ip.push_back(h.indptr.back());   // padding for the 16-byte TMA slices
+    KNP_TRY(d.indptr.upload(ip));
+  }
   KNP_TRY(d.indices.upload(h.indices));
   KNP_TRY(d.vals.upload(h.vals));
   std::vector<int32_t> blk;
