@@ -47,6 +47,10 @@ struct knp_ctx {
   knp::DevBuf<int32_t> d_send_cols;
   knp::DevBuf<double> d_send_buf;
   int64_t n_phi_global = 0;   // global number of potential dofs (nullspace normalisation)
+  std::vector<int32_t> h_recv_cols;   // ghost columns in receive order (host copy)
+  // two-level additive Schwarz coarse space: one constant per (rank, field block)
+  bool cz_on = false;
+  knp::DevBuf<double> cz_sums, cz_einv, cz_partial;
   // timers
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   double last_ms[5] = {0, 0, 0, 0, 0};

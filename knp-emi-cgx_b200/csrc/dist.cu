@@ -146,6 +146,7 @@ int knp_dist_init(knp_ctx* c, int32_t rank, int32_t nranks, const char* unique_i
     KNP_CHECK(recv_cols[i] >= nrows && recv_cols[i] < ncols, "recv column %d is not a ghost column", recv_cols[i]);
     cols[ns + i] = recv_cols[i];
   }
+  c->h_recv_cols.assign(recv_cols, recv_cols + nr);
   KNP_TRY(c->d_send_cols.upload(cols));
   KNP_TRY(c->d_send_buf.alloc((size_t)(ns + nr) + 1));
   return KNP_OK;

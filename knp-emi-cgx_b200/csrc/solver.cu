@@ -49,9 +49,160 @@ static int upload_csr(const CsrHost& h, CsrDev& d) {
   return KNP_OK;
 }
 
+// ---- two-level additive Schwarz coarse space for multi-GPU runs -------------------------------------------------
+// The processor-local AMG drops the couplings to ghost columns, which destroys the near-null constants of the phi
+// blocks (K_w - (C_M/F) M_Gamma): the membrane-capacitor modes would then be left to GMRES alone (thousands of
+// iterations).  One constant per (rank, field block) restores them: z += Z (Z^T P Z)^-1 Z^T r, with Z^T P Z formed
+// from the *global* P (ghost couplings included) and inverted redundantly on every rank (8 nranks x nranks systems).
+constexpr int CZ_BLOCKS = 64;
+
+__global__ void __launch_bounds__(256) cz_partial_kernel(Layout L, const double* __restrict__ r, double* __restrict__ partial) {
+  __shared__ double red[8];
+  const int fb = blockIdx.y;                    // field block 0..7
+  const int s = fb >> 2, f = fb & 3;
+  const int lo = L.row(s, f, 0), n = L.n_own[s];
+  const int per = (n + gridDim.x - 1) / gridDim.x;
+  const int a = blockIdx.x * per, b = min(n, a + per);
+  double acc = 0.0;
+  for (int i = a + threadIdx.x; i < b; i += 256) acc += r[lo + i];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+  if (lane == 0) red[wid] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    partial[fb * gridDim.x + blockIdx.x] = t;
+  }
+}
+__global__ void cz_final_kernel(int nranks, int rank, int nb, const double* __restrict__ partial, double* __restrict__ sums) {
+  // sums[r*8 + fb]: zero except this rank's 8 entries
+  const int t = threadIdx.x;
+  if (t < 8 * nranks) {
+    double v = 0.0;
+    if (t / 8 == rank) {
+      const int fb = t % 8;
+      for (int i = 0; i < nb; ++i) v += partial[fb * nb + i];
+    }
+    sums[t] = v;
+  }
+}
+__global__ void cz_add_kernel(Layout L, int nranks, const double* __restrict__ sums, const double* __restrict__ einv,
+                              double* __restrict__ z) {
+  __shared__ double y[8];
+  if (threadIdx.x < 8) {
+    double t = 0.0;
+    for (int r = 0; r < nranks; ++r) t += einv[threadIdx.x * nranks + r] * sums[r * 8 + threadIdx.x];
+    y[threadIdx.x] = t;
+  }
+  __syncthreads();
+  const int n0 = 4 * L.n_own[0];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L.n_rows; i += gridDim.x * blockDim.x) {
+    const int fb = i < n0 ? i / max(L.n_own[0], 1) : 4 + (i - n0) / max(L.n_own[1], 1);
+    z[i] += y[fb];
+  }
+}
+
+static int coarse_setup(knp_ctx* c, const std::vector<int32_t>& idx, const std::vector<double>& val) {
+  c->cz_on = false;
+  if (c->nranks <= 1) return KNP_OK;
+  const Layout& L = c->T.L;
+  const int n = L.n_rows, nr = c->nranks, np = (int)c->peers.size();
+  std::vector<int32_t> ghost_owner((size_t)(L.n_cols - n), -1);
+  for (int i = 0; i < np; ++i)
+    for (int64_t k = c->recv_ptr[i]; k < c->recv_ptr[i + 1]; ++k) ghost_owner[c->h_recv_cols[k] - n] = c->peers[i];
+  std::vector<double> E((size_t)8 * nr * nr, 0.0);      // E[(r', fb), r] flattened as ((r'*8 + fb) * nr + r)
+  for (int s = 0; s < 2; ++s)
+    for (int f = 0; f < 4; ++f)
+      for (int p = 0; p < L.n_own[s]; ++p) {
+        const int row = L.row(s, f, p);
+        double* e = &E[((size_t)c->rank * 8 + 4 * s + f) * nr];
+        for (int j = c->H.indptr_P[row]; j < c->H.indptr_P[row + 1]; ++j) {
+          const int col = idx[j];
+          const int rj = col < n ? c->rank : ghost_owner[col - n];
+          if (rj < 0) {
+            set_error("coarse space: ghost column %d has no owner in the halo lists", col);
+            return KNP_E_INVALID;
+          }
+          e[rj] += val[j];
+        }
+      }
+  DevBuf<double> dE;
+  KNP_TRY(dE.upload(E));
+  KNP_TRY(allreduce_sum(c, dE.p, (int)E.size(), c->stream));
+  KNP_CUDA(cudaMemcpyAsync(E.data(), dE.p, E.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  KNP_CUDA(cudaStreamSynchronize(c->stream));
+  // per field block: invert the nr x nr matrix, keep this rank's row
+  std::vector<double> einv((size_t)8 * nr, 0.0);
+  for (int fb = 0; fb < 8; ++fb) {
+    std::vector<double> M((size_t)nr * nr), inv((size_t)nr * nr, 0.0);
+    for (int a = 0; a < nr; ++a)
+      for (int b = 0; b < nr; ++b) M[(size_t)a * nr + b] = E[((size_t)a * 8 + fb) * nr + b];
+    for (int a = 0; a < nr; ++a) {
+      bool empty = true;
+      for (int b = 0; b < nr; ++b) empty = empty && M[(size_t)a * nr + b] == 0.0 && M[(size_t)b * nr + a] == 0.0;
+      if (empty) M[(size_t)a * nr + a] = 1.0;      // rank without dofs of this field
+      inv[(size_t)a * nr + a] = 1.0;
+    }
+    for (int k = 0; k < nr; ++k) {                 // Gauss-Jordan with partial pivoting
+      int piv = k;
+      for (int a = k + 1; a < nr; ++a)
+        if (std::fabs(M[(size_t)a * nr + k]) > std::fabs(M[(size_t)piv * nr + k])) piv = a;
+      if (M[(size_t)piv * nr + k] == 0.0) {
+        set_error("coarse space matrix of field block %d is singular", fb);
+        return KNP_E_INVALID;
+      }
+      for (int b = 0; b < nr; ++b) {
+        std::swap(M[(size_t)k * nr + b], M[(size_t)piv * nr + b]);
+        std::swap(inv[(size_t)k * nr + b], inv[(size_t)piv * nr + b]);
+      }
+      const double d = 1.0 / M[(size_t)k * nr + k];
+      for (int b = 0; b < nr; ++b) {
+        M[(size_t)k * nr + b] *= d;
+        inv[(size_t)k * nr + b] *= d;
+      }
+      for (int a = 0; a < nr; ++a) {
+        if (a == k) continue;
+        const double fct = M[(size_t)a * nr + k];
+        for (int b = 0; b < nr; ++b) {
+          M[(size_t)a * nr + b] -= fct * M[(size_t)k * nr + b];
+          inv[(size_t)a * nr + b] -= fct * inv[(size_t)k * nr + b];
+        }
+      }
+    }
+    for (int b = 0; b < nr; ++b) einv[(size_t)fb * nr + b] = inv[(size_t)c->rank * nr + b];
+  }
+  KNP_TRY(c->cz_einv.upload(einv));
+  KNP_TRY(c->cz_sums.alloc((size_t)8 * nr));
+  KNP_TRY(c->cz_partial.alloc((size_t)8 * CZ_BLOCKS));
+  if (8 * nr > 1024) {
+    set_error("coarse space supports at most 128 ranks");
+    return KNP_E_UNSUPPORTED;
+  }
+  c->cz_on = true;
+  return KNP_OK;
+}
+
+static int coarse_apply(knp_ctx* c, const double* r, double* z, cudaStream_t st) {
+  if (!c->cz_on) return KNP_OK;
+  const Layout& L = c->T.L;
+  cz_partial_kernel<<<dim3(CZ_BLOCKS, 8), 256, 0, st>>>(L, r, c->cz_partial.p);
+  KNP_LAUNCHED();
+  cz_final_kernel<<<1, 1024, 0, st>>>(c->nranks, c->rank, CZ_BLOCKS, c->cz_partial.p, c->cz_sums.p);
+  KNP_LAUNCHED();
+  KNP_TRY(allreduce_sum(c, c->cz_sums.p, 8 * c->nranks, st));
+  int grid = (L.n_rows + 255) / 256;
+  if (grid > 148 * 8) grid = 148 * 8;
+  cz_add_kernel<<<grid, 256, 0, st>>>(L, c->nranks, c->cz_sums.p, c->cz_einv.p, z);
+  KNP_LAUNCHED();
+  return KNP_OK;
+}
+
 int pc_setup(knp_ctx* c, const knp_solve_opts* o) {
   const int n = c->T.L.n_rows;
   c->amg.reset();
+  c->cz_on = false;
   c->pc_kind = o->pc;
   if (o->pc == 0) return KNP_OK;
   if (!c->P_assembled) {
@@ -89,6 +240,7 @@ int pc_setup(knp_ctx* c, const knp_solve_opts* o) {
         }
       P0.indptr[i + 1] = (int32_t)P0.indices.size();
     }
+    KNP_TRY(coarse_setup(c, idx, val));
   }
   std::vector<CsrHost> As, Ps, Rs;
   std::vector<double> rhos, cinv;
@@ -153,7 +305,10 @@ __global__ void dinv_mul_kernel(int n, const double* __restrict__ dinv, const do
 
 int pc_apply(knp_ctx* c, const double* r, double* z, cudaStream_t st) {
   const int n = c->T.L.n_rows;
-  if (c->pc_kind == 2 && c->amg) return vcycle(c, 0, r, z, st);
+  if (c->pc_kind == 2 && c->amg) {
+    KNP_TRY(vcycle(c, 0, r, z, st));
+    return coarse_apply(c, r, z, st);
+  }
   if (c->pc_kind == 1) {
     int grid = (n + 255) / 256;
     if (grid > 148 * 16) grid = 148 * 16;

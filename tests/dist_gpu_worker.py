@@ -35,7 +35,10 @@ if p.comm.rank == 0:
     for i in range(3):
         _, _, x, _ = o.step("gmres", lambda v: lu.solve(v), 1e-13, x, first=(i == 0))
     ref = [o.l2_norm(o.c[sd][f] if f < 3 else o.phi[sd], 1 if sd == 0 else 2) for sd in range(2) for f in range(4)]
-    err = max(abs(a - b) / b for a, b in zip(norms, ref))
+    # phi_e (index 7) is ~1e-3 of phi_i: relative to the potential scale, as in tests/test_gpu_parity.py
+    scale = list(ref)
+    scale[7] = max(ref[7], ref[3])
+    err = max(abs(a - b) / sc for a, b, sc in zip(norms, ref, scale))
     print(f"ranks {p.comm.size} iterations {s.iterations} max rel norm err {err:.3e}", flush=True)
     assert err < 1e-8, (norms, ref)
     print("MULTI_GPU_OK", flush=True)
