@@ -56,7 +56,7 @@ int launch_extract_dinv(int n_rows, const int32_t* indptr, const int32_t* indice
                         cudaStream_t st);
 int launch_dense_gemv(int n, const double* Minv, const double* b, double* x, cudaStream_t st);
 // Gram-Schmidt building blocks (deterministic two-stage reductions; no atomics)
-constexpr int RED_BLOCKS = 296;   // 2 x 148 SMs
+constexpr int RED_BLOCKS = 1184;   // 8 x 148 SMs: full occupancy for the streaming reductions
 // out[j] = sum_i V[j*ldv + i] * w[i], j < m ; out[m] = sum_i w[i]^2 ; partial is (m+1) x RED_BLOCKS scratch
 int launch_multi_dot(int n, int m, const double* V, size_t ldv, const double* w, double* partial, double* out,
                      cudaStream_t st);

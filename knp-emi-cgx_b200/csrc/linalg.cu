@@ -67,7 +67,13 @@ __global__ void __launch_bounds__(256) spmv_kernel(int n_rows, const int32_t* __
 // processed.  Every thread then owns SPMV_CAP/256 consecutive-stride elements: the x gathers of a thread are independent
 // (memory-level parallelism 8 instead of 1), products are written back in place, and each row is summed by one thread in
 // a fixed order (bitwise reproducible, no atomics).
-constexpr int SPMV_CAP = 2048;
+#ifndef KNP_SPMV_CAP
+#define KNP_SPMV_CAP 2048
+#endif
+#ifndef KNP_SPMV_CTAS
+#define KNP_SPMV_CTAS 4
+#endif
+constexpr int SPMV_CAP = KNP_SPMV_CAP;
 constexpr int SPMV_THREADS = 256;
 constexpr int SPMV_PAD = 8;
 constexpr int SPMV_ROWS = 256;          // max rows per block (multiple of 4: the row-pointer slice is TMA-loaded too)
@@ -254,7 +260,7 @@ int launch_spmv_stream(int nblk, const int32_t* blkinfo, const int32_t* indptr, 
     KNP_CUDA(cudaFuncSetAttribute(spmv_stream_kernel<EPI_ADD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  const int grid = nblk < 148 * 4 ? nblk : 148 * 4;   // persistent: 4 CTAs per SM
+  const int grid = nblk < 148 * KNP_SPMV_CTAS ? nblk : 148 * KNP_SPMV_CTAS;   // persistent CTAs
   const int4* bi = reinterpret_cast<const int4*>(blkinfo);
   switch (epi) {
     case EPI_SET: spmv_stream_kernel<EPI_SET><<<grid, SPMV_THREADS, smem, st>>>(nblk, bi, indptr, indices, vals, x, out, b, dinv, w); break;
