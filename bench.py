@@ -163,12 +163,17 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and os.environ.get("OMP_NUM_THREADS", "1") == "1":
+        # torchrun pins OMP to 1 thread; the host-side setup (topology, AMG hierarchy) is OpenMP code
+        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 8) // world))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"        # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     # weak scaling: cells per GPU fixed -> N grows with sqrt(world)
     n = args.size if world == 1 else int(round(args.size * math.sqrt(world) / 8)) * 8
@@ -267,7 +272,7 @@ def run_ours(args):
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")      # dram__bytes_read+write per launch from the ncu --set full capture
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(f"spmv_stream_kernel<0>@N={n}")
+        traffic = json.load(open(tpath)).get(f"spmv_stream_kernel<0>@N={n}") if world == 1 else None
     roof = {"bound": "hbm", "kernel": "spmv_stream_kernel<EPI_SET> (y = A x, plain CSR, TMA-staged)", "achieved": B_spmv / t_spmv / 1e6,
             "peak": peak, "unit": "GB/s", "frac": B_spmv / t_spmv / 1e6 / peak, "traffic": traffic, "peak_source": peak_src,
             "algorithmic_bytes": B_spmv, "ms_per_launch": t_spmv, "share_of_step": share_spmv}
