@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(ROWS_BLOCK) rows_kernel(DevTopo T, KParams P, 
                                                           int stride, int group, int stage_len, int nb0) {
   constexpr int NV = D + 1;
   constexpr int NS = D * (D + 1) / 2;
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   // blocks [0, nb0) serve the intracellular dofs, the rest the extracellular ones, so that the rows a warp
@@ -312,6 +312,10 @@ __global__ void __launch_bounds__(ROWS_BLOCK) rows_kernel(DevTopo T, KParams P, 
     double* a_g1 = acc + 6 * deg + 3 * gdeg;
     const int self = T.self_slot[w];
     const int nodeoff = s ? T.L.n_loc[0] : 0;
+    // column of (s, k, q): owned dofs are contiguous per field; ghosts live in the tail of the column layout
+    const int n_own_s = T.L.n_own[s], n_gh_s = T.L.n_gh[s];
+    const double* __restrict__ u_own = u + T.L.rowbase[s];
+    const double* __restrict__ u_gh = u + T.L.n_rows + T.L.gbase[s] - n_own_s;
     double bk[3] = {0.0, 0.0, 0.0}, bp = 0.0;
     double cphi[3], cpp[3];
 #pragma unroll
@@ -334,8 +338,13 @@ __global__ void __launch_bounds__(ROWS_BLOCK) rows_kernel(DevTopo T, KParams P, 
         const int q = T.adj_idx[a0 + sl[b]];
 #pragma unroll
         for (int i = 0; i < D; ++i) x[b][i] = T.node_x[(size_t)(nodeoff + q) * D + i];
+        if (q < n_own_s) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) c[k][b] = u[T.L.col(s, k, q)];
+          for (int k = 0; k < 3; ++k) c[k][b] = u_own[k * n_own_s + q];
+        } else {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) c[k][b] = u_gh[k * n_gh_s + q];
+        }
       }
       CellGeom<D> G;
       cell_geometry(x, G);
@@ -346,7 +355,7 @@ __global__ void __launch_bounds__(ROWS_BLOCK) rows_kernel(DevTopo T, KParams P, 
 #pragma unroll
         for (int b = 0; b < NV; ++b) t += c[k][b];
         csum[k] = t;
-        cbar[k] = t / NV;
+        cbar[k] = t * (1.0 / NV);
       }
       const double mv = G.vol * mfac;
       // gradient of this node's own basis function (runtime local index la -> register select)
@@ -484,7 +493,21 @@ __global__ void __launch_bounds__(ROWS_BLOCK) rows_kernel(DevTopo T, KParams P, 
       }
       const int total = __reduce_max_sync(0xffffffffu, mine ? rs + len - base : 0);
       __syncwarp();
-      for (int q = lane; q < total; q += 32) vals[(size_t)base + q] = stg[q];
+      // coalesced copy-out, 128-bit where the global address allows it (the strip itself is 16-byte aligned)
+      {
+        const int head = base & 1;                      // vals + base is 16-byte aligned iff base is even
+        if (head && lane == 0 && total > 0) vals[(size_t)base] = stg[0];
+        const int npair = (total - head) >> 1;
+        if (head == 0) {
+          const double2* s2 = reinterpret_cast<const double2*>(stg);
+          double2* g2 = reinterpret_cast<double2*>(vals + (size_t)base);
+          for (int q = lane; q < npair; q += 32) g2[q] = s2[q];
+        } else {
+          double2* g2 = reinterpret_cast<double2*>(vals + (size_t)base + 1);
+          for (int q = lane; q < npair; q += 32) g2[q] = make_double2(stg[2 * q + 1], stg[2 * q + 2]);
+        }
+        if (((total - head) & 1) && lane == 0) vals[(size_t)base + total - 1] = stg[total - 1];
+      }
       __syncwarp();
     }
   }
@@ -611,7 +634,7 @@ void rows_config(int max_deg, int max_gdeg, int mode, int& block, int& group, in
   while (group > 1 && acc + (size_t)(block / 32) * group * maxrow * 8 > budget) group >>= 1;
   if (const char* e = getenv("KNP_ROWS_BLOCK")) block = atoi(e);
   if (const char* e = getenv("KNP_ROWS_GROUP")) group = atoi(e);
-  stage_len = group * maxrow;
+  stage_len = (group * maxrow + 1) & ~1;   // even: every warp's strip stays 16-byte aligned
   smem = (size_t)block * stride * 8 + (size_t)(block / 32) * stage_len * 8;
 }
 
