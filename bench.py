@@ -86,12 +86,12 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------------------------- CPU arm
 def cpu_oracle_run(n_sample, cells_per_dim, warmup, steps, n_full_rows=None):
-    """Times the CPU oracle (numpy/scipy restatement of the reference path + the same SA-AMG/GMRES algorithm) on a
+    """Times the CPU oracle (numpy/scipy restatement of the reference path + the same GMRES + Schur/SA-AMG algorithm) on a
     bounded sample of the workload: same tissue-block generator at a smaller N, same step indices."""
     import cgx_b200 as kb
     from oracle.fixtures import from_arrays
     from oracle.knpemi import KNPEMIOracle, OracleParams
-    from oracle.amg import SAAMG
+    from oracle.amg import SchurPC
     m = kb.mesh.cell_array_mesh(2, n_sample, cells_per_dim)
     om = from_arrays(2, m.x, m.cells, m.cell_tags, m.intra_tags)
     it = tuple(m.intra_tags)
@@ -104,7 +104,7 @@ def cpu_oracle_run(n_sample, cells_per_dim, warmup, steps, n_full_rows=None):
     dphi = 0.005 * np.cos(2 * np.pi * X[:, 0])
     o.phi_m += dphi
     o.phi[0] += dphi
-    amg = SAAMG(o.assemble_P())
+    amg = SchurPC(o)
     x = o.pack()
     t_asm, t_step, its = [], [], []
     for i in range(warmup + steps):
@@ -290,7 +290,7 @@ def run_ours(args):
         r = cpu_oracle_run(args.cpu_sample_n, 8, args.warmup, min(args.steps, 2))
         scale = ctx.n_rows / r["rows"]
         cpu = {"value": r["ms_sample"] * scale, "unit": "ms", "cores": 1, "kind": "port",
-               "sample": f"CPU oracle (numpy/scipy restatement of the DOLFINx/PETSc path, same GMRES+SA-AMG algorithm) on the same "
+               "sample": f"CPU oracle (numpy/scipy restatement of the DOLFINx/PETSc path, same GMRES + Schur/SA-AMG algorithm) on the same "
                          f"generator at N={args.cpu_sample_n} ({r['rows']} rows, iterations {r['iterations']}), steps {args.warmup + 1}.."
                          f"{args.warmup + min(args.steps, 2)}: {r['ms_sample']:.0f} ms/step (assembly {r['assembly_ms_sample']:.0f} ms), "
                          f"scaled x{scale:.1f} by DOFs"}
@@ -299,7 +299,7 @@ def run_ours(args):
                 "ms_per_step": ms, "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
                 "config": {"workload": f"BASELINE C3: synthetic 2D tissue block N={n} ({'x'.join(['8'] * 2)} cells), Na/K/Cl + HH+ATP+KCC2, "
-                                       f"GMRES({args.restart})+SA-AMG rtol 1e-9, ICs perturbed as SURVEY 8(d)",
+                                       f"GMRES({args.restart}) + charge-conservation Schur PC (SA-AMG blocks) rtol 1e-9, ICs perturbed as SURVEY 8(d)",
                            "dofs": dofs_global, "nnz": nnz_global, "cells": int(p.global_mesh_info["n_cells"]),
                            "iterations_per_step": its, "timed_step_indices": [args.warmup + 1, args.warmup + args.steps],
                            "l2_policy": "inputs (A: %.1f GB) larger than L2" % (12 * ctx.nnz / 1e9), "setup_s": t_setup},

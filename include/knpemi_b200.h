@@ -103,7 +103,8 @@ typedef struct {
   double rtol;                  /* ksp_rtol, preconditioned residual norm relative to ||B b|| */
   int32_t max_it;               /* ksp_max_it (5000) */
   int32_t restart;              /* GMRES restart (PETSc default 30) */
-  int32_t pc;                   /* 0 none, 1 Jacobi(P), 2 smoothed-aggregation AMG V-cycle on P */
+  int32_t pc;                   /* 0 none, 1 Jacobi(P), 2 smoothed-aggregation AMG V-cycle on P,
+                                   3 charge-conservation Schur preconditioner (AMG on the ion and potential blocks) */
   int32_t project_nullspace;    /* remove the phi-constant nullspace after each PC apply (:324-333) */
   int32_t zero_mean_solution;   /* direct-solver convention: return the solution with ns^T x = 0 */
   int32_t refine;               /* "direct" mode: keep restarting until the true residual stagnates `refine` times */
@@ -186,6 +187,9 @@ int knp_copy(knp_ctx* ctx, void* dst, const void* src, int64_t nbytes, int32_t k
 
 /* AMG hierarchy inspection for level-by-level parity tests */
 int knp_amg_num_levels(const knp_ctx* ctx);
+/* levels of hierarchy `part`: pc 2 -> part 0 = the hierarchy on P; pc 3 -> part 0 = ion blocks, part 1 = potential blocks
+   (levels are numbered part 0 first) */
+int knp_amg_part_levels(const knp_ctx* ctx, int32_t part);
 int knp_amg_level_sizes(const knp_ctx* ctx, int32_t level, int64_t* n, int64_t* nnz);
 int knp_amg_level_host(const knp_ctx* ctx, int32_t level, int32_t* indptr, int32_t* indices, double* vals);
 

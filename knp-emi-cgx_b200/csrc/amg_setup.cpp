@@ -4,7 +4,7 @@
 // which is assembled ONCE (reassemble_P = False; KNPEMIx_solver.py:33-34,118-135,269-273,358-362,386).
 // hypre is a third-party library that is not vendored in the reference; this is our own algorithm:
 // MIS(2) aggregation with deterministic hashed priorities, constant tentative prolongator smoothed by one
-// damped-Jacobi step, Galerkin coarse operators, dense inverse on the coarsest level.  The V-cycle itself
+// damped-Jacobi step (with the filtered matrix on dense Galerkin levels), Galerkin coarse operators, dense inverse on the coarsest level.  The V-cycle itself
 // (all per-iteration work) runs on the GPU (solver.cu).  oracle/amg.py restates the same algorithm in
 // numpy/scipy and tests compare the two hierarchies level by level.
 #include <algorithm>
@@ -261,12 +261,18 @@ int amg_setup_host(const CsrHost& A0, double theta, int coarse_size, int max_lev
   while (As.back().n_rows > coarse_size && (int)As.size() < max_levels) {
     const CsrHost& A = As.back();
     const int n = A.n_rows;
+    // strength threshold: halved until the strength graph has at least 3 edges per row on average -- Galerkin
+    // operators of 3D meshes spread their weight over many small entries and would otherwise coarsen 2x per level
     Graph S;
-    strength_graph(A, theta, S);
+    double theta_l = theta;
+    for (int attempt = 0; attempt < 4; ++attempt, theta_l *= 0.5) {
+      strength_graph(A, theta_l, S);
+      if ((double)S.idx.size() >= 3.0 * n) break;
+    }
     std::vector<int32_t> agg;
     const int nagg = mis2_aggregate(S, agg);
     if (nagg >= 0.8 * n) break;
-    // Gershgorin bound on rho(D^-1 A) and D^-1
+    // Gershgorin bound on rho(D^-1 A) (used by the Jacobi smoother of the V-cycle) and D^-1
     std::vector<double> dinv(n);
     double rho = 0.0;
 #pragma omp parallel for schedule(static) reduction(max : rho)
@@ -279,56 +285,64 @@ int amg_setup_host(const CsrHost& A0, double theta, int coarse_size, int max_lev
       dinv[i] = 1.0 / d;
       rho = std::max(rho, std::fabs(dinv[i]) * s);
     }
-    // P = T - (omega/rho) D^-1 A T, T(i, agg[i]) = 1
-    CsrHost T;
-    T.n_rows = n;
-    T.n_cols = nagg;
-    T.indptr.resize(n + 1);
-    T.indices.resize(n);
-    T.vals.assign(n, 1.0);
-    for (int i = 0; i <= n; ++i) T.indptr[i] = i;
-    for (int i = 0; i < n; ++i) T.indices[i] = agg[i];
-    CsrHost AT;
-    spgemm(A, T, AT);
+    // Prolongator smoothing with the FILTERED matrix A_F (strong off-diagonals only, weak ones lumped into the
+    // diagonal so that row sums are kept): P = T - (omega/rho_F) D^-1 A_F T, T(i, agg[i]) = 1.  Without the filter the
+    // Galerkin operators of 3D meshes fill in (hundreds of entries per row on level 2) and coarsening stalls.
+    // The filter is on for the finest level (mesh edges with vanishing stiffness) and for operators denser than 32
+    // entries per row (the Galerkin levels of 3D meshes); on sparse coarse levels the unfiltered smoother gives the
+    // better prolongator (2D: 40 instead of 49 GMRES iterations at N = 512).
+    const bool filtered = As.size() == 1 || (double)A.nnz() > 32.0 * n;
+    std::vector<std::vector<std::pair<int32_t, double>>> prow(n);
+    double rhoF = 0.0;
+#pragma omp parallel for schedule(dynamic, 1024) reduction(max : rhoF)
+    for (int i = 0; i < n; ++i) {
+      auto& row = prow[i];
+      double diagF = 0.0, sabs = 0.0;
+      int sp = S.ptr[i];
+      const int se = S.ptr[i + 1];
+      for (int j = A.indptr[i]; j < A.indptr[i + 1]; ++j) {
+        const int c = A.indices[j];
+        const double v = A.vals[j];
+        while (sp < se && S.idx[sp] < c) ++sp;
+        const bool strong = !filtered || (sp < se && S.idx[sp] == c);
+        if (c == i || !strong) {
+          diagF += v;
+        } else {
+          row.emplace_back(agg[c], v);
+          sabs += std::fabs(v);
+        }
+      }
+      row.emplace_back(agg[i], diagF);
+      rhoF = std::max(rhoF, std::fabs(dinv[i]) * (std::fabs(diagF) + sabs));
+      std::sort(row.begin(), row.end(), [](const std::pair<int32_t, double>& a, const std::pair<int32_t, double>& b) {
+        return a.first < b.first;
+      });
+      size_t w = 0;
+      for (size_t r = 0; r < row.size(); ++r) {
+        if (w > 0 && row[w - 1].first == row[r].first) row[w - 1].second += row[r].second;
+        else row[w++] = row[r];
+      }
+      row.resize(w);
+    }
     CsrHost P;
     P.n_rows = n;
     P.n_cols = nagg;
     P.indptr.assign(n + 1, 0);
-    std::vector<int32_t> plen(n);
-#pragma omp parallel for schedule(static)
-    for (int i = 0; i < n; ++i) {
-      bool has = false;
-      for (int j = AT.indptr[i]; j < AT.indptr[i + 1]; ++j) has |= (AT.indices[j] == agg[i]);
-      plen[i] = AT.indptr[i + 1] - AT.indptr[i] + (has ? 0 : 1);
-    }
-    for (int i = 0; i < n; ++i) P.indptr[i + 1] = P.indptr[i] + plen[i];
+    for (int i = 0; i < n; ++i) P.indptr[i + 1] = P.indptr[i] + (int32_t)prow[i].size();
     P.indices.resize(P.indptr[n]);
     P.vals.resize(P.indptr[n]);
-    const double sc = omega / rho;
+    const double sc = omega / rhoF;
 #pragma omp parallel for schedule(static)
     for (int i = 0; i < n; ++i) {
       int pos = P.indptr[i];
-      bool placed = false;
-      for (int j = AT.indptr[i]; j < AT.indptr[i + 1]; ++j) {
-        const int c = AT.indices[j];
-        if (!placed && c > agg[i]) {
-          P.indices[pos] = agg[i];
-          P.vals[pos++] = 1.0;
-          placed = true;
-        }
-        double v = -(sc * dinv[i]) * AT.vals[j];
-        if (c == agg[i]) {
-          v = 1.0 + v;
-          placed = true;
-        }
-        P.indices[pos] = c;
+      for (const auto& e : prow[i]) {
+        double v = -(sc * dinv[i]) * e.second;
+        if (e.first == agg[i]) v += 1.0;
+        P.indices[pos] = e.first;
         P.vals[pos++] = v;
       }
-      if (!placed) {
-        P.indices[pos] = agg[i];
-        P.vals[pos++] = 1.0;
-      }
     }
+    std::vector<std::vector<std::pair<int32_t, double>>>().swap(prow);
     CsrHost R, AP, Ac;
     transpose(P, R);
     spgemm(A, P, AP);

@@ -1,4 +1,5 @@
 // extern "C" entry points of libknpemi_b200.so (see include/knpemi_b200.h for the reference call sites).
+#include <algorithm>
 #include <cmath>
 #include <dlfcn.h>
 #include "context.cuh"
@@ -58,6 +59,7 @@ int knp_create(knp_ctx** out, const knp_mesh_desc* mesh, int device) {
   KNP_TRY(c->d_inc_slots.upload(H.inc_slots));
   KNP_TRY(c->d_self_slot.upload(H.self_slot));
   KNP_TRY(c->d_mv_of_node.upload(H.mv_of_node));
+  KNP_TRY(c->d_gpre.upload(H.gpre));
   KNP_TRY(c->d_mv_node0.upload(H.mv_node[0]));
   KNP_TRY(c->d_mv_node1.upload(H.mv_node[1]));
   KNP_TRY(c->d_mf_mv.upload(H.mf_mv));
@@ -120,6 +122,8 @@ int knp_create(knp_ctx** out, const knp_mesh_desc* mesh, int device) {
   T.indptr_P = c->d_indptr_P.p;
   T.qb = c->d_qb.p;
   T.qw = c->d_qw.p;
+  T.gpre = c->d_gpre.p;
+  T.max_inc = H.max_inc;
   // CSR column indices on the device
   KNP_TRY(c->d_indices.alloc(H.nnz));
   KNP_TRY(c->d_indices_P.alloc(H.nnz_P));
@@ -133,7 +137,6 @@ int knp_create(knp_ctx** out, const knp_mesh_desc* mesh, int device) {
   KNP_TRY(c->b.alloc(T.L.n_rows));
   KNP_TRY(c->fe.alloc((size_t)facet_ncomp(H.gdim) * (T.n_mf > 0 ? T.n_mf : 1)));
   KNP_CUDA(cudaMemsetAsync(c->u.p, 0, (size_t)T.L.n_cols * sizeof(double), c->stream));
-  c->rows_stride = rows_smem_stride(H.max_deg, H.max_gdeg);
   KNP_TRY(c->fpartial.alloc(1024));
   KNP_TRY(c->fout.alloc(8));
   KNP_TRY(c->ftags.alloc(4096));
@@ -505,21 +508,42 @@ int knp_copy(knp_ctx* c, void* dst, const void* src, int64_t nbytes, int32_t kin
   return KNP_OK;
 }
 
-int knp_amg_num_levels(const knp_ctx* c) { return (c && c->amg) ? (int)c->amg->hostA.size() : 0; }
+// Hierarchy inspection.  Levels are numbered over the hierarchies in use: pc kind 2 has one (on P); pc kind 3 has the
+// ion-block hierarchy first and the potential-block hierarchy after it (knp_amg_part_levels tells where it starts).
+static const CsrHost* amg_level(const knp_ctx* c, int level) {
+  if (!c || level < 0) return nullptr;
+  const Amg* parts[3] = {c->amg.get(), c->amg_c.get(), c->amg_p.get()};
+  for (const Amg* a : parts) {
+    if (!a) continue;
+    if (level < (int)a->hostA.size()) return &a->hostA[level];
+    level -= (int)a->hostA.size();
+  }
+  return nullptr;
+}
+
+int knp_amg_part_levels(const knp_ctx* c, int32_t part) {
+  if (!c) return 0;
+  if (c->amg) return part == 0 ? (int)c->amg->hostA.size() : 0;
+  const Amg* a = part == 0 ? c->amg_c.get() : (part == 1 ? c->amg_p.get() : nullptr);
+  return a ? (int)a->hostA.size() : 0;
+}
+
+int knp_amg_num_levels(const knp_ctx* c) { return knp_amg_part_levels(c, 0) + knp_amg_part_levels(c, 1); }
 
 int knp_amg_level_sizes(const knp_ctx* c, int32_t level, int64_t* n, int64_t* nnz) {
-  KNP_CHECK(c && c->amg && level >= 0 && level < (int)c->amg->hostA.size(), "no such AMG level");
-  if (n) *n = c->amg->hostA[level].n_rows;
-  if (nnz) *nnz = c->amg->hostA[level].nnz();
+  const CsrHost* A = amg_level(c, level);
+  KNP_CHECK(A, "no such AMG level");
+  if (n) *n = A->n_rows;
+  if (nnz) *nnz = A->nnz();
   return KNP_OK;
 }
 
 int knp_amg_level_host(const knp_ctx* c, int32_t level, int32_t* indptr, int32_t* indices, double* vals) {
-  KNP_CHECK(c && c->amg && level >= 0 && level < (int)c->amg->hostA.size(), "no such AMG level");
-  const CsrHost& A = c->amg->hostA[level];
-  if (indptr) memcpy(indptr, A.indptr.data(), A.indptr.size() * sizeof(int32_t));
-  if (indices) memcpy(indices, A.indices.data(), A.indices.size() * sizeof(int32_t));
-  if (vals) memcpy(vals, A.vals.data(), A.vals.size() * sizeof(double));
+  const CsrHost* A = amg_level(c, level);
+  KNP_CHECK(A, "no such AMG level");
+  if (indptr) memcpy(indptr, A->indptr.data(), A->indptr.size() * sizeof(int32_t));
+  if (indices) memcpy(indices, A->indices.data(), A->indices.size() * sizeof(int32_t));
+  if (vals) memcpy(vals, A->vals.data(), A->vals.size() * sizeof(double));
   return KNP_OK;
 }
 

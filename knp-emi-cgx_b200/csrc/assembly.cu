@@ -5,16 +5,17 @@
 //   facet_kernel   K3  membrane-facet element tensors: alpha_k, Nernst potentials, channel currents at
 //                      the facet quadrature points (dS terms of KNPEMIx_problem.py:594-642 with the
 //                      IonicModel._eval family), written to a facet-major SoA staging buffer
-//   rows_kernel    K1/K2  one thread per restricted dof ("node"): loops over its incident cells in a
-//                      fixed order, recomputes the P1 element row from the vertex coordinates, accumulates
-//                      per-adjacency-slot values in a private shared-memory strip (no atomics), adds the
-//                      membrane-facet rows, and then each warp streams the finished CSR rows out
+//   rows_kernel    K1/K2  one CTA per tile of restricted dofs ("nodes"), one thread per (node, adjacency slot):
+//                      neighbour data staged once in shared memory, the P1 element rows recomputed from the
+//                      coordinates per (node, cell), fixed-order accumulation in registers (no atomics), membrane
+//                      facet rows added, finished CSR rows streamed out through a staging strip
 //                      (every A value and b entry is written exactly once -> bitwise reproducible).
 //   csr_indices_kernel   column indices of A / P from the node adjacency (setup)
 //
 // Design note: all ten (d+1)x(d+1) cell blocks of KNPEMIx_problem.py:598-605,633-634 are linear
 // combinations of M^T, K^T and cbar_k K^T, and each block row shares the node's adjacency list, so the
 // "cell -> nnz map" collapses to one byte per (node, cell, local vertex): the adjacency slot.
+#include <algorithm>
 #include <cstdlib>
 #include "common.cuh"
 #include "kernels.cuh"
@@ -277,240 +278,319 @@ __device__ __forceinline__ void cell_geometry(const double (&x)[4][3], CellGeom<
 }
 
 // MODE 0: system matrix A and right-hand side b.   MODE 1: block-Jacobi preconditioner matrix P.
+//
+// One CTA owns a TILE of consecutive owned dofs ("nodes") of one subdomain.  A node is served by a group of G lanes
+// (G = power of two >= the largest vertex degree): lane e of the group owns adjacency slot e, i.e. one column position
+// of all ten block rows of that node, and (on membrane nodes) gamma slot e.
+//   phase 1  gather: coordinates and concentrations of the lane's neighbour into shared memory (one gather per
+//            (node, slot), all independent -> memory-level parallelism)
+//   phase 2a one thread per (node, incident cell): P1 geometry from the staged coordinates, the cell's stiffness row
+//            of that node, mass weight and cell-mean concentrations -> shared memory
+//   phase 2b every lane walks its node's incident cells in ascending order (fixed order, no atomics -> bitwise
+//            reproducible), picks the cells that contain its slot (byte-wise SIMD compare on the packed slots) and
+//            accumulates mass, stiffness and cbar_k-weighted stiffness in registers; membrane nodes add the facet
+//            tensors of facet_kernel the same way
+//   phase 3  all ten block rows are formed from the five accumulators and dropped at their CSR-relative offsets of a
+//            staging strip; the tile's rows of one field are ONE contiguous span of the CSR value array, which an
+//            elected thread hands to the TMA engine (cp.async.bulk shared -> global), so the 8 B/nnz output stream
+//            never passes through registers again; b_k = sum_e m_e c_k(e) is a fixed-order segmented sum.
+// Every A value and b entry is written exactly once; index traffic is 1 byte per (node, cell, vertex).
+constexpr int ROWS_THREADS = 256;
+constexpr int ROWS_MIN_CTAS = 4;
+
+struct RowsSmem {       // computed on the host
+  int tile;             // nodes per CTA = ROWS_THREADS / G
+  int lgG, lgI;         // log2 of the lanes per node and of the incidence slots per node
+  int off_res, off_packed;
+  int off_prod;         // products m_e c_k(e) for the right-hand side (inside the staging alias, after the rows)
+  int off_rs;           // CSR row starts of the tile (not aliased)
+  int total;
+};
+
+struct RowCoef {        // constants of the forms, folded on the host (KNPEMIx_problem.py:598-610,633-642)
+  double dtD[3];        // dt D_k
+  double cphi[3];       // dt D_k z_k / psi
+  double cpp[3];        // dt D_k z_k^2 / psi
+  double ck[3];         // dt z_k D_k
+  double cmz[3];        // C_M / (F z_k)
+  double cf;            // C_M / F
+};
+
+__device__ __forceinline__ void bulk_store(double* gdst, const double* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+               "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+               : "memory");
+}
+
 template <int D, int MODE>
-__global__ void __launch_bounds__(ROWS_BLOCK) rows_kernel(DevTopo T, KParams P, const double* __restrict__ u,
-                                                          const double* __restrict__ fe,
-                                                          double* __restrict__ vals, double* __restrict__ bvec,
-                                                          int stride, int group, int stage_len, int nb0) {
+__global__ void __launch_bounds__(ROWS_THREADS, ROWS_MIN_CTAS) rows_kernel(DevTopo T, RowCoef C, const double* __restrict__ u,
+                                                               const double* __restrict__ fe,
+                                                               double* __restrict__ vals, double* __restrict__ bvec,
+                                                               RowsSmem S, int ntile0) {
   constexpr int NV = D + 1;
   constexpr int NS = D * (D + 1) / 2;
-  extern __shared__ __align__(16) double sm[];
-  const int tid = threadIdx.x;
-  const int lane = tid & 31;
-  // blocks [0, nb0) serve the intracellular dofs, the rest the extracellular ones, so that the rows a warp
-  // produces for one field are one contiguous CSR span
-  const int s = blockIdx.x >= nb0 ? 1 : 0;
-  const int p = (blockIdx.x - (s ? nb0 : 0)) * blockDim.x + tid;
-  const bool active = p < T.L.n_own[s];
-  const int w = (s ? T.L.n_own[0] : 0) + p;
-  double* acc = sm + (size_t)tid * stride;
-  double* stg = sm + (size_t)blockDim.x * stride + (size_t)(tid >> 5) * stage_len;
+  constexpr int NB = D + 3;                 // doubles per staged neighbour: coordinates + 3 concentrations
+  constexpr int NR = NV + 4;                // doubles per (node, cell) result: stiffness row, mass weight, cbar[3]
+  constexpr uint32_t VMASK = NV == 4 ? 0xFFFFFFFFu : 0x00FFFFFFu;
+  constexpr uint32_t FMASK = D == 3 ? 0x00FFFFFFu : 0x0000FFFFu;
+  extern __shared__ __align__(16) unsigned char smraw[];
+  double* nbr = reinterpret_cast<double*>(smraw);
+  double* stg = nbr;                                             // alias: neighbours and cell results are dead by phase 3
+  double* res = reinterpret_cast<double*>(smraw + S.off_res);
+  uint32_t* packed = reinterpret_cast<uint32_t*>(smraw + S.off_packed);
+  double* prod = reinterpret_cast<double*>(smraw + S.off_prod);
+  int* rstart = reinterpret_cast<int*>(smraw + S.off_rs);        // [4][tile + 1] CSR row starts of the tile's rows
 
-  int deg = 0, gdeg = 0, g = -1;
-  if (active) {
+  const int tid = threadIdx.x;
+  const int lgG = S.lgG, lgI = S.lgI, GI = 1 << lgI;
+  const int tile = S.tile;
+  const int s = blockIdx.x >= ntile0 ? 1 : 0;
+  const int p0 = (blockIdx.x - (s ? ntile0 : 0)) * tile;
+  const int n_own_s = T.L.n_own[s];
+  const int nt = min(tile, n_own_s - p0);
+  const int w0 = (s ? T.L.n_own[0] : 0) + p0;
+  const int nodeoff = s ? T.L.n_loc[0] : 0;
+  const int* __restrict__ iptr = MODE == 0 ? T.indptr : T.indptr_P;
+
+  const int lw = tid >> lgG, e = tid & ((1 << lgG) - 1);
+  const bool node_ok = lw < nt;
+  int deg = 0, gdeg = 0, self = -1, g = -1, ninc = 0;
+  if (node_ok) {
+    const int w = w0 + lw;
     const int a0 = T.adj_ptr[w];
     deg = T.adj_ptr[w + 1] - a0;
+    self = T.self_slot[w];
     g = T.mv_of_node[w];
-    gdeg = g >= 0 ? T.gam_ptr[g + 1] - T.gam_ptr[g] : 0;
-    const int nacc = 6 * deg + 4 * gdeg;
-    for (int i = 0; i < nacc; ++i) acc[i] = 0.0;
-    double* a_m = acc;
-    double* a_kk = acc + deg;
-    double* a_kphi = acc + 2 * deg;      // [3][deg]
-    double* a_pp = acc + 5 * deg;
-    double* a_ga = acc + 6 * deg;        // [3][gdeg]
-    double* a_g1 = acc + 6 * deg + 3 * gdeg;
-    const int self = T.self_slot[w];
-    const int nodeoff = s ? T.L.n_loc[0] : 0;
-    // column of (s, k, q): owned dofs are contiguous per field; ghosts live in the tail of the column layout
-    const int n_own_s = T.L.n_own[s], n_gh_s = T.L.n_gh[s];
-    const double* __restrict__ u_own = u + T.L.rowbase[s];
-    const double* __restrict__ u_gh = u + T.L.n_rows + T.L.gbase[s] - n_own_s;
-    double bk[3] = {0.0, 0.0, 0.0}, bp = 0.0;
-    double cphi[3], cpp[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      cphi[k] = P.dt * P.D[k] * P.z[k] / P.psi;
-      cpp[k] = P.dt * P.D[k] * P.z[k] * P.z[k] / P.psi;
+    ninc = T.inc_ptr[w + 1] - T.inc_ptr[w];
+    if (MODE == 0) gdeg = T.gpre[w + 1] - T.gpre[w];
+    if (e < 4) {
+      rstart[e * (tile + 1) + lw] = iptr[T.L.row(s, e, p0 + lw)];
+      if (lw == nt - 1) rstart[e * (tile + 1) + nt] = iptr[T.L.row(s, e, p0 + nt)];
     }
-    const double mfac = 1.0 / ((D + 1) * (D + 2));
-    // ---- cell (dx) terms: KNPEMIx_problem.py:598,600,603,605,633-634 ----
-    const int i1 = T.inc_ptr[w + 1];
-    for (int inc = T.inc_ptr[w]; inc < i1; ++inc) {
-      const uint32_t packed = T.inc_slots[inc];
-      int sl[NV];
-      double x[NV][D], c[3][NV];
-      int la = 0;
+    // ---- phase 1: one gather per (node, slot) ----
+    if (e < deg) {
+      const int q = T.adj_idx[a0 + e];
+      double* o = nbr + (size_t)tid * NB;
 #pragma unroll
-      for (int b = 0; b < NV; ++b) {
-        sl[b] = (packed >> (8 * b)) & 255u;
-        if (sl[b] == self) la = b;
-        const int q = T.adj_idx[a0 + sl[b]];
+      for (int i = 0; i < D; ++i) o[i] = T.node_x[(size_t)(nodeoff + q) * D + i];
+      const double* __restrict__ uc = q < n_own_s ? u + T.L.rowbase[s] + q : u + T.L.n_rows + T.L.gbase[s] + (q - n_own_s);
+      const int fstride = q < n_own_s ? n_own_s : T.L.n_gh[s];
 #pragma unroll
-        for (int i = 0; i < D; ++i) x[b][i] = T.node_x[(size_t)(nodeoff + q) * D + i];
-        if (q < n_own_s) {
-#pragma unroll
-          for (int k = 0; k < 3; ++k) c[k][b] = u_own[k * n_own_s + q];
-        } else {
-#pragma unroll
-          for (int k = 0; k < 3; ++k) c[k][b] = u_gh[k * n_gh_s + q];
-        }
-      }
-      CellGeom<D> G;
-      cell_geometry(x, G);
-      double cbar[3], csum[3];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        double t = 0.0;
-#pragma unroll
-        for (int b = 0; b < NV; ++b) t += c[k][b];
-        csum[k] = t;
-        cbar[k] = t * (1.0 / NV);
-      }
-      const double mv = G.vol * mfac;
-      // gradient of this node's own basis function (runtime local index la -> register select)
-      double gl[D];
-#pragma unroll
-      for (int i = 0; i < D; ++i) {
-        double t = G.g[0][i];
-#pragma unroll
-        for (int a = 1; a < NV; ++a) t = (la == a) ? G.g[a][i] : t;
-        gl[i] = t;
-      }
-#pragma unroll
-      for (int b = 0; b < NV; ++b) {
-        double dot = 0.0;
-#pragma unroll
-        for (int i = 0; i < D; ++i) dot += gl[i] * G.g[b][i];
-        const double Kab = G.vol * dot;
-        const int e = sl[b];
-        a_m[e] += (b == la) ? 2.0 * mv : mv;
-        a_kk[e] += Kab;
-        double kp = 0.0;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          if (MODE == 0) a_kphi[k * deg + e] += cphi[k] * cbar[k] * Kab;
-          kp += cpp[k] * cbar[k] * Kab;
-        }
-        a_pp[e] += kp;
-      }
-      if (MODE == 0) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          double cl = c[k][0];
-#pragma unroll
-          for (int a = 1; a < NV; ++a) cl = (la == a) ? c[k][a] : cl;
-          bk[k] += mv * (csum[k] + cl);
-        }
-      }
-    }
-    // ---- membrane (dS) terms: KNPEMIx_problem.py:599,604,609-610,637-638,641-642 (P: :737-738) ----
-    if (g >= 0) {
-      const size_t nf = (size_t)T.n_mf;
-      const double sgn = s == 0 ? 1.0 : -1.0;
-      const double cf = P.C_M / P.F;
-      const int m1 = T.minc_ptr[g + 1];
-      for (int mi = T.minc_ptr[g]; mi < m1; ++mi) {
-        const uint4 rec = reinterpret_cast<const uint4*>(T.minc)[mi];
-        const int f = (int)rec.x;
-        const int a = rec.y & 255u;
-        const uint32_t ss = s == 0 ? (rec.y >> 8) : rec.z;
-        const uint32_t gs = rec.w;
-        const double area = T.mf_area[f];
-#pragma unroll
-        for (int b = 0; b < D; ++b) {
-          const int es = (ss >> (8 * b)) & 255u;
-          const int eg = (gs >> (8 * b)) & 255u;
-          const double G1 = area * ((a == b) ? 2.0 : 1.0) / (D * (D + 1));
-          if (MODE == 0) {
-            const int ab = a <= b ? symidx(a, b, D) : symidx(b, a, D);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-              const double v = (P.C_M / (P.F * P.z[k])) * fe[(size_t)((s * 3 + k) * NS + ab) * nf + f];
-              a_kphi[k * deg + es] += v;
-              a_ga[k * gdeg + eg] += v;
-            }
-            a_pp[es] += cf * G1;
-            a_g1[eg] += cf * G1;
-          } else {
-            a_pp[es] -= cf * G1;
-          }
-        }
-        if (MODE == 0) {
-#pragma unroll
-          for (int k = 0; k < 3; ++k) bk[k] -= sgn * fe[(size_t)(6 * NS + (s * 3 + k) * D + a) * nf + f];
-          bp -= sgn * fe[(size_t)(6 * NS + 6 * D + a) * nf + f];
-        }
-      }
-    }
-    if (MODE == 0) {
-#pragma unroll
-      for (int k = 0; k < 3; ++k) bvec[T.L.row(s, k, p)] = bk[k];
-      bvec[T.L.row(s, 3, p)] = bp;
+      for (int k = 0; k < 3; ++k) o[D + k] = uc[(size_t)k * fstride];
     }
   }
-  __syncwarp();
-  // ---- output: each thread writes its finished row into the warp's staging strip at its CSR-relative offset, then
-  //      the warp copies the contiguous span to global memory with fully coalesced stores (one pass per field) ----
-  const int* __restrict__ iptr = MODE == 0 ? T.indptr : T.indptr_P;
-  const double* a_m = acc;
-  const double* a_kk = acc + deg;
-  const double* a_kphi = acc + 2 * deg;
-  const double* a_pp = acc + 5 * deg;
-  const double* a_ga = acc + 6 * deg;
-  const double* a_g1 = acc + 6 * deg + 3 * gdeg;
-  const int gd = MODE == 0 ? gdeg : 0;
-#pragma unroll 1
-  for (int f = 0; f < 4; ++f) {
-    const int nseg = MODE == 0 ? (f < 3 ? 2 : 4) : 1;
-    const int rs = active ? iptr[T.L.row(s, f, p)] : 0;
-    const int len = active ? nseg * deg + gd : 0;
-#pragma unroll 1
-    for (int g0 = 0; g0 < 32; g0 += group) {
-      const int base = __shfl_sync(0xffffffffu, rs, g0);
-      const bool mine = active && lane >= g0 && lane < g0 + group;
-      if (mine) {
-        double* o = stg + (rs - base);
+  const bool has_ent = node_ok && e < deg;
+  __syncthreads();
+
+  // ---- phase 2a: one thread per (node, incident cell) ----
+  for (int i = tid; i < (nt << lgI); i += ROWS_THREADS) {
+    const int n = i >> lgI, j = i & (GI - 1);
+    const int ii0 = T.inc_ptr[w0 + n];
+    if (j >= T.inc_ptr[w0 + n + 1] - ii0) continue;
+    const uint32_t pk = T.inc_slots[ii0 + j];
+    packed[i] = pk;
+    const int la = (__ffs(__vcmpeq4(pk, (uint32_t)T.self_slot[w0 + n] * 0x01010101u) & VMASK) - 1) >> 3;
+    const double* nb = nbr + ((size_t)n << lgG) * NB;
+    double x[NV][D], csum[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int b = 0; b < NV; ++b) {
+      const double* v = nb + ((pk >> (8 * b)) & 255u) * NB;
+#pragma unroll
+      for (int d = 0; d < D; ++d) x[b][d] = v[d];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) csum[k] += v[D + k];
+    }
+    CellGeom<D> G;
+    cell_geometry(x, G);
+    double gl[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      double t = G.g[0][d];
+#pragma unroll
+      for (int a = 1; a < NV; ++a) t = (la == a) ? G.g[a][d] : t;
+      gl[d] = t;
+    }
+    double* r = res + (size_t)i * NR;
+#pragma unroll
+    for (int b = 0; b < NV; ++b) {
+      double dot = 0.0;
+#pragma unroll
+      for (int d = 0; d < D; ++d) dot += gl[d] * G.g[b][d];
+      r[b] = G.vol * dot;
+    }
+    r[NV] = G.vol * (1.0 / ((D + 1) * (D + 2)));
+#pragma unroll
+    for (int k = 0; k < 3; ++k) r[NV + 1 + k] = csum[k] * (1.0 / NV);
+  }
+  __syncthreads();
+
+  // ---- phase 2b: accumulate per (node, slot) in registers, cells in ascending order ----
+  double a_m = 0.0, a_kk = 0.0, X[3] = {0.0, 0.0, 0.0}, kphi_m[3] = {0.0, 0.0, 0.0}, pp_m = 0.0;
+  double bmem[4] = {0.0, 0.0, 0.0, 0.0}, ce[3] = {0.0, 0.0, 0.0};
+  double ga[3] = {0.0, 0.0, 0.0}, g1 = 0.0;
+  const bool is_self = has_ent && e == self;
+  const bool has_gam = MODE == 0 && node_ok && e < gdeg;
+  const uint32_t rep = (uint32_t)e * 0x01010101u;
+  if (has_ent) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) ce[k] = nbr[(size_t)tid * NB + D + k];
+    const uint32_t* pk = packed + ((size_t)lw << lgI);
+    const double* rbase = res + ((size_t)lw << lgI) * NR;
+    for (int j = 0; j < ninc; ++j) {
+      const uint32_t m = __vcmpeq4(pk[j], rep) & VMASK;
+      if (m) {
+        const int b = (__ffs(m) - 1) >> 3;
+        const double* r = rbase + j * NR;
+        const double kab = r[b], mv = r[NV];
+        a_m += is_self ? 2.0 * mv : mv;
+        a_kk += kab;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) X[k] += r[NV + 1 + k] * kab;
+      }
+    }
+  }
+  // membrane (dS) terms: KNPEMIx_problem.py:599,604,609-610,637-638,641-642 (P: :737-738); lane e serves adjacency
+  // slot e and gamma slot e (couplings to the potential on the other side of the membrane)
+  if (g >= 0 && (has_ent || has_gam)) {
+    const size_t nf = (size_t)T.n_mf;
+    const double sgn = s == 0 ? 1.0 : -1.0;
+    const int m1 = T.minc_ptr[g + 1];
+    for (int mi = T.minc_ptr[g]; mi < m1; ++mi) {
+      const uint4 rec = reinterpret_cast<const uint4*>(T.minc)[mi];
+      const int f = (int)rec.x;
+      const int a = rec.y & 255u;
+      const uint32_t ss = s == 0 ? (rec.y >> 8) : rec.z;
+      const uint32_t ms = has_ent ? (__vcmpeq4(ss, rep) & FMASK) : 0u;
+      const uint32_t mg = has_gam ? (__vcmpeq4(rec.w, rep) & FMASK) : 0u;
+      if (ms) {
+        const int b = (__ffs(ms) - 1) >> 3;
+        const double G1 = T.mf_area[f] * ((a == b) ? 2.0 : 1.0) * (1.0 / (D * (D + 1)));
+        if (MODE == 0) {
+          const int ab = a <= b ? symidx(a, b, D) : symidx(b, a, D);
+#pragma unroll
+          for (int k = 0; k < 3; ++k) kphi_m[k] += C.cmz[k] * fe[(size_t)((s * 3 + k) * NS + ab) * nf + f];
+          pp_m += C.cf * G1;
+        } else {
+          pp_m -= C.cf * G1;
+        }
+      }
+      if (MODE == 0 && mg) {
+        const int b = (__ffs(mg) - 1) >> 3;
+        const int ab = a <= b ? symidx(a, b, D) : symidx(b, a, D);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) ga[k] += C.cmz[k] * fe[(size_t)((s * 3 + k) * NS + ab) * nf + f];
+        g1 += C.cf * (T.mf_area[f] * ((a == b) ? 2.0 : 1.0) * (1.0 / (D * (D + 1))));
+      }
+      if (MODE == 0 && is_self) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) bmem[k] -= sgn * fe[(size_t)(6 * NS + (s * 3 + k) * D + a) * nf + f];
+        bmem[3] -= sgn * fe[(size_t)(6 * NS + 6 * D + a) * nf + f];
+      }
+    }
+  }
+  __syncthreads();          // neighbour data and cell results are dead: the staging strip may overwrite them
+
+  // ---- phase 3: form the ten block rows at their CSR-relative offsets of the staging strip ----
+  int so[4], base[4], total[4];
+  {
+    int acc = 0;
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      base[f] = rstart[f * (tile + 1)];
+      total[f] = rstart[f * (tile + 1) + nt] - base[f];
+      so[f] = acc;                                   // even: 16-byte aligned start of the field's strip
+      acc += (total[f] + 3) & ~1;                    // room for the phase shift (base & 1), rounded to even
+    }
+  }
+  if (node_ok) {
+    const int goff = s == 1 ? gdeg : 0;
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      const int rsf = rstart[f * (tile + 1) + lw] - base[f];
+      double* o = stg + so[f] + (base[f] & 1) + rsf;
+      if (has_ent) {
+        double* oe = o + goff + e;
         if (MODE == 0) {
           if (f < 3) {
-            if (s == 1)
-              for (int e = 0; e < gd; ++e) *o++ = -a_ga[f * gdeg + e];
-            const double dk = P.dt * P.D[f];
-            for (int e = 0; e < deg; ++e) *o++ = a_m[e] + dk * a_kk[e];
-            for (int e = 0; e < deg; ++e) *o++ = a_kphi[f * deg + e];
-            if (s == 0)
-              for (int e = 0; e < gd; ++e) *o++ = -a_ga[f * gdeg + e];
+            oe[0] = a_m + C.dtD[f] * a_kk;
+            oe[deg] = C.cphi[f] * X[f] + kphi_m[f];
           } else {
-            if (s == 1)
-              for (int e = 0; e < gd; ++e) *o++ = -a_g1[e];
+            double pp = pp_m;
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-              const double ck = P.dt * P.z[k] * P.D[k];
-              for (int e = 0; e < deg; ++e) *o++ = ck * a_kk[e];
+              oe[k * deg] = C.ck[k] * a_kk;
+              pp += C.cpp[k] * X[k];
             }
-            for (int e = 0; e < deg; ++e) *o++ = a_pp[e];
-            if (s == 0)
-              for (int e = 0; e < gd; ++e) *o++ = -a_g1[e];
+            oe[3 * deg] = pp;
           }
         } else {
           if (f < 3) {
-            const double dk = P.dt * P.D[f];
-            for (int e = 0; e < deg; ++e) *o++ = a_m[e] + dk * a_kk[e];
+            oe[0] = a_m + C.dtD[f] * a_kk;
           } else {
-            for (int e = 0; e < deg; ++e) *o++ = a_pp[e];
+            double pp = pp_m;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) pp += C.cpp[k] * X[k];
+            oe[0] = pp;
           }
         }
       }
-      const int total = __reduce_max_sync(0xffffffffu, mine ? rs + len - base : 0);
-      __syncwarp();
-      // coalesced copy-out, 128-bit where the global address allows it (the strip itself is 16-byte aligned)
-      {
-        const int head = base & 1;                      // vals + base is 16-byte aligned iff base is even
-        if (head && lane == 0 && total > 0) vals[(size_t)base] = stg[0];
-        const int npair = (total - head) >> 1;
-        if (head == 0) {
-          const double2* s2 = reinterpret_cast<const double2*>(stg);
-          double2* g2 = reinterpret_cast<double2*>(vals + (size_t)base);
-          for (int q = lane; q < npair; q += 32) g2[q] = s2[q];
-        } else {
-          double2* g2 = reinterpret_cast<double2*>(vals + (size_t)base + 1);
-          for (int q = lane; q < npair; q += 32) g2[q] = make_double2(stg[2 * q + 1], stg[2 * q + 2]);
-        }
-        if (((total - head) & 1) && lane == 0) vals[(size_t)base + total - 1] = stg[total - 1];
-      }
-      __syncwarp();
+      if (has_gam) o[(s == 1 ? 0 : (f < 3 ? 2 : 4) * deg) + e] = f < 3 ? -ga[f] : -g1;
+    }
+    if (MODE == 0 && has_ent && lgG > 5) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) prod[(size_t)tid * 3 + k] = a_m * ce[k];
     }
   }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staging writes -> visible to the TMA (async proxy)
+  __syncthreads();
+
+  // ---- copy-out: one TMA bulk store per field for the 16-byte aligned body, scalar head/tail ----
+  if (tid == 0) {
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      const int sh = base[f] & 1;
+      const int nbody = (total[f] - sh) & ~1;
+      if (nbody > 0) bulk_store(vals + (size_t)base[f] + sh, stg + so[f] + 2 * sh, (uint32_t)nbody * 8u);
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  } else if (tid >= 32 && tid < 36) {
+#pragma unroll
+    for (int f = 0; f < 4; ++f)
+      if (f == tid - 32) {
+        const int sh = base[f] & 1;
+        if (sh && total[f] > 0) vals[(size_t)base[f]] = stg[so[f] + 1];
+        if ((total[f] - sh) & 1) vals[(size_t)base[f] + total[f] - 1] = stg[so[f] + sh + total[f] - 1];
+      }
+  }
+  // right-hand side: b_k = sum_e m_e c_k(e) (KNPEMIx_problem.py:613-614,641-642): segmented warp-shuffle reduction over
+  // the node's lane group (fixed butterfly order -> reproducible); groups wider than a warp fall back to a serial sum
+  if (MODE == 0) {
+    if (lgG <= 5) {
+      double bk[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) bk[k] = has_ent ? a_m * ce[k] : 0.0;
+      for (int off = (1 << lgG) >> 1; off > 0; off >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) bk[k] += __shfl_xor_sync(0xffffffffu, bk[k], off);
+      }
+      if (is_self) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) bvec[T.L.row(s, k, p0 + lw)] = bk[k] + bmem[k];
+        bvec[T.L.row(s, 3, p0 + lw)] = bmem[3];
+      }
+    } else if (is_self) {
+      const double* pr = prod + ((size_t)lw << lgG) * 3;
+      double bk[3] = {0.0, 0.0, 0.0};
+      for (int j = 0; j < deg; ++j) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) bk[k] += pr[j * 3 + k];
+      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) bvec[T.L.row(s, k, p0 + lw)] = bk[k] + bmem[k];
+      bvec[T.L.row(s, 3, p0 + lw)] = bmem[3];
+    }
+  }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------------------------ CSR indices
@@ -616,45 +696,64 @@ int launch_facets(const DevTopo& T, const KParams& P, const uint32_t* tag_models
   return KNP_OK;
 }
 
-int rows_smem_stride(int max_deg, int max_gdeg) {
-  int st = 6 * max_deg + 4 * max_gdeg;
-  if (st % 2 == 0) ++st;   // odd stride (in doubles): conflict-free when all lanes touch the same offset
-  return st;
+// Lanes per node (power of two >= the largest degree) and the shared-memory layout of the row kernel.
+static int ceil_log2(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
 }
 
-// block size / staging group for the row kernel from the mesh's maximum degrees (shared-memory budget)
-void rows_config(int max_deg, int max_gdeg, int mode, int& block, int& group, int& stage_len, size_t& smem) {
-  const int stride = rows_smem_stride(max_deg, max_gdeg);
-  const int maxrow = mode == 0 ? 4 * max_deg + max_gdeg : max_deg;
-  block = 128;
-  while (block > 32 && (size_t)block * stride * 8 > 64 * 1024) block >>= 1;
-  const size_t acc = (size_t)block * stride * 8;
-  const size_t budget = acc <= 60 * 1024 ? 74 * 1024 : (acc <= 100 * 1024 ? 112 * 1024 : 226 * 1024);
-  group = 32;
-  while (group > 1 && acc + (size_t)(block / 32) * group * maxrow * 8 > budget) group >>= 1;
-  if (const char* e = getenv("KNP_ROWS_BLOCK")) block = atoi(e);
-  if (const char* e = getenv("KNP_ROWS_GROUP")) group = atoi(e);
-  stage_len = (group * maxrow + 1) & ~1;   // even: every warp's strip stays 16-byte aligned
-  smem = (size_t)block * stride * 8 + (size_t)(block / 32) * stage_len * 8;
+int rows_tile_size(int max_deg, int max_gdeg) {
+  const int lgG = ceil_log2(std::max(std::max(max_deg, max_gdeg), 1));
+  return std::max(1, ROWS_THREADS >> lgG);
+}
+
+static RowsSmem rows_layout(int gdim, int mode, int max_deg, int max_gdeg, int max_inc) {
+  RowsSmem S{};
+  S.lgG = ceil_log2(std::max(std::max(max_deg, max_gdeg), 1));
+  S.lgI = ceil_log2(std::max(max_inc, 1));
+  S.tile = std::max(1, ROWS_THREADS >> S.lgG);
+  const int NB = gdim + 3, NR = gdim + 1 + 4;
+  const size_t nbr = (size_t)ROWS_THREADS * NB * 8;
+  const size_t res = ((size_t)S.tile << S.lgI) * NR * 8;
+  const size_t packed = ((size_t)S.tile << S.lgI) * 4;
+  S.off_res = (int)nbr;
+  S.off_packed = (int)(nbr + res);
+  const size_t work = (nbr + res + packed + 15) & ~(size_t)15;
+  // staging strip: all four fields of the tile (+ phase shift and rounding per field), then the rhs products
+  const size_t rows = (size_t)S.tile * (mode == 0 ? 10 * max_deg + 4 * max_gdeg : 4 * max_deg) + 16;
+  S.off_prod = (int)(rows * 8);
+  const size_t stage = rows * 8 + (mode == 0 ? (size_t)ROWS_THREADS * 3 * 8 : 0);
+  S.off_rs = (int)((std::max(work, stage) + 15) & ~(size_t)15);
+  S.total = S.off_rs + 4 * (S.tile + 1) * 4;
+  return S;
 }
 
 template <int D, int MODE>
 static int launch_rows_t(const DevTopo& T, const KParams& P, const double* u, const double* fe, double* vals,
-                         double* b, int stride, int max_deg, int max_gdeg, cudaStream_t st) {
-  int block, group, stage_len;
-  size_t smem;
-  rows_config(max_deg, max_gdeg, MODE, block, group, stage_len, smem);
-  if (smem > 227 * 1024) {
-    set_error("vertex degree too large for the row kernel's shared-memory strip (%zu bytes)", smem);
+                         double* b, int max_deg, int max_gdeg, cudaStream_t st) {
+  const RowsSmem S = rows_layout(D, MODE, max_deg, max_gdeg, T.max_inc);
+  if (S.total > 227 * 1024 || (1 << S.lgG) > ROWS_THREADS) {
+    set_error("vertex degree %d / valence %d too large for the row kernel (%d bytes of shared memory)", max_deg,
+              T.max_inc, S.total);
     return KNP_E_UNSUPPORTED;
   }
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    KNP_CUDA(cudaFuncSetAttribute(rows_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+  static int configured = 0;
+  if (S.total > 48 * 1024 && S.total > configured) {
+    KNP_CUDA(cudaFuncSetAttribute(rows_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, S.total));
+    configured = S.total;
   }
-  const int nb0 = (T.L.n_own[0] + block - 1) / block, nb1 = (T.L.n_own[1] + block - 1) / block;
-  rows_kernel<D, MODE><<<nb0 + nb1, block, smem, st>>>(T, P, u, fe, vals, b, stride, group, stage_len, nb0);
+  RowCoef C;
+  for (int k = 0; k < 3; ++k) {
+    C.dtD[k] = P.dt * P.D[k];
+    C.cphi[k] = P.dt * P.D[k] * P.z[k] / P.psi;
+    C.cpp[k] = P.dt * P.D[k] * P.z[k] * P.z[k] / P.psi;
+    C.ck[k] = P.dt * P.z[k] * P.D[k];
+    C.cmz[k] = P.C_M / (P.F * P.z[k]);
+  }
+  C.cf = P.C_M / P.F;
+  const int nt0 = (T.L.n_own[0] + S.tile - 1) / S.tile, nt1 = (T.L.n_own[1] + S.tile - 1) / S.tile;
+  rows_kernel<D, MODE><<<nt0 + nt1, ROWS_THREADS, S.total, st>>>(T, C, u, fe, vals, b, S, nt0);
   KNP_LAUNCHED();
   return KNP_OK;
 }
@@ -662,11 +761,10 @@ static int launch_rows_t(const DevTopo& T, const KParams& P, const double* u, co
 int launch_rows(const DevTopo& T, const KParams& P, int mode, const double* u, const double* fe, double* vals,
                 double* b, int max_deg, int max_gdeg, cudaStream_t st) {
   if (T.n_work == 0) return KNP_OK;
-  const int stride = rows_smem_stride(max_deg, max_gdeg);
-  if (T.gdim == 2) return mode == 0 ? launch_rows_t<2, 0>(T, P, u, fe, vals, b, stride, max_deg, max_gdeg, st)
-                                    : launch_rows_t<2, 1>(T, P, u, fe, vals, b, stride, max_deg, max_gdeg, st);
-  return mode == 0 ? launch_rows_t<3, 0>(T, P, u, fe, vals, b, stride, max_deg, max_gdeg, st)
-                   : launch_rows_t<3, 1>(T, P, u, fe, vals, b, stride, max_deg, max_gdeg, st);
+  if (T.gdim == 2) return mode == 0 ? launch_rows_t<2, 0>(T, P, u, fe, vals, b, max_deg, max_gdeg, st)
+                                    : launch_rows_t<2, 1>(T, P, u, fe, vals, b, max_deg, max_gdeg, st);
+  return mode == 0 ? launch_rows_t<3, 0>(T, P, u, fe, vals, b, max_deg, max_gdeg, st)
+                   : launch_rows_t<3, 1>(T, P, u, fe, vals, b, max_deg, max_gdeg, st);
 }
 
 int launch_csr_indices(const DevTopo& T, int mode, int32_t* indices, cudaStream_t st) {

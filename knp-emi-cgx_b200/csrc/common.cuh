@@ -113,7 +113,7 @@ struct HostTopo {
   std::vector<int32_t> cell_nodes[2];         // [(gdim+1) per cell] subdomain-local node ids
   std::vector<int32_t> cell_tag[2];
   std::vector<int32_t> cell_owned[2];         // 1 if the cell's lowest-id vertex is owned (integrate once)
-  int max_deg = 0, max_gdeg = 0;
+  int max_deg = 0, max_gdeg = 0, max_inc = 0;
   // CSR sizes
   int64_t nnz = 0, nnz_P = 0;
   std::vector<int32_t> indptr, indptr_P;      // computed on host (n_rows+1)
@@ -137,6 +137,8 @@ struct DevTopo {
   const uint32_t* minc;
   const int32_t *indptr, *indptr_P;
   const double *qb, *qw;
+  const int32_t* gpre;       // per owned node: prefix of the gamma degree
+  int max_inc;               // largest number of cells incident to one owned node
 };
 
 struct Params {

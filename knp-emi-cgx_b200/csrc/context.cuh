@@ -13,7 +13,7 @@ struct knp_ctx {
   knp::DevTopo T{};
   // device copies of the topology
   knp::DevBuf<double> d_node_x, d_mf_area, d_qb, d_qw;
-  knp::DevBuf<int32_t> d_adj_ptr, d_adj_idx, d_inc_ptr, d_self_slot, d_mv_of_node;
+  knp::DevBuf<int32_t> d_adj_ptr, d_adj_idx, d_inc_ptr, d_self_slot, d_mv_of_node, d_gpre;
   knp::DevBuf<uint32_t> d_inc_slots, d_minc;
   knp::DevBuf<int32_t> d_mv_node0, d_mv_node1, d_mf_mv, d_mf_tagidx, d_gam_ptr, d_gam_mv, d_minc_ptr;
   knp::DevBuf<int32_t> d_indptr, d_indices, d_indptr_P, d_indices_P, d_rowblk_A;
@@ -28,7 +28,6 @@ struct knp_ctx {
   // state and system
   knp::DevBuf<double> u, gates, A_vals, P_vals, b, fe;
   bool P_assembled = false;
-  int rows_stride = 0;
   double t = 0.0;
   int step_index = 0;
   // Krylov workspace
@@ -39,6 +38,9 @@ struct knp_ctx {
   // preconditioner
   int pc_kind = -1;
   std::unique_ptr<knp::Amg> amg;
+  // charge-conservation Schur preconditioner (pc kind 3): hierarchies of the ion and of the potential blocks
+  std::unique_ptr<knp::Amg> amg_c, amg_p;
+  knp::DevBuf<double> M_vals, msig_inv, sch_vc, sch_zc, sch_t, sch_zp, sch_q, sch_rhs;
   // distributed
   ncclComm* comm = nullptr;
   int rank = 0, nranks = 1;

@@ -4,7 +4,6 @@
 
 namespace knp {
 
-constexpr int ROWS_BLOCK = 128;
 
 // Plain-old-data copy of the constants that enter the forms (passed by value to kernels).
 struct KParams {
@@ -21,7 +20,7 @@ int launch_gate(const DevTopo& T, const KParams& P, const double* u, double* gat
 int facet_ncomp(int gdim);
 int launch_facets(const DevTopo& T, const KParams& P, const uint32_t* tag_models, const int32_t* tag_stim,
                   const double* u, const double* gates, double stim_fac, double* fe, cudaStream_t st);
-int rows_smem_stride(int max_deg, int max_gdeg);
+int rows_tile_size(int max_deg, int max_gdeg);
 int launch_rows(const DevTopo& T, const KParams& P, int mode, const double* u, const double* fe, double* vals,
                 double* b, int max_deg, int max_gdeg, cudaStream_t st);
 int launch_csr_indices(const DevTopo& T, int mode, int32_t* indices, cudaStream_t st);

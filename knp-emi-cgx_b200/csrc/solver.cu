@@ -199,12 +199,218 @@ static int coarse_apply(knp_ctx* c, const double* r, double* z, cudaStream_t st)
   return KNP_OK;
 }
 
+static int vcycle(Amg& M, int l, const double* bl, double* xout, cudaStream_t st);
+
+// builds the hierarchy of A0 on the host and uploads it
+static int build_amg(knp_ctx* c, const CsrHost& A0, std::unique_ptr<Amg>& out) {
+  std::vector<CsrHost> As, Ps, Rs;
+  std::vector<double> rhos, cinv;
+  KNP_TRY(amg_setup_host(A0, 0.08, 600, 16, As, Ps, Rs, rhos, cinv));
+  auto amg = std::make_unique<Amg>();
+  const int nl = (int)Ps.size();
+  for (int l = 0; l < nl; ++l) {
+    auto* lv = new AmgLevelDev();
+    amg->levels.push_back(lv);
+    KNP_TRY(upload_csr(As[l], lv->A));
+    KNP_TRY(upload_csr(Ps[l], lv->P));
+    KNP_TRY(upload_csr(Rs[l], lv->R));
+    lv->rho = rhos[l];
+    const int nr = As[l].n_rows;
+    KNP_TRY(lv->dinv.alloc(nr));
+    KNP_TRY(lv->x.alloc(nr));
+    KNP_TRY(lv->b.alloc(nr));
+    KNP_TRY(lv->r.alloc(nr));
+    KNP_TRY(launch_extract_dinv(nr, lv->A.indptr.p, lv->A.indices.p, lv->A.vals.p, lv->dinv.p, c->stream));
+  }
+  amg->n_coarse = As.back().n_rows;
+  KNP_TRY(amg->coarse_inv.upload(cinv));
+  KNP_TRY(amg->cb.alloc(amg->n_coarse));
+  KNP_TRY(amg->cx.alloc(amg->n_coarse));
+  amg->hostA = std::move(As);
+  KNP_CUDA(cudaStreamSynchronize(c->stream));
+  out = std::move(amg);
+  return KNP_OK;
+}
+
+// ---- charge-conservation Schur preconditioner (pc kind 3) ---------------------------------------------------------
+// The potential row of `a` (KNPEMIx_problem.py:603-610) equals the z_k-weighted sum of the ion rows (:598-600) minus
+// sum_k z_k M c_k (the membrane terms cancel too because sum_k alpha_k = 1), so with L = [I 0; -Z I] the system matrix
+// becomes  L A = [A_cc A_cphi; -Z M 0].  Its Schur complement Z M A_cc^-1 A_cphi behaves like sum_k (z_k^2 c_k/psi) M at
+// high and like the phi block K_phi + (C_M/F) M_Gamma at low frequencies, which gives
+//      S~^-1 = (K_phi + (C_M/F) M_Gamma)^-1 + M_sigma^-1          (M_sigma lumped)
+// and the block lower-triangular application
+//      v = L r ;  z_c = AMG_c(v_c) ;  t = v_phi + M (sum_k z_k z_ck) ;  z_phi = AMG_phi(t) + t / M_sigma.
+// Unlike the block-Jacobi form P of the reference (KNPEMIx_problem.py:657-744) no cancellation between the c and phi
+// blocks has to be resolved by the inexact block solves: 20-30 GMRES iterations instead of 100-1500 on transient
+// states (scripts/pc_experiment.py).  oracle/amg.py::SchurPC restates it for the tests.
+__global__ void schur_split_kernel(Layout L, double z0, double z1, double z2, const double* __restrict__ r,
+                                   double* __restrict__ vc, double* __restrict__ t) {
+  const int n0 = L.n_own[0], n1 = L.n_own[1];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n0 + n1; i += gridDim.x * blockDim.x) {
+    const int s = i >= n0, p = s ? i - n0 : i, ns = s ? n1 : n0;
+    const double* rs = r + L.rowbase[s];
+    double* vs = vc + (s ? 3 * n0 : 0);
+    const double a = rs[p], b = rs[ns + p], c = rs[2 * ns + p];
+    vs[p] = a;
+    vs[ns + p] = b;
+    vs[2 * ns + p] = c;
+    t[i] = rs[3 * ns + p] - ((z0 * a + z1 * b) + z2 * c);
+  }
+}
+// q (full column layout, stored in the field-0 slots) = sum_k z_k z_ck
+__global__ void schur_q_kernel(Layout L, double z0, double z1, double z2, const double* __restrict__ zc,
+                               double* __restrict__ q) {
+  const int n0 = L.n_own[0], n1 = L.n_own[1];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n0 + n1; i += gridDim.x * blockDim.x) {
+    const int s = i >= n0, p = s ? i - n0 : i, ns = s ? n1 : n0;
+    const double* zs = zc + (s ? 3 * n0 : 0);
+    q[L.rowbase[s] + p] = (z0 * zs[p] + z1 * zs[ns + p]) + z2 * zs[2 * ns + p];
+  }
+}
+// z (full layout) <- [z_c ; z_phi + t / M_sigma] ; rhs (optional, full layout) <- [v_c ; t]
+__global__ void schur_merge_kernel(Layout L, const double* __restrict__ zc, const double* __restrict__ zp,
+                                   const double* __restrict__ t, const double* __restrict__ msig_inv,
+                                   const double* __restrict__ vc, double* __restrict__ z, double* __restrict__ rhs) {
+  const int n0 = L.n_own[0], n1 = L.n_own[1];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n0 + n1; i += gridDim.x * blockDim.x) {
+    const int s = i >= n0, p = s ? i - n0 : i, ns = s ? n1 : n0;
+    const double* zs = zc + (s ? 3 * n0 : 0);
+    double* out = z + L.rowbase[s];
+    out[p] = zs[p];
+    out[ns + p] = zs[ns + p];
+    out[2 * ns + p] = zs[2 * ns + p];
+    out[3 * ns + p] = zp[i] + t[i] * msig_inv[i];
+    if (rhs) {
+      const double* vs = vc + (s ? 3 * n0 : 0);
+      double* ro = rhs + L.rowbase[s];
+      ro[p] = vs[p];
+      ro[ns + p] = vs[ns + p];
+      ro[2 * ns + p] = vs[2 * ns + p];
+      ro[3 * ns + p] = t[i];
+    }
+  }
+}
+
+static int schur_setup(knp_ctx* c) {
+  const Layout& L = c->T.L;
+  const int n = L.n_rows, n0 = L.n_own[0], n1 = L.n_own[1];
+  KNP_CHECK(L.rowbase[0] == 0 && L.rowbase[1] == 4 * n0, "unexpected row layout");
+  cudaStream_t st = c->stream;
+  // P~: ion blocks M + dt D_k K, phi blocks K_phi + (C_M/F) M_Gamma (the sign the membrane term has in `a`)
+  KParams kp = c->kp;
+  kp.C_M = -c->kp.C_M;
+  KNP_TRY(launch_rows(c->T, kp, 1, c->u.p, c->fe.p, c->P_vals.p, nullptr, c->H.max_deg, c->H.max_gdeg, st));
+  c->P_assembled = true;
+  // mass matrices: the same kernel with D = 0 leaves M in the ion blocks
+  kp = c->kp;
+  for (int k = 0; k < 3; ++k) kp.D[k] = 0.0;
+  KNP_TRY(c->M_vals.alloc(c->H.nnz_P));
+  KNP_TRY(launch_rows(c->T, kp, 1, c->u.p, c->fe.p, c->M_vals.p, nullptr, c->H.max_deg, c->H.max_gdeg, st));
+  KNP_CUDA(cudaStreamSynchronize(st));
+  std::vector<int32_t> idx(c->H.nnz_P);
+  std::vector<double> val(c->H.nnz_P), mval(c->H.nnz_P), u(L.n_cols);
+  KNP_CUDA(cudaMemcpy(idx.data(), c->d_indices_P.p, idx.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  KNP_CUDA(cudaMemcpy(val.data(), c->P_vals.p, val.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  KNP_CUDA(cudaMemcpy(mval.data(), c->M_vals.p, mval.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  KNP_CUDA(cudaMemcpy(u.data(), c->u.p, u.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  const std::vector<int32_t>& ip = c->H.indptr_P;
+  // compact numbering: c part [s=0: 3 n0 | s=1: 3 n1], phi part [n0 | n1]; ghost columns are dropped (processor-local)
+  auto cmap = [&](int i) -> int {   // full row/col -> compact index in its part, or -1 if it belongs to the other part
+    if (i < 3 * n0) return i;
+    if (i < 4 * n0) return -1;
+    if (i < 4 * n0 + 3 * n1) return i - n0;
+    return -1;
+  };
+  auto pmap = [&](int i) -> int {
+    if (i < 3 * n0) return -1;
+    if (i < 4 * n0) return i - 3 * n0;
+    if (i < 4 * n0 + 3 * n1) return -1;
+    return i - 3 * n0 - 3 * n1;
+  };
+  CsrHost Acc, App;
+  Acc.n_rows = Acc.n_cols = 3 * (n0 + n1);
+  App.n_rows = App.n_cols = n0 + n1;
+  Acc.indptr.assign(1, 0);
+  App.indptr.assign(1, 0);
+  for (int i = 0; i < n; ++i) {
+    const bool isc = cmap(i) >= 0;
+    CsrHost& M = isc ? Acc : App;
+    for (int j = ip[i]; j < ip[i + 1]; ++j) {
+      if (idx[j] >= n) continue;
+      const int cc = isc ? cmap(idx[j]) : pmap(idx[j]);
+      if (cc < 0) continue;
+      M.indices.push_back(cc);
+      M.vals.push_back(val[j]);
+    }
+    M.indptr.push_back((int32_t)M.indices.size());
+  }
+  // rows were visited in the order c(s=0), phi(s=0), c(s=1), phi(s=1) = ascending compact order in both parts
+  KNP_TRY(coarse_setup(c, idx, val));
+  KNP_TRY(build_amg(c, Acc, c->amg_c));
+  KNP_TRY(build_amg(c, App, c->amg_p));
+  // lumped M_sigma = (sum_k z_k^2 c_k / psi) at the node  x  row sum of the mass matrix
+  std::vector<double> msig_inv((size_t)n0 + n1);
+  const double* z = c->kp.z;
+  for (int s = 0; s < 2; ++s)
+    for (int p = 0; p < L.n_own[s]; ++p) {
+      const int row = L.row(s, 0, p);
+      double ms = 0.0;
+      for (int j = ip[row]; j < ip[row + 1]; ++j) ms += mval[j];
+      double sig = 0.0;
+      for (int k = 0; k < 3; ++k) sig += z[k] * z[k] / c->kp.psi * u[L.col(s, k, p)];
+      msig_inv[(size_t)(s ? n0 : 0) + p] = 1.0 / (sig * ms);
+    }
+  KNP_TRY(c->msig_inv.upload(msig_inv));
+  KNP_TRY(c->sch_vc.alloc((size_t)3 * (n0 + n1)));
+  KNP_TRY(c->sch_zc.alloc((size_t)3 * (n0 + n1)));
+  KNP_TRY(c->sch_t.alloc((size_t)n0 + n1));
+  KNP_TRY(c->sch_zp.alloc((size_t)n0 + n1));
+  KNP_TRY(c->sch_q.alloc(L.n_cols));
+  KNP_TRY(c->sch_rhs.alloc(L.n_rows));
+  KNP_CUDA(cudaMemset(c->sch_q.p, 0, (size_t)L.n_cols * sizeof(double)));
+  return KNP_OK;
+}
+
+static int schur_apply(knp_ctx* c, const double* r, double* zout, cudaStream_t st) {
+  const Layout& L = c->T.L;
+  const int n0 = L.n_own[0], n1 = L.n_own[1];
+  const double* z = c->kp.z;
+  int grid = (n0 + n1 + 255) / 256;
+  if (grid > 148 * 8) grid = 148 * 8;
+  if (grid < 1) grid = 1;
+  schur_split_kernel<<<grid, 256, 0, st>>>(L, z[0], z[1], z[2], r, c->sch_vc.p, c->sch_t.p);
+  KNP_LAUNCHED();
+  KNP_TRY(vcycle(*c->amg_c, 0, c->sch_vc.p, c->sch_zc.p, st));
+  schur_q_kernel<<<grid, 256, 0, st>>>(L, z[0], z[1], z[2], c->sch_zc.p, c->sch_q.p);
+  KNP_LAUNCHED();
+  KNP_TRY(halo_exchange(c, c->sch_q.p, st));
+  for (int s = 0; s < 2; ++s) {
+    if (L.n_own[s] == 0) continue;
+    const int row0 = L.row(s, 0, 0);
+    const int64_t nnz_s = (int64_t)c->H.indptr_P[row0 + L.n_own[s]] - c->H.indptr_P[row0];
+    KNP_TRY(launch_spmv(L.n_own[s], nnz_s, c->d_indptr_P.p + row0, c->d_indices_P.p, c->M_vals.p, c->sch_q.p,
+                        c->sch_t.p + (s ? n0 : 0), EPI_ADD, nullptr, nullptr, 0.0, st));
+  }
+  KNP_TRY(vcycle(*c->amg_p, 0, c->sch_t.p, c->sch_zp.p, st));
+  schur_merge_kernel<<<grid, 256, 0, st>>>(L, c->sch_zc.p, c->sch_zp.p, c->sch_t.p, c->msig_inv.p, c->sch_vc.p, zout,
+                                           c->cz_on ? c->sch_rhs.p : nullptr);
+  KNP_LAUNCHED();
+  if (c->cz_on) KNP_TRY(coarse_apply(c, c->sch_rhs.p, zout, st));
+  return KNP_OK;
+}
+
 int pc_setup(knp_ctx* c, const knp_solve_opts* o) {
   const int n = c->T.L.n_rows;
   c->amg.reset();
+  c->amg_c.reset();
+  c->amg_p.reset();
   c->cz_on = false;
   c->pc_kind = o->pc;
   if (o->pc == 0) return KNP_OK;
+  if (o->pc == 3) {
+    KNP_CHECK(c->params_set, "knp_set_params must be called first");
+    return schur_setup(c);
+  }
   if (!c->P_assembled) {
     set_error("knp_pc_setup: assemble P first (knp_assemble_P)");
     return KNP_E_INVALID;
@@ -242,33 +448,7 @@ int pc_setup(knp_ctx* c, const knp_solve_opts* o) {
     }
     KNP_TRY(coarse_setup(c, idx, val));
   }
-  std::vector<CsrHost> As, Ps, Rs;
-  std::vector<double> rhos, cinv;
-  KNP_TRY(amg_setup_host(P0, 0.08, 600, 16, As, Ps, Rs, rhos, cinv));
-  auto amg = std::make_unique<Amg>();
-  const int nl = (int)Ps.size();
-  for (int l = 0; l < nl; ++l) {
-    auto* lv = new AmgLevelDev();
-    amg->levels.push_back(lv);
-    KNP_TRY(upload_csr(As[l], lv->A));
-    KNP_TRY(upload_csr(Ps[l], lv->P));
-    KNP_TRY(upload_csr(Rs[l], lv->R));
-    lv->rho = rhos[l];
-    const int nr = As[l].n_rows;
-    KNP_TRY(lv->dinv.alloc(nr));
-    KNP_TRY(lv->x.alloc(nr));
-    KNP_TRY(lv->b.alloc(nr));
-    KNP_TRY(lv->r.alloc(nr));
-    KNP_TRY(launch_extract_dinv(nr, lv->A.indptr.p, lv->A.indices.p, lv->A.vals.p, lv->dinv.p, c->stream));
-  }
-  amg->n_coarse = As.back().n_rows;
-  KNP_TRY(amg->coarse_inv.upload(cinv));
-  KNP_TRY(amg->cb.alloc(amg->n_coarse));
-  KNP_TRY(amg->cx.alloc(amg->n_coarse));
-  amg->hostA = std::move(As);
-  KNP_CUDA(cudaStreamSynchronize(c->stream));
-  c->amg = std::move(amg);
-  return KNP_OK;
+  return build_amg(c, P0, c->amg);
 }
 
 // z = V-cycle(r); level-l right-hand side in bl, result written to xout (distinct from bl)
@@ -276,8 +456,7 @@ static CsrView view(const CsrDev& M) {
   return CsrView{M.n_rows, M.nnz, M.indptr.p, M.indices.p, M.vals.p, M.rowblk.p, M.nblk};
 }
 
-static int vcycle(knp_ctx* c, int l, const double* bl, double* xout, cudaStream_t st) {
-  Amg& M = *c->amg;
+static int vcycle(Amg& M, int l, const double* bl, double* xout, cudaStream_t st) {
   const int nl = (int)M.levels.size();
   if (l == nl) return launch_dense_gemv(M.n_coarse, M.coarse_inv.p, bl, xout, st);
   AmgLevelDev& L = *M.levels[l];
@@ -291,7 +470,7 @@ static int vcycle(knp_ctx* c, int l, const double* bl, double* xout, cudaStream_
   double* bc = (l + 1 == nl) ? M.cb.p : M.levels[l + 1]->b.p;
   double* xc = L.r.p;
   KNP_TRY(spmv(view(L.R), L.r.p, bc, EPI_SET, nullptr, nullptr, 0.0, st));
-  KNP_TRY(vcycle(c, l + 1, bc, xc, st));
+  KNP_TRY(vcycle(M, l + 1, bc, xc, st));
   // x += P x_c
   KNP_TRY(spmv(view(L.P), xc, L.x.p, EPI_ADD, nullptr, nullptr, 0.0, st));
   // post-smooth, out of place into xout
@@ -306,9 +485,10 @@ __global__ void dinv_mul_kernel(int n, const double* __restrict__ dinv, const do
 int pc_apply(knp_ctx* c, const double* r, double* z, cudaStream_t st) {
   const int n = c->T.L.n_rows;
   if (c->pc_kind == 2 && c->amg) {
-    KNP_TRY(vcycle(c, 0, r, z, st));
+    KNP_TRY(vcycle(*c->amg, 0, r, z, st));
     return coarse_apply(c, r, z, st);
   }
+  if (c->pc_kind == 3 && c->amg_c && c->amg_p) return schur_apply(c, r, z, st);
   if (c->pc_kind == 1) {
     int grid = (n + 255) / 256;
     if (grid > 148 * 16) grid = 148 * 16;

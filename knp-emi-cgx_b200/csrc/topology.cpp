@@ -127,7 +127,11 @@ int build_topology(const knp_mesh_desc* m, HostTopo& T) {
     }
   }
   // every owned node must touch a cell
-  for (int w = 0; w < W; ++w) KNP_CHECK(T.inc_ptr[w + 1] > T.inc_ptr[w], "owned dof %d has no incident cell", w);
+  T.max_inc = 0;
+  for (int w = 0; w < W; ++w) {
+    KNP_CHECK(T.inc_ptr[w + 1] > T.inc_ptr[w], "owned dof %d has no incident cell", w);
+    T.max_inc = std::max(T.max_inc, T.inc_ptr[w + 1] - T.inc_ptr[w]);
+  }
 
   // ---- adjacency (sorted unique subdomain-local node ids, includes the node itself) ----
   T.adj_ptr.assign(W + 1, 0);

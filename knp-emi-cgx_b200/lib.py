@@ -65,7 +65,7 @@ SYMBOLS = [
     "knp_csr_P_host", "knp_dofmap_host", "knp_mverts_host", "knp_set_params", "knp_stimulus_area_local",
     "knp_set_state", "knp_get_state", "knp_state_dev", "knp_phi_m_host", "knp_gate_step", "knp_assemble",
     "knp_assemble_P", "knp_values_dev", "knp_spmv", "knp_pc_setup", "knp_pc_apply", "knp_solve", "knp_step",
-    "knp_step_host", "knp_set_time", "knp_get_time", "knp_l2_norm_sq", "knp_last_timings", "knp_amg_num_levels",
+    "knp_step_host", "knp_set_time", "knp_get_time", "knp_l2_norm_sq", "knp_last_timings", "knp_amg_num_levels", "knp_amg_part_levels",
     "knp_copy", "knp_amg_level_sizes", "knp_amg_level_host", "knp_nccl_unique_id", "knp_dist_init", "knp_halo_exchange",
     "knp_allreduce_sum",
 ]
@@ -120,6 +120,7 @@ def load():
     lib.knp_last_timings.argtypes = [vp, vp]
     lib.knp_copy.argtypes = [vp, vp, vp, C.c_int64, C.c_int32]
     lib.knp_amg_num_levels.argtypes = [vp]
+    lib.knp_amg_part_levels.argtypes = [vp, C.c_int32]
     lib.knp_amg_level_sizes.argtypes = [vp, C.c_int32, c_i64p, c_i64p]
     lib.knp_amg_level_host.argtypes = [vp, C.c_int32, vp, vp, vp]
     lib.knp_nccl_unique_id.argtypes = [C.c_char_p]
@@ -332,10 +333,14 @@ class Context:
         d = self.dev_ptrs()
         return (self.to_host(d["A"], self.nnz), self.to_host(d["b"], self.n_rows), self.to_host(d["P"], self.nnz_P))
 
-    def amg_levels(self):
+    def amg_levels(self, part=None):
+        """Level operators as scipy CSR; part=None: all hierarchies in order, else only hierarchy `part`."""
         import scipy.sparse as sp
         out = []
-        for l in range(self._lib.knp_amg_num_levels(self.h)):
+        n0 = self._lib.knp_amg_part_levels(self.h, 0)
+        rng = range(self._lib.knp_amg_num_levels(self.h)) if part is None else (
+            range(n0) if part == 0 else range(n0, n0 + self._lib.knp_amg_part_levels(self.h, part)))
+        for l in rng:
             n, nnz = C.c_int64(), C.c_int64()
             check(self._lib.knp_amg_level_sizes(self.h, l, C.byref(n), C.byref(nnz)))
             ip = np.empty(n.value + 1, np.int32)

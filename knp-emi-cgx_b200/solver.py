@@ -8,8 +8,11 @@ falls back to the CPU.
 Solver mapping (documented in DESIGN.md):
   * ``direct: True``  (PREONLY + MUMPS LU, :167-172)  -> GMRES + SA-AMG driven to the fp64 floor
     (``direct_rtol``) followed by the projection ns^T x = 0 that KSP applies after MUMPS (:324-333).
-  * ``pc_type: hypre`` (one BoomerAMG V-cycle on P, :269-273) -> one V(1,1) cycle of our smoothed-aggregation
-    hierarchy on the same P.  Iteration counts are therefore ours, not hypre's.
+  * ``pc_type: hypre`` (one BoomerAMG V-cycle on P, :269-273) -> our charge-conservation Schur preconditioner
+    (``amg_form = "schur"``, csrc/solver.cu): smoothed-aggregation V-cycles on the ion and potential blocks combined
+    block-triangularly after the row operation that turns the potential equation into charge conservation.
+    ``pc_type: gamg`` (or ``amg_form = "block_jacobi"``) -> one SA-AMG V(1,1) cycle on the reference's own
+    block-diagonal P.  Iteration counts are ours, not hypre's.
 """
 import time
 import numpy as np
@@ -43,6 +46,7 @@ class SolverKNPEMI:
     direct_rtol = 1e-13         # "direct" = Krylov solve to the fp64 floor
     direct_refine = 2
     direct_restart = 60
+    amg_form = "schur"          # what ``pc_type: hypre`` maps to: "schur" | "block_jacobi"
 
     def __init__(self, problem, solver_config: dict):
         self.problem = problem
@@ -83,7 +87,7 @@ class SolverKNPEMI:
         pure_neumann = not self.problem.dirichlet_bcs and not self.problem.pin_ecs_potential
         if self.direct_solver:
             o.rtol, o.max_it, o.restart = self.direct_rtol, self.ksp_max_it, self.direct_restart
-            o.pc, o.project_nullspace = 2, int(pure_neumann)
+            o.pc, o.project_nullspace = (3 if self.amg_form == "schur" else 2), int(pure_neumann)
             o.zero_mean_solution, o.refine = int(pure_neumann), self.direct_refine
             # balance concentrations (~1e2) against potentials (~1e-2) in the residual norm
             p = self.problem
@@ -97,9 +101,11 @@ class SolverKNPEMI:
                 raise NotImplementedError(f"ksp_type {self.ksp_type!r}: the system is nonsymmetric; only gmres is implemented")
             if self.norm_type != "preconditioned":
                 raise NotImplementedError("only the preconditioned residual norm (the reference default) is implemented")
-            pcs = {"hypre": 2, "gamg": 2, "amg": 2, "jacobi": 1, "none": 0}
+            if self.amg_form not in ("schur", "block_jacobi"):
+                raise ValueError(f"amg_form {self.amg_form!r}: expected 'schur' or 'block_jacobi'")
+            pcs = {"hypre": 3 if self.amg_form == "schur" else 2, "schur": 3, "gamg": 2, "amg": 2, "jacobi": 1, "none": 0}
             if self.pc_type not in pcs:
-                raise NotImplementedError(f"pc_type {self.pc_type!r} is not implemented (hypre|gamg|jacobi|none)")
+                raise NotImplementedError(f"pc_type {self.pc_type!r} is not implemented (hypre|schur|gamg|jacobi|none)")
             o.rtol, o.max_it, o.restart = self.ksp_rtol, self.ksp_max_it, self.gmres_restart
             o.pc = pcs[self.pc_type] if self.use_P_mat else 0
             o.project_nullspace, o.zero_mean_solution, o.refine = int(pure_neumann), 0, 0

@@ -84,17 +84,30 @@ def mis2_aggregate(S):
     return agg, roots.size + left.size
 
 
-def sa_level(A, theta=0.08, omega=4.0 / 3.0):
-    """One smoothed-aggregation coarsening: returns (P, R, A_c, rho) with constant near-nullspace."""
+def sa_level(A, theta=0.08, omega=4.0 / 3.0, filtered=None, level=0):
+    """One smoothed-aggregation coarsening: returns (P, R, A_c, rho) with constant near-nullspace.
+    The prolongator is smoothed with the filtered matrix (strong off-diagonals, weak ones lumped into the diagonal)."""
     A = A.tocsr()
     n = A.shape[0]
-    S = strength_graph(A, theta)
+    for attempt in range(4):                 # threshold halved until the strength graph has >= 3 edges per row
+        S = strength_graph(A, theta * 0.5 ** attempt)
+        if S.nnz >= 3.0 * n:
+            break
     agg, nagg = mis2_aggregate(S)
     # unnormalised tentative prolongator: the constant stays the near-nullspace vector on every level
     T = sp.csr_matrix((np.ones(n), (np.arange(n), agg)), shape=(n, nagg))
     dinv = 1.0 / A.diagonal()
     rho = float(np.max(np.abs(dinv) * np.asarray(np.abs(A).sum(axis=1)).ravel()))   # Gershgorin bound on rho(D^-1 A)
-    P = (T - sp.diags((omega / rho) * dinv) @ (A @ T)).tocsr()
+    keep = (S + sp.identity(n, dtype=np.int8, format="csr")).astype(float)
+    AF = A.multiply(keep).tocsr()
+    AF = (AF + sp.diags(np.asarray(A.sum(axis=1)).ravel() - np.asarray(AF.sum(axis=1)).ravel())).tocsr()
+    if filtered is None:
+        # the finest level (mesh edges with vanishing stiffness) and the dense Galerkin levels of 3D meshes
+        filtered = level == 0 or A.nnz > 32.0 * n
+    if not filtered:
+        AF = A
+    rhoF = float(np.max(np.abs(dinv) * np.asarray(np.abs(AF).sum(axis=1)).ravel()))
+    P = (T - sp.diags((omega / rhoF) * dinv) @ (AF @ T)).tocsr()
     P.sort_indices()
     R = P.T.tocsr()
     R.sort_indices()
@@ -106,12 +119,13 @@ def sa_level(A, theta=0.08, omega=4.0 / 3.0):
 class SAAMG:
     """V(1,1)-cycle with weighted Jacobi (or Chebyshev) smoothing; dense inverse on the coarsest level."""
 
-    def __init__(self, A, theta=0.08, max_levels=12, coarse_size=600, smoother="jacobi", cheb_deg=2):
+    def __init__(self, A, theta=0.08, max_levels=12, coarse_size=600, smoother="jacobi", cheb_deg=2, filtered=None,
+                 theta_decay=1.0):
         self.levels = []
         self.smoother, self.cheb_deg = smoother, cheb_deg
         A = A.tocsr()
         while A.shape[0] > coarse_size and len(self.levels) < max_levels - 1:
-            P, R, Ac, rho = sa_level(A, theta)
+            P, R, Ac, rho = sa_level(A, theta * theta_decay ** len(self.levels), filtered=filtered, level=len(self.levels))
             if Ac.shape[0] >= 0.8 * A.shape[0]:
                 break
             self.levels.append(dict(A=A, P=P, R=R, dinv=1.0 / A.diagonal(), rho=rho))
@@ -155,3 +169,57 @@ class SAAMG:
     def complexity(self):
         nnz = [lv["A"].nnz for lv in self.levels] + [self.Ac.nnz]
         return sum(nnz) / nnz[0], [lv["A"].shape[0] for lv in self.levels] + [self.Ac.shape[0]]
+
+
+class SchurPC:
+    """CPU restatement of the product's charge-conservation Schur preconditioner (TEST INFRASTRUCTURE; the
+    reference has no counterpart -- it uses hypre on the block-diagonal P, KNPEMIx_solver.py:269-273).
+
+    The potential row of `a` (KNPEMIx_problem.py:603-610) is the z_k-weighted sum of the ion rows (:598-600) minus
+    sum_k z_k M c_k, so L A with L = [I 0; -Z I] has the block form [A_cc A_cphi; -Z M 0].  Its Schur complement
+    Z M A_cc^-1 A_cphi behaves like sum_k (z_k^2 cbar_k/psi) M at high and like the phi block of P at low
+    frequencies, hence  S~^-1 = (K_phi + (C_M/F) M_Gamma)^-1 + M_sigma^-1  (M_sigma lumped).  Application:
+        v = L r ;  z_c = AMG_c(v_c) ;  t = v_phi + M (sum_k z_k z_ck) ;  z_phi = AMG_phi(t) + t / M_sigma.
+    Everything is frozen at the state the oracle had when the object was built (the reference assembles P once)."""
+
+    def __init__(self, o, theta=0.08, smoother="jacobi", exact=False, **amg_kw):
+        p = o.p
+        self.o = o
+        ns = o.ns
+        self.ic = np.concatenate([np.arange(o.base[s], o.base[s] + 3 * ns[s]) for s in range(2)])
+        self.ip = np.concatenate([np.arange(o.base[s] + 3 * ns[s], o.base[s] + 4 * ns[s]) for s in range(2)])
+        Pt = o.assemble_P(membrane_sign=+1.0).tocsr()
+        Mm = o.assemble_P(membrane_sign=0.0, D_scale=0.0).tocsr()
+        self.M = [Mm[o.base[s]: o.base[s] + ns[s]][:, o.base[s]: o.base[s] + ns[s]].tocsr() for s in range(2)]
+        self.msig = []
+        for s in range(2):
+            sigma = sum(p.z[k] ** 2 / p.psi * o.c[s][k][o.S[s]] for k in range(3))
+            self.msig.append(sigma * np.asarray(self.M[s].sum(axis=1)).ravel())
+        Acc = Pt[self.ic][:, self.ic].tocsr()
+        App = Pt[self.ip][:, self.ip].tocsr()
+        if exact:
+            import scipy.sparse.linalg as spla
+            self.amg_c, self.amg_p = spla.splu(Acc.tocsc()).solve, spla.splu(App.tocsc()).solve
+        else:
+            self.amg_c = SAAMG(Acc, theta=theta, smoother=smoother, **amg_kw)
+            self.amg_p = SAAMG(App, theta=theta, smoother=smoother, **amg_kw)
+        self.z = np.asarray(p.z, float)
+
+    def __call__(self, r):
+        o, ns = self.o, self.o.ns
+        vc = r[self.ic]
+        zc = self.amg_c(vc)
+        t = []
+        off = 0
+        for s in range(2):
+            rc = vc[off: off + 3 * ns[s]].reshape(3, ns[s])
+            zz = zc[off: off + 3 * ns[s]].reshape(3, ns[s])
+            rphi = r[o.base[s] + 3 * ns[s]: o.base[s] + 4 * ns[s]]
+            t.append(rphi - self.z @ rc + self.M[s] @ (self.z @ zz))
+            off += 3 * ns[s]
+        t = np.concatenate(t)
+        zp = self.amg_p(t) + t / np.concatenate(self.msig)
+        out = np.empty_like(r)
+        out[self.ic] = zc
+        out[self.ip] = zp
+        return out

@@ -371,8 +371,10 @@ class KNPEMIOracle:
         A.sort_indices()
         return A, b
 
-    def assemble_P(self):
-        """Block-Jacobi preconditioner form (KNPEMIx_problem.py:717-738), from the current fields."""
+    def assemble_P(self, membrane_sign=-1.0, D_scale=1.0):
+        """Block-Jacobi preconditioner form (KNPEMIx_problem.py:717-738), from the current fields.
+        membrane_sign=+1 / D_scale=0 give the two auxiliary matrices of the product's own Schur preconditioner
+        (oracle/amg.py::SchurPC): the phi blocks with the sign the membrane term has in `a`, and the mass matrices."""
         p, m = self.p, self.mesh
         psi = p.psi
         rows, cols, vals = [], [], []
@@ -390,15 +392,15 @@ class KNPEMIOracle:
             Kphi = np.zeros_like(K)
             for k in range(3):
                 Rk = self.row(s, k, cells)
-                add(Rk[:, :, None], Rk[:, None, :], M + p.dt * p.D[k] * K)
-                Kphi = Kphi + (p.dt * p.D[k] * p.z[k] ** 2 / psi) * cbar[k][:, None, None] * K
+                add(Rk[:, :, None], Rk[:, None, :], M + (D_scale * p.dt * p.D[k]) * K)
+                Kphi = Kphi + (D_scale * p.dt * p.D[k] * p.z[k] ** 2 / psi) * cbar[k][:, None, None] * K
             add(Rphi[:, :, None], Rphi[:, None, :], Kphi)
         NN = np.einsum("qa,qb->qab", self.qb, self.qb)
         G1 = np.einsum("fq,qab->fab", self.farea[:, None] * self.qw[None, :], NN)
         fv = m.mf_verts
         for s in range(2):
             Rp = self.row(s, 3, fv)
-            add(Rp[:, :, None], Rp[:, None, :], -(p.C_M / p.F) * G1)
+            add(Rp[:, :, None], Rp[:, None, :], membrane_sign * (p.C_M / p.F) * G1)
         P = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))),
                           shape=(self.n, self.n)).tocsr()
         P.sum_duplicates()

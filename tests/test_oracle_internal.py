@@ -158,3 +158,43 @@ def test_gate_update_closed_form():
     an = 0.01e3 * (10 - V) / (np.exp((10 - V) / 10) - 1); bn = 0.125e3 * np.exp(-V / 80)
     yinf, tau = an / (an + bn), 1 / (an + bn)
     np.testing.assert_allclose(o.gates[0], yinf + (g0[0] - yinf) * np.exp(-o.p.dt / tau), rtol=1e-12)
+
+
+def test_charge_conservation_row_operation_and_schur_pc():
+    """The identity the product's Schur preconditioner rests on: (phi row) - sum_k z_k (ion row k) = -sum_k z_k M c_k,
+    i.e. L A has a vanishing (phi, phi) block and a static mass-matrix (phi, c) block; and GMRES preconditioned with
+    oracle/amg.py::SchurPC reaches the sparse-LU solution of a transient step in a few dozen iterations."""
+    import scipy.sparse as sp
+    from oracle.amg import SchurPC
+    o = KNPEMIOracle(unit_square(16), OracleParams(), MODELS_TEST)
+    rng = np.random.default_rng(2)
+    for s in range(2):
+        o.c[s] *= 1 + 0.05 * rng.random(o.c[s].shape)
+    o.phi[0] += 0.004 * rng.standard_normal(o.phi[0].shape)
+    o.phi_m = o.phi[0] - o.phi[1]
+    pc = SchurPC(o)
+    A, b = o.assemble(o.p.dt)
+    n = o.n
+    rows, cols, vals = [], [], []
+    for s in range(2):
+        q = np.arange(o.ns[s])
+        for k in range(3):
+            rows.append(o.base[s] + 3 * o.ns[s] + q); cols.append(o.base[s] + k * o.ns[s] + q)
+            vals.append(np.full(o.ns[s], -o.p.z[k]))
+    L = sp.identity(n) + sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n))
+    LA = (L @ A).tocsr()
+    App = A[pc.ip][:, pc.ip]
+    assert abs(LA[pc.ip][:, pc.ip]).max() < 1e-12 * abs(App).max()
+    Bpc = LA[pc.ip][:, pc.ic].tocsr()
+    Mz = sp.bmat([[sp.hstack([-o.p.z[k] * pc.M[0] for k in range(3)]), None],
+                  [None, sp.hstack([-o.p.z[k] * pc.M[1] for k in range(3)])]]).tocsr()
+    assert abs(Bpc - Mz).max() < 1e-9 * abs(Mz).max()       # cancellation against dt D_k K (1e5 larger) costs ~5 digits
+    ns = o.nullspace()
+    b = b - ns * (ns @ b)
+    x, its = o.solve_gmres(A, b, o.pack(), ns, pc, 1e-10)
+    xd = o.solve_direct(A, b, ns)
+    assert its < 60
+    for s in range(2):
+        for f in range(3):
+            sl = slice(o.base[s] + f * o.ns[s], o.base[s] + (f + 1) * o.ns[s])
+            assert np.linalg.norm(x[sl] - xd[sl]) <= 1e-8 * np.linalg.norm(xd[sl])
