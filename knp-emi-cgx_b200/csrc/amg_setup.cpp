@@ -251,7 +251,7 @@ static int dense_inverse(int n, std::vector<double>& M, std::vector<double>& inv
 
 int amg_setup_host(const CsrHost& A0, double theta, int coarse_size, int max_levels, std::vector<CsrHost>& As,
                    std::vector<CsrHost>& Ps, std::vector<CsrHost>& Rs, std::vector<double>& rhos,
-                   std::vector<double>& coarse_inv) {
+                   std::vector<double>& coarse_inv, bool invert) {
   As.clear();
   Ps.clear();
   Rs.clear();
@@ -362,6 +362,10 @@ int amg_setup_host(const CsrHost& A0, double theta, int coarse_size, int max_lev
   std::vector<double> M((size_t)nc * nc, 0.0);
   for (int i = 0; i < nc; ++i)
     for (int j = Ac.indptr[i]; j < Ac.indptr[i + 1]; ++j) M[(size_t)i * nc + Ac.indices[j]] += Ac.vals[j];
+  if (!invert) {            // the caller inverts the dense coarsest operator on the device
+    coarse_inv.swap(M);
+    return KNP_OK;
+  }
   return dense_inverse(nc, M, coarse_inv);
 }
 

@@ -296,7 +296,9 @@ __device__ __forceinline__ void cell_geometry(const double (&x)[4][3], CellGeom<
 //            never passes through registers again; b_k = sum_e m_e c_k(e) is a fixed-order segmented sum.
 // Every A value and b entry is written exactly once; index traffic is 1 byte per (node, cell, vertex).
 constexpr int ROWS_THREADS = 256;
-constexpr int ROWS_MIN_CTAS = 4;
+#ifndef ROWS_MIN_CTAS
+#define ROWS_MIN_CTAS 4
+#endif
 
 struct RowsSmem {       // computed on the host
   int tile;             // nodes per CTA = ROWS_THREADS / G

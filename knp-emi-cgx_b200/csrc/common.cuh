@@ -178,6 +178,8 @@ struct Amg {
   DevBuf<double> coarse_inv;          // dense n_c x n_c (row-major)
   DevBuf<double> cb, cx;
   int n_coarse = 0;
+  int gamma = 1;                      // cycle index on levels 1..gamma_last (1: V-cycle, 2: W-cycle below the finest level)
+  int gamma_last = 1 << 20;
   std::vector<CsrHost> hostA;         // kept for inspection
   ~Amg() {
     for (auto* l : levels) delete l;
@@ -186,6 +188,6 @@ struct Amg {
 
 int amg_setup_host(const CsrHost& A0, double theta, int coarse_size, int max_levels,
                    std::vector<CsrHost>& As, std::vector<CsrHost>& Ps, std::vector<CsrHost>& Rs,
-                   std::vector<double>& rhos, std::vector<double>& coarse_inv);
+                   std::vector<double>& rhos, std::vector<double>& coarse_inv, bool invert = true);
 
 }  // namespace knp

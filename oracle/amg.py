@@ -120,9 +120,10 @@ class SAAMG:
     """V(1,1)-cycle with weighted Jacobi (or Chebyshev) smoothing; dense inverse on the coarsest level."""
 
     def __init__(self, A, theta=0.08, max_levels=12, coarse_size=600, smoother="jacobi", cheb_deg=2, filtered=None,
-                 theta_decay=1.0):
+                 theta_decay=1.0, gamma=1, gamma_last=1 << 20):
         self.levels = []
         self.smoother, self.cheb_deg = smoother, cheb_deg
+        self.gamma, self.gamma_last = gamma, gamma_last   # cycle index on levels 1..gamma_last (2: W-cycle)
         A = A.tocsr()
         while A.shape[0] > coarse_size and len(self.levels) < max_levels - 1:
             P, R, Ac, rho = sa_level(A, theta * theta_decay ** len(self.levels), filtered=filtered, level=len(self.levels))
@@ -159,8 +160,9 @@ class SAAMG:
             return self.Ac_inv @ b
         lv = self.levels[lvl]
         x = self._smooth(lv, np.zeros_like(b), b)
-        rc = lv["R"] @ (b - lv["A"] @ x)
-        x = x + lv["P"] @ self.vcycle(rc, lvl + 1)
+        for _ in range(self.gamma if 1 <= lvl <= self.gamma_last else 1):
+            rc = lv["R"] @ (b - lv["A"] @ x)
+            x = x + lv["P"] @ self.vcycle(rc, lvl + 1)
         return self._smooth(lv, x, b)
 
     def __call__(self, b):
@@ -201,6 +203,9 @@ class SchurPC:
             import scipy.sparse.linalg as spla
             self.amg_c, self.amg_p = spla.splu(Acc.tocsc()).solve, spla.splu(App.tocsc()).solve
         else:
+            amg_kw.setdefault("gamma", 2)
+            amg_kw.setdefault("gamma_last", 3)
+            amg_kw.setdefault("coarse_size", 2500)      # dense coarsest solve (inverted on the device in the product)
             self.amg_c = SAAMG(Acc, theta=theta, smoother=smoother, **amg_kw)
             self.amg_p = SAAMG(App, theta=theta, smoother=smoother, **amg_kw)
         self.z = np.asarray(p.z, float)
