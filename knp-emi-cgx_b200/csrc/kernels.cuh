@@ -38,7 +38,8 @@ int launch_spmv(int n_rows, int64_t nnz, const int32_t* indptr, const int32_t* i
 // TMA-staged streaming SpMV over precomputed row blocks (falls back to launch_spmv when nblk <= 0)
 int build_rowblocks(const int32_t* indptr_host, int n_rows, std::vector<int32_t>& blk);
 int launch_spmv_stream(int nblk, const int32_t* rowblk, const int32_t* indptr, const int32_t* indices, const double* vals,
-                       const double* x, double* out, int epi, const double* b, const double* dinv, double w, cudaStream_t st);
+                       const double* x, double* out, int epi, const double* b, const double* dinv, double w, cudaStream_t st,
+                       double avg_row = 16.0);
 struct CsrView {
   int n_rows;
   int64_t nnz;

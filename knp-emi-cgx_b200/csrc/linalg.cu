@@ -111,7 +111,7 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
 }
 
 // blkinfo[blk] = {first row r0 (multiple of 4), number of rows, a4 = 4-aligned first non-zero, staged element count}
-template <int EPI>
+template <int EPI, int LANES>
 __global__ void __launch_bounds__(SPMV_THREADS) spmv_stream_kernel(int nblk, const int4* __restrict__ blkinfo,
                                                                     const int32_t* __restrict__ indptr,
                                                                     const int32_t* __restrict__ indices,
@@ -177,37 +177,30 @@ __global__ void __launch_bounds__(SPMV_THREADS) spmv_stream_kernel(int nblk, con
     }
     mbar_wait(&bar[s], (uint32_t)((it >> 1) & 1));
     __syncthreads();
-    // products, in place.  All gathers of a thread are issued before the first one is consumed (the in-place
-    // store would otherwise serialise them through possible shared-memory aliasing): memory-level parallelism 8-9.
-    {
-      constexpr int NI = (SPMV_CAP + SPMV_PAD + SPMV_THREADS - 1) / SPMV_THREADS;
-      double xv[NI];
-#pragma unroll
-      for (int i = 0; i < NI; ++i) {
-        const int j = tid + i * SPMV_THREADS;
-        const int col = j < n ? sc[j] : 0;
-        xv[i] = __ldg(x + col);
-      }
-#pragma unroll
-      for (int i = 0; i < NI; ++i) {
-        const int j = tid + i * SPMV_THREADS;
-        if (j < n) sv[j] *= xv[i];
-      }
-    }
-    __syncthreads();
-    // 8 lanes per row, fixed summation order (lane-strided partial sums, then a shuffle tree) -> rsum[]
-    const int sub = tid & 7;
-    for (int i0 = 0; i0 < nrows; i0 += SPMV_THREADS / 8) {
-      const int i = i0 + (tid >> 3);
+    // LANES lanes per row walk the staged row: lane l takes elements j0 + l, j0 + l + LANES, ... so that one warp-level
+    // gather touches the same stencil column of 32 / LANES consecutive rows -- neighbouring rows have neighbouring
+    // columns, i.e. the x gathers coalesce into a few cache lines.  Four gathers are in flight per lane; the partial
+    // sums are combined in a fixed order (bitwise reproducible, no atomics).
+    for (int i0 = 0; i0 < nrows; i0 += SPMV_THREADS / LANES) {
+      const int i = i0 + tid / LANES;
+      const int l = tid % LANES;
       double sum = 0.0;
       if (i < nrows) {
         const int j1 = rp[i + 1] - a4;
-        for (int j = rp[i] - a4 + sub; j < j1; j += 8) sum += sv[j];
+        int j = rp[i] - a4 + l;
+        for (; j + 3 * LANES < j1; j += 4 * LANES) {
+          const double x0 = __ldg(x + sc[j]), x1 = __ldg(x + sc[j + LANES]);
+          const double x2 = __ldg(x + sc[j + 2 * LANES]), x3 = __ldg(x + sc[j + 3 * LANES]);
+          sum += sv[j] * x0;
+          sum += sv[j + LANES] * x1;
+          sum += sv[j + 2 * LANES] * x2;
+          sum += sv[j + 3 * LANES] * x3;
+        }
+        for (; j < j1; j += LANES) sum += sv[j] * __ldg(x + sc[j]);
       }
-      sum += __shfl_down_sync(0xffffffffu, sum, 4, 8);
-      sum += __shfl_down_sync(0xffffffffu, sum, 2, 8);
-      sum += __shfl_down_sync(0xffffffffu, sum, 1, 8);
-      if (sub == 0 && i < nrows) rsum[i] = sum;
+#pragma unroll
+      for (int off = LANES >> 1; off > 0; off >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, off, LANES);
+      if (l == 0 && i < nrows) rsum[i] = sum;
     }
     __syncthreads();
     if (tid < nrows) {
@@ -248,28 +241,43 @@ int build_rowblocks(const int32_t* indptr, int n_rows, std::vector<int32_t>& inf
   return (int)(info.size() / 4);
 }
 
-int launch_spmv_stream(int nblk, const int32_t* blkinfo, const int32_t* indptr, const int32_t* indices, const double* vals,
-                       const double* x, double* out, int epi, const double* b, const double* dinv, double w, cudaStream_t st) {
-  if (nblk == 0) return KNP_OK;
+template <int LANES>
+static int launch_spmv_stream_l(int nblk, const int32_t* blkinfo, const int32_t* indptr, const int32_t* indices,
+                                const double* vals, const double* x, double* out, int epi, const double* b,
+                                const double* dinv, double w, cudaStream_t st) {
   const size_t smem = 2 * sizeof(SpmvStage) + 2 * sizeof(uint64_t);
   static bool configured = false;
   if (!configured) {
-    KNP_CUDA(cudaFuncSetAttribute(spmv_stream_kernel<EPI_SET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    KNP_CUDA(cudaFuncSetAttribute(spmv_stream_kernel<EPI_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    KNP_CUDA(cudaFuncSetAttribute(spmv_stream_kernel<EPI_JACOBI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    KNP_CUDA(cudaFuncSetAttribute(spmv_stream_kernel<EPI_ADD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    KNP_CUDA(cudaFuncSetAttribute(spmv_stream_kernel<EPI_SET, LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    KNP_CUDA(cudaFuncSetAttribute(spmv_stream_kernel<EPI_RESID, LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    KNP_CUDA(cudaFuncSetAttribute(spmv_stream_kernel<EPI_JACOBI, LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    KNP_CUDA(cudaFuncSetAttribute(spmv_stream_kernel<EPI_ADD, LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   const int grid = nblk < 148 * KNP_SPMV_CTAS ? nblk : 148 * KNP_SPMV_CTAS;   // persistent CTAs
   const int4* bi = reinterpret_cast<const int4*>(blkinfo);
   switch (epi) {
-    case EPI_SET: spmv_stream_kernel<EPI_SET><<<grid, SPMV_THREADS, smem, st>>>(nblk, bi, indptr, indices, vals, x, out, b, dinv, w); break;
-    case EPI_RESID: spmv_stream_kernel<EPI_RESID><<<grid, SPMV_THREADS, smem, st>>>(nblk, bi, indptr, indices, vals, x, out, b, dinv, w); break;
-    case EPI_JACOBI: spmv_stream_kernel<EPI_JACOBI><<<grid, SPMV_THREADS, smem, st>>>(nblk, bi, indptr, indices, vals, x, out, b, dinv, w); break;
-    default: spmv_stream_kernel<EPI_ADD><<<grid, SPMV_THREADS, smem, st>>>(nblk, bi, indptr, indices, vals, x, out, b, dinv, w); break;
+    case EPI_SET: spmv_stream_kernel<EPI_SET, LANES><<<grid, SPMV_THREADS, smem, st>>>(nblk, bi, indptr, indices, vals, x, out, b, dinv, w); break;
+    case EPI_RESID: spmv_stream_kernel<EPI_RESID, LANES><<<grid, SPMV_THREADS, smem, st>>>(nblk, bi, indptr, indices, vals, x, out, b, dinv, w); break;
+    case EPI_JACOBI: spmv_stream_kernel<EPI_JACOBI, LANES><<<grid, SPMV_THREADS, smem, st>>>(nblk, bi, indptr, indices, vals, x, out, b, dinv, w); break;
+    default: spmv_stream_kernel<EPI_ADD, LANES><<<grid, SPMV_THREADS, smem, st>>>(nblk, bi, indptr, indices, vals, x, out, b, dinv, w); break;
   }
   KNP_LAUNCHED();
   return KNP_OK;
+}
+
+int launch_spmv_stream(int nblk, const int32_t* blkinfo, const int32_t* indptr, const int32_t* indices, const double* vals,
+                       const double* x, double* out, int epi, const double* b, const double* dinv, double w, cudaStream_t st,
+                       double avg_row) {
+  if (nblk == 0) return KNP_OK;
+  static const int force = getenv("KNP_SPMV_LANES") ? atoi(getenv("KNP_SPMV_LANES")) : 0;
+  const int lanes = force ? force : (avg_row <= 10.0 ? 1 : avg_row <= 24.0 ? 2 : 4);
+  switch (lanes) {
+    case 1: return launch_spmv_stream_l<1>(nblk, blkinfo, indptr, indices, vals, x, out, epi, b, dinv, w, st);
+    case 2: return launch_spmv_stream_l<2>(nblk, blkinfo, indptr, indices, vals, x, out, epi, b, dinv, w, st);
+    case 4: return launch_spmv_stream_l<4>(nblk, blkinfo, indptr, indices, vals, x, out, epi, b, dinv, w, st);
+    default: return launch_spmv_stream_l<8>(nblk, blkinfo, indptr, indices, vals, x, out, epi, b, dinv, w, st);
+  }
 }
 
 template <int LANES>
@@ -312,7 +320,7 @@ int spmv(const CsrView& M, const double* x, double* out, int epi, const double* 
   static const int min_blk = getenv("KNP_SPMV_STREAM_MIN_BLK") ? atoi(getenv("KNP_SPMV_STREAM_MIN_BLK")) : 1;
   const double avg = M.n_rows > 0 ? (double)M.nnz / M.n_rows : 0.0;
   if (M.nblk >= min_blk && M.rowblk && aligned && avg >= min_avg)
-    return launch_spmv_stream(M.nblk, M.rowblk, M.indptr, M.indices, M.vals, x, out, epi, b, dinv, w, st);
+    return launch_spmv_stream(M.nblk, M.rowblk, M.indptr, M.indices, M.vals, x, out, epi, b, dinv, w, st, avg);
   return launch_spmv(M.n_rows, M.nnz, M.indptr, M.indices, M.vals, x, out, epi, b, dinv, w, st);
 }
 
