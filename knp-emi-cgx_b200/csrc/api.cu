@@ -8,6 +8,7 @@ using namespace knp;
 
 namespace knp {
 int nullspace_remove(knp_ctx* c, double* x, cudaStream_t st);
+void pc_graphs_clear(knp_ctx* c);
 }
 
 static cudaStream_t pick(knp_ctx* c, void* stream) { return stream ? (cudaStream_t)stream : c->stream; }
@@ -154,6 +155,7 @@ int knp_destroy(knp_ctx* c) {
   if (!c) return KNP_OK;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
+  pc_graphs_clear(c);
   if (c->comm) {
     void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
     if (h) {

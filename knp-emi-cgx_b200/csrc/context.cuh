@@ -41,6 +41,15 @@ struct knp_ctx {
   // charge-conservation Schur preconditioner (pc kind 3): hierarchies of the ion and of the potential blocks
   std::unique_ptr<knp::Amg> amg_c, amg_p;
   knp::DevBuf<double> M_vals, msig_inv, sch_vc, sch_zc, sch_t, sch_zp, sch_q, sch_rhs;
+  // CUDA graphs of the preconditioner application, keyed by the (r, z) pointer pair (single-GPU runs)
+  struct PcGraph {
+    const double* r;
+    double* z;
+    cudaGraphExec_t exec;
+    unsigned long long launches;
+  };
+  std::vector<PcGraph> pc_graphs;
+  int pc_applies = 0;
   // distributed
   ncclComm* comm = nullptr;
   int rank = 0, nranks = 1;

@@ -68,10 +68,10 @@ __global__ void __launch_bounds__(256) spmv_kernel(int n_rows, const int32_t* __
 // (memory-level parallelism 8 instead of 1), products are written back in place, and each row is summed by one thread in
 // a fixed order (bitwise reproducible, no atomics).
 #ifndef KNP_SPMV_CAP
-#define KNP_SPMV_CAP 2048
+#define KNP_SPMV_CAP 1280
 #endif
 #ifndef KNP_SPMV_CTAS
-#define KNP_SPMV_CTAS 4
+#define KNP_SPMV_CTAS 6
 #endif
 constexpr int SPMV_CAP = KNP_SPMV_CAP;
 constexpr int SPMV_THREADS = 256;

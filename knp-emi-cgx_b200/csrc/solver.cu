@@ -440,8 +440,11 @@ static int schur_apply(knp_ctx* c, const double* r, double* zout, cudaStream_t s
   return KNP_OK;
 }
 
+void pc_graphs_clear(knp_ctx* c);
+
 int pc_setup(knp_ctx* c, const knp_solve_opts* o) {
   const int n = c->T.L.n_rows;
+  pc_graphs_clear(c);
   c->amg.reset();
   c->amg_c.reset();
   c->amg_p.reset();
@@ -528,13 +531,49 @@ __global__ void dinv_mul_kernel(int n, const double* __restrict__ dinv, const do
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) z[i] = dinv[i] * r[i];
 }
 
+void pc_graphs_clear(knp_ctx* c) {
+  for (auto& g : c->pc_graphs) cudaGraphExecDestroy(g.exec);
+  c->pc_graphs.clear();
+  c->pc_applies = 0;
+}
+
+// The Schur application is ~200 small launches (W-cycle over two hierarchies): on one GPU it is captured once per
+// (r, z) pointer pair into a CUDA graph and replayed (GMRES always applies it to the same two buffers).
+static int schur_apply_graphed(knp_ctx* c, const double* r, double* z, cudaStream_t st) {
+  static const bool enabled = !(getenv("KNP_PC_GRAPH") && atoi(getenv("KNP_PC_GRAPH")) == 0);
+  if (!enabled || c->nranks > 1) return schur_apply(c, r, z, st);
+  for (auto& g : c->pc_graphs)
+    if (g.r == r && g.z == z) {
+      KNP_CUDA(cudaGraphLaunch(g.exec, st));
+      g_kernel_launches += g.launches;
+      return KNP_OK;
+    }
+  if (c->pc_applies++ < 1 || c->pc_graphs.size() >= 8) return schur_apply(c, r, z, st);   // first call warms up attributes
+  const unsigned long long l0 = g_kernel_launches;
+  KNP_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  const int rc = schur_apply(c, r, z, st);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(st, &graph);
+  if (rc != KNP_OK || e != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    if (rc == KNP_OK) set_error("CUDA graph capture of the preconditioner failed: %s", cudaGetErrorString(e));
+    return rc != KNP_OK ? rc : KNP_E_CUDA;
+  }
+  cudaGraphExec_t exec = nullptr;
+  KNP_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+  cudaGraphDestroy(graph);
+  c->pc_graphs.push_back({r, z, exec, g_kernel_launches - l0});
+  KNP_CUDA(cudaGraphLaunch(exec, st));
+  return KNP_OK;
+}
+
 int pc_apply(knp_ctx* c, const double* r, double* z, cudaStream_t st) {
   const int n = c->T.L.n_rows;
   if (c->pc_kind == 2 && c->amg) {
     KNP_TRY(vcycle(*c->amg, 0, r, z, st));
     return coarse_apply(c, r, z, st);
   }
-  if (c->pc_kind == 3 && c->amg_c && c->amg_p) return schur_apply(c, r, z, st);
+  if (c->pc_kind == 3 && c->amg_c && c->amg_p) return schur_apply_graphed(c, r, z, st);
   if (c->pc_kind == 1) {
     int grid = (n + 255) / 256;
     if (grid > 148 * 16) grid = 148 * 16;
