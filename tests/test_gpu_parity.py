@@ -347,7 +347,7 @@ def test_c2_iterative_solver_matches_oracle_per_timestep(kb, cfgdir, form):
                 scale = ref if f < 3 else max(ref, o.l2_norm(o.phi[0], 1))
                 assert abs(got - ref) <= 1e-8 * scale, (i, sd, f, got, ref)
     assert its_gpu == its_cpu
-    assert sum(its_gpu) / 10 <= (8.0 if form == "schur" else 4.0)   # the reference's hypre needs 3.0 (...iterative_solver.py:81)
+    assert sum(its_gpu) / 10 <= 4.0          # the reference's hypre needs 3.0 (tests/...iterative_solver.py:81); ours 3.1 / 3.3
 
 
 @pytest.mark.parametrize("name", ["square32", "cells2d", "cells3d"])
