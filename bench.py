@@ -186,6 +186,8 @@ def run_ours(args):
     p.solver_config["view_ksp"] = False
     s = kb.SolverKNPEMI(p, solver_config=p.solver_config)
     s.gmres_restart = args.restart
+    if args.amg_form:
+        s.amg_form = args.amg_form
     s.setup_solver()
     p.setup_preconditioner(True)
     ctx = s.ctx
@@ -199,7 +201,9 @@ def run_ours(args):
         comm.Barrier()
 
     for _ in range(args.warmup):
-        ctx.step(s.opts)
+        info = ctx.step(s.opts)
+        if rank == 0:
+            print(f"bench.py: warm-up step, {info.iterations} GMRES iterations", file=sys.stderr, flush=True)
     sampler = ClockSampler(local)
     u_start, g_start = ctx.get_state()          # the e2e leg below repeats exactly these K steps through host buffers
     t_start, i_start = ctx.get_time()
@@ -326,6 +330,7 @@ def main():
     ap.add_argument("--restart", type=int, default=30)
     ap.add_argument("--cpu-sample-n", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--amg-form", default=None, choices=["schur", "block_jacobi"], help="override SolverKNPEMI.amg_form")
     args = ap.parse_args()
     if args.warmup < 3:
         print("bench.py: warm-up raised to 3 (timing rules)", file=sys.stderr)

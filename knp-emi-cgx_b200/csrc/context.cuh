@@ -41,6 +41,17 @@ struct knp_ctx {
   // charge-conservation Schur preconditioner (pc kind 3): hierarchies of the ion and of the potential blocks
   std::unique_ptr<knp::Amg> amg_c, amg_p;
   knp::DevBuf<double> M_vals, msig_inv, sch_vc, sch_zc, sch_t, sch_zp, sch_q, sch_rhs;
+  knp::DevBuf<int32_t> sch_mblk[2];   // row blocks of the mass-matrix rows (s, field 0) for the streaming SpMV
+  int sch_nmblk[2] = {0, 0};
+  // multi-GPU: FIELD-parallel hierarchies.  The eight diagonal blocks of the preconditioner are independent, so every
+  // block (field) gets ONE global hierarchy on one rank; right-hand-side pieces travel to the owner over NVLink.
+  struct FieldPar {
+    bool on = false;
+    int owner[8] = {0, 0, 0, 0, 0, 0, 0, 0};        // field (s, f) -> rank, index 4 s + f
+    int64_t base[8] = {0, 0, 0, 0, 0, 0, 0, 0};     // offset of the field inside its owner's merged ion / potential vector
+    std::vector<int64_t> off[2];                    // per subdomain: prefix sums of the ranks' owned node counts
+    knp::DevBuf<double> gc_in, gc_out, gp_in, gp_out;
+  } fp;
   // CUDA graphs of the preconditioner application, keyed by the (r, z) pointer pair (single-GPU runs)
   struct PcGraph {
     const double* r;
@@ -71,6 +82,13 @@ struct knp_ctx {
 };
 
 namespace knp {
+struct P2POp {
+  int peer;
+  void* buf;
+  size_t bytes;
+  bool send;
+};
+int p2p_exchange(knp_ctx* c, const std::vector<P2POp>& ops, cudaStream_t st);
 int ensure_workspace(knp_ctx* c, int restart);
 int pc_setup(knp_ctx* c, const knp_solve_opts* o);
 int pc_apply(knp_ctx* c, const double* r, double* z, cudaStream_t st);

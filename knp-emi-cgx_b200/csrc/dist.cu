@@ -91,6 +91,22 @@ int halo_exchange(knp_ctx* c, double* x, cudaStream_t st) {
   return KNP_OK;
 }
 
+// grouped point-to-point transfers of raw device bytes (setup and the field-parallel preconditioner); transfers between
+// one pair of ranks are matched in the order of the list, so both sides must enumerate them identically
+int p2p_exchange(knp_ctx* c, const std::vector<P2POp>& ops, cudaStream_t st) {
+  if (ops.empty()) return KNP_OK;
+  NcclApi* api = nccl_api();
+  if (!api) return KNP_E_NCCL;
+  KNP_NCCL(api->GroupStart());
+  for (const P2POp& o : ops) {
+    if (o.bytes == 0) continue;
+    if (o.send) KNP_NCCL(api->Send(o.buf, o.bytes, ncclChar, o.peer, c->comm, st));
+    else KNP_NCCL(api->Recv(o.buf, o.bytes, ncclChar, o.peer, c->comm, st));
+  }
+  KNP_NCCL(api->GroupEnd());
+  return KNP_OK;
+}
+
 int allreduce_sum(knp_ctx* c, double* buf, int n, cudaStream_t st) {
   if (c->nranks <= 1) return KNP_OK;
   NcclApi* api = nccl_api();

@@ -4,6 +4,7 @@
 // (KNPEMIx_solver.py:212-214,276-280,324-333,386-389,435; PETSc defaults restated in SURVEY.md Appendix F).
 // The preconditioner B is one V(1,1) cycle of our smoothed-aggregation hierarchy on P (amg_setup.cpp),
 // Jacobi on P, or the identity.
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include "context.cuh"
@@ -327,6 +328,205 @@ __global__ void schur_merge_kernel(Layout L, const double* __restrict__ zc, cons
   }
 }
 
+// ---- multi-GPU: field-parallel hierarchies ---------------------------------------------------------------------
+// Processor-local hierarchies (block Jacobi over the ranks) ruin the Schur form: the truncated ion solves are wrong
+// near every rank boundary and GMRES needs 10-100x the iterations (2100 on 8 GPUs).  The eight diagonal blocks of the
+// preconditioner are independent problems, so instead of cutting every block into nranks pieces, every block gets ONE
+// global smoothed-aggregation hierarchy on ONE rank (ion fields round-robin, the two potential fields on the last
+// ranks): the preconditioner is then the same operator as on a single GPU, independent of the partition.  Per
+// application every rank ships its piece of each right-hand side to the field's owner and gets its piece of the result
+// back (grouped ncclSend/ncclRecv over NVLink, 2 x 8 B per dof).
+static int field_owner(int nranks, int s, int f) {
+  return f < 3 ? (3 * s + f) % nranks : (6 + s) % nranks;
+}
+
+static int schur_setup_fieldpar(knp_ctx* c, const std::vector<int32_t>& idx, const std::vector<double>& val) {
+  const Layout& L = c->T.L;
+  const int R = c->nranks, me = c->rank;
+  cudaStream_t st = c->stream;
+  knp_ctx::FieldPar& F = c->fp;
+  const std::vector<int32_t>& ip = c->H.indptr_P;
+  // owned node counts of every rank and nnz of every (rank, field) piece
+  std::vector<double> tab((size_t)R * 10, 0.0);
+  for (int s = 0; s < 2; ++s) tab[(size_t)me * 10 + s] = L.n_own[s];
+  for (int s = 0; s < 2; ++s)
+    for (int f = 0; f < 4; ++f)
+      tab[(size_t)me * 10 + 2 + 4 * s + f] = L.n_own[s] ? (double)(ip[L.row(s, f, 0) + L.n_own[s]] - ip[L.row(s, f, 0)]) : 0.0;
+  {
+    DevBuf<double> d;
+    KNP_TRY(d.upload(tab));
+    KNP_TRY(allreduce_sum(c, d.p, (int)tab.size(), st));
+    KNP_CUDA(cudaMemcpyAsync(tab.data(), d.p, tab.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    KNP_CUDA(cudaStreamSynchronize(st));
+  }
+  auto nown = [&](int r, int s) { return (int64_t)tab[(size_t)r * 10 + s]; };
+  auto pnnz = [&](int r, int fld) { return (int64_t)tab[(size_t)r * 10 + 2 + fld]; };
+  for (int s = 0; s < 2; ++s) {
+    F.off[s].assign(R + 1, 0);
+    for (int r = 0; r < R; ++r) F.off[s][r + 1] = F.off[s][r] + nown(r, s);
+    KNP_CHECK(F.off[s][R] < ((int64_t)1 << 31), "global field too large for int32 columns");
+  }
+  // global node ids of the ghost columns: one halo exchange of an id vector (field-0 slots)
+  std::vector<double> ids(L.n_cols, 0.0);
+  for (int s = 0; s < 2; ++s)
+    for (int p = 0; p < L.n_own[s]; ++p) ids[L.col(s, 0, p)] = (double)(F.off[s][me] + p);
+  {
+    DevBuf<double> d;
+    KNP_TRY(d.upload(ids));
+    KNP_TRY(halo_exchange(c, d.p, st));
+    KNP_CUDA(cudaMemcpyAsync(ids.data(), d.p, ids.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    KNP_CUDA(cudaStreamSynchronize(st));
+  }
+  // my piece of every field: row lengths, GLOBAL columns, values
+  int64_t c_size = 0, p_size = 0;
+  for (int s = 0; s < 2; ++s)
+    for (int f = 0; f < 4; ++f) {
+      const int fld = 4 * s + f;
+      F.owner[fld] = field_owner(R, s, f);
+      if (F.owner[fld] == me) {
+        int64_t& acc = f < 3 ? c_size : p_size;
+        F.base[fld] = acc;
+        acc += F.off[s][R];
+      }
+    }
+  struct Piece {
+    std::vector<int32_t> len, col;
+    std::vector<double> val;
+  };
+  std::vector<Piece> mine(8);
+  for (int s = 0; s < 2; ++s)
+    for (int f = 0; f < 4; ++f) {
+      Piece& P = mine[4 * s + f];
+      const int n_s = L.n_own[s];
+      P.len.resize(n_s);
+      for (int p = 0; p < n_s; ++p) {
+        const int row = L.row(s, f, p);
+        P.len[p] = ip[row + 1] - ip[row];
+        for (int j = ip[row]; j < ip[row + 1]; ++j) {
+          // column (s, f, q) -> global node id of q through the field-0 slot of the id vector
+          const int cfull = idx[j];
+          const int q = cfull < L.n_rows ? cfull - L.row(s, f, 0) : (cfull - L.n_rows - L.gbase[s] - f * L.n_gh[s]) + n_s;
+          P.col.push_back((int32_t)ids[L.col(s, 0, q)]);
+          P.val.push_back(val[j]);
+        }
+      }
+    }
+  // ship the pieces to the owners (device staging; one grouped exchange)
+  std::vector<DevBuf<int32_t>> d_len(8), d_col(8);
+  std::vector<DevBuf<double>> d_val(8);
+  std::vector<std::vector<DevBuf<int32_t>>> r_len(8), r_col(8);
+  std::vector<std::vector<DevBuf<double>>> r_val(8);
+  std::vector<P2POp> ops;
+  for (int fld = 0; fld < 8; ++fld) {
+    const int s = fld >> 2, o = F.owner[fld];
+    if (o != me) {
+      KNP_TRY(d_len[fld].upload(mine[fld].len));
+      KNP_TRY(d_col[fld].upload(mine[fld].col));
+      KNP_TRY(d_val[fld].upload(mine[fld].val));
+      ops.push_back({o, d_len[fld].p, mine[fld].len.size() * 4, true});
+      ops.push_back({o, d_col[fld].p, mine[fld].col.size() * 4, true});
+      ops.push_back({o, d_val[fld].p, mine[fld].val.size() * 8, true});
+    } else {
+      r_len[fld] = std::vector<DevBuf<int32_t>>(R);
+      r_col[fld] = std::vector<DevBuf<int32_t>>(R);
+      r_val[fld] = std::vector<DevBuf<double>>(R);
+      for (int r = 0; r < R; ++r) {
+        if (r == me) continue;
+        KNP_TRY(r_len[fld][r].alloc((size_t)nown(r, s)));
+        KNP_TRY(r_col[fld][r].alloc((size_t)pnnz(r, fld)));
+        KNP_TRY(r_val[fld][r].alloc((size_t)pnnz(r, fld)));
+        ops.push_back({r, r_len[fld][r].p, (size_t)nown(r, s) * 4, false});
+        ops.push_back({r, r_col[fld][r].p, (size_t)pnnz(r, fld) * 4, false});
+        ops.push_back({r, r_val[fld][r].p, (size_t)pnnz(r, fld) * 8, false});
+      }
+    }
+  }
+  KNP_TRY(p2p_exchange(c, ops, st));
+  KNP_CUDA(cudaStreamSynchronize(st));
+  // merged global matrices of the fields this rank owns (block diagonal over the fields)
+  CsrHost Gc, Gp;
+  Gc.n_rows = Gc.n_cols = (int)c_size;
+  Gp.n_rows = Gp.n_cols = (int)p_size;
+  Gc.indptr.assign(1, 0);
+  Gp.indptr.assign(1, 0);
+  for (int pass = 0; pass < 2; ++pass)            // ion fields first, then the potential fields, each in base order
+    for (int fld = 0; fld < 8; ++fld) {
+      if (F.owner[fld] != me || ((fld & 3) < 3) != (pass == 0)) continue;
+      CsrHost& G = pass == 0 ? Gc : Gp;
+      const int s = fld >> 2;
+      KNP_CHECK((int64_t)G.indptr.size() - 1 == F.base[fld], "field-parallel layout mismatch");
+      for (int r = 0; r < R; ++r) {
+        std::vector<int32_t> len, col;
+        std::vector<double> v;
+        if (r == me) {
+          len.swap(mine[fld].len);
+          col.swap(mine[fld].col);
+          v.swap(mine[fld].val);
+        } else {
+          len.resize((size_t)nown(r, s));
+          col.resize((size_t)pnnz(r, fld));
+          v.resize((size_t)pnnz(r, fld));
+          if (!len.empty()) KNP_CUDA(cudaMemcpy(len.data(), r_len[fld][r].p, len.size() * 4, cudaMemcpyDeviceToHost));
+          if (!col.empty()) KNP_CUDA(cudaMemcpy(col.data(), r_col[fld][r].p, col.size() * 4, cudaMemcpyDeviceToHost));
+          if (!v.empty()) KNP_CUDA(cudaMemcpy(v.data(), r_val[fld][r].p, v.size() * 8, cudaMemcpyDeviceToHost));
+          r_len[fld][r].free();
+          r_col[fld][r].free();
+          r_val[fld][r].free();
+        }
+        size_t at = 0;
+        for (size_t p = 0; p < len.size(); ++p) {
+          // columns of one row sorted by global id (ghost columns interleave with owned ones)
+          std::vector<std::pair<int32_t, double>> row(len[p]);
+          for (int j = 0; j < len[p]; ++j, ++at) row[j] = {(int32_t)(col[at] + F.base[fld]), v[at]};
+          std::sort(row.begin(), row.end());
+          for (auto& e : row) {
+            G.indices.push_back(e.first);
+            G.vals.push_back(e.second);
+          }
+          G.indptr.push_back((int32_t)G.indices.size());
+        }
+      }
+    }
+  if (c_size > 0) KNP_TRY(build_amg(c, Gc, c->amg_c, 2500, true));
+  if (p_size > 0) KNP_TRY(build_amg(c, Gp, c->amg_p, 2500, true));
+  KNP_TRY(F.gc_in.alloc((size_t)c_size));
+  KNP_TRY(F.gc_out.alloc((size_t)c_size));
+  KNP_TRY(F.gp_in.alloc((size_t)p_size));
+  KNP_TRY(F.gp_out.alloc((size_t)p_size));
+  F.on = true;
+  return KNP_OK;
+}
+
+// moves the ranks' pieces of the given fields to the owners' merged vectors (to_owner) or the results back
+static int fieldpar_move(knp_ctx* c, bool ions, bool to_owner, double* local, double* merged, cudaStream_t st) {
+  const Layout& L = c->T.L;
+  knp_ctx::FieldPar& F = c->fp;
+  const int R = c->nranks, me = c->rank, n0 = L.n_own[0];
+  std::vector<P2POp> ops;
+  for (int fld = 0; fld < 8; ++fld) {
+    const int s = fld >> 2, f = fld & 3;
+    if ((f < 3) != ions) continue;
+    // my piece inside the compact local vector: ions [s=0: 3 n0 | s=1: 3 n1] field-major, potentials [n0 | n1]
+    double* piece = ions ? local + (s ? 3 * n0 : 0) + (size_t)f * L.n_own[s] : local + (s ? n0 : 0);
+    const size_t mine = (size_t)L.n_own[s] * 8;
+    const int o = F.owner[fld];
+    if (o != me) {
+      ops.push_back({o, piece, mine, to_owner});
+    } else {
+      for (int r = 0; r < R; ++r) {
+        double* at = merged + F.base[fld] + F.off[s][r];
+        const size_t bytes = (size_t)(F.off[s][r + 1] - F.off[s][r]) * 8;
+        if (r == me) {
+          if (bytes) KNP_CUDA(cudaMemcpyAsync(to_owner ? at : piece, to_owner ? piece : at, bytes, cudaMemcpyDeviceToDevice, st));
+        } else {
+          ops.push_back({r, at, bytes, !to_owner});
+        }
+      }
+    }
+  }
+  return p2p_exchange(c, ops, st);
+}
+
 static int schur_setup(knp_ctx* c) {
   const Layout& L = c->T.L;
   const int n = L.n_rows, n0 = L.n_own[0], n1 = L.n_own[1];
@@ -381,14 +581,23 @@ static int schur_setup(knp_ctx* c) {
     M.indptr.push_back((int32_t)M.indices.size());
   }
   // rows were visited in the order c(s=0), phi(s=0), c(s=1), phi(s=1) = ascending compact order in both parts
-  KNP_TRY(coarse_setup(c, idx, val));
-  KNP_TRY(build_amg(c, Acc, c->amg_c, 2500, true));
-  KNP_TRY(build_amg(c, App, c->amg_p, 2500, true));
+  c->fp.on = false;
+  if (c->nranks > 1) {
+    Acc = CsrHost();
+    App = CsrHost();
+    KNP_TRY(schur_setup_fieldpar(c, idx, val));
+  } else {
+    KNP_TRY(build_amg(c, Acc, c->amg_c, 2500, true));
+    KNP_TRY(build_amg(c, App, c->amg_p, 2500, true));
+  }
   // W-cycle on levels 1..3, V-cycle below: measured optimum on C3 (36 -> 15 iterations; deeper W recursion only adds
   // launch-bound visits of tiny levels)
-  c->amg_c->gamma = c->amg_p->gamma = 2;
-  c->amg_c->gamma_last = c->amg_p->gamma_last = 3;
-  if (const char* e = getenv("KNP_W_LEVELS")) c->amg_c->gamma_last = c->amg_p->gamma_last = atoi(e);
+  for (Amg* a : {c->amg_c.get(), c->amg_p.get()})
+    if (a) {
+      a->gamma = 2;
+      a->gamma_last = 3;
+      if (const char* e = getenv("KNP_W_LEVELS")) a->gamma_last = atoi(e);
+    }
   // lumped M_sigma = (sum_k z_k^2 c_k / psi) at the node  x  row sum of the mass matrix
   std::vector<double> msig_inv((size_t)n0 + n1);
   const double* z = c->kp.z;
@@ -402,6 +611,17 @@ static int schur_setup(knp_ctx* c) {
       msig_inv[(size_t)(s ? n0 : 0) + p] = 1.0 / (sig * ms);
     }
   KNP_TRY(c->msig_inv.upload(msig_inv));
+  // row blocks of the two mass-matrix row ranges (rows (s, 0, .) of the P pattern): TMA-staged SpMV on sub-ranges
+  for (int s = 0; s < 2; ++s) {
+    c->sch_nmblk[s] = 0;
+    if (L.n_own[s] == 0) continue;
+    std::vector<int32_t> blk;
+    const int nb = build_rowblocks(ip.data() + L.row(s, 0, 0), L.n_own[s], blk);
+    if (nb > 0 && L.row(s, 0, 0) % 4 == 0) {
+      KNP_TRY(c->sch_mblk[s].upload(blk));
+      c->sch_nmblk[s] = nb;
+    }
+  }
   KNP_TRY(c->sch_vc.alloc((size_t)3 * (n0 + n1)));
   KNP_TRY(c->sch_zc.alloc((size_t)3 * (n0 + n1)));
   KNP_TRY(c->sch_t.alloc((size_t)n0 + n1));
@@ -421,7 +641,13 @@ static int schur_apply(knp_ctx* c, const double* r, double* zout, cudaStream_t s
   if (grid < 1) grid = 1;
   schur_split_kernel<<<grid, 256, 0, st>>>(L, z[0], z[1], z[2], r, c->sch_vc.p, c->sch_t.p);
   KNP_LAUNCHED();
-  KNP_TRY(vcycle(*c->amg_c, 0, c->sch_vc.p, c->sch_zc.p, st));
+  if (c->fp.on) {
+    KNP_TRY(fieldpar_move(c, true, true, c->sch_vc.p, c->fp.gc_in.p, st));
+    if (c->amg_c) KNP_TRY(vcycle(*c->amg_c, 0, c->fp.gc_in.p, c->fp.gc_out.p, st));
+    KNP_TRY(fieldpar_move(c, true, false, c->sch_zc.p, c->fp.gc_out.p, st));
+  } else {
+    KNP_TRY(vcycle(*c->amg_c, 0, c->sch_vc.p, c->sch_zc.p, st));
+  }
   schur_q_kernel<<<grid, 256, 0, st>>>(L, z[0], z[1], z[2], c->sch_zc.p, c->sch_q.p);
   KNP_LAUNCHED();
   KNP_TRY(halo_exchange(c, c->sch_q.p, st));
@@ -429,10 +655,21 @@ static int schur_apply(knp_ctx* c, const double* r, double* zout, cudaStream_t s
     if (L.n_own[s] == 0) continue;
     const int row0 = L.row(s, 0, 0);
     const int64_t nnz_s = (int64_t)c->H.indptr_P[row0 + L.n_own[s]] - c->H.indptr_P[row0];
-    KNP_TRY(launch_spmv(L.n_own[s], nnz_s, c->d_indptr_P.p + row0, c->d_indices_P.p, c->M_vals.p, c->sch_q.p,
-                        c->sch_t.p + (s ? n0 : 0), EPI_ADD, nullptr, nullptr, 0.0, st));
+    double* tout = c->sch_t.p + (s ? n0 : 0);
+    if (c->sch_nmblk[s] > 0 && ((uintptr_t)tout & 7u) == 0)
+      KNP_TRY(launch_spmv_stream(c->sch_nmblk[s], c->sch_mblk[s].p, c->d_indptr_P.p + row0, c->d_indices_P.p, c->M_vals.p,
+                                 c->sch_q.p, tout, EPI_ADD, nullptr, nullptr, 0.0, st, (double)nnz_s / L.n_own[s]));
+    else
+      KNP_TRY(launch_spmv(L.n_own[s], nnz_s, c->d_indptr_P.p + row0, c->d_indices_P.p, c->M_vals.p, c->sch_q.p, tout,
+                          EPI_ADD, nullptr, nullptr, 0.0, st));
   }
-  KNP_TRY(vcycle(*c->amg_p, 0, c->sch_t.p, c->sch_zp.p, st));
+  if (c->fp.on) {
+    KNP_TRY(fieldpar_move(c, false, true, c->sch_t.p, c->fp.gp_in.p, st));
+    if (c->amg_p) KNP_TRY(vcycle(*c->amg_p, 0, c->fp.gp_in.p, c->fp.gp_out.p, st));
+    KNP_TRY(fieldpar_move(c, false, false, c->sch_zp.p, c->fp.gp_out.p, st));
+  } else {
+    KNP_TRY(vcycle(*c->amg_p, 0, c->sch_t.p, c->sch_zp.p, st));
+  }
   schur_merge_kernel<<<grid, 256, 0, st>>>(L, c->sch_zc.p, c->sch_zp.p, c->sch_t.p, c->msig_inv.p, c->sch_vc.p, zout,
                                            c->cz_on ? c->sch_rhs.p : nullptr);
   KNP_LAUNCHED();
@@ -573,7 +810,7 @@ int pc_apply(knp_ctx* c, const double* r, double* z, cudaStream_t st) {
     KNP_TRY(vcycle(*c->amg, 0, r, z, st));
     return coarse_apply(c, r, z, st);
   }
-  if (c->pc_kind == 3 && c->amg_c && c->amg_p) return schur_apply_graphed(c, r, z, st);
+  if (c->pc_kind == 3 && (c->fp.on || (c->amg_c && c->amg_p))) return schur_apply_graphed(c, r, z, st);
   if (c->pc_kind == 1) {
     int grid = (n + 255) / 256;
     if (grid > 148 * 16) grid = 148 * 16;
