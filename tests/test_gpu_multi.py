@@ -17,3 +17,29 @@ def test_two_gpu_time_loop_matches_oracle():
                         "--master-addr", "127.0.0.1", "--master-port", "29531", worker],
                        capture_output=True, text=True, env=dict(os.environ, PYTHONPATH=ROOT), timeout=600)
     assert r.returncode == 0 and "MULTI_GPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_two_gpu_3d_time_loop_equals_single_gpu():
+    """BASELINE config C4 in miniature (3D, passive membrane): the field-parallel preconditioner is the same operator
+    for every partition, so a 2-GPU run needs the same GMRES iterations as a 1-GPU run and the per-field norms agree
+    to solver tolerance."""
+    import re
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = os.path.join(ROOT, "scripts", "dist_c4.py")
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    outs = []
+    for cmd in ([sys.executable, script, "16", "3"],
+                [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                 "127.0.0.1", "--master-port", "29533", script, "16", "3"]):
+        r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+        its = re.search(r"iterations (\[[^\]]*\])", r.stdout).group(1)
+        norms = [float(v) for v in re.search(r"norms (.*)", r.stdout).group(1).split()]
+        outs.append((its, norms))
+    assert outs[0][0] == outs[1][0], outs
+    scale = max(outs[0][1][3], outs[0][1][7])
+    for k, (a, b) in enumerate(zip(outs[0][1], outs[1][1])):
+        ref = a if k % 4 != 3 else max(a, scale)          # potentials relative to the potential scale
+        assert abs(a - b) <= 1e-6 * ref, (k, a, b)
