@@ -468,3 +468,56 @@ def test_3d_passive_time_loop_matches_oracle(kb):
                 sl = slice(o.base[s] + f * o.ns[s], o.base[s] + (f + 1) * o.ns[s])
                 assert np.linalg.norm(u[sl] - x[sl]) <= 1e-8 * np.linalg.norm(x[sl])
     ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------- full BASELINE sizes
+@pytest.mark.parametrize("which", ["c3_2d_n2048", "c4_3d_n120"])
+def test_full_size_properties(kb, cfgdir, which):
+    """Size-independent properties at the BASELINE sizes the oracle cannot reach (16.9 M / 7.4 M unknowns):
+    the potential constants are in the kernel of A (KNPEMIx_solver.py:327), the mass part of the ion rows integrates
+    the subdomain measures exactly (sum of the rows of A applied to c = 1 equals |Omega_s|), and two assemblies are
+    bitwise identical (no atomics)."""
+    import torch
+    if which.startswith("c3"):
+        cfg, gdim, models = os.path.join(cfgdir, "c3_square2048_cells64.yaml"), 2, None
+    else:
+        cfg, gdim, models = os.path.join(cfgdir, "c4_cube120_cells64_passive.yaml"), 3, "passive"
+    p = kb.ProblemKNPEMI(cfg, verbose=False)
+    p.set_initial_conditions()
+    p.init_ionic_models([kb.PassiveModel(p)] if models else [kb.NeuronalCotransporters(p), kb.HodgkinHuxley(p), kb.ATPPump(p)])
+    p.setup_variational_form()
+    ctx = p._ctx
+    sz = ctx.sizes
+    n0, n1 = sz.n_own[0], sz.n_own[1]
+    ctx.assemble(float(p.dt.value))
+    A1, b1, _ = ctx.values_host()
+    ctx.assemble(float(p.dt.value))
+    A2, b2, _ = ctx.values_host()
+    assert np.array_equal(A1, A2) and np.array_equal(b1, b2)
+    del A2, b2
+    x = torch.zeros(ctx.n_cols, dtype=torch.float64, device="cuda")
+    y = torch.empty(ctx.n_rows, dtype=torch.float64, device="cuda")
+    # nullspace: phi_i = phi_e = 1
+    x[3 * n0:4 * n0] = 1.0
+    x[4 * n0 + 3 * n1:4 * n0 + 4 * n1] = 1.0
+    torch.cuda.synchronize()
+    ctx.spmv(x.data_ptr(), y.data_ptr())
+    ctx.to_host(y.data_ptr(), 1)
+    assert y.abs().max().item() < 1e-20
+    # measures: c_k = 1 everywhere, phi = 0 -> sum over the rows of ion block (s, k) = |Omega_s| (stiffness rows sum to 0)
+    x.zero_()
+    x[:3 * n0] = 1.0
+    x[4 * n0:4 * n0 + 3 * n1] = 1.0
+    torch.cuda.synchronize()
+    ctx.spmv(x.data_ptr(), y.data_ptr())
+    ctx.to_host(y.data_ptr(), 1)
+    m = p.mesh                                   # subdomain measures from the mesh arrays (host, independent of the device)
+    xc = m.x[m.cells]
+    vol = np.abs(np.linalg.det(xc[:, 1:] - xc[:, :1])) / (2.0 if gdim == 2 else 6.0)
+    intra = np.isin(m.cell_tags, np.asarray(m.intra_tags))
+    meas = [float(vol[intra].sum()), float(vol[m.cell_tags == m.extra_tag].sum())]
+    for s, (lo, n_s) in enumerate(((0, n0), (4 * n0, n1))):
+        for k in range(3):
+            tot = y[lo + k * n_s: lo + (k + 1) * n_s].sum().item()
+            assert abs(tot - meas[s]) <= 1e-9 * meas[s], (s, k, tot, meas[s])
+    ctx.close()
