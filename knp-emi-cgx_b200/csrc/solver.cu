@@ -279,7 +279,7 @@ static int build_amg(knp_ctx* c, const CsrHost& A0, std::unique_ptr<Amg>& out, i
 //      v = L r ;  z_c = AMG_c(v_c) ;  t = v_phi + M (sum_k z_k z_ck) ;  z_phi = AMG_phi(t) + t / M_sigma.
 // Unlike the block-Jacobi form P of the reference (KNPEMIx_problem.py:657-744) no cancellation between the c and phi
 // blocks has to be resolved by the inexact block solves: 20-30 GMRES iterations instead of 100-1500 on transient
-// states (scripts/pc_experiment.py).  oracle/amg.py::SchurPC restates it for the tests.
+// states (tests/experiments/pc_experiment.py).  oracle/amg.py::SchurPC restates it for the tests.
 __global__ void schur_split_kernel(Layout L, double z0, double z1, double z2, const double* __restrict__ r,
                                    double* __restrict__ vc, double* __restrict__ t) {
   const int n0 = L.n_own[0], n1 = L.n_own[1];

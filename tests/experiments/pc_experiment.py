@@ -1,8 +1,8 @@
-"""Design experiment (CPU, oracle-side): GMRES iteration counts of candidate preconditioners on the perturbed C3
+"""Design experiment (CPU, oracle-side; lives under tests/ because only test infrastructure may import oracle/): GMRES iteration counts of candidate preconditioners on the perturbed C3
 workload.  Not product code; its output motivates the Schur-complement preconditioner documented in DESIGN.md."""
 import sys, os, time
 import numpy as np, scipy.sparse as sp, scipy.sparse.linalg as spla
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import cgx_b200 as kb
 from oracle.fixtures import from_arrays
 from oracle.knpemi import KNPEMIOracle, OracleParams
