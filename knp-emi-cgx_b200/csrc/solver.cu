@@ -332,12 +332,32 @@ __global__ void schur_merge_kernel(Layout L, const double* __restrict__ zc, cons
 // Processor-local hierarchies (block Jacobi over the ranks) ruin the Schur form: the truncated ion solves are wrong
 // near every rank boundary and GMRES needs 10-100x the iterations (2100 on 8 GPUs).  The eight diagonal blocks of the
 // preconditioner are independent problems, so instead of cutting every block into nranks pieces, every block gets ONE
-// global smoothed-aggregation hierarchy on ONE rank (ion fields round-robin, the two potential fields on the last
-// ranks): the preconditioner is then the same operator as on a single GPU, independent of the partition.  Per
+// global smoothed-aggregation hierarchy on ONE rank (each stage balanced by field size): the preconditioner is then the same operator as on a single GPU, independent of the partition.  Per
 // application every rank ships its piece of each right-hand side to the field's owner and gets its piece of the result
 // back (grouped ncclSend/ncclRecv over NVLink, 2 x 8 B per dof).
-static int field_owner(int nranks, int s, int f) {
-  return f < 3 ? (3 * s + f) % nranks : (6 + s) % nranks;
+// Field -> rank: the two stages (ion fields, then potential fields) run one after the other, so each stage is balanced
+// on its own: longest-processing-time-first over the global field sizes (ECS fields are ~3x the ICS ones).
+static void assign_field_owners(int nranks, const int64_t size_s[2], int owner[8]) {
+  std::vector<int64_t> load(nranks, 0);
+  auto least = [&](int exclude) {
+    int best = -1;
+    for (int r = 0; r < nranks; ++r)
+      if (r != exclude && (best < 0 || load[r] < load[best])) best = r;
+    return best < 0 ? 0 : best;
+  };
+  const int big = size_s[1] >= size_s[0] ? 1 : 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    const int s = pass == 0 ? big : 1 - big;
+    for (int f = 0; f < 3; ++f) {
+      const int r = least(-1);
+      owner[4 * s + f] = r;
+      load[r] += size_s[s];
+    }
+  }
+  // potentials: the larger one on the rank with the least ion work, the other one on a different rank
+  const int r_big = least(-1);
+  owner[4 * big + 3] = r_big;
+  owner[4 * (1 - big) + 3] = nranks > 1 ? least(r_big) : r_big;
 }
 
 static int schur_setup_fieldpar(knp_ctx* c, const std::vector<int32_t>& idx, const std::vector<double>& val) {
@@ -379,10 +399,13 @@ static int schur_setup_fieldpar(knp_ctx* c, const std::vector<int32_t>& idx, con
   }
   // my piece of every field: row lengths, GLOBAL columns, values
   int64_t c_size = 0, p_size = 0;
+  {
+    const int64_t size_s[2] = {F.off[0][R], F.off[1][R]};
+    assign_field_owners(R, size_s, F.owner);
+  }
   for (int s = 0; s < 2; ++s)
     for (int f = 0; f < 4; ++f) {
       const int fld = 4 * s + f;
-      F.owner[fld] = field_owner(R, s, f);
       if (F.owner[fld] == me) {
         int64_t& acc = f < 3 ? c_size : p_size;
         F.base[fld] = acc;
