@@ -1,6 +1,8 @@
 // extern "C" entry points of libknpemi_b200.so (see include/knpemi_b200.h for the reference call sites).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
+#include <string>
 #include <dlfcn.h>
 #include "context.cuh"
 
@@ -125,6 +127,21 @@ int knp_create(knp_ctx** out, const knp_mesh_desc* mesh, int device) {
   T.qw = c->d_qw.p;
   T.gpre = c->d_gpre.p;
   T.max_inc = H.max_inc;
+  T.Wp = (T.n_work + 31) / 32 * 32;
+  T.adjE = nullptr;
+  T.incE = nullptr;
+  T.geoK = T.mslot = T.kslot = nullptr;
+  const int nvv = H.gdim + 1;
+  const double ell_bytes = ((double)H.max_inc * (nvv * 8 + 4) + (double)H.max_deg * 20) * T.Wp;
+  if (getenv("KNP_ROWS") && std::string(getenv("KNP_ROWS")) == "ell" && T.n_work > 0 && ell_bytes < 24e9) {
+    // static geometry of the thread-per-dof row kernel: (nv max_inc + 2 max_deg) doubles per dof
+    KNP_TRY(c->d_adjE.alloc((size_t)H.max_deg * T.Wp));
+    KNP_TRY(c->d_incE.alloc((size_t)H.max_inc * T.Wp));
+    KNP_TRY(c->d_geoK.alloc((size_t)H.max_inc * nvv * T.Wp));
+    KNP_TRY(c->d_mslot.alloc((size_t)H.max_deg * T.Wp));
+    KNP_TRY(c->d_kslot.alloc((size_t)H.max_deg * T.Wp));
+    KNP_TRY(build_static_geometry(T, H.max_deg, c->d_adjE.p, c->d_incE.p, c->d_geoK.p, c->d_mslot.p, c->d_kslot.p, c->stream));
+  }
   // CSR column indices on the device
   KNP_TRY(c->d_indices.alloc(H.nnz));
   KNP_TRY(c->d_indices_P.alloc(H.nnz_P));

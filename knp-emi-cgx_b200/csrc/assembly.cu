@@ -17,6 +17,7 @@
 // "cell -> nnz map" collapses to one byte per (node, cell, local vertex): the adjacency slot.
 #include <algorithm>
 #include <cstdlib>
+#include <string>
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -698,6 +699,293 @@ int launch_facets(const DevTopo& T, const KParams& P, const uint32_t* tag_models
   return KNP_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Row kernel, second form: ONE THREAD PER DOF over static, TMA-friendly geometry tables.
+//
+// The mesh does not move, so everything geometric is computed once at setup (geo_build_kernel) and stored in
+// structure-of-arrays ELL tables whose leading dimension is the dof index (coalesced for a warp of 32 dofs):
+//   adjE[e][w]      neighbour of slot e                       incE[j][w]   packed slots of incident cell j
+//   geoK[j][b][w]   stiffness row of dof w in cell j          mslot/kslot[e][w]  assembled mass / stiffness per slot
+// Per timestep only the concentration-weighted stiffness X_k[e] = sum_j cbar_k(j) K_j[b(e)] depends on the solution.
+// A thread walks its dof's cells in ascending order (fixed order, no atomics), gathers the three concentrations of the
+// cell's vertices, and adds cbar_k K into its PRIVATE column of a shared-memory table (dynamic slot index, conflict-free
+// because the dof index is the fastest dimension).  The ten block rows are then formed field by field into a staging
+// strip at their CSR-relative offsets and leave through TMA bulk stores (two strips, ping-pong, so a store overlaps the
+// next field).  ~35 warp instructions per dof instead of ~245 for the lane-group kernel; the price is the static
+// tables (2D: +0.34 kB per dof of reads on top of 0.67 kB of algorithmic traffic).
+// MEASURED (B200, round 1): 2.54 ms on C3 and 5.96 ms on C4 against 1.75 / 3.17 ms for the lane-group kernel -- with
+// 0.5-1.2 kB of shared memory per thread only 12 (2D) / 4 (3D) warps fit an SM and the dependent incE -> adjE -> u
+// chain is latency-bound.  The kernel is therefore OPT-IN (KNP_ROWS=ell at context creation); it passes the same parity
+// tests and is kept as the starting point for a software-pipelined version.
+
+struct EllSmem {
+  int max_deg, max_inc, Wp;
+  int off_strip0, off_strip1;   // bytes
+  int total;
+};
+
+template <int D>
+__global__ void geo_build_kernel(DevTopo T, int Wp, int max_deg, int32_t* __restrict__ adjE, uint32_t* __restrict__ incE,
+                                 double* __restrict__ geoK, double* __restrict__ mslot, double* __restrict__ kslot) {
+  constexpr int NV = D + 1;
+  constexpr uint32_t VMASK = NV == 4 ? 0xFFFFFFFFu : 0x00FFFFFFu;
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= T.n_work) return;
+  const int s = w >= T.L.n_own[0] ? 1 : 0;
+  const int nodeoff = s ? T.L.n_loc[0] : 0;
+  const int a0 = T.adj_ptr[w], deg = T.adj_ptr[w + 1] - a0;
+  const int i0 = T.inc_ptr[w], ninc = T.inc_ptr[w + 1] - i0;
+  const int self = T.self_slot[w];
+  for (int e = 0; e < max_deg; ++e) {
+    adjE[(size_t)e * Wp + w] = e < deg ? T.adj_idx[a0 + e] : -1;
+    mslot[(size_t)e * Wp + w] = 0.0;
+    kslot[(size_t)e * Wp + w] = 0.0;
+  }
+  for (int j = 0; j < T.max_inc; ++j) {
+    if (j >= ninc) {
+      incE[(size_t)j * Wp + w] = 0xFFFFFFFFu;
+#pragma unroll
+      for (int b = 0; b < NV; ++b) geoK[((size_t)j * NV + b) * Wp + w] = 0.0;
+      continue;
+    }
+    const uint32_t pk = T.inc_slots[i0 + j];
+    incE[(size_t)j * Wp + w] = pk;
+    const int la = (__ffs(__vcmpeq4(pk, (uint32_t)self * 0x01010101u) & VMASK) - 1) >> 3;
+    double x[NV][D];
+#pragma unroll
+    for (int b = 0; b < NV; ++b) {
+      const int q = T.adj_idx[a0 + ((pk >> (8 * b)) & 255u)];
+#pragma unroll
+      for (int d = 0; d < D; ++d) x[b][d] = T.node_x[(size_t)(nodeoff + q) * D + d];
+    }
+    CellGeom<D> G;
+    cell_geometry(x, G);
+    double gl[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      double t = G.g[0][d];
+#pragma unroll
+      for (int a = 1; a < NV; ++a) t = (la == a) ? G.g[a][d] : t;
+      gl[d] = t;
+    }
+    const double mv = G.vol * (1.0 / ((D + 1) * (D + 2)));
+#pragma unroll
+    for (int b = 0; b < NV; ++b) {
+      double dot = 0.0;
+#pragma unroll
+      for (int d = 0; d < D; ++d) dot += gl[d] * G.g[b][d];
+      const double kab = G.vol * dot;
+      geoK[((size_t)j * NV + b) * Wp + w] = kab;
+      const int e = (pk >> (8 * b)) & 255u;
+      mslot[(size_t)e * Wp + w] += (b == la) ? 2.0 * mv : mv;
+      kslot[(size_t)e * Wp + w] += kab;
+    }
+  }
+}
+
+template <int D, int MODE, int TB>
+__global__ void __launch_bounds__(TB) rows_ell_kernel(DevTopo T, RowCoef C, const double* __restrict__ u,
+                                                               const double* __restrict__ fe,
+                                                               double* __restrict__ vals, double* __restrict__ bvec,
+                                                               EllSmem S, int nb0) {
+  constexpr int NV = D + 1;
+  constexpr int NS = D * (D + 1) / 2;
+  constexpr uint32_t FMASK = D == 3 ? 0x00FFFFFFu : 0x0000FFFFu;
+  extern __shared__ __align__(16) unsigned char smraw[];
+  double* X = reinterpret_cast<double*>(smraw);                 // [3][max_deg][TB], thread-private columns
+  double* strips[2] = {reinterpret_cast<double*>(smraw + S.off_strip0), reinterpret_cast<double*>(smraw + S.off_strip1)};
+  __shared__ int sh_base[4], sh_end[4];
+  const int tid = threadIdx.x;
+  const int s = blockIdx.x >= nb0 ? 1 : 0;
+  const int p0 = (blockIdx.x - (s ? nb0 : 0)) * TB;
+  const int n_own_s = T.L.n_own[s], n_gh_s = T.L.n_gh[s];
+  const int nt = min(TB, n_own_s - p0);
+  const int p = p0 + tid;
+  const bool active = tid < nt;
+  const int w = (s ? T.L.n_own[0] : 0) + p;
+  const int Wp = S.Wp, max_deg = S.max_deg;
+  const int* __restrict__ iptr = MODE == 0 ? T.indptr : T.indptr_P;
+  const double* __restrict__ u_own = u + T.L.rowbase[s];
+  const double* __restrict__ u_gh = u + T.L.n_rows + T.L.gbase[s] - n_own_s;
+
+  int deg = 0, gdeg = 0, g = -1, rs[4] = {0, 0, 0, 0};
+  if (active) {
+    deg = T.adj_ptr[w + 1] - T.adj_ptr[w];
+    g = T.mv_of_node[w];
+    if (MODE == 0) gdeg = T.gpre[w + 1] - T.gpre[w];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) rs[f] = iptr[T.L.row(s, f, p)];
+    if (tid == 0) {
+#pragma unroll
+      for (int f = 0; f < 4; ++f) sh_base[f] = rs[f];
+    }
+    if (tid == nt - 1) {
+#pragma unroll
+      for (int f = 0; f < 4; ++f) sh_end[f] = iptr[T.L.row(s, f, p) + 1];
+    }
+    for (int e = 0; e < deg; ++e) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) X[(size_t)(k * max_deg + e) * TB + tid] = 0.0;
+    }
+    // ---- X_k[e] += cbar_k(j) K_j[b]: cells in ascending order; the packed slots and the stiffness row of the next
+    //      cell are fetched (read-only path) while the current one is processed ----
+    const uint32_t* __restrict__ incE = T.incE;
+    const int32_t* __restrict__ adjE = T.adjE;
+    const double* __restrict__ geoK = T.geoK;
+    uint32_t pk = __ldg(incE + w);
+    double kb[NV];
+#pragma unroll
+    for (int b = 0; b < NV; ++b) kb[b] = __ldg(geoK + (size_t)b * Wp + w);
+    for (int j = 0; j < S.max_inc && pk != 0xFFFFFFFFu; ++j) {
+      uint32_t pk_n = 0xFFFFFFFFu;
+      double kb_n[NV];
+      if (j + 1 < S.max_inc) {
+        pk_n = __ldg(incE + (size_t)(j + 1) * Wp + w);
+#pragma unroll
+        for (int b = 0; b < NV; ++b) kb_n[b] = __ldg(geoK + ((size_t)(j + 1) * NV + b) * Wp + w);
+      }
+      int sl[NV], q[NV];
+#pragma unroll
+      for (int b = 0; b < NV; ++b) {
+        sl[b] = (pk >> (8 * b)) & 255u;
+        q[b] = __ldg(adjE + (size_t)sl[b] * Wp + w);
+      }
+      double cv[3][NV];
+#pragma unroll
+      for (int b = 0; b < NV; ++b) {
+        const double* __restrict__ uc = q[b] < n_own_s ? u_own + q[b] : u_gh + q[b];
+        const int fs = q[b] < n_own_s ? n_own_s : n_gh_s;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) cv[k][b] = __ldg(uc + (size_t)k * fs);
+      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        double cs = 0.0;
+#pragma unroll
+        for (int b = 0; b < NV; ++b) cs += cv[k][b];
+        const double cb = cs * (1.0 / NV);
+#pragma unroll
+        for (int b = 0; b < NV; ++b) X[(size_t)(k * max_deg + sl[b]) * TB + tid] += cb * kb[b];
+      }
+      pk = pk_n;
+#pragma unroll
+      for (int b = 0; b < NV; ++b) kb[b] = kb_n[b];
+    }
+  }
+  __syncthreads();
+
+  const size_t nf = (size_t)T.n_mf;
+  const double sgn = s == 0 ? 1.0 : -1.0;
+  const int m0 = g >= 0 ? T.minc_ptr[g] : 0, m1 = g >= 0 ? T.minc_ptr[g + 1] : 0;
+  const int goff = s == 1 ? gdeg : 0;
+#pragma unroll
+  for (int f = 0; f < 4; ++f) {
+    double* strip = strips[f & 1];
+    if (f >= 2) {                                   // the strip was last read by the bulk store of field f - 2
+      if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      __syncthreads();
+    }
+    const int base = sh_base[f], total = sh_end[f] - base, sh = base & 1;
+    if (active) {
+      double* o = strip + sh + (rs[f] - base);
+      double bsum = 0.0;
+      double m_n = f < 3 ? __ldg(T.mslot + w) : 0.0, k_n = (f < 3 || MODE == 0) ? __ldg(T.kslot + w) : 0.0;
+      int q_n = (f < 3 && MODE == 0) ? __ldg(T.adjE + w) : 0;
+      for (int e = 0; e < deg; ++e) {
+        double kphi_m = 0.0, pp_m = 0.0;
+        if (g >= 0) {      // membrane (dS) terms: KNPEMIx_problem.py:599,604,609-610,637-638 (P: :737-738)
+          const uint32_t rep = (uint32_t)e * 0x01010101u;
+          for (int mi = m0; mi < m1; ++mi) {
+            const uint4 rec = reinterpret_cast<const uint4*>(T.minc)[mi];
+            const uint32_t ss = s == 0 ? (rec.y >> 8) : rec.z;
+            const uint32_t ms = __vcmpeq4(ss, rep) & FMASK;
+            if (ms) {
+              const int fct = (int)rec.x, a = rec.y & 255u, b = (__ffs(ms) - 1) >> 3;
+              if (f < 3) {
+                if (MODE == 0) {
+                  const int ab = a <= b ? symidx(a, b, D) : symidx(b, a, D);
+                  kphi_m += C.cmz[f] * fe[(size_t)((s * 3 + f) * NS + ab) * nf + fct];
+                }
+              } else {
+                const double G1 = T.mf_area[fct] * ((a == b) ? 2.0 : 1.0) * (1.0 / (D * (D + 1)));
+                pp_m += (MODE == 0 ? C.cf : -C.cf) * G1;
+              }
+            }
+          }
+        }
+        const double m = m_n, kk = k_n;
+        const int q = q_n;
+        if (e + 1 < deg) {
+          const size_t at = (size_t)(e + 1) * Wp + w;
+          if (f < 3) m_n = __ldg(T.mslot + at);
+          if (f < 3 || MODE == 0) k_n = __ldg(T.kslot + at);
+          if (f < 3 && MODE == 0) q_n = __ldg(T.adjE + at);
+        }
+        if (f < 3) {
+          o[goff + e] = m + C.dtD[f] * kk;
+          if (MODE == 0) {
+            o[goff + deg + e] = C.cphi[f] * X[(size_t)(f * max_deg + e) * TB + tid] + kphi_m;
+            bsum += m * (q < n_own_s ? __ldg(u_own + (size_t)f * n_own_s + q) : __ldg(u_gh + (size_t)f * n_gh_s + q));
+          }
+        } else {
+          double pp = pp_m;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) pp += C.cpp[k] * X[(size_t)(k * max_deg + e) * TB + tid];
+          if (MODE == 0) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) o[goff + k * deg + e] = C.ck[k] * kk;
+            o[goff + 3 * deg + e] = pp;
+          } else {
+            o[e] = pp;
+          }
+        }
+      }
+      if (MODE == 0) {
+        double bm = 0.0;
+        if (g >= 0) {
+          // gamma entries (couplings to the potential on the other side of the membrane) and the membrane rhs
+          double* og = o + (s == 1 ? 0 : (f < 3 ? 2 : 4) * deg);
+          for (int eg = 0; eg < gdeg; ++eg) {
+            const uint32_t rep = (uint32_t)eg * 0x01010101u;
+            double acc = 0.0;
+            for (int mi = m0; mi < m1; ++mi) {
+              const uint4 rec = reinterpret_cast<const uint4*>(T.minc)[mi];
+              const uint32_t mg = __vcmpeq4(rec.w, rep) & FMASK;
+              if (mg) {
+                const int fct = (int)rec.x, a = rec.y & 255u, b = (__ffs(mg) - 1) >> 3;
+                if (f < 3) {
+                  const int ab = a <= b ? symidx(a, b, D) : symidx(b, a, D);
+                  acc += C.cmz[f] * fe[(size_t)((s * 3 + f) * NS + ab) * nf + fct];
+                } else {
+                  acc += C.cf * (T.mf_area[fct] * ((a == b) ? 2.0 : 1.0) * (1.0 / (D * (D + 1))));
+                }
+              }
+            }
+            og[eg] = -acc;
+          }
+          for (int mi = m0; mi < m1; ++mi) {
+            const uint4 rec = reinterpret_cast<const uint4*>(T.minc)[mi];
+            const int fct = (int)rec.x, a = rec.y & 255u;
+            bm -= sgn * (f < 3 ? fe[(size_t)(6 * NS + (s * 3 + f) * D + a) * nf + fct] : fe[(size_t)(6 * NS + 6 * D + a) * nf + fct]);
+          }
+        }
+        bvec[T.L.row(s, f, p)] = bsum + bm;
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      const int nbody = (total - sh) & ~1;
+      if (nbody > 0) bulk_store(vals + (size_t)base + sh, strip + 2 * sh, (uint32_t)nbody * 8u);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    } else if (tid == 32) {
+      if (sh && total > 0) vals[(size_t)base] = strip[1];
+      if ((total - sh) & 1) vals[(size_t)base + total - 1] = strip[sh + total - 1];
+    }
+  }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 // Lanes per node (power of two >= the largest degree) and the shared-memory layout of the row kernel.
 static int ceil_log2(int v) {
   int l = 0;
@@ -760,9 +1048,91 @@ static int launch_rows_t(const DevTopo& T, const KParams& P, const double* u, co
   return KNP_OK;
 }
 
+static EllSmem ell_layout(int mode, int max_deg, int max_gdeg, int max_inc, int Wp, int ELL_THREADS) {
+  EllSmem S{};
+  S.max_deg = max_deg;
+  S.max_inc = max_inc;
+  S.Wp = Wp;
+  const size_t x = (size_t)3 * max_deg * ELL_THREADS * 8;
+  // strip 0 serves fields 0 and 2 (ion rows), strip 1 fields 1 and 3 (the potential rows are the long ones)
+  const size_t ion = mode == 0 ? 2 * max_deg + max_gdeg : max_deg;
+  const size_t pot = mode == 0 ? 4 * max_deg + max_gdeg : max_deg;
+  const size_t s0 = ((size_t)ELL_THREADS * ion + 4) * 8, s1 = ((size_t)ELL_THREADS * std::max(ion, pot) + 4) * 8;
+  S.off_strip0 = (int)x;
+  S.off_strip1 = (int)(x + ((s0 + 15) & ~(size_t)15));
+  S.total = S.off_strip1 + (int)((s1 + 15) & ~(size_t)15);
+  return S;
+}
+
+// dofs per CTA: 128 when three CTAs fit an SM, else 64 (3D: the X table and the strips grow with the degree); 0 = use
+// the lane-group kernel
+static int ell_block(int mode, int max_deg, int max_gdeg, int max_inc, int Wp) {
+  if (ell_layout(mode, max_deg, max_gdeg, max_inc, Wp, 128).total <= 75 * 1024) return 128;
+  if (ell_layout(mode, max_deg, max_gdeg, max_inc, Wp, 64).total <= 110 * 1024) return 64;
+  return 0;
+}
+
+template <int D, int MODE, int TB>
+static int launch_rows_ell_t(const DevTopo& T, const KParams& P, const double* u, const double* fe, double* vals,
+                             double* b, int max_deg, int max_gdeg, cudaStream_t st) {
+  const EllSmem S = ell_layout(MODE, max_deg, max_gdeg, T.max_inc, T.Wp, TB);
+  static int configured = 0;
+  if (S.total > 48 * 1024 && S.total > configured) {
+    KNP_CUDA(cudaFuncSetAttribute(rows_ell_kernel<D, MODE, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, S.total));
+    configured = S.total;
+  }
+  RowCoef C;
+  for (int k = 0; k < 3; ++k) {
+    C.dtD[k] = P.dt * P.D[k];
+    C.cphi[k] = P.dt * P.D[k] * P.z[k] / P.psi;
+    C.cpp[k] = P.dt * P.D[k] * P.z[k] * P.z[k] / P.psi;
+    C.ck[k] = P.dt * P.z[k] * P.D[k];
+    C.cmz[k] = P.C_M / (P.F * P.z[k]);
+  }
+  C.cf = P.C_M / P.F;
+  const int nb0 = (T.L.n_own[0] + TB - 1) / TB, nb1 = (T.L.n_own[1] + TB - 1) / TB;
+  rows_ell_kernel<D, MODE, TB><<<nb0 + nb1, TB, S.total, st>>>(T, C, u, fe, vals, b, S, nb0);
+  KNP_LAUNCHED();
+  return KNP_OK;
+}
+
+template <int D, int MODE>
+static int launch_rows_ell(const DevTopo& T, const KParams& P, const double* u, const double* fe, double* vals,
+                           double* b, int max_deg, int max_gdeg, int tb, cudaStream_t st) {
+  return tb == 128 ? launch_rows_ell_t<D, MODE, 128>(T, P, u, fe, vals, b, max_deg, max_gdeg, st)
+                   : launch_rows_ell_t<D, MODE, 64>(T, P, u, fe, vals, b, max_deg, max_gdeg, st);
+}
+
+// static geometry tables of the ELL row kernel (setup, once per context)
+int build_static_geometry(DevTopo& T, int max_deg, int32_t* adjE, uint32_t* incE, double* geoK, double* mslot,
+                          double* kslot, cudaStream_t st) {
+  if (T.n_work == 0) return KNP_OK;
+  const int grid = (T.n_work + 127) / 128;
+  if (T.gdim == 2) geo_build_kernel<2><<<grid, 128, 0, st>>>(T, T.Wp, max_deg, adjE, incE, geoK, mslot, kslot);
+  else geo_build_kernel<3><<<grid, 128, 0, st>>>(T, T.Wp, max_deg, adjE, incE, geoK, mslot, kslot);
+  KNP_LAUNCHED();
+  T.adjE = adjE;
+  T.incE = incE;
+  T.geoK = geoK;
+  T.mslot = mslot;
+  T.kslot = kslot;
+  return KNP_OK;
+}
+
+static int rows_ell_block(const DevTopo& T, int mode, int max_deg, int max_gdeg) {
+  if (!T.adjE) return 0;        // static tables exist only when the context was created with KNP_ROWS=ell
+  return ell_block(mode, max_deg, max_gdeg, T.max_inc, T.Wp);
+}
+
 int launch_rows(const DevTopo& T, const KParams& P, int mode, const double* u, const double* fe, double* vals,
                 double* b, int max_deg, int max_gdeg, cudaStream_t st) {
   if (T.n_work == 0) return KNP_OK;
+  if (const int tb = rows_ell_block(T, mode, max_deg, max_gdeg)) {
+    if (T.gdim == 2) return mode == 0 ? launch_rows_ell<2, 0>(T, P, u, fe, vals, b, max_deg, max_gdeg, tb, st)
+                                      : launch_rows_ell<2, 1>(T, P, u, fe, vals, b, max_deg, max_gdeg, tb, st);
+    return mode == 0 ? launch_rows_ell<3, 0>(T, P, u, fe, vals, b, max_deg, max_gdeg, tb, st)
+                     : launch_rows_ell<3, 1>(T, P, u, fe, vals, b, max_deg, max_gdeg, tb, st);
+  }
   if (T.gdim == 2) return mode == 0 ? launch_rows_t<2, 0>(T, P, u, fe, vals, b, max_deg, max_gdeg, st)
                                     : launch_rows_t<2, 1>(T, P, u, fe, vals, b, max_deg, max_gdeg, st);
   return mode == 0 ? launch_rows_t<3, 0>(T, P, u, fe, vals, b, max_deg, max_gdeg, st)

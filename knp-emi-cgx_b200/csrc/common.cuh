@@ -139,6 +139,11 @@ struct DevTopo {
   const double *qb, *qw;
   const int32_t* gpre;       // per owned node: prefix of the gamma degree
   int max_inc;               // largest number of cells incident to one owned node
+  // static ELL tables of the thread-per-dof row kernel (leading dimension Wp = dofs rounded up to 32)
+  int Wp;
+  const int32_t* adjE;
+  const uint32_t* incE;
+  const double *geoK, *mslot, *kslot;
 };
 
 struct Params {
