@@ -179,6 +179,13 @@ int knp_get_time(const knp_ctx* ctx, double* t, int32_t* step_index);
 /* int u^2 dx over the owned share of cells of subdomain s with tag in tags (tests :45-51). */
 int knp_l2_norm_sq(knp_ctx* ctx, int32_t subdomain, int32_t field, int32_t n_tags, const int32_t* tags,
                    double* out);
+/* Conservation functionals of ProblemKNPEMI.print_conservation (KNPEMIx_problem.py:807-843): this rank's integral of
+   u^power (power 1: ion amount, power 0: measure of the tagged cells, power 2 = knp_l2_norm_sq) over the owned cells of
+   subdomain `subdomain` carrying one of `tags`; all-reduce the result over the ranks like the reference does. */
+int knp_integral(knp_ctx* ctx, int32_t subdomain, int32_t field, int32_t power, int32_t n_tags, const int32_t* tags,
+                 double* out);
+/* this rank's area of the membrane facets tagged `tag` (assemble_scalar(1*dS(tag)), KNPEMIx_problem.py:833-834) */
+int knp_membrane_area(const knp_ctx* ctx, int32_t tag, double* out);
 /* per-phase device timers of the last knp_step (ms): gate, facet, rows, solve, total */
 int knp_last_timings(const knp_ctx* ctx, double* ms5);
 

@@ -501,20 +501,39 @@ int knp_last_timings(const knp_ctx* c, double* ms5) {
   return KNP_OK;
 }
 
-int knp_l2_norm_sq(knp_ctx* c, int32_t s, int32_t field, int32_t n_tags, const int32_t* tags, double* out) {
+static int cell_functional(knp_ctx* c, int32_t s, int32_t field, int32_t power, int32_t n_tags, const int32_t* tags,
+                           double* out) {
   CTX_GUARD(c);
   KNP_CHECK(out && tags && n_tags > 0 && n_tags <= 4096, "bad tag list");
-  KNP_CHECK((s == 0 || s == 1) && field >= 0 && field < 4, "bad subdomain/field");
+  KNP_CHECK((s == 0 || s == 1) && field >= 0 && field < 4 && power >= 0 && power <= 2, "bad subdomain/field/power");
   const int nc = (int)c->H.cell_tag[s].size();
   cudaStream_t st = c->stream;
   KNP_CUDA(cudaMemcpyAsync(c->ftags.p, tags, n_tags * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   const int nb = 592;
-  KNP_TRY(launch_l2_cells(c->T.gdim, c->T.L, s, field, nc, c->d_cell_nodes[s].p, c->d_cell_tag[s].p,
+  KNP_TRY(launch_l2_cells(c->T.gdim, c->T.L, s, field, power, nc, c->d_cell_nodes[s].p, c->d_cell_tag[s].p,
                           c->d_cell_owned[s].p, c->d_node_x.p, s ? c->T.L.n_loc[0] : 0, c->ftags.p, n_tags, c->u.p,
                           c->fpartial.p, nb, st));
   KNP_TRY(launch_reduce_partials(c->fpartial.p, nb, c->fout.p, st));
   KNP_CUDA(cudaMemcpyAsync(out, c->fout.p, sizeof(double), cudaMemcpyDeviceToHost, st));
   KNP_CUDA(cudaStreamSynchronize(st));
+  return KNP_OK;
+}
+
+int knp_l2_norm_sq(knp_ctx* c, int32_t s, int32_t field, int32_t n_tags, const int32_t* tags, double* out) {
+  return cell_functional(c, s, field, 2, n_tags, tags, out);
+}
+
+int knp_integral(knp_ctx* c, int32_t s, int32_t field, int32_t power, int32_t n_tags, const int32_t* tags, double* out) {
+  return cell_functional(c, s, field, power, n_tags, tags, out);
+}
+
+int knp_membrane_area(const knp_ctx* c, int32_t tag, double* out) {
+  KNP_CHECK(c && out, "NULL argument");
+  const HostTopo& H = c->H;
+  double acc = 0.0;
+  for (int f = 0; f < H.n_mf; ++f)
+    if (H.mf_owned[f] && H.mtags[H.mf_tagidx[f]] == tag) acc += H.mf_area[f];
+  *out = acc;
   return KNP_OK;
 }
 

@@ -631,10 +631,11 @@ __global__ void csr_indices_kernel(DevTopo T, int32_t* __restrict__ indices) {
 }
 
 // ------------------------------------------------------------------------------------------------ functionals
-// int u^2 over cells (tests/KNPEMI/electric_potential_norms_direct_solver.py:45-51): per-block partial sums,
-// reduced in a fixed order by reduce_partials_kernel (linalg.cu).
+// Cell functionals over tagged cells: power 2 = int u^2 (tests/KNPEMI/electric_potential_norms_direct_solver.py:45-51),
+// power 1 = int u (ion amounts of ProblemKNPEMI.print_conservation, KNPEMIx_problem.py:807-843), power 0 = the measure of
+// the tagged cells; per-block partial sums, reduced in a fixed order by reduce_partials_kernel (linalg.cu).
 template <int D>
-__global__ void __launch_bounds__(256) l2_cells_kernel(Layout L, int s, int field, int n_cells,
+__global__ void __launch_bounds__(256) l2_cells_kernel(Layout L, int s, int field, int power, int n_cells,
                                                        const int32_t* __restrict__ cell_nodes,
                                                        const int32_t* __restrict__ cell_tag,
                                                        const int32_t* __restrict__ cell_owned,
@@ -666,7 +667,9 @@ __global__ void __launch_bounds__(256) l2_cells_kernel(Layout L, int s, int fiel
       s1 += uc[a];
       s2 += uc[a] * uc[a];
     }
-    acc += G.vol / ((D + 1) * (D + 2)) * (s2 + s1 * s1);
+    if (power == 2) acc += G.vol / ((D + 1) * (D + 2)) * (s2 + s1 * s1);
+    else if (power == 1) acc += G.vol * (s1 * (1.0 / NV));
+    else acc += G.vol;
   }
   red[threadIdx.x] = acc;
   __syncthreads();
@@ -1148,15 +1151,15 @@ int launch_csr_indices(const DevTopo& T, int mode, int32_t* indices, cudaStream_
   return KNP_OK;
 }
 
-int launch_l2_cells(int gdim, const Layout& L, int s, int field, int n_cells, const int32_t* cell_nodes,
+int launch_l2_cells(int gdim, const Layout& L, int s, int field, int power, int n_cells, const int32_t* cell_nodes,
                     const int32_t* cell_tag, const int32_t* cell_owned, const double* node_x, int nodeoff,
                     const int32_t* tags, int n_tags, const double* u, double* partial, int n_partial,
                     cudaStream_t st) {
   if (gdim == 2)
-    l2_cells_kernel<2><<<n_partial, 256, 0, st>>>(L, s, field, n_cells, cell_nodes, cell_tag, cell_owned, node_x,
+    l2_cells_kernel<2><<<n_partial, 256, 0, st>>>(L, s, field, power, n_cells, cell_nodes, cell_tag, cell_owned, node_x,
                                                   nodeoff, tags, n_tags, u, partial);
   else
-    l2_cells_kernel<3><<<n_partial, 256, 0, st>>>(L, s, field, n_cells, cell_nodes, cell_tag, cell_owned, node_x,
+    l2_cells_kernel<3><<<n_partial, 256, 0, st>>>(L, s, field, power, n_cells, cell_nodes, cell_tag, cell_owned, node_x,
                                                   nodeoff, tags, n_tags, u, partial);
   KNP_LAUNCHED();
   return KNP_OK;

@@ -26,7 +26,7 @@ int build_static_geometry(DevTopo& T, int max_deg, int32_t* adjE, uint32_t* incE
 int launch_rows(const DevTopo& T, const KParams& P, int mode, const double* u, const double* fe, double* vals,
                 double* b, int max_deg, int max_gdeg, cudaStream_t st);
 int launch_csr_indices(const DevTopo& T, int mode, int32_t* indices, cudaStream_t st);
-int launch_l2_cells(int gdim, const Layout& L, int s, int field, int n_cells, const int32_t* cell_nodes,
+int launch_l2_cells(int gdim, const Layout& L, int s, int field, int power, int n_cells, const int32_t* cell_nodes,
                     const int32_t* cell_tag, const int32_t* cell_owned, const double* node_x, int nodeoff,
                     const int32_t* tags, int n_tags, const double* u, double* partial, int n_partial,
                     cudaStream_t st);

@@ -65,7 +65,7 @@ SYMBOLS = [
     "knp_csr_P_host", "knp_dofmap_host", "knp_mverts_host", "knp_set_params", "knp_stimulus_area_local",
     "knp_set_state", "knp_get_state", "knp_state_dev", "knp_phi_m_host", "knp_gate_step", "knp_assemble",
     "knp_assemble_P", "knp_values_dev", "knp_spmv", "knp_pc_setup", "knp_pc_apply", "knp_solve", "knp_step",
-    "knp_step_host", "knp_set_time", "knp_get_time", "knp_l2_norm_sq", "knp_last_timings", "knp_amg_num_levels", "knp_amg_part_levels",
+    "knp_step_host", "knp_set_time", "knp_get_time", "knp_l2_norm_sq", "knp_integral", "knp_membrane_area", "knp_last_timings", "knp_amg_num_levels", "knp_amg_part_levels",
     "knp_copy", "knp_amg_level_sizes", "knp_amg_level_host", "knp_nccl_unique_id", "knp_dist_init", "knp_halo_exchange",
     "knp_allreduce_sum",
 ]
@@ -117,6 +117,8 @@ def load():
     lib.knp_set_time.argtypes = [vp, C.c_double, C.c_int32]
     lib.knp_get_time.argtypes = [vp, c_f64p, c_i32p]
     lib.knp_l2_norm_sq.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, vp, c_f64p]
+    lib.knp_integral.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, c_f64p]
+    lib.knp_membrane_area.argtypes = [vp, C.c_int32, c_f64p]
     lib.knp_last_timings.argtypes = [vp, vp]
     lib.knp_copy.argtypes = [vp, vp, vp, C.c_int64, C.c_int32]
     lib.knp_amg_num_levels.argtypes = [vp]
@@ -307,6 +309,18 @@ class Context:
         t, i = C.c_double(), C.c_int32()
         check(self._lib.knp_get_time(self.h, C.byref(t), C.byref(i)))
         return t.value, i.value
+
+    def integral(self, subdomain, field, tags, power=1):
+        """This rank's integral of u^power over the owned cells of `subdomain` tagged `tags` (power 0: their measure)."""
+        tags = np.ascontiguousarray(np.atleast_1d(tags), np.int32)
+        out = C.c_double()
+        check(self._lib.knp_integral(self.h, subdomain, field, power, tags.size, _ptr(tags), C.byref(out)))
+        return out.value
+
+    def membrane_area(self, tag):
+        out = C.c_double()
+        check(self._lib.knp_membrane_area(self.h, int(tag), C.byref(out)))
+        return out.value
 
     def l2_norm_sq(self, subdomain, field, tags):
         tags = np.ascontiguousarray(np.atleast_1d(tags), np.int32)

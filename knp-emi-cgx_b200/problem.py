@@ -643,3 +643,30 @@ class ProblemKNPEMI:
 
     def l2_norm(self, function, tags):
         return float(np.sqrt(self.comm.allreduce(self.l2_norm_squared(function, tags), op=MPI.SUM)))
+
+    def conservation(self):
+        """The numbers ProblemKNPEMI.print_conservation prints (KNPEMIx_problem.py:807-843), computed on the device:
+        total amount of every ion over both subdomains and, per intracellular tag, volume, membrane area and charge
+        (N_Na + N_K - N_Cl) F.  Returns {"totals": {ion: mol}, "cells": {tag: {"volume", "area", "charge"}}}."""
+        ctx = self._require_context()
+        red = lambda v: float(self.comm.allreduce(float(v), op=MPI.SUM))
+        itags, etag = list(self.intra_tags), [self.extra_tag[0]]
+        names = [ion["name"] if isinstance(ion, dict) and "name" in ion else n for ion, n in zip(self.ion_list, ("Na", "K", "Cl"))]
+        totals = {n: red(ctx.integral(0, k, itags) + ctx.integral(1, k, etag)) for k, n in enumerate(names)}
+        cells = {}
+        mtags = set(int(t) for t in np.atleast_1d(self.gamma_tags)) if hasattr(self, "gamma_tags") else set()
+        for tag in itags:
+            amount = [red(ctx.integral(0, k, [tag])) for k in range(3)]
+            cells[int(tag)] = {"volume": red(ctx.integral(0, 0, [tag], power=0)),
+                               "area": red(ctx.membrane_area(tag)) if (not mtags or int(tag) in mtags) else 0.0,
+                               "charge": (amount[0] + amount[1] - amount[2]) * float(self.F.value)}
+        return {"totals": totals, "cells": cells}
+
+    def print_conservation(self):
+        """KNPEMIx_problem.py:807-843."""
+        c = self.conservation()
+        self._print(f"Time {float(self.t.value) * 1e3:.2f} ms")
+        for n, label in zip(c["totals"], ("Na+", "K+ ", "Cl-")):
+            self._print(f"Total {label} concentration: {c['totals'][n]:.2e} mol")
+        for tag, v in c["cells"].items():
+            self._print(f"  Intra tag {tag}: Volume = {v['volume']:.2e} m^3, Area = {v['area']:.2e} m^2, Charge = {v['charge']:.2e} C")

@@ -544,6 +544,24 @@ class KNPEMIOracle:
         return its_all
 
     # -------------------------------------------------------------- functionals
+    def integral(self, u, tags, power=1):
+        """int u^power dx(tags) for a P1 field on all vertices: power 1 = the ion amounts of
+        ProblemKNPEMI.print_conservation (KNPEMIx_problem.py:807-843), power 0 = the measure of the tagged cells."""
+        m = self.mesh
+        d = m.gdim
+        sel = np.isin(m.cell_tags, np.atleast_1d(tags))
+        cells = m.cells[sel]
+        x = m.x[cells]
+        vol = np.abs(np.linalg.det(x[:, 1:] - x[:, :1])) / (2.0 if d == 2 else 6.0)
+        if power == 0:
+            return float(vol.sum())
+        if power == 1:
+            return float((vol * u[cells].mean(axis=1)).sum())
+        return self.l2_norm(u, tags) ** 2
+
+    def membrane_area(self, tag):
+        return float(self.farea[self.mesh.mf_tags == tag].sum())
+
     def l2_norm(self, u, tags):
         """sqrt(int u^2 dx(tags)) for a P1 field given on all vertices."""
         m = self.mesh

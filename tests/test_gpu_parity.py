@@ -470,6 +470,47 @@ def test_3d_passive_time_loop_matches_oracle(kb):
     ctx.close()
 
 
+@pytest.mark.parametrize("name", ["square32", "cells2d", "cells3d"])
+def test_conservation_functionals(kb, name):
+    """int u dx(tags), the measures and the membrane areas of ProblemKNPEMI.print_conservation
+    (KNPEMIx_problem.py:807-843) on the device against the oracle."""
+    om, p = MESHES[name](kb)
+    o = perturbed_oracle(om, p, MODELS_TEST, seed=7)
+    ctx = make_ctx(kb, om, p, MODELS_TEST)
+    push_oracle_state(ctx, o)
+    itags = list(p.intra_tags)
+    for s, tags in ((0, itags), (1, [p.extra_tag]), (0, itags[:1])):
+        vol = o.integral(o.c[s][0], tags, power=0)
+        assert abs(ctx.integral(s, 0, tags, power=0) - vol) <= 1e-12 * vol
+        for f in range(4):
+            u = o.c[s][f] if f < 3 else o.phi[s]
+            ref, scale = o.integral(u, tags), o.integral(np.abs(u), tags)
+            assert abs(ctx.integral(s, f, tags) - ref) <= 1e-12 * scale, (s, f)
+            assert abs(ctx.integral(s, f, tags, power=2) - o.integral(u, tags, power=2)) <= 1e-12 * o.integral(u, tags, power=2)
+    for tag in p.membrane_tags[:3]:
+        assert abs(ctx.membrane_area(tag) - o.membrane_area(tag)) <= 1e-12 * o.membrane_area(tag)
+    ctx.close()
+
+
+def test_print_conservation_mirror(kb, cfgdir):
+    """ProblemKNPEMI.conservation()/print_conservation() at the initial state of C2: closed-form amounts."""
+    p = kb.ProblemKNPEMI(os.path.join(cfgdir, "c2_square32_iterative.yaml"), verbose=False)
+    p.set_initial_conditions()
+    p.init_ionic_models([kb.NeuronalCotransporters(p), kb.HodgkinHuxley(p), kb.ATPPump(p)])
+    p.setup_variational_form()
+    s = kb.SolverKNPEMI(p, solver_config=dict(p.solver_config, view_ksp=False))
+    s.setup_solver()                                    # pushes the initial conditions to the device
+    c = p.conservation()
+    Ai, Ae, F = 0.25e-12, 0.75e-12, 96485.0
+    for name, ci, ce in (("Na", 12.0, 140.0), ("K", 130.0, 4.0), ("Cl", 5.0, 125.0)):
+        ref = ci * Ai + ce * Ae
+        assert abs(c["totals"][name] - ref) <= 1e-10 * ref, (name, c["totals"][name], ref)
+    cell = c["cells"][1]
+    assert abs(cell["volume"] - Ai) <= 1e-12 * Ai and cell["area"] == 0.0       # dS(1) is empty: the membrane tag is 4
+    assert abs(cell["charge"] - (12.0 + 130.0 - 5.0) * Ai * F) <= 1e-10 * 137 * Ai * F
+    p.print_conservation()
+
+
 # ---------------------------------------------------------------------------------------------- full BASELINE sizes
 @pytest.mark.parametrize("which", ["c3_2d_n2048", "c4_3d_n120"])
 def test_full_size_properties(kb, cfgdir, which):

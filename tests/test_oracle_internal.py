@@ -198,3 +198,15 @@ def test_charge_conservation_row_operation_and_schur_pc():
         for f in range(3):
             sl = slice(o.base[s] + f * o.ns[s], o.base[s] + (f + 1) * o.ns[s])
             assert np.linalg.norm(x[sl] - xd[sl]) <= 1e-8 * np.linalg.norm(xd[sl])
+
+
+def test_conservation_functionals_closed_form():
+    """int 1, int u and the membrane area on the C1 fixture: the intracellular square [0.25, 0.75]^2 um^2."""
+    o = KNPEMIOracle(unit_square(32), OracleParams(), MODELS_TEST)
+    L = 1e-6
+    assert abs(o.integral(o.c[0][0], 1, power=0) - 0.25 * L * L) < 1e-12 * L * L
+    assert abs(o.integral(o.c[0][0], [1, 2], power=0) - L * L) < 1e-12 * L * L
+    assert abs(o.integral(o.c[0][0], 1) - 12.0 * 0.25 * L * L) < 1e-10 * L * L          # Na_i = 12 mM
+    x = o.mesh.x[:, 0]
+    assert abs(o.integral(x, [1, 2]) - 0.5 * L ** 3) < 1e-12 * L ** 3                   # int x dx, exact for P1
+    assert abs(o.membrane_area(4) - 4 * 0.5 * L) < 1e-12 * L
