@@ -996,11 +996,6 @@ static int ceil_log2(int v) {
   return l;
 }
 
-int rows_tile_size(int max_deg, int max_gdeg) {
-  const int lgG = ceil_log2(std::max(std::max(max_deg, max_gdeg), 1));
-  return std::max(1, ROWS_THREADS >> lgG);
-}
-
 static RowsSmem rows_layout(int gdim, int mode, int max_deg, int max_gdeg, int max_inc) {
   RowsSmem S{};
   S.lgG = ceil_log2(std::max(std::max(max_deg, max_gdeg), 1));

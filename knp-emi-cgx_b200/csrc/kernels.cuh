@@ -20,7 +20,6 @@ int launch_gate(const DevTopo& T, const KParams& P, const double* u, double* gat
 int facet_ncomp(int gdim);
 int launch_facets(const DevTopo& T, const KParams& P, const uint32_t* tag_models, const int32_t* tag_stim,
                   const double* u, const double* gates, double stim_fac, double* fe, cudaStream_t st);
-int rows_tile_size(int max_deg, int max_gdeg);
 int build_static_geometry(DevTopo& T, int max_deg, int32_t* adjE, uint32_t* incE, double* geoK, double* mslot,
                           double* kslot, cudaStream_t st);
 int launch_rows(const DevTopo& T, const KParams& P, int mode, const double* u, const double* fe, double* vals,

@@ -591,7 +591,7 @@ static int schur_setup(knp_ctx* c) {
   App.n_rows = App.n_cols = n0 + n1;
   Acc.indptr.assign(1, 0);
   App.indptr.assign(1, 0);
-  for (int i = 0; i < n; ++i) {
+  for (int i = 0; i < n && c->nranks == 1; ++i) {     // multi-GPU runs build field-parallel global hierarchies instead
     const bool isc = cmap(i) >= 0;
     CsrHost& M = isc ? Acc : App;
     for (int j = ip[i]; j < ip[i + 1]; ++j) {
@@ -606,8 +606,6 @@ static int schur_setup(knp_ctx* c) {
   // rows were visited in the order c(s=0), phi(s=0), c(s=1), phi(s=1) = ascending compact order in both parts
   c->fp.on = false;
   if (c->nranks > 1) {
-    Acc = CsrHost();
-    App = CsrHost();
     KNP_TRY(schur_setup_fieldpar(c, idx, val));
   } else {
     KNP_TRY(build_amg(c, Acc, c->amg_c, 2500, true));
