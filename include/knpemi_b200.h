@@ -199,6 +199,12 @@ int knp_amg_num_levels(const knp_ctx* ctx);
 int knp_amg_part_levels(const knp_ctx* ctx, int32_t part);
 int knp_amg_level_sizes(const knp_ctx* ctx, int32_t level, int64_t* n, int64_t* nnz);
 int knp_amg_level_host(const knp_ctx* ctx, int32_t level, int32_t* indptr, int32_t* indices, double* vals);
+/* Host-only (no GPU, not thread-safe): builds the smoothed-aggregation hierarchy of a CSR matrix with the setup code the
+   preconditioners use (amg_setup.cpp; stands in for hypre's setup inside ksp.setUp, KNPEMIx_solver.py:386-389) and keeps
+   it for inspection with knp_amg_host_level; used by the CPU test suite to compare with oracle/amg.py. */
+int knp_amg_setup_host(int32_t n, const int32_t* indptr, const int32_t* indices, const double* vals, double theta,
+                       int32_t coarse_size, int32_t* n_levels);
+int knp_amg_host_level(int32_t level, int64_t* n, int64_t* nnz, int32_t* indptr, int32_t* indices, double* vals);
 
 /* ---- multi-GPU: halo exchange of ghost columns + all-reduce over NCCL (one rank per GPU) ----
  * Replaces PETSc VecScatter/ghostUpdate and MPI_Allreduce inside KSP (KNPEMI/KNPEMIx_solver.py:435,439,458-468). */

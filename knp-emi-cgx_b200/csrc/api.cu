@@ -585,4 +585,34 @@ int knp_amg_level_host(const knp_ctx* c, int32_t level, int32_t* indptr, int32_t
   return KNP_OK;
 }
 
+// ---- host-only hierarchy builder (no GPU needed): lets the CPU test suite compare amg_setup.cpp with oracle/amg.py ----
+static std::vector<CsrHost> g_host_levels;
+
+int knp_amg_setup_host(int32_t n, const int32_t* indptr, const int32_t* indices, const double* vals, double theta,
+                       int32_t coarse_size, int32_t* n_levels) {
+  KNP_CHECK(n > 0 && indptr && indices && vals && n_levels, "bad arguments");
+  CsrHost A0;
+  A0.n_rows = A0.n_cols = n;
+  A0.indptr.assign(indptr, indptr + n + 1);
+  A0.indices.assign(indices, indices + indptr[n]);
+  A0.vals.assign(vals, vals + indptr[n]);
+  std::vector<CsrHost> Ps, Rs;
+  std::vector<double> rhos, cinv;
+  g_host_levels.clear();
+  KNP_TRY(amg_setup_host(A0, theta, coarse_size, 16, g_host_levels, Ps, Rs, rhos, cinv, false));
+  *n_levels = (int32_t)g_host_levels.size();
+  return KNP_OK;
+}
+
+int knp_amg_host_level(int32_t level, int64_t* n, int64_t* nnz, int32_t* indptr, int32_t* indices, double* vals) {
+  KNP_CHECK(level >= 0 && level < (int)g_host_levels.size(), "no such level");
+  const CsrHost& A = g_host_levels[level];
+  if (n) *n = A.n_rows;
+  if (nnz) *nnz = A.nnz();
+  if (indptr) memcpy(indptr, A.indptr.data(), A.indptr.size() * sizeof(int32_t));
+  if (indices) memcpy(indices, A.indices.data(), A.indices.size() * sizeof(int32_t));
+  if (vals) memcpy(vals, A.vals.data(), A.vals.size() * sizeof(double));
+  return KNP_OK;
+}
+
 }  // extern "C"

@@ -65,7 +65,7 @@ SYMBOLS = [
     "knp_csr_P_host", "knp_dofmap_host", "knp_mverts_host", "knp_set_params", "knp_stimulus_area_local",
     "knp_set_state", "knp_get_state", "knp_state_dev", "knp_phi_m_host", "knp_gate_step", "knp_assemble",
     "knp_assemble_P", "knp_values_dev", "knp_spmv", "knp_pc_setup", "knp_pc_apply", "knp_solve", "knp_step",
-    "knp_step_host", "knp_set_time", "knp_get_time", "knp_l2_norm_sq", "knp_integral", "knp_membrane_area", "knp_last_timings", "knp_amg_num_levels", "knp_amg_part_levels",
+    "knp_step_host", "knp_set_time", "knp_get_time", "knp_l2_norm_sq", "knp_integral", "knp_membrane_area", "knp_last_timings", "knp_amg_num_levels", "knp_amg_part_levels", "knp_amg_setup_host", "knp_amg_host_level",
     "knp_copy", "knp_amg_level_sizes", "knp_amg_level_host", "knp_nccl_unique_id", "knp_dist_init", "knp_halo_exchange",
     "knp_allreduce_sum",
 ]
@@ -123,6 +123,8 @@ def load():
     lib.knp_copy.argtypes = [vp, vp, vp, C.c_int64, C.c_int32]
     lib.knp_amg_num_levels.argtypes = [vp]
     lib.knp_amg_part_levels.argtypes = [vp, C.c_int32]
+    lib.knp_amg_setup_host.argtypes = [C.c_int32, vp, vp, vp, C.c_double, C.c_int32, vp]
+    lib.knp_amg_host_level.argtypes = [C.c_int32, c_i64p, c_i64p, vp, vp, vp]
     lib.knp_amg_level_sizes.argtypes = [vp, C.c_int32, c_i64p, c_i64p]
     lib.knp_amg_level_host.argtypes = [vp, C.c_int32, vp, vp, vp]
     lib.knp_nccl_unique_id.argtypes = [C.c_char_p]
@@ -386,3 +388,24 @@ def nccl_unique_id():
     buf = C.create_string_buffer(128)
     check(load().knp_nccl_unique_id(buf))
     return buf.raw
+
+
+def amg_setup_host(A, theta=0.08, coarse_size=600):
+    """Level operators (scipy CSR) of the library's smoothed-aggregation setup for a scipy CSR matrix; host only."""
+    import scipy.sparse as sp
+    lib = load()
+    A = sp.csr_matrix(A)
+    A.sort_indices()
+    ip = np.ascontiguousarray(A.indptr, np.int32)
+    ix = np.ascontiguousarray(A.indices, np.int32)
+    va = np.ascontiguousarray(A.data, np.float64)
+    nl = C.c_int32()
+    check(lib.knp_amg_setup_host(A.shape[0], _ptr(ip), _ptr(ix), _ptr(va), theta, coarse_size, C.byref(nl)))
+    out = []
+    for l in range(nl.value):
+        n, nnz = C.c_int64(), C.c_int64()
+        check(lib.knp_amg_host_level(l, C.byref(n), C.byref(nnz), None, None, None))
+        lp, li, lv = np.empty(n.value + 1, np.int32), np.empty(nnz.value, np.int32), np.empty(nnz.value, np.float64)
+        check(lib.knp_amg_host_level(l, None, None, _ptr(lp), _ptr(li), _ptr(lv)))
+        out.append(sp.csr_matrix((lv, li, lp), shape=(n.value, n.value)))
+    return out

@@ -134,3 +134,36 @@ def test_no_cpu_fallback(kb, tmp_path):
     p.init_ionic_models([kb.PassiveModel(p)])
     with pytest.raises(kb.lib.KnpError, match="no CPU fallback"):
         p.setup_variational_form()
+
+
+@pytest.mark.parametrize("case", ["schur_ion_2d", "schur_phi_2d", "schur_ion_3d", "jacobi_P_2d"])
+def test_native_amg_setup_matches_oracle_level_by_level(kb, case):
+    """amg_setup.cpp (host code of libknpemi_b200.so, no GPU needed) against oracle/amg.py: same MIS(2) aggregates,
+    filtered prolongator smoothing, adaptive strength threshold and Galerkin products -> the level operators agree."""
+    from oracle.amg import SAAMG, SchurPC
+    from oracle.fixtures import from_arrays
+    from oracle.knpemi import KNPEMIOracle, OracleParams
+    from conftest import MODELS_TEST
+    d = 3 if case.endswith("3d") else 2
+    mm = kb.mesh.cell_array_mesh(d, 24 if d == 2 else 12, 3 if d == 2 else 2)
+    it = tuple(mm.intra_tags)
+    o = KNPEMIOracle(from_arrays(d, mm.x, mm.cells, mm.cell_tags, mm.intra_tags),
+                     OracleParams(intra_tags=it, extra_tag=1, membrane_tags=it, stimulus_tags=(2,)), MODELS_TEST)
+    rng = np.random.default_rng(4)
+    for s in range(2):
+        o.c[s] *= 1 + 0.05 * rng.random(o.c[s].shape)
+    if case == "jacobi_P_2d":
+        A = o.assemble_P().tocsr()
+    else:
+        pc = SchurPC(o, exact=True)
+        Pt = o.assemble_P(membrane_sign=+1.0).tocsr()
+        idx = pc.ic if "ion" in case else pc.ip
+        A = Pt[idx][:, idx].tocsr()
+    ref = SAAMG(A, coarse_size=100)
+    levels = kb.lib.amg_setup_host(A, theta=0.08, coarse_size=100)
+    ref_ops = [lv["A"] for lv in ref.levels] + [ref.Ac]
+    assert [a.shape[0] for a in levels] == [a.shape[0] for a in ref_ops]
+    assert len(levels) >= 2
+    for a, r in zip(levels, ref_ops):
+        dd = (a - r).tocoo()
+        assert dd.nnz == 0 or np.abs(dd.data).max() <= 1e-10 * np.abs(r.data).max()
