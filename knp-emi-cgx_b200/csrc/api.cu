@@ -585,6 +585,43 @@ int knp_amg_level_host(const knp_ctx* c, int32_t level, int32_t* indptr, int32_t
   return KNP_OK;
 }
 
+// ---- host-only structure builder (no GPU needed): restricted dof maps and the CSR pattern of A exactly as knp_create
+//      lays them out (build_topology + the index rule of csr_indices_kernel), for the CPU test suite ----
+int knp_pattern_host(const knp_mesh_desc* mesh, int64_t* n_rows, int64_t* nnz, int32_t* n_own2, int32_t* indptr,
+                     int32_t* indices, int32_t* dof_vert_i, int32_t* dof_vert_e) {
+  HostTopo H;
+  KNP_TRY(build_topology(mesh, H));
+  const Layout& L = H.L;
+  if (n_rows) *n_rows = L.n_rows;
+  if (nnz) *nnz = H.nnz;
+  if (n_own2) {
+    n_own2[0] = L.n_own[0];
+    n_own2[1] = L.n_own[1];
+  }
+  if (indptr) memcpy(indptr, H.indptr.data(), H.indptr.size() * sizeof(int32_t));
+  if (dof_vert_i) memcpy(dof_vert_i, H.node_vert[0].data(), H.node_vert[0].size() * sizeof(int32_t));
+  if (dof_vert_e) memcpy(dof_vert_e, H.node_vert[1].data(), H.node_vert[1].size() * sizeof(int32_t));
+  if (indices) {
+    for (int w = 0; w < H.n_work; ++w) {
+      const int s = w >= L.n_own[0] ? 1 : 0, p = w - (s ? L.n_own[0] : 0), o = 1 - s;
+      const int a0 = H.adj_ptr[w], deg = H.adj_ptr[w + 1] - a0;
+      const int g = H.mv_of_node[w];
+      const int g0 = g >= 0 ? H.gam_ptr[g] : 0, gdeg = g >= 0 ? H.gam_ptr[g + 1] - g0 : 0;
+      for (int f = 0; f < 4; ++f) {
+        int pos = H.indptr[L.row(s, f, p)];
+        if (s == 1)
+          for (int e = 0; e < gdeg; ++e) indices[pos++] = L.col(o, 3, H.mv_node[o][H.gam_mv[g0 + e]]);
+        for (int k = (f < 3 ? f : 0); k < (f < 3 ? f + 1 : 3); ++k)
+          for (int e = 0; e < deg; ++e) indices[pos++] = L.col(s, k, H.adj_idx[a0 + e]);
+        for (int e = 0; e < deg; ++e) indices[pos++] = L.col(s, 3, H.adj_idx[a0 + e]);
+        if (s == 0)
+          for (int e = 0; e < gdeg; ++e) indices[pos++] = L.col(o, 3, H.mv_node[o][H.gam_mv[g0 + e]]);
+      }
+    }
+  }
+  return KNP_OK;
+}
+
 // ---- host-only hierarchy builder (no GPU needed): lets the CPU test suite compare amg_setup.cpp with oracle/amg.py ----
 static std::vector<CsrHost> g_host_levels;
 

@@ -65,7 +65,7 @@ SYMBOLS = [
     "knp_csr_P_host", "knp_dofmap_host", "knp_mverts_host", "knp_set_params", "knp_stimulus_area_local",
     "knp_set_state", "knp_get_state", "knp_state_dev", "knp_phi_m_host", "knp_gate_step", "knp_assemble",
     "knp_assemble_P", "knp_values_dev", "knp_spmv", "knp_pc_setup", "knp_pc_apply", "knp_solve", "knp_step",
-    "knp_step_host", "knp_set_time", "knp_get_time", "knp_l2_norm_sq", "knp_integral", "knp_membrane_area", "knp_last_timings", "knp_amg_num_levels", "knp_amg_part_levels", "knp_amg_setup_host", "knp_amg_host_level",
+    "knp_step_host", "knp_set_time", "knp_get_time", "knp_l2_norm_sq", "knp_integral", "knp_membrane_area", "knp_last_timings", "knp_amg_num_levels", "knp_amg_part_levels", "knp_amg_setup_host", "knp_amg_host_level", "knp_pattern_host",
     "knp_copy", "knp_amg_level_sizes", "knp_amg_level_host", "knp_nccl_unique_id", "knp_dist_init", "knp_halo_exchange",
     "knp_allreduce_sum",
 ]
@@ -123,6 +123,7 @@ def load():
     lib.knp_copy.argtypes = [vp, vp, vp, C.c_int64, C.c_int32]
     lib.knp_amg_num_levels.argtypes = [vp]
     lib.knp_amg_part_levels.argtypes = [vp, C.c_int32]
+    lib.knp_pattern_host.argtypes = [vp, c_i64p, c_i64p, vp, vp, vp, vp, vp]
     lib.knp_amg_setup_host.argtypes = [C.c_int32, vp, vp, vp, C.c_double, C.c_int32, vp]
     lib.knp_amg_host_level.argtypes = [C.c_int32, c_i64p, c_i64p, vp, vp, vp]
     lib.knp_amg_level_sizes.argtypes = [vp, C.c_int32, c_i64p, c_i64p]
@@ -145,6 +146,56 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+def mesh_desc(gdim, coords, cells, cell_tags, intra_tags, extra_tag, mf_verts, mf_tags, quad_bary, quad_w,
+              n_owned_vertices=None, cell_owned=None, mfacet_owned=None):
+    """knp_mesh_desc for numpy arrays; returns (descriptor, dict of the arrays that must stay alive)."""
+    k = dict(
+        coords=np.ascontiguousarray(coords, np.float64),
+        cells=np.ascontiguousarray(cells, np.int32),
+        cell_tags=np.ascontiguousarray(cell_tags, np.int32),
+        intra=np.ascontiguousarray(intra_tags, np.int32),
+        mfv=np.ascontiguousarray(mf_verts, np.int32).reshape(-1, gdim),
+        mft=np.ascontiguousarray(mf_tags, np.int32),
+        qb=np.ascontiguousarray(quad_bary, np.float64),
+        qw=np.ascontiguousarray(quad_w, np.float64),
+        co=None if cell_owned is None else np.ascontiguousarray(cell_owned, np.uint8),
+        fo=None if mfacet_owned is None else np.ascontiguousarray(mfacet_owned, np.uint8),
+    )
+    d = MeshDesc()
+    d.gdim = gdim
+    d.n_vertices = k["coords"].shape[0]
+    d.n_owned_vertices = d.n_vertices if n_owned_vertices is None else int(n_owned_vertices)
+    d.coords = k["coords"].ctypes.data_as(c_f64p)
+    d.n_cells = k["cells"].shape[0]
+    d.cell_verts = k["cells"].ctypes.data_as(c_i32p)
+    d.cell_tags = k["cell_tags"].ctypes.data_as(c_i32p)
+    d.n_intra_tags = k["intra"].size
+    d.intra_tags = k["intra"].ctypes.data_as(c_i32p)
+    d.extra_tag = int(extra_tag)
+    d.n_mfacets = k["mfv"].shape[0]
+    d.mfacet_verts = k["mfv"].ctypes.data_as(c_i32p)
+    d.mfacet_tags = k["mft"].ctypes.data_as(c_i32p)
+    d.cell_owned = None if k["co"] is None else k["co"].ctypes.data_as(c_u8p)
+    d.mfacet_owned = None if k["fo"] is None else k["fo"].ctypes.data_as(c_u8p)
+    d.n_quad = k["qw"].size
+    d.quad_bary = k["qb"].ctypes.data_as(c_f64p)
+    d.quad_w = k["qw"].ctypes.data_as(c_f64p)
+    return d, k
+
+
+def pattern_host(gdim, coords, cells, cell_tags, intra_tags, extra_tag, mf_verts, mf_tags, quad_bary, quad_w, **kw):
+    """(indptr, indices, dof_vert_i, dof_vert_e) of the system matrix as knp_create lays it out; host only, no GPU."""
+    lib = load()
+    d, keep = mesh_desc(gdim, coords, cells, cell_tags, intra_tags, extra_tag, mf_verts, mf_tags, quad_bary, quad_w, **kw)
+    n, nnz = C.c_int64(), C.c_int64()
+    own = (C.c_int32 * 2)()
+    check(lib.knp_pattern_host(C.byref(d), C.byref(n), C.byref(nnz), own, None, None, None, None))
+    indptr, indices = np.empty(n.value + 1, np.int32), np.empty(nnz.value, np.int32)
+    vi, ve = np.empty(own[0], np.int32), np.empty(own[1], np.int32)
+    check(lib.knp_pattern_host(C.byref(d), None, None, None, _ptr(indptr), _ptr(indices), _ptr(vi), _ptr(ve)))
+    return indptr, indices, vi, ve
+
+
 class Context:
     """Thin object wrapper around a knp_ctx*; numpy in, numpy out; device pointers as ints."""
 
@@ -152,37 +203,8 @@ class Context:
                  n_owned_vertices=None, cell_owned=None, mfacet_owned=None, device=0):
         lib = load()
         self._lib = lib
-        k = dict(
-            coords=np.ascontiguousarray(coords, np.float64),
-            cells=np.ascontiguousarray(cells, np.int32),
-            cell_tags=np.ascontiguousarray(cell_tags, np.int32),
-            intra=np.ascontiguousarray(intra_tags, np.int32),
-            mfv=np.ascontiguousarray(mf_verts, np.int32).reshape(-1, gdim),
-            mft=np.ascontiguousarray(mf_tags, np.int32),
-            qb=np.ascontiguousarray(quad_bary, np.float64),
-            qw=np.ascontiguousarray(quad_w, np.float64),
-            co=None if cell_owned is None else np.ascontiguousarray(cell_owned, np.uint8),
-            fo=None if mfacet_owned is None else np.ascontiguousarray(mfacet_owned, np.uint8),
-        )
-        d = MeshDesc()
-        d.gdim = gdim
-        d.n_vertices = k["coords"].shape[0]
-        d.n_owned_vertices = d.n_vertices if n_owned_vertices is None else int(n_owned_vertices)
-        d.coords = k["coords"].ctypes.data_as(c_f64p)
-        d.n_cells = k["cells"].shape[0]
-        d.cell_verts = k["cells"].ctypes.data_as(c_i32p)
-        d.cell_tags = k["cell_tags"].ctypes.data_as(c_i32p)
-        d.n_intra_tags = k["intra"].size
-        d.intra_tags = k["intra"].ctypes.data_as(c_i32p)
-        d.extra_tag = int(extra_tag)
-        d.n_mfacets = k["mfv"].shape[0]
-        d.mfacet_verts = k["mfv"].ctypes.data_as(c_i32p)
-        d.mfacet_tags = k["mft"].ctypes.data_as(c_i32p)
-        d.cell_owned = None if k["co"] is None else k["co"].ctypes.data_as(c_u8p)
-        d.mfacet_owned = None if k["fo"] is None else k["fo"].ctypes.data_as(c_u8p)
-        d.n_quad = k["qw"].size
-        d.quad_bary = k["qb"].ctypes.data_as(c_f64p)
-        d.quad_w = k["qw"].ctypes.data_as(c_f64p)
+        d, k = mesh_desc(gdim, coords, cells, cell_tags, intra_tags, extra_tag, mf_verts, mf_tags, quad_bary, quad_w,
+                         n_owned_vertices, cell_owned, mfacet_owned)
         h = C.c_void_p()
         check(lib.knp_create(C.byref(h), C.byref(d), device))
         self.h = h

@@ -167,3 +167,28 @@ def test_native_amg_setup_matches_oracle_level_by_level(kb, case):
     for a, r in zip(levels, ref_ops):
         dd = (a - r).tocoo()
         assert dd.nnz == 0 or np.abs(dd.data).max() <= 1e-10 * np.abs(r.data).max()
+
+
+@pytest.mark.parametrize("name", ["square32", "square7", "cube6", "cells2d", "cells3d"])
+def test_native_csr_pattern_and_dofmaps_bit_exact_on_host(kb, name):
+    """The structure builder of libknpemi_b200.so (topology.cpp; host code, no GPU) against the oracle: restricted dof
+    maps and the CSR pattern of A bit for bit (north star: 'bit-exact CSR structure and DOF maps')."""
+    from oracle.fixtures import from_arrays, unit_cube, unit_square
+    from oracle.knpemi import KNPEMIOracle, OracleParams
+    from conftest import MODELS_TEST
+    if name.startswith("cells"):
+        d = 2 if name == "cells2d" else 3
+        mm = kb.mesh.cell_array_mesh(d, 24 if d == 2 else 8, 3 if d == 2 else 2)
+        om = from_arrays(d, mm.x, mm.cells, mm.cell_tags, mm.intra_tags)
+        it = tuple(mm.intra_tags)
+        p = OracleParams(intra_tags=it, extra_tag=1, membrane_tags=it, stimulus_tags=(2,))
+    else:
+        om = {"square32": lambda: unit_square(32), "square7": lambda: unit_square(7), "cube6": lambda: unit_cube(6)}[name]()
+        p = OracleParams()
+    o = KNPEMIOracle(om, p, MODELS_TEST)
+    A, _ = o.assemble(p.dt)
+    qb, qw = kb.mesh.facet_quadrature(om.gdim)
+    ip, ix, vi, ve = kb.lib.pattern_host(om.gdim, om.x, om.cells, om.cell_tags, p.intra_tags, p.extra_tag, om.mf_verts,
+                                         om.mf_tags, qb, qw)
+    assert np.array_equal(ip, A.indptr) and np.array_equal(ix, A.indices)
+    assert np.array_equal(vi, o.S[0]) and np.array_equal(ve, o.S[1])
