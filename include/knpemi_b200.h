@@ -200,9 +200,10 @@ int knp_amg_part_levels(const knp_ctx* ctx, int32_t part);
 int knp_amg_level_sizes(const knp_ctx* ctx, int32_t level, int64_t* n, int64_t* nnz);
 int knp_amg_level_host(const knp_ctx* ctx, int32_t level, int32_t* indptr, int32_t* indices, double* vals);
 /* Host-only (no GPU): sizes, restricted dof maps (DofMapRestriction, KNPEMIx_problem.py:85-94) and the CSR pattern of A
-   (create_matrix_block, KNPEMIx_solver.py:157) exactly as knp_create lays them out.  Call once with NULL arrays for the
-   sizes, then with arrays of n_rows + 1, nnz, n_own[0], n_own[1] entries. */
-int knp_pattern_host(const knp_mesh_desc* mesh, int64_t* n_rows, int64_t* nnz, int32_t* n_own2, int32_t* indptr,
+   (create_matrix_block, KNPEMIx_solver.py:157) exactly as knp_create lays them out (owned rows; columns in the
+   [owned | ghost tail] column layout).  Call once with NULL arrays for the sizes (n_own_loc4 = owned and local dof
+   counts of the two subdomains), then with arrays of n_rows + 1, nnz, n_loc[0], n_loc[1] entries. */
+int knp_pattern_host(const knp_mesh_desc* mesh, int64_t* n_rows, int64_t* nnz, int32_t* n_own_loc4, int32_t* indptr,
                      int32_t* indices, int32_t* dof_vert_i, int32_t* dof_vert_e);
 /* Host-only (no GPU, not thread-safe): builds the smoothed-aggregation hierarchy of a CSR matrix with the setup code the
    preconditioners use (amg_setup.cpp; stands in for hypre's setup inside ksp.setUp, KNPEMIx_solver.py:386-389) and keeps

@@ -587,16 +587,18 @@ int knp_amg_level_host(const knp_ctx* c, int32_t level, int32_t* indptr, int32_t
 
 // ---- host-only structure builder (no GPU needed): restricted dof maps and the CSR pattern of A exactly as knp_create
 //      lays them out (build_topology + the index rule of csr_indices_kernel), for the CPU test suite ----
-int knp_pattern_host(const knp_mesh_desc* mesh, int64_t* n_rows, int64_t* nnz, int32_t* n_own2, int32_t* indptr,
+int knp_pattern_host(const knp_mesh_desc* mesh, int64_t* n_rows, int64_t* nnz, int32_t* n_own_loc4, int32_t* indptr,
                      int32_t* indices, int32_t* dof_vert_i, int32_t* dof_vert_e) {
   HostTopo H;
   KNP_TRY(build_topology(mesh, H));
   const Layout& L = H.L;
   if (n_rows) *n_rows = L.n_rows;
   if (nnz) *nnz = H.nnz;
-  if (n_own2) {
-    n_own2[0] = L.n_own[0];
-    n_own2[1] = L.n_own[1];
+  if (n_own_loc4) {
+    n_own_loc4[0] = L.n_own[0];
+    n_own_loc4[1] = L.n_own[1];
+    n_own_loc4[2] = L.n_loc[0];
+    n_own_loc4[3] = L.n_loc[1];
   }
   if (indptr) memcpy(indptr, H.indptr.data(), H.indptr.size() * sizeof(int32_t));
   if (dof_vert_i) memcpy(dof_vert_i, H.node_vert[0].data(), H.node_vert[0].size() * sizeof(int32_t));

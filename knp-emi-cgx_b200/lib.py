@@ -188,10 +188,10 @@ def pattern_host(gdim, coords, cells, cell_tags, intra_tags, extra_tag, mf_verts
     lib = load()
     d, keep = mesh_desc(gdim, coords, cells, cell_tags, intra_tags, extra_tag, mf_verts, mf_tags, quad_bary, quad_w, **kw)
     n, nnz = C.c_int64(), C.c_int64()
-    own = (C.c_int32 * 2)()
+    own = (C.c_int32 * 4)()
     check(lib.knp_pattern_host(C.byref(d), C.byref(n), C.byref(nnz), own, None, None, None, None))
     indptr, indices = np.empty(n.value + 1, np.int32), np.empty(nnz.value, np.int32)
-    vi, ve = np.empty(own[0], np.int32), np.empty(own[1], np.int32)
+    vi, ve = np.empty(own[2], np.int32), np.empty(own[3], np.int32)      # local dofs: owned first, then ghosts
     check(lib.knp_pattern_host(C.byref(d), None, None, None, _ptr(indptr), _ptr(indices), _ptr(vi), _ptr(ve)))
     return indptr, indices, vi, ve
 

@@ -118,3 +118,41 @@ def test_gloo_world_size_2():
                        capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("WORKER_OK") == 2
+
+
+@pytest.mark.parametrize("gdim,n,m,size", [(2, 24, 3, 3), (3, 8, 2, 4)])
+def test_native_local_patterns_tile_the_global_pattern(kb, gdim, n, m, size):
+    """topology.cpp on every rank's local mesh (owned vertices + ghost-cell layer): the owned rows, mapped through the
+    [owned | ghost tail] column layout back to global numbering, are exactly the rows of the global pattern -- the
+    structure side of owner-computes assembly, checked on the host without a GPU."""
+    part, mesh, locs, lays, _ = _setup(kb, gdim, n, m, size)
+    it = tuple(mesh.intra_tags)
+    og = KNPEMIOracle(from_arrays(gdim, mesh.x, mesh.cells, mesh.cell_tags, it),
+                      OracleParams(intra_tags=it, extra_tag=1, membrane_tags=it, stimulus_tags=(2,)), MODELS_TEST)
+    Ag, _ = og.assemble(og.p.dt)
+    Ag = Ag.tocsr()
+    qb, qw = kb.mesh.facet_quadrature(gdim)
+    seen = np.zeros(og.n, bool)
+    for (l, info), lay in zip(locs, lays):
+        ip, ix, vi, ve = kb.lib.pattern_host(gdim, l.x, l.cells, l.cell_tags, it, 1, l.mf_verts, l.mf_tags, qb, qw,
+                                             n_owned_vertices=l.n_owned, cell_owned=l.cell_owned, mfacet_owned=l.mf_owned)
+        assert np.array_equal(vi, lay.node_vert[0]) and np.array_equal(ve, lay.node_vert[1])
+        assert ip.size - 1 == lay.n_rows
+        l2g = info["l2g"]
+        # local column -> global column
+        gcol = np.empty(lay.n_cols, np.int64)
+        for s in range(2):
+            gv = l2g[lay.node_vert[s]]
+            for f in range(4):
+                gcol[lay.col(s, f, np.arange(lay.n_loc[s]))] = og.row(s, f, gv)
+        for s in range(2):
+            gv = l2g[lay.node_vert[s][:lay.n_own[s]]]
+            for f in range(4):
+                lrows = lay.rowbase[s] + f * lay.n_own[s] + np.arange(lay.n_own[s])
+                grows = og.row(s, f, gv)
+                for lr, gr in zip(lrows.tolist(), grows.tolist()):
+                    mine = np.sort(gcol[ix[ip[lr]:ip[lr + 1]]])
+                    ref = Ag.indices[Ag.indptr[gr]:Ag.indptr[gr + 1]]
+                    assert np.array_equal(mine, ref), (s, f, lr, gr)
+                    seen[gr] = True
+    assert seen.all()
