@@ -184,6 +184,9 @@ int knp_l2_norm_sq(knp_ctx* ctx, int32_t subdomain, int32_t field, int32_t n_tag
    subdomain `subdomain` carrying one of `tags`; all-reduce the result over the ranks like the reference does. */
 int knp_integral(knp_ctx* ctx, int32_t subdomain, int32_t field, int32_t power, int32_t n_tags, const int32_t* tags,
                  double* out);
+/* this rank's part of the total stimulus current int stim_expr dS(stimulus_tags) at time t from the current state
+   (SolverKNPEMI.init_png_data / save_png, KNPEMIx_solver.py:578-610; stim_expr: KNPEMIx_ionic_model.py:517-603) */
+int knp_stimulus_current(knp_ctx* ctx, double t, double* out);
 /* this rank's area of the membrane facets tagged `tag` (assemble_scalar(1*dS(tag)), KNPEMIx_problem.py:833-834) */
 int knp_membrane_area(const knp_ctx* ctx, int32_t tag, double* out);
 /* per-phase device timers of the last knp_step (ms): gate, facet, rows, solve, total */

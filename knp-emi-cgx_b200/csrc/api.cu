@@ -68,6 +68,7 @@ int knp_create(knp_ctx** out, const knp_mesh_desc* mesh, int device) {
   KNP_TRY(c->d_mf_mv.upload(H.mf_mv));
   KNP_TRY(c->d_mf_tagidx.upload(H.mf_tagidx));
   KNP_TRY(c->d_mf_area.upload(H.mf_area));
+  KNP_TRY(c->d_mf_owned.upload(H.mf_owned));
   KNP_TRY(c->d_gam_ptr.upload(H.gam_ptr));
   KNP_TRY(c->d_gam_mv.upload(H.gam_mv));
   KNP_TRY(c->d_minc_ptr.upload(H.minc_ptr));
@@ -525,6 +526,25 @@ int knp_l2_norm_sq(knp_ctx* c, int32_t s, int32_t field, int32_t n_tags, const i
 
 int knp_integral(knp_ctx* c, int32_t s, int32_t field, int32_t power, int32_t n_tags, const int32_t* tags, double* out) {
   return cell_functional(c, s, field, power, n_tags, tags, out);
+}
+
+int knp_stimulus_current(knp_ctx* c, double t, double* out) {
+  CTX_GUARD(c);
+  KNP_CHECK(out, "NULL argument");
+  KNP_CHECK(c->params_set, "knp_set_params must be called first");
+  *out = 0.0;
+  if (c->T.n_mf == 0 || !c->params.any_hh) return KNP_OK;
+  const knp_params& p = c->params.p;
+  const double t_mod = std::fmod(t + 1e-12, p.T_stim);            // HodgkinHuxley.update_t_mod, KNPEMIx_ionic_model.py:673-674
+  double stim_fac = p.g_syn_bar * std::exp(-t_mod / p.a_syn);
+  if (p.scale_stimulus) stim_fac *= 1.0 / c->params.stim_area;
+  cudaStream_t st = c->stream;
+  const int nb = 592;
+  KNP_TRY(launch_stim_current(c->T, c->kp, c->d_tag_stim.p, c->d_mf_owned.p, c->u.p, stim_fac, c->fpartial.p, nb, st));
+  KNP_TRY(launch_reduce_partials(c->fpartial.p, nb, c->fout.p, st));
+  KNP_CUDA(cudaMemcpyAsync(out, c->fout.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+  KNP_CUDA(cudaStreamSynchronize(st));
+  return KNP_OK;
 }
 
 int knp_membrane_area(const knp_ctx* c, int32_t tag, double* out) {

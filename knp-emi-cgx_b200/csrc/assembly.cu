@@ -680,6 +680,61 @@ __global__ void __launch_bounds__(256) l2_cells_kernel(Layout L, int s, int fiel
   if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
 }
 
+// Total stimulus current int stim_expr dS(stimulus_tags) (SolverKNPEMI.init_png_data / save_png, KNPEMIx_solver.py:578-610,
+// with stim_expr of HodgkinHuxley._add_stimulus, KNPEMIx_ionic_model.py:517-603): thread per owned stimulated facet,
+// per-block partial sums in a fixed order.
+template <int D>
+__global__ void __launch_bounds__(256) stim_current_kernel(DevTopo T, KParams P, const int32_t* __restrict__ tag_stim,
+                                                           const int32_t* __restrict__ mf_owned,
+                                                           const double* __restrict__ u, double stim_fac,
+                                                           double* __restrict__ partial) {
+  __shared__ double red[256];
+  double acc = 0.0;
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < T.n_mf; f += gridDim.x * blockDim.x) {
+    if (!mf_owned[f] || tag_stim[T.mf_tagidx[f]] == 0) continue;
+    double ci[D], ce[D], pm[D], xs[D];
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+      const int g = T.mf_mv[(size_t)f * D + a];
+      const int qi = T.mv_node0[g], qe = T.mv_node1[g];
+      ci[a] = u[T.L.col(0, 0, qi)];
+      ce[a] = u[T.L.col(1, 0, qe)];
+      pm[a] = u[T.L.col(0, 3, qi)] - u[T.L.col(1, 3, qe)];
+      xs[a] = P.stim_dir >= 0 ? T.node_x[(size_t)qi * D + P.stim_dir] : 0.0;
+    }
+    const double area = T.mf_area[f];
+    for (int q = 0; q < T.nq; ++q) {
+      double ciq = 0.0, ceq = 0.0, pmq = 0.0, xq = 0.0;
+#pragma unroll
+      for (int a = 0; a < D; ++a) {
+        const double lam = T.qb[q * D + a];
+        ciq += lam * ci[a];
+        ceq += lam * ce[a];
+        pmq += lam * pm[a];
+        xq += lam * xs[a];
+      }
+      const double E_Na = (P.psi / P.z[0]) * log(ceq / ciq);
+      const double mask = (P.stim_dir < 0 || (xq > P.stim_lo && xq < P.stim_hi)) ? 1.0 : 0.0;
+      acc += area * T.qw[q] * mask * stim_fac * (pmq - E_Na);
+    }
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if (threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+
+int launch_stim_current(const DevTopo& T, const KParams& P, const int32_t* tag_stim, const int32_t* mf_owned,
+                        const double* u, double stim_fac, double* partial, int n_partial, cudaStream_t st) {
+  if (T.gdim == 2) stim_current_kernel<2><<<n_partial, 256, 0, st>>>(T, P, tag_stim, mf_owned, u, stim_fac, partial);
+  else stim_current_kernel<3><<<n_partial, 256, 0, st>>>(T, P, tag_stim, mf_owned, u, stim_fac, partial);
+  KNP_LAUNCHED();
+  return KNP_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ launchers
 int launch_gate(const DevTopo& T, const KParams& P, const double* u, double* gates, cudaStream_t st) {
   if (T.n_mv == 0) return KNP_OK;

@@ -22,7 +22,7 @@ struct knp_ctx {
   int nblk_A = 0;
   knp::DevBuf<int32_t> d_cell_nodes[2], d_cell_tag[2], d_cell_owned[2];
   knp::DevBuf<uint32_t> d_tag_models;
-  knp::DevBuf<int32_t> d_tag_stim;
+  knp::DevBuf<int32_t> d_tag_stim, d_mf_owned;
   // parameters
   knp::Params params{};
   knp::KParams kp{};

@@ -30,6 +30,9 @@ int launch_l2_cells(int gdim, const Layout& L, int s, int field, int power, int 
                     const int32_t* tags, int n_tags, const double* u, double* partial, int n_partial,
                     cudaStream_t st);
 
+int launch_stim_current(const DevTopo& T, const KParams& P, const int32_t* tag_stim, const int32_t* mf_owned,
+                        const double* u, double stim_fac, double* partial, int n_partial, cudaStream_t st);
+
 // ---- linalg.cu ----
 enum SpmvEpi { EPI_SET = 0, EPI_RESID = 1, EPI_JACOBI = 2, EPI_ADD = 3 };
 // out = epilogue(A x): SET: A x | RESID: b - A x | JACOBI: x + w*dinv*(b - A x) | ADD: out + A x

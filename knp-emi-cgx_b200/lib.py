@@ -65,7 +65,7 @@ SYMBOLS = [
     "knp_csr_P_host", "knp_dofmap_host", "knp_mverts_host", "knp_set_params", "knp_stimulus_area_local",
     "knp_set_state", "knp_get_state", "knp_state_dev", "knp_phi_m_host", "knp_gate_step", "knp_assemble",
     "knp_assemble_P", "knp_values_dev", "knp_spmv", "knp_pc_setup", "knp_pc_apply", "knp_solve", "knp_step",
-    "knp_step_host", "knp_set_time", "knp_get_time", "knp_l2_norm_sq", "knp_integral", "knp_membrane_area", "knp_last_timings", "knp_amg_num_levels", "knp_amg_part_levels", "knp_amg_setup_host", "knp_amg_host_level", "knp_pattern_host",
+    "knp_step_host", "knp_set_time", "knp_get_time", "knp_l2_norm_sq", "knp_integral", "knp_membrane_area", "knp_stimulus_current", "knp_last_timings", "knp_amg_num_levels", "knp_amg_part_levels", "knp_amg_setup_host", "knp_amg_host_level", "knp_pattern_host",
     "knp_copy", "knp_amg_level_sizes", "knp_amg_level_host", "knp_nccl_unique_id", "knp_dist_init", "knp_halo_exchange",
     "knp_allreduce_sum",
 ]
@@ -119,6 +119,7 @@ def load():
     lib.knp_l2_norm_sq.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, vp, c_f64p]
     lib.knp_integral.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, c_f64p]
     lib.knp_membrane_area.argtypes = [vp, C.c_int32, c_f64p]
+    lib.knp_stimulus_current.argtypes = [vp, C.c_double, c_f64p]
     lib.knp_last_timings.argtypes = [vp, vp]
     lib.knp_copy.argtypes = [vp, vp, vp, C.c_int64, C.c_int32]
     lib.knp_amg_num_levels.argtypes = [vp]
@@ -339,6 +340,12 @@ class Context:
         tags = np.ascontiguousarray(np.atleast_1d(tags), np.int32)
         out = C.c_double()
         check(self._lib.knp_integral(self.h, subdomain, field, power, tags.size, _ptr(tags), C.byref(out)))
+        return out.value
+
+    def stimulus_current(self, t):
+        """This rank's part of int stim_expr dS(stimulus_tags) at time t from the state on the device."""
+        out = C.c_double()
+        check(self._lib.knp_stimulus_current(self.h, float(t), C.byref(out)))
         return out.value
 
     def membrane_area(self, tag):

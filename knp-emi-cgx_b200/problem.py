@@ -662,6 +662,12 @@ class ProblemKNPEMI:
                                "charge": (amount[0] + amount[1] - amount[2]) * float(self.F.value)}
         return {"totals": totals, "cells": cells}
 
+    def stimulus_current(self):
+        """Total stimulus current int stim_expr dS(stimulus_tags) at the current time and state, like
+        SolverKNPEMI.save_png accumulates it in stim_t (KNPEMIx_solver.py:578-610); computed on the device."""
+        ctx = self._require_context()
+        return float(self.comm.allreduce(ctx.stimulus_current(float(self.t.value)), op=MPI.SUM))
+
     def print_conservation(self):
         """KNPEMIx_problem.py:807-843."""
         c = self.conservation()

@@ -562,6 +562,20 @@ class KNPEMIOracle:
     def membrane_area(self, tag):
         return float(self.farea[self.mesh.mf_tags == tag].sum())
 
+    def stimulus_current(self, t):
+        """int stim_expr dS(stimulus_tags) (KNPEMIx_solver.py:578-610 with the expression of
+        HodgkinHuxley._add_stimulus, KNPEMIx_ionic_model.py:517-603), from the current fields."""
+        p, m = self.p, self.mesh
+        self._stim_area = self.stimulus_area() if p.scale_stimulus else 1.0
+        t_mod = np.mod(t + 1e-12, p.T_stim)
+        ci, ce, phim, gq, xq = self._facet_quadrature_fields()
+        sel = np.isin(m.mf_tags, np.asarray(p.stimulus_tags))
+        E_Na = (p.psi / p.z[0]) * np.log(ce[0] / ci[0])
+        stim = self.stimulus_mask(xq) * p.g_syn_bar * np.exp(-t_mod / p.a_syn) * (phim - E_Na)
+        if p.scale_stimulus:
+            stim = stim / self._stim_area
+        return float(np.sum((self.farea[:, None] * self.qw[None, :] * stim)[sel]))
+
     def l2_norm(self, u, tags):
         """sqrt(int u^2 dx(tags)) for a P1 field given on all vertices."""
         m = self.mesh

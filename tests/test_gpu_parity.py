@@ -489,6 +489,9 @@ def test_conservation_functionals(kb, name):
             assert abs(ctx.integral(s, f, tags, power=2) - o.integral(u, tags, power=2)) <= 1e-12 * o.integral(u, tags, power=2)
     for tag in p.membrane_tags[:3]:
         assert abs(ctx.membrane_area(tag) - o.membrane_area(tag)) <= 1e-12 * o.membrane_area(tag)
+    # total stimulus current (KNPEMIx_solver.py:578-610)
+    ref = o.stimulus_current(3 * p.dt)
+    assert ref != 0.0 and abs(ctx.stimulus_current(3 * p.dt) - ref) <= 1e-11 * abs(ref)
     ctx.close()
 
 
