@@ -305,6 +305,9 @@ struct RowsSmem {       // computed on the host
   int tile;             // nodes per CTA = ROWS_THREADS / G
   int lgG, lgI;         // log2 of the lanes per node and of the incidence slots per node
   int off_res, off_packed;
+  int res_stride;       // doubles per node in the cell-result block, padded so that the lane groups of one warp hit
+                        // different banks (stride mod 16 doubles = 4)
+  int pk_stride;        // words per node in the packed-slot block (odd)
   int off_prod;         // products m_e c_k(e) for the right-hand side (inside the staging alias, after the rows)
   int off_rs;           // CSR row starts of the tile (not aliased)
   int total;
@@ -391,7 +394,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, ROWS_MIN_CTAS) rows_kernel(DevTo
     const int ii0 = T.inc_ptr[w0 + n];
     if (j >= T.inc_ptr[w0 + n + 1] - ii0) continue;
     const uint32_t pk = T.inc_slots[ii0 + j];
-    packed[i] = pk;
+    packed[(size_t)n * S.pk_stride + j] = pk;
     const int la = (__ffs(__vcmpeq4(pk, (uint32_t)T.self_slot[w0 + n] * 0x01010101u) & VMASK) - 1) >> 3;
     const double* nb = nbr + ((size_t)n << lgG) * NB;
     double x[NV][D], csum[3] = {0.0, 0.0, 0.0};
@@ -413,7 +416,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, ROWS_MIN_CTAS) rows_kernel(DevTo
       for (int a = 1; a < NV; ++a) t = (la == a) ? G.g[a][d] : t;
       gl[d] = t;
     }
-    double* r = res + (size_t)i * NR;
+    double* r = res + (size_t)n * S.res_stride + (size_t)j * NR;
 #pragma unroll
     for (int b = 0; b < NV; ++b) {
       double dot = 0.0;
@@ -437,8 +440,8 @@ __global__ void __launch_bounds__(ROWS_THREADS, ROWS_MIN_CTAS) rows_kernel(DevTo
   if (has_ent) {
 #pragma unroll
     for (int k = 0; k < 3; ++k) ce[k] = nbr[(size_t)tid * NB + D + k];
-    const uint32_t* pk = packed + ((size_t)lw << lgI);
-    const double* rbase = res + ((size_t)lw << lgI) * NR;
+    const uint32_t* pk = packed + (size_t)lw * S.pk_stride;
+    const double* rbase = res + (size_t)lw * S.res_stride;
     for (int j = 0; j < ninc; ++j) {
       const uint32_t m = __vcmpeq4(pk[j], rep) & VMASK;
       if (m) {
@@ -1058,8 +1061,11 @@ static RowsSmem rows_layout(int gdim, int mode, int max_deg, int max_gdeg, int m
   S.tile = std::max(1, ROWS_THREADS >> S.lgG);
   const int NB = gdim + 3, NR = gdim + 1 + 4;
   const size_t nbr = (size_t)ROWS_THREADS * NB * 8;
-  const size_t res = ((size_t)S.tile << S.lgI) * NR * 8;
-  const size_t packed = ((size_t)S.tile << S.lgI) * 4;
+  S.res_stride = (NR << S.lgI);
+  while (S.res_stride % 16 != 4) ++S.res_stride;
+  S.pk_stride = (1 << S.lgI) | 1;
+  const size_t res = (size_t)S.tile * S.res_stride * 8;
+  const size_t packed = (size_t)S.tile * S.pk_stride * 4;
   S.off_res = (int)nbr;
   S.off_packed = (int)(nbr + res);
   const size_t work = (nbr + res + packed + 15) & ~(size_t)15;
