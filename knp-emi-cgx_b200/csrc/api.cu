@@ -63,6 +63,12 @@ int knp_create(knp_ctx** out, const knp_mesh_desc* mesh, int device) {
   KNP_TRY(c->d_self_slot.upload(H.self_slot));
   KNP_TRY(c->d_mv_of_node.upload(H.mv_of_node));
   KNP_TRY(c->d_gpre.upload(H.gpre));
+  // opt-in (KNP_ROWS_LISTS=1): list-driven phase 2b of the row kernel; measured SLOWER than the byte-compare scan
+  // (2D 1.99 vs 1.76 ms, 3D 4.29 vs 3.09 ms: the code -> address -> value chain serialises), kept for the record
+  if (H.elist_ok && getenv("KNP_ROWS_LISTS") && atoi(getenv("KNP_ROWS_LISTS"))) {
+    KNP_TRY(c->d_ecnt.upload(H.ecnt));
+    KNP_TRY(c->d_elist.upload(H.elist));
+  }
   KNP_TRY(c->d_mv_node0.upload(H.mv_node[0]));
   KNP_TRY(c->d_mv_node1.upload(H.mv_node[1]));
   KNP_TRY(c->d_mf_mv.upload(H.mf_mv));
@@ -128,6 +134,8 @@ int knp_create(knp_ctx** out, const knp_mesh_desc* mesh, int device) {
   T.qw = c->d_qw.p;
   T.gpre = c->d_gpre.p;
   T.max_inc = H.max_inc;
+  T.ecnt = c->d_ecnt.p;
+  T.elist = c->d_elist.p;
   T.Wp = (T.n_work + 31) / 32 * 32;
   T.adjE = nullptr;
   T.incE = nullptr;
@@ -165,6 +173,8 @@ int knp_create(knp_ctx** out, const knp_mesh_desc* mesh, int device) {
   std::vector<uint32_t>().swap(H.inc_slots);
   std::vector<uint32_t>().swap(H.minc);
   std::vector<int32_t>().swap(H.adj_idx);
+  std::vector<uint8_t>().swap(H.elist);
+  std::vector<uint8_t>().swap(H.ecnt);
   *out = c.release();
   return KNP_OK;
 }

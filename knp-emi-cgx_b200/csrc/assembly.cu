@@ -308,6 +308,9 @@ struct RowsSmem {       // computed on the host
   int res_stride;       // doubles per node in the cell-result block, padded so that the lane groups of one warp hit
                         // different banks (stride mod 16 doubles = 4)
   int pk_stride;        // words per node in the packed-slot block (odd)
+  int off_self;         // [tile][5] sums over all incident cells for the self slot
+  int off_el;           // the tile's (node, slot) cell lists (bytes)
+  int use_lists;
   int off_prod;         // products m_e c_k(e) for the right-hand side (inside the staging alias, after the rows)
   int off_rs;           // CSR row starts of the tile (not aliased)
   int total;
@@ -346,6 +349,9 @@ __global__ void __launch_bounds__(ROWS_THREADS, ROWS_MIN_CTAS) rows_kernel(DevTo
   uint32_t* packed = reinterpret_cast<uint32_t*>(smraw + S.off_packed);
   double* prod = reinterpret_cast<double*>(smraw + S.off_prod);
   int* rstart = reinterpret_cast<int*>(smraw + S.off_rs);        // [4][tile + 1] CSR row starts of the tile's rows
+  double* selfacc = reinterpret_cast<double*>(smraw + S.off_self);   // [tile][5]: sums over all cells for the self slot
+  uint8_t* el = smraw + S.off_el;                                // the tile's (node, slot) cell lists
+  const bool lists = S.use_lists != 0;
 
   const int tid = threadIdx.x;
   const int lgG = S.lgG, lgI = S.lgI, GI = 1 << lgI;
@@ -360,14 +366,17 @@ __global__ void __launch_bounds__(ROWS_THREADS, ROWS_MIN_CTAS) rows_kernel(DevTo
 
   const int lw = tid >> lgG, e = tid & ((1 << lgG) - 1);
   const bool node_ok = lw < nt;
-  int deg = 0, gdeg = 0, self = -1, g = -1, ninc = 0;
+  int deg = 0, gdeg = 0, self = -1, g = -1, ninc = 0, i0 = 0, ecnt = 0;
+  const int i_tile = T.inc_ptr[w0];
   if (node_ok) {
     const int w = w0 + lw;
     const int a0 = T.adj_ptr[w];
     deg = T.adj_ptr[w + 1] - a0;
     self = T.self_slot[w];
     g = T.mv_of_node[w];
-    ninc = T.inc_ptr[w + 1] - T.inc_ptr[w];
+    i0 = T.inc_ptr[w];
+    ninc = T.inc_ptr[w + 1] - i0;
+    if (lists && e < deg) ecnt = T.ecnt[a0 + e];
     if (MODE == 0) gdeg = T.gpre[w + 1] - T.gpre[w];
     if (e < 4) {
       rstart[e * (tile + 1) + lw] = iptr[T.L.row(s, e, p0 + lw)];
@@ -388,45 +397,78 @@ __global__ void __launch_bounds__(ROWS_THREADS, ROWS_MIN_CTAS) rows_kernel(DevTo
   const bool has_ent = node_ok && e < deg;
   __syncthreads();
 
-  // ---- phase 2a: one thread per (node, incident cell) ----
-  for (int i = tid; i < (nt << lgI); i += ROWS_THREADS) {
+  // ---- phase 2a: one thread per (node, incident cell); the loop bound is warp-uniform because the GI threads of a node
+  //      also reduce the node's self-slot sums (all cells contribute to the self slot) with a shuffle butterfly ----
+  for (int i = tid; i < (tile << lgI); i += ROWS_THREADS) {
     const int n = i >> lgI, j = i & (GI - 1);
-    const int ii0 = T.inc_ptr[w0 + n];
-    if (j >= T.inc_ptr[w0 + n + 1] - ii0) continue;
-    const uint32_t pk = T.inc_slots[ii0 + j];
-    packed[(size_t)n * S.pk_stride + j] = pk;
-    const int la = (__ffs(__vcmpeq4(pk, (uint32_t)T.self_slot[w0 + n] * 0x01010101u) & VMASK) - 1) >> 3;
-    const double* nb = nbr + ((size_t)n << lgG) * NB;
-    double x[NV][D], csum[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-    for (int b = 0; b < NV; ++b) {
-      const double* v = nb + ((pk >> (8 * b)) & 255u) * NB;
-#pragma unroll
-      for (int d = 0; d < D; ++d) x[b][d] = v[d];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) csum[k] += v[D + k];
+    bool valid = n < nt;
+    int ii0 = 0;
+    if (valid) {
+      ii0 = T.inc_ptr[w0 + n];
+      valid = j < T.inc_ptr[w0 + n + 1] - ii0;
     }
-    CellGeom<D> G;
-    cell_geometry(x, G);
-    double gl[D];
+    double sself[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    if (valid) {
+      const uint32_t pk = T.inc_slots[ii0 + j];
+      packed[(size_t)n * S.pk_stride + j] = pk;
+      const int la = (__ffs(__vcmpeq4(pk, (uint32_t)T.self_slot[w0 + n] * 0x01010101u) & VMASK) - 1) >> 3;
+      const double* nb = nbr + ((size_t)n << lgG) * NB;
+      double x[NV][D], csum[3] = {0.0, 0.0, 0.0};
 #pragma unroll
-    for (int d = 0; d < D; ++d) {
-      double t = G.g[0][d];
+      for (int b = 0; b < NV; ++b) {
+        const double* v = nb + ((pk >> (8 * b)) & 255u) * NB;
 #pragma unroll
-      for (int a = 1; a < NV; ++a) t = (la == a) ? G.g[a][d] : t;
-      gl[d] = t;
+        for (int d = 0; d < D; ++d) x[b][d] = v[d];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) csum[k] += v[D + k];
+      }
+      CellGeom<D> G;
+      cell_geometry(x, G);
+      double gl[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        double t = G.g[0][d];
+#pragma unroll
+        for (int a = 1; a < NV; ++a) t = (la == a) ? G.g[a][d] : t;
+        gl[d] = t;
+      }
+      double* r = res + (size_t)n * S.res_stride + (size_t)j * NR;
+      double kself = 0.0;
+#pragma unroll
+      for (int b = 0; b < NV; ++b) {
+        double dot = 0.0;
+#pragma unroll
+        for (int d = 0; d < D; ++d) dot += gl[d] * G.g[b][d];
+        const double kab = G.vol * dot;
+        r[b] = kab;
+        kself = (b == la) ? kab : kself;
+      }
+      const double mv = G.vol * (1.0 / ((D + 1) * (D + 2)));
+      r[NV] = mv;
+      sself[0] = mv;
+      sself[1] = kself;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const double cb = csum[k] * (1.0 / NV);
+        r[NV + 1 + k] = cb;
+        sself[2 + k] = cb * kself;
+      }
     }
-    double* r = res + (size_t)n * S.res_stride + (size_t)j * NR;
+    if (lists) {
+      for (int off = GI >> 1; off > 0; off >>= 1) {
 #pragma unroll
-    for (int b = 0; b < NV; ++b) {
-      double dot = 0.0;
+        for (int q = 0; q < 5; ++q) sself[q] += __shfl_xor_sync(0xffffffffu, sself[q], off);
+      }
+      if (j == 0 && n < nt) {
 #pragma unroll
-      for (int d = 0; d < D; ++d) dot += gl[d] * G.g[b][d];
-      r[b] = G.vol * dot;
+        for (int q = 0; q < 5; ++q) selfacc[n * 5 + q] = sself[q];
+      }
     }
-    r[NV] = G.vol * (1.0 / ((D + 1) * (D + 2)));
-#pragma unroll
-    for (int k = 0; k < 3; ++k) r[NV + 1 + k] = csum[k] * (1.0 / NV);
+  }
+  if (lists) {      // the tile's cell lists: one contiguous byte range of the global table
+    const int nbytes = (NV - 1) * (T.inc_ptr[w0 + nt] - i_tile);
+    const uint8_t* __restrict__ src = T.elist + (size_t)(NV - 1) * i_tile;
+    for (int i = tid; i < nbytes; i += ROWS_THREADS) el[i] = src[i];
   }
   __syncthreads();
 
@@ -437,18 +479,46 @@ __global__ void __launch_bounds__(ROWS_THREADS, ROWS_MIN_CTAS) rows_kernel(DevTo
   const bool is_self = has_ent && e == self;
   const bool has_gam = MODE == 0 && node_ok && e < gdeg;
   const uint32_t rep = (uint32_t)e * 0x01010101u;
+  int eoff = 0;
+  if (lists) {      // start of this lane's list inside its node's block: exclusive prefix sum of the list lengths
+    int incl = ecnt;
+    for (int off = 1; off < (1 << lgG); off <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, off, 1 << lgG);
+      if (e >= off) incl += v;
+    }
+    eoff = incl - ecnt;
+  }
   if (has_ent) {
 #pragma unroll
     for (int k = 0; k < 3; ++k) ce[k] = nbr[(size_t)tid * NB + D + k];
-    const uint32_t* pk = packed + (size_t)lw * S.pk_stride;
     const double* rbase = res + (size_t)lw * S.res_stride;
-    for (int j = 0; j < ninc; ++j) {
-      const uint32_t m = __vcmpeq4(pk[j], rep) & VMASK;
-      if (m) {
-        const int b = (__ffs(m) - 1) >> 3;
-        const double* r = rbase + j * NR;
-        const double kab = r[b], mv = r[NV];
-        a_m += is_self ? 2.0 * mv : mv;
+    if (!lists) {
+      const uint32_t* pk = packed + (size_t)lw * S.pk_stride;
+      for (int j = 0; j < ninc; ++j) {
+        const uint32_t m = __vcmpeq4(pk[j], rep) & VMASK;
+        if (m) {
+          const int b = (__ffs(m) - 1) >> 3;
+          const double* r = rbase + j * NR;
+          const double kab = r[b], mv = r[NV];
+          a_m += is_self ? 2.0 * mv : mv;
+          a_kk += kab;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) X[k] += r[NV + 1 + k] * kab;
+        }
+      }
+    } else if (is_self) {
+      const double* sa = selfacc + lw * 5;
+      a_m = 2.0 * sa[0];
+      a_kk = sa[1];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) X[k] = sa[2 + k];
+    } else {
+      const uint8_t* lst = el + (NV - 1) * (i0 - i_tile) + eoff;
+      for (int t = 0; t < ecnt; ++t) {
+        const int code = lst[t];
+        const double* r = rbase + (code >> 2) * NR;
+        const double kab = r[code & 3];
+        a_m += r[NV];
         a_kk += kab;
 #pragma unroll
         for (int k = 0; k < 3; ++k) X[k] += r[NV + 1 + k] * kab;
@@ -1068,7 +1138,11 @@ static RowsSmem rows_layout(int gdim, int mode, int max_deg, int max_gdeg, int m
   const size_t packed = (size_t)S.tile * S.pk_stride * 4;
   S.off_res = (int)nbr;
   S.off_packed = (int)(nbr + res);
-  const size_t work = (nbr + res + packed + 15) & ~(size_t)15;
+  size_t work = (nbr + res + packed + 15) & ~(size_t)15;
+  S.off_self = (int)work;
+  work += (size_t)S.tile * 5 * 8;
+  S.off_el = (int)work;
+  work += ((size_t)S.tile * gdim * max_inc + 15) & ~(size_t)15;
   // staging strip: all four fields of the tile (+ phase shift and rounding per field), then the rhs products
   const size_t rows = (size_t)S.tile * (mode == 0 ? 10 * max_deg + 4 * max_gdeg : 4 * max_deg) + 16;
   S.off_prod = (int)(rows * 8);
@@ -1081,7 +1155,9 @@ static RowsSmem rows_layout(int gdim, int mode, int max_deg, int max_gdeg, int m
 template <int D, int MODE>
 static int launch_rows_t(const DevTopo& T, const KParams& P, const double* u, const double* fe, double* vals,
                          double* b, int max_deg, int max_gdeg, cudaStream_t st) {
-  const RowsSmem S = rows_layout(D, MODE, max_deg, max_gdeg, T.max_inc);
+  RowsSmem S = rows_layout(D, MODE, max_deg, max_gdeg, T.max_inc);
+  // list-driven phase 2b needs the lane groups (adjacency and incidence) inside one warp
+  S.use_lists = (T.elist && T.ecnt && S.lgG <= 5 && S.lgI <= 5 && ((S.tile << S.lgI) % 32) == 0) ? 1 : 0;
   if (S.total > 227 * 1024 || (1 << S.lgG) > ROWS_THREADS) {
     set_error("vertex degree %d / valence %d too large for the row kernel (%d bytes of shared memory)", max_deg,
               T.max_inc, S.total);

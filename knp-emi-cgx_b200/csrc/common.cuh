@@ -97,6 +97,8 @@ struct HostTopo {
   std::vector<int32_t> inc_ptr;           // per owned node
   std::vector<uint32_t> inc_slots;        // per (node, cell): adjacency slots of the cell's vertices (8 bit each)
   std::vector<int32_t> self_slot;         // per owned node: slot of itself in its adjacency
+  std::vector<uint8_t> ecnt, elist;       // per (node, slot): cells containing the slot (see topology.cpp)
+  int elist_ok = 0;
   std::vector<int32_t> mv_of_node;        // per owned node: membrane vertex id or -1
   // membrane
   int n_mv = 0, n_mf = 0;
@@ -139,6 +141,7 @@ struct DevTopo {
   const double *qb, *qw;
   const int32_t* gpre;       // per owned node: prefix of the gamma degree
   int max_inc;               // largest number of cells incident to one owned node
+  const uint8_t *ecnt, *elist;   // per (node, slot) cell lists of the row kernel (nullptr: scan all incident cells)
   // static ELL tables of the thread-per-dof row kernel (leading dimension Wp = dofs rounded up to 32)
   int Wp;
   const int32_t* adjE;

@@ -15,6 +15,7 @@ struct knp_ctx {
   knp::DevBuf<double> d_node_x, d_mf_area, d_qb, d_qw;
   knp::DevBuf<int32_t> d_adj_ptr, d_adj_idx, d_inc_ptr, d_self_slot, d_mv_of_node, d_gpre;
   knp::DevBuf<uint32_t> d_inc_slots, d_minc, d_incE;
+  knp::DevBuf<uint8_t> d_ecnt, d_elist;
   knp::DevBuf<int32_t> d_adjE;
   knp::DevBuf<double> d_geoK, d_mslot, d_kslot;
   knp::DevBuf<int32_t> d_mv_node0, d_mv_node1, d_mf_mv, d_mf_tagidx, d_gam_ptr, d_gam_mv, d_minc_ptr;

@@ -183,6 +183,33 @@ int build_topology(const knp_mesh_desc* m, HostTopo& T) {
     }
   }
 
+  // ---- per (node, slot) list of the cells that contain the slot (ascending cell order), self slot excluded: the
+  //      row kernel's phase 2b walks these lists instead of scanning all incident cells.  One byte per entry:
+  //      (incidence index << 2) | local vertex; one byte per adjacency entry for the list length ----
+  T.ecnt.assign(T.adj_idx.size(), 0);
+  T.elist.assign((size_t)(nv - 1) * inc_cell.size(), 0);
+  T.elist_ok = T.max_inc <= 64 ? 1 : 0;
+  if (T.elist_ok) {
+#pragma omp parallel for schedule(static)
+    for (int w = 0; w < W; ++w) {
+      const int i0 = T.inc_ptr[w], ninc = T.inc_ptr[w + 1] - i0, dg = T.adj_ptr[w + 1] - T.adj_ptr[w];
+      size_t pos = (size_t)(nv - 1) * i0;
+      for (int e = 0; e < dg; ++e) {
+        if (e == T.self_slot[w]) continue;
+        int cnt = 0;
+        for (int j = 0; j < ninc; ++j) {
+          const uint32_t pk = T.inc_slots[i0 + j];
+          for (int b = 0; b < nv; ++b)
+            if ((int)((pk >> (8 * b)) & 255u) == e) {
+              T.elist[pos++] = (uint8_t)((j << 2) | b);
+              ++cnt;
+            }
+        }
+        T.ecnt[T.adj_ptr[w] + e] = (uint8_t)cnt;
+      }
+    }
+  }
+
   // ---- membrane ----
   T.n_mf = (int)NF;
   std::vector<int32_t> mvid(NV, -1);
