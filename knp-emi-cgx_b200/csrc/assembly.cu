@@ -331,7 +331,7 @@ __device__ __forceinline__ void bulk_store(double* gdst, const double* ssrc, uin
                : "memory");
 }
 
-template <int D, int MODE>
+template <int D, int MODE, bool LISTS>
 __global__ void __launch_bounds__(ROWS_THREADS, ROWS_MIN_CTAS) rows_kernel(DevTopo T, RowCoef C, const double* __restrict__ u,
                                                                const double* __restrict__ fe,
                                                                double* __restrict__ vals, double* __restrict__ bvec,
@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, ROWS_MIN_CTAS) rows_kernel(DevTo
   int* rstart = reinterpret_cast<int*>(smraw + S.off_rs);        // [4][tile + 1] CSR row starts of the tile's rows
   double* selfacc = reinterpret_cast<double*>(smraw + S.off_self);   // [tile][5]: sums over all cells for the self slot
   uint8_t* el = smraw + S.off_el;                                // the tile's (node, slot) cell lists
-  const bool lists = S.use_lists != 0;
+  constexpr bool lists = LISTS;           // compile-time: the default (scan) kernel carries none of the list code
 
   const int tid = threadIdx.x;
   const int lgG = S.lgG, lgI = S.lgI, GI = 1 << lgI;
@@ -445,13 +445,15 @@ __global__ void __launch_bounds__(ROWS_THREADS, ROWS_MIN_CTAS) rows_kernel(DevTo
       }
       const double mv = G.vol * (1.0 / ((D + 1) * (D + 2)));
       r[NV] = mv;
-      sself[0] = mv;
-      sself[1] = kself;
+      if (lists) {
+        sself[0] = mv;
+        sself[1] = kself;
+      }
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         const double cb = csum[k] * (1.0 / NV);
         r[NV + 1 + k] = cb;
-        sself[2 + k] = cb * kself;
+        if (lists) sself[2 + k] = cb * kself;
       }
     }
     if (lists) {
@@ -1165,7 +1167,8 @@ static int launch_rows_t(const DevTopo& T, const KParams& P, const double* u, co
   }
   static int configured = 0;
   if (S.total > 48 * 1024 && S.total > configured) {
-    KNP_CUDA(cudaFuncSetAttribute(rows_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, S.total));
+    KNP_CUDA(cudaFuncSetAttribute(rows_kernel<D, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S.total));
+    KNP_CUDA(cudaFuncSetAttribute(rows_kernel<D, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S.total));
     configured = S.total;
   }
   RowCoef C;
@@ -1178,7 +1181,8 @@ static int launch_rows_t(const DevTopo& T, const KParams& P, const double* u, co
   }
   C.cf = P.C_M / P.F;
   const int nt0 = (T.L.n_own[0] + S.tile - 1) / S.tile, nt1 = (T.L.n_own[1] + S.tile - 1) / S.tile;
-  rows_kernel<D, MODE><<<nt0 + nt1, ROWS_THREADS, S.total, st>>>(T, C, u, fe, vals, b, S, nt0);
+  if (S.use_lists) rows_kernel<D, MODE, true><<<nt0 + nt1, ROWS_THREADS, S.total, st>>>(T, C, u, fe, vals, b, S, nt0);
+  else rows_kernel<D, MODE, false><<<nt0 + nt1, ROWS_THREADS, S.total, st>>>(T, C, u, fe, vals, b, S, nt0);
   KNP_LAUNCHED();
   return KNP_OK;
 }
