@@ -64,6 +64,16 @@ struct knp_ctx {
   };
   std::vector<PcGraph> pc_graphs;
   int pc_applies = 0;
+  // multi-GPU: the cycles of the field owners are captured on their own (the NCCL transfers stay outside the graphs)
+  struct CycleGraph {
+    const void* amg;
+    const double* in;
+    double* out;
+    cudaGraphExec_t exec;
+    unsigned long long launches;
+  };
+  std::vector<CycleGraph> cycle_graphs;
+  int cycle_calls = 0;
   // distributed
   ncclComm* comm = nullptr;
   int rank = 0, nranks = 1;

@@ -653,6 +653,35 @@ static int schur_setup(knp_ctx* c) {
   return KNP_OK;
 }
 
+// one cycle of a field owner's hierarchy, replayed from a CUDA graph after the first two calls (multi-GPU path)
+static int vcycle_graphed(knp_ctx* c, Amg& M, const double* in, double* out, cudaStream_t st) {
+  static const bool enabled = !(getenv("KNP_PC_GRAPH") && atoi(getenv("KNP_PC_GRAPH")) == 0);
+  if (!enabled) return vcycle(M, 0, in, out, st);
+  for (auto& g : c->cycle_graphs)
+    if (g.amg == &M && g.in == in && g.out == out) {
+      KNP_CUDA(cudaGraphLaunch(g.exec, st));
+      g_kernel_launches += g.launches;
+      return KNP_OK;
+    }
+  if (c->cycle_calls++ < 2 || c->cycle_graphs.size() >= 8) return vcycle(M, 0, in, out, st);   // warm-up first
+  const unsigned long long l0 = g_kernel_launches;
+  KNP_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  const int rc = vcycle(M, 0, in, out, st);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(st, &graph);
+  if (rc != KNP_OK || e != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    if (rc == KNP_OK) set_error("CUDA graph capture of a cycle failed: %s", cudaGetErrorString(e));
+    return rc != KNP_OK ? rc : KNP_E_CUDA;
+  }
+  cudaGraphExec_t exec = nullptr;
+  KNP_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+  cudaGraphDestroy(graph);
+  c->cycle_graphs.push_back({&M, in, out, exec, g_kernel_launches - l0});
+  KNP_CUDA(cudaGraphLaunch(exec, st));
+  return KNP_OK;
+}
+
 static int schur_apply(knp_ctx* c, const double* r, double* zout, cudaStream_t st) {
   const Layout& L = c->T.L;
   const int n0 = L.n_own[0], n1 = L.n_own[1];
@@ -664,7 +693,7 @@ static int schur_apply(knp_ctx* c, const double* r, double* zout, cudaStream_t s
   KNP_LAUNCHED();
   if (c->fp.on) {
     KNP_TRY(fieldpar_move(c, true, true, c->sch_vc.p, c->fp.gc_in.p, st));
-    if (c->amg_c) KNP_TRY(vcycle(*c->amg_c, 0, c->fp.gc_in.p, c->fp.gc_out.p, st));
+    if (c->amg_c) KNP_TRY(vcycle_graphed(c, *c->amg_c, c->fp.gc_in.p, c->fp.gc_out.p, st));
     KNP_TRY(fieldpar_move(c, true, false, c->sch_zc.p, c->fp.gc_out.p, st));
   } else {
     KNP_TRY(vcycle(*c->amg_c, 0, c->sch_vc.p, c->sch_zc.p, st));
@@ -686,7 +715,7 @@ static int schur_apply(knp_ctx* c, const double* r, double* zout, cudaStream_t s
   }
   if (c->fp.on) {
     KNP_TRY(fieldpar_move(c, false, true, c->sch_t.p, c->fp.gp_in.p, st));
-    if (c->amg_p) KNP_TRY(vcycle(*c->amg_p, 0, c->fp.gp_in.p, c->fp.gp_out.p, st));
+    if (c->amg_p) KNP_TRY(vcycle_graphed(c, *c->amg_p, c->fp.gp_in.p, c->fp.gp_out.p, st));
     KNP_TRY(fieldpar_move(c, false, false, c->sch_zp.p, c->fp.gp_out.p, st));
   } else {
     KNP_TRY(vcycle(*c->amg_p, 0, c->sch_t.p, c->sch_zp.p, st));
@@ -793,6 +822,9 @@ void pc_graphs_clear(knp_ctx* c) {
   for (auto& g : c->pc_graphs) cudaGraphExecDestroy(g.exec);
   c->pc_graphs.clear();
   c->pc_applies = 0;
+  for (auto& g : c->cycle_graphs) cudaGraphExecDestroy(g.exec);
+  c->cycle_graphs.clear();
+  c->cycle_calls = 0;
 }
 
 // The Schur application is ~200 small launches (W-cycle over two hierarchies): on one GPU it is captured once per
