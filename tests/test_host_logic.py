@@ -192,3 +192,24 @@ def test_native_csr_pattern_and_dofmaps_bit_exact_on_host(kb, name):
                                          om.mf_tags, qb, qw)
     assert np.array_equal(ip, A.indptr) and np.array_equal(ix, A.indices)
     assert np.array_equal(vi, o.S[0]) and np.array_equal(ve, o.S[1])
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU oracle timed on a bounded sample) runs without a GPU and prints ONE JSON line
+    with the keys the driver reads."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "3",
+                        "--cpu-sample-n", "64"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["higher_is_better"] is False and d["unit"] == "ms"
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert "workload" in d["config"] and d["value"] > 0
