@@ -208,6 +208,13 @@ int knp_amg_level_host(const knp_ctx* ctx, int32_t level, int32_t* indptr, int32
    counts of the two subdomains), then with arrays of n_rows + 1, nnz, n_loc[0], n_loc[1] entries. */
 int knp_pattern_host(const knp_mesh_desc* mesh, int64_t* n_rows, int64_t* nnz, int32_t* n_own_loc4, int32_t* indptr,
                      int32_t* indices, int32_t* dof_vert_i, int32_t* dof_vert_e);
+/* Host-only: the row blocks the TMA-staged SpMV (the MatMult of ksp.solve, KNPEMIx_solver.py:435) walks over --
+   blocks4 = {first row (multiple of 4), rows, 4-aligned first non-zero, staged non-zeros} per block; n_blocks = -1 when a
+   group of four rows exceeds the stage capacity (the CSR-vector kernel is used then). */
+int knp_rowblocks_host(int32_t n_rows, const int32_t* indptr, int32_t max_blocks, int32_t* blocks4, int32_t* n_blocks);
+/* Host-only: which rank owns the global hierarchy of field 4 s + f in a multi-GPU run (replaces the processor-local hypre
+   hierarchies of the reference's MPI runs, KNPEMIx_solver.py:269-273). */
+int knp_field_owners_host(int32_t nranks, int64_t n_intra_global, int64_t n_extra_global, int32_t* owner8);
 /* Host-only (no GPU, not thread-safe): builds the smoothed-aggregation hierarchy of a CSR matrix with the setup code the
    preconditioners use (amg_setup.cpp; stands in for hypre's setup inside ksp.setUp, KNPEMIx_solver.py:386-389) and keeps
    it for inspection with knp_amg_host_level; used by the CPU test suite to compare with oracle/amg.py. */

@@ -654,6 +654,28 @@ int knp_pattern_host(const knp_mesh_desc* mesh, int64_t* n_rows, int64_t* nnz, i
   return KNP_OK;
 }
 
+// ---- host-only views of two more setup decisions, for the CPU test tier ----
+int knp_rowblocks_host(int32_t n_rows, const int32_t* indptr, int32_t max_blocks, int32_t* blocks4, int32_t* n_blocks) {
+  KNP_CHECK(n_rows >= 0 && indptr && n_blocks, "bad arguments");
+  std::vector<int32_t> blk;
+  const int nb = build_rowblocks(indptr, n_rows, blk);
+  *n_blocks = nb;
+  if (nb > 0 && blocks4) {
+    KNP_CHECK(nb <= max_blocks, "block buffer too small (%d blocks)", nb);
+    memcpy(blocks4, blk.data(), blk.size() * sizeof(int32_t));
+  }
+  return KNP_OK;
+}
+
+int knp_field_owners_host(int32_t nranks, int64_t n_intra_global, int64_t n_extra_global, int32_t* owner8) {
+  KNP_CHECK(nranks >= 1 && owner8, "bad arguments");
+  const int64_t size_s[2] = {n_intra_global, n_extra_global};
+  int owner[8];
+  assign_field_owners(nranks, size_s, owner);
+  for (int i = 0; i < 8; ++i) owner8[i] = owner[i];
+  return KNP_OK;
+}
+
 // ---- host-only hierarchy builder (no GPU needed): lets the CPU test suite compare amg_setup.cpp with oracle/amg.py ----
 static std::vector<CsrHost> g_host_levels;
 

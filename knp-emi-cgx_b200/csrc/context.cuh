@@ -102,6 +102,7 @@ struct P2POp {
   bool send;
 };
 int p2p_exchange(knp_ctx* c, const std::vector<P2POp>& ops, cudaStream_t st);
+void assign_field_owners(int nranks, const int64_t size_s[2], int owner[8]);
 int ensure_workspace(knp_ctx* c, int restart);
 int pc_setup(knp_ctx* c, const knp_solve_opts* o);
 int pc_apply(knp_ctx* c, const double* r, double* z, cudaStream_t st);

@@ -337,7 +337,7 @@ __global__ void schur_merge_kernel(Layout L, const double* __restrict__ zc, cons
 // back (grouped ncclSend/ncclRecv over NVLink, 2 x 8 B per dof).
 // Field -> rank: the two stages (ion fields, then potential fields) run one after the other, so each stage is balanced
 // on its own: longest-processing-time-first over the global field sizes (ECS fields are ~3x the ICS ones).
-static void assign_field_owners(int nranks, const int64_t size_s[2], int owner[8]) {
+void assign_field_owners(int nranks, const int64_t size_s[2], int owner[8]) {
   std::vector<int64_t> load(nranks, 0);
   auto least = [&](int exclude) {
     int best = -1;

@@ -65,7 +65,7 @@ SYMBOLS = [
     "knp_csr_P_host", "knp_dofmap_host", "knp_mverts_host", "knp_set_params", "knp_stimulus_area_local",
     "knp_set_state", "knp_get_state", "knp_state_dev", "knp_phi_m_host", "knp_gate_step", "knp_assemble",
     "knp_assemble_P", "knp_values_dev", "knp_spmv", "knp_pc_setup", "knp_pc_apply", "knp_solve", "knp_step",
-    "knp_step_host", "knp_set_time", "knp_get_time", "knp_l2_norm_sq", "knp_integral", "knp_membrane_area", "knp_stimulus_current", "knp_last_timings", "knp_amg_num_levels", "knp_amg_part_levels", "knp_amg_setup_host", "knp_amg_host_level", "knp_pattern_host",
+    "knp_step_host", "knp_set_time", "knp_get_time", "knp_l2_norm_sq", "knp_integral", "knp_membrane_area", "knp_stimulus_current", "knp_last_timings", "knp_amg_num_levels", "knp_amg_part_levels", "knp_amg_setup_host", "knp_amg_host_level", "knp_pattern_host", "knp_rowblocks_host", "knp_field_owners_host",
     "knp_copy", "knp_amg_level_sizes", "knp_amg_level_host", "knp_nccl_unique_id", "knp_dist_init", "knp_halo_exchange",
     "knp_allreduce_sum",
 ]
@@ -124,6 +124,8 @@ def load():
     lib.knp_copy.argtypes = [vp, vp, vp, C.c_int64, C.c_int32]
     lib.knp_amg_num_levels.argtypes = [vp]
     lib.knp_amg_part_levels.argtypes = [vp, C.c_int32]
+    lib.knp_rowblocks_host.argtypes = [C.c_int32, vp, C.c_int32, vp, vp]
+    lib.knp_field_owners_host.argtypes = [C.c_int32, C.c_int64, C.c_int64, vp]
     lib.knp_pattern_host.argtypes = [vp, c_i64p, c_i64p, vp, vp, vp, vp, vp]
     lib.knp_amg_setup_host.argtypes = [C.c_int32, vp, vp, vp, C.c_double, C.c_int32, vp]
     lib.knp_amg_host_level.argtypes = [C.c_int32, c_i64p, c_i64p, vp, vp, vp]
@@ -437,4 +439,25 @@ def amg_setup_host(A, theta=0.08, coarse_size=600):
         lp, li, lv = np.empty(n.value + 1, np.int32), np.empty(nnz.value, np.int32), np.empty(nnz.value, np.float64)
         check(lib.knp_amg_host_level(l, None, None, _ptr(lp), _ptr(li), _ptr(lv)))
         out.append(sp.csr_matrix((lv, li, lp), shape=(n.value, n.value)))
+    return out
+
+
+def rowblocks_host(indptr):
+    """Row blocks of the streaming SpMV for a CSR row-pointer array: (n_blocks, 4) int32 or None (fallback kernel)."""
+    lib = load()
+    ip = np.ascontiguousarray(indptr, np.int32)
+    n = ip.size - 1
+    nb = C.c_int32()
+    check(lib.knp_rowblocks_host(n, _ptr(ip), 0, None, C.byref(nb)))
+    if nb.value <= 0:
+        return None
+    out = np.empty((nb.value, 4), np.int32)
+    check(lib.knp_rowblocks_host(n, _ptr(ip), nb.value, _ptr(out), C.byref(nb)))
+    return out
+
+
+def field_owners_host(nranks, n_intra, n_extra):
+    lib = load()
+    out = np.empty(8, np.int32)
+    check(lib.knp_field_owners_host(int(nranks), int(n_intra), int(n_extra), _ptr(out)))
     return out

@@ -213,3 +213,44 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["impl"] == "reference" and d["higher_is_better"] is False and d["unit"] == "ms"
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
     assert "workload" in d["config"] and d["value"] > 0
+
+
+def test_native_spmv_rowblocks_cover_every_row_once(kb):
+    """Row blocks of the TMA-staged SpMV (linalg.cu::build_rowblocks): every row in exactly one block, 16-byte aligned
+    TMA sources (first row and staged start multiples of 4), stage capacity and row limit respected."""
+    rng = np.random.default_rng(3)
+    for lens in (rng.integers(7, 29, 5000), np.full(3000, 7), rng.integers(1, 120, 2000), np.array([3]), np.zeros(0, int)):
+        indptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+        blk = kb.lib.rowblocks_host(indptr)
+        n = indptr.size - 1
+        if n == 0:
+            assert blk is None
+            continue
+        assert blk is not None
+        r0, nr, a4, cnt = blk.T
+        assert r0[0] == 0 and np.array_equal(r0[1:], (r0 + nr)[:-1]) and r0[-1] + nr[-1] == n      # contiguous cover
+        assert (r0 % 4 == 0).all() and (a4 % 4 == 0).all()
+        assert np.array_equal(a4, indptr[r0] & ~3) and np.array_equal(cnt, indptr[r0 + nr] - a4)
+        assert (nr <= 256).all() and (cnt <= 1280).all() and (nr > 0).all()
+    # a group of four rows that cannot fit one stage -> no blocks (the CSR-vector kernel takes over)
+    assert kb.lib.rowblocks_host(np.array([0, 2000, 4000], np.int32)) is None
+
+
+@pytest.mark.parametrize("nranks", [2, 3, 4, 8, 16])
+def test_native_field_owner_assignment(kb, nranks):
+    """Multi-GPU field -> rank map (solver.cu::assign_field_owners): each stage balanced largest-first, the two potential
+    fields on different ranks, deterministic."""
+    ni, ne = 1_000_000, 3_000_000
+    own = kb.lib.field_owners_host(nranks, ni, ne)
+    assert np.array_equal(own, kb.lib.field_owners_host(nranks, ni, ne))
+    assert ((own >= 0) & (own < nranks)).all()
+    load = np.zeros(nranks)
+    for s, size in ((0, ni), (1, ne)):
+        for f in range(3):
+            load[own[4 * s + f]] += size
+    total = 3 * (ni + ne)
+    assert load.max() <= max(ne, total / nranks + ne)          # LPT bound: within one largest job of the average
+    if nranks >= 6:
+        assert load.max() == ne                                  # every ion field alone on a rank
+    assert own[3] != own[7]
+    assert own[7] == int(np.argmin(load))                        # the large potential field goes to the least loaded rank
