@@ -22,5 +22,8 @@ Parity pinning: the only results the reference's tests hold for this path are
 four end-to-end L2 norms (tests/KNPEMI/electric_potential_norms_*_solver.py).
 ``tests/test_oracle_golden.py`` checks the oracle against them.  There are no
 golden matrices / vectors / CSR patterns in the reference, so entry-level parity
-("CSR structure", "entries within 1e-12") is *pinned only through those norms*.
+("CSR structure", "entries within 1e-12") is *pinned only through those norms*:
+with respect to the real DOLFINx numbering and per-entry values it is PARITY UNPINNED
+(DESIGN.md section 3).  ``oracle/amg.py`` restates the product's OWN preconditioners
+(SA-AMG cycle, charge-conservation Schur form); hypre is not restated.
 """
