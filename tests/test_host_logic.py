@@ -254,3 +254,34 @@ def test_native_field_owner_assignment(kb, nranks):
         assert load.max() == ne                                  # every ion field alone on a rank
     assert own[3] != own[7]
     assert own[7] == int(np.argmin(load))                        # the large potential field goes to the least loaded rank
+
+
+def test_solver_option_mapping(kb, tmp_path):
+    """SolverKNPEMI._opts: how the reference's solver settings (KNPEMIx_solver.py:25-51,164-291) map onto the C-ABI
+    knp_solve_opts -- `pc_type: hypre` -> the Schur preconditioner (pc 3) unless amg_form says block_jacobi, gamg -> the
+    SA-AMG cycle on the reference's P (pc 2); unsupported choices raise instead of silently doing something else."""
+    it = BASE.replace("solver: {direct: True, output: {save_xdmf: False}}",
+                      "solver: {direct: False, ksp_settings: {ksp_rtol: 1.0e-9, ksp_type: gmres, pc_type: hypre, "
+                      "norm_type: preconditioned, non_zero_init_guess: True}, output: {save_xdmf: False}}")
+    p = kb.ProblemKNPEMI(write(tmp_path, it), verbose=False)
+    p.solver_config["view_ksp"] = False
+    s = kb.SolverKNPEMI(p, solver_config=p.solver_config)
+    o = s._opts()
+    assert (o.pc, o.rtol, o.restart, o.max_it, o.project_nullspace, o.zero_mean_solution, o.refine) == (3, 1e-9, 30, 5000, 1, 0, 0)
+    s.amg_form = "block_jacobi"
+    assert s._opts().pc == 2
+    s.amg_form = "schur"
+    for pc_type, pc in (("gamg", 2), ("schur", 3), ("jacobi", 1), ("none", 0)):
+        s.pc_type = pc_type
+        assert s._opts().pc == pc
+    s.pc_type = "hypre"
+    s.use_P_mat = False
+    assert s._opts().pc == 0
+    s.use_P_mat = True
+    for attr, val, exc in (("pc_type", "ilu", NotImplementedError), ("ksp_type", "cg", NotImplementedError),
+                           ("norm_type", "unpreconditioned", NotImplementedError), ("amg_form", "bogus", ValueError)):
+        old = getattr(s, attr)
+        setattr(s, attr, val)
+        with pytest.raises(exc):
+            s._opts()
+        setattr(s, attr, old)
