@@ -8,11 +8,25 @@
 // (all per-iteration work) runs on the GPU (solver.cu).  oracle/amg.py restates the same algorithm in
 // numpy/scipy and tests compare the two hierarchies level by level.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <numeric>
 #include "common.cuh"
 
 namespace knp {
+
+// KNP_AMG_TIMING=1 prints the setup phases per level (host profiling aid)
+struct PhaseTimer {
+  bool on = getenv("KNP_AMG_TIMING") && atoi(getenv("KNP_AMG_TIMING"));
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  void lap(const char* what, int level, int n) {
+    if (!on) return;
+    const auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "amg setup level %d (n = %d): %-10s %.3f s\n", level, n, what, std::chrono::duration<double>(t1 - t0).count());
+    t0 = t1;
+  }
+};
 
 static inline int64_t hash32(int64_t i) {
   uint64_t x = ((uint64_t)i + 0x9E3779B9ull) & 0xFFFFFFFFull;
@@ -48,7 +62,47 @@ static void strength_graph(const CsrHost& A, double theta, Graph& S) {
       const double v = A.vals[j];
       if (c != i && v != 0.0 && std::fabs(v) >= theta * std::sqrt(d[i] * d[c])) strong[j] = 1;
     }
-  // symmetrise: collect (i,c) and (c,i)
+  // symmetrise S + S^T.  Fast path (structurally symmetric pattern with sorted rows -- every matrix of this library):
+  // entry (i,c) is strong if it or its transposed entry (c,i), found by binary search in row c, passes the test; rows
+  // are independent.  A missing transposed entry switches to the general (serial) construction below.
+  bool sym = true;
+  std::vector<uint8_t> ssym(strong);          // written per row, `strong` is only read: no race
+#pragma omp parallel for schedule(static) reduction(&& : sym)
+  for (int i = 0; i < n; ++i)
+    for (int j = A.indptr[i]; j < A.indptr[i + 1]; ++j) {
+      const int c = A.indices[j];
+      if (c == i) continue;
+      if (j > A.indptr[i] && A.indices[j - 1] >= c) sym = false;          // unsorted row
+      const int32_t* rb = A.indices.data() + A.indptr[c];
+      const int32_t* re = A.indices.data() + A.indptr[c + 1];
+      const int32_t* it = std::lower_bound(rb, re, i);
+      if (it == re || *it != i) {
+        if (strong[j]) sym = false;                                        // a strong entry without a transposed partner
+      } else if (strong[it - A.indices.data()]) {
+        ssym[j] = 1;                                                       // strong through the transposed entry
+      }
+    }
+  if (sym) {
+    S.n = n;
+    S.ptr.assign(n + 1, 0);
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; ++i) {
+      int k = 0;
+      for (int j = A.indptr[i]; j < A.indptr[i + 1]; ++j) k += ssym[j] != 0;
+      cnt[i + 1] = k;
+    }
+    for (int i = 0; i < n; ++i) S.ptr[i + 1] = S.ptr[i] + cnt[i + 1];
+    S.idx.resize(S.ptr[n]);
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; ++i) {
+      int pos = S.ptr[i];
+      for (int j = A.indptr[i]; j < A.indptr[i + 1]; ++j)
+        if (ssym[j]) S.idx[pos++] = A.indices[j];
+    }
+    return;
+  }
+  std::vector<uint8_t>().swap(ssym);
+  // general case: collect (i,c) and (c,i)
   for (int i = 0; i < n; ++i)
     for (int j = A.indptr[i]; j < A.indptr[i + 1]; ++j)
       if (strong[j]) {
@@ -258,6 +312,7 @@ int amg_setup_host(const CsrHost& A0, double theta, int coarse_size, int max_lev
   rhos.clear();
   As.push_back(A0);
   const double omega = 4.0 / 3.0;
+  PhaseTimer tm;
   while (As.back().n_rows > coarse_size && (int)As.size() < max_levels) {
     const CsrHost& A = As.back();
     const int n = A.n_rows;
@@ -269,8 +324,10 @@ int amg_setup_host(const CsrHost& A0, double theta, int coarse_size, int max_lev
       strength_graph(A, theta_l, S);
       if ((double)S.idx.size() >= 3.0 * n) break;
     }
+    tm.lap("strength", (int)As.size() - 1, n);
     std::vector<int32_t> agg;
     const int nagg = mis2_aggregate(S, agg);
+    tm.lap("mis2", (int)As.size() - 1, n);
     if (nagg >= 0.8 * n) break;
     // Gershgorin bound on rho(D^-1 A) (used by the Jacobi smoother of the V-cycle) and D^-1
     std::vector<double> dinv(n);
@@ -343,10 +400,14 @@ int amg_setup_host(const CsrHost& A0, double theta, int coarse_size, int max_lev
       }
     }
     std::vector<std::vector<std::pair<int32_t, double>>>().swap(prow);
+    tm.lap("prolong", (int)As.size() - 1, n);
     CsrHost R, AP, Ac;
     transpose(P, R);
+    tm.lap("transpose", (int)As.size() - 1, n);
     spgemm(A, P, AP);
+    tm.lap("A*P", (int)As.size() - 1, n);
     spgemm(R, AP, Ac);
+    tm.lap("R*(AP)", (int)As.size() - 1, n);
     rhos.push_back(rho);
     Ps.push_back(std::move(P));
     Rs.push_back(std::move(R));
