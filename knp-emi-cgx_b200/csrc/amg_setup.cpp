@@ -204,47 +204,61 @@ static int mis2_aggregate(const Graph& S, std::vector<int32_t>& agg) {
   return nagg;
 }
 
-// C = A * B (CSR, sorted columns out), row-parallel with a dense accumulator per thread
+// C = A * B (CSR, sorted columns out): two passes over the rows (count, then fill) with a dense marker / accumulator
+// per thread -- no per-row allocations
 static void spgemm(const CsrHost& A, const CsrHost& B, CsrHost& C) {
   const int n = A.n_rows, mcols = B.n_cols;
   C.n_rows = n;
   C.n_cols = mcols;
   C.indptr.assign(n + 1, 0);
-  std::vector<std::vector<int32_t>> rcols(n);
-  std::vector<std::vector<double>> rvals(n);
+  std::vector<int32_t> cnt(n, 0);
+#pragma omp parallel
+  {
+    std::vector<int32_t> mark(mcols, -1);
+#pragma omp for schedule(dynamic, 2048)
+    for (int i = 0; i < n; ++i) {
+      int k = 0;
+      for (int j = A.indptr[i]; j < A.indptr[i + 1]; ++j) {
+        const int r = A.indices[j];
+        for (int l = B.indptr[r]; l < B.indptr[r + 1]; ++l) {
+          const int c = B.indices[l];
+          if (mark[c] != i) {
+            mark[c] = i;
+            ++k;
+          }
+        }
+      }
+      cnt[i] = k;
+    }
+  }
+  for (int i = 0; i < n; ++i) C.indptr[i + 1] = C.indptr[i] + cnt[i];
+  C.indices.resize(C.indptr[n]);
+  C.vals.resize(C.indptr[n]);
 #pragma omp parallel
   {
     std::vector<double> acc(mcols, 0.0);
-    std::vector<int32_t> mark(mcols, -1), list;
-#pragma omp for schedule(dynamic, 1024)
+    std::vector<int32_t> mark(mcols, -1);
+#pragma omp for schedule(dynamic, 2048)
     for (int i = 0; i < n; ++i) {
-      list.clear();
+      int32_t* list = C.indices.data() + C.indptr[i];
+      int k = 0;
       for (int j = A.indptr[i]; j < A.indptr[i + 1]; ++j) {
-        const int k = A.indices[j];
+        const int r = A.indices[j];
         const double a = A.vals[j];
-        for (int l = B.indptr[k]; l < B.indptr[k + 1]; ++l) {
+        for (int l = B.indptr[r]; l < B.indptr[r + 1]; ++l) {
           const int c = B.indices[l];
           if (mark[c] != i) {
             mark[c] = i;
             acc[c] = 0.0;
-            list.push_back(c);
+            list[k++] = c;
           }
           acc[c] += a * B.vals[l];
         }
       }
-      std::sort(list.begin(), list.end());
-      rcols[i] = list;
-      rvals[i].resize(list.size());
-      for (size_t t = 0; t < list.size(); ++t) rvals[i][t] = acc[list[t]];
+      std::sort(list, list + k);
+      double* v = C.vals.data() + C.indptr[i];
+      for (int t = 0; t < k; ++t) v[t] = acc[list[t]];
     }
-  }
-  for (int i = 0; i < n; ++i) C.indptr[i + 1] = C.indptr[i] + (int32_t)rcols[i].size();
-  C.indices.resize(C.indptr[n]);
-  C.vals.resize(C.indptr[n]);
-#pragma omp parallel for schedule(static)
-  for (int i = 0; i < n; ++i) {
-    std::copy(rcols[i].begin(), rcols[i].end(), C.indices.begin() + C.indptr[i]);
-    std::copy(rvals[i].begin(), rvals[i].end(), C.vals.begin() + C.indptr[i]);
   }
 }
 
@@ -349,57 +363,85 @@ int amg_setup_host(const CsrHost& A0, double theta, int coarse_size, int max_lev
     // entries per row (the Galerkin levels of 3D meshes); on sparse coarse levels the unfiltered smoother gives the
     // better prolongator (2D: 40 instead of 49 GMRES iterations at N = 512).
     const bool filtered = As.size() == 1 || (double)A.nnz() > 32.0 * n;
-    std::vector<std::vector<std::pair<int32_t, double>>> prow(n);
-    double rhoF = 0.0;
-#pragma omp parallel for schedule(dynamic, 1024) reduction(max : rhoF)
-    for (int i = 0; i < n; ++i) {
-      auto& row = prow[i];
-      double diagF = 0.0, sabs = 0.0;
-      int sp = S.ptr[i];
-      const int se = S.ptr[i + 1];
-      for (int j = A.indptr[i]; j < A.indptr[i + 1]; ++j) {
-        const int c = A.indices[j];
-        const double v = A.vals[j];
-        while (sp < se && S.idx[sp] < c) ++sp;
-        const bool strong = !filtered || (sp < se && S.idx[sp] == c);
-        if (c == i || !strong) {
-          diagF += v;
-        } else {
-          row.emplace_back(agg[c], v);
-          sabs += std::fabs(v);
-        }
-      }
-      row.emplace_back(agg[i], diagF);
-      rhoF = std::max(rhoF, std::fabs(dinv[i]) * (std::fabs(diagF) + sabs));
-      std::sort(row.begin(), row.end(), [](const std::pair<int32_t, double>& a, const std::pair<int32_t, double>& b) {
-        return a.first < b.first;
-      });
-      size_t w = 0;
-      for (size_t r = 0; r < row.size(); ++r) {
-        if (w > 0 && row[w - 1].first == row[r].first) row[w - 1].second += row[r].second;
-        else row[w++] = row[r];
-      }
-      row.resize(w);
-    }
+    // two passes over the rows (count + Gershgorin bound, then fill) with a dense marker / accumulator per thread
     CsrHost P;
     P.n_rows = n;
     P.n_cols = nagg;
     P.indptr.assign(n + 1, 0);
-    for (int i = 0; i < n; ++i) P.indptr[i + 1] = P.indptr[i] + (int32_t)prow[i].size();
+    std::vector<int32_t> plen(n);
+    double rhoF = 0.0;
+#pragma omp parallel
+    {
+      std::vector<int32_t> mark(nagg, -1);
+#pragma omp for schedule(static) reduction(max : rhoF)
+      for (int i = 0; i < n; ++i) {
+        double diagF = 0.0, sabs = 0.0;
+        int sp = S.ptr[i], k = 1;
+        const int se = S.ptr[i + 1];
+        mark[agg[i]] = i;
+        for (int j = A.indptr[i]; j < A.indptr[i + 1]; ++j) {
+          const int c = A.indices[j];
+          const double v = A.vals[j];
+          while (sp < se && S.idx[sp] < c) ++sp;
+          const bool strong = !filtered || (sp < se && S.idx[sp] == c);
+          if (c == i || !strong) {
+            diagF += v;
+          } else {
+            sabs += std::fabs(v);
+            if (mark[agg[c]] != i) {
+              mark[agg[c]] = i;
+              ++k;
+            }
+          }
+        }
+        plen[i] = k;
+        rhoF = std::max(rhoF, std::fabs(dinv[i]) * (std::fabs(diagF) + sabs));
+      }
+    }
+    for (int i = 0; i < n; ++i) P.indptr[i + 1] = P.indptr[i] + plen[i];
     P.indices.resize(P.indptr[n]);
     P.vals.resize(P.indptr[n]);
     const double sc = omega / rhoF;
-#pragma omp parallel for schedule(static)
-    for (int i = 0; i < n; ++i) {
-      int pos = P.indptr[i];
-      for (const auto& e : prow[i]) {
-        double v = -(sc * dinv[i]) * e.second;
-        if (e.first == agg[i]) v += 1.0;
-        P.indices[pos] = e.first;
-        P.vals[pos++] = v;
+#pragma omp parallel
+    {
+      std::vector<int32_t> mark(nagg, -1);
+      std::vector<double> acc(nagg, 0.0);
+#pragma omp for schedule(static)
+      for (int i = 0; i < n; ++i) {
+        int32_t* list = P.indices.data() + P.indptr[i];
+        int sp = S.ptr[i], k = 0;
+        const int se = S.ptr[i + 1];
+        mark[agg[i]] = i;
+        acc[agg[i]] = 0.0;
+        list[k++] = agg[i];
+        double diagF = 0.0;
+        for (int j = A.indptr[i]; j < A.indptr[i + 1]; ++j) {
+          const int c = A.indices[j];
+          const double v = A.vals[j];
+          while (sp < se && S.idx[sp] < c) ++sp;
+          const bool strong = !filtered || (sp < se && S.idx[sp] == c);
+          if (c == i || !strong) {
+            diagF += v;
+          } else {
+            const int g = agg[c];
+            if (mark[g] != i) {
+              mark[g] = i;
+              acc[g] = 0.0;
+              list[k++] = g;
+            }
+            acc[g] += v;
+          }
+        }
+        acc[agg[i]] += diagF;
+        std::sort(list, list + k);
+        double* pv = P.vals.data() + P.indptr[i];
+        for (int t = 0; t < k; ++t) {
+          double v = -(sc * dinv[i]) * acc[list[t]];
+          if (list[t] == agg[i]) v += 1.0;
+          pv[t] = v;
+        }
       }
     }
-    std::vector<std::vector<std::pair<int32_t, double>>>().swap(prow);
     tm.lap("prolong", (int)As.size() - 1, n);
     CsrHost R, AP, Ac;
     transpose(P, R);
