@@ -27,15 +27,76 @@ sys.path.insert(0, ROOT)
 METRIC = "ms per KNP-EMI timestep (assembly+solve)"
 
 
-def workload_yaml(kb, n, cells_per_dim=8):
-    txt = open(os.path.join(os.path.dirname(kb.__file__), "configs", "c3_square2048_cells64.yaml")).read()
-    txt = txt.replace("N: 2048", f"N: {n}").replace("cells_per_dim: 8", f"cells_per_dim: {cells_per_dim}")
-    hi = 2 + cells_per_dim ** 2
-    txt = txt.replace("!range [2, 66]", f"!range [2, {hi}]")
+WORKLOADS = {
+    # name: (config file, N in the file, cells_per_dim in the file, gdim, models)
+    "c3": ("c3_square2048_cells64.yaml", 2048, 8, 2, ("NeuronalCT", "HH", "ATP")),
+    "c4": ("c4_cube120_cells64_passive.yaml", 120, 4, 3, ("Passive",)),
+}
+
+
+def workload_yaml(kb, workload, n, cells_per_dim=None, rtol=None):
+    fname, n0, m0, gdim, _ = WORKLOADS[workload]
+    m = cells_per_dim or m0
+    txt = open(os.path.join(os.path.dirname(kb.__file__), "configs", fname)).read()
+    txt = txt.replace(f"N: {n0}", f"N: {n}").replace(f"cells_per_dim: {m0}", f"cells_per_dim: {m}")
+    txt = txt.replace("!range [2, 66]", f"!range [2, {2 + m ** gdim}]")
+    if rtol is not None:
+        txt = txt.replace("ksp_rtol: 1.0e-9", f"ksp_rtol: {rtol:.1e}")
     f = tempfile.NamedTemporaryFile("w", suffix=".yaml", delete=False)
     f.write(txt)
     f.close()
     return f.name
+
+
+def build_problem(kb, workload, n, local, cells_per_dim=None, rtol=None, restart=30, amg_form=None):
+    """ProblemKNPEMI + SolverKNPEMI of one workload through the reference-facing API, preconditioner set up, t = 0."""
+    cfg = workload_yaml(kb, workload, n, cells_per_dim, rtol)
+    p = kb.ProblemKNPEMI(cfg, verbose=False, device=local)
+    os.unlink(cfg)
+    p.set_initial_conditions()
+    ctor = {"NeuronalCT": kb.NeuronalCotransporters, "HH": kb.HodgkinHuxley, "ATP": kb.ATPPump, "Passive": kb.PassiveModel}
+    p.init_ionic_models([ctor[nm](p) for nm in WORKLOADS[workload][4]])
+    p.setup_variational_form()
+    p.solver_config["view_ksp"] = False
+    s = kb.SolverKNPEMI(p, solver_config=p.solver_config)
+    s.gmres_restart = restart
+    if amg_form:
+        s.amg_form = amg_form
+    s.setup_solver()
+    p.setup_preconditioner(True)
+    s.ctx.pc_setup(s.opts)
+    s.ctx.set_time(0.0, 0)
+    return p, s
+
+
+def field_norms(kb, p):
+    """Global L2 norms of the eight fields (int u^2 over the field's own subdomain), all-reduced over the ranks."""
+    it, et = list(p.intra_tags), [p.extra_tag[0]]
+    return [math.sqrt(p.comm.allreduce(p.l2_norm_squared(p.wh[s][f], it if s == 0 else et), op=kb.MPI.SUM))
+            for s in range(2) for f in range(4)]
+
+
+def parity_check(kb, local):
+    """Rank-count independence of the distributed path, recorded in every bench line: two small fixed problems (BASELINE C3
+    and C4 in miniature) are stepped on ALL ranks of this run and the L2 norms of the eight fields are compared with the
+    values the CPU oracle produced for the same problems (tests/golden/parity_small.json, committed with its generating
+    script; the oracle itself is not imported here).  Tolerance 1e-8 relative (north star), potentials relative to the
+    potential scale."""
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "parity_small.json")))
+    out = {"tolerance": 1e-8, "ok": True, "cases": {}}
+    for name, wl in (("c3_mini", "c3"), ("c4_mini", "c4")):
+        g = gold[name]
+        p, s = build_problem(kb, wl, g["N"], local, cells_per_dim=g["cells_per_dim"], rtol=1e-12)
+        its = [int(s.ctx.step(s.opts).iterations) for _ in range(g["steps"])]
+        p._mark_device_newer()
+        got, ref = field_norms(kb, p), g["norms"]
+        scale = list(ref)
+        scale[3] = scale[7] = max(ref[3], ref[7])
+        err = max(abs(a - b) / sc for a, b, sc in zip(got, ref, scale))
+        out["cases"][name] = {"max_rel_err": err, "iterations": its, "ranks": p.comm.size}
+        out["ok"] = out["ok"] and bool(err < out["tolerance"])
+        s.ctx.close()
+    return out
 
 
 def peaks():
@@ -135,7 +196,7 @@ def run_reference(args):
         return
     n_s, cpd = args.cpu_sample_n, 8
     # the full workload's row count, needed to scale the sample to the metric's unit
-    per_dim = args.size
+    per_dim = args.size or 2048
     full_rows = None
     t0 = time.time()
     r = cpu_oracle_run(n_s, cpd, args.warmup, args.steps, None)
@@ -159,6 +220,29 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
+def timed_steps(ctx, opts, steps, barrier, comm, kb, world):
+    """K steps of the time loop, device-timed with the CUDA events knp_step records on its launching stream, bracketed by
+    barrier + synchronize; returns per-step means (max over ranks) and the iteration counts."""
+    barrier()
+    tot = asm = sol = 0.0
+    its = []
+    wall0 = time.perf_counter()
+    for _ in range(steps):
+        info = ctx.step(opts)
+        tm = ctx.last_timings()
+        tot += tm["total"]
+        asm += tm["gate"] + tm["facet"] + tm["rows"]
+        sol += tm["solve"]
+        its.append(int(info.iterations))
+    barrier()
+    wall = (time.perf_counter() - wall0) * 1e3 / steps
+    ms_dev = comm.allreduce(tot / steps, op=kb.MPI.MAX)
+    ms_wall = comm.allreduce(wall, op=kb.MPI.MAX)
+    return dict(ms=max(ms_dev, ms_wall) if world > 1 else ms_dev, ms_device=ms_dev, ms_wall=ms_wall,
+                assembly_ms=comm.allreduce(asm / steps, op=kb.MPI.MAX), solve_ms=comm.allreduce(sol / steps, op=kb.MPI.MAX),
+                iterations=its, local_total_ms=tot / steps)
+
+
 def run_ours(args):
     import torch
     import cgx_b200 as kb
@@ -177,24 +261,18 @@ def run_ours(args):
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"        # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    # weak scaling: cells per GPU fixed -> N grows with sqrt(world)
-    n = args.size if world == 1 else int(round(args.size * math.sqrt(world) / 8)) * 8
-    cfg = workload_yaml(kb, n)
+    wl = args.workload
+    gdim = WORKLOADS[wl][3]
+    base_n = args.size if args.size else WORKLOADS[wl][1]
+    if wl == "c3":
+        # weak scaling: cells per GPU fixed -> N grows with sqrt(world), rounded to the 8 x 8 cell array
+        n = base_n if world == 1 else int(round(base_n * math.sqrt(world) / 8)) * 8
+        scaling = "weak"
+    else:
+        n, scaling = base_n, "strong"                  # BASELINE C4: one fixed mesh sharded over the GPUs
     t_setup = time.time()
-    p = kb.ProblemKNPEMI(cfg, verbose=False, device=local)
-    p.set_initial_conditions()
-    p.init_ionic_models([kb.NeuronalCotransporters(p), kb.HodgkinHuxley(p), kb.ATPPump(p)])
-    p.setup_variational_form()
-    p.solver_config["view_ksp"] = False
-    s = kb.SolverKNPEMI(p, solver_config=p.solver_config)
-    s.gmres_restart = args.restart
-    if args.amg_form:
-        s.amg_form = args.amg_form
-    s.setup_solver()
-    p.setup_preconditioner(True)
+    p, s = build_problem(kb, wl, n, local, restart=args.restart, amg_form=args.amg_form)
     ctx = s.ctx
-    ctx.pc_setup(s.opts)
-    ctx.set_time(0.0, 0)
     t_setup = time.time() - t_setup
     comm = p.comm
 
@@ -213,22 +291,10 @@ def run_ours(args):
     sampler.start()
     l0 = kb.lib.launch_count()
     print(f"bench.py: {l0} kernel launches before the timed region (ncu -s)", file=sys.stderr, flush=True)
-    tot, asm, sol, its = 0.0, 0.0, 0.0, []
-    wall0 = time.perf_counter()
-    for _ in range(args.steps):
-        info = ctx.step(s.opts)
-        tm = ctx.last_timings()              # CUDA events on the launching stream, recorded inside knp_step
-        tot += tm["total"]
-        asm += tm["gate"] + tm["facet"] + tm["rows"]
-        sol += tm["solve"]
-        its.append(int(info.iterations))
-    barrier()
-    wall = (time.perf_counter() - wall0) * 1e3 / args.steps
+    T = timed_steps(ctx, s.opts, args.steps, barrier, comm, kb, world)
     launches = kb.lib.launch_count() - l0
     clocks = sampler.stop()
-    ms_dev = comm.allreduce(tot / args.steps, op=kb.MPI.MAX)
-    ms_wall = comm.allreduce(wall, op=kb.MPI.MAX)
-    ms = max(ms_dev, ms_wall) if world > 1 else ms_dev
+    ms, its = T["ms"], T["iterations"]
 
     # ---- end to end through the host-buffer C-ABI call (H2D of the state + step + D2H of the result every step)
     nst = ctx.n_cols
@@ -266,60 +332,108 @@ def run_ours(args):
 
     t_spmv = timeit(lambda: ctx.spmv(x.data_ptr(), y.data_ptr(), stream=sp), 20)
     t_asm = timeit(lambda: ctx.assemble(1e-4, stream=sp), 10)
+    comm.Barrier()
     t_pc = timeit(lambda: ctx.pc_apply(x.data_ptr(), y.data_ptr(), stream=sp), 10)
     m = p.mesh
     nvert, ncell = m.x.shape[0], m.cells.shape[0]
     B_spmv = 12 * ctx.nnz + 20 * ctx.n_rows
     B_asm = (8 * ctx.nnz + 16 * ctx.n_rows + 8 * m.gdim * nvert + (4 * (m.gdim + 1) + 4) * ncell
              + 32 * ctx.n_mverts + 16 * ctx.sizes.n_mfacets)
+    B_pc = ctx.pc_bytes() if hasattr(ctx, "pc_bytes") else None
     peak, peak_src = peaks()
     mean_its = float(np.mean(its))
-    share_spmv = (mean_its + 1) * t_spmv / (tot / args.steps)
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")      # dram__bytes_read+write per launch from the ncu --set full capture
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(f"spmv_stream_kernel<0>@N={n}") if world == 1 else None
-    roof = {"bound": "hbm", "kernel": "spmv_stream_kernel<EPI_SET> (y = A x, plain CSR, TMA-staged)", "achieved": B_spmv / t_spmv / 1e6,
-            "peak": peak, "unit": "GB/s", "frac": B_spmv / t_spmv / 1e6 / peak, "traffic": traffic, "peak_source": peak_src,
-            "algorithmic_bytes": B_spmv, "ms_per_launch": t_spmv, "share_of_step": share_spmv}
+    step_local = T["local_total_ms"]
+    # per step: (its + 1) A-SpMVs (one true residual per restart cycle) and (its + 2) preconditioner applications
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")      # dram__bytes_read+write per launch from the ncu --set full captures
+    if os.path.exists(tpath) and world == 1:
+        traffic = json.load(open(tpath))
     kernels = {
         "assembly (facet_kernel + rows_kernel)": {"ms": t_asm, "algorithmic_bytes": B_asm, "GB/s": B_asm / t_asm / 1e6,
-                                                  "frac": B_asm / t_asm / 1e6 / peak},
-        "spmv A": {"ms": t_spmv, "algorithmic_bytes": B_spmv, "GB/s": B_spmv / t_spmv / 1e6, "frac": roof["frac"]},
-        "amg_vcycle (pc_apply)": {"ms": t_pc},
+                                                  "frac": B_asm / t_asm / 1e6 / peak, "share_of_step": t_asm / step_local},
+        "spmv A (spmv_stream_kernel<EPI_SET>, plain CSR, TMA-staged)": {
+            "ms": t_spmv, "algorithmic_bytes": B_spmv, "GB/s": B_spmv / t_spmv / 1e6, "frac": B_spmv / t_spmv / 1e6 / peak,
+            "share_of_step": (mean_its + 1) * t_spmv / step_local, "traffic": traffic.get(f"spmv_stream_kernel<0>@{wl}:N={n}")},
+        "pc_apply (Schur preconditioner: two SA-AMG cycles + mass SpMV)": {
+            "ms": t_pc, "algorithmic_bytes": B_pc, "GB/s": (B_pc / t_pc / 1e6) if B_pc else None,
+            "frac": (B_pc / t_pc / 1e6 / peak) if B_pc else None, "share_of_step": (mean_its + 2) * t_pc / step_local,
+            "traffic": traffic.get(f"pc_apply@{wl}:N={n}")},
     }
+    # the roofline key names the kernel group with the largest share of the step
+    top = max((k for k in kernels if kernels[k].get("frac") is not None), key=lambda k: kernels[k]["share_of_step"])
+    kt = kernels[top]
+    roof = {"bound": "hbm", "kernel": top, "achieved": kt["GB/s"], "peak": peak, "unit": "GB/s", "frac": kt["frac"],
+            "traffic": kt.get("traffic"), "peak_source": peak_src, "algorithmic_bytes": kt["algorithmic_bytes"],
+            "ms_per_launch": kt["ms"], "share_of_step": kt["share_of_step"]}
     dofs_global = int(comm.allreduce(float(ctx.n_rows), op=kb.MPI.SUM))
     nnz_global = int(comm.allreduce(float(ctx.nnz), op=kb.MPI.SUM))
+    n_cells_global = int(p.global_mesh_info["n_cells"])
+    names = {"c3": f"BASELINE C3: synthetic 2D tissue block N={n} (8x8 cells), Na/K/Cl + HH+ATP+KCC2",
+             "c4": f"BASELINE C4: synthetic 3D tissue block N={n} (4x4x4 cells, {n_cells_global} tetrahedra), Na/K/Cl + passive membrane"}
+    ctx.close()
+    del p, s, ctx, x, y
+
+    # ---- BASELINE C4 (3D, ~10 M tetrahedra, passive membrane) sharded over the same GPUs: strong scaling, reported beside
+    #      the headline so that every driver-run record holds it (skipped when it IS the headline)
+    c4 = None
+    if wl != "c4" and not args.skip_c4:
+        tc = time.time()
+        p4, s4 = build_problem(kb, "c4", args.c4_size, local, restart=args.restart, amg_form=args.amg_form)
+        tc = time.time() - tc
+        for _ in range(3):
+            s4.ctx.step(s4.opts)
+        T4 = timed_steps(s4.ctx, s4.opts, max(3, min(args.steps, 5)), barrier, comm, kb, world)
+        c4 = {"workload": f"BASELINE C4: 3D tissue block N={args.c4_size} (4x4x4 cells), passive membrane, sharded over {world} GPU(s)",
+              "scaling": "strong", "ms_per_step": T4["ms"], "assembly_ms": T4["assembly_ms"], "solve_ms": T4["solve_ms"],
+              "iterations_per_step": T4["iterations"],
+              "ms_per_iteration": T4["solve_ms"] / max(1.0, float(np.mean(T4["iterations"]))),
+              "dofs": int(comm.allreduce(float(s4.ctx.n_rows), op=kb.MPI.SUM)),
+              "nnz": int(comm.allreduce(float(s4.ctx.nnz), op=kb.MPI.SUM)), "setup_s": tc}
+        s4.ctx.close()
+        del p4, s4
+
+    par = parity_check(kb, local) if not args.skip_parity else None
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = cpu_oracle_run(args.cpu_sample_n, 8, args.warmup, min(args.steps, 2))
-        scale = ctx.n_rows / r["rows"]
-        cpu = {"value": r["ms_sample"] * scale, "unit": "ms", "cores": 1, "kind": "port",
-               "sample": f"CPU oracle (numpy/scipy restatement of the DOLFINx/PETSc path, same GMRES + Schur/SA-AMG algorithm) on the same "
-                         f"generator at N={args.cpu_sample_n} ({r['rows']} rows, iterations {r['iterations']}), steps {args.warmup + 1}.."
-                         f"{args.warmup + min(args.steps, 2)}: {r['ms_sample']:.0f} ms/step (assembly {r['assembly_ms_sample']:.0f} ms), "
-                         f"scaled x{scale:.1f} by DOFs"}
+        cpu = cpu_baseline_leg(args)
     if rank == 0:
         line = {"metric": METRIC, "value": ms, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms, "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "ms_per_step": ms, "higher_is_better": False, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
-                "config": {"workload": f"BASELINE C3: synthetic 2D tissue block N={n} ({'x'.join(['8'] * 2)} cells), Na/K/Cl + HH+ATP+KCC2, "
-                                       f"GMRES({args.restart}) + charge-conservation Schur PC (SA-AMG blocks) rtol 1e-9, ICs perturbed as SURVEY 8(d)",
-                           "dofs": dofs_global, "nnz": nnz_global, "cells": int(p.global_mesh_info["n_cells"]),
+                "config": {"workload": names[wl] + f", GMRES({args.restart}) + charge-conservation Schur PC (SA-AMG blocks) rtol 1e-9"
+                                       + (", ICs perturbed as SURVEY 8(d)" if wl == "c3" else ""),
+                           "dofs": dofs_global, "nnz": nnz_global, "cells": n_cells_global,
                            "iterations_per_step": its, "timed_step_indices": [args.warmup + 1, args.warmup + args.steps],
-                           "l2_policy": "inputs (A: %.1f GB) larger than L2" % (12 * ctx.nnz / 1e9), "setup_s": t_setup},
-                "phases_ms": {"assembly": asm / args.steps, "solve": sol / args.steps},
+                           "l2_policy": "inputs (A: %.1f GB per GPU) larger than L2" % (12 * nnz_global / world / 1e9),
+                           "setup_s": t_setup},
+                "phases_ms": {"assembly": T["assembly_ms"], "solve": T["solve_ms"]},
+                "ms_per_iteration": T["solve_ms"] / max(1.0, mean_its),
                 "clocks": clocks,
                 "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": io_bytes, "d2h_bytes_per_step": io_bytes},
                 "gpu_launches": int(launches),
                 "roofline": roof, "kernels": kernels}
+        if c4:
+            line["c4"] = c4
+        if par:
+            line["parity_check"] = par
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
+    if par and not par["ok"]:
+        raise SystemExit(f"bench.py: parity check failed: {par}")
+
+
+def cpu_baseline_leg(args):
+    r = cpu_oracle_run(args.cpu_sample_n, 8, args.warmup, min(args.steps, 2))
+    return {"value": r["ms_sample"], "unit": "ms", "cores": 1, "kind": "port", "extrapolated": False,
+            "sample": f"CPU oracle (numpy/scipy restatement of the DOLFINx/PETSc path, same GMRES + Schur/SA-AMG algorithm) on the same "
+                      f"generator at N={args.cpu_sample_n} ({r['rows']} rows, iterations {r['iterations']}), steps {args.warmup + 1}.."
+                      f"{args.warmup + min(args.steps, 2)}: {r['ms_sample']:.0f} ms/step (assembly {r['assembly_ms_sample']:.0f} ms); "
+                      f"value is the measured sample, NOT scaled to the full workload"}
 
 
 def main():
@@ -328,7 +442,12 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--size", type=int, default=2048, help="grid squares per side on one GPU (BASELINE C3: 2048)")
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS),
+                    help="headline workload: c3 = BASELINE configs[2] (weak-scaled per GPU), c4 = configs[3] (strong)")
+    ap.add_argument("--size", type=int, default=0, help="grid squares per side (default: the BASELINE size of the workload)")
+    ap.add_argument("--c4-size", type=int, default=120, help="N of the C4 section reported beside the headline")
+    ap.add_argument("--skip-c4", action="store_true")
+    ap.add_argument("--skip-parity", action="store_true")
     ap.add_argument("--restart", type=int, default=30)
     ap.add_argument("--cpu-sample-n", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -445,6 +445,56 @@ def test_step_host_roundtrip_equals_device_resident(kb, cfgdir):
     assert np.array_equal(ps[0][0], ps[1][0]) and np.array_equal(ps[0][1], ps[1][1])
 
 
+@pytest.mark.parametrize("which", ["c3_2d_n256", "c4_3d_n32"])
+def test_midsize_time_loop_matches_oracle(kb, cfgdir, which):
+    """Mid-size multi-step comparison with the oracle through the reference-facing classes: BASELINE C3 at N = 256 (8 x 8
+    cells, HH + ATP + KCC2, perturbed initial state, 280 580 unknowns) and C4 at N = 32 (4 x 4 x 4 cells, passive,
+    143 748 vertices).  Both sides solve to rtol 1e-11 with their own preconditioner (the oracle with exact block solves in the
+    same Schur form), so the per-field norms of every timestep must agree to the north-star tolerance 1e-8."""
+    import tempfile
+    d3 = which.startswith("c4")
+    src = "c4_cube120_cells64_passive.yaml" if d3 else "c3_square2048_cells64.yaml"
+    txt = open(os.path.join(cfgdir, src)).read().replace("N: 120" if d3 else "N: 2048", "N: 32" if d3 else "N: 256")
+    txt = txt.replace("ksp_rtol: 1.0e-9", "ksp_rtol: 1.0e-11")
+    with tempfile.NamedTemporaryFile("w", suffix=".yaml", delete=False) as fh:
+        fh.write(txt)
+    p = kb.ProblemKNPEMI(fh.name, verbose=False)
+    os.unlink(fh.name)
+    p.set_initial_conditions()
+    models = [("Passive", None)] if d3 else MODELS_TEST
+    p.init_ionic_models([kb.PassiveModel(p)] if d3 else [kb.NeuronalCotransporters(p), kb.HodgkinHuxley(p), kb.ATPPump(p)])
+    p.setup_variational_form()
+    p.solver_config["view_ksp"] = False
+    s = kb.SolverKNPEMI(p, solver_config=p.solver_config)
+    s.setup_solver(); p.setup_preconditioner(True); s.ctx.pc_setup(s.opts); s.ctx.set_time(0.0, 0)
+    m = p.mesh
+    om = from_arrays(m.gdim, m.x, m.cells, m.cell_tags, m.intra_tags)
+    it = tuple(m.intra_tags)
+    op = OracleParams(intra_tags=it, extra_tag=1, membrane_tags=it, stimulus_tags=(2,) if not d3 else it)
+    o = KNPEMIOracle(om, op, models)
+    if not d3:                                       # configs/c3_*.yaml initial_perturbation
+        X = om.x / 1e-6
+        fac = 1 + 0.01 * np.sin(2 * np.pi * X[:, 0]) * np.sin(2 * np.pi * X[:, 1])
+        for sd in range(2):
+            o.c[sd] *= fac[None, :]
+        dphi = 0.005 * np.cos(2 * np.pi * X[:, 0])
+        o.phi_m += dphi
+        o.phi[0] += dphi
+    pc = SchurPC(o, exact=not d3)                   # 3D: sparse LU of the blocks takes a minute, the AMG form seconds
+    x = o.pack()
+    for i in range(3):
+        info = s.ctx.step(s.opts); p._mark_device_newer()
+        _, _, x, _ = o.step("gmres", pc, 1e-11, x, first=(i == 0))
+        for sd in range(2):
+            tags = list(it) if sd == 0 else [1]
+            for f in range(4):
+                ref = o.l2_norm(o.c[sd][f] if f < 3 else o.phi[sd], tags)
+                got = p.l2_norm(p.wh[sd][f], tags)
+                scale = ref if f < 3 else max(ref, o.l2_norm(o.phi[0], list(it)))
+                assert abs(got - ref) <= 1e-8 * scale, (i, sd, f, got, ref, info.iterations)
+    s.ctx.close()
+
+
 def test_3d_passive_time_loop_matches_oracle(kb):
     """BASELINE config C4 in miniature: 3D tissue block, PassiveModel, GMRES + AMG; full-size property:
     the assembled system keeps the phi-constant nullspace and the solution matches the oracle's."""
