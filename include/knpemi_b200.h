@@ -212,15 +212,23 @@ int knp_pattern_host(const knp_mesh_desc* mesh, int64_t* n_rows, int64_t* nnz, i
    blocks4 = {first row (multiple of 4), rows, 4-aligned first non-zero, staged non-zeros} per block; n_blocks = -1 when a
    group of four rows exceeds the stage capacity (the CSR-vector kernel is used then). */
 int knp_rowblocks_host(int32_t n_rows, const int32_t* indptr, int32_t max_blocks, int32_t* blocks4, int32_t* n_blocks);
-/* Host-only: which rank owns the global hierarchy of field 4 s + f in a multi-GPU run (replaces the processor-local hypre
-   hierarchies of the reference's MPI runs, KNPEMIx_solver.py:269-273). */
-int knp_field_owners_host(int32_t nranks, int64_t n_intra_global, int64_t n_extra_global, int32_t* owner8);
 /* Host-only (no GPU, not thread-safe): builds the smoothed-aggregation hierarchy of a CSR matrix with the setup code the
    preconditioners use (amg_setup.cpp; stands in for hypre's setup inside ksp.setUp, KNPEMIx_solver.py:386-389) and keeps
    it for inspection with knp_amg_host_level; used by the CPU test suite to compare with oracle/amg.py. */
 int knp_amg_setup_host(int32_t n, const int32_t* indptr, const int32_t* indices, const double* vals, double theta,
                        int32_t coarse_size, int32_t* n_levels);
 int knp_amg_host_level(int32_t level, int64_t* n, int64_t* nnz, int32_t* indptr, int32_t* indices, double* vals);
+/* Host-only (no GPU): the ROW-DISTRIBUTED hierarchy setup of multi-GPU runs (amg_dist.cpp; our counterpart of hypre running
+   across the MPI ranks, KNPEMIx_solver.py:269-273) on `nranks` SIMULATED ranks: the matrix is split by owner[] (rows with
+   owner == r belong to rank r), every rank runs the collective setup in its own thread, and the per-rank pieces are
+   assembled into global level operators / prolongators for inspection.  n_levels = distributed levels + the replicated
+   one.  knp_amg_dist_sim_level: which = 0 level operator, 1 prolongator to the next level; call with NULL arrays for the
+   sizes first.  knp_amg_dist_sim_perm: level-0 numbering of the assembled operators (new index -> input index). */
+int knp_amg_dist_sim_host(int32_t nranks, int32_t n, const int32_t* indptr, const int32_t* indices, const double* vals,
+                          const int32_t* owner, double theta, int64_t repl_threshold, int32_t* n_levels);
+int knp_amg_dist_sim_level(int32_t level, int32_t which, int64_t* n_rows, int64_t* n_cols, int64_t* nnz, double* rho,
+                           int32_t* indptr, int32_t* indices, double* vals);
+int knp_amg_dist_sim_perm(int32_t* perm0);
 
 /* ---- multi-GPU: halo exchange of ghost columns + all-reduce over NCCL (one rank per GPU) ----
  * Replaces PETSc VecScatter/ghostUpdate and MPI_Allreduce inside KSP (KNPEMI/KNPEMIx_solver.py:435,439,458-468). */

@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <numeric>
 #include "common.cuh"
+#include "amg_host.h"
 
 namespace knp {
 
@@ -36,13 +37,8 @@ static inline int64_t hash32(int64_t i) {
   return (int64_t)x;
 }
 
-struct Graph {
-  int n = 0;
-  std::vector<int32_t> ptr, idx;
-};
-
 // symmetric strength graph |a_ij| >= theta sqrt(|a_ii a_jj|), i != j, a_ij != 0; symmetrised (S + S^T)
-static void strength_graph(const CsrHost& A, double theta, Graph& S) {
+void strength_graph(const CsrHost& A, double theta, Graph& S) {
   const int n = A.n_rows;
   std::vector<double> d(n, 0.0);
 #pragma omp parallel for schedule(static)
@@ -148,7 +144,7 @@ static void nbr_max(const Graph& S, const std::vector<int64_t>& key, std::vector
 }
 
 // MIS(2) aggregation; identical decisions to oracle/amg.py::mis2_aggregate
-static int mis2_aggregate(const Graph& S, std::vector<int32_t>& agg) {
+int mis2_aggregate(const Graph& S, std::vector<int32_t>& agg) {
   const int n = S.n;
   std::vector<int64_t> pr(n), key(n), k1, k2;
   std::vector<int8_t> state(n, 0);
@@ -206,7 +202,7 @@ static int mis2_aggregate(const Graph& S, std::vector<int32_t>& agg) {
 
 // C = A * B (CSR, sorted columns out): two passes over the rows (count, then fill) with a dense marker / accumulator
 // per thread -- no per-row allocations
-static void spgemm(const CsrHost& A, const CsrHost& B, CsrHost& C) {
+void spgemm(const CsrHost& A, const CsrHost& B, CsrHost& C) {
   const int n = A.n_rows, mcols = B.n_cols;
   C.n_rows = n;
   C.n_cols = mcols;
@@ -262,7 +258,7 @@ static void spgemm(const CsrHost& A, const CsrHost& B, CsrHost& C) {
   }
 }
 
-static void transpose(const CsrHost& A, CsrHost& At) {
+void transpose(const CsrHost& A, CsrHost& At) {
   const int n = A.n_rows, m = A.n_cols;
   At.n_rows = m;
   At.n_cols = n;
@@ -282,7 +278,7 @@ static void transpose(const CsrHost& A, CsrHost& At) {
 }
 
 // dense inverse by LU with partial pivoting (coarsest level only; n <= a few thousand)
-static int dense_inverse(int n, std::vector<double>& M, std::vector<double>& inv) {
+int dense_inverse(int n, std::vector<double>& M, std::vector<double>& inv) {
   inv.assign((size_t)n * n, 0.0);
   for (int i = 0; i < n; ++i) inv[(size_t)i * n + i] = 1.0;
   for (int k = 0; k < n; ++k) {
@@ -317,6 +313,116 @@ static int dense_inverse(int n, std::vector<double>& M, std::vector<double>& inv
   return KNP_OK;
 }
 
+// Gershgorin bounds on rho(D^-1 A) (used by the Jacobi smoother of the cycle) and on rho(D^-1 A_F), and D^-1, for the
+// rows of A.  A may carry ghost columns (index >= n_own_cols, distributed levels): they count for rho and are lumped into
+// the diagonal of A_F like weak connections.
+void prolongator_bounds(const CsrHost& A, int n_own_cols, const Graph& S, bool filtered, std::vector<double>& dinv,
+                        double& rho_out, double& rhoF_out) {
+  const int n = A.n_rows;
+  dinv.resize(n);
+  double rho = 0.0, rhoF = 0.0;
+#pragma omp parallel for schedule(static) reduction(max : rho, rhoF)
+  for (int i = 0; i < n; ++i) {
+    double d = 0.0, s = 0.0;
+    for (int j = A.indptr[i]; j < A.indptr[i + 1]; ++j) {
+      if (A.indices[j] == i) d += A.vals[j];
+      s += std::fabs(A.vals[j]);
+    }
+    dinv[i] = 1.0 / d;
+    rho = std::max(rho, std::fabs(dinv[i]) * s);
+    double diagF = 0.0, sabs = 0.0;
+    int sp = S.ptr[i];
+    const int se = S.ptr[i + 1];
+    for (int j = A.indptr[i]; j < A.indptr[i + 1]; ++j) {
+      const int c = A.indices[j];
+      const double v = A.vals[j];
+      while (sp < se && S.idx[sp] < c) ++sp;
+      const bool strong = c < n_own_cols && (!filtered || (sp < se && S.idx[sp] == c));
+      if (c == i || !strong) diagF += v;
+      else sabs += std::fabs(v);
+    }
+    rhoF = std::max(rhoF, std::fabs(dinv[i]) * (std::fabs(diagF) + sabs));
+  }
+  rho_out = rho;
+  rhoF_out = rhoF;
+}
+
+// Prolongator smoothing with the FILTERED matrix A_F (strong off-diagonals only, weak ones -- and ghost columns -- lumped
+// into the diagonal so that row sums are kept): P = T - sc D^-1 A_F T, T(i, agg[i]) = 1, sc = omega / rho_F.  Without the
+// filter the Galerkin operators of 3D meshes fill in (hundreds of entries per row on level 2) and coarsening stalls.
+// Two passes over the rows (count, then fill) with a dense marker / accumulator per thread.
+void prolongator_build(const CsrHost& A, int n_own_cols, const Graph& S, const std::vector<int32_t>& agg, int nagg,
+                       bool filtered, const std::vector<double>& dinv, double sc, CsrHost& P) {
+  const int n = A.n_rows;
+  P.n_rows = n;
+  P.n_cols = nagg;
+  P.indptr.assign(n + 1, 0);
+  std::vector<int32_t> plen(n);
+#pragma omp parallel
+  {
+    std::vector<int32_t> mark(nagg, -1);
+#pragma omp for schedule(static)
+    for (int i = 0; i < n; ++i) {
+      int sp = S.ptr[i], k = 1;
+      const int se = S.ptr[i + 1];
+      mark[agg[i]] = i;
+      for (int j = A.indptr[i]; j < A.indptr[i + 1]; ++j) {
+        const int c = A.indices[j];
+        while (sp < se && S.idx[sp] < c) ++sp;
+        const bool strong = c < n_own_cols && (!filtered || (sp < se && S.idx[sp] == c));
+        if (c != i && strong && mark[agg[c]] != i) {
+          mark[agg[c]] = i;
+          ++k;
+        }
+      }
+      plen[i] = k;
+    }
+  }
+  for (int i = 0; i < n; ++i) P.indptr[i + 1] = P.indptr[i] + plen[i];
+  P.indices.resize(P.indptr[n]);
+  P.vals.resize(P.indptr[n]);
+#pragma omp parallel
+  {
+    std::vector<int32_t> mark(nagg, -1);
+    std::vector<double> acc(nagg, 0.0);
+#pragma omp for schedule(static)
+    for (int i = 0; i < n; ++i) {
+      int32_t* list = P.indices.data() + P.indptr[i];
+      int sp = S.ptr[i], k = 0;
+      const int se = S.ptr[i + 1];
+      mark[agg[i]] = i;
+      acc[agg[i]] = 0.0;
+      list[k++] = agg[i];
+      double diagF = 0.0;
+      for (int j = A.indptr[i]; j < A.indptr[i + 1]; ++j) {
+        const int c = A.indices[j];
+        const double v = A.vals[j];
+        while (sp < se && S.idx[sp] < c) ++sp;
+        const bool strong = c < n_own_cols && (!filtered || (sp < se && S.idx[sp] == c));
+        if (c == i || !strong) {
+          diagF += v;
+        } else {
+          const int g = agg[c];
+          if (mark[g] != i) {
+            mark[g] = i;
+            acc[g] = 0.0;
+            list[k++] = g;
+          }
+          acc[g] += v;
+        }
+      }
+      acc[agg[i]] += diagF;
+      std::sort(list, list + k);
+      double* pv = P.vals.data() + P.indptr[i];
+      for (int t = 0; t < k; ++t) {
+        double v = -(sc * dinv[i]) * acc[list[t]];
+        if (list[t] == agg[i]) v += 1.0;
+        pv[t] = v;
+      }
+    }
+  }
+}
+
 int amg_setup_host(const CsrHost& A0, double theta, int coarse_size, int max_levels, std::vector<CsrHost>& As,
                    std::vector<CsrHost>& Ps, std::vector<CsrHost>& Rs, std::vector<double>& rhos,
                    std::vector<double>& coarse_inv, bool invert) {
@@ -343,105 +449,16 @@ int amg_setup_host(const CsrHost& A0, double theta, int coarse_size, int max_lev
     const int nagg = mis2_aggregate(S, agg);
     tm.lap("mis2", (int)As.size() - 1, n);
     if (nagg >= 0.8 * n) break;
-    // Gershgorin bound on rho(D^-1 A) (used by the Jacobi smoother of the V-cycle) and D^-1
-    std::vector<double> dinv(n);
-    double rho = 0.0;
-#pragma omp parallel for schedule(static) reduction(max : rho)
-    for (int i = 0; i < n; ++i) {
-      double d = 0.0, s = 0.0;
-      for (int j = A.indptr[i]; j < A.indptr[i + 1]; ++j) {
-        if (A.indices[j] == i) d += A.vals[j];
-        s += std::fabs(A.vals[j]);
-      }
-      dinv[i] = 1.0 / d;
-      rho = std::max(rho, std::fabs(dinv[i]) * s);
-    }
-    // Prolongator smoothing with the FILTERED matrix A_F (strong off-diagonals only, weak ones lumped into the
-    // diagonal so that row sums are kept): P = T - (omega/rho_F) D^-1 A_F T, T(i, agg[i]) = 1.  Without the filter the
-    // Galerkin operators of 3D meshes fill in (hundreds of entries per row on level 2) and coarsening stalls.
-    // The filter is on for the finest level (mesh edges with vanishing stiffness) and for operators denser than 32
-    // entries per row (the Galerkin levels of 3D meshes); on sparse coarse levels the unfiltered smoother gives the
-    // better prolongator (2D: 40 instead of 49 GMRES iterations at N = 512).
+    // Gershgorin bounds, D^-1 and the smoothed prolongator (prolongator_bounds / prolongator_build below).  The filter is
+    // on for the finest level (mesh edges with vanishing stiffness) and for operators denser than 32 entries per row (the
+    // Galerkin levels of 3D meshes); on sparse coarse levels the unfiltered smoother gives the better prolongator
+    // (2D: 40 instead of 49 GMRES iterations at N = 512).
     const bool filtered = As.size() == 1 || (double)A.nnz() > 32.0 * n;
-    // two passes over the rows (count + Gershgorin bound, then fill) with a dense marker / accumulator per thread
+    std::vector<double> dinv;
+    double rho = 0.0, rhoF = 0.0;
+    prolongator_bounds(A, n, S, filtered, dinv, rho, rhoF);
     CsrHost P;
-    P.n_rows = n;
-    P.n_cols = nagg;
-    P.indptr.assign(n + 1, 0);
-    std::vector<int32_t> plen(n);
-    double rhoF = 0.0;
-#pragma omp parallel
-    {
-      std::vector<int32_t> mark(nagg, -1);
-#pragma omp for schedule(static) reduction(max : rhoF)
-      for (int i = 0; i < n; ++i) {
-        double diagF = 0.0, sabs = 0.0;
-        int sp = S.ptr[i], k = 1;
-        const int se = S.ptr[i + 1];
-        mark[agg[i]] = i;
-        for (int j = A.indptr[i]; j < A.indptr[i + 1]; ++j) {
-          const int c = A.indices[j];
-          const double v = A.vals[j];
-          while (sp < se && S.idx[sp] < c) ++sp;
-          const bool strong = !filtered || (sp < se && S.idx[sp] == c);
-          if (c == i || !strong) {
-            diagF += v;
-          } else {
-            sabs += std::fabs(v);
-            if (mark[agg[c]] != i) {
-              mark[agg[c]] = i;
-              ++k;
-            }
-          }
-        }
-        plen[i] = k;
-        rhoF = std::max(rhoF, std::fabs(dinv[i]) * (std::fabs(diagF) + sabs));
-      }
-    }
-    for (int i = 0; i < n; ++i) P.indptr[i + 1] = P.indptr[i] + plen[i];
-    P.indices.resize(P.indptr[n]);
-    P.vals.resize(P.indptr[n]);
-    const double sc = omega / rhoF;
-#pragma omp parallel
-    {
-      std::vector<int32_t> mark(nagg, -1);
-      std::vector<double> acc(nagg, 0.0);
-#pragma omp for schedule(static)
-      for (int i = 0; i < n; ++i) {
-        int32_t* list = P.indices.data() + P.indptr[i];
-        int sp = S.ptr[i], k = 0;
-        const int se = S.ptr[i + 1];
-        mark[agg[i]] = i;
-        acc[agg[i]] = 0.0;
-        list[k++] = agg[i];
-        double diagF = 0.0;
-        for (int j = A.indptr[i]; j < A.indptr[i + 1]; ++j) {
-          const int c = A.indices[j];
-          const double v = A.vals[j];
-          while (sp < se && S.idx[sp] < c) ++sp;
-          const bool strong = !filtered || (sp < se && S.idx[sp] == c);
-          if (c == i || !strong) {
-            diagF += v;
-          } else {
-            const int g = agg[c];
-            if (mark[g] != i) {
-              mark[g] = i;
-              acc[g] = 0.0;
-              list[k++] = g;
-            }
-            acc[g] += v;
-          }
-        }
-        acc[agg[i]] += diagF;
-        std::sort(list, list + k);
-        double* pv = P.vals.data() + P.indptr[i];
-        for (int t = 0; t < k; ++t) {
-          double v = -(sc * dinv[i]) * acc[list[t]];
-          if (list[t] == agg[i]) v += 1.0;
-          pv[t] = v;
-        }
-      }
-    }
+    prolongator_build(A, n, S, agg, nagg, filtered, dinv, omega / rhoF, P);
     tm.lap("prolong", (int)As.size() - 1, n);
     CsrHost R, AP, Ac;
     transpose(P, R);

@@ -667,15 +667,6 @@ int knp_rowblocks_host(int32_t n_rows, const int32_t* indptr, int32_t max_blocks
   return KNP_OK;
 }
 
-int knp_field_owners_host(int32_t nranks, int64_t n_intra_global, int64_t n_extra_global, int32_t* owner8) {
-  KNP_CHECK(nranks >= 1 && owner8, "bad arguments");
-  const int64_t size_s[2] = {n_intra_global, n_extra_global};
-  int owner[8];
-  assign_field_owners(nranks, size_s, owner);
-  for (int i = 0; i < 8; ++i) owner8[i] = owner[i];
-  return KNP_OK;
-}
-
 // ---- host-only hierarchy builder (no GPU needed): lets the CPU test suite compare amg_setup.cpp with oracle/amg.py ----
 static std::vector<CsrHost> g_host_levels;
 

@@ -188,6 +188,7 @@ struct Amg {
   int n_coarse = 0;
   int gamma = 1;                      // cycle index on levels 1..gamma_last (1: V-cycle, 2: W-cycle below the finest level)
   int gamma_last = 1 << 20;
+  int level0 = 0;                     // level number of levels[0] when this is the replicated tail of a distributed hierarchy
   std::vector<CsrHost> hostA;         // kept for inspection
   ~Amg() {
     for (auto* l : levels) delete l;

@@ -3,8 +3,39 @@
 #include <memory>
 #include "common.cuh"
 #include "kernels.cuh"
+#include "amg_host.h"
 
 struct ncclComm;
+
+namespace knp {
+// device side of HaloHost: ghosts are received in place at x + n_own + recv_ptr[i]
+struct HaloDev {
+  std::vector<int32_t> peers;
+  std::vector<int64_t> send_ptr, recv_ptr;
+  DevBuf<int32_t> send_idx;
+  DevBuf<double> sbuf;
+  int n_own = 0;
+};
+
+struct DistLevelDev {
+  int n_own = 0, n_ghost = 0;
+  CsrDev A, P, R;
+  DevBuf<double> dinv, x, b, r;
+  HaloDev halo;
+  double rho = 2.0;
+};
+
+// Row-distributed hierarchy: levels split by rows over the ranks (halo exchange per level SpMV), then one level gathered
+// onto every rank where the serial hierarchy `tail` continues redundantly (amg_dist.cpp).
+struct DistAmg {
+  std::vector<std::unique_ptr<DistLevelDev>> levels;
+  std::unique_ptr<Amg> tail;
+  std::vector<int64_t> off;            // row offsets of the ranks inside the replicated level
+  DevBuf<double> gb, gx, rb;           // replicated right-hand side / solution; this rank's piece of the right-hand side
+  int gamma = 1, gamma_last = 1 << 20;
+  std::vector<CsrHost> hostA;          // this rank's rows of the distributed level operators (inspection)
+};
+}  // namespace knp
 
 struct knp_ctx {
   int device = 0;
@@ -43,18 +74,11 @@ struct knp_ctx {
   std::unique_ptr<knp::Amg> amg;
   // charge-conservation Schur preconditioner (pc kind 3): hierarchies of the ion and of the potential blocks
   std::unique_ptr<knp::Amg> amg_c, amg_p;
+  // multi-GPU: the same hierarchies (and the one of pc kind 2) distributed by rows
+  std::unique_ptr<knp::DistAmg> damg, damg_c, damg_p;
   knp::DevBuf<double> M_vals, msig_inv, sch_vc, sch_zc, sch_t, sch_zp, sch_q, sch_rhs;
   knp::DevBuf<int32_t> sch_mblk[2];   // row blocks of the mass-matrix rows (s, field 0) for the streaming SpMV
   int sch_nmblk[2] = {0, 0};
-  // multi-GPU: FIELD-parallel hierarchies.  The eight diagonal blocks of the preconditioner are independent, so every
-  // block (field) gets ONE global hierarchy on one rank; right-hand-side pieces travel to the owner over NVLink.
-  struct FieldPar {
-    bool on = false;
-    int owner[8] = {0, 0, 0, 0, 0, 0, 0, 0};        // field (s, f) -> rank, index 4 s + f
-    int64_t base[8] = {0, 0, 0, 0, 0, 0, 0, 0};     // offset of the field inside its owner's merged ion / potential vector
-    std::vector<int64_t> off[2];                    // per subdomain: prefix sums of the ranks' owned node counts
-    knp::DevBuf<double> gc_in, gc_out, gp_in, gp_out;
-  } fp;
   // CUDA graphs of the preconditioner application, keyed by the (r, z) pointer pair (single-GPU runs)
   struct PcGraph {
     const double* r;
@@ -64,16 +88,6 @@ struct knp_ctx {
   };
   std::vector<PcGraph> pc_graphs;
   int pc_applies = 0;
-  // multi-GPU: the cycles of the field owners are captured on their own (the NCCL transfers stay outside the graphs)
-  struct CycleGraph {
-    const void* amg;
-    const double* in;
-    double* out;
-    cudaGraphExec_t exec;
-    unsigned long long launches;
-  };
-  std::vector<CycleGraph> cycle_graphs;
-  int cycle_calls = 0;
   // distributed
   ncclComm* comm = nullptr;
   int rank = 0, nranks = 1;
@@ -83,9 +97,7 @@ struct knp_ctx {
   knp::DevBuf<double> d_send_buf;
   int64_t n_phi_global = 0;   // global number of potential dofs (nullspace normalisation)
   std::vector<int32_t> h_recv_cols;   // ghost columns in receive order (host copy)
-  // two-level additive Schwarz coarse space: one constant per (rank, field block)
-  bool cz_on = false;
-  knp::DevBuf<double> cz_sums, cz_einv, cz_partial;
+  std::vector<int32_t> h_send_cols;   // owned columns in send order (host copy)
   // timers
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   double last_ms[5] = {0, 0, 0, 0, 0};
@@ -102,7 +114,18 @@ struct P2POp {
   bool send;
 };
 int p2p_exchange(knp_ctx* c, const std::vector<P2POp>& ops, cudaStream_t st);
-void assign_field_owners(int nranks, const int64_t size_s[2], int owner[8]);
+int halo_exchange_inplace(knp_ctx* c, HaloDev& H, double* x, cudaStream_t st);
+int halo_upload(const HaloHost& h, int n_own, HaloDev& d);
+struct NcclAmgComm : AmgComm {
+  knp_ctx* c;
+  explicit NcclAmgComm(knp_ctx* ctx) : c(ctx) {
+    rank = ctx->rank;
+    size = ctx->nranks;
+  }
+  int alltoallv(const std::vector<std::vector<char>>& send, std::vector<std::vector<char>>& recv) override;
+  int allreduce(double* v, int n, bool take_max) override;
+  int allgatherv(const std::vector<char>& mine, std::vector<std::vector<char>>& all) override;
+};
 int ensure_workspace(knp_ctx* c, int restart);
 int pc_setup(knp_ctx* c, const knp_solve_opts* o);
 int pc_apply(knp_ctx* c, const double* r, double* z, cudaStream_t st);

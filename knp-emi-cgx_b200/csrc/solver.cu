@@ -51,156 +51,6 @@ static int upload_csr(const CsrHost& h, CsrDev& d) {
   return KNP_OK;
 }
 
-// ---- two-level additive Schwarz coarse space for multi-GPU runs -------------------------------------------------
-// The processor-local AMG drops the couplings to ghost columns, which destroys the near-null constants of the phi
-// blocks (K_w - (C_M/F) M_Gamma): the membrane-capacitor modes would then be left to GMRES alone (thousands of
-// iterations).  One constant per (rank, field block) restores them: z += Z (Z^T P Z)^-1 Z^T r, with Z^T P Z formed
-// from the *global* P (ghost couplings included) and inverted redundantly on every rank (8 nranks x nranks systems).
-constexpr int CZ_BLOCKS = 64;
-
-__global__ void __launch_bounds__(256) cz_partial_kernel(Layout L, const double* __restrict__ r, double* __restrict__ partial) {
-  __shared__ double red[8];
-  const int fb = blockIdx.y;                    // field block 0..7
-  const int s = fb >> 2, f = fb & 3;
-  const int lo = L.row(s, f, 0), n = L.n_own[s];
-  const int per = (n + gridDim.x - 1) / gridDim.x;
-  const int a = blockIdx.x * per, b = min(n, a + per);
-  double acc = 0.0;
-  for (int i = a + threadIdx.x; i < b; i += 256) acc += r[lo + i];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
-  if (lane == 0) red[wid] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double t = 0.0;
-    for (int i = 0; i < 8; ++i) t += red[i];
-    partial[fb * gridDim.x + blockIdx.x] = t;
-  }
-}
-__global__ void cz_final_kernel(int nranks, int rank, int nb, const double* __restrict__ partial, double* __restrict__ sums) {
-  // sums[r*8 + fb]: zero except this rank's 8 entries
-  const int t = threadIdx.x;
-  if (t < 8 * nranks) {
-    double v = 0.0;
-    if (t / 8 == rank) {
-      const int fb = t % 8;
-      for (int i = 0; i < nb; ++i) v += partial[fb * nb + i];
-    }
-    sums[t] = v;
-  }
-}
-__global__ void cz_add_kernel(Layout L, int nranks, const double* __restrict__ sums, const double* __restrict__ einv,
-                              double* __restrict__ z) {
-  __shared__ double y[8];
-  if (threadIdx.x < 8) {
-    double t = 0.0;
-    for (int r = 0; r < nranks; ++r) t += einv[threadIdx.x * nranks + r] * sums[r * 8 + threadIdx.x];
-    y[threadIdx.x] = t;
-  }
-  __syncthreads();
-  const int n0 = 4 * L.n_own[0];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L.n_rows; i += gridDim.x * blockDim.x) {
-    const int fb = i < n0 ? i / max(L.n_own[0], 1) : 4 + (i - n0) / max(L.n_own[1], 1);
-    z[i] += y[fb];
-  }
-}
-
-static int coarse_setup(knp_ctx* c, const std::vector<int32_t>& idx, const std::vector<double>& val) {
-  c->cz_on = false;
-  if (c->nranks <= 1) return KNP_OK;
-  const Layout& L = c->T.L;
-  const int n = L.n_rows, nr = c->nranks, np = (int)c->peers.size();
-  std::vector<int32_t> ghost_owner((size_t)(L.n_cols - n), -1);
-  for (int i = 0; i < np; ++i)
-    for (int64_t k = c->recv_ptr[i]; k < c->recv_ptr[i + 1]; ++k) ghost_owner[c->h_recv_cols[k] - n] = c->peers[i];
-  std::vector<double> E((size_t)8 * nr * nr, 0.0);      // E[(r', fb), r] flattened as ((r'*8 + fb) * nr + r)
-  for (int s = 0; s < 2; ++s)
-    for (int f = 0; f < 4; ++f)
-      for (int p = 0; p < L.n_own[s]; ++p) {
-        const int row = L.row(s, f, p);
-        double* e = &E[((size_t)c->rank * 8 + 4 * s + f) * nr];
-        for (int j = c->H.indptr_P[row]; j < c->H.indptr_P[row + 1]; ++j) {
-          const int col = idx[j];
-          const int rj = col < n ? c->rank : ghost_owner[col - n];
-          if (rj < 0) {
-            set_error("coarse space: ghost column %d has no owner in the halo lists", col);
-            return KNP_E_INVALID;
-          }
-          e[rj] += val[j];
-        }
-      }
-  DevBuf<double> dE;
-  KNP_TRY(dE.upload(E));
-  KNP_TRY(allreduce_sum(c, dE.p, (int)E.size(), c->stream));
-  KNP_CUDA(cudaMemcpyAsync(E.data(), dE.p, E.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  KNP_CUDA(cudaStreamSynchronize(c->stream));
-  // per field block: invert the nr x nr matrix, keep this rank's row
-  std::vector<double> einv((size_t)8 * nr, 0.0);
-  for (int fb = 0; fb < 8; ++fb) {
-    std::vector<double> M((size_t)nr * nr), inv((size_t)nr * nr, 0.0);
-    for (int a = 0; a < nr; ++a)
-      for (int b = 0; b < nr; ++b) M[(size_t)a * nr + b] = E[((size_t)a * 8 + fb) * nr + b];
-    for (int a = 0; a < nr; ++a) {
-      bool empty = true;
-      for (int b = 0; b < nr; ++b) empty = empty && M[(size_t)a * nr + b] == 0.0 && M[(size_t)b * nr + a] == 0.0;
-      if (empty) M[(size_t)a * nr + a] = 1.0;      // rank without dofs of this field
-      inv[(size_t)a * nr + a] = 1.0;
-    }
-    for (int k = 0; k < nr; ++k) {                 // Gauss-Jordan with partial pivoting
-      int piv = k;
-      for (int a = k + 1; a < nr; ++a)
-        if (std::fabs(M[(size_t)a * nr + k]) > std::fabs(M[(size_t)piv * nr + k])) piv = a;
-      if (M[(size_t)piv * nr + k] == 0.0) {
-        set_error("coarse space matrix of field block %d is singular", fb);
-        return KNP_E_INVALID;
-      }
-      for (int b = 0; b < nr; ++b) {
-        std::swap(M[(size_t)k * nr + b], M[(size_t)piv * nr + b]);
-        std::swap(inv[(size_t)k * nr + b], inv[(size_t)piv * nr + b]);
-      }
-      const double d = 1.0 / M[(size_t)k * nr + k];
-      for (int b = 0; b < nr; ++b) {
-        M[(size_t)k * nr + b] *= d;
-        inv[(size_t)k * nr + b] *= d;
-      }
-      for (int a = 0; a < nr; ++a) {
-        if (a == k) continue;
-        const double fct = M[(size_t)a * nr + k];
-        for (int b = 0; b < nr; ++b) {
-          M[(size_t)a * nr + b] -= fct * M[(size_t)k * nr + b];
-          inv[(size_t)a * nr + b] -= fct * inv[(size_t)k * nr + b];
-        }
-      }
-    }
-    for (int b = 0; b < nr; ++b) einv[(size_t)fb * nr + b] = inv[(size_t)c->rank * nr + b];
-  }
-  KNP_TRY(c->cz_einv.upload(einv));
-  KNP_TRY(c->cz_sums.alloc((size_t)8 * nr));
-  KNP_TRY(c->cz_partial.alloc((size_t)8 * CZ_BLOCKS));
-  if (8 * nr > 1024) {
-    set_error("coarse space supports at most 128 ranks");
-    return KNP_E_UNSUPPORTED;
-  }
-  c->cz_on = true;
-  return KNP_OK;
-}
-
-static int coarse_apply(knp_ctx* c, const double* r, double* z, cudaStream_t st) {
-  if (!c->cz_on) return KNP_OK;
-  const Layout& L = c->T.L;
-  cz_partial_kernel<<<dim3(CZ_BLOCKS, 8), 256, 0, st>>>(L, r, c->cz_partial.p);
-  KNP_LAUNCHED();
-  cz_final_kernel<<<1, 1024, 0, st>>>(c->nranks, c->rank, CZ_BLOCKS, c->cz_partial.p, c->cz_sums.p);
-  KNP_LAUNCHED();
-  KNP_TRY(allreduce_sum(c, c->cz_sums.p, 8 * c->nranks, st));
-  int grid = (L.n_rows + 255) / 256;
-  if (grid > 148 * 8) grid = 148 * 8;
-  cz_add_kernel<<<grid, 256, 0, st>>>(L, c->nranks, c->cz_sums.p, c->cz_einv.p, z);
-  KNP_LAUNCHED();
-  return KNP_OK;
-}
-
 static int vcycle(Amg& M, int l, const double* bl, double* xout, cudaStream_t st);
 
 // In-place Gauss-Jordan inversion of a dense SPD matrix on the device (no pivoting needed for SPD operators): the
@@ -238,7 +88,8 @@ static int dense_inverse_device(int n, double* A, cudaStream_t st) {
 
 // builds the hierarchy of A0 on the host and uploads it; spd: coarsest operator (<= coarse_size unknowns) inverted on
 // the device
-static int build_amg(knp_ctx* c, const CsrHost& A0, std::unique_ptr<Amg>& out, int coarse_size = 600, bool spd = false) {
+static int build_amg(knp_ctx* c, const CsrHost& A0, std::unique_ptr<Amg>& out, int coarse_size = 600, bool spd = false,
+                     int level0 = 0) {
   std::vector<CsrHost> As, Ps, Rs;
   std::vector<double> rhos, cinv;
   KNP_TRY(amg_setup_host(A0, 0.08, coarse_size, 16, As, Ps, Rs, rhos, cinv, !spd));
@@ -264,8 +115,57 @@ static int build_amg(knp_ctx* c, const CsrHost& A0, std::unique_ptr<Amg>& out, i
   KNP_TRY(amg->cb.alloc(amg->n_coarse));
   KNP_TRY(amg->cx.alloc(amg->n_coarse));
   amg->hostA = std::move(As);
+  amg->level0 = level0;
   KNP_CUDA(cudaStreamSynchronize(c->stream));
   out = std::move(amg);
+  return KNP_OK;
+}
+
+// ---- multi-GPU: row-distributed hierarchies (amg_dist.cpp) --------------------------------------------------------
+// Every level operator is split by rows over the ranks like the system matrix itself; a level SpMV is preceded by one
+// packed halo exchange of its input (in-place receives, dist.cu).  Below `repl_threshold` global rows the level is
+// gathered onto every rank and the serial hierarchy continues redundantly, so the deep, latency-bound levels cost no
+// communication at all.  The reference gets the same structure from hypre running across its MPI ranks
+// (KNPEMIx_solver.py:269-273).
+static int64_t repl_threshold() {
+  static const int64_t v = getenv("KNP_AMG_REPL") ? atoll(getenv("KNP_AMG_REPL")) : 300000;
+  return v;
+}
+
+static int build_dist_amg(knp_ctx* c, CsrHost&& A0, HaloHost&& halo0, std::vector<int32_t>&& gown, std::vector<int32_t>&& goidx,
+                          std::unique_ptr<DistAmg>& out, int coarse_size, bool spd) {
+  NcclAmgComm comm(c);
+  DistHierarchyHost H;
+  KNP_TRY(amg_dist_setup(comm, std::move(A0), std::move(halo0), std::move(gown), std::move(goidx), 0.08, repl_threshold(), 16, H));
+  auto M = std::make_unique<DistAmg>();
+  for (DistLevelHost& h : H.levels) {
+    auto lv = std::make_unique<DistLevelDev>();
+    lv->n_own = h.n_own;
+    lv->n_ghost = h.n_ghost;
+    lv->rho = h.rho;
+    KNP_TRY(upload_csr(h.A, lv->A));
+    KNP_TRY(upload_csr(h.P, lv->P));
+    KNP_TRY(upload_csr(h.R, lv->R));
+    KNP_TRY(halo_upload(h.halo, h.n_own, lv->halo));
+    KNP_TRY(lv->dinv.alloc(h.n_own));
+    KNP_TRY(lv->x.alloc((size_t)h.n_own + h.n_ghost));
+    KNP_TRY(lv->b.alloc(h.n_own));
+    KNP_TRY(lv->r.alloc(h.n_own));
+    KNP_CUDA(cudaMemsetAsync(lv->x.p, 0, ((size_t)h.n_own + h.n_ghost) * sizeof(double), c->stream));
+    KNP_TRY(launch_extract_dinv(h.n_own, lv->A.indptr.p, lv->A.indices.p, lv->A.vals.p, lv->dinv.p, c->stream));
+    h.P = CsrHost();
+    h.R = CsrHost();
+    M->hostA.push_back(std::move(h.A));
+    M->levels.push_back(std::move(lv));
+  }
+  M->off = H.repl_off;
+  const int64_t ng = H.repl_off.back();
+  KNP_TRY(M->gb.alloc((size_t)ng));
+  KNP_TRY(M->gx.alloc((size_t)ng));
+  KNP_TRY(M->rb.alloc((size_t)(H.repl_off[c->rank + 1] - H.repl_off[c->rank]) + 1));
+  KNP_TRY(build_amg(c, H.Arepl, M->tail, coarse_size, spd, (int)M->levels.size()));
+  KNP_CUDA(cudaStreamSynchronize(c->stream));
+  out = std::move(M);
   return KNP_OK;
 }
 
@@ -328,226 +228,97 @@ __global__ void schur_merge_kernel(Layout L, const double* __restrict__ zc, cons
   }
 }
 
-// ---- multi-GPU: field-parallel hierarchies ---------------------------------------------------------------------
-// Processor-local hierarchies (block Jacobi over the ranks) ruin the Schur form: the truncated ion solves are wrong
-// near every rank boundary and GMRES needs 10-100x the iterations (2100 on 8 GPUs).  The eight diagonal blocks of the
-// preconditioner are independent problems, so instead of cutting every block into nranks pieces, every block gets ONE
-// global smoothed-aggregation hierarchy on ONE rank (each stage balanced by field size): the preconditioner is then the same operator as on a single GPU, independent of the partition.  Per
-// application every rank ships its piece of each right-hand side to the field's owner and gets its piece of the result
-// back (grouped ncclSend/ncclRecv over NVLink, 2 x 8 B per dof).
-// Field -> rank: the two stages (ion fields, then potential fields) run one after the other, so each stage is balanced
-// on its own: longest-processing-time-first over the global field sizes (ECS fields are ~3x the ICS ones).
-void assign_field_owners(int nranks, const int64_t size_s[2], int owner[8]) {
-  std::vector<int64_t> load(nranks, 0);
-  auto least = [&](int exclude) {
-    int best = -1;
-    for (int r = 0; r < nranks; ++r)
-      if (r != exclude && (best < 0 || load[r] < load[best])) best = r;
-    return best < 0 ? 0 : best;
-  };
-  const int big = size_s[1] >= size_s[0] ? 1 : 0;
-  for (int pass = 0; pass < 2; ++pass) {
-    const int s = pass == 0 ? big : 1 - big;
-    for (int f = 0; f < 3; ++f) {
-      const int r = least(-1);
-      owner[4 * s + f] = r;
-      load[r] += size_s[s];
-    }
-  }
-  // potentials: the larger one on the rank with the least ion work, the other one on a different rank
-  const int r_big = least(-1);
-  owner[4 * big + 3] = r_big;
-  owner[4 * (1 - big) + 3] = nranks > 1 ? least(r_big) : r_big;
-}
-
-static int schur_setup_fieldpar(knp_ctx* c, const std::vector<int32_t>& idx, const std::vector<double>& val) {
+// Level-0 operator of one part of the preconditioner on a multi-GPU run: this rank's rows in the part's compact numbering
+// with the ghost columns KEPT (numbered in the order the main halo receives them, so that the part's own halo receives in
+// place), the part's halo lists (the main lists filtered to the part) and, per ghost, the owner's compact index (obtained
+// with one exchange of an index vector through the main halo).  map(i): full row / owned column -> compact index or -1;
+// field_in_part(s, f): does field block (s, f) belong to the part.
+template <class MapFn, class FieldFn>
+static int dist_part(knp_ctx* c, const std::vector<int32_t>& ip, const std::vector<int32_t>& idx, const std::vector<double>& val,
+                     const std::vector<double>& owner_index, MapFn map, FieldFn field_in_part, int n_part, CsrHost& A,
+                     HaloHost& halo, std::vector<int32_t>& gown, std::vector<int32_t>& goidx) {
   const Layout& L = c->T.L;
-  const int R = c->nranks, me = c->rank;
-  cudaStream_t st = c->stream;
-  knp_ctx::FieldPar& F = c->fp;
-  const std::vector<int32_t>& ip = c->H.indptr_P;
-  // owned node counts of every rank and nnz of every (rank, field) piece
-  std::vector<double> tab((size_t)R * 10, 0.0);
-  for (int s = 0; s < 2; ++s) tab[(size_t)me * 10 + s] = L.n_own[s];
-  for (int s = 0; s < 2; ++s)
-    for (int f = 0; f < 4; ++f)
-      tab[(size_t)me * 10 + 2 + 4 * s + f] = L.n_own[s] ? (double)(ip[L.row(s, f, 0) + L.n_own[s]] - ip[L.row(s, f, 0)]) : 0.0;
-  {
-    DevBuf<double> d;
-    KNP_TRY(d.upload(tab));
-    KNP_TRY(allreduce_sum(c, d.p, (int)tab.size(), st));
-    KNP_CUDA(cudaMemcpyAsync(tab.data(), d.p, tab.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
-    KNP_CUDA(cudaStreamSynchronize(st));
-  }
-  auto nown = [&](int r, int s) { return (int64_t)tab[(size_t)r * 10 + s]; };
-  auto pnnz = [&](int r, int fld) { return (int64_t)tab[(size_t)r * 10 + 2 + fld]; };
-  for (int s = 0; s < 2; ++s) {
-    F.off[s].assign(R + 1, 0);
-    for (int r = 0; r < R; ++r) F.off[s][r + 1] = F.off[s][r] + nown(r, s);
-    KNP_CHECK(F.off[s][R] < ((int64_t)1 << 31), "global field too large for int32 columns");
-  }
-  // global node ids of the ghost columns: one halo exchange of an id vector (field-0 slots)
-  std::vector<double> ids(L.n_cols, 0.0);
-  for (int s = 0; s < 2; ++s)
-    for (int p = 0; p < L.n_own[s]; ++p) ids[L.col(s, 0, p)] = (double)(F.off[s][me] + p);
-  {
-    DevBuf<double> d;
-    KNP_TRY(d.upload(ids));
-    KNP_TRY(halo_exchange(c, d.p, st));
-    KNP_CUDA(cudaMemcpyAsync(ids.data(), d.p, ids.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
-    KNP_CUDA(cudaStreamSynchronize(st));
-  }
-  // my piece of every field: row lengths, GLOBAL columns, values
-  int64_t c_size = 0, p_size = 0;
-  {
-    const int64_t size_s[2] = {F.off[0][R], F.off[1][R]};
-    assign_field_owners(R, size_s, F.owner);
-  }
-  for (int s = 0; s < 2; ++s)
-    for (int f = 0; f < 4; ++f) {
-      const int fld = 4 * s + f;
-      if (F.owner[fld] == me) {
-        int64_t& acc = f < 3 ? c_size : p_size;
-        F.base[fld] = acc;
-        acc += F.off[s][R];
-      }
-    }
-  struct Piece {
-    std::vector<int32_t> len, col;
-    std::vector<double> val;
+  const int n = L.n_rows, np = (int)c->peers.size();
+  const int ngh_full = L.n_cols - n;
+  // field block of a full-layout ghost column
+  auto ghost_in_part = [&](int col) -> bool {
+    const int g = col - n;
+    const int s = g >= L.gbase[1] ? 1 : 0;
+    const int f = L.n_gh[s] > 0 ? (g - L.gbase[s]) / L.n_gh[s] : 0;
+    return field_in_part(s, f);
   };
-  std::vector<Piece> mine(8);
-  for (int s = 0; s < 2; ++s)
-    for (int f = 0; f < 4; ++f) {
-      Piece& P = mine[4 * s + f];
-      const int n_s = L.n_own[s];
-      P.len.resize(n_s);
-      for (int p = 0; p < n_s; ++p) {
-        const int row = L.row(s, f, p);
-        P.len[p] = ip[row + 1] - ip[row];
-        for (int j = ip[row]; j < ip[row + 1]; ++j) {
-          // column (s, f, q) -> global node id of q through the field-0 slot of the id vector
-          const int cfull = idx[j];
-          const int q = cfull < L.n_rows ? cfull - L.row(s, f, 0) : (cfull - L.n_rows - L.gbase[s] - f * L.n_gh[s]) + n_s;
-          P.col.push_back((int32_t)ids[L.col(s, 0, q)]);
-          P.val.push_back(val[j]);
-        }
-      }
+  std::vector<int32_t> ghost_id(ngh_full, -1);
+  halo.peers.clear();
+  halo.send_ptr.assign(1, 0);
+  halo.recv_ptr.assign(1, 0);
+  halo.send_idx.clear();
+  gown.clear();
+  goidx.clear();
+  for (int i = 0; i < np; ++i) {
+    for (int64_t k = c->send_ptr[i]; k < c->send_ptr[i + 1]; ++k) {
+      const int cc = map(c->h_send_cols[k]);
+      if (cc >= 0) halo.send_idx.push_back(cc);
     }
-  // ship the pieces to the owners (device staging; one grouped exchange)
-  std::vector<DevBuf<int32_t>> d_len(8), d_col(8);
-  std::vector<DevBuf<double>> d_val(8);
-  std::vector<std::vector<DevBuf<int32_t>>> r_len(8), r_col(8);
-  std::vector<std::vector<DevBuf<double>>> r_val(8);
-  std::vector<P2POp> ops;
-  for (int fld = 0; fld < 8; ++fld) {
-    const int s = fld >> 2, o = F.owner[fld];
-    if (o != me) {
-      KNP_TRY(d_len[fld].upload(mine[fld].len));
-      KNP_TRY(d_col[fld].upload(mine[fld].col));
-      KNP_TRY(d_val[fld].upload(mine[fld].val));
-      ops.push_back({o, d_len[fld].p, mine[fld].len.size() * 4, true});
-      ops.push_back({o, d_col[fld].p, mine[fld].col.size() * 4, true});
-      ops.push_back({o, d_val[fld].p, mine[fld].val.size() * 8, true});
-    } else {
-      r_len[fld] = std::vector<DevBuf<int32_t>>(R);
-      r_col[fld] = std::vector<DevBuf<int32_t>>(R);
-      r_val[fld] = std::vector<DevBuf<double>>(R);
-      for (int r = 0; r < R; ++r) {
-        if (r == me) continue;
-        KNP_TRY(r_len[fld][r].alloc((size_t)nown(r, s)));
-        KNP_TRY(r_col[fld][r].alloc((size_t)pnnz(r, fld)));
-        KNP_TRY(r_val[fld][r].alloc((size_t)pnnz(r, fld)));
-        ops.push_back({r, r_len[fld][r].p, (size_t)nown(r, s) * 4, false});
-        ops.push_back({r, r_col[fld][r].p, (size_t)pnnz(r, fld) * 4, false});
-        ops.push_back({r, r_val[fld][r].p, (size_t)pnnz(r, fld) * 8, false});
-      }
+    for (int64_t k = c->recv_ptr[i]; k < c->recv_ptr[i + 1]; ++k) {
+      const int col = c->h_recv_cols[k];
+      if (!ghost_in_part(col)) continue;
+      ghost_id[col - n] = (int32_t)gown.size();
+      gown.push_back(c->peers[i]);
+      goidx.push_back((int32_t)owner_index[col]);
     }
+    halo.peers.push_back(c->peers[i]);
+    halo.send_ptr.push_back((int64_t)halo.send_idx.size());
+    halo.recv_ptr.push_back((int64_t)gown.size());
   }
-  KNP_TRY(p2p_exchange(c, ops, st));
-  KNP_CUDA(cudaStreamSynchronize(st));
-  // merged global matrices of the fields this rank owns (block diagonal over the fields)
-  CsrHost Gc, Gp;
-  Gc.n_rows = Gc.n_cols = (int)c_size;
-  Gp.n_rows = Gp.n_cols = (int)p_size;
-  Gc.indptr.assign(1, 0);
-  Gp.indptr.assign(1, 0);
-  for (int pass = 0; pass < 2; ++pass)            // ion fields first, then the potential fields, each in base order
-    for (int fld = 0; fld < 8; ++fld) {
-      if (F.owner[fld] != me || ((fld & 3) < 3) != (pass == 0)) continue;
-      CsrHost& G = pass == 0 ? Gc : Gp;
-      const int s = fld >> 2;
-      KNP_CHECK((int64_t)G.indptr.size() - 1 == F.base[fld], "field-parallel layout mismatch");
-      for (int r = 0; r < R; ++r) {
-        std::vector<int32_t> len, col;
-        std::vector<double> v;
-        if (r == me) {
-          len.swap(mine[fld].len);
-          col.swap(mine[fld].col);
-          v.swap(mine[fld].val);
-        } else {
-          len.resize((size_t)nown(r, s));
-          col.resize((size_t)pnnz(r, fld));
-          v.resize((size_t)pnnz(r, fld));
-          if (!len.empty()) KNP_CUDA(cudaMemcpy(len.data(), r_len[fld][r].p, len.size() * 4, cudaMemcpyDeviceToHost));
-          if (!col.empty()) KNP_CUDA(cudaMemcpy(col.data(), r_col[fld][r].p, col.size() * 4, cudaMemcpyDeviceToHost));
-          if (!v.empty()) KNP_CUDA(cudaMemcpy(v.data(), r_val[fld][r].p, v.size() * 8, cudaMemcpyDeviceToHost));
-          r_len[fld][r].free();
-          r_col[fld][r].free();
-          r_val[fld][r].free();
-        }
-        size_t at = 0;
-        for (size_t p = 0; p < len.size(); ++p) {
-          // columns of one row sorted by global id (ghost columns interleave with owned ones)
-          std::vector<std::pair<int32_t, double>> row(len[p]);
-          for (int j = 0; j < len[p]; ++j, ++at) row[j] = {(int32_t)(col[at] + F.base[fld]), v[at]};
-          std::sort(row.begin(), row.end());
-          for (auto& e : row) {
-            G.indices.push_back(e.first);
-            G.vals.push_back(e.second);
-          }
-          G.indptr.push_back((int32_t)G.indices.size());
-        }
+  A.n_rows = n_part;
+  A.n_cols = n_part + (int)gown.size();
+  A.indptr.assign(1, 0);
+  A.indices.clear();
+  A.vals.clear();
+  for (int i = 0; i < n; ++i) {
+    if (map(i) < 0) continue;
+    const size_t row0 = A.indices.size();
+    bool sorted = true;
+    for (int j = ip[i]; j < ip[i + 1]; ++j) {
+      int cc;
+      if (idx[j] < n) {
+        cc = map(idx[j]);
+      } else {
+        cc = ghost_id[idx[j] - n];
+        if (cc >= 0) cc += n_part;
+      }
+      if (cc < 0) continue;
+      if (A.indices.size() > row0 && A.indices.back() >= cc) sorted = false;
+      A.indices.push_back(cc);
+      A.vals.push_back(val[j]);
+    }
+    if (!sorted) {                                   // ghost columns arrive in halo order, not ascending
+      std::vector<std::pair<int32_t, double>> row(A.indices.size() - row0);
+      for (size_t t = 0; t < row.size(); ++t) row[t] = {A.indices[row0 + t], A.vals[row0 + t]};
+      std::sort(row.begin(), row.end());
+      for (size_t t = 0; t < row.size(); ++t) {
+        A.indices[row0 + t] = row[t].first;
+        A.vals[row0 + t] = row[t].second;
       }
     }
-  if (c_size > 0) KNP_TRY(build_amg(c, Gc, c->amg_c, 2500, true));
-  if (p_size > 0) KNP_TRY(build_amg(c, Gp, c->amg_p, 2500, true));
-  KNP_TRY(F.gc_in.alloc((size_t)c_size));
-  KNP_TRY(F.gc_out.alloc((size_t)c_size));
-  KNP_TRY(F.gp_in.alloc((size_t)p_size));
-  KNP_TRY(F.gp_out.alloc((size_t)p_size));
-  F.on = true;
+    A.indptr.push_back((int32_t)A.indices.size());
+  }
+  KNP_CHECK((int)A.indptr.size() == n_part + 1, "distributed preconditioner part: row count mismatch");
   return KNP_OK;
 }
 
-// moves the ranks' pieces of the given fields to the owners' merged vectors (to_owner) or the results back
-static int fieldpar_move(knp_ctx* c, bool ions, bool to_owner, double* local, double* merged, cudaStream_t st) {
+// owner's compact index of every ghost column: x[i] = index(i) on owned rows, one main halo exchange
+template <class IndexFn>
+static int exchange_owner_index(knp_ctx* c, IndexFn index, std::vector<double>& out) {
   const Layout& L = c->T.L;
-  knp_ctx::FieldPar& F = c->fp;
-  const int R = c->nranks, me = c->rank, n0 = L.n_own[0];
-  std::vector<P2POp> ops;
-  for (int fld = 0; fld < 8; ++fld) {
-    const int s = fld >> 2, f = fld & 3;
-    if ((f < 3) != ions) continue;
-    // my piece inside the compact local vector: ions [s=0: 3 n0 | s=1: 3 n1] field-major, potentials [n0 | n1]
-    double* piece = ions ? local + (s ? 3 * n0 : 0) + (size_t)f * L.n_own[s] : local + (s ? n0 : 0);
-    const size_t mine = (size_t)L.n_own[s] * 8;
-    const int o = F.owner[fld];
-    if (o != me) {
-      ops.push_back({o, piece, mine, to_owner});
-    } else {
-      for (int r = 0; r < R; ++r) {
-        double* at = merged + F.base[fld] + F.off[s][r];
-        const size_t bytes = (size_t)(F.off[s][r + 1] - F.off[s][r]) * 8;
-        if (r == me) {
-          if (bytes) KNP_CUDA(cudaMemcpyAsync(to_owner ? at : piece, to_owner ? piece : at, bytes, cudaMemcpyDeviceToDevice, st));
-        } else {
-          ops.push_back({r, at, bytes, !to_owner});
-        }
-      }
-    }
-  }
-  return p2p_exchange(c, ops, st);
+  out.assign(L.n_cols, -1.0);
+  for (int i = 0; i < L.n_rows; ++i) out[i] = (double)index(i);
+  DevBuf<double> d;
+  KNP_TRY(d.upload(out));
+  KNP_TRY(halo_exchange(c, d.p, c->stream));
+  KNP_CUDA(cudaMemcpyAsync(out.data(), d.p, out.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  KNP_CUDA(cudaStreamSynchronize(c->stream));
+  return KNP_OK;
 }
 
 static int schur_setup(knp_ctx* c) {
@@ -559,7 +330,6 @@ static int schur_setup(knp_ctx* c) {
   KParams kp = c->kp;
   kp.C_M = -c->kp.C_M;
   KNP_TRY(launch_rows(c->T, kp, 1, c->u.p, c->fe.p, c->P_vals.p, nullptr, c->H.max_deg, c->H.max_gdeg, st));
-  c->P_assembled = true;
   // mass matrices: the same kernel with D = 0 leaves M in the ion blocks
   kp = c->kp;
   for (int k = 0; k < 3; ++k) kp.D[k] = 0.0;
@@ -591,7 +361,7 @@ static int schur_setup(knp_ctx* c) {
   App.n_rows = App.n_cols = n0 + n1;
   Acc.indptr.assign(1, 0);
   App.indptr.assign(1, 0);
-  for (int i = 0; i < n && c->nranks == 1; ++i) {     // multi-GPU runs build field-parallel global hierarchies instead
+  for (int i = 0; i < n && c->nranks == 1; ++i) {     // multi-GPU runs keep the ghost columns (dist_part below)
     const bool isc = cmap(i) >= 0;
     CsrHost& M = isc ? Acc : App;
     for (int j = ip[i]; j < ip[i + 1]; ++j) {
@@ -604,21 +374,36 @@ static int schur_setup(knp_ctx* c) {
     M.indptr.push_back((int32_t)M.indices.size());
   }
   // rows were visited in the order c(s=0), phi(s=0), c(s=1), phi(s=1) = ascending compact order in both parts
-  c->fp.on = false;
   if (c->nranks > 1) {
-    KNP_TRY(schur_setup_fieldpar(c, idx, val));
+    std::vector<double> oidx;
+    KNP_TRY(exchange_owner_index(c, [&](int i) { return cmap(i) >= 0 ? cmap(i) : pmap(i); }, oidx));
+    HaloHost hc, hp;
+    std::vector<int32_t> goc, gic, gop, gip;
+    KNP_TRY(dist_part(c, ip, idx, val, oidx, cmap, [](int, int f) { return f < 3; }, 3 * (n0 + n1), Acc, hc, goc, gic));
+    KNP_TRY(dist_part(c, ip, idx, val, oidx, pmap, [](int, int f) { return f == 3; }, n0 + n1, App, hp, gop, gip));
+    KNP_TRY(build_dist_amg(c, std::move(Acc), std::move(hc), std::move(goc), std::move(gic), c->damg_c, 2500, true));
+    KNP_TRY(build_dist_amg(c, std::move(App), std::move(hp), std::move(gop), std::move(gip), c->damg_p, 2500, true));
   } else {
     KNP_TRY(build_amg(c, Acc, c->amg_c, 2500, true));
     KNP_TRY(build_amg(c, App, c->amg_p, 2500, true));
   }
   // W-cycle on levels 1..3, V-cycle below: measured optimum on C3 (36 -> 15 iterations; deeper W recursion only adds
   // launch-bound visits of tiny levels)
-  for (Amg* a : {c->amg_c.get(), c->amg_p.get()})
+  int gamma_last = 3;
+  if (const char* e = getenv("KNP_W_LEVELS")) gamma_last = atoi(e);
+  for (Amg* a : {c->amg_c.get(), c->amg_p.get(), c->damg_c ? c->damg_c->tail.get() : nullptr,
+                 c->damg_p ? c->damg_p->tail.get() : nullptr})
     if (a) {
       a->gamma = 2;
-      a->gamma_last = 3;
-      if (const char* e = getenv("KNP_W_LEVELS")) a->gamma_last = atoi(e);
+      a->gamma_last = gamma_last;
     }
+  for (DistAmg* a : {c->damg_c.get(), c->damg_p.get()})
+    if (a) {
+      a->gamma = 2;
+      a->gamma_last = gamma_last;
+    }
+  // the P buffer now holds the sign-flipped Schur form, not the reference's block-Jacobi P: pc kinds 1 / 2 must re-assemble
+  c->P_assembled = false;
   // lumped M_sigma = (sum_k z_k^2 c_k / psi) at the node  x  row sum of the mass matrix
   std::vector<double> msig_inv((size_t)n0 + n1);
   const double* z = c->kp.z;
@@ -653,34 +438,7 @@ static int schur_setup(knp_ctx* c) {
   return KNP_OK;
 }
 
-// one cycle of a field owner's hierarchy, replayed from a CUDA graph after the first two calls (multi-GPU path)
-static int vcycle_graphed(knp_ctx* c, Amg& M, const double* in, double* out, cudaStream_t st) {
-  static const bool enabled = !(getenv("KNP_PC_GRAPH") && atoi(getenv("KNP_PC_GRAPH")) == 0);
-  if (!enabled) return vcycle(M, 0, in, out, st);
-  for (auto& g : c->cycle_graphs)
-    if (g.amg == &M && g.in == in && g.out == out) {
-      KNP_CUDA(cudaGraphLaunch(g.exec, st));
-      g_kernel_launches += g.launches;
-      return KNP_OK;
-    }
-  if (c->cycle_calls++ < 2 || c->cycle_graphs.size() >= 8) return vcycle(M, 0, in, out, st);   // warm-up first
-  const unsigned long long l0 = g_kernel_launches;
-  KNP_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-  const int rc = vcycle(M, 0, in, out, st);
-  cudaGraph_t graph = nullptr;
-  const cudaError_t e = cudaStreamEndCapture(st, &graph);
-  if (rc != KNP_OK || e != cudaSuccess || !graph) {
-    if (graph) cudaGraphDestroy(graph);
-    if (rc == KNP_OK) set_error("CUDA graph capture of a cycle failed: %s", cudaGetErrorString(e));
-    return rc != KNP_OK ? rc : KNP_E_CUDA;
-  }
-  cudaGraphExec_t exec = nullptr;
-  KNP_CUDA(cudaGraphInstantiate(&exec, graph, 0));
-  cudaGraphDestroy(graph);
-  c->cycle_graphs.push_back({&M, in, out, exec, g_kernel_launches - l0});
-  KNP_CUDA(cudaGraphLaunch(exec, st));
-  return KNP_OK;
-}
+static int vcycle_dist(knp_ctx* c, DistAmg& M, int l, const double* bl, double* xout, cudaStream_t st);
 
 static int schur_apply(knp_ctx* c, const double* r, double* zout, cudaStream_t st) {
   const Layout& L = c->T.L;
@@ -691,13 +449,8 @@ static int schur_apply(knp_ctx* c, const double* r, double* zout, cudaStream_t s
   if (grid < 1) grid = 1;
   schur_split_kernel<<<grid, 256, 0, st>>>(L, z[0], z[1], z[2], r, c->sch_vc.p, c->sch_t.p);
   KNP_LAUNCHED();
-  if (c->fp.on) {
-    KNP_TRY(fieldpar_move(c, true, true, c->sch_vc.p, c->fp.gc_in.p, st));
-    if (c->amg_c) KNP_TRY(vcycle_graphed(c, *c->amg_c, c->fp.gc_in.p, c->fp.gc_out.p, st));
-    KNP_TRY(fieldpar_move(c, true, false, c->sch_zc.p, c->fp.gc_out.p, st));
-  } else {
-    KNP_TRY(vcycle(*c->amg_c, 0, c->sch_vc.p, c->sch_zc.p, st));
-  }
+  if (c->damg_c) KNP_TRY(vcycle_dist(c, *c->damg_c, 0, c->sch_vc.p, c->sch_zc.p, st));
+  else KNP_TRY(vcycle(*c->amg_c, 0, c->sch_vc.p, c->sch_zc.p, st));
   schur_q_kernel<<<grid, 256, 0, st>>>(L, z[0], z[1], z[2], c->sch_zc.p, c->sch_q.p);
   KNP_LAUNCHED();
   KNP_TRY(halo_exchange(c, c->sch_q.p, st));
@@ -713,17 +466,10 @@ static int schur_apply(knp_ctx* c, const double* r, double* zout, cudaStream_t s
       KNP_TRY(launch_spmv(L.n_own[s], nnz_s, c->d_indptr_P.p + row0, c->d_indices_P.p, c->M_vals.p, c->sch_q.p, tout,
                           EPI_ADD, nullptr, nullptr, 0.0, st));
   }
-  if (c->fp.on) {
-    KNP_TRY(fieldpar_move(c, false, true, c->sch_t.p, c->fp.gp_in.p, st));
-    if (c->amg_p) KNP_TRY(vcycle_graphed(c, *c->amg_p, c->fp.gp_in.p, c->fp.gp_out.p, st));
-    KNP_TRY(fieldpar_move(c, false, false, c->sch_zp.p, c->fp.gp_out.p, st));
-  } else {
-    KNP_TRY(vcycle(*c->amg_p, 0, c->sch_t.p, c->sch_zp.p, st));
-  }
-  schur_merge_kernel<<<grid, 256, 0, st>>>(L, c->sch_zc.p, c->sch_zp.p, c->sch_t.p, c->msig_inv.p, c->sch_vc.p, zout,
-                                           c->cz_on ? c->sch_rhs.p : nullptr);
+  if (c->damg_p) KNP_TRY(vcycle_dist(c, *c->damg_p, 0, c->sch_t.p, c->sch_zp.p, st));
+  else KNP_TRY(vcycle(*c->amg_p, 0, c->sch_t.p, c->sch_zp.p, st));
+  schur_merge_kernel<<<grid, 256, 0, st>>>(L, c->sch_zc.p, c->sch_zp.p, c->sch_t.p, c->msig_inv.p, c->sch_vc.p, zout, nullptr);
   KNP_LAUNCHED();
-  if (c->cz_on) KNP_TRY(coarse_apply(c, c->sch_rhs.p, zout, st));
   return KNP_OK;
 }
 
@@ -735,7 +481,9 @@ int pc_setup(knp_ctx* c, const knp_solve_opts* o) {
   c->amg.reset();
   c->amg_c.reset();
   c->amg_p.reset();
-  c->cz_on = false;
+  c->damg.reset();
+  c->damg_c.reset();
+  c->damg_p.reset();
   c->pc_kind = o->pc;
   if (o->pc == 0) return KNP_OK;
   if (o->pc == 3) {
@@ -756,29 +504,26 @@ int pc_setup(knp_ctx* c, const knp_solve_opts* o) {
     set_error("unknown preconditioner kind %d", o->pc);
     return KNP_E_INVALID;
   }
-  // host copy of the owned-column part of P (processor-local block on multi-GPU runs)
+  // host copy of P: the whole matrix on one GPU, this rank's rows with their ghost columns on several
+  std::vector<int32_t> idx(c->H.nnz_P);
+  std::vector<double> val(c->H.nnz_P);
+  KNP_CUDA(cudaStreamSynchronize(c->stream));
+  KNP_CUDA(cudaMemcpy(idx.data(), c->d_indices_P.p, idx.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  KNP_CUDA(cudaMemcpy(val.data(), c->P_vals.p, val.size() * sizeof(double), cudaMemcpyDeviceToHost));
   CsrHost P0;
-  {
-    std::vector<int32_t> idx(c->H.nnz_P);
-    std::vector<double> val(c->H.nnz_P);
-    KNP_CUDA(cudaStreamSynchronize(c->stream));
-    KNP_CUDA(cudaMemcpy(idx.data(), c->d_indices_P.p, idx.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
-    KNP_CUDA(cudaMemcpy(val.data(), c->P_vals.p, val.size() * sizeof(double), cudaMemcpyDeviceToHost));
-    P0.n_rows = n;
-    P0.n_cols = n;
-    P0.indptr.assign(n + 1, 0);
-    P0.indices.reserve(idx.size());
-    P0.vals.reserve(idx.size());
-    for (int i = 0; i < n; ++i) {
-      for (int j = c->H.indptr_P[i]; j < c->H.indptr_P[i + 1]; ++j)
-        if (idx[j] < n) {
-          P0.indices.push_back(idx[j]);
-          P0.vals.push_back(val[j]);
-        }
-      P0.indptr[i + 1] = (int32_t)P0.indices.size();
-    }
-    KNP_TRY(coarse_setup(c, idx, val));
+  if (c->nranks > 1) {
+    std::vector<double> oidx;
+    KNP_TRY(exchange_owner_index(c, [](int i) { return i; }, oidx));
+    HaloHost h;
+    std::vector<int32_t> go, gi;
+    KNP_TRY(dist_part(c, c->H.indptr_P, idx, val, oidx, [](int i) { return i; }, [](int, int) { return true; }, n, P0, h, go, gi));
+    return build_dist_amg(c, std::move(P0), std::move(h), std::move(go), std::move(gi), c->damg, 600, false);
   }
+  P0.n_rows = n;
+  P0.n_cols = n;
+  P0.indptr = c->H.indptr_P;
+  P0.indices.swap(idx);
+  P0.vals.swap(val);
   return build_amg(c, P0, c->amg);
 }
 
@@ -797,7 +542,8 @@ static int vcycle(Amg& M, int l, const double* bl, double* xout, cudaStream_t st
   KNP_TRY(launch_scale_dinv(n, w, L.dinv.p, bl, L.x.p, st));
   // coarse-grid correction; levels >= 1 repeat it `gamma` times (gamma = 2: W-cycle below the finest level, which
   // restores the two-level convergence rate of deep hierarchies at ~25 % extra cost because level 0 is visited once)
-  const int reps = (l >= 1 && l <= M.gamma_last) ? M.gamma : 1;
+  const int lg = l + M.level0;        // level number inside a distributed hierarchy whose tail this is
+  const int reps = (lg >= 1 && lg <= M.gamma_last) ? M.gamma : 1;
   for (int rep = 0; rep < reps; ++rep) {
     // r = b - A x ; b_{l+1} = R r
     KNP_TRY(spmv(view(L.A), L.x.p, L.r.p, EPI_RESID, bl, nullptr, 0.0, st));
@@ -814,6 +560,46 @@ static int vcycle(Amg& M, int l, const double* bl, double* xout, cudaStream_t st
   return KNP_OK;
 }
 
+// the same cycle over the row-distributed levels: every SpMV with a level operator is preceded by the halo exchange of its
+// input; P and R are rank-local.  At the replicated level the ranks' pieces of the right-hand side are gathered (grouped
+// ncclSend/ncclRecv), every rank runs the serial tail and keeps its own piece of the result.
+static int vcycle_dist(knp_ctx* c, DistAmg& M, int l, const double* bl, double* xout, cudaStream_t st) {
+  const int nl = (int)M.levels.size();
+  if (l == nl) {
+    const int R = c->nranks, me = c->rank;
+    const size_t mine = (size_t)(M.off[me + 1] - M.off[me]) * sizeof(double);
+    std::vector<P2POp> ops;
+    for (int r = 0; r < R; ++r) {
+      if (r == me) continue;
+      if (mine) ops.push_back({r, const_cast<double*>(bl), mine, true});
+      const size_t theirs = (size_t)(M.off[r + 1] - M.off[r]) * sizeof(double);
+      if (theirs) ops.push_back({r, M.gb.p + M.off[r], theirs, false});
+    }
+    if (mine) KNP_CUDA(cudaMemcpyAsync(M.gb.p + M.off[me], bl, mine, cudaMemcpyDeviceToDevice, st));
+    KNP_TRY(p2p_exchange(c, ops, st));
+    KNP_TRY(vcycle(*M.tail, 0, M.gb.p, M.gx.p, st));
+    if (mine) KNP_CUDA(cudaMemcpyAsync(xout, M.gx.p + M.off[me], mine, cudaMemcpyDeviceToDevice, st));
+    return KNP_OK;
+  }
+  DistLevelDev& L = *M.levels[l];
+  const int n = L.n_own;
+  const double w = (4.0 / 3.0) / L.rho;
+  KNP_TRY(launch_scale_dinv(n, w, L.dinv.p, bl, L.x.p, st));
+  const int reps = (l >= 1 && l <= M.gamma_last) ? M.gamma : 1;
+  for (int rep = 0; rep < reps; ++rep) {
+    KNP_TRY(halo_exchange_inplace(c, L.halo, L.x.p, st));
+    KNP_TRY(spmv(view(L.A), L.x.p, L.r.p, EPI_RESID, bl, nullptr, 0.0, st));
+    double* bc = (l + 1 == nl) ? M.rb.p : M.levels[l + 1]->b.p;
+    double* xc = L.r.p;
+    KNP_TRY(spmv(view(L.R), L.r.p, bc, EPI_SET, nullptr, nullptr, 0.0, st));
+    KNP_TRY(vcycle_dist(c, M, l + 1, bc, xc, st));
+    KNP_TRY(spmv(view(L.P), xc, L.x.p, EPI_ADD, nullptr, nullptr, 0.0, st));
+  }
+  KNP_TRY(halo_exchange_inplace(c, L.halo, L.x.p, st));
+  KNP_TRY(spmv(view(L.A), L.x.p, xout, EPI_JACOBI, bl, L.dinv.p, w, st));
+  return KNP_OK;
+}
+
 __global__ void dinv_mul_kernel(int n, const double* __restrict__ dinv, const double* __restrict__ r, double* __restrict__ z) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) z[i] = dinv[i] * r[i];
 }
@@ -822,16 +608,15 @@ void pc_graphs_clear(knp_ctx* c) {
   for (auto& g : c->pc_graphs) cudaGraphExecDestroy(g.exec);
   c->pc_graphs.clear();
   c->pc_applies = 0;
-  for (auto& g : c->cycle_graphs) cudaGraphExecDestroy(g.exec);
-  c->cycle_graphs.clear();
-  c->cycle_calls = 0;
 }
 
 // The Schur application is ~200 small launches (W-cycle over two hierarchies): on one GPU it is captured once per
 // (r, z) pointer pair into a CUDA graph and replayed (GMRES always applies it to the same two buffers).
 static int schur_apply_graphed(knp_ctx* c, const double* r, double* z, cudaStream_t st) {
   static const bool enabled = !(getenv("KNP_PC_GRAPH") && atoi(getenv("KNP_PC_GRAPH")) == 0);
-  if (!enabled || c->nranks > 1) return schur_apply(c, r, z, st);
+  // multi-GPU: the application holds NCCL point-to-point groups; capturing them is opt-in (KNP_PC_GRAPH_MULTI=1)
+  static const bool multi = getenv("KNP_PC_GRAPH_MULTI") && atoi(getenv("KNP_PC_GRAPH_MULTI")) != 0;
+  if (!enabled || (c->nranks > 1 && !multi)) return schur_apply(c, r, z, st);
   for (auto& g : c->pc_graphs)
     if (g.r == r && g.z == z) {
       KNP_CUDA(cudaGraphLaunch(g.exec, st));
@@ -859,11 +644,9 @@ static int schur_apply_graphed(knp_ctx* c, const double* r, double* z, cudaStrea
 
 int pc_apply(knp_ctx* c, const double* r, double* z, cudaStream_t st) {
   const int n = c->T.L.n_rows;
-  if (c->pc_kind == 2 && c->amg) {
-    KNP_TRY(vcycle(*c->amg, 0, r, z, st));
-    return coarse_apply(c, r, z, st);
-  }
-  if (c->pc_kind == 3 && (c->fp.on || (c->amg_c && c->amg_p))) return schur_apply_graphed(c, r, z, st);
+  if (c->pc_kind == 2 && c->damg) return vcycle_dist(c, *c->damg, 0, r, z, st);
+  if (c->pc_kind == 2 && c->amg) return vcycle(*c->amg, 0, r, z, st);
+  if (c->pc_kind == 3 && ((c->damg_c && c->damg_p) || (c->amg_c && c->amg_p))) return schur_apply_graphed(c, r, z, st);
   if (c->pc_kind == 1) {
     int grid = (n + 255) / 256;
     if (grid > 148 * 16) grid = 148 * 16;

@@ -65,7 +65,8 @@ SYMBOLS = [
     "knp_csr_P_host", "knp_dofmap_host", "knp_mverts_host", "knp_set_params", "knp_stimulus_area_local",
     "knp_set_state", "knp_get_state", "knp_state_dev", "knp_phi_m_host", "knp_gate_step", "knp_assemble",
     "knp_assemble_P", "knp_values_dev", "knp_spmv", "knp_pc_setup", "knp_pc_apply", "knp_solve", "knp_step",
-    "knp_step_host", "knp_set_time", "knp_get_time", "knp_l2_norm_sq", "knp_integral", "knp_membrane_area", "knp_stimulus_current", "knp_last_timings", "knp_amg_num_levels", "knp_amg_part_levels", "knp_amg_setup_host", "knp_amg_host_level", "knp_pattern_host", "knp_rowblocks_host", "knp_field_owners_host",
+    "knp_step_host", "knp_set_time", "knp_get_time", "knp_l2_norm_sq", "knp_integral", "knp_membrane_area", "knp_stimulus_current", "knp_last_timings", "knp_amg_num_levels", "knp_amg_part_levels", "knp_amg_setup_host", "knp_amg_host_level", "knp_pattern_host", "knp_rowblocks_host",
+    "knp_amg_dist_sim_host", "knp_amg_dist_sim_level", "knp_amg_dist_sim_perm",
     "knp_copy", "knp_amg_level_sizes", "knp_amg_level_host", "knp_nccl_unique_id", "knp_dist_init", "knp_halo_exchange",
     "knp_allreduce_sum",
 ]
@@ -125,11 +126,13 @@ def load():
     lib.knp_amg_num_levels.argtypes = [vp]
     lib.knp_amg_part_levels.argtypes = [vp, C.c_int32]
     lib.knp_rowblocks_host.argtypes = [C.c_int32, vp, C.c_int32, vp, vp]
-    lib.knp_field_owners_host.argtypes = [C.c_int32, C.c_int64, C.c_int64, vp]
     lib.knp_pattern_host.argtypes = [vp, c_i64p, c_i64p, vp, vp, vp, vp, vp]
     lib.knp_amg_setup_host.argtypes = [C.c_int32, vp, vp, vp, C.c_double, C.c_int32, vp]
     lib.knp_amg_host_level.argtypes = [C.c_int32, c_i64p, c_i64p, vp, vp, vp]
     lib.knp_amg_level_sizes.argtypes = [vp, C.c_int32, c_i64p, c_i64p]
+    lib.knp_amg_dist_sim_host.argtypes = [C.c_int32, C.c_int32, vp, vp, vp, vp, C.c_double, C.c_int64, vp]
+    lib.knp_amg_dist_sim_level.argtypes = [C.c_int32, C.c_int32, c_i64p, c_i64p, c_i64p, c_f64p, vp, vp, vp]
+    lib.knp_amg_dist_sim_perm.argtypes = [vp]
     lib.knp_amg_level_host.argtypes = [vp, C.c_int32, vp, vp, vp]
     lib.knp_nccl_unique_id.argtypes = [C.c_char_p]
     lib.knp_dist_init.argtypes = [vp, C.c_int32, C.c_int32, C.c_char_p, C.c_int64, C.c_int32, vp, vp, vp, vp, vp]
@@ -442,6 +445,34 @@ def amg_setup_host(A, theta=0.08, coarse_size=600):
     return out
 
 
+def amg_dist_sim_host(A, owner, nranks, theta=0.08, repl_threshold=600):
+    """Row-distributed hierarchy setup on `nranks` simulated ranks (host only).  Returns (As, Ps, rhos, perm0): global level
+    operators (the last one is the replicated level), prolongators between them, the smoother bounds of the distributed
+    levels and the level-0 numbering (new index -> index in A)."""
+    import scipy.sparse as sp
+    lib = load()
+    A = sp.csr_matrix(A)
+    A.sort_indices()
+    ip, ix = np.ascontiguousarray(A.indptr, np.int32), np.ascontiguousarray(A.indices, np.int32)
+    va, ow = np.ascontiguousarray(A.data, np.float64), np.ascontiguousarray(owner, np.int32)
+    nl = C.c_int32()
+    check(lib.knp_amg_dist_sim_host(int(nranks), A.shape[0], _ptr(ip), _ptr(ix), _ptr(va), _ptr(ow), theta,
+                                    int(repl_threshold), C.byref(nl)))
+
+    def level(l, which):
+        nr, nc, nnz, rho = C.c_int64(), C.c_int64(), C.c_int64(), C.c_double()
+        check(lib.knp_amg_dist_sim_level(l, which, C.byref(nr), C.byref(nc), C.byref(nnz), C.byref(rho), None, None, None))
+        lp, li, lv = np.empty(nr.value + 1, np.int32), np.empty(nnz.value, np.int32), np.empty(nnz.value, np.float64)
+        check(lib.knp_amg_dist_sim_level(l, which, None, None, None, None, _ptr(lp), _ptr(li), _ptr(lv)))
+        return sp.csr_matrix((lv, li, lp), shape=(nr.value, nc.value)), rho.value
+
+    As = [level(l, 0) for l in range(nl.value)]
+    Ps = [level(l, 1)[0] for l in range(nl.value - 1)]
+    perm = np.empty(A.shape[0], np.int32)
+    check(lib.knp_amg_dist_sim_perm(_ptr(perm)))
+    return [a for a, _ in As], Ps, [r for _, r in As[:-1]], perm
+
+
 def rowblocks_host(indptr):
     """Row blocks of the streaming SpMV for a CSR row-pointer array: (n_blocks, 4) int32 or None (fallback kernel)."""
     lib = load()
@@ -453,11 +484,4 @@ def rowblocks_host(indptr):
         return None
     out = np.empty((nb.value, 4), np.int32)
     check(lib.knp_rowblocks_host(n, _ptr(ip), nb.value, _ptr(out), C.byref(nb)))
-    return out
-
-
-def field_owners_host(nranks, n_intra, n_extra):
-    lib = load()
-    out = np.empty(8, np.int32)
-    check(lib.knp_field_owners_host(int(nranks), int(n_intra), int(n_extra), _ptr(out)))
     return out

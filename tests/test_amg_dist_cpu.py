@@ -1,0 +1,118 @@
+"""CPU tier: the row-distributed smoothed-aggregation setup of multi-GPU runs (csrc/amg_dist.cpp) on SIMULATED ranks.
+
+The product's counterpart of hypre running across the MPI ranks (KNPEMIx_solver.py:269-273).  Checked without a GPU:
+  * one rank reproduces the serial setup (csrc/amg_setup.cpp, itself checked against oracle/amg.py) bit for bit;
+  * for 2, 4, 7 ranks the assembled level operators are the exact Galerkin products P^T A P of the GLOBAL operator
+    (couplings across rank boundaries are kept on every level), P is block diagonal over the ranks and reproduces
+    constants, and the replicated level is identical on every rank;
+  * the resulting cycle preconditions like the serial one as long as the distributed levels keep a few hundred rows per
+    rank (the product replicates a level once it has <= 300 000 rows globally): CG iterations within +3 of the serial
+    hierarchy for every partition.  Forcing distributed levels of ~20-80 rows per rank (threshold 200 on these 5 k - 30 k
+    row fixtures), where nearly every node sits on a rank boundary and the prolongator smoother is truncated, costs up to
+    +9 iterations (21 -> 28 on 7 ranks) -- which is why the threshold exists."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from oracle.fixtures import from_arrays
+from oracle.knpemi import KNPEMIOracle, OracleParams
+from oracle.amg import SAAMG
+
+
+def _blocks(kb, gdim, n, m):
+    """Ion block (M + dt D K of the three species on both subdomains) and coordinates of its rows."""
+    mesh = kb.mesh.cell_array_mesh(gdim, n, m)
+    om = from_arrays(gdim, mesh.x, mesh.cells, mesh.cell_tags, mesh.intra_tags)
+    it = tuple(mesh.intra_tags)
+    o = KNPEMIOracle(om, OracleParams(intra_tags=it, extra_tag=1, membrane_tags=it, stimulus_tags=it), [("Passive", None)])
+    Pt = o.assemble_P(membrane_sign=+1.0).tocsr()
+    ns = o.ns
+    ic = np.concatenate([np.arange(o.base[s], o.base[s] + 3 * ns[s]) for s in range(2)])
+    ip = np.concatenate([np.arange(o.base[s] + 3 * ns[s], o.base[s] + 4 * ns[s]) for s in range(2)])
+    xc = np.concatenate([np.tile(om.x[o.S[s]], (3, 1)) for s in range(2)])
+    xp = np.concatenate([om.x[o.S[s]] for s in range(2)])
+    return (Pt[ic][:, ic].tocsr(), xc), (Pt[ip][:, ip].tocsr(), xp)
+
+
+def _owners(kb, x, nranks):
+    import importlib
+    part = importlib.import_module("knp-emi-cgx_b200.partition")
+    return part.rcb_owner(x, nranks)
+
+
+class Cycle:
+    """V(1,1) cycle over given level operators / prolongators with a serial SAAMG tail on the last operator."""
+
+    def __init__(self, As, Ps, rhos, coarse_size=60):
+        self.As, self.Ps, self.rhos = As, Ps, rhos
+        self.tail = SAAMG(As[-1], coarse_size=coarse_size)
+
+    def __call__(self, b, l=0):
+        if l == len(self.Ps):
+            return self.tail(b)
+        A, P = self.As[l], self.Ps[l]
+        w = (4.0 / 3.0) / self.rhos[l]
+        dinv = 1.0 / A.diagonal()
+        x = w * dinv * b
+        x = x + P @ self(P.T @ (b - A @ x), l + 1)
+        return x + w * dinv * (b - A @ x)
+
+
+def _cg_iterations(A, M, rtol=1e-8):
+    rng = np.random.default_rng(0)
+    b = rng.standard_normal(A.shape[0])
+    its = [0]
+    x, info = spla.cg(A, b, rtol=rtol, maxiter=200, M=spla.LinearOperator(A.shape, matvec=M),
+                      callback=lambda xk: its.__setitem__(0, its[0] + 1))
+    assert info == 0
+    return its[0]
+
+
+@pytest.mark.parametrize("gdim,n,m", [(2, 48, 2), (3, 12, 2)])
+def test_one_rank_equals_serial_setup(kb, gdim, n, m):
+    (Acc, _), _ = _blocks(kb, gdim, n, m)
+    serial = kb.lib.amg_setup_host(Acc, coarse_size=60)
+    As, Ps, rhos, perm = kb.lib.amg_dist_sim_host(Acc, np.zeros(Acc.shape[0], np.int32), 1, repl_threshold=60)
+    assert np.array_equal(perm, np.arange(Acc.shape[0]))
+    assert len(As) == len(serial) and len(As) >= 3
+    for a, b in zip(As, serial):
+        assert a.shape == b.shape and np.array_equal(a.indptr, b.indptr) and np.array_equal(a.indices, b.indices)
+        assert np.array_equal(a.data, b.data)
+
+
+@pytest.mark.parametrize("gdim,n,m", [(2, 96, 2), (3, 16, 2)])
+@pytest.mark.parametrize("nranks", [2, 4, 7])
+def test_distributed_levels_are_galerkin_and_precondition_like_serial(kb, gdim, n, m, nranks):
+    for part, (A, x) in enumerate(_blocks(kb, gdim, n, m)):
+        owner = _owners(kb, x, nranks)
+        As, Ps, rhos, perm = kb.lib.amg_dist_sim_host(A, owner, nranks, repl_threshold=200)
+        assert len(Ps) >= 1, "the test must exercise at least one distributed level"
+        # level 0 is the input in rank order
+        A0 = A[perm][:, perm].tocsr()
+        A0.sort_indices()
+        assert abs(As[0] - A0).max() == 0.0
+        assert np.all(np.diff(owner[perm]) >= 0)
+        own_l = owner[perm]
+        for l, P in enumerate(Ps):
+            # exact Galerkin product of the global operator, couplings across the rank boundaries included
+            G = (P.T @ As[l] @ P).tocsr()
+            scale = abs(G).max()
+            assert abs(G - As[l + 1]).max() <= 1e-13 * scale
+            # constants are reproduced (row sums of the smoothed prolongator are 1 where A has zero row sums; the mass term
+            # perturbs them only slightly) and P is block diagonal over the ranks
+            Pc = P.tocoo()
+            counts = np.bincount(own_l, minlength=nranks)
+            coarse_counts = [np.unique(Pc.col[own_l[Pc.row] == r]).size for r in range(nranks)]
+            coarse_owner = np.repeat(np.arange(nranks), coarse_counts)
+            assert coarse_owner.size == P.shape[1]
+            assert np.array_equal(coarse_owner[Pc.col], own_l[Pc.row])
+            assert counts.sum() == P.shape[0]
+            own_l = coarse_owner
+        # the cycle built on the distributed hierarchy preconditions like the serial one
+        As, Ps, rhos, perm = kb.lib.amg_dist_sim_host(A, owner, nranks, repl_threshold=5000)
+        assert len(Ps) >= 1
+        serial = SAAMG(A, coarse_size=60)
+        its_serial = _cg_iterations(A, serial)
+        its_dist = _cg_iterations(As[0], Cycle(As, Ps, rhos))
+        assert its_dist <= its_serial + 3, (part, nranks, its_serial, its_dist)

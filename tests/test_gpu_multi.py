@@ -1,5 +1,10 @@
-"""2-GPU run of the distributed path (skipped when fewer than 2 GPUs are visible)."""
+"""2-GPU runs of the distributed path (skipped when fewer than 2 GPUs are visible).
+
+The preconditioner hierarchies are distributed by rows (csrc/amg_dist.cpp); KNP_AMG_REPL sets the global size below which a
+level is replicated on every rank.  The small fixtures here fall below the default (300 000), so every test also runs with
+a tiny threshold that forces genuinely distributed levels (halo exchange per level, rank-local prolongators)."""
 import os
+import re
 import subprocess
 import sys
 import pytest
@@ -8,37 +13,44 @@ from conftest import ROOT
 pytestmark = pytest.mark.gpu
 
 
-def test_two_gpu_time_loop_matches_oracle():
+def _torchrun(script, args, port, env_extra=None, nproc=2):
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    env.update(env_extra or {})
+    return subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+                           "--master-addr", "127.0.0.1", "--master-port", str(port), script] + list(args),
+                          capture_output=True, text=True, env=env, timeout=900)
+
+
+@pytest.mark.parametrize("repl", ["default", "300"])
+def test_two_gpu_time_loop_matches_oracle(repl):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     worker = os.path.join(os.path.dirname(__file__), "dist_gpu_worker.py")
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29531", worker],
-                       capture_output=True, text=True, env=dict(os.environ, PYTHONPATH=ROOT), timeout=600)
+    r = _torchrun(worker, [], 29531, {} if repl == "default" else {"KNP_AMG_REPL": repl})
     assert r.returncode == 0 and "MULTI_GPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
 
-def test_two_gpu_3d_time_loop_equals_single_gpu():
-    """BASELINE config C4 in miniature (3D, passive membrane): the field-parallel preconditioner is the same operator
-    for every partition, so a 2-GPU run needs the same GMRES iterations as a 1-GPU run and the per-field norms agree
-    to solver tolerance."""
-    import re
+@pytest.mark.parametrize("repl", ["default", "2000"])
+def test_two_gpu_3d_time_loop_equals_single_gpu(repl):
+    """BASELINE config C4 in miniature (3D, passive membrane): a 2-GPU run reaches the same solution as a 1-GPU run (per-field
+    norms to solver tolerance) in about as many GMRES iterations -- the distributed hierarchy keeps all couplings across the
+    rank boundary, only the aggregates (and the prolongator smoothing) stop at it."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     script = os.path.join(ROOT, "scripts", "dist_c4.py")
     env = dict(os.environ, PYTHONPATH=ROOT)
+    extra = {} if repl == "default" else {"KNP_AMG_REPL": repl}
     outs = []
-    for cmd in ([sys.executable, script, "16", "3"],
-                [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
-                 "127.0.0.1", "--master-port", "29533", script, "16", "3"]):
-        r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
+    r1 = subprocess.run([sys.executable, script, "16", "3"], capture_output=True, text=True, env=env, timeout=600)
+    r2 = _torchrun(script, ["16", "3"], 29533, extra)
+    for r in (r1, r2):
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
-        its = re.search(r"iterations (\[[^\]]*\])", r.stdout).group(1)
+        its = [int(v) for v in re.search(r"iterations \[([^\]]*)\]", r.stdout).group(1).split(",")]
         norms = [float(v) for v in re.search(r"norms (.*)", r.stdout).group(1).split()]
         outs.append((its, norms))
-    assert outs[0][0] == outs[1][0], outs
+    assert all(abs(a - b) <= 2 for a, b in zip(outs[0][0], outs[1][0])), outs
     scale = max(outs[0][1][3], outs[0][1][7])
     for k, (a, b) in enumerate(zip(outs[0][1], outs[1][1])):
         ref = a if k % 4 != 3 else max(a, scale)          # potentials relative to the potential scale

@@ -236,26 +236,6 @@ def test_native_spmv_rowblocks_cover_every_row_once(kb):
     assert kb.lib.rowblocks_host(np.array([0, 2000, 4000], np.int32)) is None
 
 
-@pytest.mark.parametrize("nranks", [2, 3, 4, 8, 16])
-def test_native_field_owner_assignment(kb, nranks):
-    """Multi-GPU field -> rank map (solver.cu::assign_field_owners): each stage balanced largest-first, the two potential
-    fields on different ranks, deterministic."""
-    ni, ne = 1_000_000, 3_000_000
-    own = kb.lib.field_owners_host(nranks, ni, ne)
-    assert np.array_equal(own, kb.lib.field_owners_host(nranks, ni, ne))
-    assert ((own >= 0) & (own < nranks)).all()
-    load = np.zeros(nranks)
-    for s, size in ((0, ni), (1, ne)):
-        for f in range(3):
-            load[own[4 * s + f]] += size
-    total = 3 * (ni + ne)
-    assert load.max() <= max(ne, total / nranks + ne)          # LPT bound: within one largest job of the average
-    if nranks >= 6:
-        assert load.max() == ne                                  # every ion field alone on a rank
-    assert own[3] != own[7]
-    assert own[7] == int(np.argmin(load))                        # the large potential field goes to the least loaded rank
-
-
 def test_solver_option_mapping(kb, tmp_path):
     """SolverKNPEMI._opts: how the reference's solver settings (KNPEMIx_solver.py:25-51,164-291) map onto the C-ABI
     knp_solve_opts -- `pc_type: hypre` -> the Schur preconditioner (pc 3) unless amg_form says block_jacobi, gamg -> the
