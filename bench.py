@@ -146,77 +146,92 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- CPU arm
-def cpu_oracle_run(n_sample, cells_per_dim, warmup, steps, n_full_rows=None):
-    """Times the CPU oracle (numpy/scipy restatement of the reference path + the same GMRES + Schur/SA-AMG algorithm) on a
-    bounded sample of the workload: same tissue-block generator at a smaller N, same step indices."""
+def cpu_workload(workload, n, restart=30):
+    """The C++/OpenMP CPU baseline (oracle/cpu.py -> oracle/libknpemi_cpu.so: restatement of the reference's time-loop body
+    with the same GMRES + Schur/SA-AMG algorithm, all host cores) set up on the FULL workload: same generator, same initial
+    state, same models as the GPU arm.  Returns (baseline, description)."""
     import cgx_b200 as kb
-    from oracle.fixtures import from_arrays
-    from oracle.knpemi import KNPEMIOracle, OracleParams
-    from oracle.amg import SchurPC
-    m = kb.mesh.cell_array_mesh(2, n_sample, cells_per_dim)
-    om = from_arrays(2, m.x, m.cells, m.cell_tags, m.intra_tags)
-    it = tuple(m.intra_tags)
-    p = OracleParams(intra_tags=it, extra_tag=1, membrane_tags=it, stimulus_tags=(2,))
-    o = KNPEMIOracle(om, p, [("NeuronalCT", None), ("HH", None), ("ATP", None)])
-    X = om.x / 1e-6
-    fac = 1 + 0.01 * np.sin(2 * np.pi * X[:, 0]) * np.sin(2 * np.pi * X[:, 1])
-    for s in range(2):
-        o.c[s] *= fac[None, :]
-    dphi = 0.005 * np.cos(2 * np.pi * X[:, 0])
-    o.phi_m += dphi
-    o.phi[0] += dphi
-    amg = SchurPC(o)
-    x = o.pack()
-    t_asm, t_step, its = [], [], []
+    from oracle.cpu import CpuBaseline
+    from oracle.knpemi import OracleParams
+    _, _, m, gdim, model_names = WORKLOADS[workload]
+    mesh = kb.mesh.cell_array_mesh(gdim, n, m)
+    it = tuple(mesh.intra_tags)
+    p = OracleParams(intra_tags=it, extra_tag=1, membrane_tags=it, stimulus_tags=(2,) if workload == "c3" else it)
+    qb, qw = kb.mesh.facet_quadrature(gdim)
+    # CSR pattern and dof maps of the contract layout from the host-only builder (no GPU involved)
+    pat = kb.lib.pattern_host(gdim, mesh.x, mesh.cells, mesh.cell_tags, it, 1, mesh.mf_verts, mesh.mf_tags, qb, qw)
+    cb = CpuBaseline(gdim, mesh.x, mesh.cells, mesh.cell_tags, mesh.mf_verts, mesh.mf_tags, p, [(nm, None) for nm in model_names],
+                     pat, restart=restart)
+    # initial state of configs/c3_*.yaml / c4_*.yaml (initial_conditions + initial_perturbation), packed like the oracle
+    nv = mesh.x.shape[0]
+    ci = np.array(p.c_i_init)[:, None] * np.ones(nv)
+    ce = np.array(p.c_e_init)[:, None] * np.ones(nv)
+    phi_i = np.full(nv, p.phi_m_init)
+    if workload == "c3":
+        X = mesh.x / 1e-6
+        fac = 1 + 0.01 * np.sin(2 * np.pi * X[:, 0]) * np.sin(2 * np.pi * X[:, 1])
+        ci, ce = ci * fac, ce * fac
+        phi_i = phi_i + 0.005 * np.cos(2 * np.pi * X[:, 0])
+    vi, ve = pat[2], pat[3]
+    u = np.concatenate([ci[0][vi], ci[1][vi], ci[2][vi], phi_i[vi], ce[0][ve], ce[1][ve], ce[2][ve], np.zeros(ve.size)])
+    gates = np.array([p.n_init, p.m_init, p.h_init])[:, None] * np.ones(cb.n_mv)
+    cb.set_state(u, gates)
+    return cb, dict(rows=cb.n, nnz=cb.nnz, cells=int(mesh.cells.shape[0]))
+
+
+def cpu_run(workload, n, warmup, steps, restart=30):
+    t0 = time.time()
+    cb, info = cpu_workload(workload, n, restart)
+    cb.pc_setup()
+    info["setup_s"] = time.time() - t0
+    its, tot, asm = [], [], []
     for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        o.t += p.dt
-        o.gate_update()
-        A, b = o.assemble(o.t)
-        t1 = time.perf_counter()
-        ns = o.nullspace()
-        if i == 0:
-            b = b - ns * (ns @ b)
-        x, k = o.solve_gmres(A, b, x, ns, amg, 1e-9)
-        o.unpack(x)
-        t2 = time.perf_counter()
+        k, ms = cb.step(1e-9)
         if i >= warmup:
-            t_asm.append(t1 - t0)
-            t_step.append(t2 - t0)
             its.append(k)
-    ms = 1e3 * float(np.mean(t_step))
-    scale = (n_full_rows / o.n) if n_full_rows else 1.0
-    return dict(ms_sample=ms, ms_scaled=ms * scale, rows=o.n, nnz=int(A.nnz), iterations=its,
-                assembly_ms_sample=1e3 * float(np.mean(t_asm)), scale=scale)
+            tot.append(ms["total"])
+            asm.append(ms["assembly"])
+    info.update(ms=float(np.mean(tot)), assembly_ms=float(np.mean(asm)), iterations=its, threads=cb.threads)
+    cb.close()
+    return info
+
+
+def weak_n(base_n, world):
+    return base_n if world == 1 else int(round(base_n * math.sqrt(world) / 8)) * 8
 
 
 def run_reference(args):
+    """Reference arm: the CPU implementation of the path (C++/OpenMP port of the oracle; the DOLFINx/PETSc stack itself is
+    not installable here) on ALL host cores, on the same workload at the same size as the GPU arm -- no scaling factor."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_s, cpd = args.cpu_sample_n, 8
-    # the full workload's row count, needed to scale the sample to the metric's unit
-    per_dim = args.size or 2048
-    full_rows = None
+    wl = args.workload
+    base_n = args.size if args.size else WORKLOADS[wl][1]
+    n = weak_n(base_n, args.gpus) if wl == "c3" else base_n
+    os.environ.pop("OMP_NUM_THREADS", None) if os.environ.get("OMP_NUM_THREADS") == "1" else None
     t0 = time.time()
-    r = cpu_oracle_run(n_s, cpd, args.warmup, args.steps, None)
-    # rows scale with N^2 for this generator; the GPU arm grows N with sqrt(GPUs) (weak scaling)
-    n_full = per_dim if args.gpus <= 1 else int(round(per_dim * math.sqrt(args.gpus) / 8)) * 8
-    scale = (per_dim / n_s) ** 2 * max(1, args.gpus)
-    val = r["ms_sample"] * scale
-    line = {"metric": METRIC, "value": val, "unit": "ms", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": val, "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "impl": "reference",
-            "config": {"workload": f"BASELINE C3: synthetic 2D tissue block N={n_full} (8x8 cells), Na/K/Cl + HH+ATP+KCC2, "
-                                   f"GMRES({args.restart}) + charge-conservation Schur PC (SA-AMG blocks) rtol 1e-9, ICs perturbed as SURVEY 8(d)",
-                       "sample_N": n_s, "sample_rows": r["rows"], "iterations": r["iterations"]},
-            "cpu_baseline": {"value": val, "unit": "ms", "cores": 1, "kind": "port",
-                             "sample": f"CPU oracle (numpy/scipy restatement; DOLFINx/PETSc not installable) on the same generator at N={n_s} "
-                                       f"({r['rows']} rows), steps {args.warmup + 1}..{args.warmup + args.steps}, {r['ms_sample']:.0f} ms/step measured, "
-                                       f"scaled x{scale:.0f} by DOFs to the full workload"},
-            "e2e": {"value": val, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    r = cpu_run(wl, n, args.warmup, args.steps, args.restart)
+    line = {"metric": METRIC, "value": r["ms"], "unit": "ms", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": r["ms"], "higher_is_better": False, "scaling": "weak" if wl == "c3" else "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": workload_name(wl, n, r["cells"]) + f", GMRES({args.restart}) + charge-conservation Schur PC (SA-AMG blocks) rtol 1e-9"
+                                   + (", ICs perturbed as SURVEY 8(d)" if wl == "c3" else ""),
+                       "dofs": r["rows"], "nnz": r["nnz"], "cells": r["cells"], "iterations_per_step": r["iterations"],
+                       "timed_step_indices": [args.warmup + 1, args.warmup + args.steps], "setup_s": r["setup_s"]},
+            "phases_ms": {"assembly": r["assembly_ms"], "solve": r["ms"] - r["assembly_ms"]},
+            "cpu_baseline": {"value": r["ms"], "unit": "ms", "cores": r["threads"], "kind": "port", "extrapolated": False,
+                             "sample": f"C++/OpenMP port of the CPU oracle (restatement of the DOLFINx/PETSc time-loop body; the stack itself is "
+                                       f"not installable) on the FULL workload ({r['rows']} rows), {r['threads']} threads of {os.cpu_count()} host "
+                                       f"cores, steps {args.warmup + 1}..{args.warmup + args.steps}, measured, not scaled"},
+            "e2e": {"value": r["ms"], "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.time() - t0}
     print(json.dumps(line), flush=True)
+
+
+def workload_name(wl, n, n_cells):
+    return {"c3": f"BASELINE C3: synthetic 2D tissue block N={n} (8x8 cells), Na/K/Cl + HH+ATP+KCC2",
+            "c4": f"BASELINE C4: synthetic 3D tissue block N={n} (4x4x4 cells, {n_cells} tetrahedra), Na/K/Cl + passive membrane"}[wl]
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
@@ -266,7 +281,7 @@ def run_ours(args):
     base_n = args.size if args.size else WORKLOADS[wl][1]
     if wl == "c3":
         # weak scaling: cells per GPU fixed -> N grows with sqrt(world), rounded to the 8 x 8 cell array
-        n = base_n if world == 1 else int(round(base_n * math.sqrt(world) / 8)) * 8
+        n = weak_n(base_n, world)
         scaling = "weak"
     else:
         n, scaling = base_n, "strong"                  # BASELINE C4: one fixed mesh sharded over the GPUs
@@ -368,8 +383,7 @@ def run_ours(args):
     dofs_global = int(comm.allreduce(float(ctx.n_rows), op=kb.MPI.SUM))
     nnz_global = int(comm.allreduce(float(ctx.nnz), op=kb.MPI.SUM))
     n_cells_global = int(p.global_mesh_info["n_cells"])
-    names = {"c3": f"BASELINE C3: synthetic 2D tissue block N={n} (8x8 cells), Na/K/Cl + HH+ATP+KCC2",
-             "c4": f"BASELINE C4: synthetic 3D tissue block N={n} (4x4x4 cells, {n_cells_global} tetrahedra), Na/K/Cl + passive membrane"}
+    names = {wl: workload_name(wl, n, n_cells_global)}
     ctx.close()
     del p, s, ctx, x, y
 
@@ -428,12 +442,17 @@ def run_ours(args):
 
 
 def cpu_baseline_leg(args):
-    r = cpu_oracle_run(args.cpu_sample_n, 8, args.warmup, min(args.steps, 2))
-    return {"value": r["ms_sample"], "unit": "ms", "cores": 1, "kind": "port", "extrapolated": False,
-            "sample": f"CPU oracle (numpy/scipy restatement of the DOLFINx/PETSc path, same GMRES + Schur/SA-AMG algorithm) on the same "
-                      f"generator at N={args.cpu_sample_n} ({r['rows']} rows, iterations {r['iterations']}), steps {args.warmup + 1}.."
-                      f"{args.warmup + min(args.steps, 2)}: {r['ms_sample']:.0f} ms/step (assembly {r['assembly_ms_sample']:.0f} ms); "
-                      f"value is the measured sample, NOT scaled to the full workload"}
+    """cpu_baseline of the GPU arm's line (rank 0, N = 1): the C++/OpenMP CPU port on the same workload at the same size, all
+    host cores, bounded to 2 timed steps after the same warm-up steps (about 10-30 s of CPU work)."""
+    wl = args.workload
+    n = args.size if args.size else WORKLOADS[wl][1]
+    k = min(args.steps, 2)
+    r = cpu_run(wl, n, args.warmup, k, args.restart)
+    return {"value": r["ms"], "unit": "ms", "cores": r["threads"], "kind": "port", "extrapolated": False,
+            "iterations": r["iterations"], "assembly_ms": r["assembly_ms"], "setup_s": r["setup_s"],
+            "sample": f"C++/OpenMP port of the CPU oracle (restatement of the DOLFINx/PETSc time-loop body, same GMRES + Schur/SA-AMG "
+                      f"algorithm) on the FULL workload ({r['rows']} rows), {r['threads']} threads of {os.cpu_count()} host cores, "
+                      f"steps {args.warmup + 1}..{args.warmup + k}, measured, not scaled"}
 
 
 def main():
@@ -449,7 +468,6 @@ def main():
     ap.add_argument("--skip-c4", action="store_true")
     ap.add_argument("--skip-parity", action="store_true")
     ap.add_argument("--restart", type=int, default=30)
-    ap.add_argument("--cpu-sample-n", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--amg-form", default=None, choices=["schur", "block_jacobi"], help="override SolverKNPEMI.amg_form")
     args = ap.parse_args()

@@ -177,6 +177,125 @@ def cell_array_mesh(gdim, n, m, scale=1e-6, fill=0.5, first_tag=2, extra_tag=1):
     return Mesh(gdim, x * scale, cells, tags, intra, extra_tag, fv, ft, grid=(n,) * gdim)
 
 
+def rank_grid(gdim, size):
+    """Process grid of the block partition: the prime factors of `size`, largest first, go to the axis that currently has
+    the fewest blocks (2 -> 2x1(x1), 4 -> 2x2(x1), 8 -> 4x2 / 2x2x2, 6 -> 3x2 ...)."""
+    dims = [1] * gdim
+    f, rest, primes = 2, size, []
+    while rest > 1:
+        while rest % f == 0:
+            primes.append(f)
+            rest //= f
+        f += 1
+    for q in sorted(primes, reverse=True):
+        dims[int(np.argmin(dims))] *= q
+    return tuple(dims)
+
+
+class BlockOwner:
+    """Vertex -> rank map of the block partition of an (n+1)^gdim structured vertex grid, evaluated by formula (no global
+    array): axis a is cut into dims[a] slabs of near-equal vertex counts; rank = sum_a block_a * stride_a (x fastest)."""
+
+    def __init__(self, gdim, n, size):
+        self.gdim, self.n, self.size = gdim, n, size
+        self.dims = rank_grid(gdim, size)
+        self.cuts = [np.array([(b * (n + 1)) // d for b in range(d + 1)], np.int64) for d in self.dims]
+
+    def box(self, rank):
+        lo, hi, r = [], [], rank
+        for a in range(self.gdim):
+            b = r % self.dims[a]
+            r //= self.dims[a]
+            lo.append(int(self.cuts[a][b]))
+            hi.append(int(self.cuts[a][b + 1]))
+        return lo, hi
+
+    def __call__(self, gid):
+        gid = np.asarray(gid, np.int64)
+        m = self.n + 1
+        rank = np.zeros(gid.shape, np.int64)
+        stride, rest = 1, gid
+        for a in range(self.gdim):
+            i = rest % m
+            rest = rest // m
+            rank += (np.searchsorted(self.cuts[a], i, side="right") - 1) * stride
+            stride *= self.dims[a]
+        return rank.astype(np.int32)
+
+
+def cell_array_mesh_local(gdim, n, m, rank, size, scale=1e-6, fill=0.5, first_tag=2, extra_tag=1):
+    """This rank's part of cell_array_mesh(gdim, n, m, ...) under the block partition, generated WITHOUT building the global
+    mesh: owned vertices first (ascending global id), then ghosts; every cell / membrane facet touching an owned vertex;
+    ownership flags for functionals -- the same local mesh partition.partition_mesh(global mesh, owner=BlockOwner) returns.
+    Returns (Mesh, info) with info = {owner_of, l2g, rank, size}."""
+    assert n % m == 0
+    own = BlockOwner(gdim, n, size)
+    lo, hi = own.box(rank)
+    # grid squares / cubes touching an owned vertex: one layer around the owned vertex box
+    rng = [np.arange(max(lo[a] - 1, 0), min(hi[a], n), dtype=np.int64) for a in range(gdim)]
+    mv = n + 1
+    bs = n // m
+    lo_in = int(round(bs * (1 - fill) / 2))
+    hi_in = bs - lo_in
+    ins = [((r % bs) >= lo_in) & ((r % bs) < hi_in) for r in rng]
+    blk = [r // bs for r in rng]
+    if gdim == 2:
+        IY, IX = np.meshgrid(rng[1], rng[0], indexing="ij")
+        v0 = (IY * mv + IX).ravel()
+        v1, v2, v3 = v0 + 1, v0 + mv, v0 + mv + 1
+        cells = np.stack([np.stack([v0, v1, v3], 1), np.stack([v0, v2, v3], 1)], 1).reshape(-1, 3)
+        IN = ins[1][:, None] & ins[0][None, :]
+        tag = first_tag + blk[1][:, None] * m + blk[0][None, :]
+        tags = np.repeat(np.where(IN, tag, extra_tag).ravel(), 2)
+    else:
+        IZ, IY, IX = np.meshgrid(rng[2], rng[1], rng[0], indexing="ij")
+        v0 = (IZ * mv * mv + IY * mv + IX).ravel()
+        v1, v2, v3 = v0 + 1, v0 + mv, v0 + mv + 1
+        v4, v5, v6, v7 = v0 + mv * mv, v1 + mv * mv, v2 + mv * mv, v3 + mv * mv
+        tets = [(v0, v1, v3, v7), (v0, v1, v7, v5), (v0, v5, v7, v4), (v0, v3, v2, v7), (v0, v6, v4, v7), (v0, v2, v6, v7)]
+        cells = np.stack([np.stack(t, 1) for t in tets], 1).reshape(-1, 4)
+        IN = ins[2][:, None, None] & ins[1][None, :, None] & ins[0][None, None, :]
+        tag = first_tag + (blk[2][:, None, None] * m + blk[1][None, :, None]) * m + blk[0][None, None, :]
+        tags = np.repeat(np.where(IN, tag, extra_tag).ravel(), 6)
+    cell_owner = own(cells)
+    keep = (cell_owner == rank).any(axis=1)
+    cells, tags, cell_owner = cells[keep], tags[keep].astype(np.int32), cell_owner[keep]
+    used = np.unique(cells.ravel())
+    mine = own(used) == rank
+    l2g = np.concatenate([used[mine], used[~mine]])
+    lcells = np.searchsorted(used, cells)                  # index into `used`, then into the owned-first order
+    pos = np.empty(used.size, np.int64)
+    pos[np.concatenate([np.flatnonzero(mine), np.flatnonzero(~mine)])] = np.arange(used.size)
+    lcells = pos[lcells].astype(np.int32)
+    # coordinates from the structured index
+    idx, rest = [], l2g
+    for a in range(gdim):
+        idx.append(rest % mv)
+        rest = rest // mv
+    x = np.stack([i / n for i in idx], 1) * scale
+    # a cell / facet is integrated by the rank that owns its lowest-numbered (global) vertex
+    cell_owned = (np.take_along_axis(cell_owner, np.argmin(cells, axis=1)[:, None], 1)[:, 0] == rank).astype(np.uint8)
+    intra = tuple(range(first_tag, first_tag + m ** gdim))
+    fv, ft = membrane_facets(lcells, tags, intra, extra_tag)
+    n_owned = int(mine.sum())
+    if fv.size:
+        f_has = (fv < n_owned).any(axis=1)
+        fv, ft = fv[f_has], ft[f_has]
+        fg = l2g[fv]
+        # facets sorted like the global generator sorts them (by their sorted global vertex ids)
+        key = np.sort(fg, 1)
+        order = np.lexsort(tuple(key[:, j] for j in range(gdim - 1, -1, -1)))
+        fv, ft, fg, key = fv[order], ft[order], fg[order], key[order]
+        fv = np.searchsorted(used, key)
+        fv = pos[fv].astype(np.int32)
+        mf_owned = (own(key[:, 0]) == rank).astype(np.uint8)
+    else:
+        mf_owned = np.zeros(0, np.uint8)
+    local = Mesh(gdim, x, lcells, tags, intra, extra_tag, fv.astype(np.int32).reshape(-1, gdim), ft.astype(np.int32),
+                 grid=(n,) * gdim, n_owned=n_owned, cell_owned=cell_owned, mf_owned=mf_owned, vert_global=l2g)
+    return local, dict(owner_of=own, l2g=l2g, rank=rank, size=size)
+
+
 def from_descriptor(desc, scale):
     """``synthetic_mesh`` YAML block -> Mesh.  kinds: square, cube (reference fixtures), cell_array."""
     kind = desc.get("kind", "square")

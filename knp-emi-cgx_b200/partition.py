@@ -36,10 +36,12 @@ def rcb_owner(x, nparts):
     return owner
 
 
-def partition_mesh(m: Mesh, rank: int, size: int):
+def partition_mesh(m: Mesh, rank: int, size: int, owner=None):
     """Local mesh of `rank`: owned vertices first (ascending global id), then ghosts; every cell / membrane
-    facet touching an owned vertex; ownership flags for functionals.  Returns (local Mesh, info dict)."""
-    owner = rcb_owner(m.x, size)
+    facet touching an owned vertex; ownership flags for functionals.  Returns (local Mesh, info dict).
+    owner: vertex -> rank array (default: recursive coordinate bisection)."""
+    if owner is None:
+        owner = rcb_owner(m.x, size)
     nv = m.x.shape[0]
     mine = owner == rank
     cell_has = mine[m.cells].any(axis=1)
@@ -63,7 +65,7 @@ def partition_mesh(m: Mesh, rank: int, size: int):
     local = Mesh(m.gdim, m.x[l2g], lcells, ltags.astype(np.int32), m.intra_tags, m.extra_tag, lfv,
                  m.mf_tags[f_has].astype(np.int32), grid=m.grid, n_owned=int(owned_ids.size), cell_owned=cell_owned,
                  mf_owned=mf_owned, vert_global=l2g)
-    info = dict(owner=owner, l2g=l2g, rank=rank, size=size)
+    info = dict(owner_of=lambda gid, _o=owner: _o[gid], l2g=l2g, rank=rank, size=size)
     return local, info
 
 
@@ -98,12 +100,12 @@ class Layout:
 
 def ghost_requests(local: Mesh, info, lay: Layout):
     """For each owner rank: the (subdomain, global vertex ids) this rank needs, ascending global id."""
-    owner, l2g = info["owner"], info["l2g"]
+    owner_of, l2g = info["owner_of"], info["l2g"]
     req = {}
     for s in range(2):
         gh_nodes = np.arange(lay.n_own[s], lay.n_loc[s])
         gv = l2g[lay.node_vert[s][gh_nodes]]
-        ow = owner[gv]
+        ow = np.asarray(owner_of(gv))
         for r in np.unique(ow):
             sel = ow == r
             req.setdefault(int(r), {})[s] = (gv[sel], gh_nodes[sel])

@@ -290,7 +290,16 @@ class ProblemKNPEMI:
         """Mesh ingest (utils/mixed_dim_problem.py:634-733).  There is no HDF5/XDMF reader in this image:
         the fixture is generated in memory from ``synthetic_mesh`` or from the file name
         (``square{N}.xdmf`` / ``cube{N}.xdmf``, as written by utils/generate_square_mesh.py)."""
-        if self.synthetic_mesh is not None:
+        local_info = None
+        sm = self.synthetic_mesh
+        if sm is not None and self.comm.size > 1 and sm.get("kind") == "cell_array" and self.gamma_tags == self.intra_tags:
+            # structured tissue block on several GPUs: every rank generates only its own slab (block partition by formula)
+            gdim, n = int(sm.get("dim", 2)), int(sm.get("N", 32))
+            m, local_info = _mesh.cell_array_mesh_local(gdim, n, int(sm.get("cells_per_dim", 8)), self.comm.rank, self.comm.size,
+                                                        self.mesh_conversion_factor, float(sm.get("fill", 0.5)),
+                                                        int(sm.get("first_tag", 2)), int(sm.get("extra_tag", 1)))
+            self.global_mesh_info = dict(n_vertices=(n + 1) ** gdim, n_cells=(2 if gdim == 2 else 6) * n ** gdim)
+        elif sm is not None:
             m = _mesh.from_descriptor(self.synthetic_mesh, self.mesh_conversion_factor)
         else:
             base = os.path.basename(self.input_files["mesh_file"])
@@ -307,11 +316,16 @@ class ProblemKNPEMI:
         keep = np.isin(m.mf_tags, np.asarray(self.gamma_tags))
         m.mf_verts, m.mf_tags = m.mf_verts[keep], m.mf_tags[keep]
         m.intra_tags, m.extra_tag = self.intra_tags, self.extra_tag[0]
-        self.global_mesh_info = dict(n_vertices=m.x.shape[0], n_cells=m.cells.shape[0])
-        if self.comm.size > 1:
+        if local_info is not None:
+            if m.mf_owned is not None:
+                m.mf_owned = m.mf_owned[keep]
+            self.halo = local_info
+        elif self.comm.size > 1:
+            self.global_mesh_info = dict(n_vertices=m.x.shape[0], n_cells=m.cells.shape[0])
             from .partition import partition_mesh
             m, self.halo = partition_mesh(m, self.comm.rank, self.comm.size)
         else:
+            self.global_mesh_info = dict(n_vertices=m.x.shape[0], n_cells=m.cells.shape[0])
             self.halo = None
         self.mesh = m
         self.dx = Measure(self)

@@ -1,0 +1,887 @@
+// C++/OpenMP restatement of the oracle's KNP-EMI timestep (TEST / BASELINE INFRASTRUCTURE -- never on the product path).
+//
+// Why it exists: the reference's own CPU path (DOLFINx + multiphenicsx + PETSc, all un-vendored third-party libraries)
+// cannot be built or imported here, and the numpy oracle (oracle/knpemi.py) is single-threaded.  This file restates the
+// same algorithm, function by function, so that bench.py can time "the reference's CPU implementation of the path" on ALL
+// host cores at the ACTUAL configuration size (cpu_baseline.kind = "port"):
+//
+//   gate_update     <- HodgkinHuxley.update_gating_variables      (KNPEMIx_ionic_model.py:605-671)   oracle: gate_update
+//   channel currents<- IonicModel._eval family + _add_stimulus    (KNPEMIx_ionic_model.py:89-603)    oracle: channel_currents
+//   assemble        <- SolverKNPEMI.assemble on the forms a, L    (KNPEMIx_solver.py:104-116,        oracle: assemble
+//                      KNPEMIx_problem.py:454-655): element tensors scattered with a sorted-row search, the way
+//                      assemble_matrix_block / MatSetValuesLocal do it
+//   gmres           <- KSP GMRES(30), left PC, preconditioned norm, nullspace removed after every PC application
+//                      (KNPEMIx_solver.py:212-214,276-280,324-333,386-389,435)                       oracle: solve_gmres
+//   schur_pc        <- what `pc_type: hypre` maps to in the product (oracle/amg.py::SchurPC + SAAMG cycle); the AMG
+//                      hierarchy SETUP (untimed, once) reuses the product's host code csrc/amg_setup.cpp, the cycle,
+//                      the Krylov solver and the assembly are restated here.
+//
+// Validated against the numpy oracle in tests/test_cpu_baseline.py (matrix / vector entries 1e-12, identical GMRES
+// iteration counts, solutions 1e-9).  Layout: rows (s, f, p) = base[s] + f * ns[s] + p, base = {0, 4 ns[0]}.
+#include <omp.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <cstdlib>
+#include <string>
+#include <vector>
+#include "amg_host.h"
+
+using knp::CsrHost;
+
+namespace {
+
+struct Params {
+  double dt, F, R, T, C_M, phi_rest;
+  double z[3], D[3];
+  double g_Na_bar, g_K_bar, g_leak[3], g_leak_g[3];
+  double g_syn_bar, a_syn, T_stim;
+  int32_t scale_stimulus, stim_dir;
+  double stim_lo, stim_hi;
+  double K_e_init, K_i_g_init;
+  int32_t ode_substeps, rush_larsen;
+};
+
+enum { M_PASSIVE = 1, M_KIRNA = 2, M_GLIAL_CT = 4, M_NEURONAL_CT = 8, M_ATP = 16, M_HH = 32 };
+
+struct Level {
+  CsrHost A, P, R;
+  std::vector<double> dinv, x, b, r;
+  double rho;
+};
+struct Amg {
+  std::vector<Level> lv;
+  std::vector<double> cinv, cb;
+  int nc = 0, gamma = 2, gamma_last = 3;
+};
+
+struct Ctx {
+  int d;
+  int ns[2], base[2], n;
+  std::vector<double> x[2];                 // node coordinates per subdomain
+  std::vector<int32_t> cells[2];            // (d+1) restricted nodes per cell
+  int n_mv, n_mf, nq;
+  std::vector<int32_t> mv_node[2], mf_mv;
+  std::vector<uint32_t> mf_models;
+  std::vector<uint8_t> mf_stim;
+  std::vector<double> qb, qw, farea;
+  CsrHost A;                                // pattern given by the caller (sorted rows), values assembled here
+  std::vector<double> b, u, gates;          // u: packed solution (n); gates 3 x n_mv
+  Params p;
+  double psi, stim_area, t;
+  int step;
+  // Schur preconditioner
+  Amg amg_c, amg_p;
+  CsrHost Mass[2];
+  std::vector<double> msig_inv;
+  std::vector<double> vc, zc, tt, zp;
+  // Krylov workspace
+  int restart;
+  std::vector<double> V, w, tmp;
+  std::string err;
+};
+
+inline void spmv(const CsrHost& M, const double* x, double* y) {
+  const int n = M.n_rows;
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n; ++i) {
+    double s = 0.0;
+    for (int j = M.indptr[i]; j < M.indptr[i + 1]; ++j) s += M.vals[j] * x[M.indices[j]];
+    y[i] = s;
+  }
+}
+
+// sorted-row search + atomic add: the MatSetValues of the restatement
+inline void add(CsrHost& M, int row, int col, double v) {
+  const int32_t* lo = M.indices.data() + M.indptr[row];
+  const int32_t* hi = M.indices.data() + M.indptr[row + 1];
+  const int32_t* it = std::lower_bound(lo, hi, col);
+  double* dst = M.vals.data() + (it - M.indices.data());
+#pragma omp atomic
+  *dst += v;
+}
+
+// P1 element: volume, stiffness K (unit coefficient) and mass M of a simplex with vertex coordinates xv[(d+1)][d]
+template <int D>
+inline void element(const double (*xv)[D], double& vol, double K[D + 1][D + 1]) {
+  double J[D][D];
+  for (int a = 0; a < D; ++a)
+    for (int i = 0; i < D; ++i) J[i][a] = xv[a + 1][i] - xv[0][i];
+  double det, inv[D][D];
+  if (D == 2) {
+    det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+    inv[0][0] = J[1][1] / det;
+    inv[0][1] = -J[0][1] / det;
+    inv[1][0] = -J[1][0] / det;
+    inv[1][1] = J[0][0] / det;
+  } else {
+    const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1], c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2],
+                 c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+    det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
+    inv[0][0] = c00 / det;
+    inv[1][0] = c01 / det;
+    inv[2][0] = c02 / det;
+    inv[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) / det;
+    inv[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) / det;
+    inv[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) / det;
+    inv[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) / det;
+    inv[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) / det;
+    inv[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / det;
+  }
+  vol = std::fabs(det) / (D == 2 ? 2.0 : 6.0);
+  double g[D + 1][D];                       // gradients of the barycentric coordinates: rows of J^-1, minus their sum
+  for (int i = 0; i < D; ++i) {
+    double s = 0.0;
+    for (int a = 0; a < D; ++a) {
+      g[a + 1][i] = inv[a][i];
+      s += inv[a][i];
+    }
+    g[0][i] = -s;
+  }
+  for (int a = 0; a <= D; ++a)
+    for (int b = 0; b <= D; ++b) {
+      double s = 0.0;
+      for (int i = 0; i < D; ++i) s += g[a][i] * g[b][i];
+      K[a][b] = vol * s;
+    }
+}
+
+template <int D>
+void assemble_cells(Ctx& c, int mode, double membrane_sign, double D_scale, CsrHost* Acc, CsrHost* App, CsrHost* Ms) {
+  // mode 0: system matrix A and vector b; mode 1: the Schur preconditioner's ion blocks (Acc), potential blocks (App) and
+  // mass matrices (Ms) in their compact numberings (oracle: assemble_P(membrane_sign, D_scale))
+  const Params& p = c.p;
+  const double psi = c.psi;
+  for (int s = 0; s < 2; ++s) {
+    const int nc = (int)(c.cells[s].size() / (D + 1)), ns = c.ns[s], base = c.base[s];
+    const int cbase = s ? 3 * c.ns[0] : 0, pbase = s ? c.ns[0] : 0;
+#pragma omp parallel for schedule(static)
+    for (int e = 0; e < nc; ++e) {
+      const int32_t* nd = &c.cells[s][(size_t)e * (D + 1)];
+      double xv[D + 1][D], K[D + 1][D + 1], vol;
+      for (int a = 0; a <= D; ++a)
+        for (int i = 0; i < D; ++i) xv[a][i] = c.x[s][(size_t)nd[a] * D + i];
+      element<D>(xv, vol, K);
+      const double mfac = vol / ((D + 1) * (D + 2));
+      double cv[3][D + 1], cbar[3];
+      for (int k = 0; k < 3; ++k) {
+        double sum = 0.0;
+        for (int a = 0; a <= D; ++a) {
+          cv[k][a] = c.u[base + k * ns + nd[a]];
+          sum += cv[k][a];
+        }
+        cbar[k] = sum / (D + 1);
+      }
+      for (int a = 0; a <= D; ++a) {
+        for (int bb = 0; bb <= D; ++bb) {
+          const double Mab = mfac * (a == bb ? 2.0 : 1.0), Kab = K[a][bb];
+          double kphi = 0.0;
+          for (int k = 0; k < 3; ++k) {
+            const int rk = base + k * ns + nd[a], ck = base + k * ns + nd[bb];
+            const int rphi = base + 3 * ns + nd[a], cphi = base + 3 * ns + nd[bb];
+            if (mode == 0) {
+              add(c.A, rk, ck, Mab + p.dt * p.D[k] * Kab);
+              add(c.A, rk, cphi, (p.dt * p.D[k] * p.z[k] / psi) * cbar[k] * Kab);
+              add(c.A, rphi, ck, (p.dt * p.z[k] * p.D[k]) * Kab);
+              kphi += (p.dt * p.D[k] * p.z[k] * p.z[k] / psi) * cbar[k] * Kab;
+            } else {
+              add(*Acc, cbase + k * ns + nd[a], cbase + k * ns + nd[bb], Mab + (D_scale * p.dt * p.D[k]) * Kab);
+              kphi += (D_scale * p.dt * p.D[k] * p.z[k] * p.z[k] / psi) * cbar[k] * Kab;
+            }
+          }
+          if (mode == 0) {
+            add(c.A, base + 3 * ns + nd[a], base + 3 * ns + nd[bb], kphi);
+          } else {
+            add(*App, pbase + nd[a], pbase + nd[bb], kphi);
+            add(Ms[s], nd[a], nd[bb], Mab);
+          }
+        }
+        if (mode == 0)
+          for (int k = 0; k < 3; ++k) {
+            double s2 = 0.0;
+            for (int bb = 0; bb <= D; ++bb) s2 += mfac * (a == bb ? 2.0 : 1.0) * cv[k][bb];
+#pragma omp atomic
+            c.b[base + k * ns + nd[a]] += s2;
+          }
+      }
+    }
+  }
+  (void)membrane_sign;
+}
+
+// I_ch,k at one quadrature point (oracle: channel_currents)
+inline void currents(const Ctx& c, uint32_t models, bool stimulated, const double ci[3], const double ce[3], double phim,
+                     const double g[3], double xdir, double stim_fac, double I[3]) {
+  const Params& p = c.p;
+  const double psi = c.psi;
+  double E[3];
+  for (int k = 0; k < 3; ++k) E[k] = (psi / p.z[k]) * std::log(ce[k] / ci[k]);
+  I[0] = I[1] = I[2] = 0.0;
+  if (models & M_PASSIVE)
+    for (int k = 0; k < 3; ++k) I[k] += phim;
+  if (models & M_NEURONAL_CT) {
+    const double kcc2 = 0.0068 * std::log((ci[1] * ci[2]) / (ce[1] * ce[2]));
+    const double nkcc1 = 0.0023 * 0.0 * std::log((ce[0] * ce[1] * ce[2] * ce[2]) / (ci[0] * ci[1] * ci[2] * ci[2]));
+    I[0] += -nkcc1;
+    I[1] += -nkcc1 + kcc2;
+    I[2] += nkcc1 - kcc2;
+  }
+  if (models & M_GLIAL_CT) {
+    const double kcc1 = (7e-2 * psi) * std::log((ci[1] * ci[2]) / (ce[1] * ce[2]));
+    const double nkcc1 = (2e-2 * psi) * 0.0 * std::log((ce[0] * ce[1] * ce[2] * ce[2]) / (ci[0] * ci[1] * ci[2] * ci[2]));
+    I[0] += -nkcc1;
+    I[1] += -nkcc1 + kcc1;
+    I[2] += 2 * nkcc1 - kcc1;
+  }
+  if (models & M_ATP) {
+    const double par1 = 1.0 + 1.5 / ce[1], par2 = 1.0 + 10.0 / ci[0];
+    const double atp = 0.25 / (par1 * par1 * par2 * par2 * par2);
+    I[0] += 3 * atp;
+    I[1] += -2 * atp;
+  }
+  if (models & M_HH) {
+    const double n = g[0], m = g[1], h = g[2];
+    const double gg[3] = {p.g_leak[0] + p.g_Na_bar * m * m * m * h, p.g_leak[1] + p.g_K_bar * n * n * n * n, p.g_leak[2] + 0.0 * n};
+    double Ik[3];
+    for (int k = 0; k < 3; ++k) Ik[k] = gg[k] * (phim - E[k]);
+    if (stimulated) {
+      double mask = 1.0;
+      if (p.stim_dir >= 0) mask = (xdir > p.stim_lo && xdir < p.stim_hi) ? 1.0 : 0.0;
+      Ik[0] += mask * stim_fac * (phim - E[0]);
+    }
+    for (int k = 0; k < 3; ++k) I[k] += Ik[k];
+  }
+  if (models & M_KIRNA) {
+    const double E_K_init = psi * std::log(p.K_e_init / p.K_i_g_init);
+    const double rho = 1.1 * 1.12e-6;
+    const double pump = (1.0 / (1.0 + std::pow(10.0 / ci[0], 1.5))) * (1.0 / (1.0 + 1.5 / ce[1])) * rho;
+    const double A_ = 1 + std::exp(0.433), B_ = 1 + std::exp(-(0.1186 + E_K_init) / 0.0441);
+    const double C_ = 1 + std::exp(((phim - E[1]) + 0.0185) / 0.0425), D_ = 1 + std::exp(-(0.1186 + phim) / 0.0441);
+    const double f_kir = std::sqrt(ce[1] / p.K_e_init) * A_ * B_ / (C_ * D_);
+    I[0] += 1.0 * p.g_leak_g[0] * (phim - E[0]) + 3 * p.z[0] * p.F * pump;
+    I[1] += f_kir * p.g_leak_g[1] * (phim - E[1]) + (-2 * p.z[1] * p.F * pump);
+    I[2] += 1.0 * p.g_leak_g[2] * (phim - E[2]);
+  }
+}
+
+template <int D>
+void facet_areas(Ctx& c) {
+  c.farea.resize(c.n_mf);
+  for (int f = 0; f < c.n_mf; ++f) {
+    double xv[D][D];
+    for (int a = 0; a < D; ++a)
+      for (int i = 0; i < D; ++i) xv[a][i] = c.x[0][(size_t)c.mv_node[0][c.mf_mv[(size_t)f * D + a]] * D + i];
+    if (D == 2) {
+      c.farea[f] = std::hypot(xv[1][0] - xv[0][0], xv[1][1] - xv[0][1]);
+    } else {
+      double u[3], v[3];
+      for (int i = 0; i < 3; ++i) {
+        u[i] = xv[1][i] - xv[0][i];
+        v[i] = xv[2 % D][i] - xv[0][i];
+      }
+      const double cx = u[1] * v[2] - u[2] * v[1], cy = u[2] * v[0] - u[0] * v[2], cz = u[0] * v[1] - u[1] * v[0];
+      c.farea[f] = 0.5 * std::sqrt(cx * cx + cy * cy + cz * cz);
+    }
+  }
+}
+
+template <int D>
+double stimulus_area(const Ctx& c) {
+  double acc = 0.0;
+  for (int f = 0; f < c.n_mf; ++f) {
+    if (!c.mf_stim[f]) continue;
+    for (int q = 0; q < c.nq; ++q) {
+      double mask = 1.0;
+      if (c.p.stim_dir >= 0) {
+        double xq = 0.0;
+        for (int a = 0; a < D; ++a)
+          xq += c.qb[(size_t)q * D + a] * c.x[0][(size_t)c.mv_node[0][c.mf_mv[(size_t)f * D + a]] * D + c.p.stim_dir];
+        mask = (xq > c.p.stim_lo && xq < c.p.stim_hi) ? 1.0 : 0.0;
+      }
+      acc += c.farea[f] * c.qw[q] * mask;
+    }
+  }
+  return acc;
+}
+
+// membrane facet integrals of a and L (oracle: facet_tensors + the facet part of assemble)
+template <int D>
+void assemble_facets(Ctx& c, double t) {
+  const Params& p = c.p;
+  const double t_mod = std::fmod(t + 1e-12, p.T_stim);
+  double stim_fac = p.g_syn_bar * std::exp(-t_mod / p.a_syn);
+  if (p.scale_stimulus) stim_fac *= 1.0 / c.stim_area;
+  const int n0 = c.ns[0], n1 = c.ns[1];
+#pragma omp parallel for schedule(static)
+  for (int f = 0; f < c.n_mf; ++f) {
+    int node[2][D];
+    double cvert[2][3][D], phimv[D], gv[3][D], xdirv[D];
+    for (int a = 0; a < D; ++a) {
+      const int g = c.mf_mv[(size_t)f * D + a];
+      for (int s = 0; s < 2; ++s) {
+        node[s][a] = c.mv_node[s][g];
+        for (int k = 0; k < 3; ++k) cvert[s][k][a] = c.u[c.base[s] + k * c.ns[s] + node[s][a]];
+      }
+      phimv[a] = c.u[3 * n0 + node[0][a]] - c.u[4 * n0 + 3 * n1 + node[1][a]];
+      for (int j = 0; j < 3; ++j) gv[j][a] = c.gates[(size_t)j * c.n_mv + g];
+      xdirv[a] = p.stim_dir >= 0 ? c.x[0][(size_t)node[0][a] * D + p.stim_dir] : 0.0;
+    }
+    double GA[2][3][D][D] = {}, G1[D][D] = {}, bc[2][3][D] = {}, bphi[D] = {};
+    for (int q = 0; q < c.nq; ++q) {
+      const double* N = &c.qb[(size_t)q * D];
+      const double wq = c.farea[f] * c.qw[q];
+      double cq[2][3] = {}, phim = 0.0, g[3] = {}, xdir = 0.0;
+      for (int a = 0; a < D; ++a) {
+        for (int s = 0; s < 2; ++s)
+          for (int k = 0; k < 3; ++k) cq[s][k] += N[a] * cvert[s][k][a];
+        phim += N[a] * phimv[a];
+        for (int j = 0; j < 3; ++j) g[j] += N[a] * gv[j][a];
+        xdir += N[a] * xdirv[a];
+      }
+      double I[3];
+      currents(c, c.mf_models[f], c.mf_stim[f] != 0, cq[0], cq[1], phim, g, xdir, stim_fac, I);
+      const double Itot = (I[0] + I[1]) + I[2];
+      double alpha[2][3];
+      for (int s = 0; s < 2; ++s) {
+        double den = 0.0;
+        for (int j = 0; j < 3; ++j) den += p.D[j] * p.z[j] * p.z[j] * cq[s][j];
+        for (int k = 0; k < 3; ++k) alpha[s][k] = p.D[k] * p.z[k] * p.z[k] * cq[s][k] / den;
+      }
+      for (int a = 0; a < D; ++a) {
+        for (int bb = 0; bb < D; ++bb) {
+          const double nn = wq * N[a] * N[bb];
+          G1[a][bb] += nn;
+          for (int s = 0; s < 2; ++s)
+            for (int k = 0; k < 3; ++k) GA[s][k][a][bb] += nn * alpha[s][k];
+        }
+        for (int s = 0; s < 2; ++s)
+          for (int k = 0; k < 3; ++k) bc[s][k][a] += wq * (p.dt * I[k] - alpha[s][k] * p.C_M * phim) * N[a] / (p.F * p.z[k]);
+        bphi[a] += wq * (p.dt * Itot - p.C_M * phim) * N[a] / p.F;
+      }
+    }
+    const double sign[2] = {1.0, -1.0};
+    for (int s = 0; s < 2; ++s) {
+      for (int a = 0; a < D; ++a) {
+        const int rp = c.base[s] + 3 * c.ns[s] + node[s][a];
+        for (int k = 0; k < 3; ++k) {
+          const int rk = c.base[s] + k * c.ns[s] + node[s][a];
+          const double coef = p.C_M / (p.F * p.z[k]);
+          for (int bb = 0; bb < D; ++bb) {
+            add(c.A, rk, 3 * n0 + node[0][bb], sign[s] * coef * GA[s][k][a][bb]);
+            add(c.A, rk, 4 * n0 + 3 * n1 + node[1][bb], -sign[s] * coef * GA[s][k][a][bb]);
+          }
+#pragma omp atomic
+          c.b[rk] += -sign[s] * bc[s][k][a];
+        }
+        for (int bb = 0; bb < D; ++bb) {
+          add(c.A, rp, 3 * n0 + node[0][bb], sign[s] * (p.C_M / p.F) * G1[a][bb]);
+          add(c.A, rp, 4 * n0 + 3 * n1 + node[1][bb], -sign[s] * (p.C_M / p.F) * G1[a][bb]);
+        }
+#pragma omp atomic
+        c.b[rp] += -sign[s] * bphi[a];
+      }
+    }
+  }
+}
+
+void gate_update(Ctx& c) {
+  const Params& p = c.p;
+  const double dt_ode = p.dt / p.ode_substeps;
+  const int n0 = c.ns[0], n1 = c.ns[1];
+#pragma omp parallel for schedule(static)
+  for (int g = 0; g < c.n_mv; ++g) {
+    const double phim = c.u[3 * n0 + c.mv_node[0][g]] - c.u[4 * n0 + 3 * n1 + c.mv_node[1][g]];
+    const double V = 1000.0 * (phim - p.phi_rest);
+    const double al[3] = {0.01e3 * (10.0 - V) / (std::exp((10.0 - V) / 10.0) - 1.0), 0.1e3 * (25.0 - V) / (std::exp((25.0 - V) / 10.0) - 1.0),
+                          0.07e3 * std::exp(-V / 20.0)};
+    const double be[3] = {0.125e3 * std::exp(-V / 80.0), 4.0e3 * std::exp(-V / 18.0), 1.0e3 / (std::exp((30.0 - V) / 10.0) + 1.0)};
+    for (int j = 0; j < 3; ++j) {
+      double y = c.gates[(size_t)j * c.n_mv + g];
+      if (p.rush_larsen) {
+        const double tau = 1.0 / (al[j] + be[j]), yinf = al[j] * tau, yexp = std::exp(-dt_ode / tau);
+        for (int it = 0; it < p.ode_substeps; ++it) y = yinf + (y - yinf) * yexp;
+      } else {
+        const double aa = al[j] * dt_ode, bb = be[j] * dt_ode;
+        for (int it = 0; it < p.ode_substeps; ++it) y = y + (aa * (1.0 - y) - bb * y);
+      }
+      c.gates[(size_t)j * c.n_mv + g] = y;
+    }
+  }
+}
+
+// ---- preconditioner -------------------------------------------------------------------------------------------------
+int build_amg(const CsrHost& A0, Amg& M) {
+  std::vector<CsrHost> As, Ps, Rs;
+  std::vector<double> rhos;
+  const int rc = knp::amg_setup_host(A0, 0.08, 2500, 16, As, Ps, Rs, rhos, M.cinv, true);
+  if (rc != 0) return rc;
+  const int nl = (int)Ps.size();
+  M.lv.resize(nl);
+  for (int l = 0; l < nl; ++l) {
+    Level& L = M.lv[l];
+    L.A = std::move(As[l]);
+    L.P = std::move(Ps[l]);
+    L.R = std::move(Rs[l]);
+    L.rho = rhos[l];
+    const int n = L.A.n_rows;
+    L.dinv.resize(n);
+    L.x.resize(n);
+    L.b.resize(n);
+    L.r.resize(n);
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; ++i) {
+      double dd = 0.0;
+      for (int j = L.A.indptr[i]; j < L.A.indptr[i + 1]; ++j)
+        if (L.A.indices[j] == i) dd += L.A.vals[j];
+      L.dinv[i] = 1.0 / dd;
+    }
+  }
+  M.nc = As.back().n_rows;
+  M.cb.resize(M.nc);
+  return 0;
+}
+
+// oracle/amg.py::SAAMG.vcycle with weighted Jacobi; W-cycle on levels 1..gamma_last
+void cycle(Amg& M, int l, const double* b, double* xout) {
+  const int nl = (int)M.lv.size();
+  if (l == nl) {
+    const int n = M.nc;
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; ++i) {
+      double s = 0.0;
+      for (int j = 0; j < n; ++j) s += M.cinv[(size_t)i * n + j] * b[j];
+      xout[i] = s;
+    }
+    return;
+  }
+  Level& L = M.lv[l];
+  const int n = L.A.n_rows;
+  const double w = (4.0 / 3.0) / L.rho;
+  double* x = L.x.data();
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n; ++i) x[i] = w * L.dinv[i] * b[i];
+  const int reps = (l >= 1 && l <= M.gamma_last) ? M.gamma : 1;
+  for (int rep = 0; rep < reps; ++rep) {
+    double* r = L.r.data();
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; ++i) {
+      double s = 0.0;
+      for (int j = L.A.indptr[i]; j < L.A.indptr[i + 1]; ++j) s += L.A.vals[j] * x[L.A.indices[j]];
+      r[i] = b[i] - s;
+    }
+    double* bc = (l + 1 == nl) ? M.cb.data() : M.lv[l + 1].b.data();
+    spmv(L.R, r, bc);
+    cycle(M, l + 1, bc, r);               // the child's result lands in this level's r (free after the restriction)
+    const int ncoarse = L.P.n_cols;
+    (void)ncoarse;
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; ++i) {
+      double s = 0.0;
+      for (int j = L.P.indptr[i]; j < L.P.indptr[i + 1]; ++j) s += L.P.vals[j] * r[L.P.indices[j]];
+      x[i] += s;
+    }
+  }
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n; ++i) {
+    double s = 0.0;
+    for (int j = L.A.indptr[i]; j < L.A.indptr[i + 1]; ++j) s += L.A.vals[j] * x[L.A.indices[j]];
+    xout[i] = x[i] + w * L.dinv[i] * (b[i] - s);
+  }
+}
+
+CsrHost adjacency_pattern(int n_nodes, const std::vector<int32_t>& cells, int nv, int blocks, int block_stride) {
+  // node adjacency (sorted, self included) replicated `blocks` times block-diagonally
+  std::vector<std::vector<int32_t>> adj(n_nodes);
+  const size_t nc = cells.size() / nv;
+  for (size_t e = 0; e < nc; ++e)
+    for (int a = 0; a < nv; ++a)
+      for (int b = 0; b < nv; ++b) adj[cells[e * nv + a]].push_back(cells[e * nv + b]);
+  CsrHost M;
+  M.n_rows = M.n_cols = blocks * block_stride;
+  M.indptr.assign(1, 0);
+#pragma omp parallel for schedule(dynamic, 4096)
+  for (int i = 0; i < n_nodes; ++i) {
+    std::sort(adj[i].begin(), adj[i].end());
+    adj[i].erase(std::unique(adj[i].begin(), adj[i].end()), adj[i].end());
+  }
+  for (int k = 0; k < blocks; ++k)
+    for (int i = 0; i < n_nodes; ++i) {
+      for (int32_t j : adj[i]) M.indices.push_back(k * block_stride + j);
+      M.indptr.push_back((int32_t)M.indices.size());
+    }
+  M.vals.assign(M.indices.size(), 0.0);
+  return M;
+}
+
+template <int D>
+int schur_setup(Ctx& c) {
+  // oracle/amg.py::SchurPC.__init__: ion blocks M + dt D_k K, potential blocks K_phi + (C_M/F) M_Gamma, mass matrices
+  const int n0 = c.ns[0], n1 = c.ns[1];
+  CsrHost Acc, App;
+  {
+    CsrHost a0 = adjacency_pattern(n0, c.cells[0], D + 1, 3, n0), a1 = adjacency_pattern(n1, c.cells[1], D + 1, 3, n1);
+    Acc.n_rows = Acc.n_cols = 3 * (n0 + n1);
+    Acc.indptr = a0.indptr;
+    Acc.indices = a0.indices;
+    const int off = (int)a0.indices.size();
+    for (size_t i = 1; i < a1.indptr.size(); ++i) Acc.indptr.push_back(off + a1.indptr[i]);
+    for (int32_t j : a1.indices) Acc.indices.push_back(3 * n0 + j);
+    Acc.vals.assign(Acc.indices.size(), 0.0);
+    CsrHost p0 = adjacency_pattern(n0, c.cells[0], D + 1, 1, n0), p1 = adjacency_pattern(n1, c.cells[1], D + 1, 1, n1);
+    c.Mass[0] = p0;
+    c.Mass[1] = p1;
+    App.n_rows = App.n_cols = n0 + n1;
+    App.indptr = p0.indptr;
+    App.indices = p0.indices;
+    const int off2 = (int)p0.indices.size();
+    for (size_t i = 1; i < p1.indptr.size(); ++i) App.indptr.push_back(off2 + p1.indptr[i]);
+    for (int32_t j : p1.indices) App.indices.push_back(n0 + j);
+    App.vals.assign(App.indices.size(), 0.0);
+  }
+  assemble_cells<D>(c, 1, +1.0, 1.0, &Acc, &App, c.Mass);
+  // membrane mass term of the potential blocks, with the sign it has in `a`
+  for (int f = 0; f < c.n_mf; ++f) {
+    double G1[D][D] = {};
+    for (int q = 0; q < c.nq; ++q)
+      for (int a = 0; a < D; ++a)
+        for (int b = 0; b < D; ++b) G1[a][b] += c.farea[f] * c.qw[q] * c.qb[(size_t)q * D + a] * c.qb[(size_t)q * D + b];
+    for (int s = 0; s < 2; ++s)
+      for (int a = 0; a < D; ++a)
+        for (int b = 0; b < D; ++b)
+          add(App, (s ? n0 : 0) + c.mv_node[s][c.mf_mv[(size_t)f * D + a]], (s ? n0 : 0) + c.mv_node[s][c.mf_mv[(size_t)f * D + b]],
+              (c.p.C_M / c.p.F) * G1[a][b]);
+  }
+  // mass matrices must not carry the D_scale = 1 stiffness: they were filled with the pure mass term above
+  c.msig_inv.resize((size_t)n0 + n1);
+  for (int s = 0; s < 2; ++s)
+    for (int i = 0; i < c.ns[s]; ++i) {
+      double ms = 0.0;
+      for (int j = c.Mass[s].indptr[i]; j < c.Mass[s].indptr[i + 1]; ++j) ms += c.Mass[s].vals[j];
+      double sig = 0.0;
+      for (int k = 0; k < 3; ++k) sig += c.p.z[k] * c.p.z[k] / c.psi * c.u[c.base[s] + k * c.ns[s] + i];
+      c.msig_inv[(s ? n0 : 0) + i] = 1.0 / (sig * ms);
+    }
+  if (build_amg(Acc, c.amg_c) != 0 || build_amg(App, c.amg_p) != 0) {
+    c.err = knp::last_error();
+    return -1;
+  }
+  c.vc.resize(3 * (size_t)(n0 + n1));
+  c.zc.resize(3 * (size_t)(n0 + n1));
+  c.tt.resize((size_t)n0 + n1);
+  c.zp.resize((size_t)n0 + n1);
+  return 0;
+}
+
+// oracle/amg.py::SchurPC.__call__
+void schur_apply(Ctx& c, const double* r, double* z) {
+  const int n0 = c.ns[0], n1 = c.ns[1];
+  const double* zz = c.p.z;
+  for (int s = 0; s < 2; ++s) {
+    const int ns = c.ns[s], base = c.base[s], cb = s ? 3 * n0 : 0;
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < 3 * ns; ++i) c.vc[cb + i] = r[base + i];
+  }
+  cycle(c.amg_c, 0, c.vc.data(), c.zc.data());
+  for (int s = 0; s < 2; ++s) {
+    const int ns = c.ns[s], base = c.base[s], cb = s ? 3 * n0 : 0, pb = s ? n0 : 0;
+    std::vector<double>& q = c.tmp;                 // scratch of length >= ns
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < ns; ++i) q[i] = (zz[0] * c.zc[cb + i] + zz[1] * c.zc[cb + ns + i]) + zz[2] * c.zc[cb + 2 * ns + i];
+    const CsrHost& M = c.Mass[s];
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < ns; ++i) {
+      double acc = 0.0;
+      for (int j = M.indptr[i]; j < M.indptr[i + 1]; ++j) acc += M.vals[j] * q[M.indices[j]];
+      c.tt[pb + i] = r[base + 3 * ns + i] - ((zz[0] * c.vc[cb + i] + zz[1] * c.vc[cb + ns + i]) + zz[2] * c.vc[cb + 2 * ns + i]) + acc;
+    }
+  }
+  cycle(c.amg_p, 0, c.tt.data(), c.zp.data());
+  for (int s = 0; s < 2; ++s) {
+    const int ns = c.ns[s], base = c.base[s], cb = s ? 3 * n0 : 0, pb = s ? n0 : 0;
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < ns; ++i) {
+      z[base + i] = c.zc[cb + i];
+      z[base + ns + i] = c.zc[cb + ns + i];
+      z[base + 2 * ns + i] = c.zc[cb + 2 * ns + i];
+      z[base + 3 * ns + i] = c.zp[pb + i] + c.tt[pb + i] * c.msig_inv[pb + i];
+    }
+  }
+  (void)n1;
+}
+
+double dot(const double* a, const double* b, int n) {
+  double s = 0.0;
+#pragma omp parallel for schedule(static) reduction(+ : s)
+  for (int i = 0; i < n; ++i) s += a[i] * b[i];
+  return s;
+}
+
+// x -= ns (ns . x), ns = normalised indicator of the phi rows
+void project(const Ctx& c, double* x) {
+  const int n0 = c.ns[0], n1 = c.ns[1];
+  double s = 0.0;
+#pragma omp parallel for schedule(static) reduction(+ : s)
+  for (int i = 0; i < n0 + n1; ++i) s += x[i < n0 ? 3 * n0 + i : 4 * n0 + 3 * n1 + (i - n0)];
+  const double sh = s / (n0 + n1);
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n0 + n1; ++i) x[i < n0 ? 3 * n0 + i : 4 * n0 + 3 * n1 + (i - n0)] -= sh;
+}
+
+void apply_B(Ctx& c, const double* v, double* z) {
+  schur_apply(c, v, z);
+  project(c, z);
+}
+
+// oracle: solve_gmres
+int gmres(Ctx& c, double rtol, int maxit, int* iterations) {
+  const int n = c.n, m = c.restart;
+  double* x = c.u.data();
+  double* w = c.w.data();
+  std::vector<double> r(n), H((size_t)(m + 1) * m), g(m + 1), cs(m), sn(m), y(m), h(m + 1), h2(m + 1);
+  auto Hat = [&](int i, int j) -> double& { return H[(size_t)i * m + j]; };
+  apply_B(c, c.b.data(), w);
+  const double bnorm = std::sqrt(dot(w, w, n));
+  int its = 0;
+  double tA = 0, tB = 0, tG = 0, tq;
+  const bool prof = getenv("KCPU_PROFILE") != nullptr;
+  while (true) {
+    spmv(c.A, x, r.data());
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; ++i) r[i] = c.b[i] - r[i];
+    apply_B(c, r.data(), w);
+    const double beta = std::sqrt(dot(w, w, n));
+    if (!(beta == beta)) return -3;
+    if (beta <= rtol * bnorm || its >= maxit) break;
+    double* V = c.V.data();
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; ++i) V[i] = w[i] / beta;
+    std::fill(g.begin(), g.end(), 0.0);
+    std::fill(H.begin(), H.end(), 0.0);
+    g[0] = beta;
+    int jdone = 0;
+    for (int j = 0; j < m; ++j) {
+      tq = omp_get_wtime();
+      spmv(c.A, V + (size_t)j * n, r.data());
+      tA += omp_get_wtime() - tq;
+      tq = omp_get_wtime();
+      apply_B(c, r.data(), w);
+      tB += omp_get_wtime() - tq;
+      tq = omp_get_wtime();
+      double before = 0.0;
+      std::fill(h.begin(), h.end(), 0.0);
+#pragma omp parallel
+      {
+        std::vector<double> loc(j + 2, 0.0);
+#pragma omp for schedule(static)
+        for (int i = 0; i < n; ++i) {
+          const double wi = w[i];
+          for (int k = 0; k <= j; ++k) loc[k] += V[(size_t)k * n + i] * wi;
+          loc[j + 1] += wi * wi;
+        }
+#pragma omp critical
+        {
+          for (int k = 0; k <= j; ++k) h[k] += loc[k];
+          before += loc[j + 1];
+        }
+      }
+#pragma omp parallel for schedule(static)
+      for (int i = 0; i < n; ++i) {
+        double acc = 0.0;
+        for (int k = 0; k <= j; ++k) acc += h[k] * V[(size_t)k * n + i];
+        w[i] -= acc;
+      }
+      double hh = 0.0;
+      for (int k = 0; k <= j; ++k) hh += h[k] * h[k];
+      double nrm2 = before - hh;
+      if (!(nrm2 > 0.5 * before)) {              // DGKS refinement only if needed (PETSc default)
+        double w2 = 0.0;
+        std::fill(h2.begin(), h2.end(), 0.0);
+        for (int k = 0; k <= j; ++k) h2[k] = dot(V + (size_t)k * n, w, n);
+        w2 = dot(w, w, n);
+#pragma omp parallel for schedule(static)
+        for (int i = 0; i < n; ++i) {
+          double acc = 0.0;
+          for (int k = 0; k <= j; ++k) acc += h2[k] * V[(size_t)k * n + i];
+          w[i] -= acc;
+        }
+        double hh2 = 0.0;
+        for (int k = 0; k <= j; ++k) {
+          h[k] += h2[k];
+          hh2 += h2[k] * h2[k];
+        }
+        nrm2 = w2 - hh2;
+      }
+      for (int k = 0; k <= j; ++k) Hat(k, j) = h[k];
+      const double hn = std::sqrt(std::max(nrm2, 0.0));
+      Hat(j + 1, j) = hn;
+      if (hn > 0.0) {
+        double* vn = V + (size_t)(j + 1) * n;
+#pragma omp parallel for schedule(static)
+        for (int i = 0; i < n; ++i) vn[i] = w[i] / hn;
+      }
+      for (int i = 0; i < j; ++i) {
+        const double t = cs[i] * Hat(i, j) + sn[i] * Hat(i + 1, j);
+        Hat(i + 1, j) = -sn[i] * Hat(i, j) + cs[i] * Hat(i + 1, j);
+        Hat(i, j) = t;
+      }
+      const double den = std::hypot(Hat(j, j), Hat(j + 1, j));
+      cs[j] = Hat(j, j) / den;
+      sn[j] = Hat(j + 1, j) / den;
+      Hat(j, j) = den;
+      Hat(j + 1, j) = 0.0;
+      g[j + 1] = -sn[j] * g[j];
+      g[j] = cs[j] * g[j];
+      ++its;
+      jdone = j + 1;
+      tG += omp_get_wtime() - tq;
+      if (std::fabs(g[j + 1]) <= rtol * bnorm || its >= maxit) break;
+    }
+    for (int i = jdone - 1; i >= 0; --i) {
+      double s = g[i];
+      for (int k = i + 1; k < jdone; ++k) s -= Hat(i, k) * y[k];
+      y[i] = s / Hat(i, i);
+    }
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; ++i) {
+      double acc = 0.0;
+      for (int k = 0; k < jdone; ++k) acc += y[k] * V[(size_t)k * n + i];
+      x[i] += acc;
+    }
+    if (std::fabs(g[jdone]) <= rtol * bnorm || its >= maxit) break;
+  }
+  *iterations = its;
+  if (prof) fprintf(stderr, "gmres: %d its, spmv %.1f ms, pc %.1f ms, gram-schmidt %.1f ms\n", its, 1e3 * tA, 1e3 * tB, 1e3 * tG);
+  return 0;
+}
+
+template <int D>
+void assemble(Ctx& c, double t) {
+  std::fill(c.A.vals.begin(), c.A.vals.end(), 0.0);
+  std::fill(c.b.begin(), c.b.end(), 0.0);
+  assemble_cells<D>(c, 0, 0.0, 1.0, nullptr, nullptr, nullptr);
+  assemble_facets<D>(c, t);
+}
+
+}  // namespace
+
+extern "C" {
+
+struct kcpu_mesh {
+  int32_t gdim;
+  int32_t ns[2];
+  const double* x[2];            // ns[s] x gdim node coordinates
+  int64_t n_cells[2];
+  const int32_t* cells[2];       // n_cells[s] x (gdim+1) restricted nodes
+  int32_t n_mv, n_mf, nq;
+  const int32_t* mv_node[2];     // per membrane vertex: restricted node on either side
+  const int32_t* mf_mv;          // n_mf x gdim membrane-vertex ids
+  const uint32_t* mf_models;     // OR of the model flags active on the facet's tag
+  const uint8_t* mf_stim;        // facet tag in stimulus_tags
+  const double *qb, *qw;         // facet quadrature (barycentric nq x gdim, weights)
+  const int32_t *indptr, *indices;   // CSR pattern of the system matrix (sorted rows)
+};
+
+void* kcpu_create(const kcpu_mesh* m, const Params* p, int32_t restart) {
+  Ctx* c = new Ctx();
+  c->d = m->gdim;
+  const int D = m->gdim;
+  for (int s = 0; s < 2; ++s) {
+    c->ns[s] = m->ns[s];
+    c->x[s].assign(m->x[s], m->x[s] + (size_t)m->ns[s] * D);
+    c->cells[s].assign(m->cells[s], m->cells[s] + (size_t)m->n_cells[s] * (D + 1));
+    c->mv_node[s].assign(m->mv_node[s], m->mv_node[s] + m->n_mv);
+  }
+  c->base[0] = 0;
+  c->base[1] = 4 * c->ns[0];
+  c->n = 4 * (c->ns[0] + c->ns[1]);
+  c->n_mv = m->n_mv;
+  c->n_mf = m->n_mf;
+  c->nq = m->nq;
+  c->mf_mv.assign(m->mf_mv, m->mf_mv + (size_t)m->n_mf * D);
+  c->mf_models.assign(m->mf_models, m->mf_models + m->n_mf);
+  c->mf_stim.assign(m->mf_stim, m->mf_stim + m->n_mf);
+  c->qb.assign(m->qb, m->qb + (size_t)m->nq * D);
+  c->qw.assign(m->qw, m->qw + m->nq);
+  c->A.n_rows = c->A.n_cols = c->n;
+  c->A.indptr.assign(m->indptr, m->indptr + c->n + 1);
+  c->A.indices.assign(m->indices, m->indices + m->indptr[c->n]);
+  c->A.vals.assign(c->A.indices.size(), 0.0);
+  c->b.assign(c->n, 0.0);
+  c->u.assign(c->n, 0.0);
+  c->gates.assign((size_t)3 * c->n_mv, 0.0);
+  c->p = *p;
+  c->psi = p->R * p->T / p->F;
+  c->t = 0.0;
+  c->step = 0;
+  c->restart = restart > 0 ? restart : 30;
+  if (D == 2) facet_areas<2>(*c);
+  else facet_areas<3>(*c);
+  c->stim_area = p->scale_stimulus ? (D == 2 ? stimulus_area<2>(*c) : stimulus_area<3>(*c)) : 1.0;
+  c->V.assign((size_t)(c->restart + 1) * c->n, 0.0);
+  c->w.assign(c->n, 0.0);
+  c->tmp.assign(c->n, 0.0);
+  return c;
+}
+
+void kcpu_destroy(void* h) { delete (Ctx*)h; }
+int kcpu_threads(void) { return omp_get_max_threads(); }
+const char* kcpu_error(void* h) { return ((Ctx*)h)->err.c_str(); }
+
+void kcpu_set_state(void* h, const double* u, const double* gates) {
+  Ctx* c = (Ctx*)h;
+  if (u) std::copy(u, u + c->n, c->u.begin());
+  if (gates) std::copy(gates, gates + (size_t)3 * c->n_mv, c->gates.begin());
+}
+void kcpu_get_state(void* h, double* u, double* gates) {
+  Ctx* c = (Ctx*)h;
+  if (u) std::copy(c->u.begin(), c->u.end(), u);
+  if (gates) std::copy(c->gates.begin(), c->gates.end(), gates);
+}
+
+// assembled values for the tests
+void kcpu_assemble(void* h, double t, double* A_vals, double* b) {
+  Ctx* c = (Ctx*)h;
+  if (c->d == 2) assemble<2>(*c, t);
+  else assemble<3>(*c, t);
+  if (A_vals) std::copy(c->A.vals.begin(), c->A.vals.end(), A_vals);
+  if (b) std::copy(c->b.begin(), c->b.end(), b);
+}
+
+void kcpu_gate_update(void* h) { gate_update(*(Ctx*)h); }
+
+// builds the Schur preconditioner from the CURRENT state (the reference assembles P once, KNPEMIx_solver.py:358-362)
+int kcpu_pc_setup(void* h) {
+  Ctx* c = (Ctx*)h;
+  return c->d == 2 ? schur_setup<2>(*c) : schur_setup<3>(*c);
+}
+
+void kcpu_pc_apply(void* h, const double* r, double* z) { schur_apply(*(Ctx*)h, r, z); }
+
+void kcpu_spmv(void* h, const double* x, double* y) { spmv(((Ctx*)h)->A, x, y); }
+
+// one pass of the SolverKNPEMI.solve loop body (KNPEMIx_solver.py:365-468; oracle: step); ms3 = {assembly, solve, total}
+int kcpu_step(void* h, double rtol, int32_t any_hh, int32_t* iterations, double* ms3) {
+  Ctx* c = (Ctx*)h;
+  const double t0 = omp_get_wtime();
+  c->t += c->p.dt;
+  c->step += 1;
+  if (any_hh) gate_update(*c);
+  if (c->d == 2) assemble<2>(*c, c->t);
+  else assemble<3>(*c, c->t);
+  const double t1 = omp_get_wtime();
+  if (c->step == 1) project(*c, c->b.data());          // nullspace.remove(b), step 1 only
+  int its = 0;
+  const int rc = gmres(*c, rtol, 5000, &its);
+  const double t2 = omp_get_wtime();
+  if (iterations) *iterations = its;
+  if (ms3) {
+    ms3[0] = 1e3 * (t1 - t0);
+    ms3[1] = 1e3 * (t2 - t1);
+    ms3[2] = 1e3 * (t2 - t0);
+  }
+  return rc;
+}
+
+}  // extern "C"

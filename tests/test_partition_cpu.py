@@ -156,3 +156,25 @@ def test_native_local_patterns_tile_the_global_pattern(kb, gdim, n, m, size):
                     assert np.array_equal(mine, ref), (s, f, lr, gr)
                     seen[gr] = True
     assert seen.all()
+
+
+@pytest.mark.parametrize("gdim,n,m,size", [(2, 24, 3, 2), (2, 24, 3, 4), (2, 32, 2, 8), (3, 8, 2, 2), (3, 12, 2, 8), (3, 8, 2, 6)])
+def test_local_slab_generator_equals_partition_of_the_global_mesh(kb, gdim, n, m, size):
+    """Multi-GPU runs of the structured tissue blocks generate only their own slab (mesh.cell_array_mesh_local); it must be
+    exactly the local mesh partition_mesh cuts out of the global mesh under the same (block) vertex -> rank map."""
+    part = __import__("importlib").import_module("knp-emi-cgx_b200.partition")
+    g = kb.mesh.cell_array_mesh(gdim, n, m)
+    own = kb.mesh.BlockOwner(gdim, n, size)
+    owner = own(np.arange(g.x.shape[0]))
+    assert np.bincount(owner, minlength=size).min() > 0
+    for rank in range(size):
+        a, ia = part.partition_mesh(g, rank, size, owner=owner)
+        b, ib = kb.mesh.cell_array_mesh_local(gdim, n, m, rank, size)
+        assert a.n_owned == b.n_owned and np.array_equal(ia["l2g"], ib["l2g"])
+        assert np.allclose(a.x, b.x, rtol=0, atol=1e-22)
+        assert np.array_equal(a.cells, b.cells) and np.array_equal(a.cell_tags, b.cell_tags)
+        assert np.array_equal(a.cell_owned, b.cell_owned)
+        assert np.array_equal(a.mf_verts, b.mf_verts) and np.array_equal(a.mf_tags, b.mf_tags)
+        assert np.array_equal(a.mf_owned, b.mf_owned)
+        gv = ia["l2g"]
+        assert np.array_equal(ia["owner_of"](gv), ib["owner_of"](gv))
