@@ -195,14 +195,14 @@ def test_native_csr_pattern_and_dofmaps_bit_exact_on_host(kb, name):
 
 
 def test_bench_reference_arm_prints_the_contract_line():
-    """`bench.py --impl reference` (the CPU oracle timed on a bounded sample) runs without a GPU and prints ONE JSON line
-    with the keys the driver reads."""
+    """`bench.py --impl reference` (the C++/OpenMP CPU port of the oracle, all host cores, unscaled) runs without a GPU and
+    prints ONE JSON line with the keys the driver reads; here on a reduced mesh (--size 64) to keep the CPU tier short."""
     import json
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "3",
-                        "--cpu-sample-n", "64"], capture_output=True, text=True, timeout=600, cwd=root)
+                        "--size", "64"], capture_output=True, text=True, timeout=600, cwd=root)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
@@ -212,6 +212,8 @@ def test_bench_reference_arm_prints_the_contract_line():
         assert k in d, k
     assert d["impl"] == "reference" and d["higher_is_better"] is False and d["unit"] == "ms"
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["extrapolated"] is False
+    assert d["cpu_baseline"]["value"] == d["value"] and "N=64" in d["config"]["workload"]
     assert "workload" in d["config"] and d["value"] > 0
 
 
