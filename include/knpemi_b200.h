@@ -165,6 +165,10 @@ int knp_spmv(knp_ctx* ctx, const double* A_vals_dev, const double* x_dev, double
 int knp_pc_setup(knp_ctx* ctx, const knp_solve_opts* opts);
 /* z = B r : one preconditioner application (hypre V-cycle in the reference). */
 int knp_pc_apply(knp_ctx* ctx, const double* r_dev, double* z_dev, void* stream);
+/* Algorithmic bytes of ONE preconditioner application on this rank (every product / vector of the cycle counted once:
+   12 B per non-zero, row pointers, input / output / epilogue vectors, the dense coarsest inverse per visit): the roofline
+   denominator bench.py reports for the cycle that replaces hypre's (KNPEMIx_solver.py:269-273). */
+int knp_pc_bytes(const knp_ctx* ctx, double* bytes);
 /* ksp.solve(b, x) (:435) incl. nullspace handling (:297-335). x_dev in/out (column layout). */
 int knp_solve(knp_ctx* ctx, const double* A_vals_dev, const double* b_dev, double* x_dev,
               const knp_solve_opts* opts, knp_solve_info* info, void* stream);

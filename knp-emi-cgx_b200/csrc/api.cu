@@ -442,6 +442,13 @@ int knp_pc_apply(knp_ctx* c, const double* r, double* z, void* stream) {
   return pc_apply(c, r, z, pick(c, stream));
 }
 
+int knp_pc_bytes(const knp_ctx* c, double* bytes) {
+  KNP_CHECK(c && bytes, "NULL argument");
+  KNP_CHECK(c->pc_kind >= 0, "knp_pc_setup must be called first");
+  *bytes = pc_bytes(c);
+  return KNP_OK;
+}
+
 int knp_solve(knp_ctx* c, const double* A_vals, const double* b, double* x, const knp_solve_opts* o,
               knp_solve_info* info, void* stream) {
   CTX_GUARD(c);

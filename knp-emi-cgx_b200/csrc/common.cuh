@@ -189,6 +189,13 @@ struct Amg {
   int gamma = 1;                      // cycle index on levels 1..gamma_last (1: V-cycle, 2: W-cycle below the finest level)
   int gamma_last = 1 << 20;
   int level0 = 0;                     // level number of levels[0] when this is the replicated tail of a distributed hierarchy
+  // fused tail: levels >= fuse_from run as ONE persistent kernel over a prebuilt operation list (linalg.cu::amg_tail_kernel)
+  int fuse_from = -1;                 // -1: not fused
+  int tail_nops = 0;
+  const double* tail_in = nullptr;    // right-hand side / result pointers the list was built for
+  double* tail_out = nullptr;
+  DevBuf<unsigned char> tail_ops;     // TailOp array (kernels.cuh)
+  DevBuf<unsigned> tail_bar;
   std::vector<CsrHost> hostA;         // kept for inspection
   ~Amg() {
     for (auto* l : levels) delete l;

@@ -129,6 +129,7 @@ struct NcclAmgComm : AmgComm {
 int ensure_workspace(knp_ctx* c, int restart);
 int pc_setup(knp_ctx* c, const knp_solve_opts* o);
 int pc_apply(knp_ctx* c, const double* r, double* z, cudaStream_t st);
+double pc_bytes(const knp_ctx* c);
 int gmres_solve(knp_ctx* c, const double* A_vals, const double* b, double* x, const knp_solve_opts* o,
                 knp_solve_info* info, cudaStream_t st);
 int halo_exchange(knp_ctx* c, double* x, cudaStream_t st);

@@ -34,7 +34,8 @@ int launch_stim_current(const DevTopo& T, const KParams& P, const int32_t* tag_s
                         const double* u, double stim_fac, double* partial, int n_partial, cudaStream_t st);
 
 // ---- linalg.cu ----
-enum SpmvEpi { EPI_SET = 0, EPI_RESID = 1, EPI_JACOBI = 2, EPI_ADD = 3 };
+enum SpmvEpi { EPI_SET = 0, EPI_RESID = 1, EPI_JACOBI = 2, EPI_ADD = 3, EPI_RESID0 = 4 };
+// EPI_RESID0 (fused cycle tail only): the pre-smoothed iterate x = w dinv b is formed on the fly, out2 = x, out = b - A x
 // out = epilogue(A x): SET: A x | RESID: b - A x | JACOBI: x + w*dinv*(b - A x) | ADD: out + A x
 int launch_spmv(int n_rows, int64_t nnz, const int32_t* indptr, const int32_t* indices, const double* vals,
                 const double* x, double* out, int epi, const double* b, const double* dinv, double w,
@@ -59,6 +60,19 @@ int launch_scale_dinv(int n, double w, const double* dinv, const double* b, doub
 int launch_extract_dinv(int n_rows, const int32_t* indptr, const int32_t* indices, const double* vals, double* dinv,
                         cudaStream_t st);
 int launch_dense_gemv(int n, const double* Minv, const double* b, double* x, cudaStream_t st);
+// one operation of the fused cycle tail (linalg.cu::amg_tail_kernel)
+enum TailType { TAIL_SPMV = 0, TAIL_DENSE = 1, TAIL_SCALE = 2 };
+struct TailOp {
+  int type, epi, n, lanes;
+  const int32_t *indptr, *indices;
+  const double* vals;        // CSR values, or the dense inverse
+  const double* x;           // input vector
+  double* out;
+  double* out2;
+  const double *b, *dinv;
+  double w;
+};
+int launch_amg_tail(const TailOp* ops_dev, int nops, unsigned* bar, cudaStream_t st);
 // Gram-Schmidt building blocks (deterministic two-stage reductions; no atomics)
 constexpr int RED_BLOCKS = 1184;   // 8 x 148 SMs: full occupancy for the streaming reductions
 // out[j] = sum_i V[j*ldv + i] * w[i], j < m ; out[m] = sum_i w[i]^2 ; partial is (m+1) x RED_BLOCKS scratch

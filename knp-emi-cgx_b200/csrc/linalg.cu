@@ -373,6 +373,112 @@ int launch_dense_gemv(int n, const double* Minv, const double* b, double* x, cud
   return KNP_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Fused tail of an AMG cycle.  Below the first one or two levels every operator of the hierarchy fits in L2 and a kernel
+// launch per SpMV costs more than the SpMV (round-1 launch list: 100 of the 143 launches of one preconditioner
+// application took < 12 us).  amg_tail_kernel is ONE persistent launch that executes the whole sub-cycle below a given
+// level -- pre-smoothing, residuals, restrictions, the recursive W-cycle visits, the dense coarsest solve, prolongations,
+// post-smoothing -- as a host-built list of operations separated by grid-wide barriers (sense-reversing counter in global
+// memory; the grid is sized so that every CTA is resident).  Matrix data is read through the read-only path, vectors
+// that other CTAs wrote earlier in the same launch through L2 (ld.global.cg).
+__device__ __forceinline__ void tail_grid_barrier(unsigned* bar, unsigned nblocks) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned gen;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(bar + 1) : "memory");
+    unsigned prev;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(bar) : "memory");
+    if (prev == nblocks - 1) {
+      asm volatile("st.relaxed.gpu.global.u32 [%0], 0;" ::"l"(bar) : "memory");
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(bar + 1), "r"(gen + 1) : "memory");
+    } else {
+      unsigned cur;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(bar + 1) : "memory");
+      } while (cur == gen);
+    }
+  }
+  __syncthreads();
+}
+
+constexpr int TAIL_THREADS = 512;
+
+__global__ void __launch_bounds__(TAIL_THREADS) amg_tail_kernel(const TailOp* __restrict__ ops, int nops, unsigned* bar) {
+  const int tid = threadIdx.x;
+  const int gtid = blockIdx.x * TAIL_THREADS + tid;
+  const int gthreads = gridDim.x * TAIL_THREADS;
+  for (int o = 0; o < nops; ++o) {
+    const TailOp op = ops[o];
+    if (op.type == TAIL_SPMV) {
+      const int lanes = op.lanes;
+      const int lane = tid & (lanes - 1);
+      const int sub = gtid / lanes, nsub = gthreads / lanes;
+      for (int base = 0; base < op.n; base += nsub) {          // uniform trip count: the sub-warp shuffles stay convergent
+        const int row = base + sub;
+        const bool valid = row < op.n;
+        double sum = 0.0;
+        if (valid) {
+          const int r0 = __ldg(op.indptr + row), r1 = __ldg(op.indptr + row + 1);
+          if (op.epi == EPI_RESID0) {
+            for (int j = r0 + lane; j < r1; j += lanes) {
+              const int c = __ldg(op.indices + j);
+              sum += __ldg(op.vals + j) * (op.w * __ldg(op.dinv + c) * __ldcg(op.b + c));
+            }
+          } else {
+            for (int j = r0 + lane; j < r1; j += lanes) sum += __ldg(op.vals + j) * __ldcg(op.x + __ldg(op.indices + j));
+          }
+        }
+        for (int off = lanes >> 1; off > 0; off >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, off, lanes);
+        if (valid && lane == 0) {
+          double r;
+          switch (op.epi) {
+            case EPI_SET: r = sum; break;
+            case EPI_RESID: r = __ldcg(op.b + row) - sum; break;
+            case EPI_JACOBI: r = __ldcg(op.x + row) + op.w * __ldg(op.dinv + row) * (__ldcg(op.b + row) - sum); break;
+            case EPI_ADD: r = __ldcg(op.out + row) + sum; break;
+            default: {   // EPI_RESID0: x = w dinv b (written to out2), r = b - A x
+              const double bi = __ldcg(op.b + row);
+              op.out2[row] = op.w * __ldg(op.dinv + row) * bi;
+              r = bi - sum;
+            }
+          }
+          op.out[row] = r;
+        }
+      }
+    } else if (op.type == TAIL_DENSE) {
+      // x = Minv b, dense row-major n x n: one warp per row
+      const int lane = tid & 31;
+      const int wrp = gtid >> 5, nw = gthreads >> 5;
+      for (int row = wrp; row < op.n; row += nw) {
+        const double* m = op.vals + (size_t)row * op.n;
+        double acc = 0.0;
+        for (int j = lane; j < op.n; j += 32) acc += __ldg(m + j) * __ldcg(op.x + j);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+        if (lane == 0) op.out[row] = acc;
+      }
+    } else {   // TAIL_SCALE: out = w dinv b
+      for (int i = gtid; i < op.n; i += gthreads) op.out[i] = op.w * __ldg(op.dinv + i) * __ldcg(op.b + i);
+    }
+    if (o + 1 < nops) {
+      __threadfence();
+      tail_grid_barrier(bar, gridDim.x);
+    }
+  }
+}
+
+int tail_grid_size() {
+  static const int g = getenv("KNP_TAIL_GRID") ? atoi(getenv("KNP_TAIL_GRID")) : 148;
+  return g < 1 ? 1 : (g > 148 ? 148 : g);      // one CTA per SM at most: every CTA is resident, the barrier cannot deadlock
+}
+
+int launch_amg_tail(const TailOp* ops_dev, int nops, unsigned* bar, cudaStream_t st) {
+  if (nops == 0) return KNP_OK;
+  amg_tail_kernel<<<tail_grid_size(), TAIL_THREADS, 0, st>>>(ops_dev, nops, bar);
+  KNP_LAUNCHED();
+  return KNP_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ reductions
 __device__ __forceinline__ double block_reduce_256(double v, double* red) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;

@@ -121,6 +121,92 @@ static int build_amg(knp_ctx* c, const CsrHost& A0, std::unique_ptr<Amg>& out, i
   return KNP_OK;
 }
 
+// ---- fused cycle tail ------------------------------------------------------------------------------------------------
+// Operation list of the sub-cycle below level `l` (the recursion of vcycle() written out; see linalg.cu::amg_tail_kernel).
+static int tail_lanes(const CsrDev& M) {
+  const double avg = M.n_rows > 0 ? (double)M.nnz / M.n_rows : 1.0;
+  return avg <= 6.0 ? 4 : avg <= 12.0 ? 8 : avg <= 24.0 ? 16 : 32;
+}
+static TailOp tail_spmv(const CsrDev& M, int epi, const double* x, double* out, const double* b, const double* dinv, double w,
+                        double* out2 = nullptr) {
+  TailOp o{};
+  o.type = TAIL_SPMV;
+  o.epi = epi;
+  o.n = M.n_rows;
+  o.lanes = tail_lanes(M);
+  o.indptr = M.indptr.p;
+  o.indices = M.indices.p;
+  o.vals = M.vals.p;
+  o.x = x;
+  o.out = out;
+  o.out2 = out2;
+  o.b = b;
+  o.dinv = dinv;
+  o.w = w;
+  return o;
+}
+static void emit_cycle(Amg& M, int l, const double* bl, double* xout, std::vector<TailOp>& ops) {
+  const int nl = (int)M.levels.size();
+  if (l == nl) {
+    TailOp o{};
+    o.type = TAIL_DENSE;
+    o.n = M.n_coarse;
+    o.vals = M.coarse_inv.p;
+    o.x = bl;
+    o.out = xout;
+    ops.push_back(o);
+    return;
+  }
+  AmgLevelDev& L = *M.levels[l];
+  const double w = (4.0 / 3.0) / L.rho;
+  const int lg = l + M.level0;
+  const int reps = (lg >= 1 && lg <= M.gamma_last) ? M.gamma : 1;
+  for (int rep = 0; rep < reps; ++rep) {
+    // the first residual forms the pre-smoothed iterate x = w dinv b on the fly (no separate pass)
+    if (rep == 0) ops.push_back(tail_spmv(L.A, EPI_RESID0, nullptr, L.r.p, bl, L.dinv.p, w, L.x.p));
+    else ops.push_back(tail_spmv(L.A, EPI_RESID, L.x.p, L.r.p, bl, nullptr, 0.0));
+    double* bc = (l + 1 == nl) ? M.cb.p : M.levels[l + 1]->b.p;
+    ops.push_back(tail_spmv(L.R, EPI_SET, L.r.p, bc, nullptr, nullptr, 0.0));
+    emit_cycle(M, l + 1, bc, L.r.p, ops);
+    ops.push_back(tail_spmv(L.P, EPI_ADD, L.r.p, L.x.p, nullptr, nullptr, 0.0));
+  }
+  ops.push_back(tail_spmv(L.A, EPI_JACOBI, L.x.p, xout, bl, L.dinv.p, w));
+}
+
+// Chooses the first level whose operator is L2-resident and prebuilds the operation list of everything below it.  For
+// fuse_from >= 1 the right-hand side / result pointers are the level buffers; a hierarchy that is small from level 0 on
+// (test fixtures, the replicated tail of a distributed hierarchy) is fused for the caller's (in, out) pair.
+static int prepare_tail(Amg& M, const double* in0, double* out0) {
+  static const int64_t fuse_nnz = getenv("KNP_FUSE_NNZ") ? atoll(getenv("KNP_FUSE_NNZ")) : 4000000;
+  M.fuse_from = -1;
+  M.tail_nops = 0;
+  const int nl = (int)M.levels.size();
+  if (fuse_nnz <= 0 || nl == 0) return KNP_OK;
+  int from = -1;
+  for (int l = 0; l < nl; ++l)
+    if (M.levels[l]->A.nnz <= fuse_nnz) {
+      from = l;
+      break;
+    }
+  if (from < 0) return KNP_OK;
+  if (from == 0 && (!in0 || !out0)) from = 1;
+  if (from >= nl) return KNP_OK;
+  std::vector<TailOp> ops;
+  M.tail_in = from == 0 ? in0 : M.levels[from]->b.p;
+  M.tail_out = from == 0 ? out0 : M.levels[from - 1]->r.p;
+  emit_cycle(M, from, M.tail_in, M.tail_out, ops);
+  std::vector<unsigned char> raw(ops.size() * sizeof(TailOp));
+  memcpy(raw.data(), ops.data(), raw.size());
+  KNP_TRY(M.tail_ops.upload(raw));
+  if (!M.tail_bar.p) {
+    KNP_TRY(M.tail_bar.alloc(2));
+    KNP_CUDA(cudaMemset(M.tail_bar.p, 0, 2 * sizeof(unsigned)));
+  }
+  M.tail_nops = (int)ops.size();
+  M.fuse_from = from;
+  return KNP_OK;
+}
+
 // ---- multi-GPU: row-distributed hierarchies (amg_dist.cpp) --------------------------------------------------------
 // Every level operator is split by rows over the ranks like the system matrix itself; a level SpMV is preceded by one
 // packed halo exchange of its input (in-place receives, dist.cu).  Below `repl_threshold` global rows the level is
@@ -404,6 +490,14 @@ static int schur_setup(knp_ctx* c) {
     }
   // the P buffer now holds the sign-flipped Schur form, not the reference's block-Jacobi P: pc kinds 1 / 2 must re-assemble
   c->P_assembled = false;
+  KNP_TRY(c->sch_vc.alloc((size_t)3 * (n0 + n1)));
+  KNP_TRY(c->sch_zc.alloc((size_t)3 * (n0 + n1)));
+  KNP_TRY(c->sch_t.alloc((size_t)n0 + n1));
+  KNP_TRY(c->sch_zp.alloc((size_t)n0 + n1));
+  if (c->amg_c) KNP_TRY(prepare_tail(*c->amg_c, c->sch_vc.p, c->sch_zc.p));
+  if (c->amg_p) KNP_TRY(prepare_tail(*c->amg_p, c->sch_t.p, c->sch_zp.p));
+  for (DistAmg* a : {c->damg_c.get(), c->damg_p.get()})
+    if (a) KNP_TRY(prepare_tail(*a->tail, a->gb.p, a->gx.p));
   // lumped M_sigma = (sum_k z_k^2 c_k / psi) at the node  x  row sum of the mass matrix
   std::vector<double> msig_inv((size_t)n0 + n1);
   const double* z = c->kp.z;
@@ -428,10 +522,6 @@ static int schur_setup(knp_ctx* c) {
       c->sch_nmblk[s] = nb;
     }
   }
-  KNP_TRY(c->sch_vc.alloc((size_t)3 * (n0 + n1)));
-  KNP_TRY(c->sch_zc.alloc((size_t)3 * (n0 + n1)));
-  KNP_TRY(c->sch_t.alloc((size_t)n0 + n1));
-  KNP_TRY(c->sch_zp.alloc((size_t)n0 + n1));
   KNP_TRY(c->sch_q.alloc(L.n_cols));
   KNP_TRY(c->sch_rhs.alloc(L.n_rows));
   KNP_CUDA(cudaMemset(c->sch_q.p, 0, (size_t)L.n_cols * sizeof(double)));
@@ -517,14 +607,16 @@ int pc_setup(knp_ctx* c, const knp_solve_opts* o) {
     HaloHost h;
     std::vector<int32_t> go, gi;
     KNP_TRY(dist_part(c, c->H.indptr_P, idx, val, oidx, [](int i) { return i; }, [](int, int) { return true; }, n, P0, h, go, gi));
-    return build_dist_amg(c, std::move(P0), std::move(h), std::move(go), std::move(gi), c->damg, 600, false);
+    KNP_TRY(build_dist_amg(c, std::move(P0), std::move(h), std::move(go), std::move(gi), c->damg, 600, false));
+    return prepare_tail(*c->damg->tail, c->damg->gb.p, c->damg->gx.p);
   }
   P0.n_rows = n;
   P0.n_cols = n;
   P0.indptr = c->H.indptr_P;
   P0.indices.swap(idx);
   P0.vals.swap(val);
-  return build_amg(c, P0, c->amg);
+  KNP_TRY(build_amg(c, P0, c->amg));
+  return prepare_tail(*c->amg, nullptr, nullptr);
 }
 
 // z = V-cycle(r); level-l right-hand side in bl, result written to xout (distinct from bl)
@@ -534,6 +626,8 @@ static CsrView view(const CsrDev& M) {
 
 static int vcycle(Amg& M, int l, const double* bl, double* xout, cudaStream_t st) {
   const int nl = (int)M.levels.size();
+  if (l == M.fuse_from && M.tail_nops > 0 && bl == M.tail_in && xout == M.tail_out)
+    return launch_amg_tail(reinterpret_cast<const TailOp*>(M.tail_ops.p), M.tail_nops, M.tail_bar.p, st);
   if (l == nl) return launch_dense_gemv(M.n_coarse, M.coarse_inv.p, bl, xout, st);
   AmgLevelDev& L = *M.levels[l];
   const int n = L.A.n_rows;
@@ -640,6 +734,51 @@ static int schur_apply_graphed(knp_ctx* c, const double* r, double* z, cudaStrea
   c->pc_graphs.push_back({r, z, exec, g_kernel_launches - l0});
   KNP_CUDA(cudaGraphLaunch(exec, st));
   return KNP_OK;
+}
+
+// ---- algorithmic bytes of one preconditioner application (roofline denominator of bench.py) -----------------------
+// Every operation of the cycle counted once with its minimal traffic: a CSR product moves 12 B per non-zero (value +
+// column), 4 B per row pointer, its input and its output vector once, plus the epilogue operands (b, D^-1, the updated
+// iterate); the dense coarsest solve reads the inverse once per visit; the Schur glue kernels read / write each of their
+// vectors once.  Visits follow the cycle index (W on levels 1..gamma_last).
+static double spmv_bytes(const CsrDev& M, int extra_vectors) {
+  return 12.0 * (double)M.nnz + 4.0 * M.n_rows + 8.0 * M.n_cols + 8.0 * M.n_rows + 8.0 * (double)extra_vectors * M.n_rows;
+}
+static double level_bytes(const CsrDev& A, const CsrDev& P, const CsrDev& R, int reps, double child) {
+  double b = 24.0 * A.n_rows;                                                     // x = w D^-1 b
+  b += reps * (spmv_bytes(A, 1) + spmv_bytes(R, 0) + child + spmv_bytes(P, 1));  // residual, restriction, child, x += P x_c
+  return b + spmv_bytes(A, 2);                                                    // Jacobi sweep (b, D^-1)
+}
+static double amg_bytes(const Amg& M, int l) {
+  const int nl = (int)M.levels.size();
+  if (l == nl) return 8.0 * (double)M.n_coarse * M.n_coarse + 16.0 * M.n_coarse;
+  const AmgLevelDev& L = *M.levels[l];
+  const int lg = l + M.level0;
+  const int reps = (lg >= 1 && lg <= M.gamma_last) ? M.gamma : 1;
+  return level_bytes(L.A, L.P, L.R, reps, amg_bytes(M, l + 1));
+}
+static double damg_bytes(const DistAmg& M, int l) {
+  if (l == (int)M.levels.size()) return 16.0 * (double)M.off.back() + amg_bytes(*M.tail, 0);   // gather + replicated tail
+  const DistLevelDev& L = *M.levels[l];
+  const int reps = (l >= 1 && l <= M.gamma_last) ? M.gamma : 1;
+  return level_bytes(L.A, L.P, L.R, reps, damg_bytes(M, l + 1)) + 16.0 * (reps + 1) * L.n_ghost;   // halo: packed + received
+}
+double pc_bytes(const knp_ctx* c) {
+  const Layout& L = c->T.L;
+  const double n01 = (double)L.n_own[0] + L.n_own[1];
+  if (c->pc_kind == 1) return 24.0 * L.n_rows;
+  if (c->pc_kind == 2) return c->damg ? damg_bytes(*c->damg, 0) : (c->amg ? amg_bytes(*c->amg, 0) : 0.0);
+  if (c->pc_kind != 3) return 16.0 * L.n_rows;
+  double b = 64.0 * n01 + 32.0 * n01 + 80.0 * n01;                 // split (4 in, 4 out), q (3 in, 1 out), merge (6 in, 4 out)
+  for (int s = 0; s < 2; ++s) {
+    if (L.n_own[s] == 0) continue;
+    const int row0 = L.row(s, 0, 0);
+    const double nnz_s = (double)c->H.indptr_P[row0 + L.n_own[s]] - c->H.indptr_P[row0];
+    b += 12.0 * nnz_s + 28.0 * L.n_own[s];                          // t += M q
+  }
+  b += c->damg_c ? damg_bytes(*c->damg_c, 0) : (c->amg_c ? amg_bytes(*c->amg_c, 0) : 0.0);
+  b += c->damg_p ? damg_bytes(*c->damg_p, 0) : (c->amg_p ? amg_bytes(*c->amg_p, 0) : 0.0);
+  return b;
 }
 
 int pc_apply(knp_ctx* c, const double* r, double* z, cudaStream_t st) {

@@ -64,7 +64,7 @@ SYMBOLS = [
     "knp_last_error", "knp_version", "knp_launch_count", "knp_create", "knp_destroy", "knp_get_sizes", "knp_csr_dev", "knp_csr_host",
     "knp_csr_P_host", "knp_dofmap_host", "knp_mverts_host", "knp_set_params", "knp_stimulus_area_local",
     "knp_set_state", "knp_get_state", "knp_state_dev", "knp_phi_m_host", "knp_gate_step", "knp_assemble",
-    "knp_assemble_P", "knp_values_dev", "knp_spmv", "knp_pc_setup", "knp_pc_apply", "knp_solve", "knp_step",
+    "knp_assemble_P", "knp_values_dev", "knp_spmv", "knp_pc_setup", "knp_pc_apply", "knp_pc_bytes", "knp_solve", "knp_step",
     "knp_step_host", "knp_set_time", "knp_get_time", "knp_l2_norm_sq", "knp_integral", "knp_membrane_area", "knp_stimulus_current", "knp_last_timings", "knp_amg_num_levels", "knp_amg_part_levels", "knp_amg_setup_host", "knp_amg_host_level", "knp_pattern_host", "knp_rowblocks_host",
     "knp_amg_dist_sim_host", "knp_amg_dist_sim_level", "knp_amg_dist_sim_perm",
     "knp_copy", "knp_amg_level_sizes", "knp_amg_level_host", "knp_nccl_unique_id", "knp_dist_init", "knp_halo_exchange",
@@ -112,6 +112,7 @@ def load():
     lib.knp_spmv.argtypes = [vp, vp, vp, vp, vp]
     lib.knp_pc_setup.argtypes = [vp, C.POINTER(SolveOpts)]
     lib.knp_pc_apply.argtypes = [vp, vp, vp, vp]
+    lib.knp_pc_bytes.argtypes = [vp, c_f64p]
     lib.knp_solve.argtypes = [vp, vp, vp, vp, C.POINTER(SolveOpts), C.POINTER(SolveInfo), vp]
     lib.knp_step.argtypes = [vp, C.POINTER(SolveOpts), C.POINTER(SolveInfo), vp]
     lib.knp_step_host.argtypes = [vp, vp, vp, C.POINTER(SolveOpts), C.POINTER(SolveInfo)]
@@ -316,6 +317,11 @@ class Context:
 
     def pc_apply(self, r_ptr, z_ptr, stream=None):
         check(self._lib.knp_pc_apply(self.h, r_ptr, z_ptr, stream))
+
+    def pc_bytes(self):
+        out = C.c_double()
+        check(self._lib.knp_pc_bytes(self.h, C.byref(out)))
+        return out.value
 
     def solve(self, opts: SolveOpts, A_ptr=None, b_ptr=None, x_ptr=None, stream=None):
         info = SolveInfo()
