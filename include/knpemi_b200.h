@@ -84,8 +84,9 @@ typedef struct {
   double g_Na_bar, g_K_bar, g_leak[3], g_leak_g[3];
   double g_syn_bar, a_syn, T_stim;
   int32_t scale_stimulus;
-  int32_t stim_dir;             /* -1: no stimulus_region; else axis */
-  double stim_lo, stim_hi;
+  int32_t stim_dir[3];          /* stimulus_region (utils/mixed_dim_problem.py:334-356): up to three axes (`multiple`), -1 = unused;
+                                   stim_dir[0] = -1: no region */
+  double stim_lo[3], stim_hi[3];  /* mask = prod_i [lo_i < x_{dir_i} < hi_i]  (KNPEMIx_ionic_model.py:558-587) */
   double K_e_init, K_i_g_init;  /* KirNaKPumpModel.E_K_init (:117) */
   int32_t ode_substeps;         /* HodgkinHuxley time_steps_ODE (:431) */
   int32_t rush_larsen;          /* use_Rush_Larsen (:430) */

@@ -270,13 +270,13 @@ int knp_stimulus_area_local(knp_ctx* c, double* out) {
     if (!H.mf_owned[f] || !c->params.tag_stim[H.mf_tagidx[f]]) continue;
     for (size_t q = 0; q < qw.size(); ++q) {
       double mask = 1.0;
-      if (p.stim_dir >= 0) {
+      for (int i = 0; i < 3 && p.stim_dir[i] >= 0; ++i) {
         double xq = 0.0;
         for (int a = 0; a < d; ++a) {
           const int node = H.mv_node[0][H.mf_mv[(size_t)f * d + a]];
-          xq += qb[q * d + a] * H.node_x[(size_t)node * d + p.stim_dir];
+          xq += qb[q * d + a] * H.node_x[(size_t)node * d + p.stim_dir[i]];
         }
-        mask = (xq > p.stim_lo && xq < p.stim_hi) ? 1.0 : 0.0;
+        mask *= (xq > p.stim_lo[i] && xq < p.stim_hi[i]) ? 1.0 : 0.0;
       }
       acc += H.mf_area[f] * qw[q] * mask;
     }
@@ -329,11 +329,14 @@ int knp_set_params(knp_ctx* c, const knp_params* p, int32_t n_tags, const knp_ta
   }
   K.g_Na_bar = p->g_Na_bar;
   K.g_K_bar = p->g_K_bar;
-  K.stim_lo = p->stim_lo;
-  K.stim_hi = p->stim_hi;
+  for (int i = 0; i < 3; ++i) {
+    KNP_CHECK(p->stim_dir[i] < c->H.gdim, "stimulus_region direction %d on a %dD mesh", p->stim_dir[i], c->H.gdim);
+    K.stim_dir[i] = p->stim_dir[i];
+    K.stim_lo[i] = p->stim_lo[i];
+    K.stim_hi[i] = p->stim_hi[i];
+  }
   K.K_e_init = p->K_e_init;
   K.K_i_g_init = p->K_i_g_init;
-  K.stim_dir = p->stim_dir;
   K.ode_substeps = p->ode_substeps;
   K.rush_larsen = p->rush_larsen;
   c->params_set = true;

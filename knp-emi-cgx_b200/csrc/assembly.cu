@@ -71,7 +71,8 @@ __global__ void __launch_bounds__(128) facet_kernel(DevTopo T, KParams P, const 
   constexpr int NS = D * (D + 1) / 2;
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= T.n_mf) return;
-  double ci[3][D], ce[3][D], pm[D], gn[D], gm[D], gh[D], xs[D];
+  double ci[3][D], ce[3][D], pm[D], gn[D], gm[D], gh[D];
+  int nodei[D];
 #pragma unroll
   for (int a = 0; a < D; ++a) {
     const int g = T.mf_mv[(size_t)f * D + a];
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(128) facet_kernel(DevTopo T, KParams P, const 
     gn[a] = gates[g];
     gm[a] = gates[(size_t)T.n_mv + g];
     gh[a] = gates[(size_t)2 * T.n_mv + g];
-    xs[a] = P.stim_dir >= 0 ? T.node_x[(size_t)qi * D + P.stim_dir] : 0.0;
+    nodei[a] = qi;
   }
   const double area = T.mf_area[f];
   const int ti = T.mf_tagidx[f];
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(128) facet_kernel(DevTopo T, KParams P, const 
 #pragma unroll
     for (int a = 0; a < D; ++a) lam[a] = T.qb[q * D + a];
     const double w = area * T.qw[q];
-    double ciq[3], ceq[3], pmq = 0.0, nq = 0.0, mq = 0.0, hq = 0.0, xq = 0.0;
+    double ciq[3], ceq[3], pmq = 0.0, nq = 0.0, mq = 0.0, hq = 0.0;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       ciq[k] = 0.0;
@@ -128,7 +129,6 @@ __global__ void __launch_bounds__(128) facet_kernel(DevTopo T, KParams P, const 
       nq += lam[a] * gn[a];
       mq += lam[a] * gm[a];
       hq += lam[a] * gh[a];
-      xq += lam[a] * xs[a];
     }
     // alpha_{k,s} (KNPEMIx_problem.py:512-513,582-583)
     double al[2][3];
@@ -160,7 +160,14 @@ __global__ void __launch_bounds__(128) facet_kernel(DevTopo T, KParams P, const 
       const double gK = P.g_leak[1] + P.g_K_bar * (nq * nq) * (nq * nq);
       double INa = gNa * (pmq - E[0]);
       if (stim_on) {
-        const double mask = (P.stim_dir < 0 || (xq > P.stim_lo && xq < P.stim_hi)) ? 1.0 : 0.0;
+        // mask = prod_i [lo_i < x_{dir_i} < hi_i] at the quadrature point (:558-587, incl. `multiple` directions)
+        double mask = 1.0;
+        for (int i = 0; i < 3 && P.stim_dir[i] >= 0; ++i) {
+          double xq = 0.0;
+#pragma unroll
+          for (int a = 0; a < D; ++a) xq += lam[a] * T.node_x[(size_t)nodei[a] * D + P.stim_dir[i]];
+          mask *= (xq > P.stim_lo[i] && xq < P.stim_hi[i]) ? 1.0 : 0.0;
+        }
         INa += mask * stim_fac * (pmq - E[0]);
       }
       I[0] += INa;
@@ -767,7 +774,8 @@ __global__ void __launch_bounds__(256) stim_current_kernel(DevTopo T, KParams P,
   double acc = 0.0;
   for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < T.n_mf; f += gridDim.x * blockDim.x) {
     if (!mf_owned[f] || tag_stim[T.mf_tagidx[f]] == 0) continue;
-    double ci[D], ce[D], pm[D], xs[D];
+    double ci[D], ce[D], pm[D];
+    int nodei[D];
 #pragma unroll
     for (int a = 0; a < D; ++a) {
       const int g = T.mf_mv[(size_t)f * D + a];
@@ -775,21 +783,26 @@ __global__ void __launch_bounds__(256) stim_current_kernel(DevTopo T, KParams P,
       ci[a] = u[T.L.col(0, 0, qi)];
       ce[a] = u[T.L.col(1, 0, qe)];
       pm[a] = u[T.L.col(0, 3, qi)] - u[T.L.col(1, 3, qe)];
-      xs[a] = P.stim_dir >= 0 ? T.node_x[(size_t)qi * D + P.stim_dir] : 0.0;
+      nodei[a] = qi;
     }
     const double area = T.mf_area[f];
     for (int q = 0; q < T.nq; ++q) {
-      double ciq = 0.0, ceq = 0.0, pmq = 0.0, xq = 0.0;
+      double ciq = 0.0, ceq = 0.0, pmq = 0.0;
 #pragma unroll
       for (int a = 0; a < D; ++a) {
         const double lam = T.qb[q * D + a];
         ciq += lam * ci[a];
         ceq += lam * ce[a];
         pmq += lam * pm[a];
-        xq += lam * xs[a];
       }
       const double E_Na = (P.psi / P.z[0]) * log(ceq / ciq);
-      const double mask = (P.stim_dir < 0 || (xq > P.stim_lo && xq < P.stim_hi)) ? 1.0 : 0.0;
+      double mask = 1.0;
+      for (int i = 0; i < 3 && P.stim_dir[i] >= 0; ++i) {
+        double xq = 0.0;
+#pragma unroll
+        for (int a = 0; a < D; ++a) xq += T.qb[q * D + a] * T.node_x[(size_t)nodei[a] * D + P.stim_dir[i]];
+        mask *= (xq > P.stim_lo[i] && xq < P.stim_hi[i]) ? 1.0 : 0.0;
+      }
       acc += area * T.qw[q] * mask * stim_fac * (pmq - E_Na);
     }
   }

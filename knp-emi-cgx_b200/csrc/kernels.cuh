@@ -10,9 +10,9 @@ struct KParams {
   double dt, F, C_M, psi, phi_rest;
   double z[3], D[3];
   double g_Na_bar, g_K_bar, g_leak[3], g_leak_g[3];
-  double stim_lo, stim_hi;
+  double stim_lo[3], stim_hi[3];
   double K_e_init, K_i_g_init;
-  int stim_dir;
+  int stim_dir[3];     // axes of the stimulus region (-1: unused; [0] = -1: no region)
   int ode_substeps, rush_larsen;
 };
 

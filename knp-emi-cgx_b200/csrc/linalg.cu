@@ -401,9 +401,43 @@ __device__ __forceinline__ void tail_grid_barrier(unsigned* bar, unsigned nblock
   __syncthreads();
 }
 
-constexpr int TAIL_THREADS = 512;
+constexpr int TAIL_THREADS = 1024;
 
-__global__ void __launch_bounds__(TAIL_THREADS) amg_tail_kernel(const TailOp* __restrict__ ops, int nops, unsigned* bar) {
+// four independent (index -> x) gathers in flight per lane: these levels are L2-resident, so the loop is latency-bound
+template <bool RESID0>
+__device__ __forceinline__ double tail_row_sum(const TailOp& op, int r0, int r1, int lane, int lanes) {
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int j = r0 + lane;
+  for (; j + 3 * lanes < r1; j += 4 * lanes) {
+    const int c0 = __ldg(op.indices + j), c1 = __ldg(op.indices + j + lanes), c2 = __ldg(op.indices + j + 2 * lanes),
+              c3 = __ldg(op.indices + j + 3 * lanes);
+    const double v0 = __ldg(op.vals + j), v1 = __ldg(op.vals + j + lanes), v2 = __ldg(op.vals + j + 2 * lanes),
+                 v3 = __ldg(op.vals + j + 3 * lanes);
+    double x0, x1, x2, x3;
+    if (RESID0) {
+      x0 = op.w * __ldg(op.dinv + c0) * __ldcg(op.b + c0);
+      x1 = op.w * __ldg(op.dinv + c1) * __ldcg(op.b + c1);
+      x2 = op.w * __ldg(op.dinv + c2) * __ldcg(op.b + c2);
+      x3 = op.w * __ldg(op.dinv + c3) * __ldcg(op.b + c3);
+    } else {
+      x0 = __ldcg(op.x + c0);
+      x1 = __ldcg(op.x + c1);
+      x2 = __ldcg(op.x + c2);
+      x3 = __ldcg(op.x + c3);
+    }
+    s0 += v0 * x0;
+    s1 += v1 * x1;
+    s2 += v2 * x2;
+    s3 += v3 * x3;
+  }
+  for (; j < r1; j += lanes) {
+    const int c = __ldg(op.indices + j);
+    s0 += __ldg(op.vals + j) * (RESID0 ? op.w * __ldg(op.dinv + c) * __ldcg(op.b + c) : __ldcg(op.x + c));
+  }
+  return (s0 + s1) + (s2 + s3);
+}
+
+__global__ void __launch_bounds__(TAIL_THREADS, 1) amg_tail_kernel(const TailOp* __restrict__ ops, int nops, unsigned* bar) {
   const int tid = threadIdx.x;
   const int gtid = blockIdx.x * TAIL_THREADS + tid;
   const int gthreads = gridDim.x * TAIL_THREADS;
@@ -419,14 +453,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) amg_tail_kernel(const TailOp* __
         double sum = 0.0;
         if (valid) {
           const int r0 = __ldg(op.indptr + row), r1 = __ldg(op.indptr + row + 1);
-          if (op.epi == EPI_RESID0) {
-            for (int j = r0 + lane; j < r1; j += lanes) {
-              const int c = __ldg(op.indices + j);
-              sum += __ldg(op.vals + j) * (op.w * __ldg(op.dinv + c) * __ldcg(op.b + c));
-            }
-          } else {
-            for (int j = r0 + lane; j < r1; j += lanes) sum += __ldg(op.vals + j) * __ldcg(op.x + __ldg(op.indices + j));
-          }
+          sum = op.epi == EPI_RESID0 ? tail_row_sum<true>(op, r0, r1, lane, lanes) : tail_row_sum<false>(op, r0, r1, lane, lanes);
         }
         for (int off = lanes >> 1; off > 0; off >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, off, lanes);
         if (valid && lane == 0) {
@@ -446,13 +473,23 @@ __global__ void __launch_bounds__(TAIL_THREADS) amg_tail_kernel(const TailOp* __
         }
       }
     } else if (op.type == TAIL_DENSE) {
-      // x = Minv b, dense row-major n x n: one warp per row
+      // x = Minv b, dense row-major n x n: one warp per row, eight loads in flight per lane
       const int lane = tid & 31;
       const int wrp = gtid >> 5, nw = gthreads >> 5;
       for (int row = wrp; row < op.n; row += nw) {
         const double* m = op.vals + (size_t)row * op.n;
-        double acc = 0.0;
-        for (int j = lane; j < op.n; j += 32) acc += __ldg(m + j) * __ldcg(op.x + j);
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int j = lane;
+        for (; j + 224 < op.n; j += 256) {
+          const double m0 = __ldg(m + j), m1 = __ldg(m + j + 32), m2 = __ldg(m + j + 64), m3 = __ldg(m + j + 96);
+          const double m4 = __ldg(m + j + 128), m5 = __ldg(m + j + 160), m6 = __ldg(m + j + 192), m7 = __ldg(m + j + 224);
+          a0 += m0 * __ldcg(op.x + j) + m4 * __ldcg(op.x + j + 128);
+          a1 += m1 * __ldcg(op.x + j + 32) + m5 * __ldcg(op.x + j + 160);
+          a2 += m2 * __ldcg(op.x + j + 64) + m6 * __ldcg(op.x + j + 192);
+          a3 += m3 * __ldcg(op.x + j + 96) + m7 * __ldcg(op.x + j + 224);
+        }
+        for (; j < op.n; j += 32) a0 += __ldg(m + j) * __ldcg(op.x + j);
+        double acc = (a0 + a1) + (a2 + a3);
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
         if (lane == 0) op.out[row] = acc;

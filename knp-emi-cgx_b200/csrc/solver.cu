@@ -124,8 +124,11 @@ static int build_amg(knp_ctx* c, const CsrHost& A0, std::unique_ptr<Amg>& out, i
 // ---- fused cycle tail ------------------------------------------------------------------------------------------------
 // Operation list of the sub-cycle below level `l` (the recursion of vcycle() written out; see linalg.cu::amg_tail_kernel).
 static int tail_lanes(const CsrDev& M) {
+  // few lanes per row = many rows in flight; every lane keeps four gathers in flight (linalg.cu::tail_row_sum)
   const double avg = M.n_rows > 0 ? (double)M.nnz / M.n_rows : 1.0;
-  return avg <= 6.0 ? 4 : avg <= 12.0 ? 8 : avg <= 24.0 ? 16 : 32;
+  static const int force = getenv("KNP_TAIL_LANES") ? atoi(getenv("KNP_TAIL_LANES")) : 0;
+  if (force) return force;
+  return avg <= 8.0 ? 1 : avg <= 16.0 ? 2 : avg <= 32.0 ? 4 : 8;
 }
 static TailOp tail_spmv(const CsrDev& M, int epi, const double* x, double* out, const double* b, const double* dinv, double w,
                         double* out2 = nullptr) {

@@ -39,8 +39,8 @@ class Params(C.Structure):
                 ("phi_rest", C.c_double), ("z", C.c_double * 3), ("D", C.c_double * 3),
                 ("g_Na_bar", C.c_double), ("g_K_bar", C.c_double), ("g_leak", C.c_double * 3),
                 ("g_leak_g", C.c_double * 3), ("g_syn_bar", C.c_double), ("a_syn", C.c_double),
-                ("T_stim", C.c_double), ("scale_stimulus", C.c_int32), ("stim_dir", C.c_int32),
-                ("stim_lo", C.c_double), ("stim_hi", C.c_double), ("K_e_init", C.c_double),
+                ("T_stim", C.c_double), ("scale_stimulus", C.c_int32), ("stim_dir", C.c_int32 * 3),
+                ("stim_lo", C.c_double * 3), ("stim_hi", C.c_double * 3), ("K_e_init", C.c_double),
                 ("K_i_g_init", C.c_double), ("ode_substeps", C.c_int32), ("rush_larsen", C.c_int32),
                 ("stim_area", C.c_double)]
 

@@ -241,9 +241,14 @@ class ProblemKNPEMI:
             self.stimulus_region_range = np.array(config["stimulus_region"]["range"]) * self.mesh_conversion_factor
             axes = {"x": 0, "y": 1, "z": 2}
             if config["stimulus_region"].get("multiple", False):
-                raise NotImplementedError("stimulus_region with multiple directions is not supported by the B200 path yet")
-            self.multiple_stimulus_directions = False
-            self.stimulus_region_direction = axes[str(config["stimulus_region"]["direction"])]
+                # several directions: range = [[lo, hi], ...], direction = [axis, ...] (mixed_dim_problem.py:346-351)
+                self.multiple_stimulus_directions = True
+                self.stimulus_region_directions = [axes[str(d)] for d in config["stimulus_region"]["direction"]]
+                if len(self.stimulus_region_directions) > 3 or np.shape(self.stimulus_region_range) != (len(self.stimulus_region_directions), 2):
+                    raise RuntimeError("stimulus_region with multiple: give one [lo, hi] range per direction (at most 3).")
+            else:
+                self.multiple_stimulus_directions = False
+                self.stimulus_region_direction = axes[str(config["stimulus_region"]["direction"])]
         else:
             self.stimulus_region = False
         if "initial_conditions" in config:
@@ -545,11 +550,15 @@ class ProblemKNPEMI:
         P.g_Na_bar, P.g_K_bar = self.g_Na_bar.value, self.g_K_bar.value
         P.g_syn_bar, P.a_syn, P.T_stim = self.g_syn_bar.value, self.a_syn.value, self.T_stim.value
         P.scale_stimulus = int(bool(self.scale_stimulus))
-        if self.stimulus_region:
-            P.stim_dir = int(self.stimulus_region_direction)
-            P.stim_lo, P.stim_hi = float(self.stimulus_region_range[0]), float(self.stimulus_region_range[1])
-        else:
-            P.stim_dir, P.stim_lo, P.stim_hi = -1, 0.0, 0.0
+        for i in range(3):
+            P.stim_dir[i], P.stim_lo[i], P.stim_hi[i] = -1, 0.0, 0.0
+        if self.stimulus_region and self.multiple_stimulus_directions:
+            for i, d in enumerate(self.stimulus_region_directions):
+                P.stim_dir[i] = int(d)
+                P.stim_lo[i], P.stim_hi[i] = float(self.stimulus_region_range[i][0]), float(self.stimulus_region_range[i][1])
+        elif self.stimulus_region:
+            P.stim_dir[0] = int(self.stimulus_region_direction)
+            P.stim_lo[0], P.stim_hi[0] = float(self.stimulus_region_range[0]), float(self.stimulus_region_range[1])
         P.K_e_init, P.K_i_g_init = self.K_e_init.value, self.K_i_g_init.value
         P.ode_substeps, P.rush_larsen = int(self.ode_substeps), int(self.rush_larsen)
         P.stim_area = stim_area

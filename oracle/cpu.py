@@ -22,8 +22,8 @@ class _Params(C.Structure):
     _fields_ = [("dt", C.c_double), ("F", C.c_double), ("R", C.c_double), ("T", C.c_double), ("C_M", C.c_double),
                 ("phi_rest", C.c_double), ("z", C.c_double * 3), ("D", C.c_double * 3), ("g_Na_bar", C.c_double),
                 ("g_K_bar", C.c_double), ("g_leak", C.c_double * 3), ("g_leak_g", C.c_double * 3), ("g_syn_bar", C.c_double),
-                ("a_syn", C.c_double), ("T_stim", C.c_double), ("scale_stimulus", C.c_int32), ("stim_dir", C.c_int32),
-                ("stim_lo", C.c_double), ("stim_hi", C.c_double), ("K_e_init", C.c_double), ("K_i_g_init", C.c_double),
+                ("a_syn", C.c_double), ("T_stim", C.c_double), ("scale_stimulus", C.c_int32), ("stim_dir", C.c_int32 * 3),
+                ("stim_lo", C.c_double * 3), ("stim_hi", C.c_double * 3), ("K_e_init", C.c_double), ("K_i_g_init", C.c_double),
                 ("ode_substeps", C.c_int32), ("rush_larsen", C.c_int32)]
 
 
@@ -117,10 +117,12 @@ class CpuBaseline:
             P.z[i], P.D[i], P.g_leak[i], P.g_leak_g[i] = p.z[i], p.D[i], p.g_leak[i], p.g_leak_g[i]
         P.g_Na_bar, P.g_K_bar, P.g_syn_bar, P.a_syn, P.T_stim = p.g_Na_bar, p.g_K_bar, p.g_syn_bar, p.a_syn, p.T_stim
         P.scale_stimulus = int(p.scale_stimulus)
-        if p.stimulus_region is None:
-            P.stim_dir = -1
-        else:
-            P.stim_dir, P.stim_lo, P.stim_hi = p.stimulus_region
+        for i in range(3):
+            P.stim_dir[i] = -1
+        if p.stimulus_region is not None:
+            regions = p.stimulus_region if isinstance(p.stimulus_region[0], (tuple, list)) else [p.stimulus_region]
+            for i, (d, lo, hi) in enumerate(regions):
+                P.stim_dir[i], P.stim_lo[i], P.stim_hi[i] = d, lo, hi
         P.K_e_init, P.K_i_g_init = p.c_e_init[1], p.c_i_g_init[1]
         P.ode_substeps, P.rush_larsen = p.ode_substeps, int(p.rush_larsen)
         self.any_hh = any(nm == "HH" for nm, _ in models)

@@ -38,8 +38,8 @@ struct Params {
   double z[3], D[3];
   double g_Na_bar, g_K_bar, g_leak[3], g_leak_g[3];
   double g_syn_bar, a_syn, T_stim;
-  int32_t scale_stimulus, stim_dir;
-  double stim_lo, stim_hi;
+  int32_t scale_stimulus, stim_dir[3];
+  double stim_lo[3], stim_hi[3];
   double K_e_init, K_i_g_init;
   int32_t ode_substeps, rush_larsen;
 };
@@ -213,7 +213,7 @@ void assemble_cells(Ctx& c, int mode, double membrane_sign, double D_scale, CsrH
 
 // I_ch,k at one quadrature point (oracle: channel_currents)
 inline void currents(const Ctx& c, uint32_t models, bool stimulated, const double ci[3], const double ce[3], double phim,
-                     const double g[3], double xdir, double stim_fac, double I[3]) {
+                     const double g[3], double mask, double stim_fac, double I[3]) {
   const Params& p = c.p;
   const double psi = c.psi;
   double E[3];
@@ -246,11 +246,7 @@ inline void currents(const Ctx& c, uint32_t models, bool stimulated, const doubl
     const double gg[3] = {p.g_leak[0] + p.g_Na_bar * m * m * m * h, p.g_leak[1] + p.g_K_bar * n * n * n * n, p.g_leak[2] + 0.0 * n};
     double Ik[3];
     for (int k = 0; k < 3; ++k) Ik[k] = gg[k] * (phim - E[k]);
-    if (stimulated) {
-      double mask = 1.0;
-      if (p.stim_dir >= 0) mask = (xdir > p.stim_lo && xdir < p.stim_hi) ? 1.0 : 0.0;
-      Ik[0] += mask * stim_fac * (phim - E[0]);
-    }
+    if (stimulated) Ik[0] += mask * stim_fac * (phim - E[0]);
     for (int k = 0; k < 3; ++k) I[k] += Ik[k];
   }
   if (models & M_KIRNA) {
@@ -294,11 +290,11 @@ double stimulus_area(const Ctx& c) {
     if (!c.mf_stim[f]) continue;
     for (int q = 0; q < c.nq; ++q) {
       double mask = 1.0;
-      if (c.p.stim_dir >= 0) {
+      for (int i = 0; i < 3 && c.p.stim_dir[i] >= 0; ++i) {
         double xq = 0.0;
         for (int a = 0; a < D; ++a)
-          xq += c.qb[(size_t)q * D + a] * c.x[0][(size_t)c.mv_node[0][c.mf_mv[(size_t)f * D + a]] * D + c.p.stim_dir];
-        mask = (xq > c.p.stim_lo && xq < c.p.stim_hi) ? 1.0 : 0.0;
+          xq += c.qb[(size_t)q * D + a] * c.x[0][(size_t)c.mv_node[0][c.mf_mv[(size_t)f * D + a]] * D + c.p.stim_dir[i]];
+        mask *= (xq > c.p.stim_lo[i] && xq < c.p.stim_hi[i]) ? 1.0 : 0.0;
       }
       acc += c.farea[f] * c.qw[q] * mask;
     }
@@ -317,7 +313,7 @@ void assemble_facets(Ctx& c, double t) {
 #pragma omp parallel for schedule(static)
   for (int f = 0; f < c.n_mf; ++f) {
     int node[2][D];
-    double cvert[2][3][D], phimv[D], gv[3][D], xdirv[D];
+    double cvert[2][3][D], phimv[D], gv[3][D];
     for (int a = 0; a < D; ++a) {
       const int g = c.mf_mv[(size_t)f * D + a];
       for (int s = 0; s < 2; ++s) {
@@ -326,22 +322,25 @@ void assemble_facets(Ctx& c, double t) {
       }
       phimv[a] = c.u[3 * n0 + node[0][a]] - c.u[4 * n0 + 3 * n1 + node[1][a]];
       for (int j = 0; j < 3; ++j) gv[j][a] = c.gates[(size_t)j * c.n_mv + g];
-      xdirv[a] = p.stim_dir >= 0 ? c.x[0][(size_t)node[0][a] * D + p.stim_dir] : 0.0;
     }
     double GA[2][3][D][D] = {}, G1[D][D] = {}, bc[2][3][D] = {}, bphi[D] = {};
     for (int q = 0; q < c.nq; ++q) {
       const double* N = &c.qb[(size_t)q * D];
       const double wq = c.farea[f] * c.qw[q];
-      double cq[2][3] = {}, phim = 0.0, g[3] = {}, xdir = 0.0;
+      double cq[2][3] = {}, phim = 0.0, g[3] = {}, mask = 1.0;
       for (int a = 0; a < D; ++a) {
         for (int s = 0; s < 2; ++s)
           for (int k = 0; k < 3; ++k) cq[s][k] += N[a] * cvert[s][k][a];
         phim += N[a] * phimv[a];
         for (int j = 0; j < 3; ++j) g[j] += N[a] * gv[j][a];
-        xdir += N[a] * xdirv[a];
+      }
+      for (int i = 0; i < 3 && p.stim_dir[i] >= 0; ++i) {       // stimulus region mask (incl. `multiple` directions)
+        double xq = 0.0;
+        for (int a = 0; a < D; ++a) xq += N[a] * c.x[0][(size_t)node[0][a] * D + p.stim_dir[i]];
+        mask *= (xq > p.stim_lo[i] && xq < p.stim_hi[i]) ? 1.0 : 0.0;
       }
       double I[3];
-      currents(c, c.mf_models[f], c.mf_stim[f] != 0, cq[0], cq[1], phim, g, xdir, stim_fac, I);
+      currents(c, c.mf_models[f], c.mf_stim[f] != 0, cq[0], cq[1], phim, g, mask, stim_fac, I);
       const double Itot = (I[0] + I[1]) + I[2];
       double alpha[2][3];
       for (int s = 0; s < 2; ++s) {

@@ -65,7 +65,7 @@ class OracleParams:
     extra_tag: int = 2
     membrane_tags: tuple = (4,)
     stimulus_tags: tuple = (4,)
-    stimulus_region: tuple = None      # (direction, lo, hi) or None
+    stimulus_region: tuple = None      # (direction, lo, hi), a tuple of such triples (`multiple` directions), or None
     ode_substeps: int = 25
     rush_larsen: bool = True
 
@@ -205,9 +205,12 @@ class KNPEMIOracle:
         p = self.p
         if p.stimulus_region is None:
             return np.ones(xq.shape[:-1])
-        direction, lo, hi = p.stimulus_region
-        c = xq[..., direction]
-        return ((c > lo) & (c < hi)).astype(float)
+        regions = p.stimulus_region if isinstance(p.stimulus_region[0], (tuple, list)) else [p.stimulus_region]
+        mask = np.ones(xq.shape[:-1])
+        for direction, lo, hi in regions:                  # product of the per-direction masks (ionic_model.py:574-587)
+            c = xq[..., direction]
+            mask = mask * ((c > lo) & (c < hi)).astype(float)
+        return mask
 
     def stimulus_area(self):
         """p.stimulus_area = assemble(mask * dS(stimulus_tags)) (KNPEMIx_ionic_model.py:591-601)."""

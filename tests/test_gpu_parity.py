@@ -30,10 +30,12 @@ def make_ctx(kb, om, p: OracleParams, models, device=0):
         P.z[k], P.D[k], P.g_leak[k], P.g_leak_g[k] = p.z[k], p.D[k], p.g_leak[k], p.g_leak_g[k]
     P.g_Na_bar, P.g_K_bar, P.g_syn_bar, P.a_syn, P.T_stim = p.g_Na_bar, p.g_K_bar, p.g_syn_bar, p.a_syn, p.T_stim
     P.scale_stimulus = int(p.scale_stimulus)
-    if p.stimulus_region is None:
-        P.stim_dir = -1
-    else:
-        P.stim_dir, P.stim_lo, P.stim_hi = p.stimulus_region
+    for i in range(3):
+        P.stim_dir[i] = -1
+    if p.stimulus_region is not None:
+        regions = p.stimulus_region if isinstance(p.stimulus_region[0], (tuple, list)) else [p.stimulus_region]
+        for i, (d, lo, hi) in enumerate(regions):
+            P.stim_dir[i], P.stim_lo[i], P.stim_hi[i] = d, lo, hi
     P.K_e_init, P.K_i_g_init = p.c_e_init[1], p.c_i_g_init[1]
     P.ode_substeps, P.rush_larsen, P.stim_area = p.ode_substeps, int(p.rush_larsen), 0.0
     table = {}
