@@ -243,6 +243,10 @@ int knp_dist_init(knp_ctx* ctx, int32_t rank, int32_t nranks, const char* unique
                   int32_t n_peers, const int32_t* peers,
                   const int64_t* send_ptr, const int32_t* send_cols,   /* owned columns packed per peer */
                   const int64_t* recv_ptr, const int32_t* recv_cols);  /* ghost columns filled per peer */
+/* 1 when ghost exchanges and all-reduces run as the library's own kernels over NVLink / NVSwitch peer memory (CUDA IPC
+   mappings set up in knp_dist_init), 0 when they go through NCCL point-to-point / all-reduce (KNP_HALO=nccl or IPC
+   unavailable). */
+int knp_peer_direct(const knp_ctx* ctx);
 int knp_halo_exchange(knp_ctx* ctx, double* x_dev, void* stream);
 int knp_allreduce_sum(knp_ctx* ctx, double* buf_dev, int32_t n, void* stream);
 

@@ -8,6 +8,22 @@
 struct ncclComm;
 
 namespace knp {
+// One peer of a direct NVLink exchange (dist.cu::peer_push_kernel): where this rank's data and flags go in the PEER's memory
+// (pointers obtained through CUDA IPC) and where the peer's flags arrive here.
+struct PushPeer {
+  int64_t send_begin, send_count;
+  double* remote_data;                 // peer memory: the slice of its ghost tail (or receive buffer) that belongs to this rank
+  unsigned long long* remote_flags;    // peer memory: [0] = "I have consumed epoch e-1", [1] = "epoch e data is complete"
+  unsigned long long* local_flags;     // own memory: the same two counters written by the peer
+};
+// A fixed exchange pattern executed by ONE kernel: pack + remote stores + flag handshake over NVLink / NVSwitch peer memory
+struct PeerLink {
+  bool ready = false;
+  int np = 0;
+  DevBuf<PushPeer> peers;
+  DevBuf<unsigned long long> epoch;    // per peer: completed exchanges
+};
+
 // device side of HaloHost: ghosts are received in place at x + n_own + recv_ptr[i]
 struct HaloDev {
   std::vector<int32_t> peers;
@@ -15,12 +31,15 @@ struct HaloDev {
   DevBuf<int32_t> send_idx;
   DevBuf<double> sbuf;
   int n_own = 0;
+  PeerLink link;                       // direct peer-memory path (falls back to grouped ncclSend / ncclRecv when not ready)
+  const double* link_x = nullptr;      // the vector the link was built for (its ghost tail is the remote target)
 };
 
 struct DistLevelDev {
   int n_own = 0, n_ghost = 0;
   CsrDev A, P, R;
-  DevBuf<double> dinv, x, b, r;
+  DevBuf<double> dinv, b, r;
+  double* x = nullptr;                 // [owned | ghosts], lives in the hierarchy's peer-visible arena
   HaloDev halo;
   double rho = 2.0;
 };
@@ -31,7 +50,10 @@ struct DistAmg {
   std::vector<std::unique_ptr<DistLevelDev>> levels;
   std::unique_ptr<Amg> tail;
   std::vector<int64_t> off;            // row offsets of the ranks inside the replicated level
-  DevBuf<double> gb, gx, rb;           // replicated right-hand side / solution; this rank's piece of the right-hand side
+  DevBuf<double> arena;                // peer-visible (CUDA IPC) allocation holding every level's x and the gathered rhs gb
+  double* gb = nullptr;                // replicated right-hand side (in the arena: the peers write their pieces into it)
+  DevBuf<double> gx, rb;               // replicated solution; this rank's piece of the right-hand side
+  PeerLink gather;                     // all-to-all of the rhs pieces at the replicated level
   int gamma = 1, gamma_last = 1 << 20;
   std::vector<CsrHost> hostA;          // this rank's rows of the distributed level operators (inspection)
 };
@@ -98,6 +120,15 @@ struct knp_ctx {
   int64_t n_phi_global = 0;   // global number of potential dofs (nullspace normalisation)
   std::vector<int32_t> h_recv_cols;   // ghost columns in receive order (host copy)
   std::vector<int32_t> h_send_cols;   // owned columns in send order (host copy)
+  // direct NVLink exchanges: flag arena (peer-writable through CUDA IPC), the peers' arenas, opened IPC mappings
+  knp::DevBuf<unsigned long long> flag_arena;
+  int flag_slots_used = 0;
+  std::vector<unsigned long long*> peer_flag_arena;    // per rank (nullptr: not mapped)
+  std::vector<std::pair<std::string, void*>> ipc_open;  // (rank + handle bytes) -> mapped base pointer
+  bool peer_direct = false;
+  knp::PeerLink main_link;                              // main 8-field halo: pushes into the peers' receive buffers
+  knp::PeerLink red_link;                               // all-reduce: every rank's partial sums into every peer's slot
+  knp::DevBuf<double> red_slots;                        // nranks x RED_MAX doubles (peer-visible)
   // timers
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   double last_ms[5] = {0, 0, 0, 0, 0};
@@ -116,6 +147,14 @@ struct P2POp {
 int p2p_exchange(knp_ctx* c, const std::vector<P2POp>& ops, cudaStream_t st);
 int halo_exchange_inplace(knp_ctx* c, HaloDev& H, double* x, cudaStream_t st);
 int halo_upload(const HaloHost& h, int n_own, HaloDev& d);
+constexpr int RED_MAX = 64;            // doubles per rank in the peer-memory all-reduce
+// Builds the direct peer-memory exchange for a pattern (collective over the ranks): `target_base` is the base of a cudaMalloc
+// allocation of THIS rank that the peers write into, starting `target_offset[i]` doubles from the base for peer i.
+int peer_link_create(knp_ctx* c, const std::vector<int32_t>& peers, const std::vector<int64_t>& send_begin,
+                     const std::vector<int64_t>& send_count, void* target_base, const std::vector<int64_t>& target_offset,
+                     PeerLink& out);
+int peer_error_check(knp_ctx* c);
+int peer_push(knp_ctx* c, PeerLink& L, const int32_t* send_idx, const double* x, cudaStream_t st);
 struct NcclAmgComm : AmgComm {
   knp_ctx* c;
   explicit NcclAmgComm(knp_ctx* ctx) : c(ctx) {

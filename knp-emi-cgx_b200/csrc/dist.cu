@@ -5,6 +5,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 #include <mutex>
+#include <string>
 #include "context.cuh"
 
 namespace knp {
@@ -82,6 +83,16 @@ int halo_exchange(knp_ctx* c, double* x, cudaStream_t st) {
   const int64_t ns = c->send_ptr[np], nr = c->recv_ptr[np];
   double* sbuf = c->d_send_buf.p;
   double* rbuf = c->d_send_buf.p + ns;
+  if (c->main_link.ready) {
+    KNP_TRY(peer_push(c, c->main_link, c->d_send_cols.p, x, st));
+    if (nr > 0) {
+      int grid = (int)((nr + 255) / 256);
+      if (grid > 148 * 8) grid = 148 * 8;
+      unpack_kernel<<<grid, 256, 0, st>>>(nr, c->d_send_cols.p + ns, rbuf, x);
+      KNP_LAUNCHED();
+    }
+    return KNP_OK;
+  }
   if (ns > 0) {
     int grid = (int)((ns + 255) / 256);
     if (grid > 148 * 8) grid = 148 * 8;
@@ -104,11 +115,239 @@ int halo_exchange(knp_ctx* c, double* x, cudaStream_t st) {
   return KNP_OK;
 }
 
+// ---- direct NVLink / NVSwitch exchanges through peer memory (CUDA IPC) ----------------------------------------------
+// One kernel per exchange instead of pack kernel + NCCL group (+ unpack): CTA i serves peer i.  It (1) tells the peer that
+// this rank has finished reading what the peer sent last time (true by stream order: the consumer kernel precedes this
+// launch), (2) waits for the peer's matching acknowledgement, (3) gathers its boundary values and stores them straight into
+// the peer's ghost tail over NVLink, (4) publishes "epoch e complete" with a system-scope release and (5) waits for the
+// peer's data of the same epoch.  All waits are bounded (PEER_SPIN_LIMIT cycles) so that a lost rank cannot hang the GPU:
+// a timeout raises a flag that the host checks after the solve.
+constexpr long long PEER_SPIN_LIMIT = 40000000000ll;     // ~20 s at 2 GHz
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void peer_wait(const unsigned long long* flag, unsigned long long e, unsigned long long* err) {
+  const long long t0 = clock64();
+  while (ld_acquire_sys(flag) < e) {
+    if (clock64() - t0 > PEER_SPIN_LIMIT) {
+      *err = 1ull;
+      break;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(1024) peer_push_kernel(const PushPeer* __restrict__ peers, const int32_t* __restrict__ send_idx,
+                                                         const double* __restrict__ x, unsigned long long* __restrict__ epoch,
+                                                         int64_t count_override, unsigned long long* __restrict__ err) {
+  const PushPeer P = peers[blockIdx.x];
+  const unsigned long long e = epoch[blockIdx.x] + 1ull;
+  const int64_t count = count_override >= 0 ? count_override : P.send_count;
+  if (threadIdx.x == 0) {
+    st_release_sys(P.remote_flags, e);
+    peer_wait(P.local_flags, e, err);
+  }
+  __syncthreads();
+  for (int64_t k = threadIdx.x; k < count; k += blockDim.x) {
+    const int64_t sidx = P.send_begin + k;
+    P.remote_data[k] = x[send_idx ? (int64_t)send_idx[sidx] : sidx];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    st_release_sys(P.remote_flags + 1, e);
+    peer_wait(P.local_flags + 1, e, err);
+    epoch[blockIdx.x] = e;
+  }
+}
+
+// out[j] = sum over the ranks in rank order of their j-th partial (own partial read from buf): identical on every rank
+__global__ void peer_reduce_kernel(int n, int nranks, int me, const double* __restrict__ slots, double* __restrict__ buf) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  double s = 0.0;
+  for (int r = 0; r < nranks; ++r) s += r == me ? buf[j] : __ldcg(slots + (size_t)r * RED_MAX + j);
+  buf[j] = s;
+}
+
+int peer_push(knp_ctx* c, PeerLink& L, const int32_t* send_idx, const double* x, cudaStream_t st) {
+  if (L.np == 0) return KNP_OK;
+  const int threads = 1024;
+  peer_push_kernel<<<L.np, threads, 0, st>>>(L.peers.p, send_idx, x, L.epoch.p, -1, c->flag_arena.p);
+  KNP_LAUNCHED();
+  return KNP_OK;
+}
+
+static int ipc_open(knp_ctx* c, int rank, const char* handle64, void** out) {
+  std::string key((const char*)&rank, sizeof(int));
+  key.append(handle64, sizeof(cudaIpcMemHandle_t));
+  for (auto& e : c->ipc_open)
+    if (e.first == key) {
+      *out = e.second;
+      return KNP_OK;
+    }
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  void* p = nullptr;
+  KNP_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  c->ipc_open.push_back({key, p});
+  *out = p;
+  return KNP_OK;
+}
+
+constexpr int FLAG_SLOTS = 8192;       // pairs of counters in the flag arena; slot 0 word 0 is the timeout flag
+
+// Collective over ALL ranks (every rank calls it in the same order, also with an empty peer list).
+int peer_link_create(knp_ctx* c, const std::vector<int32_t>& peers, const std::vector<int64_t>& send_begin,
+                     const std::vector<int64_t>& send_count, void* target_base, const std::vector<int64_t>& target_offset,
+                     PeerLink& out) {
+  out.ready = false;
+  out.np = 0;
+  if (!c->peer_direct) return KNP_OK;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+  const int np = (int)peers.size(), R = c->nranks;
+  struct Msg {
+    char handle[64];
+    int64_t offset;
+    int32_t slot, pad;
+  };
+  std::vector<std::vector<char>> send(R), recv;
+  std::vector<int32_t> myslot(np);
+  if (np > 0) {
+    cudaIpcMemHandle_t h;
+    KNP_CUDA(cudaIpcGetMemHandle(&h, target_base));
+    for (int i = 0; i < np; ++i) {
+      KNP_CHECK(c->flag_slots_used < FLAG_SLOTS, "peer links: flag arena exhausted");
+      Msg m{};
+      memcpy(m.handle, &h, 64);
+      m.offset = target_offset[i];
+      m.slot = myslot[i] = c->flag_slots_used++;
+      send[peers[i]].resize(sizeof(Msg));
+      memcpy(send[peers[i]].data(), &m, sizeof(Msg));
+    }
+  }
+  NcclAmgComm comm(c);
+  KNP_TRY(comm.alltoallv(send, recv));
+  std::vector<PushPeer> pp(np);
+  for (int i = 0; i < np; ++i) {
+    const int q = peers[i];
+    KNP_CHECK(recv[q].size() == sizeof(Msg), "peer links: rank %d did not answer rank %d (asymmetric exchange pattern)", q, c->rank);
+    Msg m;
+    memcpy(&m, recv[q].data(), sizeof(Msg));
+    void* base = nullptr;
+    KNP_TRY(ipc_open(c, q, m.handle, &base));
+    pp[i].send_begin = send_begin[i];
+    pp[i].send_count = send_count[i];
+    pp[i].remote_data = reinterpret_cast<double*>(base) + m.offset;
+    pp[i].remote_flags = c->peer_flag_arena[q] + 2 * (size_t)m.slot;
+    pp[i].local_flags = c->flag_arena.p + 2 * (size_t)myslot[i];
+  }
+  if (np > 0) {
+    KNP_TRY(out.peers.upload(pp));
+    KNP_TRY(out.epoch.alloc(np));
+    KNP_CUDA(cudaMemset(out.epoch.p, 0, np * sizeof(unsigned long long)));
+  }
+  out.np = np;
+  out.ready = true;
+  return KNP_OK;
+}
+
+// flag arena + all-reduce slots + the main halo's link; decides collectively whether the direct path is usable
+static int peer_direct_init(knp_ctx* c) {
+  c->peer_direct = false;
+  const char* mode = getenv("KNP_HALO");
+  const bool want = !(mode && std::string(mode) == "nccl");
+  const int R = c->nranks;
+  NcclAmgComm comm(c);
+  // every rank exports its flag arena; a rank that cannot (or does not want to) sends an empty handle
+  std::vector<char> mine;
+  if (want && c->flag_arena.alloc(2 * (size_t)FLAG_SLOTS) == KNP_OK &&
+      cudaMemset(c->flag_arena.p, 0, 2 * (size_t)FLAG_SLOTS * sizeof(unsigned long long)) == cudaSuccess) {
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, c->flag_arena.p) == cudaSuccess) mine.assign((const char*)&h, (const char*)&h + 64);
+  }
+  cudaGetLastError();
+  std::vector<std::vector<char>> all;
+  KNP_TRY(comm.allgatherv(mine, all));
+  double ok = 1.0;
+  c->peer_flag_arena.assign(R, nullptr);
+  for (int r = 0; r < R && ok > 0.0; ++r) {
+    if (all[r].size() != 64) {
+      ok = 0.0;
+      break;
+    }
+    if (r == c->rank) {
+      c->peer_flag_arena[r] = c->flag_arena.p;
+      continue;
+    }
+    void* p = nullptr;
+    if (ipc_open(c, r, all[r].data(), &p) != KNP_OK) {
+      ok = 0.0;
+      cudaGetLastError();
+      break;
+    }
+    c->peer_flag_arena[r] = reinterpret_cast<unsigned long long*>(p);
+  }
+  double agree[1] = {ok};
+  KNP_TRY(comm.allreduce(agree, 1, false));
+  if (agree[0] < (double)R - 0.5) {
+    if (want && c->rank == 0) fprintf(stderr, "libknpemi_b200: CUDA IPC peer mapping unavailable, halo exchanges use NCCL point-to-point\n");
+    return KNP_OK;
+  }
+  c->peer_direct = true;
+  c->flag_slots_used = 1;            // slot 0 holds the timeout flag
+  // main halo: the peers push into this rank's receive buffer (second half of d_send_buf)
+  {
+    const int np = (int)c->peers.size();
+    const int64_t ns = c->send_ptr.empty() ? 0 : c->send_ptr[np];
+    std::vector<int64_t> sb(np), sc(np), off(np);
+    for (int i = 0; i < np; ++i) {
+      sb[i] = c->send_ptr[i];
+      sc[i] = c->send_ptr[i + 1] - c->send_ptr[i];
+      off[i] = ns + c->recv_ptr[i];
+    }
+    KNP_TRY(peer_link_create(c, c->peers, sb, sc, c->d_send_buf.p, off, c->main_link));
+  }
+  // all-reduce: every rank owns nranks x RED_MAX slots; rank r writes its partial sums into slot r of every peer
+  {
+    KNP_TRY(c->red_slots.alloc((size_t)R * RED_MAX));
+    KNP_CUDA(cudaMemset(c->red_slots.p, 0, (size_t)R * RED_MAX * sizeof(double)));
+    std::vector<int32_t> peers;
+    std::vector<int64_t> sb, sc, off;
+    for (int r = 0; r < R; ++r)
+      if (r != c->rank) {
+        peers.push_back(r);
+        sb.push_back(0);
+        sc.push_back(RED_MAX);
+        off.push_back((int64_t)r * RED_MAX);            // where rank r writes into MY array: slot r
+      }
+    KNP_TRY(peer_link_create(c, peers, sb, sc, c->red_slots.p, off, c->red_link));
+  }
+  return KNP_OK;
+}
+
+int peer_error_check(knp_ctx* c) {
+  if (!c->peer_direct) return KNP_OK;
+  unsigned long long flag = 0;
+  KNP_CUDA(cudaMemcpy(&flag, c->flag_arena.p, sizeof(flag), cudaMemcpyDeviceToHost));
+  if (flag) {
+    set_error("a peer-memory exchange timed out: a rank of the job stopped participating");
+    return KNP_E_NCCL;
+  }
+  return KNP_OK;
+}
+
 // Ghost exchange of a vector laid out [owned | ghosts grouped by peer in the order the peer packs them] (the layout of
 // every level of the row-distributed hierarchies): one pack kernel, then grouped ncclSend / ncclRecv where every receive
 // lands IN PLACE in the ghost tail -- no unpack pass.
 int halo_exchange_inplace(knp_ctx* c, HaloDev& H, double* x, cudaStream_t st) {
   if (c->nranks <= 1 || H.peers.empty()) return KNP_OK;
+  if (H.link.ready && x == H.link_x) return peer_push(c, H.link, H.send_idx.p, x, st);
   NcclApi* api = nccl_api();
   if (!api) return KNP_E_NCCL;
   const int np = (int)H.peers.size();
@@ -231,6 +470,14 @@ int p2p_exchange(knp_ctx* c, const std::vector<P2POp>& ops, cudaStream_t st) {
 
 int allreduce_sum(knp_ctx* c, double* buf, int n, cudaStream_t st) {
   if (c->nranks <= 1) return KNP_OK;
+  if (c->red_link.ready && n <= RED_MAX) {
+    // every rank stores its partial sums into its slot on every peer, then sums the slots in rank order
+    peer_push_kernel<<<c->red_link.np, 64, 0, st>>>(c->red_link.peers.p, nullptr, buf, c->red_link.epoch.p, n, c->flag_arena.p);
+    KNP_LAUNCHED();
+    peer_reduce_kernel<<<1, 64, 0, st>>>(n, c->nranks, c->rank, c->red_slots.p, buf);
+    KNP_LAUNCHED();
+    return KNP_OK;
+  }
   NcclApi* api = nccl_api();
   if (!api) return KNP_E_NCCL;
   KNP_NCCL(api->AllReduce(buf, buf, (size_t)n, ncclFloat64, ncclSum, c->comm, st));
@@ -292,8 +539,10 @@ int knp_dist_init(knp_ctx* c, int32_t rank, int32_t nranks, const char* unique_i
   c->h_send_cols.assign(send_cols, send_cols + ns);
   KNP_TRY(c->d_send_cols.upload(cols));
   KNP_TRY(c->d_send_buf.alloc((size_t)(ns + nr) + 1));
-  return KNP_OK;
+  return peer_direct_init(c);
 }
+
+int knp_peer_direct(const knp_ctx* c) { return c && c->peer_direct ? 1 : 0; }
 
 int knp_halo_exchange(knp_ctx* c, double* x_dev, void* stream) {
   KNP_CHECK(c, "context is NULL");

@@ -67,7 +67,7 @@ SYMBOLS = [
     "knp_assemble_P", "knp_values_dev", "knp_spmv", "knp_pc_setup", "knp_pc_apply", "knp_pc_bytes", "knp_solve", "knp_step",
     "knp_step_host", "knp_set_time", "knp_get_time", "knp_l2_norm_sq", "knp_integral", "knp_membrane_area", "knp_stimulus_current", "knp_last_timings", "knp_amg_num_levels", "knp_amg_part_levels", "knp_amg_setup_host", "knp_amg_host_level", "knp_pattern_host", "knp_rowblocks_host",
     "knp_amg_dist_sim_host", "knp_amg_dist_sim_level", "knp_amg_dist_sim_perm",
-    "knp_copy", "knp_amg_level_sizes", "knp_amg_level_host", "knp_nccl_unique_id", "knp_dist_init", "knp_halo_exchange",
+    "knp_copy", "knp_amg_level_sizes", "knp_amg_level_host", "knp_nccl_unique_id", "knp_dist_init", "knp_halo_exchange", "knp_peer_direct",
     "knp_allreduce_sum",
 ]
 
@@ -138,6 +138,7 @@ def load():
     lib.knp_nccl_unique_id.argtypes = [C.c_char_p]
     lib.knp_dist_init.argtypes = [vp, C.c_int32, C.c_int32, C.c_char_p, C.c_int64, C.c_int32, vp, vp, vp, vp, vp]
     lib.knp_halo_exchange.argtypes = [vp, vp, vp]
+    lib.knp_peer_direct.argtypes = [vp]
     lib.knp_allreduce_sum.argtypes = [vp, vp, C.c_int32, vp]
     _lib = lib
     return lib
@@ -415,6 +416,9 @@ class Context:
         recv_cols = np.ascontiguousarray(recv_cols, np.int32)
         check(self._lib.knp_dist_init(self.h, rank, nranks, unique_id, int(n_phi_global), peers.size, _ptr(peers),
                                       _ptr(send_ptr), _ptr(send_cols), _ptr(recv_ptr), _ptr(recv_cols)))
+
+    def peer_direct(self):
+        return bool(self._lib.knp_peer_direct(self.h))
 
     def halo_exchange(self, x_ptr=None, stream=None):
         check(self._lib.knp_halo_exchange(self.h, x_ptr, stream))

@@ -39,7 +39,8 @@ if p.comm.rank == 0:
     scale = list(ref)
     scale[7] = max(ref[7], ref[3])
     err = max(abs(a - b) / sc for a, b, sc in zip(norms, ref, scale))
-    print(f"ranks {p.comm.size} iterations {s.iterations} max rel norm err {err:.3e}", flush=True)
+    print(f"ranks {p.comm.size} iterations {s.iterations} max rel norm err {err:.3e} transport "
+          f"{'peer' if s.ctx.peer_direct() else 'nccl'}", flush=True)
     assert err < 1e-8, (norms, ref)
     print("MULTI_GPU_OK", flush=True)
 dist.destroy_process_group()

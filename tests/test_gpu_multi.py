@@ -21,14 +21,20 @@ def _torchrun(script, args, port, env_extra=None, nproc=2):
                           capture_output=True, text=True, env=env, timeout=900)
 
 
-@pytest.mark.parametrize("repl", ["default", "300"])
-def test_two_gpu_time_loop_matches_oracle(repl):
+@pytest.mark.parametrize("repl,transport", [("default", "peer"), ("300", "peer"), ("300", "nccl")])
+def test_two_gpu_time_loop_matches_oracle(repl, transport):
+    """transport: "peer" = halo exchanges / all-reduces as our own kernels over NVLink peer memory (CUDA IPC, the default),
+    "nccl" = grouped ncclSend / ncclRecv + ncclAllReduce (KNP_HALO=nccl)."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     worker = os.path.join(os.path.dirname(__file__), "dist_gpu_worker.py")
-    r = _torchrun(worker, [], 29531, {} if repl == "default" else {"KNP_AMG_REPL": repl})
+    env = {} if repl == "default" else {"KNP_AMG_REPL": repl}
+    if transport == "nccl":
+        env["KNP_HALO"] = "nccl"
+    r = _torchrun(worker, [], 29531, env)
     assert r.returncode == 0 and "MULTI_GPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+    assert ("transport peer" in r.stdout) == (transport == "peer"), r.stdout[-2000:]
 
 
 @pytest.mark.parametrize("repl", ["default", "2000"])
