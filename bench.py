@@ -31,6 +31,7 @@ WORKLOADS = {
     # name: (config file, N in the file, cells_per_dim in the file, gdim, models)
     "c3": ("c3_square2048_cells64.yaml", 2048, 8, 2, ("NeuronalCT", "HH", "ATP")),
     "c4": ("c4_cube120_cells64_passive.yaml", 120, 4, 3, ("Passive",)),
+    "c5": ("c5_cube256_tissue512_hh.yaml", 256, 8, 3, ("NeuronalCT", "HH", "ATP")),
 }
 
 
@@ -39,7 +40,7 @@ def workload_yaml(kb, workload, n, cells_per_dim=None, rtol=None):
     m = cells_per_dim or m0
     txt = open(os.path.join(os.path.dirname(kb.__file__), "configs", fname)).read()
     txt = txt.replace(f"N: {n0}", f"N: {n}").replace(f"cells_per_dim: {m0}", f"cells_per_dim: {m}")
-    txt = txt.replace("!range [2, 66]", f"!range [2, {2 + m ** gdim}]")
+    txt = txt.replace(f"!range [2, {2 + m0 ** gdim}]", f"!range [2, {2 + m ** gdim}]")
     if rtol is not None:
         txt = txt.replace("ksp_rtol: 1.0e-9", f"ksp_rtol: {rtol:.1e}")
     f = tempfile.NamedTemporaryFile("w", suffix=".yaml", delete=False)
@@ -148,33 +149,42 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------- CPU arm
 def cpu_workload(workload, n, restart=30):
     """The C++/OpenMP CPU baseline (oracle/cpu.py -> oracle/libknpemi_cpu.so: restatement of the reference's time-loop body
-    with the same GMRES + Schur/SA-AMG algorithm, all host cores) set up on the FULL workload: same generator, same initial
-    state, same models as the GPU arm.  Returns (baseline, description)."""
+    with the same GMRES + Schur/SA-AMG algorithm, all host cores) set up on the FULL workload through the same config file,
+    mesh generator, initial state and model list as the GPU arm (the host mirror of the reference classes parses the YAML;
+    no device context is created).  Returns (baseline, description)."""
     import cgx_b200 as kb
     from oracle.cpu import CpuBaseline
     from oracle.knpemi import OracleParams
-    _, _, m, gdim, model_names = WORKLOADS[workload]
-    mesh = kb.mesh.cell_array_mesh(gdim, n, m)
-    it = tuple(mesh.intra_tags)
-    p = OracleParams(intra_tags=it, extra_tag=1, membrane_tags=it, stimulus_tags=(2,) if workload == "c3" else it)
+    _, _, _, gdim, model_names = WORKLOADS[workload]
+    cfg = workload_yaml(kb, workload, n)
+    pr = kb.ProblemKNPEMI(cfg, verbose=False)
+    os.unlink(cfg)
+    pr.set_initial_conditions()
+    ctor = {"NeuronalCT": kb.NeuronalCotransporters, "HH": kb.HodgkinHuxley, "ATP": kb.ATPPump, "Passive": kb.PassiveModel}
+    pr.init_ionic_models([ctor[nm](pr) for nm in model_names])
+    mesh = pr.mesh
+    region = None
+    if pr.stimulus_region:
+        region = (int(pr.stimulus_region_direction), float(pr.stimulus_region_range[0]), float(pr.stimulus_region_range[1]))
+    ions = pr.ion_list
+    p = OracleParams(dt=float(pr.dt.value), T=pr.T.value, F=pr.F.value, R=pr.R.value, C_M=pr.C_M.value,
+                     z=tuple(i["z"].value for i in ions), D=tuple(i["Di"].value for i in ions), phi_rest=pr.phi_rest.value,
+                     g_Na_bar=pr.g_Na_bar.value, g_K_bar=pr.g_K_bar.value, g_leak=tuple(i["g_leak"].value for i in ions),
+                     g_leak_g=tuple(i["g_leak_g"].value for i in ions), g_syn_bar=pr.g_syn_bar.value, a_syn=pr.a_syn.value,
+                     T_stim=pr.T_stim.value, scale_stimulus=bool(pr.scale_stimulus), intra_tags=tuple(pr.intra_tags),
+                     extra_tag=pr.extra_tag[0], membrane_tags=tuple(pr.gamma_tags), stimulus_tags=tuple(pr.stimulus_tags),
+                     stimulus_region=region, c_e_init=tuple(i["ke_init"].value for i in ions))
     qb, qw = kb.mesh.facet_quadrature(gdim)
     # CSR pattern and dof maps of the contract layout from the host-only builder (no GPU involved)
-    pat = kb.lib.pattern_host(gdim, mesh.x, mesh.cells, mesh.cell_tags, it, 1, mesh.mf_verts, mesh.mf_tags, qb, qw)
+    pat = kb.lib.pattern_host(gdim, mesh.x, mesh.cells, mesh.cell_tags, p.intra_tags, p.extra_tag, mesh.mf_verts, mesh.mf_tags, qb, qw)
     cb = CpuBaseline(gdim, mesh.x, mesh.cells, mesh.cell_tags, mesh.mf_verts, mesh.mf_tags, p, [(nm, None) for nm in model_names],
                      pat, restart=restart)
-    # initial state of configs/c3_*.yaml / c4_*.yaml (initial_conditions + initial_perturbation), packed like the oracle
-    nv = mesh.x.shape[0]
-    ci = np.array(p.c_i_init)[:, None] * np.ones(nv)
-    ce = np.array(p.c_e_init)[:, None] * np.ones(nv)
-    phi_i = np.full(nv, p.phi_m_init)
-    if workload == "c3":
-        X = mesh.x / 1e-6
-        fac = 1 + 0.01 * np.sin(2 * np.pi * X[:, 0]) * np.sin(2 * np.pi * X[:, 1])
-        ci, ce = ci * fac, ce * fac
-        phi_i = phi_i + 0.005 * np.cos(2 * np.pi * X[:, 0])
     vi, ve = pat[2], pat[3]
-    u = np.concatenate([ci[0][vi], ci[1][vi], ci[2][vi], phi_i[vi], ce[0][ve], ce[1][ve], ce[2][ve], np.zeros(ve.size)])
-    gates = np.array([p.n_init, p.m_init, p.h_init])[:, None] * np.ones(cb.n_mv)
+    u = np.concatenate([pr.wh[0][f]._data[vi] for f in range(4)] + [pr.wh[1][f]._data[ve] for f in range(4)])
+    if pr.gating_variables:
+        gates = np.stack([pr.n._data[cb.mverts], pr.m._data[cb.mverts], pr.h._data[cb.mverts]])
+    else:
+        gates = np.zeros((3, cb.n_mv))
     cb.set_state(u, gates)
     return cb, dict(rows=cb.n, nnz=cb.nnz, cells=int(mesh.cells.shape[0]))
 
@@ -231,7 +241,9 @@ def run_reference(args):
 
 def workload_name(wl, n, n_cells):
     return {"c3": f"BASELINE C3: synthetic 2D tissue block N={n} (8x8 cells), Na/K/Cl + HH+ATP+KCC2",
-            "c4": f"BASELINE C4: synthetic 3D tissue block N={n} (4x4x4 cells, {n_cells} tetrahedra), Na/K/Cl + passive membrane"}[wl]
+            "c4": f"BASELINE C4: synthetic 3D tissue block N={n} (4x4x4 cells, {n_cells} tetrahedra), Na/K/Cl + passive membrane",
+            "c5": f"BASELINE C5: synthetic dense-tissue-like 3D mesh N={n} (8x8x8 plate-stack cells, {n_cells} tetrahedra), "
+                  f"Na/K/Cl + HH+ATP+KCC2, stimulus region"}[wl]
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
@@ -416,7 +428,7 @@ def run_ours(args):
                 "ms_per_step": ms, "higher_is_better": False, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
                 "config": {"workload": names[wl] + f", GMRES({args.restart}) + charge-conservation Schur PC (SA-AMG blocks) rtol 1e-9"
-                                       + (", ICs perturbed as SURVEY 8(d)" if wl == "c3" else ""),
+                                       + (", ICs perturbed as SURVEY 8(d)" if wl != "c4" else ""),
                            "dofs": dofs_global, "nnz": nnz_global, "cells": n_cells_global,
                            "iterations_per_step": its, "timed_step_indices": [args.warmup + 1, args.warmup + args.steps],
                            "l2_policy": "inputs (A: %.1f GB per GPU) larger than L2" % (12 * nnz_global / world / 1e9),
@@ -462,7 +474,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS),
-                    help="headline workload: c3 = BASELINE configs[2] (weak-scaled per GPU), c4 = configs[3] (strong)")
+                    help="headline workload: c3 = BASELINE configs[2] (weak-scaled per GPU), c4 = configs[3] (strong), "
+                         "c5 = configs[4] (strong, sized for 8 GPUs)")
     ap.add_argument("--size", type=int, default=0, help="grid squares per side (default: the BASELINE size of the workload)")
     ap.add_argument("--c4-size", type=int, default=120, help="N of the C4 section reported beside the headline")
     ap.add_argument("--skip-c4", action="store_true")

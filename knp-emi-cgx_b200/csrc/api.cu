@@ -295,6 +295,8 @@ int knp_set_params(knp_ctx* c, const knp_params* p, int32_t n_tags, const knp_ta
   P.psi = p->R * p->T / p->F;
   P.n_tags = (int)c->H.mtags.size();
   P.any_hh = false;
+  P.tag_models.clear();
+  P.tag_stim.clear();
   std::vector<uint32_t> tm(P.n_tags > 0 ? P.n_tags : 1, 0u);
   std::vector<int32_t> ts(P.n_tags > 0 ? P.n_tags : 1, 0);
   for (int i = 0; i < P.n_tags; ++i) {
@@ -307,8 +309,8 @@ int knp_set_params(knp_ctx* c, const knp_params* p, int32_t n_tags, const knp_ta
       }
     KNP_CHECK(found, "membrane tag %d present in the mesh has no ionic model (Mismatch between membrane tags and ionic models tags)",
               c->H.mtags[i]);
-    P.tag_models[i] = tm[i];
-    P.tag_stim[i] = ts[i];
+    P.tag_models.push_back(tm[i]);
+    P.tag_stim.push_back(ts[i]);
     if (tm[i] & KNP_MODEL_HH) P.any_hh = true;
   }
   for (int j = 0; j < n_tags; ++j)

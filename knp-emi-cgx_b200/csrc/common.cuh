@@ -154,8 +154,8 @@ struct Params {
   double psi;
   double stim_area;
   int n_tags;
-  uint32_t tag_models[256];
-  int tag_stim[256];
+  std::vector<uint32_t> tag_models;   // per membrane tag present on this rank (index = position in HostTopo::mtags)
+  std::vector<int> tag_stim;
   bool any_hh;
 };
 

@@ -238,7 +238,6 @@ int build_topology(const knp_mesh_desc* m, HostTopo& T) {
   T.mtags.assign(m->mfacet_tags, m->mfacet_tags + NF);
   std::sort(T.mtags.begin(), T.mtags.end());
   T.mtags.erase(std::unique(T.mtags.begin(), T.mtags.end()), T.mtags.end());
-  KNP_CHECK(T.mtags.size() <= 256, "more than 256 distinct membrane tags on one rank are not supported yet");
   T.mf_tagidx.resize(NF);
   T.mf_owned.resize(NF);
   T.mf_area.resize(NF);

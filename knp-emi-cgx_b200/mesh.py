@@ -148,25 +148,44 @@ def unit_cube_fixture(n=8, scale=1e-6):
     return Mesh(3, x * scale, cells, tags, (1,), 2, fv, ft, grid=(n, n, n))
 
 
-def cell_array_mesh(gdim, n, m, scale=1e-6, fill=0.5, first_tag=2, extra_tag=1):
-    """Synthetic tissue block (BASELINE configs C3/C4): an m^gdim array of square/cubic biological cells.
-    Cell (p,q[,r]) occupies the middle `fill` fraction of its n/m-wide block; intracellular tags
-    first_tag..first_tag+m^gdim-1, extracellular tag `extra_tag`, membrane tag = intracellular tag."""
-    assert n % m == 0
-    bs = n // m
+def _inside(offs, bs, fill, shape):
+    """Which grid squares / cubes of an n/m-wide block belong to its biological cell.  offs: per axis (x, y[, z]) the offset
+    of the square inside its block, broadcastable against each other.
+      shape None          : the middle `fill` fraction of the block, a square / cube (BASELINE C3 / C4)
+      shape {"plates": ..}: dense-tissue-like (BASELINE C5): inside the same middle region the cell is a stack of thin plates
+                            normal to the last axis (`thickness` grid units thick, one every `pitch`) joined by a spine of
+                            `spine` units along the first axis -- membrane facets / cells >= 0.2 and membrane vertices /
+                            vertices >= 0.5 for thickness 1, pitch 2 (real tissue: 0.30 / 0.88)."""
     lo = int(round(bs * (1 - fill) / 2))
     hi = bs - lo
+    box = None
+    for o in offs:
+        a = (o >= lo) & (o < hi)
+        box = a if box is None else box & a
+    if not shape:
+        return box
+    t, pitch, spine = int(shape.get("thickness", 1)), int(shape.get("pitch", 2)), int(shape.get("spine", 1))
+    plate = ((offs[-1] - lo) % pitch) < t
+    return box & (plate | ((offs[0] - lo) < spine))
+
+
+def cell_array_mesh(gdim, n, m, scale=1e-6, fill=0.5, first_tag=2, extra_tag=1, shape=None):
+    """Synthetic tissue block (BASELINE configs C3/C4/C5): an m^gdim array of biological cells.
+    Cell (p,q[,r]) occupies the middle `fill` fraction of its n/m-wide block (as a square / cube, or as a stack of thin
+    plates: see _inside); intracellular tags first_tag..first_tag+m^gdim-1, extracellular tag `extra_tag`, membrane tag =
+    intracellular tag."""
+    assert n % m == 0
+    bs = n // m
     idx = np.arange(n)
     blk, off = idx // bs, idx % bs
-    ins = (off >= lo) & (off < hi)
     if gdim == 2:
-        IN = ins[None, :] & ins[:, None]                       # [iy, ix]
+        IN = _inside([off[None, :], off[:, None]], bs, fill, shape)      # [iy, ix]
         tag = first_tag + blk[:, None] * m + blk[None, :]      # q*m + p
         gt = np.where(IN, tag, extra_tag).ravel()
         cells = _square_cells(n)
         tags = np.repeat(gt, 2).astype(np.int32)
     else:
-        IN = ins[:, None, None] & ins[None, :, None] & ins[None, None, :]   # [iz, iy, ix]
+        IN = _inside([off[None, None, :], off[None, :, None], off[:, None, None]], bs, fill, shape)   # [iz, iy, ix]
         tag = first_tag + (blk[:, None, None] * m + blk[None, :, None]) * m + blk[None, None, :]
         gt = np.where(IN, tag, extra_tag).ravel()
         cells = _cube_cells(n)
@@ -223,7 +242,7 @@ class BlockOwner:
         return rank.astype(np.int32)
 
 
-def cell_array_mesh_local(gdim, n, m, rank, size, scale=1e-6, fill=0.5, first_tag=2, extra_tag=1):
+def cell_array_mesh_local(gdim, n, m, rank, size, scale=1e-6, fill=0.5, first_tag=2, extra_tag=1, shape=None):
     """This rank's part of cell_array_mesh(gdim, n, m, ...) under the block partition, generated WITHOUT building the global
     mesh: owned vertices first (ascending global id), then ghosts; every cell / membrane facet touching an owned vertex;
     ownership flags for functionals -- the same local mesh partition.partition_mesh(global mesh, owner=BlockOwner) returns.
@@ -235,16 +254,14 @@ def cell_array_mesh_local(gdim, n, m, rank, size, scale=1e-6, fill=0.5, first_ta
     rng = [np.arange(max(lo[a] - 1, 0), min(hi[a], n), dtype=np.int64) for a in range(gdim)]
     mv = n + 1
     bs = n // m
-    lo_in = int(round(bs * (1 - fill) / 2))
-    hi_in = bs - lo_in
-    ins = [((r % bs) >= lo_in) & ((r % bs) < hi_in) for r in rng]
+    off = [r % bs for r in rng]
     blk = [r // bs for r in rng]
     if gdim == 2:
         IY, IX = np.meshgrid(rng[1], rng[0], indexing="ij")
         v0 = (IY * mv + IX).ravel()
         v1, v2, v3 = v0 + 1, v0 + mv, v0 + mv + 1
         cells = np.stack([np.stack([v0, v1, v3], 1), np.stack([v0, v2, v3], 1)], 1).reshape(-1, 3)
-        IN = ins[1][:, None] & ins[0][None, :]
+        IN = _inside([off[0][None, :], off[1][:, None]], bs, fill, shape)
         tag = first_tag + blk[1][:, None] * m + blk[0][None, :]
         tags = np.repeat(np.where(IN, tag, extra_tag).ravel(), 2)
     else:
@@ -254,7 +271,7 @@ def cell_array_mesh_local(gdim, n, m, rank, size, scale=1e-6, fill=0.5, first_ta
         v4, v5, v6, v7 = v0 + mv * mv, v1 + mv * mv, v2 + mv * mv, v3 + mv * mv
         tets = [(v0, v1, v3, v7), (v0, v1, v7, v5), (v0, v5, v7, v4), (v0, v3, v2, v7), (v0, v6, v4, v7), (v0, v2, v6, v7)]
         cells = np.stack([np.stack(t, 1) for t in tets], 1).reshape(-1, 4)
-        IN = ins[2][:, None, None] & ins[1][None, :, None] & ins[0][None, None, :]
+        IN = _inside([off[0][None, None, :], off[1][None, :, None], off[2][:, None, None]], bs, fill, shape)
         tag = first_tag + (blk[2][:, None, None] * m + blk[1][None, :, None]) * m + blk[0][None, None, :]
         tags = np.repeat(np.where(IN, tag, extra_tag).ravel(), 6)
     cell_owner = own(cells)
@@ -307,5 +324,5 @@ def from_descriptor(desc, scale):
     if kind == "cell_array":
         return cell_array_mesh(int(desc.get("dim", 2)), n, int(desc.get("cells_per_dim", 8)), scale,
                                float(desc.get("fill", 0.5)), int(desc.get("first_tag", 2)),
-                               int(desc.get("extra_tag", 1)))
+                               int(desc.get("extra_tag", 1)), desc.get("shape"))
     raise ValueError(f"unknown synthetic_mesh kind {kind!r}")

@@ -302,7 +302,7 @@ class ProblemKNPEMI:
             gdim, n = int(sm.get("dim", 2)), int(sm.get("N", 32))
             m, local_info = _mesh.cell_array_mesh_local(gdim, n, int(sm.get("cells_per_dim", 8)), self.comm.rank, self.comm.size,
                                                         self.mesh_conversion_factor, float(sm.get("fill", 0.5)),
-                                                        int(sm.get("first_tag", 2)), int(sm.get("extra_tag", 1)))
+                                                        int(sm.get("first_tag", 2)), int(sm.get("extra_tag", 1)), sm.get("shape"))
             self.global_mesh_info = dict(n_vertices=(n + 1) ** gdim, n_cells=(2 if gdim == 2 else 6) * n ** gdim)
         elif sm is not None:
             m = _mesh.from_descriptor(self.synthetic_mesh, self.mesh_conversion_factor)

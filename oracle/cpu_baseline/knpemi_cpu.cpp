@@ -83,9 +83,12 @@ struct Ctx {
   std::string err;
 };
 
+// loops over small levels stay serial: a parallel region costs more than the loop (and far more when the host is shared)
+constexpr int PAR_MIN = 20000;
+
 inline void spmv(const CsrHost& M, const double* x, double* y) {
   const int n = M.n_rows;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (n > PAR_MIN)
   for (int i = 0; i < n; ++i) {
     double s = 0.0;
     for (int j = M.indptr[i]; j < M.indptr[i + 1]; ++j) s += M.vals[j] * x[M.indices[j]];
@@ -447,7 +450,7 @@ void cycle(Amg& M, int l, const double* b, double* xout) {
   const int nl = (int)M.lv.size();
   if (l == nl) {
     const int n = M.nc;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if ((size_t)n * n > 400000)
     for (int i = 0; i < n; ++i) {
       double s = 0.0;
       for (int j = 0; j < n; ++j) s += M.cinv[(size_t)i * n + j] * b[j];
@@ -459,12 +462,12 @@ void cycle(Amg& M, int l, const double* b, double* xout) {
   const int n = L.A.n_rows;
   const double w = (4.0 / 3.0) / L.rho;
   double* x = L.x.data();
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (n > PAR_MIN)
   for (int i = 0; i < n; ++i) x[i] = w * L.dinv[i] * b[i];
   const int reps = (l >= 1 && l <= M.gamma_last) ? M.gamma : 1;
   for (int rep = 0; rep < reps; ++rep) {
     double* r = L.r.data();
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (n > PAR_MIN)
     for (int i = 0; i < n; ++i) {
       double s = 0.0;
       for (int j = L.A.indptr[i]; j < L.A.indptr[i + 1]; ++j) s += L.A.vals[j] * x[L.A.indices[j]];
@@ -475,14 +478,14 @@ void cycle(Amg& M, int l, const double* b, double* xout) {
     cycle(M, l + 1, bc, r);               // the child's result lands in this level's r (free after the restriction)
     const int ncoarse = L.P.n_cols;
     (void)ncoarse;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (n > PAR_MIN)
     for (int i = 0; i < n; ++i) {
       double s = 0.0;
       for (int j = L.P.indptr[i]; j < L.P.indptr[i + 1]; ++j) s += L.P.vals[j] * r[L.P.indices[j]];
       x[i] += s;
     }
   }
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (n > PAR_MIN)
   for (int i = 0; i < n; ++i) {
     double s = 0.0;
     for (int j = L.A.indptr[i]; j < L.A.indptr[i + 1]; ++j) s += L.A.vals[j] * x[L.A.indices[j]];

@@ -158,18 +158,22 @@ def test_native_local_patterns_tile_the_global_pattern(kb, gdim, n, m, size):
     assert seen.all()
 
 
-@pytest.mark.parametrize("gdim,n,m,size", [(2, 24, 3, 2), (2, 24, 3, 4), (2, 32, 2, 8), (3, 8, 2, 2), (3, 12, 2, 8), (3, 8, 2, 6)])
-def test_local_slab_generator_equals_partition_of_the_global_mesh(kb, gdim, n, m, size):
+PLATES = {"plates": True, "thickness": 1, "pitch": 2, "spine": 1}
+
+
+@pytest.mark.parametrize("gdim,n,m,size,shape", [(2, 24, 3, 2, None), (2, 24, 3, 4, None), (2, 32, 2, 8, None), (3, 8, 2, 2, None),
+                                                 (3, 12, 2, 8, None), (3, 8, 2, 6, None), (3, 16, 2, 8, PLATES), (2, 32, 2, 4, PLATES)])
+def test_local_slab_generator_equals_partition_of_the_global_mesh(kb, gdim, n, m, size, shape):
     """Multi-GPU runs of the structured tissue blocks generate only their own slab (mesh.cell_array_mesh_local); it must be
     exactly the local mesh partition_mesh cuts out of the global mesh under the same (block) vertex -> rank map."""
     part = __import__("importlib").import_module("knp-emi-cgx_b200.partition")
-    g = kb.mesh.cell_array_mesh(gdim, n, m)
+    g = kb.mesh.cell_array_mesh(gdim, n, m, fill=0.75 if shape else 0.5, shape=shape)
     own = kb.mesh.BlockOwner(gdim, n, size)
     owner = own(np.arange(g.x.shape[0]))
     assert np.bincount(owner, minlength=size).min() > 0
     for rank in range(size):
         a, ia = part.partition_mesh(g, rank, size, owner=owner)
-        b, ib = kb.mesh.cell_array_mesh_local(gdim, n, m, rank, size)
+        b, ib = kb.mesh.cell_array_mesh_local(gdim, n, m, rank, size, fill=0.75 if shape else 0.5, shape=shape)
         assert a.n_owned == b.n_owned and np.array_equal(ia["l2g"], ib["l2g"])
         assert np.allclose(a.x, b.x, rtol=0, atol=1e-22)
         assert np.array_equal(a.cells, b.cells) and np.array_equal(a.cell_tags, b.cell_tags)
@@ -178,3 +182,12 @@ def test_local_slab_generator_equals_partition_of_the_global_mesh(kb, gdim, n, m
         assert np.array_equal(a.mf_owned, b.mf_owned)
         gv = ia["l2g"]
         assert np.array_equal(ia["owner_of"](gv), ib["owner_of"](gv))
+
+
+def test_tissue_like_plates_meet_the_c5_statistics(kb):
+    """BASELINE C5: the plate-stack cells must give membrane facets / cells >= 0.2 and membrane
+    vertices / vertices >= 0.5 (real tissue: 0.30 / 0.88); checked on a reduced block array with the C5 block size 32."""
+    m = kb.mesh.cell_array_mesh(3, 64, 2, fill=0.875, shape=PLATES)
+    nv, nc, nf = m.x.shape[0], m.cells.shape[0], m.mf_verts.shape[0]
+    assert nf / nc >= 0.2, nf / nc
+    assert np.unique(m.mf_verts).size / nv >= 0.5, np.unique(m.mf_verts).size / nv
