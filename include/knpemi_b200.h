@@ -192,6 +192,12 @@ int knp_integral(knp_ctx* ctx, int32_t subdomain, int32_t field, int32_t power, 
 /* this rank's part of the total stimulus current int stim_expr dS(stimulus_tags) at time t from the current state
    (SolverKNPEMI.init_png_data / save_png, KNPEMIx_solver.py:578-610; stim_expr: KNPEMIx_ionic_model.py:517-603) */
 int knp_stimulus_current(knp_ctx* ctx, double t, double* out);
+/* Point probes (scifem.evaluate_function in SolverKNPEMI.init_data / save_data, KNPEMI/KNPEMIx_solver.py:612-643): n_out sparse
+   linear functionals out[i] = sum_{t in [ptr[i], ptr[i+1])} weights[t] * u[cols[t]] of the device state (columns in the
+   column layout; the host mirror locates the containing cell and the barycentric weights once).  knp_probe_eval evaluates them
+   on the device and copies the n_out values -- not the state -- to the host. */
+int knp_probe_setup(knp_ctx* ctx, int32_t n_out, const int32_t* ptr, const int32_t* cols, const double* weights);
+int knp_probe_eval(knp_ctx* ctx, double* out_host);
 /* this rank's area of the membrane facets tagged `tag` (assemble_scalar(1*dS(tag)), KNPEMIx_problem.py:833-834) */
 int knp_membrane_area(const knp_ctx* ctx, int32_t tag, double* out);
 /* per-phase device timers of the last knp_step (ms): gate, facet, rows, solve, total */

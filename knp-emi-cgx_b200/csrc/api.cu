@@ -569,6 +569,32 @@ int knp_stimulus_current(knp_ctx* c, double t, double* out) {
   return KNP_OK;
 }
 
+int knp_probe_setup(knp_ctx* c, int32_t n_out, const int32_t* ptr, const int32_t* cols, const double* weights) {
+  CTX_GUARD(c);
+  KNP_CHECK(n_out >= 0 && (n_out == 0 || (ptr && cols && weights)), "bad probe tables");
+  c->n_probe = 0;
+  if (n_out == 0) return KNP_OK;
+  const int nt = ptr[n_out];
+  for (int t = 0; t < nt; ++t) KNP_CHECK(cols[t] >= 0 && cols[t] < c->T.L.n_cols, "probe column %d out of range", cols[t]);
+  KNP_TRY(c->probe_ptr.upload(std::vector<int32_t>(ptr, ptr + n_out + 1)));
+  KNP_TRY(c->probe_col.upload(std::vector<int32_t>(cols, cols + nt)));
+  KNP_TRY(c->probe_w.upload(std::vector<double>(weights, weights + nt)));
+  KNP_TRY(c->probe_out.alloc(n_out));
+  c->n_probe = n_out;
+  return KNP_OK;
+}
+
+int knp_probe_eval(knp_ctx* c, double* out_host) {
+  CTX_GUARD(c);
+  KNP_CHECK(out_host || c->n_probe == 0, "NULL argument");
+  if (c->n_probe == 0) return KNP_OK;
+  cudaStream_t st = c->stream;
+  KNP_TRY(launch_probe(c->n_probe, c->probe_ptr.p, c->probe_col.p, c->probe_w.p, c->u.p, c->probe_out.p, st));
+  KNP_CUDA(cudaMemcpyAsync(out_host, c->probe_out.p, c->n_probe * sizeof(double), cudaMemcpyDeviceToHost, st));
+  KNP_CUDA(cudaStreamSynchronize(st));
+  return KNP_OK;
+}
+
 int knp_membrane_area(const knp_ctx* c, int32_t tag, double* out) {
   KNP_CHECK(c && out, "NULL argument");
   const HostTopo& H = c->H;

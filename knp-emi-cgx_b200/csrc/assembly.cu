@@ -678,6 +678,25 @@ __global__ void __launch_bounds__(ROWS_THREADS, ROWS_MIN_CTAS) rows_kernel(DevTo
   if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
+// ------------------------------------------------------------------------------------------------ point probes
+// out[i] = sum_{t in [ptr[i], ptr[i+1])} w[t] * u[col[t]]: point evaluation of P1 fields (scifem.evaluate_function in
+// SolverKNPEMI.init_data / save_data, KNPEMIx_solver.py:612-643) with the containing cell and the barycentric weights found
+// once on the host; one thread per output value, fixed summation order.
+__global__ void probe_kernel(int n_out, const int32_t* __restrict__ ptr, const int32_t* __restrict__ col,
+                             const double* __restrict__ w, const double* __restrict__ u, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_out) return;
+  double s = 0.0;
+  for (int t = ptr[i]; t < ptr[i + 1]; ++t) s += w[t] * u[col[t]];
+  out[i] = s;
+}
+int launch_probe(int n_out, const int32_t* ptr, const int32_t* col, const double* w, const double* u, double* out, cudaStream_t st) {
+  if (n_out == 0) return KNP_OK;
+  probe_kernel<<<(n_out + 127) / 128, 128, 0, st>>>(n_out, ptr, col, w, u, out);
+  KNP_LAUNCHED();
+  return KNP_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ CSR indices
 template <int MODE>
 __global__ void csr_indices_kernel(DevTopo T, int32_t* __restrict__ indices) {

@@ -132,6 +132,10 @@ struct knp_ctx {
   // timers
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   double last_ms[5] = {0, 0, 0, 0, 0};
+  // point probes: sparse linear functionals of the state (knp_probe_setup / knp_probe_eval)
+  knp::DevBuf<int32_t> probe_ptr, probe_col;
+  knp::DevBuf<double> probe_w, probe_out;
+  int n_probe = 0;
   // scratch for functionals
   knp::DevBuf<double> fpartial, fout;
   knp::DevBuf<int32_t> ftags;

@@ -30,6 +30,7 @@ int launch_l2_cells(int gdim, const Layout& L, int s, int field, int power, int 
                     const int32_t* tags, int n_tags, const double* u, double* partial, int n_partial,
                     cudaStream_t st);
 
+int launch_probe(int n_out, const int32_t* ptr, const int32_t* col, const double* w, const double* u, double* out, cudaStream_t st);
 int launch_stim_current(const DevTopo& T, const KParams& P, const int32_t* tag_stim, const int32_t* mf_owned,
                         const double* u, double stim_fac, double* partial, int n_partial, cudaStream_t st);
 

@@ -65,7 +65,7 @@ SYMBOLS = [
     "knp_csr_P_host", "knp_dofmap_host", "knp_mverts_host", "knp_set_params", "knp_stimulus_area_local",
     "knp_set_state", "knp_get_state", "knp_state_dev", "knp_phi_m_host", "knp_gate_step", "knp_assemble",
     "knp_assemble_P", "knp_values_dev", "knp_spmv", "knp_pc_setup", "knp_pc_apply", "knp_pc_bytes", "knp_solve", "knp_step",
-    "knp_step_host", "knp_set_time", "knp_get_time", "knp_l2_norm_sq", "knp_integral", "knp_membrane_area", "knp_stimulus_current", "knp_last_timings", "knp_amg_num_levels", "knp_amg_part_levels", "knp_amg_setup_host", "knp_amg_host_level", "knp_pattern_host", "knp_rowblocks_host",
+    "knp_step_host", "knp_set_time", "knp_get_time", "knp_l2_norm_sq", "knp_integral", "knp_membrane_area", "knp_probe_setup", "knp_probe_eval", "knp_stimulus_current", "knp_last_timings", "knp_amg_num_levels", "knp_amg_part_levels", "knp_amg_setup_host", "knp_amg_host_level", "knp_pattern_host", "knp_rowblocks_host",
     "knp_amg_dist_sim_host", "knp_amg_dist_sim_level", "knp_amg_dist_sim_perm",
     "knp_copy", "knp_amg_level_sizes", "knp_amg_level_host", "knp_nccl_unique_id", "knp_dist_init", "knp_halo_exchange", "knp_peer_direct",
     "knp_allreduce_sum",
@@ -121,6 +121,8 @@ def load():
     lib.knp_l2_norm_sq.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, vp, c_f64p]
     lib.knp_integral.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, c_f64p]
     lib.knp_membrane_area.argtypes = [vp, C.c_int32, c_f64p]
+    lib.knp_probe_setup.argtypes = [vp, C.c_int32, vp, vp, vp]
+    lib.knp_probe_eval.argtypes = [vp, vp]
     lib.knp_stimulus_current.argtypes = [vp, C.c_double, c_f64p]
     lib.knp_last_timings.argtypes = [vp, vp]
     lib.knp_copy.argtypes = [vp, vp, vp, C.c_int64, C.c_int32]
@@ -359,6 +361,17 @@ class Context:
         out = C.c_double()
         check(self._lib.knp_stimulus_current(self.h, float(t), C.byref(out)))
         return out.value
+
+    def probe_setup(self, ptr, cols, weights):
+        ptr, cols = np.ascontiguousarray(ptr, np.int32), np.ascontiguousarray(cols, np.int32)
+        weights = np.ascontiguousarray(weights, np.float64)
+        self._n_probe = ptr.size - 1
+        check(self._lib.knp_probe_setup(self.h, self._n_probe, _ptr(ptr), _ptr(cols), _ptr(weights)))
+
+    def probe_eval(self):
+        out = np.zeros(getattr(self, "_n_probe", 0))
+        check(self._lib.knp_probe_eval(self.h, _ptr(out)))
+        return out
 
     def membrane_area(self, tag):
         out = C.c_double()

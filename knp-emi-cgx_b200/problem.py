@@ -202,8 +202,18 @@ class ProblemKNPEMI:
         if "ion_species" in config:
             raise NotImplementedError("custom ion_species tables are not supported by the B200 path yet (Na/K/Cl only)")
         self.source_terms = config.get("source_terms")
-        self.point_evaluation = "point_evaluation" in config
+        # point probes (mixed_dim_problem.py:278-288)
         self.gamma_points = None
+        if "point_evaluation" in config:
+            self.point_evaluation = True
+            pe = config["point_evaluation"]
+            scale = float(config.get("mesh_conversion_factor", self.mesh_conversion_factor))
+            self.ics_points = np.atleast_2d(np.array(pe["ics_points"], float)) * scale
+            self.ecs_points = np.atleast_2d(np.array(pe["ecs_points"], float)) * scale
+            if "gamma_points" in pe:
+                self.gamma_points = np.atleast_2d(np.array(pe["gamma_points"], float)) * scale
+        else:
+            self.point_evaluation = False
         if "stimulus" in config:
             try:
                 g_dict = config["stimulus"]["conductance"]
@@ -530,7 +540,104 @@ class ProblemKNPEMI:
             init_halo(self, ctx)
         self._upload_params()
         self._push_state()
+        if self.point_evaluation:
+            self._setup_probes()
         self.a = self.L = "device-resident forms (csrc/assembly.cu)"
+
+    # ------------------------------------------------------------------ point probes
+    def _locate(self, point, cells):
+        """Index into `cells` of the first cell containing `point` and its barycentric coordinates, or (None, None)."""
+        m = self.mesh
+        d = m.gdim
+        xc = m.x[cells]                                                    # (nc, d+1, d)
+        tol = 1e-9 * float(np.abs(m.x).max())
+        cand = np.flatnonzero(np.all(xc.min(1) <= point + tol, axis=1) & np.all(xc.max(1) >= point - tol, axis=1))
+        if cand.size == 0:
+            return None, None
+        T = np.transpose(xc[cand, 1:] - xc[cand, :1], (0, 2, 1))           # columns = edge vectors
+        lam = np.linalg.solve(T, (point - xc[cand, 0])[:, :, None])[:, :, 0]
+        bary = np.concatenate([1.0 - lam.sum(1, keepdims=True), lam], 1)
+        ok = np.flatnonzero(np.all(bary >= -1e-9, axis=1))
+        if ok.size == 0:
+            return None, None
+        return int(cand[ok[0]]), bary[ok[0]]
+
+    def _setup_probes(self):
+        """Containing cells and barycentric weights of the probe points (scifem.evaluate_function, KNPEMIx_solver.py:612-643),
+        found once on the host; the device evaluates the resulting sparse functionals of the state every step.  Output order:
+        [ics point p, variable j] , [ecs point p, variable j] , [gamma point p] (phi_m = phi_i - phi_e on the membrane)."""
+        from .partition import Layout
+        m, ctx = self.mesh, self._ctx
+        d = m.gdim
+        n_owned = m.x.shape[0] if m.n_owned is None else m.n_owned
+        lay = Layout(self._node_vert, n_owned)
+        inv = []
+        for s in range(2):
+            a = np.full(m.x.shape[0], -1, np.int64)
+            a[self._node_vert[s]] = np.arange(self._node_vert[s].size)
+            inv.append(a)
+        owned = np.ones(m.cells.shape[0], bool) if m.cell_owned is None else m.cell_owned.astype(bool)
+        is_in = np.isin(m.cell_tags, np.asarray(self.intra_tags)) & owned
+        is_ex = (m.cell_tags == self.extra_tag[0]) & owned
+        ptr, cols, wts = [0], [], []
+        found = []
+
+        def claim(hit):
+            # exactly one rank evaluates a point (the lowest rank that holds a containing owned cell)
+            mine = float(self.comm.rank) if hit else float(self.comm.size)
+            return self.comm.allreduce(mine, op=MPI.MIN) == float(self.comm.rank) and hit
+
+        for s, pts, sel in ((0, self.ics_points, is_in), (1, self.ecs_points, is_ex)):
+            idx = np.flatnonzero(sel)
+            for pt in pts:
+                c, bary = self._locate(pt[:d], m.cells[idx])
+                take = claim(c is not None)
+                found.append(self.comm.allreduce(float(c is not None), op=MPI.MAX) > 0)
+                for f in range(4):
+                    if take:
+                        nodes = inv[s][m.cells[idx[c]]]
+                        cols += [int(v) for v in lay.col(s, f, nodes)]
+                        wts += [float(b) for b in bary]
+                    ptr.append(len(cols))
+        if self.gamma_points is not None:
+            fowned = np.ones(m.mf_verts.shape[0], bool) if m.mf_owned is None else m.mf_owned.astype(bool)
+            fidx = np.flatnonzero(fowned)
+            for pt in self.gamma_points:
+                best, bw = None, None
+                if fidx.size:
+                    xf = m.x[m.mf_verts[fidx]]                             # (nf, d, d): closest point by facet barycentrics
+                    E = np.transpose(xf[:, 1:] - xf[:, :1], (0, 2, 1))     # (nf, d, d-1)
+                    rhs = (pt[:d] - xf[:, 0])[:, :, None]
+                    G = np.transpose(E, (0, 2, 1)) @ E
+                    lam = np.linalg.solve(G, np.transpose(E, (0, 2, 1)) @ rhs)[:, :, 0]
+                    bary = np.concatenate([1.0 - lam.sum(1, keepdims=True), lam], 1)
+                    inside = np.all(bary >= -1e-9, axis=1)
+                    proj = np.einsum("fa,fai->fi", bary, xf)
+                    dist = np.linalg.norm(proj - pt[:d], axis=1)
+                    dist[~inside] = np.inf
+                    k = int(np.argmin(dist))
+                    if np.isfinite(dist[k]) and dist[k] <= 1e-6 * float(np.abs(m.x).max()):
+                        best, bw = k, bary[k]
+                take = claim(best is not None)
+                found.append(self.comm.allreduce(float(best is not None), op=MPI.MAX) > 0)
+                if take:
+                    verts = m.mf_verts[fidx[best]]
+                    cols += [int(v) for v in lay.col(0, 3, inv[0][verts])] + [int(v) for v in lay.col(1, 3, inv[1][verts])]
+                    wts += [float(b) for b in bw] + [-float(b) for b in bw]
+                ptr.append(len(cols))
+        if not all(found):
+            raise RuntimeError("point_evaluation: a probe point lies outside its subdomain (ics_points must be inside "
+                               "intracellular cells, ecs_points inside extracellular cells, gamma_points on the membrane)")
+        ctx.probe_setup(ptr, cols if cols else [0], wts if wts else [0.0])
+
+    def evaluate_probes(self):
+        """(ics values [variable, point], ecs values [variable, point], gamma values [point]) from the device state."""
+        v = np.asarray(self.comm.allreduce(self._ctx.probe_eval(), op=MPI.SUM))
+        ni, ne = len(self.ics_points), len(self.ecs_points)
+        ng = 0 if self.gamma_points is None else len(self.gamma_points)
+        ics = v[:4 * ni].reshape(ni, 4).T
+        ecs = v[4 * ni:4 * (ni + ne)].reshape(ne, 4).T
+        return ics, ecs, v[4 * (ni + ne):4 * (ni + ne) + ng]
 
     def _tag_table(self):
         from .ionic_models import HodgkinHuxley

@@ -72,9 +72,20 @@ class SolverKNPEMI:
             if "strong_threshold" in ks: self.strong_threshold = float(ks["strong_threshold"])
             if "reassemble_P" in ks: self.reassemble_P = bool(ks["reassemble_P"])
             if "non_zero_init_guess" in ks: self.nonzero_init_guess = bool(ks["non_zero_init_guess"])
-        if any((self.save_xdmfs, self.save_pngs, self.save_cpoints, self.save_dat)) or problem.point_evaluation:
-            raise NotImplementedError("XDMF / checkpoint / PNG / point-probe output is outside the B200 hot path "
+        if any((self.save_xdmfs, self.save_pngs, self.save_cpoints, self.save_dat)):
+            raise NotImplementedError("XDMF / checkpoint / PNG output is outside the B200 hot path "
                                       "(SURVEY.md section 2, #10); switch the output options off")
+        # settings the reference hands to hypre / its stimulus variant that have no counterpart here: say so instead of
+        # silently ignoring them
+        import warnings
+        ks = solver_config.get("ksp_settings", {})
+        for key in ("strong_threshold", "max_amg_iter"):
+            if key in ks:
+                warnings.warn(f"ksp_settings.{key} configures hypre BoomerAMG in the reference; the B200 path uses its own "
+                              f"smoothed-aggregation hierarchy (strength threshold 0.08, one cycle) and ignores it", stacklevel=2)
+        if hasattr(problem, "tau_syn_rise") or hasattr(problem, "tau_syn_decay"):
+            warnings.warn("stimulus.tau_syn_rise / tau_syn_decay are parsed but unused (the reference's HodgkinHuxley._eval calls "
+                          "_add_stimulus with step=True, KNPEMIx_problem.py:538-542): the stimulus decays with a_syn", stacklevel=2)
         if self.save_mat:
             self.time_steps = 1
 
@@ -141,6 +152,21 @@ class SolverKNPEMI:
         self.ctx.assemble_P()
         self.ctx.pc_setup(self.opts)
 
+    def init_data(self):
+        """KNPEMIx_solver.py:612-626: probe arrays [time index, variable, point]; index 0 = the initial state."""
+        p = self.problem
+        nv = p.num_variables
+        self.ics_point_values = np.zeros((self.time_steps + 1, nv, len(p.ics_points)))
+        self.ecs_point_values = np.zeros((self.time_steps + 1, nv, len(p.ecs_points)))
+        ng = 0 if p.gamma_points is None else len(p.gamma_points)
+        self.gamma_point_values = np.zeros((self.time_steps + 1, ng))
+        self.save_data(0)
+
+    def save_data(self, i: int):
+        """KNPEMIx_solver.py:628-643, evaluated on the device (only the probe values travel to the host)."""
+        ics, ecs, gam = self.problem.evaluate_probes()
+        self.ics_point_values[i], self.ecs_point_values[i], self.gamma_point_values[i] = ics, ecs, gam
+
     def assemble(self):
         """KNPEMIx_solver.py:104-116."""
         self._print("Assembling linear system ...")
@@ -164,6 +190,8 @@ class SolverKNPEMI:
         ctx.pc_setup(self.opts)                                     # ksp.setOperators + ksp.setUp (:386-389)
         setup_timer += self.comm.allreduce(time.perf_counter() - tic, op=MPI.MAX)
         ctx.set_time(p.t.value, 0)
+        if p.point_evaluation:
+            self.init_data()                                            # :99
         for model in p.ionic_models:
             if isinstance(model, HodgkinHuxley):
                 p.ode_substeps, p.rush_larsen = model.time_steps_ODE, model.use_Rush_Larsen
@@ -180,6 +208,8 @@ class SolverKNPEMI:
                 if isinstance(model, HodgkinHuxley):
                     model.update_t_mod()
             p._mark_device_newer()
+            if p.point_evaluation:
+                self.save_data(i)                                       # :474
             tm = ctx.last_timings()
             asm = self.comm.allreduce((tm["gate"] + tm["facet"] + tm["rows"]) * 1e-3, op=MPI.MAX)
             sol = self.comm.allreduce(tm["solve"] * 1e-3, op=MPI.MAX)

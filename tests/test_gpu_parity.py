@@ -182,12 +182,14 @@ def test_cube_values_against_committed_golden(kb):
     [("HH", (2, 3)), ("ATP", (2, 3)), ("NeuronalCT", (2, 3)), ("GlialCT", (4, 5)), ("KirNa", (4, 5))],
 ])
 def test_membrane_models(kb, models):
-    """Every IonicModel._eval of the reference (KNPEMIx_ionic_model.py) incl. the glial set used by main.py:32-38."""
+    """Every IonicModel._eval of the reference (KNPEMIx_ionic_model.py) incl. the glial set used by main.py:32-38; the HH-only
+    case uses a stimulus region with `multiple` directions (product of two axis masks, :574-587)."""
     mm = kb.mesh.cell_array_mesh(2, 16, 2)
     om = from_arrays(2, mm.x, mm.cells, mm.cell_tags, mm.intra_tags)
     glia = (4, 5) if any(n == "KirNa" for n, _ in models) else ()
+    region = ((0, 0.2e-6, 0.45e-6), (1, 0.1e-6, 0.3e-6)) if models == [("HH", None)] else (0, 0.2e-6, 0.45e-6)
     p = OracleParams(intra_tags=(2, 3, 4, 5), extra_tag=1, membrane_tags=(2, 3, 4, 5), stimulus_tags=(2,),
-                     glia_tags=glia, stimulus_region=(0, 0.2e-6, 0.45e-6), g_syn_bar=40.0, scale_stimulus=True)
+                     glia_tags=glia, stimulus_region=region, g_syn_bar=40.0, scale_stimulus=True)
     o = perturbed_oracle(om, p, models, seed=4)
     ctx = make_ctx(kb, om, p, models)
     push_oracle_state(ctx, o)
@@ -495,6 +497,54 @@ def test_midsize_time_loop_matches_oracle(kb, cfgdir, which):
                 scale = ref if f < 3 else max(ref, o.l2_norm(o.phi[0], list(it)))
                 assert abs(got - ref) <= 1e-8 * scale, (i, sd, f, got, ref, info.iterations)
     s.ctx.close()
+
+
+def test_point_probes_match_oracle_fields(kb, cfgdir):
+    """point_evaluation (SolverKNPEMI.init_data / save_data, KNPEMIx_solver.py:612-643): probe values [time, variable, point]
+    evaluated on the device against the oracle's fields interpolated at the same points (P1, barycentric)."""
+    import tempfile
+    txt = open(os.path.join(cfgdir, "c2_square32_iterative.yaml")).read()
+    txt += "\npoint_evaluation:\n  ics_points: [[0.5, 0.5], [0.3, 0.61]]\n  ecs_points: [[0.1, 0.12]]\n  gamma_points: [[0.25, 0.5]]\n"
+    with tempfile.NamedTemporaryFile("w", suffix=".yaml", delete=False) as fh:
+        fh.write(txt)
+    p = kb.ProblemKNPEMI(fh.name, verbose=False)
+    os.unlink(fh.name)
+    p.set_initial_conditions(); p.init_ionic_models([kb.NeuronalCotransporters(p), kb.HodgkinHuxley(p), kb.ATPPump(p)])
+    p.setup_variational_form()
+    p.solver_config["view_ksp"] = False
+    s = kb.SolverKNPEMI(p, solver_config=p.solver_config)
+    s.time_steps = 3
+    s.solve()
+    om = unit_square(32)
+    o = KNPEMIOracle(om, OracleParams(), MODELS_TEST)
+    pc = SchurPC(o)
+    x = o.pack()
+
+    def interp(field, pt, tag):
+        cells = om.cells[om.cell_tags == tag]
+        xc = om.x[cells]
+        T = np.transpose(xc[:, 1:] - xc[:, :1], (0, 2, 1))
+        lam = np.linalg.solve(T, (pt - xc[:, 0])[:, :, None])[:, :, 0]
+        bary = np.concatenate([1 - lam.sum(1, keepdims=True), lam], 1)
+        c = int(np.flatnonzero(np.all(bary >= -1e-9, axis=1))[0])
+        return float(bary[c] @ field[cells[c]])
+
+    ics = np.array([[0.5, 0.5], [0.3, 0.61]]) * 1e-6
+    ecs = np.array([[0.1, 0.12]]) * 1e-6
+    gam = np.array([0.25, 0.5]) * 1e-6
+    assert s.ics_point_values.shape == (4, 4, 2) and s.ecs_point_values.shape == (4, 4, 1) and s.gamma_point_values.shape == (4, 1)
+    for i in range(4):
+        if i > 0:
+            _, _, x, _ = o.step("gmres", pc, 1e-9, x, first=(i == 1))
+        for j in range(4):
+            fi = o.c[0][j] if j < 3 else o.phi[0]
+            fe = o.c[1][j] if j < 3 else o.phi[1]
+            scale_i = 1.0 if j < 3 else 0.07
+            for k, pt in enumerate(ics):
+                assert abs(s.ics_point_values[i, j, k] - interp(fi, pt, 1)) <= 1e-8 * max(abs(interp(fi, pt, 1)), scale_i if j == 3 else 0)
+            assert abs(s.ecs_point_values[i, j, 0] - interp(fe, ecs[0], 2)) <= 1e-8 * max(abs(interp(fe, ecs[0], 2)), scale_i if j == 3 else 0)
+        ref = interp(o.phi[0], gam, 1) - interp(o.phi[1], gam, 2)
+        assert abs(s.gamma_point_values[i, 0] - ref) <= 1e-8 * abs(ref)
 
 
 def test_3d_passive_time_loop_matches_oracle(kb):

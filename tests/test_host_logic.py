@@ -267,3 +267,27 @@ def test_solver_option_mapping(kb, tmp_path):
         with pytest.raises(exc):
             s._opts()
         setattr(s, attr, old)
+
+
+def test_ignored_settings_warn(kb, tmp_path):
+    """Settings that configure hypre / an unused stimulus variant in the reference are not silently dropped: the host mirror
+    warns (KNPEMIx_solver.py:38-39,72; mixed_dim_problem.py:299-304)."""
+    it = BASE.replace("solver: {direct: True, output: {save_xdmf: False}}",
+                      "solver: {direct: False, ksp_settings: {ksp_rtol: 1.0e-9, ksp_type: gmres, pc_type: hypre, strong_threshold: 0.5, "
+                      "norm_type: preconditioned, non_zero_init_guess: True}, output: {save_xdmf: False}}")
+    it = it.replace("a_syn: 5.0e-4,", "a_syn: 5.0e-4, tau_syn_rise: 1.0e-4, tau_syn_decay: 5.0e-4,")
+    p = kb.ProblemKNPEMI(write(tmp_path, it), verbose=False)
+    p.solver_config["view_ksp"] = False
+    with pytest.warns(UserWarning) as rec:
+        kb.SolverKNPEMI(p, solver_config=p.solver_config)
+    msgs = " ".join(str(r.message) for r in rec)
+    assert "strong_threshold" in msgs and "tau_syn" in msgs
+
+
+def test_point_evaluation_and_multiple_stimulus_directions_parse(kb, tmp_path):
+    txt = BASE + "point_evaluation: {ics_points: [[0.5, 0.5]], ecs_points: [[0.1, 0.1]], gamma_points: [[0.25, 0.5]]}\n" \
+               + "stimulus_region: {multiple: True, direction: [x, y], range: [[0.0, 0.5], [0.2, 0.6]]}\n"
+    p = kb.ProblemKNPEMI(write(tmp_path, txt), verbose=False)
+    assert p.point_evaluation and np.allclose(p.ics_points, [[0.5e-6, 0.5e-6]]) and np.allclose(p.gamma_points, [[0.25e-6, 0.5e-6]])
+    assert p.multiple_stimulus_directions and p.stimulus_region_directions == [0, 1]
+    assert np.allclose(p.stimulus_region_range, np.array([[0.0, 0.5], [0.2, 0.6]]) * 1e-6)
