@@ -164,7 +164,9 @@ def cpu_workload(workload, n, restart=30):
     pr.init_ionic_models([ctor[nm](pr) for nm in model_names])
     mesh = pr.mesh
     region = None
-    if pr.stimulus_region:
+    if pr.stimulus_region and pr.multiple_stimulus_directions:
+        region = tuple((int(d), float(r[0]), float(r[1])) for d, r in zip(pr.stimulus_region_directions, pr.stimulus_region_range))
+    elif pr.stimulus_region:
         region = (int(pr.stimulus_region_direction), float(pr.stimulus_region_range[0]), float(pr.stimulus_region_range[1]))
     ions = pr.ion_list
     p = OracleParams(dt=float(pr.dt.value), T=pr.T.value, F=pr.F.value, R=pr.R.value, C_M=pr.C_M.value,

@@ -68,7 +68,7 @@ def perturbed_oracle(om, p, models, seed=0):
 
 
 # ---------------------------------------------------------------------------------------------- structure
-@pytest.mark.parametrize("name", ["square32", "square7", "cube6", "cells2d", "cells3d"])
+@pytest.mark.parametrize("name", ["square32", "square7", "cube6", "cells2d", "cells3d", "plates3d"])
 def test_csr_structure_and_dofmaps_bit_exact(kb, name):
     om, p = MESHES[name](kb)
     o = KNPEMIOracle(om, p, MODELS_TEST)
@@ -90,9 +90,12 @@ def _sq(n):
     return lambda kb: (unit_square(n), OracleParams())
 
 
-def _cells(d, n, m):
+PLATES = {"plates": True, "thickness": 1, "pitch": 2, "spine": 1}
+
+
+def _cells(d, n, m, fill=0.5, shape=None):
     def f(kb):
-        mm = kb.mesh.cell_array_mesh(d, n, m)
+        mm = kb.mesh.cell_array_mesh(d, n, m, fill=fill, shape=shape)
         om = from_arrays(d, mm.x, mm.cells, mm.cell_tags, mm.intra_tags)
         it = tuple(mm.intra_tags)
         return om, OracleParams(intra_tags=it, extra_tag=1, membrane_tags=it, stimulus_tags=(2,))
@@ -100,7 +103,9 @@ def _cells(d, n, m):
 
 
 MESHES = {"square32": _sq(32), "square7": _sq(7), "cube6": lambda kb: (unit_cube(6), OracleParams()),
-          "cells2d": _cells(2, 24, 3), "cells3d": _cells(3, 8, 2)}
+          "cells2d": _cells(2, 24, 3), "cells3d": _cells(3, 8, 2),
+          # BASELINE C5 in miniature: plate-stack cells, every intracellular vertex on the membrane
+          "plates3d": _cells(3, 16, 2, 0.75, PLATES)}
 
 
 def test_c1_structure_against_committed_golden(kb):
@@ -115,7 +120,7 @@ def test_c1_structure_against_committed_golden(kb):
 
 
 # ---------------------------------------------------------------------------------------------- values
-@pytest.mark.parametrize("name", ["square32", "square7", "cube6", "cells2d", "cells3d"])
+@pytest.mark.parametrize("name", ["square32", "square7", "cube6", "cells2d", "cells3d", "plates3d"])
 def test_assembled_matrix_and_vector(kb, name):
     om, p = MESHES[name](kb)
     o = perturbed_oracle(om, p, MODELS_TEST, seed=1)
@@ -354,7 +359,7 @@ def test_c2_iterative_solver_matches_oracle_per_timestep(kb, cfgdir, form):
     assert sum(its_gpu) / 10 <= 4.0          # the reference's hypre needs 3.0 (tests/...iterative_solver.py:81); ours 3.1 / 3.3
 
 
-@pytest.mark.parametrize("name", ["square32", "cells2d", "cells3d"])
+@pytest.mark.parametrize("name", ["square32", "cells2d", "cells3d", "plates3d"])
 def test_schur_preconditioner_matches_oracle(kb, name):
     """Hierarchies of the ion and potential blocks level by level, and one application z = B r, against
     oracle/amg.py::SchurPC frozen at the same (perturbed) state."""
