@@ -73,7 +73,7 @@ SYMBOLS = [
 
 
 class KnpError(RuntimeError):
-    pass
+    code = 0
 
 
 _lib = None
@@ -149,7 +149,9 @@ def load():
 def check(rc):
     if rc != 0:
         msg = load().knp_last_error().decode(errors="replace")
-        raise KnpError(f"libknpemi_b200 error {rc}: {msg}")
+        err = KnpError(f"libknpemi_b200 error {rc}: {msg}")
+        err.code = rc
+        raise err
 
 
 def _ptr(a):
@@ -331,9 +333,14 @@ class Context:
         check(self._lib.knp_solve(self.h, A_ptr, b_ptr, x_ptr, C.byref(opts), C.byref(info), stream))
         return info
 
-    def step(self, opts: SolveOpts, stream=None):
+    def step(self, opts: SolveOpts, stream=None, raise_on_nonconvergence=True):
+        """One timestep.  A Krylov solve that hits max_it makes knp_step return KNP_E_NOCONV (the state holds the last
+        iterate); with raise_on_nonconvergence=False that case is returned like PETSc's KSP does it (info.converged == 0)."""
         info = SolveInfo()
-        check(self._lib.knp_step(self.h, C.byref(opts), C.byref(info), stream))
+        rc = self._lib.knp_step(self.h, C.byref(opts), C.byref(info), stream)
+        if rc == -3 and not raise_on_nonconvergence and info.iterations >= opts.max_it:
+            return info
+        check(rc)
         return info
 
     def step_host(self, u_host, gates_host, opts: SolveOpts):

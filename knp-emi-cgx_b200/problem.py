@@ -319,6 +319,11 @@ class ProblemKNPEMI:
         else:
             base = os.path.basename(self.input_files["mesh_file"])
             mt = re.match(r"(square|cube)(\d+)\.xdmf$", base)
+            if os.path.exists(self.input_files["mesh_file"]):
+                # a real mesh must never be replaced by a same-named synthetic fixture behind the user's back
+                raise RuntimeError(f"{self.input_files['mesh_file']} exists, but no XDMF/HDF5 reader is available in this environment "
+                                   "(h5py / meshio absent): the B200 path cannot ingest mesh files yet.  Describe the mesh with a "
+                                   "synthetic_mesh block, or remove the file to use the generated square{N} / cube{N} fixture.")
             if not mt:
                 raise RuntimeError(f"Cannot read {self.input_files['mesh_file']}: no XDMF/HDF5 reader is available; "
                                    "use a square{N}.xdmf / cube{N}.xdmf fixture name or a synthetic_mesh block.")
