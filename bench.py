@@ -52,12 +52,15 @@ def workload_yaml(kb, workload, n, cells_per_dim=None, rtol=None):
 def build_problem(kb, workload, n, local, cells_per_dim=None, rtol=None, restart=30, amg_form=None):
     """ProblemKNPEMI + SolverKNPEMI of one workload through the reference-facing API, preconditioner set up, t = 0."""
     cfg = workload_yaml(kb, workload, n, cells_per_dim, rtol)
+    t = [time.time()]
     p = kb.ProblemKNPEMI(cfg, verbose=False, device=local)
     os.unlink(cfg)
     p.set_initial_conditions()
     ctor = {"NeuronalCT": kb.NeuronalCotransporters, "HH": kb.HodgkinHuxley, "ATP": kb.ATPPump, "Passive": kb.PassiveModel}
     p.init_ionic_models([ctor[nm](p) for nm in WORKLOADS[workload][4]])
+    t.append(time.time())
     p.setup_variational_form()
+    t.append(time.time())
     p.solver_config["view_ksp"] = False
     s = kb.SolverKNPEMI(p, solver_config=p.solver_config)
     s.gmres_restart = restart
@@ -65,8 +68,14 @@ def build_problem(kb, workload, n, local, cells_per_dim=None, rtol=None, restart
         s.amg_form = amg_form
     s.setup_solver()
     p.setup_preconditioner(True)
+    t.append(time.time())
     s.ctx.pc_setup(s.opts)
     s.ctx.set_time(0.0, 0)
+    t.append(time.time())
+    if p.comm.rank == 0 and s.ctx.n_rows > 1000000:
+        print(f"bench.py: setup of {workload} N={n}: mesh + host mirror {t[1] - t[0]:.1f} s, device context (topology, CSR pattern, halo) "
+              f"{t[2] - t[1]:.1f} s, P assembly {t[3] - t[2]:.1f} s, preconditioner setup (AMG hierarchies) {t[4] - t[3]:.1f} s",
+              file=sys.stderr, flush=True)
     return p, s
 
 
