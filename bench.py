@@ -185,12 +185,9 @@ def cpu_workload(workload, n, restart=30):
                      T_stim=pr.T_stim.value, scale_stimulus=bool(pr.scale_stimulus), intra_tags=tuple(pr.intra_tags),
                      extra_tag=pr.extra_tag[0], membrane_tags=tuple(pr.gamma_tags), stimulus_tags=tuple(pr.stimulus_tags),
                      stimulus_region=region, c_e_init=tuple(i["ke_init"].value for i in ions))
-    qb, qw = kb.mesh.facet_quadrature(gdim)
-    # CSR pattern and dof maps of the contract layout from the host-only builder (no GPU involved)
-    pat = kb.lib.pattern_host(gdim, mesh.x, mesh.cells, mesh.cell_tags, p.intra_tags, p.extra_tag, mesh.mf_verts, mesh.mf_tags, qb, qw)
     cb = CpuBaseline(gdim, mesh.x, mesh.cells, mesh.cell_tags, mesh.mf_verts, mesh.mf_tags, p, [(nm, None) for nm in model_names],
-                     pat, restart=restart)
-    vi, ve = pat[2], pat[3]
+                     restart=restart)
+    vi, ve = cb.S
     u = np.concatenate([pr.wh[0][f]._data[vi] for f in range(4)] + [pr.wh[1][f]._data[ve] for f in range(4)])
     if pr.gating_variables:
         gates = np.stack([pr.n._data[cb.mverts], pr.m._data[cb.mverts], pr.h._data[cb.mverts]])

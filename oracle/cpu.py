@@ -46,6 +46,8 @@ def load():
     lib.kcpu_create.restype = vp
     lib.kcpu_create.argtypes = [C.POINTER(_Mesh), C.POINTER(_Params), C.c_int32]
     lib.kcpu_destroy.argtypes = [vp]
+    lib.kcpu_nnz.restype = C.c_int64
+    lib.kcpu_nnz.argtypes = [vp]
     lib.kcpu_error.restype = C.c_char_p
     lib.kcpu_error.argtypes = [vp]
     lib.kcpu_set_state.argtypes = [vp, vp, vp]
@@ -64,16 +66,19 @@ def _p(a):
 
 
 class CpuBaseline:
-    """One problem instance: mesh arrays (x, cells, cell_tags, membrane facets with tags), OracleParams, model list as for
-    KNPEMIOracle, and the CSR pattern of the system matrix (indptr, indices, dof_vert_i, dof_vert_e) in the contract
-    ordering -- tests pass the oracle's own pattern, bench.py the one the product's host-side builder returns."""
+    """One problem instance: mesh arrays (x, cells, cell_tags, membrane facets with tags), OracleParams and the model list as
+    for KNPEMIOracle.  The library builds the CSR pattern of the system matrix itself (contract ordering, 64-bit row
+    pointers); `pattern` = (indptr, indices) is an optional expectation -- tests pass the oracle's CSR and construction
+    fails if the two differ in a single entry."""
 
-    def __init__(self, gdim, x, cells, cell_tags, mf_verts, mf_tags, params, models, pattern, restart=30):
+    def __init__(self, gdim, x, cells, cell_tags, mf_verts, mf_tags, params, models, pattern=None, restart=30):
         self.lib = load()
         p = params
-        indptr, indices, vi, ve = pattern
         nv = x.shape[0]
-        self.S = [np.asarray(vi, np.int64), np.asarray(ve, np.int64)]
+        is_in0 = np.isin(cell_tags, np.asarray(p.intra_tags))
+        # restricted dof sets = vertices of the subdomain's cells, ascending (DofMapRestriction, KNPEMIx_problem.py:85-89)
+        self.S = [np.unique(cells[is_in0].ravel()).astype(np.int64), np.unique(cells[cell_tags == p.extra_tag].ravel()).astype(np.int64)]
+        indptr, indices = (None, None) if pattern is None else pattern[:2]
         r = []
         for S in self.S:
             a = np.full(nv, -1, np.int64)
@@ -96,7 +101,8 @@ class CpuBaseline:
         k["mf_stim"] = np.ascontiguousarray(np.isin(mf_tags, np.asarray(p.stimulus_tags)), np.uint8)
         qb, qw = facet_rule(gdim)
         k["qb"], k["qw"] = np.ascontiguousarray(qb, np.float64), np.ascontiguousarray(qw, np.float64)
-        k["indptr"], k["indices"] = np.ascontiguousarray(indptr, np.int32), np.ascontiguousarray(indices, np.int32)
+        if indptr is not None:
+            k["indptr"], k["indices"] = np.ascontiguousarray(indptr, np.int32), np.ascontiguousarray(indices, np.int32)
         m = _Mesh()
         m.gdim = gdim
         for s in range(2):
@@ -110,7 +116,8 @@ class CpuBaseline:
         m.mf_models = k["mf_models"].ctypes.data_as(C.POINTER(C.c_uint32))
         m.mf_stim = k["mf_stim"].ctypes.data_as(C.POINTER(C.c_uint8))
         m.qb, m.qw = k["qb"].ctypes.data_as(_f64p), k["qw"].ctypes.data_as(_f64p)
-        m.indptr, m.indices = k["indptr"].ctypes.data_as(_i32p), k["indices"].ctypes.data_as(_i32p)
+        if indptr is not None:
+            m.indptr, m.indices = k["indptr"].ctypes.data_as(_i32p), k["indices"].ctypes.data_as(_i32p)
         P = _Params()
         P.dt, P.F, P.R, P.T, P.C_M, P.phi_rest = p.dt, p.F, p.R, p.T, p.C_M, p.phi_rest
         for i in range(3):
@@ -127,9 +134,11 @@ class CpuBaseline:
         P.ode_substeps, P.rush_larsen = p.ode_substeps, int(p.rush_larsen)
         self.any_hh = any(nm == "HH" for nm, _ in models)
         self.n = 4 * (self.S[0].size + self.S[1].size)
-        self.nnz = int(k["indptr"][-1])
         self.n_mv = mverts.size
         self.h = self.lib.kcpu_create(C.byref(m), C.byref(P), restart)
+        if not self.h:
+            raise RuntimeError("CPU baseline: the CSR pattern built by the library differs from the expected one")
+        self.nnz = int(self.lib.kcpu_nnz(self.h))
 
     def close(self):
         if self.h:

@@ -46,6 +46,14 @@ struct Params {
 
 enum { M_PASSIVE = 1, M_KIRNA = 2, M_GLIAL_CT = 4, M_NEURONAL_CT = 8, M_ATP = 16, M_HH = 32 };
 
+// the system matrix: 64-bit row pointers (BASELINE C3 weak-scaled to 8 GPUs has 2.4e9 non-zeros in ONE address space here)
+struct CsrBig {
+  int n_rows = 0, n_cols = 0;
+  std::vector<int64_t> indptr;
+  std::vector<int32_t> indices;
+  std::vector<double> vals;
+};
+
 struct Level {
   CsrHost A, P, R;
   std::vector<double> dinv, x, b, r;
@@ -67,7 +75,8 @@ struct Ctx {
   std::vector<uint32_t> mf_models;
   std::vector<uint8_t> mf_stim;
   std::vector<double> qb, qw, farea;
-  CsrHost A;                                // pattern given by the caller (sorted rows), values assembled here
+  std::vector<int32_t> adj_ptr[2], adj_idx[2];   // node adjacency per subdomain (sorted, self included)
+  CsrBig A;                                 // pattern built in kcpu_create (sorted rows), values assembled here
   std::vector<double> b, u, gates;          // u: packed solution (n); gates 3 x n_mv
   Params p;
   double psi, stim_area, t;
@@ -86,18 +95,20 @@ struct Ctx {
 // loops over small levels stay serial: a parallel region costs more than the loop (and far more when the host is shared)
 constexpr int PAR_MIN = 20000;
 
-inline void spmv(const CsrHost& M, const double* x, double* y) {
+template <class Mat>
+inline void spmv(const Mat& M, const double* x, double* y) {
   const int n = M.n_rows;
 #pragma omp parallel for schedule(static) if (n > PAR_MIN)
   for (int i = 0; i < n; ++i) {
     double s = 0.0;
-    for (int j = M.indptr[i]; j < M.indptr[i + 1]; ++j) s += M.vals[j] * x[M.indices[j]];
+    for (auto j = M.indptr[i]; j < M.indptr[i + 1]; ++j) s += M.vals[j] * x[M.indices[j]];
     y[i] = s;
   }
 }
 
 // sorted-row search + atomic add: the MatSetValues of the restatement
-inline void add(CsrHost& M, int row, int col, double v) {
+template <class Mat>
+inline void add(Mat& M, int row, int col, double v) {
   const int32_t* lo = M.indices.data() + M.indptr[row];
   const int32_t* hi = M.indices.data() + M.indptr[row + 1];
   const int32_t* it = std::lower_bound(lo, hi, col);
@@ -493,28 +504,97 @@ void cycle(Amg& M, int l, const double* b, double* xout) {
   }
 }
 
-CsrHost adjacency_pattern(int n_nodes, const std::vector<int32_t>& cells, int nv, int blocks, int block_stride) {
-  // node adjacency (sorted, self included) replicated `blocks` times block-diagonally
-  std::vector<std::vector<int32_t>> adj(n_nodes);
+// node adjacency of a subdomain mesh (sorted, self included) as CSR: count, fill, sort + unique per node
+void node_adjacency(int n_nodes, const std::vector<int32_t>& cells, int nv, std::vector<int32_t>& ptr, std::vector<int32_t>& idx) {
   const size_t nc = cells.size() / nv;
+  std::vector<int64_t> off(n_nodes + 1, 0);
   for (size_t e = 0; e < nc; ++e)
-    for (int a = 0; a < nv; ++a)
-      for (int b = 0; b < nv; ++b) adj[cells[e * nv + a]].push_back(cells[e * nv + b]);
+    for (int a = 0; a < nv; ++a) off[cells[e * nv + a] + 1] += nv;
+  for (int i = 0; i < n_nodes; ++i) off[i + 1] += off[i];
+  std::vector<int32_t> raw((size_t)off[n_nodes]);
+  {
+    std::vector<int64_t> fill(off.begin(), off.end() - 1);
+    for (size_t e = 0; e < nc; ++e)
+      for (int a = 0; a < nv; ++a) {
+        int64_t& f = fill[cells[e * nv + a]];
+        for (int b = 0; b < nv; ++b) raw[f++] = cells[e * nv + b];
+      }
+  }
+  std::vector<int32_t> cnt(n_nodes);
+#pragma omp parallel for schedule(dynamic, 4096)
+  for (int i = 0; i < n_nodes; ++i) {
+    std::sort(raw.begin() + off[i], raw.begin() + off[i + 1]);
+    cnt[i] = (int32_t)(std::unique(raw.begin() + off[i], raw.begin() + off[i + 1]) - (raw.begin() + off[i]));
+  }
+  ptr.assign(n_nodes + 1, 0);
+  for (int i = 0; i < n_nodes; ++i) ptr[i + 1] = ptr[i] + cnt[i];
+  idx.resize(ptr[n_nodes]);
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n_nodes; ++i) std::copy(raw.begin() + off[i], raw.begin() + off[i] + cnt[i], idx.begin() + ptr[i]);
+}
+
+// the adjacency pattern replicated `blocks` times block-diagonally with the given stride
+CsrHost block_pattern(int n_nodes, const std::vector<int32_t>& ptr, const std::vector<int32_t>& idx, int blocks, int block_stride) {
   CsrHost M;
   M.n_rows = M.n_cols = blocks * block_stride;
   M.indptr.assign(1, 0);
-#pragma omp parallel for schedule(dynamic, 4096)
-  for (int i = 0; i < n_nodes; ++i) {
-    std::sort(adj[i].begin(), adj[i].end());
-    adj[i].erase(std::unique(adj[i].begin(), adj[i].end()), adj[i].end());
-  }
+  M.indices.reserve((size_t)blocks * idx.size());
   for (int k = 0; k < blocks; ++k)
     for (int i = 0; i < n_nodes; ++i) {
-      for (int32_t j : adj[i]) M.indices.push_back(k * block_stride + j);
+      for (int j = ptr[i]; j < ptr[i + 1]; ++j) M.indices.push_back(k * block_stride + idx[j]);
       M.indptr.push_back((int32_t)M.indices.size());
     }
   M.vals.assign(M.indices.size(), 0.0);
   return M;
+}
+
+// Sparsity pattern of the system matrix in the contract ordering (minimal pattern: all dof pairs of every cell for the dx
+// blocks, facet couplings between the membrane facet's own vertices; rows sorted): the same rule the product's host-side
+// builder applies (tests compare both with the oracle's CSR).
+template <int D>
+void build_pattern(Ctx& c) {
+  const int n0 = c.ns[0], n1 = c.ns[1];
+  // membrane-vertex adjacency (vertices sharing a membrane facet, self included)
+  std::vector<int32_t> gptr, gidx;
+  node_adjacency(c.n_mv, c.mf_mv, D, gptr, gidx);
+  std::vector<int32_t> mv_of[2];
+  for (int s = 0; s < 2; ++s) {
+    mv_of[s].assign(c.ns[s], -1);
+    for (int g = 0; g < c.n_mv; ++g) mv_of[s][c.mv_node[s][g]] = g;
+  }
+  CsrBig& A = c.A;
+  A.n_rows = A.n_cols = c.n;
+  A.indptr.assign((size_t)c.n + 1, 0);
+  for (int s = 0; s < 2; ++s)
+    for (int f = 0; f < 4; ++f)
+      for (int i = 0; i < c.ns[s]; ++i) {
+        const int deg = c.adj_ptr[s][i + 1] - c.adj_ptr[s][i];
+        const int g = mv_of[s][i];
+        const int gdeg = g >= 0 ? gptr[g + 1] - gptr[g] : 0;
+        A.indptr[(size_t)c.base[s] + (size_t)f * c.ns[s] + i + 1] = (f < 3 ? 2 : 4) * deg + gdeg;
+      }
+  for (int i = 0; i < c.n; ++i) A.indptr[i + 1] += A.indptr[i];
+  A.indices.resize((size_t)A.indptr[c.n]);
+  A.vals.assign(A.indices.size(), 0.0);
+  for (int s = 0; s < 2; ++s)
+    for (int f = 0; f < 4; ++f) {
+      const int ns = c.ns[s], base = c.base[s];
+#pragma omp parallel for schedule(static)
+      for (int i = 0; i < ns; ++i) {
+        int64_t pos = A.indptr[(size_t)base + (size_t)f * ns + i];
+        const int a0 = c.adj_ptr[s][i], a1 = c.adj_ptr[s][i + 1];
+        const int g = mv_of[s][i];
+        // potential of the other side of the membrane: phi_i columns sort before the extracellular rows' own columns,
+        // phi_e columns after the intracellular rows' own columns
+        if (s == 1 && g >= 0)
+          for (int t = gptr[g]; t < gptr[g + 1]; ++t) A.indices[pos++] = 3 * n0 + c.mv_node[0][gidx[t]];
+        for (int k = (f < 3 ? f : 0); k < (f < 3 ? f + 1 : 3); ++k)
+          for (int t = a0; t < a1; ++t) A.indices[pos++] = base + k * ns + c.adj_idx[s][t];
+        for (int t = a0; t < a1; ++t) A.indices[pos++] = base + 3 * ns + c.adj_idx[s][t];
+        if (s == 0 && g >= 0)
+          for (int t = gptr[g]; t < gptr[g + 1]; ++t) A.indices[pos++] = 4 * n0 + 3 * n1 + c.mv_node[1][gidx[t]];
+      }
+    }
 }
 
 template <int D>
@@ -523,7 +603,7 @@ int schur_setup(Ctx& c) {
   const int n0 = c.ns[0], n1 = c.ns[1];
   CsrHost Acc, App;
   {
-    CsrHost a0 = adjacency_pattern(n0, c.cells[0], D + 1, 3, n0), a1 = adjacency_pattern(n1, c.cells[1], D + 1, 3, n1);
+    CsrHost a0 = block_pattern(n0, c.adj_ptr[0], c.adj_idx[0], 3, n0), a1 = block_pattern(n1, c.adj_ptr[1], c.adj_idx[1], 3, n1);
     Acc.n_rows = Acc.n_cols = 3 * (n0 + n1);
     Acc.indptr = a0.indptr;
     Acc.indices = a0.indices;
@@ -531,7 +611,7 @@ int schur_setup(Ctx& c) {
     for (size_t i = 1; i < a1.indptr.size(); ++i) Acc.indptr.push_back(off + a1.indptr[i]);
     for (int32_t j : a1.indices) Acc.indices.push_back(3 * n0 + j);
     Acc.vals.assign(Acc.indices.size(), 0.0);
-    CsrHost p0 = adjacency_pattern(n0, c.cells[0], D + 1, 1, n0), p1 = adjacency_pattern(n1, c.cells[1], D + 1, 1, n1);
+    CsrHost p0 = block_pattern(n0, c.adj_ptr[0], c.adj_idx[0], 1, n0), p1 = block_pattern(n1, c.adj_ptr[1], c.adj_idx[1], 1, n1);
     c.Mass[0] = p0;
     c.Mass[1] = p1;
     App.n_rows = App.n_cols = n0 + n1;
@@ -782,7 +862,7 @@ struct kcpu_mesh {
   const uint32_t* mf_models;     // OR of the model flags active on the facet's tag
   const uint8_t* mf_stim;        // facet tag in stimulus_tags
   const double *qb, *qw;         // facet quadrature (barycentric nq x gdim, weights)
-  const int32_t *indptr, *indices;   // CSR pattern of the system matrix (sorted rows)
+  const int32_t *indptr, *indices;   // optional: expected CSR pattern of the system matrix (checked against the one built here)
 };
 
 void* kcpu_create(const kcpu_mesh* m, const Params* p, int32_t restart) {
@@ -806,10 +886,18 @@ void* kcpu_create(const kcpu_mesh* m, const Params* p, int32_t restart) {
   c->mf_stim.assign(m->mf_stim, m->mf_stim + m->n_mf);
   c->qb.assign(m->qb, m->qb + (size_t)m->nq * D);
   c->qw.assign(m->qw, m->qw + m->nq);
-  c->A.n_rows = c->A.n_cols = c->n;
-  c->A.indptr.assign(m->indptr, m->indptr + c->n + 1);
-  c->A.indices.assign(m->indices, m->indices + m->indptr[c->n]);
-  c->A.vals.assign(c->A.indices.size(), 0.0);
+  for (int s = 0; s < 2; ++s) node_adjacency(c->ns[s], c->cells[s], D + 1, c->adj_ptr[s], c->adj_idx[s]);
+  if (D == 2) build_pattern<2>(*c);
+  else build_pattern<3>(*c);
+  if (m->indptr && m->indices) {     // the caller's expectation (tests: the oracle's CSR) must match entry for entry
+    bool same = true;
+    for (int i = 0; i <= c->n && same; ++i) same = c->A.indptr[i] == (int64_t)m->indptr[i];
+    for (size_t j = 0; j < c->A.indices.size() && same; ++j) same = c->A.indices[j] == m->indices[j];
+    if (!same) {
+      delete c;
+      return nullptr;
+    }
+  }
   c->b.assign(c->n, 0.0);
   c->u.assign(c->n, 0.0);
   c->gates.assign((size_t)3 * c->n_mv, 0.0);
@@ -828,6 +916,7 @@ void* kcpu_create(const kcpu_mesh* m, const Params* p, int32_t restart) {
 }
 
 void kcpu_destroy(void* h) { delete (Ctx*)h; }
+int64_t kcpu_nnz(void* h) { return (int64_t)((Ctx*)h)->A.indices.size(); }
 int kcpu_threads(void) { return omp_get_max_threads(); }
 const char* kcpu_error(void* h) { return ((Ctx*)h)->err.c_str(); }
 
