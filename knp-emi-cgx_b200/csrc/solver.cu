@@ -82,6 +82,7 @@ static int dense_inverse_device(int n, double* A, cudaStream_t st) {
     gj_update_kernel<<<grid, 256, 0, st>>>(n, k, A, fcol.p, prow.p);
   }
   KNP_CUDA(cudaGetLastError());
+  g_kernel_launches += 2ull * (unsigned long long)n;
   KNP_CUDA(cudaStreamSynchronize(st));
   return KNP_OK;
 }
