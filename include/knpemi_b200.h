@@ -111,6 +111,8 @@ typedef struct {
   int32_t refine;               /* "direct" mode: keep restarting until the true residual stagnates `refine` times */
   double field_scale[8];        /* >0: solve in variables scaled per field block (balances c ~ 1e2 against phi ~ 1e-2
                                    in the residual norm; used by the "direct" mode); all 0 = unscaled (PETSc semantics) */
+  int32_t ksp_type;             /* 0 gmres (default), 1 cg: preconditioned conjugate gradients, device-resident loop
+                                   (ksp_type is passed through to PETSc in the reference, KNPEMIx_solver.py:212) */
 } knp_solve_opts;
 
 typedef struct {

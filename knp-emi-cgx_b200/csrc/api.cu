@@ -459,7 +459,7 @@ int knp_solve(knp_ctx* c, const double* A_vals, const double* b, double* x, cons
   CTX_GUARD(c);
   KNP_CHECK(o && info, "NULL argument");
   KNP_CHECK(c->pc_kind == o->pc, "knp_pc_setup must be called with the same preconditioner kind before knp_solve");
-  return gmres_solve(c, A_vals ? A_vals : c->A_vals.p, b ? b : c->b.p, x ? x : c->u.p, o, info, pick(c, stream));
+  return krylov_solve(c, A_vals ? A_vals : c->A_vals.p, b ? b : c->b.p, x ? x : c->u.p, o, info, pick(c, stream));
 }
 
 int knp_set_time(knp_ctx* c, double t, int32_t step_index) {
@@ -490,7 +490,7 @@ int knp_step(knp_ctx* c, const knp_solve_opts* o, knp_solve_info* info, void* st
   KNP_TRY(knp_assemble(c, c->t, nullptr, nullptr, st));                              // :402-403 (records ev[2])
   KNP_CUDA(cudaEventRecord(c->ev[3], st));
   if (c->step_index == 1 && o->project_nullspace) KNP_TRY(nullspace_remove(c, c->b.p, st));   // :415-419,333
-  int rc = gmres_solve(c, c->A_vals.p, c->b.p, c->u.p, o, info, st);                 // :435 ; u <- x (:451-468)
+  int rc = krylov_solve(c, c->A_vals.p, c->b.p, c->u.p, o, info, st);                 // :435 ; u <- x (:451-468)
   KNP_CUDA(cudaEventRecord(c->ev[4], st));
   KNP_CUDA(cudaEventSynchronize(c->ev[4]));
   float ms;

@@ -91,6 +91,7 @@ struct knp_ctx {
   size_t ldv = 0;
   knp::DevBuf<double> V, w, tmp, tmp2, colscale, partial, hdev, ydev, pc_dinv;
   double* h_pinned = nullptr;
+  knp::DevBuf<double> cg_scal, cg_hist;   // device-resident scalars and norm history of the CG loop
   // preconditioner
   int pc_kind = -1;
   std::unique_ptr<knp::Amg> amg;
@@ -175,6 +176,8 @@ int pc_apply(knp_ctx* c, const double* r, double* z, cudaStream_t st);
 double pc_bytes(const knp_ctx* c);
 int gmres_solve(knp_ctx* c, const double* A_vals, const double* b, double* x, const knp_solve_opts* o,
                 knp_solve_info* info, cudaStream_t st);
+int krylov_solve(knp_ctx* c, const double* A_vals, const double* b, double* x, const knp_solve_opts* o,
+                 knp_solve_info* info, cudaStream_t st);
 int halo_exchange(knp_ctx* c, double* x, cudaStream_t st);
 int allreduce_sum(knp_ctx* c, double* buf, int n, cudaStream_t st);
 const char* last_error();

@@ -91,5 +91,9 @@ int launch_range_sum(const double* x, int lo0, int hi0, int lo1, int hi1, double
 int launch_range_shift(double* x, int lo0, int hi0, int lo1, int hi1, const double* sum_dev, double inv_count,
                        cudaStream_t st);
 int launch_reduce_partials(const double* partial, int n_partial, double* out, cudaStream_t st);
+// preconditioned CG with device-resident scalars (solver.cu::cg_solve)
+int launch_cg_scalar(int phase, int it, const double* dots, double* S, double* hist, cudaStream_t st);
+int launch_cg_xr(int n, const double* S, const double* p, const double* q, double* x, double* r, cudaStream_t st);
+int launch_cg_p(int n, const double* S, const double* z, double* p, cudaStream_t st);
 
 }  // namespace knp

@@ -697,4 +697,75 @@ int launch_reduce_partials(const double* partial, int n_partial, double* out, cu
   return KNP_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ conjugate gradients
+// Device-resident scalars of the preconditioned CG loop (solver.cu::cg_solve): S[0] = (r, z), S[1] = alpha, S[2] = beta,
+// S[3] = state (0 running, 1 converged, 2 breakdown: (p, A p) <= 0 or non-finite), S[4] = tol^2, S[5] = iteration at which the
+// state left 0.  Every update kernel is a no-op once the state is non-zero, so the iterate stays frozen at the converged
+// step while the host catches up (it reads S back only every few iterations).
+__global__ void cg_scalar_kernel(int phase, int it, const double* __restrict__ dots, double* __restrict__ S,
+                                 double* __restrict__ hist) {
+  if (phase == 0) {                       // after (r0, z0), ||z0||^2
+    S[0] = dots[0];
+    S[3] = 0.0;
+    S[5] = 0.0;
+    hist[0] = dots[1];
+    if (!(dots[1] == dots[1])) S[3] = 2.0;
+    else if (dots[1] <= S[4]) S[3] = 1.0;
+  } else if (S[3] == 0.0) {
+    if (phase == 1) {                     // after (p, A p)
+      const double pq = dots[0];
+      if (!(pq > 0.0)) {
+        S[3] = 2.0;
+        S[5] = (double)it;
+      } else {
+        S[1] = S[0] / pq;
+      }
+    } else {                              // after (r, z), ||z||^2 of the new residual
+      S[2] = dots[0] / S[0];
+      S[0] = dots[0];
+      hist[it] = dots[1];
+      if (!(dots[1] == dots[1])) {
+        S[3] = 2.0;
+        S[5] = (double)it;
+      } else if (dots[1] <= S[4]) {
+        S[3] = 1.0;
+        S[5] = (double)it;
+      }
+    }
+  }
+}
+int launch_cg_scalar(int phase, int it, const double* dots, double* S, double* hist, cudaStream_t st) {
+  cg_scalar_kernel<<<1, 1, 0, st>>>(phase, it, dots, S, hist);
+  KNP_LAUNCHED();
+  return KNP_OK;
+}
+// x += alpha p ; r -= alpha q   (alpha = S[1])
+__global__ void cg_xr_kernel(int n, const double* __restrict__ S, const double* __restrict__ p, const double* __restrict__ q,
+                             double* __restrict__ x, double* __restrict__ r) {
+  if (S[3] != 0.0) return;
+  const double a = S[1];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    x[i] += a * p[i];
+    r[i] -= a * q[i];
+  }
+}
+// p = z + beta p   (beta = S[2])
+__global__ void cg_p_kernel(int n, const double* __restrict__ S, const double* __restrict__ z, double* __restrict__ p) {
+  if (S[3] != 0.0) return;
+  const double b = S[2];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = z[i] + b * p[i];
+}
+int launch_cg_xr(int n, const double* S, const double* p, const double* q, double* x, double* r, cudaStream_t st) {
+  if (n == 0) return KNP_OK;
+  cg_xr_kernel<<<grid_for(n), 256, 0, st>>>(n, S, p, q, x, r);
+  KNP_LAUNCHED();
+  return KNP_OK;
+}
+int launch_cg_p(int n, const double* S, const double* z, double* p, cudaStream_t st) {
+  if (n == 0) return KNP_OK;
+  cg_p_kernel<<<grid_for(n), 256, 0, st>>>(n, S, z, p);
+  KNP_LAUNCHED();
+  return KNP_OK;
+}
+
 }  // namespace knp

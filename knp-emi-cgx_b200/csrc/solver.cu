@@ -1054,4 +1054,109 @@ int gmres_solve(knp_ctx* c, const double* A_vals, const double* b, double* x, co
   return KNP_OK;
 }
 
+// Preconditioned conjugate gradients (ksp_type "cg", KNPEMIx_solver.py:212 passes the type through to PETSc): same convergence
+// test as the GMRES path (preconditioned norm ||B r|| relative to ||B b||, nonzero initial guess, nullspace removed after
+// every preconditioner application).  The loop is device resident: alpha, beta, (r, z) and the norm history live in device
+// memory (linalg.cu::cg_scalar_kernel), the vector updates read them from there, and the host looks at the state only every
+// `KNP_CG_CHECK` (default 4) iterations; once the state is "converged" the update kernels are no-ops, so the iterate is the one
+// of the converged step whatever the check interval.  Valid for symmetric positive definite operators and preconditioners
+// only (the coupled KNP-EMI matrix is not symmetric: PETSc would run CG on it all the same, and so do we, reporting a
+// breakdown when (p, A p) <= 0).
+int cg_solve(knp_ctx* c, const double* A_vals, const double* b, double* x, const knp_solve_opts* o, knp_solve_info* info,
+             cudaStream_t st) {
+  const int n = c->T.L.n_rows;
+  KNP_TRY(ensure_workspace(c, o->restart > 3 ? o->restart : 30));
+  const int max_it = o->max_it > 0 ? o->max_it : 5000;
+  if (c->cg_hist.n < (size_t)max_it + 2) KNP_TRY(c->cg_hist.alloc((size_t)max_it + 2));
+  if (!c->cg_scal.p) KNP_TRY(c->cg_scal.alloc(8));
+  static const int check = getenv("KNP_CG_CHECK") && atoi(getenv("KNP_CG_CHECK")) > 0 ? atoi(getenv("KNP_CG_CHECK")) : 4;
+  double* hp = c->h_pinned;
+  double* r = c->V.p;
+  double* z = c->V.p + c->ldv;
+  double* p = c->V.p + 2 * c->ldv;
+  double* q = c->V.p + 3 * c->ldv;
+  double* S = c->cg_scal.p;
+  info->iterations = 0;
+  info->converged = 0;
+  // ||B b||
+  KNP_TRY(apply_B(c, o, b, z, st));
+  KNP_TRY(dots_to_host(c, 0, z, hp, st));
+  const double bnorm = std::sqrt(hp[0]);
+  info->rnorm0 = info->rnorm = bnorm;
+  if (!(bnorm == bnorm) || std::isinf(bnorm)) {
+    set_error("CG: right-hand side is not finite");
+    return KNP_E_NOCONV;
+  }
+  const double tol = o->rtol * bnorm;
+  {
+    double init[8] = {0.0, 0.0, 0.0, 0.0, tol * tol, 0.0, 0.0, 0.0};
+    for (int i = 0; i < 8; ++i) hp[i] = init[i];
+    KNP_CUDA(cudaMemcpyAsync(S, hp, 8 * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
+  // r = b - A x ; z = B r ; p = z
+  KNP_TRY(spmv_A(c, A_vals, x, r, EPI_RESID, b, st));
+  KNP_TRY(apply_B(c, o, r, z, st));
+  KNP_TRY(launch_multi_dot(n, 1, r, c->ldv, z, c->partial.p, c->hdev.p, st));
+  KNP_TRY(allreduce_sum(c, c->hdev.p, 2, st));
+  KNP_TRY(launch_cg_scalar(0, 0, c->hdev.p, S, c->cg_hist.p, st));
+  KNP_CUDA(cudaMemcpyAsync(p, z, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  int it = 0, state = 0, it_state = 0;
+  auto poll = [&]() -> int {
+    KNP_CUDA(cudaMemcpyAsync(hp, S, 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    KNP_CUDA(cudaStreamSynchronize(st));
+    state = (int)hp[3];
+    it_state = (int)hp[5];
+    return KNP_OK;
+  };
+  KNP_TRY(poll());
+  while (state == 0 && it < max_it) {
+    const int stop = std::min(max_it, it + check);
+    for (; it < stop; ++it) {
+      KNP_TRY(spmv_A(c, A_vals, p, q, EPI_SET, nullptr, st));
+      KNP_TRY(launch_multi_dot(n, 1, p, c->ldv, q, c->partial.p, c->hdev.p, st));
+      KNP_TRY(allreduce_sum(c, c->hdev.p, 2, st));
+      KNP_TRY(launch_cg_scalar(1, it + 1, c->hdev.p, S, c->cg_hist.p, st));
+      KNP_TRY(launch_cg_xr(n, S, p, q, x, r, st));
+      KNP_TRY(apply_B(c, o, r, z, st));
+      KNP_TRY(launch_multi_dot(n, 1, r, c->ldv, z, c->partial.p, c->hdev.p, st));
+      KNP_TRY(allreduce_sum(c, c->hdev.p, 2, st));
+      KNP_TRY(launch_cg_scalar(2, it + 1, c->hdev.p, S, c->cg_hist.p, st));
+      KNP_TRY(launch_cg_p(n, S, z, p, st));
+    }
+    KNP_TRY(poll());
+  }
+  const int its = state != 0 ? it_state : it;
+  info->iterations = its;
+  KNP_CUDA(cudaMemcpyAsync(hp, c->cg_hist.p + its, sizeof(double), cudaMemcpyDeviceToHost, st));
+  KNP_CUDA(cudaStreamSynchronize(st));
+  info->rnorm = std::sqrt(hp[0]);
+  if (o->zero_mean_solution) KNP_TRY(project_nullspace(c, x, st));
+  KNP_TRY(halo_exchange(c, x, st));
+  if (c->nranks > 1) {
+    KNP_CUDA(cudaStreamSynchronize(st));
+    KNP_TRY(peer_error_check(c));
+  }
+  if (state == 2) {
+    set_error("CG: breakdown at iteration %d ((p, A p) <= 0 or a non-finite norm): operator or preconditioner not SPD", its);
+    return KNP_E_NOCONV;
+  }
+  if (state == 1) {
+    info->converged = 1;
+    return KNP_OK;
+  }
+  set_error("CG did not converge: %d iterations, ||B r|| = %.3e, tol = %.3e", its, info->rnorm, tol);
+  return KNP_E_NOCONV;
+}
+
+// ksp.solve dispatch on the Krylov type
+int krylov_solve(knp_ctx* c, const double* A_vals, const double* b, double* x, const knp_solve_opts* o, knp_solve_info* info,
+                 cudaStream_t st) {
+  if (o->ksp_type == 1) return cg_solve(c, A_vals, b, x, o, info, st);
+  if (o->ksp_type != 0) {
+    set_error("unknown ksp_type %d (0 = gmres, 1 = cg)", o->ksp_type);
+    return KNP_E_INVALID;
+  }
+  return gmres_solve(c, A_vals, b, x, o, info, st);
+}
+
 }  // namespace knp

@@ -52,7 +52,7 @@ class TagModels(C.Structure):
 class SolveOpts(C.Structure):
     _fields_ = [("rtol", C.c_double), ("max_it", C.c_int32), ("restart", C.c_int32), ("pc", C.c_int32),
                 ("project_nullspace", C.c_int32), ("zero_mean_solution", C.c_int32), ("refine", C.c_int32),
-                ("field_scale", C.c_double * 8)]
+                ("field_scale", C.c_double * 8), ("ksp_type", C.c_int32)]
 
 
 class SolveInfo(C.Structure):

@@ -111,15 +111,30 @@ class SolverKNPEMI:
                 o.field_scale[4 * s + 3] = max(self.comm.allreduce(float(np.abs(p.wh[0][3]._data).max()), op=MPI.MAX),
                                                self.comm.allreduce(float(np.abs(p.wh[1][3]._data).max()), op=MPI.MAX), 1e-3)
         else:
-            if self.ksp_type != "gmres":
-                raise NotImplementedError(f"ksp_type {self.ksp_type!r}: the system is nonsymmetric; only gmres is implemented")
+            if self.ksp_type not in ("gmres", "cg"):
+                raise NotImplementedError(f"ksp_type {self.ksp_type!r} is not implemented (gmres|cg)")
+            if self.ksp_type == "cg":
+                import warnings
+                warnings.warn("ksp_type 'cg': the coupled KNP-EMI matrix is not symmetric; like PETSc's KSPCG the solver runs "
+                              "anyway and reports a breakdown when (p, A p) <= 0", stacklevel=3)
+                o.ksp_type = 1
             if self.norm_type != "preconditioned":
                 raise NotImplementedError("only the preconditioned residual norm (the reference default) is implemented")
             if self.amg_form not in ("schur", "block_jacobi"):
                 raise ValueError(f"amg_form {self.amg_form!r}: expected 'schur' or 'block_jacobi'")
-            pcs = {"hypre": 3 if self.amg_form == "schur" else 2, "schur": 3, "gamg": 2, "amg": 2, "jacobi": 1, "none": 0}
+            # fieldsplit (:216-265): additive ICS / ECS split of the block-diagonal P with an AMG-preconditioned inner solve per
+            # split.  P has no coupling between the splits (nor between the fields inside one), so one smoothed-aggregation
+            # cycle on P IS the additive split with one cycle per split; the inner Krylov iterations (rtol 1e-5) are not run.
+            pcs = {"hypre": 3 if self.amg_form == "schur" else 2, "schur": 3, "gamg": 2, "amg": 2, "fieldsplit": 2,
+                   "jacobi": 1, "none": 0}
             if self.pc_type not in pcs:
-                raise NotImplementedError(f"pc_type {self.pc_type!r} is not implemented (hypre|schur|gamg|jacobi|none)")
+                raise NotImplementedError(f"pc_type {self.pc_type!r} is not implemented "
+                                          "(hypre|schur|gamg|fieldsplit|jacobi|none)")
+            if self.pc_type == "fieldsplit":
+                import warnings
+                warnings.warn("pc_type 'fieldsplit': the additive ics/ecs split is applied as ONE smoothed-aggregation cycle per "
+                              "split on the block-diagonal P (the reference's inner gmres+hypre solves to 1e-5 are not "
+                              "iterated)", stacklevel=3)
             o.rtol, o.max_it, o.restart = self.ksp_rtol, self.ksp_max_it, self.gmres_restart
             o.pc = pcs[self.pc_type] if self.use_P_mat else 0
             o.project_nullspace, o.zero_mean_solution, o.refine = int(pure_neumann), 0, 0

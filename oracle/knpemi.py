@@ -516,6 +516,31 @@ class KNPEMIOracle:
             if abs(g[j_done]) <= rtol * bnorm or its >= maxit:
                 return x, its
 
+    @staticmethod
+    def solve_pcg(A, b, x0, Binv, rtol, maxit=5000):
+        """Preconditioned conjugate gradients with PETSc's KSPCG conventions for the options the reference passes through
+        (KNPEMIx_solver.py:212,276-280): preconditioned norm ||B r|| relative to ||B b||, nonzero initial guess.
+        Returns (x, iterations)."""
+        x = x0.copy()
+        tol = rtol * np.linalg.norm(Binv(b))
+        r = b - A @ x
+        z = Binv(r)
+        if np.linalg.norm(z) <= tol:
+            return x, 0
+        p, rz = z.copy(), r @ z
+        for it in range(1, maxit + 1):
+            q = A @ p
+            alpha = rz / (p @ q)
+            x += alpha * p
+            r -= alpha * q
+            z = Binv(r)
+            rz_new = r @ z
+            if np.linalg.norm(z) <= tol:
+                return x, it
+            p = z + (rz_new / rz) * p
+            rz = rz_new
+        return x, maxit
+
     # ----------------------------------------------------------------- time loop
     def step(self, solver="direct", Pinv=None, rtol=1e-9, x_prev=None, first=False):
         """One pass of the SolverKNPEMI.solve loop body (KNPEMIx_solver.py:365-468)."""

@@ -672,3 +672,65 @@ def test_full_size_properties(kb, cfgdir, which):
             tot = y[lo + k * n_s: lo + (k + 1) * n_s].sum().item()
             assert abs(tot - meas[s]) <= 1e-9 * meas[s], (s, k, tot, meas[s])
     ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------- conjugate gradients
+def _spd_values_on_pattern(ip, ix, n):
+    """SPD values on a CSR pattern: weighted graph Laplacian + I on the structurally symmetric entries, zero elsewhere."""
+    rows = np.repeat(np.arange(n), np.diff(ip)).astype(np.int64)
+    cols = ix.astype(np.int64)
+    sym = np.isin(cols * n + rows, rows * n + cols) & (rows != cols)
+    lo, hi = np.minimum(rows, cols), np.maximum(rows, cols)
+    w = np.where(sym, 1.0 + ((lo * 31 + hi * 17) % 7) / 7.0, 0.0)
+    vals = -w
+    diag = rows == cols
+    vals[diag] = 1.0 + np.bincount(rows, weights=w, minlength=n)[rows[diag]]
+    return vals
+
+
+@pytest.mark.parametrize("pc", [0, 1])
+def test_cg_matches_cpu_pcg_on_spd_operator(kb, pc):
+    """ksp_type cg (device-resident loop) against the oracle's PCG: same iteration count, solution to 1e-10."""
+    import torch
+    om, p = MESHES["cells2d"](kb)
+    o = perturbed_oracle(om, p, MODELS_TEST)
+    ctx = make_ctx(kb, om, p, MODELS_TEST)
+    push_oracle_state(ctx, o)
+    ip, ix = ctx.csr()
+    n = ctx.n_rows
+    vals = _spd_values_on_pattern(ip, ix, n)
+    A = sp.csr_matrix((vals, ix, ip), shape=(n, n))
+    assert abs(A - A.T).max() == 0.0
+    rng = np.random.default_rng(3)
+    b = rng.standard_normal(n)
+    x0 = rng.standard_normal(n) * 0.1
+    opts = kb.lib.SolveOpts()
+    opts.rtol, opts.max_it, opts.restart, opts.pc, opts.ksp_type = 1e-10, 500, 30, pc, 1
+    if pc == 1:
+        ctx.assemble_P()
+        ctx.pc_setup(opts)
+        _, _, Pv = ctx.values_host()
+        ipP, ixP = ctx.csr_P()
+        dinv = 1.0 / sp.csr_matrix((Pv, ixP, ipP), shape=(n, n)).diagonal()
+        assert (dinv > 0).all()
+        Binv = lambda v: dinv * v
+    else:
+        ctx.pc_setup(opts)
+        Binv = lambda v: v
+    x_ref, its_ref = KNPEMIOracle.solve_pcg(A, b, x0, Binv, 1e-10, 500)
+    Ad = torch.tensor(vals, device="cuda")
+    bd = torch.tensor(b, device="cuda")
+    xd = torch.zeros(ctx.n_cols, dtype=torch.float64, device="cuda")
+    xd[:n] = torch.tensor(x0, device="cuda")
+    torch.cuda.synchronize()
+    info = ctx.solve(opts, A_ptr=Ad.data_ptr(), b_ptr=bd.data_ptr(), x_ptr=xd.data_ptr())
+    torch.cuda.synchronize()
+    assert info.converged == 1
+    assert info.iterations == its_ref
+    x = xd[:n].cpu().numpy()
+    assert np.abs(x - x_ref).max() <= 1e-10 * np.abs(x_ref).max()
+    # a non-SPD operator is reported as a breakdown, not silently iterated on
+    Ad2 = torch.tensor(-vals, device="cuda")
+    with pytest.raises(kb.lib.KnpError, match="breakdown"):
+        ctx.solve(opts, A_ptr=Ad2.data_ptr(), b_ptr=bd.data_ptr(), x_ptr=xd.data_ptr())
+    ctx.close()

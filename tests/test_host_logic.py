@@ -260,7 +260,16 @@ def test_solver_option_mapping(kb, tmp_path):
     s.use_P_mat = False
     assert s._opts().pc == 0
     s.use_P_mat = True
-    for attr, val, exc in (("pc_type", "ilu", NotImplementedError), ("ksp_type", "cg", NotImplementedError),
+    with pytest.warns(UserWarning, match="fieldsplit"):
+        s.pc_type = "fieldsplit"
+        assert s._opts().pc == 2
+    s.pc_type = "hypre"
+    assert s._opts().ksp_type == 0
+    with pytest.warns(UserWarning, match="not symmetric"):
+        s.ksp_type = "cg"
+        assert s._opts().ksp_type == 1
+    s.ksp_type = "gmres"
+    for attr, val, exc in (("pc_type", "ilu", NotImplementedError), ("ksp_type", "bicg", NotImplementedError),
                            ("norm_type", "unpreconditioned", NotImplementedError), ("amg_form", "bogus", ValueError)):
         old = getattr(s, attr)
         setattr(s, attr, val)

@@ -210,3 +210,19 @@ def test_conservation_functionals_closed_form():
     x = o.mesh.x[:, 0]
     assert abs(o.integral(x, [1, 2]) - 0.5 * L ** 3) < 1e-12 * L ** 3                   # int x dx, exact for P1
     assert abs(o.membrane_area(4) - 4 * 0.5 * L) < 1e-12 * L
+
+
+def test_pcg_restatement_solves_spd_system():
+    """oracle PCG (checker of the device CG loop) against a dense solve, with and without a Jacobi preconditioner."""
+    import scipy.sparse as sp
+    from oracle.knpemi import KNPEMIOracle
+    n = 200
+    rng = np.random.default_rng(0)
+    T = sp.diags([-1.0, 2.5, -1.0], [-1, 0, 1], shape=(n, n)).tocsr()
+    A = (T + sp.diags(rng.random(n))).tocsr()
+    b = rng.standard_normal(n)
+    x_exact = np.linalg.solve(A.toarray(), b)
+    for Binv in (lambda v: v, lambda v: v / A.diagonal()):
+        x, its = KNPEMIOracle.solve_pcg(A, b, np.zeros(n), Binv, 1e-12)
+        assert 0 < its < n
+        assert np.abs(x - x_exact).max() <= 1e-10 * np.abs(x_exact).max()
