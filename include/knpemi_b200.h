@@ -161,6 +161,10 @@ int knp_assemble(knp_ctx* ctx, double t, double* A_vals_dev, double* b_dev, void
 /* assemble_preconditioner (KNPEMI/KNPEMIx_solver.py:118-135) for the block-Jacobi form
  * (KNPEMI/KNPEMIx_problem.py:717-738). */
 int knp_assemble_P(knp_ctx* ctx, double* P_vals_dev, void* stream);
+/* Time-independent source contribution to the right-hand side: b[rows[i]] += vals[i] in every knp_assemble / knp_step
+ * (rows unique, owned).  Carries the ion-injection terms dt * (f_e, v)_{dx_e} of KNP-EMI (KNPEMI/KNPEMIx_problem.py:200-218,
+ * 613-614), whose mass-matrix products the host forms once; n = 0 clears. */
+int knp_set_source(knp_ctx* ctx, int32_t n, const int32_t* rows_host, const double* vals_host);
 int knp_values_dev(knp_ctx* ctx, double** A_vals, double** b, double** P_vals, double** x);
 /* y = A x with the context's CSR pattern (PETSc MatMult inside ksp.solve, :435). x in column layout. */
 int knp_spmv(knp_ctx* ctx, const double* A_vals_dev, const double* x_dev, double* y_dev, void* stream);
@@ -221,6 +225,14 @@ int knp_amg_level_host(const knp_ctx* ctx, int32_t level, int32_t* indptr, int32
    counts of the two subdomains), then with arrays of n_rows + 1, nnz, n_loc[0], n_loc[1] entries. */
 int knp_pattern_host(const knp_mesh_desc* mesh, int64_t* n_rows, int64_t* nnz, int32_t* n_own_loc4, int32_t* indptr,
                      int32_t* indices, int32_t* dof_vert_i, int32_t* dof_vert_e);
+/* Host-only (no GPU): the lane-group tables the edge-lane row kernel reads (csrc/topology.cpp): per (owned dof w, slot e)
+   at (w << lgG) + e the neighbour node id (adjG, -1 beyond the degree) and the cells around the edge (w, neighbour) written
+   as the adjacency slots of their other vertices (hitG: 1 word per entry in 2D, 4 words in 3D, unused bytes 0xFF); per dof
+   metaG = {deg | self << 8 | gamma degree << 16, membrane vertex or -1}; node_x = coordinates per restricted local dof
+   (intracellular dofs first).  Call once with NULL arrays for lgG / n_work / edge_ok (0: the mesh is served by the scan
+   kernel, no tables). */
+int knp_edge_tables_host(const knp_mesh_desc* mesh, int32_t* lgG, int64_t* n_work, int32_t* edge_ok, int32_t* adjG,
+                         uint32_t* hitG, int32_t* metaG, double* node_x);
 /* Host-only: the row blocks the TMA-staged SpMV (the MatMult of ksp.solve, KNPEMIx_solver.py:435) walks over --
    blocks4 = {first row (multiple of 4), rows, 4-aligned first non-zero, staged non-zeros} per block; n_blocks = -1 when a
    group of four rows exceeds the stage capacity (the CSR-vector kernel is used then). */

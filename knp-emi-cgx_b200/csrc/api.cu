@@ -63,11 +63,13 @@ int knp_create(knp_ctx** out, const knp_mesh_desc* mesh, int device) {
   KNP_TRY(c->d_self_slot.upload(H.self_slot));
   KNP_TRY(c->d_mv_of_node.upload(H.mv_of_node));
   KNP_TRY(c->d_gpre.upload(H.gpre));
-  // opt-in (KNP_ROWS_LISTS=1): list-driven phase 2b of the row kernel; measured SLOWER than the byte-compare scan
-  // (2D 1.99 vs 1.76 ms, 3D 4.29 vs 3.09 ms: the code -> address -> value chain serialises), kept for the record
-  if (H.elist_ok && getenv("KNP_ROWS_LISTS") && atoi(getenv("KNP_ROWS_LISTS"))) {
-    KNP_TRY(c->d_ecnt.upload(H.ecnt));
-    KNP_TRY(c->d_elist.upload(H.elist));
+  // lane-group tables of the edge-lane row kernel (default); KNP_ROWS=scan keeps the scan kernel for comparison, and a
+  // mesh whose edge rings or degrees exceed the tables (HostTopo::edge_ok == 0) is served by it as well
+  const bool use_edge = H.edge_ok && !(getenv("KNP_ROWS") && std::string(getenv("KNP_ROWS")) == "scan");
+  if (use_edge) {
+    KNP_TRY(c->d_adjG.upload(H.adjG));
+    KNP_TRY(c->d_hitG.upload(H.hitG));
+    KNP_TRY(c->d_metaG.upload(H.metaG));
   }
   KNP_TRY(c->d_mv_node0.upload(H.mv_node[0]));
   KNP_TRY(c->d_mv_node1.upload(H.mv_node[1]));
@@ -134,23 +136,10 @@ int knp_create(knp_ctx** out, const knp_mesh_desc* mesh, int device) {
   T.qw = c->d_qw.p;
   T.gpre = c->d_gpre.p;
   T.max_inc = H.max_inc;
-  T.ecnt = c->d_ecnt.p;
-  T.elist = c->d_elist.p;
-  T.Wp = (T.n_work + 31) / 32 * 32;
-  T.adjE = nullptr;
-  T.incE = nullptr;
-  T.geoK = T.mslot = T.kslot = nullptr;
-  const int nvv = H.gdim + 1;
-  const double ell_bytes = ((double)H.max_inc * (nvv * 8 + 4) + (double)H.max_deg * 20) * T.Wp;
-  if (getenv("KNP_ROWS") && std::string(getenv("KNP_ROWS")) == "ell" && T.n_work > 0 && ell_bytes < 24e9) {
-    // static geometry of the thread-per-dof row kernel: (nv max_inc + 2 max_deg) doubles per dof
-    KNP_TRY(c->d_adjE.alloc((size_t)H.max_deg * T.Wp));
-    KNP_TRY(c->d_incE.alloc((size_t)H.max_inc * T.Wp));
-    KNP_TRY(c->d_geoK.alloc((size_t)H.max_inc * nvv * T.Wp));
-    KNP_TRY(c->d_mslot.alloc((size_t)H.max_deg * T.Wp));
-    KNP_TRY(c->d_kslot.alloc((size_t)H.max_deg * T.Wp));
-    KNP_TRY(build_static_geometry(T, H.max_deg, c->d_adjE.p, c->d_incE.p, c->d_geoK.p, c->d_mslot.p, c->d_kslot.p, c->stream));
-  }
+  T.lgG = H.lgG;
+  T.adjG = use_edge ? c->d_adjG.p : nullptr;
+  T.hitG = use_edge ? c->d_hitG.p : nullptr;
+  T.metaG = use_edge ? reinterpret_cast<const int2*>(c->d_metaG.p) : nullptr;
   // CSR column indices on the device
   KNP_TRY(c->d_indices.alloc(H.nnz));
   KNP_TRY(c->d_indices_P.alloc(H.nnz_P));
@@ -173,8 +162,9 @@ int knp_create(knp_ctx** out, const knp_mesh_desc* mesh, int device) {
   std::vector<uint32_t>().swap(H.inc_slots);
   std::vector<uint32_t>().swap(H.minc);
   std::vector<int32_t>().swap(H.adj_idx);
-  std::vector<uint8_t>().swap(H.elist);
-  std::vector<uint8_t>().swap(H.ecnt);
+  std::vector<int32_t>().swap(H.adjG);
+  std::vector<uint32_t>().swap(H.hitG);
+  std::vector<int32_t>().swap(H.metaG);
   *out = c.release();
   return KNP_OK;
 }
@@ -408,6 +398,21 @@ int knp_assemble(knp_ctx* c, double t, double* A_vals, double* b, void* stream) 
   KNP_TRY(launch_facets(c->T, c->kp, c->d_tag_models.p, c->d_tag_stim.p, c->u.p, c->gates.p, stim_fac, c->fe.p, st));
   KNP_CUDA(cudaEventRecord(c->ev[2], st));
   KNP_TRY(launch_rows(c->T, c->kp, 0, c->u.p, c->fe.p, A_vals ? A_vals : c->A_vals.p, b ? b : c->b.p, c->H.max_deg, c->H.max_gdeg, st));
+  if (c->n_src > 0) KNP_TRY(launch_add_sparse(c->n_src, c->src_rows.p, c->src_vals.p, b ? b : c->b.p, st));   // :613-614
+  return KNP_OK;
+}
+
+int knp_set_source(knp_ctx* c, int32_t n, const int32_t* rows, const double* vals) {
+  CTX_GUARD(c);
+  KNP_CHECK(n >= 0 && (n == 0 || (rows && vals)), "knp_set_source: invalid arguments");
+  for (int i = 0; i < n; ++i) KNP_CHECK(rows[i] >= 0 && rows[i] < c->T.L.n_rows, "knp_set_source: row out of range");
+  KNP_CUDA(cudaStreamSynchronize(c->stream));
+  c->n_src = 0;
+  if (n > 0) {
+    KNP_TRY(c->src_rows.upload(std::vector<int32_t>(rows, rows + n)));
+    KNP_TRY(c->src_vals.upload(std::vector<double>(vals, vals + n)));
+    c->n_src = n;
+  }
   return KNP_OK;
 }
 
@@ -689,6 +694,23 @@ int knp_pattern_host(const knp_mesh_desc* mesh, int64_t* n_rows, int64_t* nnz, i
       }
     }
   }
+  return KNP_OK;
+}
+
+// lane-group tables of the edge-lane row kernel, host only (CPU test tier: the tables and the closed-form cell entries are
+// checked against the oracle's matrix without a GPU)
+int knp_edge_tables_host(const knp_mesh_desc* mesh, int32_t* lgG, int64_t* n_work, int32_t* edge_ok, int32_t* adjG,
+                         uint32_t* hitG, int32_t* metaG, double* node_x) {
+  HostTopo H;
+  KNP_TRY(build_topology(mesh, H));
+  if (lgG) *lgG = H.lgG;
+  if (n_work) *n_work = H.n_work;
+  if (edge_ok) *edge_ok = H.edge_ok;
+  if (!H.edge_ok) return KNP_OK;
+  if (adjG) memcpy(adjG, H.adjG.data(), H.adjG.size() * sizeof(int32_t));
+  if (hitG) memcpy(hitG, H.hitG.data(), H.hitG.size() * sizeof(uint32_t));
+  if (metaG) memcpy(metaG, H.metaG.data(), H.metaG.size() * sizeof(int32_t));
+  if (node_x) memcpy(node_x, H.node_x.data(), H.node_x.size() * sizeof(double));
   return KNP_OK;
 }
 

@@ -315,9 +315,6 @@ struct RowsSmem {       // computed on the host
   int res_stride;       // doubles per node in the cell-result block, padded so that the lane groups of one warp hit
                         // different banks (stride mod 16 doubles = 4)
   int pk_stride;        // words per node in the packed-slot block (odd)
-  int off_self;         // [tile][5] sums over all incident cells for the self slot
-  int off_el;           // the tile's (node, slot) cell lists (bytes)
-  int use_lists;
   int off_prod;         // products m_e c_k(e) for the right-hand side (inside the staging alias, after the rows)
   int off_rs;           // CSR row starts of the tile (not aliased)
   int total;
@@ -338,7 +335,7 @@ __device__ __forceinline__ void bulk_store(double* gdst, const double* ssrc, uin
                : "memory");
 }
 
-template <int D, int MODE, bool LISTS>
+template <int D, int MODE>
 __global__ void __launch_bounds__(ROWS_THREADS, ROWS_MIN_CTAS) rows_kernel(DevTopo T, RowCoef C, const double* __restrict__ u,
                                                                const double* __restrict__ fe,
                                                                double* __restrict__ vals, double* __restrict__ bvec,
@@ -356,9 +353,6 @@ __global__ void __launch_bounds__(ROWS_THREADS, ROWS_MIN_CTAS) rows_kernel(DevTo
   uint32_t* packed = reinterpret_cast<uint32_t*>(smraw + S.off_packed);
   double* prod = reinterpret_cast<double*>(smraw + S.off_prod);
   int* rstart = reinterpret_cast<int*>(smraw + S.off_rs);        // [4][tile + 1] CSR row starts of the tile's rows
-  double* selfacc = reinterpret_cast<double*>(smraw + S.off_self);   // [tile][5]: sums over all cells for the self slot
-  uint8_t* el = smraw + S.off_el;                                // the tile's (node, slot) cell lists
-  constexpr bool lists = LISTS;           // compile-time: the default (scan) kernel carries none of the list code
 
   const int tid = threadIdx.x;
   const int lgG = S.lgG, lgI = S.lgI, GI = 1 << lgI;
@@ -373,8 +367,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, ROWS_MIN_CTAS) rows_kernel(DevTo
 
   const int lw = tid >> lgG, e = tid & ((1 << lgG) - 1);
   const bool node_ok = lw < nt;
-  int deg = 0, gdeg = 0, self = -1, g = -1, ninc = 0, i0 = 0, ecnt = 0;
-  const int i_tile = T.inc_ptr[w0];
+  int deg = 0, gdeg = 0, self = -1, g = -1, ninc = 0, i0 = 0;
   if (node_ok) {
     const int w = w0 + lw;
     const int a0 = T.adj_ptr[w];
@@ -383,7 +376,6 @@ __global__ void __launch_bounds__(ROWS_THREADS, ROWS_MIN_CTAS) rows_kernel(DevTo
     g = T.mv_of_node[w];
     i0 = T.inc_ptr[w];
     ninc = T.inc_ptr[w + 1] - i0;
-    if (lists && e < deg) ecnt = T.ecnt[a0 + e];
     if (MODE == 0) gdeg = T.gpre[w + 1] - T.gpre[w];
     if (e < 4) {
       rstart[e * (tile + 1) + lw] = iptr[T.L.row(s, e, p0 + lw)];
@@ -404,8 +396,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, ROWS_MIN_CTAS) rows_kernel(DevTo
   const bool has_ent = node_ok && e < deg;
   __syncthreads();
 
-  // ---- phase 2a: one thread per (node, incident cell); the loop bound is warp-uniform because the GI threads of a node
-  //      also reduce the node's self-slot sums (all cells contribute to the self slot) with a shuffle butterfly ----
+  // ---- phase 2a: one thread per (node, incident cell) ----
   for (int i = tid; i < (tile << lgI); i += ROWS_THREADS) {
     const int n = i >> lgI, j = i & (GI - 1);
     bool valid = n < nt;
@@ -414,7 +405,6 @@ __global__ void __launch_bounds__(ROWS_THREADS, ROWS_MIN_CTAS) rows_kernel(DevTo
       ii0 = T.inc_ptr[w0 + n];
       valid = j < T.inc_ptr[w0 + n + 1] - ii0;
     }
-    double sself[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     if (valid) {
       const uint32_t pk = T.inc_slots[ii0 + j];
       packed[(size_t)n * S.pk_stride + j] = pk;
@@ -440,44 +430,17 @@ __global__ void __launch_bounds__(ROWS_THREADS, ROWS_MIN_CTAS) rows_kernel(DevTo
         gl[d] = t;
       }
       double* r = res + (size_t)n * S.res_stride + (size_t)j * NR;
-      double kself = 0.0;
 #pragma unroll
       for (int b = 0; b < NV; ++b) {
         double dot = 0.0;
 #pragma unroll
         for (int d = 0; d < D; ++d) dot += gl[d] * G.g[b][d];
-        const double kab = G.vol * dot;
-        r[b] = kab;
-        kself = (b == la) ? kab : kself;
+        r[b] = G.vol * dot;
       }
-      const double mv = G.vol * (1.0 / ((D + 1) * (D + 2)));
-      r[NV] = mv;
-      if (lists) {
-        sself[0] = mv;
-        sself[1] = kself;
-      }
+      r[NV] = G.vol * (1.0 / ((D + 1) * (D + 2)));
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const double cb = csum[k] * (1.0 / NV);
-        r[NV + 1 + k] = cb;
-        if (lists) sself[2 + k] = cb * kself;
-      }
+      for (int k = 0; k < 3; ++k) r[NV + 1 + k] = csum[k] * (1.0 / NV);
     }
-    if (lists) {
-      for (int off = GI >> 1; off > 0; off >>= 1) {
-#pragma unroll
-        for (int q = 0; q < 5; ++q) sself[q] += __shfl_xor_sync(0xffffffffu, sself[q], off);
-      }
-      if (j == 0 && n < nt) {
-#pragma unroll
-        for (int q = 0; q < 5; ++q) selfacc[n * 5 + q] = sself[q];
-      }
-    }
-  }
-  if (lists) {      // the tile's cell lists: one contiguous byte range of the global table
-    const int nbytes = (NV - 1) * (T.inc_ptr[w0 + nt] - i_tile);
-    const uint8_t* __restrict__ src = T.elist + (size_t)(NV - 1) * i_tile;
-    for (int i = tid; i < nbytes; i += ROWS_THREADS) el[i] = src[i];
   }
   __syncthreads();
 
@@ -488,46 +451,18 @@ __global__ void __launch_bounds__(ROWS_THREADS, ROWS_MIN_CTAS) rows_kernel(DevTo
   const bool is_self = has_ent && e == self;
   const bool has_gam = MODE == 0 && node_ok && e < gdeg;
   const uint32_t rep = (uint32_t)e * 0x01010101u;
-  int eoff = 0;
-  if (lists) {      // start of this lane's list inside its node's block: exclusive prefix sum of the list lengths
-    int incl = ecnt;
-    for (int off = 1; off < (1 << lgG); off <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, off, 1 << lgG);
-      if (e >= off) incl += v;
-    }
-    eoff = incl - ecnt;
-  }
   if (has_ent) {
 #pragma unroll
     for (int k = 0; k < 3; ++k) ce[k] = nbr[(size_t)tid * NB + D + k];
     const double* rbase = res + (size_t)lw * S.res_stride;
-    if (!lists) {
-      const uint32_t* pk = packed + (size_t)lw * S.pk_stride;
-      for (int j = 0; j < ninc; ++j) {
-        const uint32_t m = __vcmpeq4(pk[j], rep) & VMASK;
-        if (m) {
-          const int b = (__ffs(m) - 1) >> 3;
-          const double* r = rbase + j * NR;
-          const double kab = r[b], mv = r[NV];
-          a_m += is_self ? 2.0 * mv : mv;
-          a_kk += kab;
-#pragma unroll
-          for (int k = 0; k < 3; ++k) X[k] += r[NV + 1 + k] * kab;
-        }
-      }
-    } else if (is_self) {
-      const double* sa = selfacc + lw * 5;
-      a_m = 2.0 * sa[0];
-      a_kk = sa[1];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) X[k] = sa[2 + k];
-    } else {
-      const uint8_t* lst = el + (NV - 1) * (i0 - i_tile) + eoff;
-      for (int t = 0; t < ecnt; ++t) {
-        const int code = lst[t];
-        const double* r = rbase + (code >> 2) * NR;
-        const double kab = r[code & 3];
-        a_m += r[NV];
+    const uint32_t* pk = packed + (size_t)lw * S.pk_stride;
+    for (int j = 0; j < ninc; ++j) {
+      const uint32_t m = __vcmpeq4(pk[j], rep) & VMASK;
+      if (m) {
+        const int b = (__ffs(m) - 1) >> 3;
+        const double* r = rbase + j * NR;
+        const double kab = r[b], mv = r[NV];
+        a_m += is_self ? 2.0 * mv : mv;
         a_kk += kab;
 #pragma unroll
         for (int k = 0; k < 3; ++k) X[k] += r[NV + 1 + k] * kab;
@@ -865,290 +800,315 @@ int launch_facets(const DevTopo& T, const KParams& P, const uint32_t* tag_models
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Row kernel, second form: ONE THREAD PER DOF over static, TMA-friendly geometry tables.
+// Row kernel, edge-lane form (the default; the scan kernel above serves meshes whose tables do not fit).
 //
-// The mesh does not move, so everything geometric is computed once at setup (geo_build_kernel) and stored in
-// structure-of-arrays ELL tables whose leading dimension is the dof index (coalesced for a warp of 32 dofs):
-//   adjE[e][w]      neighbour of slot e                       incE[j][w]   packed slots of incident cell j
-//   geoK[j][b][w]   stiffness row of dof w in cell j          mslot/kslot[e][w]  assembled mass / stiffness per slot
-// Per timestep only the concentration-weighted stiffness X_k[e] = sum_j cbar_k(j) K_j[b(e)] depends on the solution.
-// A thread walks its dof's cells in ascending order (fixed order, no atomics), gathers the three concentrations of the
-// cell's vertices, and adds cbar_k K into its PRIVATE column of a shared-memory table (dynamic slot index, conflict-free
-// because the dof index is the fastest dimension).  The ten block rows are then formed field by field into a staging
-// strip at their CSR-relative offsets and leave through TMA bulk stores (two strips, ping-pong, so a store overlaps the
-// next field).  ~35 warp instructions per dof instead of ~245 for the lane-group kernel; the price is the static
-// tables (2D: +0.34 kB per dof of reads on top of 0.67 kB of algorithmic traffic).
-// MEASURED (B200, round 1): 2.54 ms on C3 and 5.96 ms on C4 against 1.75 / 3.17 ms for the lane-group kernel -- with
-// 0.5-1.2 kB of shared memory per thread only 12 (2D) / 4 (3D) warps fit an SM and the dependent incE -> adjE -> u
-// chain is latency-bound.  The kernel is therefore OPT-IN (KNP_ROWS=ell at context creation); it passes the same parity
-// tests and is kept as the starting point for a software-pipelined version.
+// Same ownership as the scan kernel -- one CTA per tile of consecutive owned dofs, G = 2^LG lanes per dof, lane e owns
+// adjacency slot e, i.e. one column position of all ten block rows -- but a lane computes its five sums itself from the
+// cells around ITS edge (dof p, neighbour q): the setup (topology.cpp) stores per (dof, slot) the cells that contain the
+// edge, each as the adjacency slots of the cell's other vertices, so the lane reads those vertices from the staged
+// neighbour block and evaluates the P1 entries in closed form
+//     2D  cell (p, q, r):      K_pq = -(p - r).(q - r) / (2 |(p - r) x (q - r)|),      |cell| = |(p - r) x (q - r)| / 2
+//     3D  cell (p, q, r, s):   K_pq = -(n_p . n_q) / (6 |J|),  n_q = (r - p) x (s - p),  n_p = (r - q) x (s - q),
+//                              J = (q - p) . n_q,                                      |cell| = |J| / 6
+// (K_pq = |cell| grad(lambda_p) . grad(lambda_q), the entry the scan kernel forms from the barycentric gradients).  The
+// sums of the self slot follow from the row-sum identities of the element matrices, K_pp = -sum_q K_pq per cell and
+// M_pp = (2/d) sum_q M_pq, with one butterfly over the lane group.  Against the scan kernel this removes the per-(dof, cell)
+// result block in shared memory, the byte-compare scan over all incident cells in every lane, one of the three CTA-wide
+// barriers and one level of the index -> neighbour -> value load chain (the lane-group tables are read at
+// (tile base << LG) + thread id: fully coalesced, no row-pointer lookup first).  Fixed summation order, no atomics:
+// bitwise reproducible.  Membrane terms, row formation, TMA bulk stores and the right-hand side are those of the scan kernel.
+#ifndef EDGE_MIN_CTAS
+#define EDGE_MIN_CTAS 4
+#endif
+#ifndef EDGE_MIN_CTAS_3D
+#define EDGE_MIN_CTAS_3D 3      // the 3D cell formulas need ~80 registers; 4 CTAs per SM would spill
+#endif
+constexpr int EDGE_NB = 6;      // doubles per staged neighbour: 2D {x, y, c0, c1, c2, -}, 3D {x, y, z, c0, c1, c2} (16-byte units)
 
-struct EllSmem {
-  int max_deg, max_inc, Wp;
-  int off_strip0, off_strip1;   // bytes
-  int total;
-};
-
-template <int D>
-__global__ void geo_build_kernel(DevTopo T, int Wp, int max_deg, int32_t* __restrict__ adjE, uint32_t* __restrict__ incE,
-                                 double* __restrict__ geoK, double* __restrict__ mslot, double* __restrict__ kslot) {
-  constexpr int NV = D + 1;
-  constexpr uint32_t VMASK = NV == 4 ? 0xFFFFFFFFu : 0x00FFFFFFu;
-  const int w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= T.n_work) return;
-  const int s = w >= T.L.n_own[0] ? 1 : 0;
-  const int nodeoff = s ? T.L.n_loc[0] : 0;
-  const int a0 = T.adj_ptr[w], deg = T.adj_ptr[w + 1] - a0;
-  const int i0 = T.inc_ptr[w], ninc = T.inc_ptr[w + 1] - i0;
-  const int self = T.self_slot[w];
-  for (int e = 0; e < max_deg; ++e) {
-    adjE[(size_t)e * Wp + w] = e < deg ? T.adj_idx[a0 + e] : -1;
-    mslot[(size_t)e * Wp + w] = 0.0;
-    kslot[(size_t)e * Wp + w] = 0.0;
-  }
-  for (int j = 0; j < T.max_inc; ++j) {
-    if (j >= ninc) {
-      incE[(size_t)j * Wp + w] = 0xFFFFFFFFu;
-#pragma unroll
-      for (int b = 0; b < NV; ++b) geoK[((size_t)j * NV + b) * Wp + w] = 0.0;
-      continue;
-    }
-    const uint32_t pk = T.inc_slots[i0 + j];
-    incE[(size_t)j * Wp + w] = pk;
-    const int la = (__ffs(__vcmpeq4(pk, (uint32_t)self * 0x01010101u) & VMASK) - 1) >> 3;
-    double x[NV][D];
-#pragma unroll
-    for (int b = 0; b < NV; ++b) {
-      const int q = T.adj_idx[a0 + ((pk >> (8 * b)) & 255u)];
-#pragma unroll
-      for (int d = 0; d < D; ++d) x[b][d] = T.node_x[(size_t)(nodeoff + q) * D + d];
-    }
-    CellGeom<D> G;
-    cell_geometry(x, G);
-    double gl[D];
-#pragma unroll
-    for (int d = 0; d < D; ++d) {
-      double t = G.g[0][d];
-#pragma unroll
-      for (int a = 1; a < NV; ++a) t = (la == a) ? G.g[a][d] : t;
-      gl[d] = t;
-    }
-    const double mv = G.vol * (1.0 / ((D + 1) * (D + 2)));
-#pragma unroll
-    for (int b = 0; b < NV; ++b) {
-      double dot = 0.0;
-#pragma unroll
-      for (int d = 0; d < D; ++d) dot += gl[d] * G.g[b][d];
-      const double kab = G.vol * dot;
-      geoK[((size_t)j * NV + b) * Wp + w] = kab;
-      const int e = (pk >> (8 * b)) & 255u;
-      mslot[(size_t)e * Wp + w] += (b == la) ? 2.0 * mv : mv;
-      kslot[(size_t)e * Wp + w] += kab;
-    }
-  }
-}
-
-template <int D, int MODE, int TB>
-__global__ void __launch_bounds__(TB) rows_ell_kernel(DevTopo T, RowCoef C, const double* __restrict__ u,
-                                                               const double* __restrict__ fe,
-                                                               double* __restrict__ vals, double* __restrict__ bvec,
-                                                               EllSmem S, int nb0) {
-  constexpr int NV = D + 1;
+template <int D, int MODE, int LG>
+__global__ void __launch_bounds__(ROWS_THREADS, D == 3 ? EDGE_MIN_CTAS_3D : EDGE_MIN_CTAS) rows_edge_kernel(DevTopo T, RowCoef C, const double* __restrict__ u,
+                                                                                const double* __restrict__ fe,
+                                                                                double* __restrict__ vals, double* __restrict__ bvec,
+                                                                                int ntile0, int off_rs) {
+  constexpr int G = 1 << LG, TILE = ROWS_THREADS / G;
   constexpr int NS = D * (D + 1) / 2;
+  constexpr int NB = EDGE_NB;
   constexpr uint32_t FMASK = D == 3 ? 0x00FFFFFFu : 0x0000FFFFu;
   extern __shared__ __align__(16) unsigned char smraw[];
-  double* X = reinterpret_cast<double*>(smraw);                 // [3][max_deg][TB], thread-private columns
-  double* strips[2] = {reinterpret_cast<double*>(smraw + S.off_strip0), reinterpret_cast<double*>(smraw + S.off_strip1)};
-  __shared__ int sh_base[4], sh_end[4];
-  const int tid = threadIdx.x;
-  const int s = blockIdx.x >= nb0 ? 1 : 0;
-  const int p0 = (blockIdx.x - (s ? nb0 : 0)) * TB;
-  const int n_own_s = T.L.n_own[s], n_gh_s = T.L.n_gh[s];
-  const int nt = min(TB, n_own_s - p0);
-  const int p = p0 + tid;
-  const bool active = tid < nt;
-  const int w = (s ? T.L.n_own[0] : 0) + p;
-  const int Wp = S.Wp, max_deg = S.max_deg;
-  const int* __restrict__ iptr = MODE == 0 ? T.indptr : T.indptr_P;
-  const double* __restrict__ u_own = u + T.L.rowbase[s];
-  const double* __restrict__ u_gh = u + T.L.n_rows + T.L.gbase[s] - n_own_s;
+  double* nbr = reinterpret_cast<double*>(smraw);                // [ROWS_THREADS][NB]
+  double* stg = nbr;                                             // alias: the neighbour block is dead by phase 3
+  int* rstart = reinterpret_cast<int*>(smraw + off_rs);          // [4][TILE + 1] CSR row starts of the tile's rows
 
-  int deg = 0, gdeg = 0, g = -1, rs[4] = {0, 0, 0, 0};
-  if (active) {
-    deg = T.adj_ptr[w + 1] - T.adj_ptr[w];
-    g = T.mv_of_node[w];
-    if (MODE == 0) gdeg = T.gpre[w + 1] - T.gpre[w];
+  const int tid = threadIdx.x;
+  const int lw = tid >> LG, e = tid & (G - 1);
+  const int s = blockIdx.x >= ntile0 ? 1 : 0;
+  const int p0 = (blockIdx.x - (s ? ntile0 : 0)) * TILE;
+  const int n_own_s = T.L.n_own[s];
+  const int nt = min(TILE, n_own_s - p0);
+  const int w0 = (s ? T.L.n_own[0] : 0) + p0;
+  const int nodeoff = s ? T.L.n_loc[0] : 0;
+  const int* __restrict__ iptr = MODE == 0 ? T.indptr : T.indptr_P;
+  const bool node_ok = lw < nt;
+
+  // ---- phase 1: tables (coalesced), then one gather per (dof, slot) into registers and shared memory ----
+  int q = -1;
+  int2 meta = make_int2(0, -1);
+  uint32_t hit[D == 2 ? 1 : 4];
 #pragma unroll
-    for (int f = 0; f < 4; ++f) rs[f] = iptr[T.L.row(s, f, p)];
-    if (tid == 0) {
-#pragma unroll
-      for (int f = 0; f < 4; ++f) sh_base[f] = rs[f];
+  for (int i = 0; i < (D == 2 ? 1 : 4); ++i) hit[i] = 0xFFFFFFFFu;
+  if (node_ok) {
+    const size_t at = ((size_t)w0 << LG) + tid;
+    q = T.adjG[at];
+    meta = T.metaG[w0 + lw];
+    if (D == 2) {
+      hit[0] = T.hitG[at];
+    } else {
+      const uint4 h4 = reinterpret_cast<const uint4*>(T.hitG)[at];
+      hit[0] = h4.x;
+      hit[D == 2 ? 0 : 1] = h4.y;
+      hit[D == 2 ? 0 : 2] = h4.z;
+      hit[D == 2 ? 0 : 3] = h4.w;
     }
-    if (tid == nt - 1) {
-#pragma unroll
-      for (int f = 0; f < 4; ++f) sh_end[f] = iptr[T.L.row(s, f, p) + 1];
+    if (e < 4) {
+      rstart[e * (TILE + 1) + lw] = iptr[T.L.row(s, e, p0 + lw)];
+      if (lw == nt - 1) rstart[e * (TILE + 1) + nt] = iptr[T.L.row(s, e, p0 + nt)];
     }
-    for (int e = 0; e < deg; ++e) {
+  }
+  const int deg = meta.x & 255, self = (meta.x >> 8) & 255;
+  const int gdeg = MODE == 0 ? (meta.x >> 16) & 255 : 0;
+  const int g = meta.y;
+  const bool has_ent = q >= 0;
+  double xq[3] = {0.0, 0.0, 0.0}, ce[3] = {0.0, 0.0, 0.0};
+  if (has_ent) {
 #pragma unroll
-      for (int k = 0; k < 3; ++k) X[(size_t)(k * max_deg + e) * TB + tid] = 0.0;
-    }
-    // ---- X_k[e] += cbar_k(j) K_j[b]: cells in ascending order; the packed slots and the stiffness row of the next
-    //      cell are fetched (read-only path) while the current one is processed ----
-    const uint32_t* __restrict__ incE = T.incE;
-    const int32_t* __restrict__ adjE = T.adjE;
-    const double* __restrict__ geoK = T.geoK;
-    uint32_t pk = __ldg(incE + w);
-    double kb[NV];
+    for (int i = 0; i < D; ++i) xq[i] = T.node_x[(size_t)(nodeoff + q) * D + i];
+    const double* __restrict__ uc = q < n_own_s ? u + T.L.rowbase[s] + q : u + T.L.n_rows + T.L.gbase[s] + (q - n_own_s);
+    const int fstride = q < n_own_s ? n_own_s : T.L.n_gh[s];
 #pragma unroll
-    for (int b = 0; b < NV; ++b) kb[b] = __ldg(geoK + (size_t)b * Wp + w);
-    for (int j = 0; j < S.max_inc && pk != 0xFFFFFFFFu; ++j) {
-      uint32_t pk_n = 0xFFFFFFFFu;
-      double kb_n[NV];
-      if (j + 1 < S.max_inc) {
-        pk_n = __ldg(incE + (size_t)(j + 1) * Wp + w);
-#pragma unroll
-        for (int b = 0; b < NV; ++b) kb_n[b] = __ldg(geoK + ((size_t)(j + 1) * NV + b) * Wp + w);
-      }
-      int sl[NV], q[NV];
-#pragma unroll
-      for (int b = 0; b < NV; ++b) {
-        sl[b] = (pk >> (8 * b)) & 255u;
-        q[b] = __ldg(adjE + (size_t)sl[b] * Wp + w);
-      }
-      double cv[3][NV];
-#pragma unroll
-      for (int b = 0; b < NV; ++b) {
-        const double* __restrict__ uc = q[b] < n_own_s ? u_own + q[b] : u_gh + q[b];
-        const int fs = q[b] < n_own_s ? n_own_s : n_gh_s;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) cv[k][b] = __ldg(uc + (size_t)k * fs);
-      }
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        double cs = 0.0;
-#pragma unroll
-        for (int b = 0; b < NV; ++b) cs += cv[k][b];
-        const double cb = cs * (1.0 / NV);
-#pragma unroll
-        for (int b = 0; b < NV; ++b) X[(size_t)(k * max_deg + sl[b]) * TB + tid] += cb * kb[b];
-      }
-      pk = pk_n;
-#pragma unroll
-      for (int b = 0; b < NV; ++b) kb[b] = kb_n[b];
+    for (int k = 0; k < 3; ++k) ce[k] = uc[(size_t)k * fstride];
+    double2* o = reinterpret_cast<double2*>(nbr + (size_t)tid * NB);
+    if (D == 2) {
+      o[0] = make_double2(xq[0], xq[1]);
+      o[1] = make_double2(ce[0], ce[1]);
+      o[2] = make_double2(ce[2], 0.0);
+    } else {
+      o[0] = make_double2(xq[0], xq[1]);
+      o[1] = make_double2(xq[2], ce[0]);
+      o[2] = make_double2(ce[1], ce[2]);
     }
   }
   __syncthreads();
 
-  const size_t nf = (size_t)T.n_mf;
-  const double sgn = s == 0 ? 1.0 : -1.0;
-  const int m0 = g >= 0 ? T.minc_ptr[g] : 0, m1 = g >= 0 ? T.minc_ptr[g + 1] : 0;
-  const int goff = s == 1 ? gdeg : 0;
+  // ---- phase 2: the lane's five sums over the cells around its edge, ascending cell order ----
+  double a_m = 0.0, a_kk = 0.0, X[3] = {0.0, 0.0, 0.0}, kphi_m[3] = {0.0, 0.0, 0.0}, pp_m = 0.0;
+  double bmem[4] = {0.0, 0.0, 0.0, 0.0};
+  double ga[3] = {0.0, 0.0, 0.0}, g1 = 0.0;
+  const bool is_self = has_ent && e == self;
+  const bool has_gam = MODE == 0 && node_ok && e < gdeg;
+  const uint32_t rep = (uint32_t)e * 0x01010101u;
+  const double* grp = nbr + (size_t)(lw << LG) * NB;              // the dof's neighbour block
+  if (has_ent && !is_self) {
+    const double2* pn = reinterpret_cast<const double2*>(grp + (size_t)self * NB);
+    if (D == 2) {
+      const double2 xp = pn[0], c01 = pn[1];
+      const double c2 = pn[2].x;
+      const double s0 = c01.x + ce[0], s1 = c01.y + ce[1], s2 = c2 + ce[2];
 #pragma unroll
-  for (int f = 0; f < 4; ++f) {
-    double* strip = strips[f & 1];
-    if (f >= 2) {                                   // the strip was last read by the bulk store of field f - 2
-      if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-      __syncthreads();
-    }
-    const int base = sh_base[f], total = sh_end[f] - base, sh = base & 1;
-    if (active) {
-      double* o = strip + sh + (rs[f] - base);
-      double bsum = 0.0;
-      double m_n = f < 3 ? __ldg(T.mslot + w) : 0.0, k_n = (f < 3 || MODE == 0) ? __ldg(T.kslot + w) : 0.0;
-      int q_n = (f < 3 && MODE == 0) ? __ldg(T.adjE + w) : 0;
-      for (int e = 0; e < deg; ++e) {
-        double kphi_m = 0.0, pp_m = 0.0;
-        if (g >= 0) {      // membrane (dS) terms: KNPEMIx_problem.py:599,604,609-610,637-638 (P: :737-738)
-          const uint32_t rep = (uint32_t)e * 0x01010101u;
-          for (int mi = m0; mi < m1; ++mi) {
-            const uint4 rec = reinterpret_cast<const uint4*>(T.minc)[mi];
-            const uint32_t ss = s == 0 ? (rec.y >> 8) : rec.z;
-            const uint32_t ms = __vcmpeq4(ss, rep) & FMASK;
-            if (ms) {
-              const int fct = (int)rec.x, a = rec.y & 255u, b = (__ffs(ms) - 1) >> 3;
-              if (f < 3) {
-                if (MODE == 0) {
-                  const int ab = a <= b ? symidx(a, b, D) : symidx(b, a, D);
-                  kphi_m += C.cmz[f] * fe[(size_t)((s * 3 + f) * NS + ab) * nf + fct];
-                }
-              } else {
-                const double G1 = T.mf_area[fct] * ((a == b) ? 2.0 : 1.0) * (1.0 / (D * (D + 1)));
-                pp_m += (MODE == 0 ? C.cf : -C.cf) * G1;
-              }
-            }
-          }
-        }
-        const double m = m_n, kk = k_n;
-        const int q = q_n;
-        if (e + 1 < deg) {
-          const size_t at = (size_t)(e + 1) * Wp + w;
-          if (f < 3) m_n = __ldg(T.mslot + at);
-          if (f < 3 || MODE == 0) k_n = __ldg(T.kslot + at);
-          if (f < 3 && MODE == 0) q_n = __ldg(T.adjE + at);
-        }
-        if (f < 3) {
-          o[goff + e] = m + C.dtD[f] * kk;
-          if (MODE == 0) {
-            o[goff + deg + e] = C.cphi[f] * X[(size_t)(f * max_deg + e) * TB + tid] + kphi_m;
-            bsum += m * (q < n_own_s ? __ldg(u_own + (size_t)f * n_own_s + q) : __ldg(u_gh + (size_t)f * n_gh_s + q));
-          }
-        } else {
-          double pp = pp_m;
-#pragma unroll
-          for (int k = 0; k < 3; ++k) pp += C.cpp[k] * X[(size_t)(k * max_deg + e) * TB + tid];
-          if (MODE == 0) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) o[goff + k * deg + e] = C.ck[k] * kk;
-            o[goff + 3 * deg + e] = pp;
-          } else {
-            o[e] = pp;
-          }
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t sl = (hit[0] >> (8 * h)) & 255u;
+        if (sl != 255u) {
+          const double2* rn = reinterpret_cast<const double2*>(grp + (size_t)sl * NB);
+          const double2 xr = rn[0], r01 = rn[1];
+          const double r2 = rn[2].x;
+          const double e1x = xp.x - xr.x, e1y = xp.y - xr.y, e2x = xq[0] - xr.x, e2y = xq[1] - xr.y;
+          const double cr = fabs(e1x * e2y - e1y * e2x);
+          const double dt = e1x * e2x + e1y * e2y;
+          const double kab = -0.5 * dt * (1.0 / cr);
+          a_m += cr * (1.0 / 24.0);
+          a_kk += kab;
+          X[0] += ((s0 + r01.x) * (1.0 / 3.0)) * kab;
+          X[1] += ((s1 + r01.y) * (1.0 / 3.0)) * kab;
+          X[2] += ((s2 + r2) * (1.0 / 3.0)) * kab;
         }
       }
-      if (MODE == 0) {
-        double bm = 0.0;
-        if (g >= 0) {
-          // gamma entries (couplings to the potential on the other side of the membrane) and the membrane rhs
-          double* og = o + (s == 1 ? 0 : (f < 3 ? 2 : 4) * deg);
-          for (int eg = 0; eg < gdeg; ++eg) {
-            const uint32_t rep = (uint32_t)eg * 0x01010101u;
-            double acc = 0.0;
-            for (int mi = m0; mi < m1; ++mi) {
-              const uint4 rec = reinterpret_cast<const uint4*>(T.minc)[mi];
-              const uint32_t mg = __vcmpeq4(rec.w, rep) & FMASK;
-              if (mg) {
-                const int fct = (int)rec.x, a = rec.y & 255u, b = (__ffs(mg) - 1) >> 3;
-                if (f < 3) {
-                  const int ab = a <= b ? symidx(a, b, D) : symidx(b, a, D);
-                  acc += C.cmz[f] * fe[(size_t)((s * 3 + f) * NS + ab) * nf + fct];
-                } else {
-                  acc += C.cf * (T.mf_area[fct] * ((a == b) ? 2.0 : 1.0) * (1.0 / (D * (D + 1))));
-                }
-              }
-            }
-            og[eg] = -acc;
-          }
-          for (int mi = m0; mi < m1; ++mi) {
-            const uint4 rec = reinterpret_cast<const uint4*>(T.minc)[mi];
-            const int fct = (int)rec.x, a = rec.y & 255u;
-            bm -= sgn * (f < 3 ? fe[(size_t)(6 * NS + (s * 3 + f) * D + a) * nf + fct] : fe[(size_t)(6 * NS + 6 * D + a) * nf + fct]);
-          }
-        }
-        bvec[T.L.row(s, f, p)] = bsum + bm;
+    } else {
+      const double2 p01 = pn[0], p23 = pn[1], p45 = pn[2];       // {x, y} {z, c0} {c1, c2}
+      const double ax = xq[0] - p01.x, ay = xq[1] - p01.y, az = xq[2] - p23.x;
+      const double s0 = p23.y + ce[0], s1 = p45.x + ce[1], s2 = p45.y + ce[2];
+#pragma unroll 2
+      for (int h = 0; h < 8; ++h) {
+        const uint32_t wv = (h >> 1) == 0 ? hit[0] : (h >> 1) == 1 ? hit[D == 2 ? 0 : 1] : (h >> 1) == 2 ? hit[D == 2 ? 0 : 2] : hit[D == 2 ? 0 : 3];
+        const uint32_t code = (wv >> (16 * (h & 1))) & 0xFFFFu;
+        if (code == 0xFFFFu) break;
+        const double2* rn = reinterpret_cast<const double2*>(grp + (size_t)(code & 255u) * NB);
+        const double2* sn = reinterpret_cast<const double2*>(grp + (size_t)(code >> 8) * NB);
+        const double2 r01 = rn[0], r23 = rn[1], r45 = rn[2];
+        const double2 t01 = sn[0], t23 = sn[1], t45 = sn[2];
+        const double bx = r01.x - p01.x, by = r01.y - p01.y, bz = r23.x - p23.x;
+        const double cx = t01.x - p01.x, cy = t01.y - p01.y, cz = t23.x - p23.x;
+        const double nqx = by * cz - bz * cy, nqy = bz * cx - bx * cz, nqz = bx * cy - by * cx;      // (r - p) x (s - p)
+        const double J = fabs(ax * nqx + ay * nqy + az * nqz);
+        const double ux = bx - ax, uy = by - ay, uz = bz - az, vx = cx - ax, vy = cy - ay, vz = cz - az;
+        const double npx = uy * vz - uz * vy, npy = uz * vx - ux * vz, npz = ux * vy - uy * vx;      // (r - q) x (s - q)
+        const double kab = -(npx * nqx + npy * nqy + npz * nqz) * (1.0 / (6.0 * J));
+        a_m += J * (1.0 / 120.0);
+        a_kk += kab;
+        X[0] += ((s0 + r23.y + t23.y) * 0.25) * kab;
+        X[1] += ((s1 + r45.x + t45.x) * 0.25) * kab;
+        X[2] += ((s2 + r45.y + t45.y) * 0.25) * kab;
       }
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    if (tid == 0) {
-      const int nbody = (total - sh) & ~1;
-      if (nbody > 0) bulk_store(vals + (size_t)base + sh, strip + 2 * sh, (uint32_t)nbody * 8u);
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    } else if (tid == 32) {
-      if (sh && total > 0) vals[(size_t)base] = strip[1];
-      if ((total - sh) & 1) vals[(size_t)base + total - 1] = strip[sh + total - 1];
     }
   }
-  if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  {
+    // self slot: K_pp = -sum_q K_pq, (cbar K)_pp = -sum_q (cbar K)_pq, and 2 sum_c |c|/((d+1)(d+2)) = (2/d) sum_q M_pq
+    double t[5] = {a_m, a_kk, X[0], X[1], X[2]};
+#pragma unroll
+    for (int off = G >> 1; off > 0; off >>= 1) {
+#pragma unroll
+      for (int i = 0; i < 5; ++i) t[i] += __shfl_xor_sync(0xffffffffu, t[i], off);
+    }
+    if (is_self) {
+      a_m = t[0] * (2.0 / D);
+      a_kk = -t[1];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) X[k] = -t[2 + k];
+    }
+  }
+  // membrane (dS) terms: KNPEMIx_problem.py:599,604,609-610,637-638,641-642 (P: :737-738); lane e serves adjacency
+  // slot e and gamma slot e (couplings to the potential on the other side of the membrane)
+  if (g >= 0 && (has_ent || has_gam)) {
+    const size_t nf = (size_t)T.n_mf;
+    const double sgn = s == 0 ? 1.0 : -1.0;
+    const int m1 = T.minc_ptr[g + 1];
+    for (int mi = T.minc_ptr[g]; mi < m1; ++mi) {
+      const uint4 rec = reinterpret_cast<const uint4*>(T.minc)[mi];
+      const int f = (int)rec.x;
+      const int a = rec.y & 255u;
+      const uint32_t ss = s == 0 ? (rec.y >> 8) : rec.z;
+      const uint32_t ms = has_ent ? (__vcmpeq4(ss, rep) & FMASK) : 0u;
+      const uint32_t mg = has_gam ? (__vcmpeq4(rec.w, rep) & FMASK) : 0u;
+      if (ms) {
+        const int b = (__ffs(ms) - 1) >> 3;
+        const double G1 = T.mf_area[f] * ((a == b) ? 2.0 : 1.0) * (1.0 / (D * (D + 1)));
+        if (MODE == 0) {
+          const int ab = a <= b ? symidx(a, b, D) : symidx(b, a, D);
+#pragma unroll
+          for (int k = 0; k < 3; ++k) kphi_m[k] += C.cmz[k] * fe[(size_t)((s * 3 + k) * NS + ab) * nf + f];
+          pp_m += C.cf * G1;
+        } else {
+          pp_m -= C.cf * G1;
+        }
+      }
+      if (MODE == 0 && mg) {
+        const int b = (__ffs(mg) - 1) >> 3;
+        const int ab = a <= b ? symidx(a, b, D) : symidx(b, a, D);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) ga[k] += C.cmz[k] * fe[(size_t)((s * 3 + k) * NS + ab) * nf + f];
+        g1 += C.cf * (T.mf_area[f] * ((a == b) ? 2.0 : 1.0) * (1.0 / (D * (D + 1))));
+      }
+      if (MODE == 0 && is_self) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) bmem[k] -= sgn * fe[(size_t)(6 * NS + (s * 3 + k) * D + a) * nf + f];
+        bmem[3] -= sgn * fe[(size_t)(6 * NS + 6 * D + a) * nf + f];
+      }
+    }
+  }
+  __syncthreads();          // the neighbour block is dead: the staging strip may overwrite it
+
+  // ---- phase 3: form the ten block rows at their CSR-relative offsets of the staging strip ----
+  int so[4], base[4], total[4];
+  {
+    int acc = 0;
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      base[f] = rstart[f * (TILE + 1)];
+      total[f] = rstart[f * (TILE + 1) + nt] - base[f];
+      so[f] = acc;                                   // even: 16-byte aligned start of the field's strip
+      acc += (total[f] + 3) & ~1;                    // room for the phase shift (base & 1), rounded to even
+    }
+  }
+  if (node_ok) {
+    const int goff = s == 1 ? gdeg : 0;
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      const int rsf = rstart[f * (TILE + 1) + lw] - base[f];
+      double* o = stg + so[f] + (base[f] & 1) + rsf;
+      if (has_ent) {
+        double* oe = o + goff + e;
+        if (MODE == 0) {
+          if (f < 3) {
+            oe[0] = a_m + C.dtD[f] * a_kk;
+            oe[deg] = C.cphi[f] * X[f] + kphi_m[f];
+          } else {
+            double pp = pp_m;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              oe[k * deg] = C.ck[k] * a_kk;
+              pp += C.cpp[k] * X[k];
+            }
+            oe[3 * deg] = pp;
+          }
+        } else {
+          if (f < 3) {
+            oe[0] = a_m + C.dtD[f] * a_kk;
+          } else {
+            double pp = pp_m;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) pp += C.cpp[k] * X[k];
+            oe[0] = pp;
+          }
+        }
+      }
+      if (has_gam) o[(s == 1 ? 0 : (f < 3 ? 2 : 4) * deg) + e] = f < 3 ? -ga[f] : -g1;
+    }
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staging writes -> visible to the TMA (async proxy)
+  __syncthreads();
+
+  // ---- copy-out: one TMA bulk store per field for the 16-byte aligned body, scalar head/tail ----
+  if (tid < 4) {
+    const int f = tid;
+    const int bf = rstart[f * (TILE + 1)], tf = rstart[f * (TILE + 1) + nt] - bf;
+    int sof = 0;
+    for (int ff = 0; ff < f; ++ff) sof += ((rstart[ff * (TILE + 1) + nt] - rstart[ff * (TILE + 1)]) + 3) & ~1;
+    const int sh = bf & 1;
+    const int nbody = (tf - sh) & ~1;
+    if (nbody > 0) bulk_store(vals + (size_t)bf + sh, stg + sof + 2 * sh, (uint32_t)nbody * 8u);
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    if (sh && tf > 0) vals[(size_t)bf] = stg[sof + 1];
+    if ((tf - sh) & 1) vals[(size_t)bf + tf - 1] = stg[sof + sh + tf - 1];
+  }
+  // right-hand side: b_k = sum_e m_e c_k(e) (KNPEMIx_problem.py:613-614,641-642): segmented warp-shuffle reduction over
+  // the dof's lane group (fixed butterfly order -> reproducible)
+  if (MODE == 0) {
+    double bk[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) bk[k] = has_ent ? a_m * ce[k] : 0.0;
+#pragma unroll
+    for (int off = G >> 1; off > 0; off >>= 1) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) bk[k] += __shfl_xor_sync(0xffffffffu, bk[k], off);
+    }
+    if (is_self) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) bvec[T.L.row(s, k, p0 + lw)] = bk[k] + bmem[k];
+      bvec[T.L.row(s, 3, p0 + lw)] = bmem[3];
+    }
+  }
+  if (tid < 4) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+static RowCoef make_coef(const KParams& P) {
+  RowCoef C;
+  for (int k = 0; k < 3; ++k) {
+    C.dtD[k] = P.dt * P.D[k];
+    C.cphi[k] = P.dt * P.D[k] * P.z[k] / P.psi;
+    C.cpp[k] = P.dt * P.D[k] * P.z[k] * P.z[k] / P.psi;
+    C.ck[k] = P.dt * P.z[k] * P.D[k];
+    C.cmz[k] = P.C_M / (P.F * P.z[k]);
+  }
+  C.cf = P.C_M / P.F;
+  return C;
 }
 
 // Lanes per node (power of two >= the largest degree) and the shared-memory layout of the row kernel.
@@ -1172,11 +1132,7 @@ static RowsSmem rows_layout(int gdim, int mode, int max_deg, int max_gdeg, int m
   const size_t packed = (size_t)S.tile * S.pk_stride * 4;
   S.off_res = (int)nbr;
   S.off_packed = (int)(nbr + res);
-  size_t work = (nbr + res + packed + 15) & ~(size_t)15;
-  S.off_self = (int)work;
-  work += (size_t)S.tile * 5 * 8;
-  S.off_el = (int)work;
-  work += ((size_t)S.tile * gdim * max_inc + 15) & ~(size_t)15;
+  const size_t work = (nbr + res + packed + 15) & ~(size_t)15;
   // staging strip: all four fields of the tile (+ phase shift and rounding per field), then the rhs products
   const size_t rows = (size_t)S.tile * (mode == 0 ? 10 * max_deg + 4 * max_gdeg : 4 * max_deg) + 16;
   S.off_prod = (int)(rows * 8);
@@ -1190,8 +1146,6 @@ template <int D, int MODE>
 static int launch_rows_t(const DevTopo& T, const KParams& P, const double* u, const double* fe, double* vals,
                          double* b, int max_deg, int max_gdeg, cudaStream_t st) {
   RowsSmem S = rows_layout(D, MODE, max_deg, max_gdeg, T.max_inc);
-  // list-driven phase 2b needs the lane groups (adjacency and incidence) inside one warp
-  S.use_lists = (T.elist && T.ecnt && S.lgG <= 5 && S.lgI <= 5 && ((S.tile << S.lgI) % 32) == 0) ? 1 : 0;
   if (S.total > 227 * 1024 || (1 << S.lgG) > ROWS_THREADS) {
     set_error("vertex degree %d / valence %d too large for the row kernel (%d bytes of shared memory)", max_deg,
               T.max_inc, S.total);
@@ -1199,110 +1153,60 @@ static int launch_rows_t(const DevTopo& T, const KParams& P, const double* u, co
   }
   static int configured = 0;
   if (S.total > 48 * 1024 && S.total > configured) {
-    KNP_CUDA(cudaFuncSetAttribute(rows_kernel<D, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S.total));
-    KNP_CUDA(cudaFuncSetAttribute(rows_kernel<D, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S.total));
+    KNP_CUDA(cudaFuncSetAttribute(rows_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, S.total));
     configured = S.total;
   }
-  RowCoef C;
-  for (int k = 0; k < 3; ++k) {
-    C.dtD[k] = P.dt * P.D[k];
-    C.cphi[k] = P.dt * P.D[k] * P.z[k] / P.psi;
-    C.cpp[k] = P.dt * P.D[k] * P.z[k] * P.z[k] / P.psi;
-    C.ck[k] = P.dt * P.z[k] * P.D[k];
-    C.cmz[k] = P.C_M / (P.F * P.z[k]);
-  }
-  C.cf = P.C_M / P.F;
+  const RowCoef C = make_coef(P);
   const int nt0 = (T.L.n_own[0] + S.tile - 1) / S.tile, nt1 = (T.L.n_own[1] + S.tile - 1) / S.tile;
-  if (S.use_lists) rows_kernel<D, MODE, true><<<nt0 + nt1, ROWS_THREADS, S.total, st>>>(T, C, u, fe, vals, b, S, nt0);
-  else rows_kernel<D, MODE, false><<<nt0 + nt1, ROWS_THREADS, S.total, st>>>(T, C, u, fe, vals, b, S, nt0);
+  rows_kernel<D, MODE><<<nt0 + nt1, ROWS_THREADS, S.total, st>>>(T, C, u, fe, vals, b, S, nt0);
   KNP_LAUNCHED();
   return KNP_OK;
 }
 
-static EllSmem ell_layout(int mode, int max_deg, int max_gdeg, int max_inc, int Wp, int ELL_THREADS) {
-  EllSmem S{};
-  S.max_deg = max_deg;
-  S.max_inc = max_inc;
-  S.Wp = Wp;
-  const size_t x = (size_t)3 * max_deg * ELL_THREADS * 8;
-  // strip 0 serves fields 0 and 2 (ion rows), strip 1 fields 1 and 3 (the potential rows are the long ones)
-  const size_t ion = mode == 0 ? 2 * max_deg + max_gdeg : max_deg;
-  const size_t pot = mode == 0 ? 4 * max_deg + max_gdeg : max_deg;
-  const size_t s0 = ((size_t)ELL_THREADS * ion + 4) * 8, s1 = ((size_t)ELL_THREADS * std::max(ion, pot) + 4) * 8;
-  S.off_strip0 = (int)x;
-  S.off_strip1 = (int)(x + ((s0 + 15) & ~(size_t)15));
-  S.total = S.off_strip1 + (int)((s1 + 15) & ~(size_t)15);
-  return S;
-}
-
-// dofs per CTA: 128 when three CTAs fit an SM, else 64 (3D: the X table and the strips grow with the degree); 0 = use
-// the lane-group kernel
-static int ell_block(int mode, int max_deg, int max_gdeg, int max_inc, int Wp) {
-  if (ell_layout(mode, max_deg, max_gdeg, max_inc, Wp, 128).total <= 75 * 1024) return 128;
-  if (ell_layout(mode, max_deg, max_gdeg, max_inc, Wp, 64).total <= 110 * 1024) return 64;
-  return 0;
-}
-
-template <int D, int MODE, int TB>
-static int launch_rows_ell_t(const DevTopo& T, const KParams& P, const double* u, const double* fe, double* vals,
-                             double* b, int max_deg, int max_gdeg, cudaStream_t st) {
-  const EllSmem S = ell_layout(MODE, max_deg, max_gdeg, T.max_inc, T.Wp, TB);
+template <int D, int MODE, int LG>
+static int launch_rows_edge_t(const DevTopo& T, const KParams& P, const double* u, const double* fe, double* vals,
+                              double* b, int max_deg, int max_gdeg, cudaStream_t st) {
+  constexpr int TILE = ROWS_THREADS >> LG;
+  const size_t nbr = (size_t)ROWS_THREADS * EDGE_NB * 8;
+  const size_t stage = ((size_t)TILE * (MODE == 0 ? 10 * max_deg + 4 * max_gdeg : 4 * max_deg) + 16) * 8;
+  const int off_rs = (int)((std::max(nbr, stage) + 15) & ~(size_t)15);
+  const int total = off_rs + 4 * (TILE + 1) * 4;
+  if (total > 227 * 1024) {
+    set_error("vertex degree %d too large for the row kernel (%d bytes of shared memory)", max_deg, total);
+    return KNP_E_UNSUPPORTED;
+  }
   static int configured = 0;
-  if (S.total > 48 * 1024 && S.total > configured) {
-    KNP_CUDA(cudaFuncSetAttribute(rows_ell_kernel<D, MODE, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, S.total));
-    configured = S.total;
+  if (total > 48 * 1024 && total > configured) {
+    KNP_CUDA(cudaFuncSetAttribute(rows_edge_kernel<D, MODE, LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, total));
+    configured = total;
   }
-  RowCoef C;
-  for (int k = 0; k < 3; ++k) {
-    C.dtD[k] = P.dt * P.D[k];
-    C.cphi[k] = P.dt * P.D[k] * P.z[k] / P.psi;
-    C.cpp[k] = P.dt * P.D[k] * P.z[k] * P.z[k] / P.psi;
-    C.ck[k] = P.dt * P.z[k] * P.D[k];
-    C.cmz[k] = P.C_M / (P.F * P.z[k]);
-  }
-  C.cf = P.C_M / P.F;
-  const int nb0 = (T.L.n_own[0] + TB - 1) / TB, nb1 = (T.L.n_own[1] + TB - 1) / TB;
-  rows_ell_kernel<D, MODE, TB><<<nb0 + nb1, TB, S.total, st>>>(T, C, u, fe, vals, b, S, nb0);
+  const int nt0 = (T.L.n_own[0] + TILE - 1) / TILE, nt1 = (T.L.n_own[1] + TILE - 1) / TILE;
+  rows_edge_kernel<D, MODE, LG><<<nt0 + nt1, ROWS_THREADS, total, st>>>(T, make_coef(P), u, fe, vals, b, nt0, off_rs);
   KNP_LAUNCHED();
   return KNP_OK;
 }
 
 template <int D, int MODE>
-static int launch_rows_ell(const DevTopo& T, const KParams& P, const double* u, const double* fe, double* vals,
-                           double* b, int max_deg, int max_gdeg, int tb, cudaStream_t st) {
-  return tb == 128 ? launch_rows_ell_t<D, MODE, 128>(T, P, u, fe, vals, b, max_deg, max_gdeg, st)
-                   : launch_rows_ell_t<D, MODE, 64>(T, P, u, fe, vals, b, max_deg, max_gdeg, st);
-}
-
-// static geometry tables of the ELL row kernel (setup, once per context)
-int build_static_geometry(DevTopo& T, int max_deg, int32_t* adjE, uint32_t* incE, double* geoK, double* mslot,
-                          double* kslot, cudaStream_t st) {
-  if (T.n_work == 0) return KNP_OK;
-  const int grid = (T.n_work + 127) / 128;
-  if (T.gdim == 2) geo_build_kernel<2><<<grid, 128, 0, st>>>(T, T.Wp, max_deg, adjE, incE, geoK, mslot, kslot);
-  else geo_build_kernel<3><<<grid, 128, 0, st>>>(T, T.Wp, max_deg, adjE, incE, geoK, mslot, kslot);
-  KNP_LAUNCHED();
-  T.adjE = adjE;
-  T.incE = incE;
-  T.geoK = geoK;
-  T.mslot = mslot;
-  T.kslot = kslot;
-  return KNP_OK;
-}
-
-static int rows_ell_block(const DevTopo& T, int mode, int max_deg, int max_gdeg) {
-  if (!T.adjE) return 0;        // static tables exist only when the context was created with KNP_ROWS=ell
-  return ell_block(mode, max_deg, max_gdeg, T.max_inc, T.Wp);
+static int launch_rows_edge(const DevTopo& T, const KParams& P, const double* u, const double* fe, double* vals, double* b,
+                            int max_deg, int max_gdeg, cudaStream_t st) {
+  switch (T.lgG) {
+    case 2: return launch_rows_edge_t<D, MODE, 2>(T, P, u, fe, vals, b, max_deg, max_gdeg, st);
+    case 3: return launch_rows_edge_t<D, MODE, 3>(T, P, u, fe, vals, b, max_deg, max_gdeg, st);
+    case 4: return launch_rows_edge_t<D, MODE, 4>(T, P, u, fe, vals, b, max_deg, max_gdeg, st);
+    case 5: return launch_rows_edge_t<D, MODE, 5>(T, P, u, fe, vals, b, max_deg, max_gdeg, st);
+  }
+  set_error("edge-lane row kernel: unsupported lane group 2^%d", T.lgG);
+  return KNP_E_UNSUPPORTED;
 }
 
 int launch_rows(const DevTopo& T, const KParams& P, int mode, const double* u, const double* fe, double* vals,
                 double* b, int max_deg, int max_gdeg, cudaStream_t st) {
   if (T.n_work == 0) return KNP_OK;
-  if (const int tb = rows_ell_block(T, mode, max_deg, max_gdeg)) {
-    if (T.gdim == 2) return mode == 0 ? launch_rows_ell<2, 0>(T, P, u, fe, vals, b, max_deg, max_gdeg, tb, st)
-                                      : launch_rows_ell<2, 1>(T, P, u, fe, vals, b, max_deg, max_gdeg, tb, st);
-    return mode == 0 ? launch_rows_ell<3, 0>(T, P, u, fe, vals, b, max_deg, max_gdeg, tb, st)
-                     : launch_rows_ell<3, 1>(T, P, u, fe, vals, b, max_deg, max_gdeg, tb, st);
+  if (T.adjG) {      // edge-lane kernel (tables exist: every edge ring fits, lane group <= one warp)
+    if (T.gdim == 2) return mode == 0 ? launch_rows_edge<2, 0>(T, P, u, fe, vals, b, max_deg, max_gdeg, st)
+                                      : launch_rows_edge<2, 1>(T, P, u, fe, vals, b, max_deg, max_gdeg, st);
+    return mode == 0 ? launch_rows_edge<3, 0>(T, P, u, fe, vals, b, max_deg, max_gdeg, st)
+                     : launch_rows_edge<3, 1>(T, P, u, fe, vals, b, max_deg, max_gdeg, st);
   }
   if (T.gdim == 2) return mode == 0 ? launch_rows_t<2, 0>(T, P, u, fe, vals, b, max_deg, max_gdeg, st)
                                     : launch_rows_t<2, 1>(T, P, u, fe, vals, b, max_deg, max_gdeg, st);

@@ -97,8 +97,10 @@ struct HostTopo {
   std::vector<int32_t> inc_ptr;           // per owned node
   std::vector<uint32_t> inc_slots;        // per (node, cell): adjacency slots of the cell's vertices (8 bit each)
   std::vector<int32_t> self_slot;         // per owned node: slot of itself in its adjacency
-  std::vector<uint8_t> ecnt, elist;       // per (node, slot): cells containing the slot (see topology.cpp)
-  int elist_ok = 0;
+  // lane-group tables of the edge-lane row kernel (topology.cpp, end of build_topology)
+  int lgG = 0, edge_ok = 0;
+  std::vector<int32_t> adjG, metaG;
+  std::vector<uint32_t> hitG;
   std::vector<int32_t> mv_of_node;        // per owned node: membrane vertex id or -1
   // membrane
   int n_mv = 0, n_mf = 0;
@@ -141,12 +143,11 @@ struct DevTopo {
   const double *qb, *qw;
   const int32_t* gpre;       // per owned node: prefix of the gamma degree
   int max_inc;               // largest number of cells incident to one owned node
-  const uint8_t *ecnt, *elist;   // per (node, slot) cell lists of the row kernel (nullptr: scan all incident cells)
-  // static ELL tables of the thread-per-dof row kernel (leading dimension Wp = dofs rounded up to 32)
-  int Wp;
-  const int32_t* adjE;
-  const uint32_t* incE;
-  const double *geoK, *mslot, *kslot;
+  // lane-group tables of the edge-lane row kernel (nullptr: the scan kernel serves the mesh); index (w << lgG) + slot
+  int lgG;
+  const int32_t* adjG;       // neighbour node or -1
+  const uint32_t* hitG;      // cells on the edge as slots of their other vertices (1 word in 2D, 4 words in 3D)
+  const int2* metaG;         // {deg | self << 8 | gamma degree << 16, membrane vertex or -1}
 };
 
 struct Params {

@@ -67,10 +67,8 @@ struct knp_ctx {
   // device copies of the topology
   knp::DevBuf<double> d_node_x, d_mf_area, d_qb, d_qw;
   knp::DevBuf<int32_t> d_adj_ptr, d_adj_idx, d_inc_ptr, d_self_slot, d_mv_of_node, d_gpre;
-  knp::DevBuf<uint32_t> d_inc_slots, d_minc, d_incE;
-  knp::DevBuf<uint8_t> d_ecnt, d_elist;
-  knp::DevBuf<int32_t> d_adjE;
-  knp::DevBuf<double> d_geoK, d_mslot, d_kslot;
+  knp::DevBuf<uint32_t> d_inc_slots, d_minc, d_hitG;
+  knp::DevBuf<int32_t> d_adjG, d_metaG;
   knp::DevBuf<int32_t> d_mv_node0, d_mv_node1, d_mf_mv, d_mf_tagidx, d_gam_ptr, d_gam_mv, d_minc_ptr;
   knp::DevBuf<int32_t> d_indptr, d_indices, d_indptr_P, d_indices_P, d_rowblk_A;
   int nblk_A = 0;
@@ -84,6 +82,10 @@ struct knp_ctx {
   // state and system
   knp::DevBuf<double> u, gates, A_vals, P_vals, b, fe;
   bool P_assembled = false;
+  // time-independent source entries of the right-hand side (knp_set_source)
+  knp::DevBuf<int32_t> src_rows;
+  knp::DevBuf<double> src_vals;
+  int n_src = 0;
   double t = 0.0;
   int step_index = 0;
   // Krylov workspace

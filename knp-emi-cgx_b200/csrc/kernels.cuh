@@ -20,8 +20,6 @@ int launch_gate(const DevTopo& T, const KParams& P, const double* u, double* gat
 int facet_ncomp(int gdim);
 int launch_facets(const DevTopo& T, const KParams& P, const uint32_t* tag_models, const int32_t* tag_stim,
                   const double* u, const double* gates, double stim_fac, double* fe, cudaStream_t st);
-int build_static_geometry(DevTopo& T, int max_deg, int32_t* adjE, uint32_t* incE, double* geoK, double* mslot,
-                          double* kslot, cudaStream_t st);
 int launch_rows(const DevTopo& T, const KParams& P, int mode, const double* u, const double* fe, double* vals,
                 double* b, int max_deg, int max_gdeg, cudaStream_t st);
 int launch_csr_indices(const DevTopo& T, int mode, int32_t* indices, cudaStream_t st);
@@ -91,6 +89,7 @@ int launch_range_sum(const double* x, int lo0, int hi0, int lo1, int hi1, double
 int launch_range_shift(double* x, int lo0, int hi0, int lo1, int hi1, const double* sum_dev, double inv_count,
                        cudaStream_t st);
 int launch_reduce_partials(const double* partial, int n_partial, double* out, cudaStream_t st);
+int launch_add_sparse(int n, const int32_t* rows, const double* vals, double* y, cudaStream_t st);   // y[rows[i]] += vals[i]
 // preconditioned CG with device-resident scalars (solver.cu::cg_solve)
 int launch_cg_scalar(int phase, int it, const double* dots, double* S, double* hist, cudaStream_t st);
 int launch_cg_xr(int n, const double* S, const double* p, const double* q, double* x, double* r, cudaStream_t st);

@@ -697,6 +697,18 @@ int launch_reduce_partials(const double* partial, int n_partial, double* out, cu
   return KNP_OK;
 }
 
+// y[rows[i]] += vals[i] (unique rows): time-independent source entries of the right-hand side (knp_set_source)
+__global__ void add_sparse_kernel(int n, const int32_t* __restrict__ rows, const double* __restrict__ vals, double* __restrict__ y) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[rows[i]] += vals[i];
+}
+int launch_add_sparse(int n, const int32_t* rows, const double* vals, double* y, cudaStream_t st) {
+  if (n == 0) return KNP_OK;
+  add_sparse_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, rows, vals, y);
+  KNP_LAUNCHED();
+  return KNP_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ conjugate gradients
 // Device-resident scalars of the preconditioned CG loop (solver.cu::cg_solve): S[0] = (r, z), S[1] = alpha, S[2] = beta,
 // S[3] = state (0 running, 1 converged, 2 breakdown: (p, A p) <= 0 or non-finite), S[4] = tol^2, S[5] = iteration at which the

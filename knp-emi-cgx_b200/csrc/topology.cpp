@@ -183,33 +183,6 @@ int build_topology(const knp_mesh_desc* m, HostTopo& T) {
     }
   }
 
-  // ---- per (node, slot) list of the cells that contain the slot (ascending cell order), self slot excluded: the
-  //      row kernel's phase 2b walks these lists instead of scanning all incident cells.  One byte per entry:
-  //      (incidence index << 2) | local vertex; one byte per adjacency entry for the list length ----
-  T.ecnt.assign(T.adj_idx.size(), 0);
-  T.elist.assign((size_t)(nv - 1) * inc_cell.size(), 0);
-  T.elist_ok = T.max_inc <= 64 ? 1 : 0;
-  if (T.elist_ok) {
-#pragma omp parallel for schedule(static)
-    for (int w = 0; w < W; ++w) {
-      const int i0 = T.inc_ptr[w], ninc = T.inc_ptr[w + 1] - i0, dg = T.adj_ptr[w + 1] - T.adj_ptr[w];
-      size_t pos = (size_t)(nv - 1) * i0;
-      for (int e = 0; e < dg; ++e) {
-        if (e == T.self_slot[w]) continue;
-        int cnt = 0;
-        for (int j = 0; j < ninc; ++j) {
-          const uint32_t pk = T.inc_slots[i0 + j];
-          for (int b = 0; b < nv; ++b)
-            if ((int)((pk >> (8 * b)) & 255u) == e) {
-              T.elist[pos++] = (uint8_t)((j << 2) | b);
-              ++cnt;
-            }
-        }
-        T.ecnt[T.adj_ptr[w] + e] = (uint8_t)cnt;
-      }
-    }
-  }
-
   // ---- membrane ----
   T.n_mf = (int)NF;
   std::vector<int32_t> mvid(NV, -1);
@@ -357,6 +330,68 @@ int build_topology(const knp_mesh_desc* m, HostTopo& T) {
   T.indptr_P[L.n_rows] = (int32_t)posP;
   T.nnz = pos;
   T.nnz_P = posP;
+
+  // ---- lane-group tables of the edge-lane row kernel (assembly.cu::rows_edge_kernel) ----
+  // A dof is served by G = 2^lgG lanes, lane e = adjacency slot e.  Per (dof, slot), at index (w << lgG) + e:
+  //   adjG   the neighbour (subdomain-local node id), -1 beyond the degree
+  //   hitG   the cells that contain the edge (dof, neighbour), in ascending cell order, each written as the adjacency
+  //          slots of the cell's OTHER vertices: 2D one byte per cell (4 bytes = one word, at most 2 used), 3D two bytes
+  //          per cell (8 cells = four words); unused entries are 0xFF bytes.  The self slot has no hits (its sums follow
+  //          from the row-sum identities of the P1 element matrices).
+  // Per dof: metaG = {deg | self << 8 | gamma degree << 16, membrane vertex or -1}.
+  // edge_ok = 0 (ring of an edge longer than the table holds, or G > 32): the scan kernel serves the mesh.
+  {
+    int lg = 0;
+    while ((1 << lg) < std::max(std::max(T.max_deg, T.max_gdeg), 4)) ++lg;
+    T.lgG = lg;
+    const int HW = d == 2 ? 1 : 4, HMAX = d == 2 ? 4 : 8;
+    T.edge_ok = lg <= 5 ? 1 : 0;
+    if (T.edge_ok) {
+      const size_t NE = (size_t)W << lg;
+      T.adjG.assign(NE, -1);
+      T.hitG.assign(NE * HW, 0xFFFFFFFFu);
+      T.metaG.assign((size_t)W * 2, 0);
+      int bad = 0;
+#pragma omp parallel for schedule(static) reduction(+ : bad)
+      for (int w = 0; w < W; ++w) {
+        const int a0 = T.adj_ptr[w], dg = T.adj_ptr[w + 1] - a0, self = T.self_slot[w];
+        const int i0 = T.inc_ptr[w], ninc = T.inc_ptr[w + 1] - i0;
+        const int gd = T.gpre[w + 1] - T.gpre[w];
+        T.metaG[(size_t)w * 2 + 0] = dg | (self << 8) | (gd << 16);
+        T.metaG[(size_t)w * 2 + 1] = T.mv_of_node[w];
+        int cnt[256];
+        for (int e = 0; e < dg; ++e) {
+          T.adjG[((size_t)w << lg) + e] = T.adj_idx[a0 + e];
+          cnt[e] = 0;
+        }
+        uint8_t* hb = reinterpret_cast<uint8_t*>(T.hitG.data());
+        for (int j = 0; j < ninc; ++j) {
+          const uint32_t pk = T.inc_slots[i0 + j];
+          int sl[4];
+          for (int b = 0; b < nv; ++b) sl[b] = (int)((pk >> (8 * b)) & 255u);
+          for (int b = 0; b < nv; ++b) {
+            const int e = sl[b];
+            if (e == self) continue;
+            if (cnt[e] >= HMAX) {
+              ++bad;
+              continue;
+            }
+            uint8_t* dst = hb + ((((size_t)w << lg) + e) * HW) * 4 + (size_t)cnt[e] * (d - 1);
+            int k = 0;
+            for (int c = 0; c < nv; ++c)
+              if (c != b && sl[c] != self) dst[k++] = (uint8_t)sl[c];
+            ++cnt[e];
+          }
+        }
+      }
+      if (bad) {
+        T.edge_ok = 0;
+        std::vector<int32_t>().swap(T.adjG);
+        std::vector<uint32_t>().swap(T.hitG);
+        std::vector<int32_t>().swap(T.metaG);
+      }
+    }
+  }
   return KNP_OK;
 }
 

@@ -64,8 +64,8 @@ SYMBOLS = [
     "knp_last_error", "knp_version", "knp_launch_count", "knp_create", "knp_destroy", "knp_get_sizes", "knp_csr_dev", "knp_csr_host",
     "knp_csr_P_host", "knp_dofmap_host", "knp_mverts_host", "knp_set_params", "knp_stimulus_area_local",
     "knp_set_state", "knp_get_state", "knp_state_dev", "knp_phi_m_host", "knp_gate_step", "knp_assemble",
-    "knp_assemble_P", "knp_values_dev", "knp_spmv", "knp_pc_setup", "knp_pc_apply", "knp_pc_bytes", "knp_solve", "knp_step",
-    "knp_step_host", "knp_set_time", "knp_get_time", "knp_l2_norm_sq", "knp_integral", "knp_membrane_area", "knp_probe_setup", "knp_probe_eval", "knp_stimulus_current", "knp_last_timings", "knp_amg_num_levels", "knp_amg_part_levels", "knp_amg_setup_host", "knp_amg_host_level", "knp_pattern_host", "knp_rowblocks_host",
+    "knp_assemble_P", "knp_set_source", "knp_values_dev", "knp_spmv", "knp_pc_setup", "knp_pc_apply", "knp_pc_bytes", "knp_solve", "knp_step",
+    "knp_step_host", "knp_set_time", "knp_get_time", "knp_l2_norm_sq", "knp_integral", "knp_membrane_area", "knp_probe_setup", "knp_probe_eval", "knp_stimulus_current", "knp_last_timings", "knp_amg_num_levels", "knp_amg_part_levels", "knp_amg_setup_host", "knp_amg_host_level", "knp_pattern_host", "knp_edge_tables_host", "knp_rowblocks_host",
     "knp_amg_dist_sim_host", "knp_amg_dist_sim_level", "knp_amg_dist_sim_perm",
     "knp_copy", "knp_amg_level_sizes", "knp_amg_level_host", "knp_nccl_unique_id", "knp_dist_init", "knp_halo_exchange", "knp_peer_direct",
     "knp_allreduce_sum",
@@ -108,6 +108,7 @@ def load():
     lib.knp_gate_step.argtypes = [vp, vp]
     lib.knp_assemble.argtypes = [vp, C.c_double, vp, vp, vp]
     lib.knp_assemble_P.argtypes = [vp, vp, vp]
+    lib.knp_set_source.argtypes = [vp, C.c_int32, vp, vp]
     lib.knp_values_dev.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     lib.knp_spmv.argtypes = [vp, vp, vp, vp, vp]
     lib.knp_pc_setup.argtypes = [vp, C.POINTER(SolveOpts)]
@@ -130,6 +131,7 @@ def load():
     lib.knp_amg_part_levels.argtypes = [vp, C.c_int32]
     lib.knp_rowblocks_host.argtypes = [C.c_int32, vp, C.c_int32, vp, vp]
     lib.knp_pattern_host.argtypes = [vp, c_i64p, c_i64p, vp, vp, vp, vp, vp]
+    lib.knp_edge_tables_host.argtypes = [vp, c_i32p, c_i64p, c_i32p, vp, vp, vp, vp]
     lib.knp_amg_setup_host.argtypes = [C.c_int32, vp, vp, vp, C.c_double, C.c_int32, vp]
     lib.knp_amg_host_level.argtypes = [C.c_int32, c_i64p, c_i64p, vp, vp, vp]
     lib.knp_amg_level_sizes.argtypes = [vp, C.c_int32, c_i64p, c_i64p]
@@ -206,6 +208,25 @@ def pattern_host(gdim, coords, cells, cell_tags, intra_tags, extra_tag, mf_verts
     vi, ve = np.empty(own[2], np.int32), np.empty(own[3], np.int32)      # local dofs: owned first, then ghosts
     check(lib.knp_pattern_host(C.byref(d), None, None, None, _ptr(indptr), _ptr(indices), _ptr(vi), _ptr(ve)))
     return indptr, indices, vi, ve
+
+
+def edge_tables_host(gdim, coords, cells, cell_tags, intra_tags, extra_tag, mf_verts, mf_tags, quad_bary, quad_w, **kw):
+    """Lane-group tables of the edge-lane row kernel (host only): dict(lgG, adjG[W, G], hitG[W, G, words], meta[W, 2],
+    node_x[n_loc0 + n_loc1, gdim], n_own_loc) or None when the mesh does not fit the tables."""
+    lib = load()
+    d, keep = mesh_desc(gdim, coords, cells, cell_tags, intra_tags, extra_tag, mf_verts, mf_tags, quad_bary, quad_w, **kw)
+    lg, ok, W = C.c_int32(), C.c_int32(), C.c_int64()
+    check(lib.knp_edge_tables_host(C.byref(d), C.byref(lg), C.byref(W), C.byref(ok), None, None, None, None))
+    if not ok.value:
+        return None
+    n = C.c_int64()
+    own = (C.c_int32 * 4)()
+    check(lib.knp_pattern_host(C.byref(d), C.byref(n), None, own, None, None, None, None))
+    G, hw = 1 << lg.value, (1 if gdim == 2 else 4)
+    adjG, hitG = np.empty((W.value, G), np.int32), np.empty((W.value, G, hw), np.uint32)
+    meta, x = np.empty((W.value, 2), np.int32), np.empty((own[2] + own[3], gdim), np.float64)
+    check(lib.knp_edge_tables_host(C.byref(d), None, None, None, _ptr(adjG), _ptr(hitG), _ptr(meta), _ptr(x)))
+    return dict(lgG=lg.value, adjG=adjG, hitG=hitG, meta=meta, node_x=x, n_own_loc=tuple(own))
 
 
 class Context:
@@ -313,6 +334,13 @@ class Context:
 
     def assemble_P(self, P_ptr=None, stream=None):
         check(self._lib.knp_assemble_P(self.h, P_ptr, stream))
+
+    def set_source(self, rows, vals):
+        """b[rows] += vals in every assembly (ion-injection terms); empty arrays clear."""
+        rows = np.ascontiguousarray(rows, np.int32)
+        vals = np.ascontiguousarray(vals, np.float64)
+        assert rows.shape == vals.shape and np.unique(rows).size == rows.size
+        check(self._lib.knp_set_source(self.h, int(rows.size), _ptr(rows), _ptr(vals)))
 
     def spmv(self, x_ptr, y_ptr, A_ptr=None, stream=None):
         check(self._lib.knp_spmv(self.h, A_ptr, x_ptr, y_ptr, stream))

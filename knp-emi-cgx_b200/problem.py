@@ -416,8 +416,68 @@ class ProblemKNPEMI:
             raise NotImplementedError("Dirichlet conditions / ECS pinning are outside the B200 hot path (SURVEY.md 8f-3)")
         self.bcs = []
 
+    injection_current = 5e-9      # [A], KNPEMIx_problem.py:211
+
+    def _cell_volumes(self, cells):
+        x = self.mesh.x[cells]
+        d = self.mesh.gdim
+        det = np.linalg.det(x[:, 1:] - x[:, :1])
+        return np.abs(det) / (2.0 if d == 2 else 6.0)
+
     def setup_source_terms(self):
-        raise NotImplementedError("ion_injection source terms are outside the B200 hot path (SURVEY.md 8f-3)")
+        """Ion injection (KNPEMIx_problem.py:200-218; site: utils/mixed_dim_problem.py:496-540,806-811): K+ and Cl- enter the
+        extracellular space at I / F mol/s, spread over the cells whose vertices all lie within (x_max - x_min)/10 of the
+        centre of the mesh's bounding box.  f_e is a P1 function (value on every vertex of an injection cell); the form
+        dt (f_e, v) dx_e only sees extracellular cells.  The device adds the resulting constant entries to b every step
+        (knp_set_source); they are formed in _upload_source() once the dof maps exist."""
+        m = self.mesh
+        lo = np.array([self.comm.allreduce(float(v), op=MPI.MIN) for v in m.x.min(axis=0)])
+        hi = np.array([self.comm.allreduce(float(v), op=MPI.MAX) for v in m.x.max(axis=0)])
+        centre, delta, tol = 0.5 * (lo + hi), (hi[0] - lo[0]) / 10.0, 1e-14
+        self.x_L, self.y_L = centre[0] - delta, centre[1] - delta
+        self.x_U, self.y_U = centre[0] + delta, centre[1] + delta
+        inside = np.all((m.x >= centre - delta - tol) & (m.x <= centre + delta + tol), axis=1)
+        self.injection_cells = np.flatnonzero(inside[m.cells].all(axis=1))
+        vol = self._cell_volumes(m.cells[self.injection_cells])
+        if m.cell_owned is not None:
+            vol = vol * (np.asarray(m.cell_owned)[self.injection_cells] != 0)
+        self.injection_volume = self.comm.allreduce(float(vol.sum()), op=MPI.SUM)
+        if not self.injection_volume > 0.0:
+            raise RuntimeError("ion_injection: no mesh cell lies inside the injection site")
+        src_term = (self.injection_current / (1 * self.F.value)) / self.injection_volume      # [mol / (m^3 s)] = [mM / s]
+        nv = m.x.shape[0]
+        verts = np.unique(m.cells[self.injection_cells].ravel())
+        for ion in (self.K, self.Cl):
+            f = Function(self, nv, f"f_e_{ion['name']}")
+            f._data[verts] = src_term
+            ion["f_e"] = f
+
+    def _upload_source(self):
+        """Entries dt * sum_{c in ECS} (M_c f_e)|_p of the right-hand side for the owned extracellular dofs (the local mesh
+        holds every cell that touches an owned vertex)."""
+        from .partition import Layout
+        m, ctx = self.mesh, self._ctx
+        d = m.gdim
+        n_owned = m.x.shape[0] if m.n_owned is None else m.n_owned
+        lay = Layout(self._node_vert, n_owned)
+        node_of = np.full(m.x.shape[0], -1, np.int64)
+        node_of[self._node_vert[1]] = np.arange(self._node_vert[1].size)
+        cells = m.cells[m.cell_tags == self.extra_tag[0]]
+        w = self._cell_volumes(cells) / ((d + 1) * (d + 2))
+        rows, vals = [], []
+        for k, ion in enumerate(self.ion_list):
+            f = ion["f_e"]
+            if not isinstance(f, Function) or not f._data.any():
+                continue
+            fc = f._data[cells]                                              # (nc, d+1)
+            contrib = w[:, None] * (fc + fc.sum(axis=1, keepdims=True))     # M_c f = vol/((d+1)(d+2)) (f_p + sum_q f_q)
+            sv = np.bincount(cells.ravel(), weights=contrib.ravel(), minlength=m.x.shape[0]) * float(self.dt.value)
+            nodes = node_of[np.flatnonzero(sv)]
+            nodes = nodes[(nodes >= 0) & (nodes < lay.n_own[1])]
+            rows.append(lay.col(1, k, nodes))
+            vals.append(sv[self._node_vert[1][nodes]])
+        if rows:
+            ctx.set_source(np.concatenate(rows), np.concatenate(vals))
 
     # ------------------------------------------------------------------ initial conditions
     def set_initial_conditions(self):
@@ -545,6 +605,8 @@ class ProblemKNPEMI:
             init_halo(self, ctx)
         self._upload_params()
         self._push_state()
+        if self.source_terms == "ion_injection":
+            self._upload_source()
         if self.point_evaluation:
             self._setup_probes()
         self.a = self.L = "device-resident forms (csrc/assembly.cu)"

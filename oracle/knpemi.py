@@ -68,6 +68,9 @@ class OracleParams:
     stimulus_region: tuple = None      # (direction, lo, hi), a tuple of such triples (`multiple` directions), or None
     ode_substeps: int = 25
     rush_larsen: bool = True
+    # "ion_injection": K+ / Cl- source in the extracellular space around the mesh centre (KNPEMIx_problem.py:200-218)
+    source_terms: str = None
+    injection_current: float = 5e-9
 
     @property
     def psi(self):
@@ -121,6 +124,9 @@ class KNPEMIOracle:
         self.t = 0.0
         self.set_initial_conditions()
         self._pattern = None
+        self.f_e = [np.zeros(nv) for _ in range(3)]             # source functions f_e of the ions (ion['f_e'], :771-800)
+        if p.source_terms == "ion_injection":
+            self.setup_ion_injection()
 
     # ------------------------------------------------------------------ setup
     def row(self, s, f, verts):
@@ -322,6 +328,22 @@ class KNPEMIOracle:
         bphi = np.einsum("fq,fq,qa->fa", wq, (p.dt * Itot - p.C_M * phim), self.qb) / p.F
         return GA, G1, bc, bphi
 
+    def setup_ion_injection(self):
+        """Injection site = cells with every vertex inside the cube of half-width (x_max - x_min)/10 around the centre of
+        the bounding box (utils/mixed_dim_problem.py:496-540,806-811); f_e of K and Cl = I / (F vol) on all vertices of those
+        cells (KNPEMIx_problem.py:200-218).  The form integrates f_e over the extracellular cells only (:614)."""
+        m, p = self.mesh, self.p
+        lo, hi = m.x.min(axis=0), m.x.max(axis=0)
+        centre, delta, tol = 0.5 * (lo + hi), (hi[0] - lo[0]) / 10.0, 1e-14
+        inside = np.all((m.x >= centre - delta - tol) & (m.x <= centre + delta + tol), axis=1)
+        self.injection_cells = np.flatnonzero(inside[m.cells].all(axis=1))
+        vol = self._cell_geometry(m.cells[self.injection_cells])["vol"]
+        self.injection_volume = float(vol.sum())
+        src = (p.injection_current / p.F) / self.injection_volume
+        verts = np.unique(m.cells[self.injection_cells].ravel())
+        self.f_e[1][verts] = src
+        self.f_e[2][verts] = src
+
     def assemble(self, t):
         """Returns (A csr with sorted indices and explicit zeros kept, b)."""
         p, m = self.p, self.mesh
@@ -351,6 +373,8 @@ class KNPEMIOracle:
                 add(Rphi[:, :, None], Rk[:, None, :], (p.dt * p.z[k] * p.D[k]) * K)
                 Kphi = Kphi + (p.dt * p.D[k] * p.z[k] ** 2 / psi) * cbar[k][:, None, None] * K
                 np.add.at(b, Rk.ravel(), np.einsum("cab,cb->ca", M, cv[k]).ravel())
+                if s == 1 and self.f_e[k].any():                          # L += dt f_e v dx_e  (KNPEMIx_problem.py:614)
+                    np.add.at(b, Rk.ravel(), p.dt * np.einsum("cab,cb->ca", M, self.f_e[k][cells]).ravel())
             add(Rphi[:, :, None], Rphi[:, None, :], Kphi)
 
         GA, G1, bc, bphi = self.facet_tensors(t_mod)

@@ -734,3 +734,62 @@ def test_cg_matches_cpu_pcg_on_spd_operator(kb, pc):
     with pytest.raises(kb.lib.KnpError, match="breakdown"):
         ctx.solve(opts, A_ptr=Ad2.data_ptr(), b_ptr=bd.data_ptr(), x_ptr=xd.data_ptr())
     ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------- ion injection
+@pytest.mark.parametrize("d3", [False, True], ids=["2d", "3d"])
+def test_ion_injection_source_matches_oracle(kb, cfgdir, d3):
+    """source_terms: "ion_injection" (KNPEMIx_problem.py:200-218,613-614) through the reference-facing classes: injection
+    volume, the assembled right-hand side (1e-12 of its largest entry) and two timesteps of K_e / Cl_e norms against the
+    oracle (1e-8)."""
+    import tempfile
+    src = "c4_cube120_cells64_passive.yaml" if d3 else "c3_square2048_cells64.yaml"
+    txt = open(os.path.join(cfgdir, src)).read().replace("N: 120" if d3 else "N: 2048", "N: 10" if d3 else "N: 40")
+    txt = txt.replace("cells_per_dim: 4" if d3 else "cells_per_dim: 8", "cells_per_dim: 2")
+    txt = txt.replace("!range [2, 66]", "!range [2, 10]" if d3 else "!range [2, 6]")
+    txt = txt.replace("ksp_rtol: 1.0e-9", "ksp_rtol: 1.0e-12") + '\nsource_terms: "ion_injection"\n'
+    with tempfile.NamedTemporaryFile("w", suffix=".yaml", delete=False) as fh:
+        fh.write(txt)
+    p = kb.ProblemKNPEMI(fh.name, verbose=False)
+    os.unlink(fh.name)
+    p.set_initial_conditions()
+    models = [("Passive", None)] if d3 else MODELS_TEST
+    p.init_ionic_models([kb.PassiveModel(p)] if d3 else [kb.NeuronalCotransporters(p), kb.HodgkinHuxley(p), kb.ATPPump(p)])
+    p.setup_variational_form()
+    m = p.mesh
+    om = from_arrays(m.gdim, m.x, m.cells, m.cell_tags, m.intra_tags)
+    it = tuple(m.intra_tags)
+    op = OracleParams(intra_tags=it, extra_tag=1, membrane_tags=it, stimulus_tags=(2,) if not d3 else it,
+                      source_terms="ion_injection")
+    o = KNPEMIOracle(om, op, models)
+    if not d3:                                       # configs/c3_*.yaml initial_perturbation
+        X = om.x / 1e-6
+        fac = 1 + 0.01 * np.sin(2 * np.pi * X[:, 0]) * np.sin(2 * np.pi * X[:, 1])
+        for sd in range(2):
+            o.c[sd] *= fac[None, :]
+        dphi = 0.005 * np.cos(2 * np.pi * X[:, 0])
+        o.phi_m += dphi
+        o.phi[0] += dphi
+    assert o.injection_cells.size > 0 and np.array_equal(p.injection_cells, o.injection_cells)
+    assert abs(p.injection_volume - o.injection_volume) <= 1e-14 * o.injection_volume
+    ctx = p._ctx
+    ctx.assemble(op.dt)
+    _, b, _ = ctx.values_host()
+    _, b_ref = o.assemble(op.dt)
+    o0 = KNPEMIOracle(om, OracleParams(intra_tags=it, extra_tag=1, membrane_tags=it, stimulus_tags=op.stimulus_tags), models)
+    o0.c, o0.phi, o0.phi_m, o0.gates = o.c, o.phi, o.phi_m, o.gates
+    _, b_nosrc = o0.assemble(op.dt)
+    assert np.abs(b_ref - b_nosrc).max() > 0                     # the source is there ...
+    assert np.abs(b - b_ref).max() <= 1e-12 * np.abs(b_ref).max()   # ... and the device adds the same entries
+    p.solver_config["view_ksp"] = False
+    s = kb.SolverKNPEMI(p, solver_config=p.solver_config)
+    s.setup_solver(); p.setup_preconditioner(True); s.ctx.pc_setup(s.opts); s.ctx.set_time(0.0, 0)
+    pc = SchurPC(o, exact=True)
+    x = o.pack()
+    for i in range(2):
+        s.ctx.step(s.opts); p._mark_device_newer()
+        _, _, x, _ = o.step("gmres", pc, 1e-12, x, first=(i == 0))
+        for f in (1, 2):
+            ref, got = o.l2_norm(o.c[1][f], [1]), p.l2_norm(p.wh[1][f], [1])
+            assert abs(got - ref) <= 1e-8 * ref, (i, f, got, ref)
+    s.ctx.close()
