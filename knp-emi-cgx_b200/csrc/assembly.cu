@@ -818,283 +818,347 @@ int launch_facets(const DevTopo& T, const KParams& P, const uint32_t* tag_models
 // (tile base << LG) + thread id: fully coalesced, no row-pointer lookup first).  Fixed summation order, no atomics:
 // bitwise reproducible.  Membrane terms, row formation, TMA bulk stores and the right-hand side are those of the scan kernel.
 #ifndef EDGE_MIN_CTAS
-#define EDGE_MIN_CTAS 4
+#define EDGE_MIN_CTAS 3
 #endif
 #ifndef EDGE_MIN_CTAS_3D
-#define EDGE_MIN_CTAS_3D 3      // the 3D cell formulas need ~80 registers; 4 CTAs per SM would spill
+#define EDGE_MIN_CTAS_3D 2      // the 3D cell formulas plus the prefetched tables need ~100 registers
 #endif
 constexpr int EDGE_NB = 6;      // doubles per staged neighbour: 2D {x, y, c0, c1, c2, -}, 3D {x, y, z, c0, c1, c2} (16-byte units)
+
+// The kernel is PERSISTENT, software-pipelined and WARP-AUTONOMOUS.  A lane group never spans warps (G <= 32), so a warp
+// owns a mini-tile of 32 / G consecutive dofs with its own neighbour buffers and staging strip in shared memory and
+// needs no CTA-wide barrier at all: the warps of the grid walk over mini-tiles w, w + W, w + 2W, ... independently.  While
+// mini-tile i is computed, the neighbour data of mini-tile i + 1 streams into the warp's second buffer with cp.async
+// (LDGSTS: global -> shared without passing through registers) and the lane-group tables of mini-tile i + 2 are on their
+// way into registers, so neither level of the index -> neighbour load chain is on the critical path, and the finished rows
+// leave through per-warp TMA bulk stores.  (Round-2 profiles: the one-shot CTA form spent 35 % of its stall samples on
+// those two loads; the persistent CTA form that hid them spent 22-28 % on the two CTA barriers per tile instead.)
+__device__ __forceinline__ void cp_async8(void* sdst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
+}
+
+template <int D>
+struct EdgeTables {      // what one lane holds of a tile before the tile is computed
+  int q;                 // neighbour node of (dof, slot), -1: none
+  uint32_t hit[D == 2 ? 1 : 4];
+  int2 meta;
+  int rs_a, rs_b;        // CSR row start of (field e, dof lw) for e < 4, and the end of the tile's last row (dof nt - 1)
+};
 
 template <int D, int MODE, int LG>
 __global__ void __launch_bounds__(ROWS_THREADS, D == 3 ? EDGE_MIN_CTAS_3D : EDGE_MIN_CTAS) rows_edge_kernel(DevTopo T, RowCoef C, const double* __restrict__ u,
                                                                                 const double* __restrict__ fe,
                                                                                 double* __restrict__ vals, double* __restrict__ bvec,
-                                                                                int ntile0, int off_rs) {
-  constexpr int G = 1 << LG, TILE = ROWS_THREADS / G;
+                                                                                int ntile0, int ntiles, int stg_doubles) {
+  constexpr int G = 1 << LG, TILE = 32 / G;                                      // dofs per warp (mini-tile)
   constexpr int NS = D * (D + 1) / 2;
   constexpr int NB = EDGE_NB;
+  constexpr int HW = D == 2 ? 1 : 4;
   constexpr uint32_t FMASK = D == 3 ? 0x00FFFFFFu : 0x0000FFFFu;
   extern __shared__ __align__(16) unsigned char smraw[];
-  double* nbr = reinterpret_cast<double*>(smraw);                // [ROWS_THREADS][NB]
-  double* stg = nbr;                                             // alias: the neighbour block is dead by phase 3
-  int* rstart = reinterpret_cast<int*>(smraw + off_rs);          // [4][TILE + 1] CSR row starts of the tile's rows
-
-  const int tid = threadIdx.x;
+  const int wid = threadIdx.x >> 5, tid = threadIdx.x & 31;                      // warp in the CTA, lane
+  double* nbr2 = reinterpret_cast<double*>(smraw) + (size_t)wid * (2 * 32 * NB + stg_doubles);   // [2][32][NB] of this warp
+  double* stg = nbr2 + 2 * 32 * NB;                                              // staging strip of the warp's rows
   const int lw = tid >> LG, e = tid & (G - 1);
-  const int s = blockIdx.x >= ntile0 ? 1 : 0;
-  const int p0 = (blockIdx.x - (s ? ntile0 : 0)) * TILE;
-  const int n_own_s = T.L.n_own[s];
-  const int nt = min(TILE, n_own_s - p0);
-  const int w0 = (s ? T.L.n_own[0] : 0) + p0;
-  const int nodeoff = s ? T.L.n_loc[0] : 0;
   const int* __restrict__ iptr = MODE == 0 ? T.indptr : T.indptr_P;
-  const bool node_ok = lw < nt;
+  const int stride = gridDim.x * (ROWS_THREADS / 32);                            // warps in the grid
 
-  // ---- phase 1: tables (coalesced), then one gather per (dof, slot) into registers and shared memory ----
-  int q = -1;
-  int2 meta = make_int2(0, -1);
-  uint32_t hit[D == 2 ? 1 : 4];
+  auto load_tables = [&](int t, EdgeTables<D>& E) {
+    E.q = -1;
+    E.meta = make_int2(0, -1);
+    E.rs_a = E.rs_b = 0;
 #pragma unroll
-  for (int i = 0; i < (D == 2 ? 1 : 4); ++i) hit[i] = 0xFFFFFFFFu;
-  if (node_ok) {
-    const size_t at = ((size_t)w0 << LG) + tid;
-    q = T.adjG[at];
-    meta = T.metaG[w0 + lw];
-    if (D == 2) {
-      hit[0] = T.hitG[at];
-    } else {
-      const uint4 h4 = reinterpret_cast<const uint4*>(T.hitG)[at];
-      hit[0] = h4.x;
-      hit[D == 2 ? 0 : 1] = h4.y;
-      hit[D == 2 ? 0 : 2] = h4.z;
-      hit[D == 2 ? 0 : 3] = h4.w;
+    for (int i = 0; i < HW; ++i) E.hit[i] = 0xFFFFFFFFu;
+    if (t >= ntiles) return;
+    const int s = t >= ntile0 ? 1 : 0;
+    const int p0 = (t - (s ? ntile0 : 0)) * TILE;
+    const int nt = min(TILE, T.L.n_own[s] - p0);
+    const int w0 = (s ? T.L.n_own[0] : 0) + p0;
+    if (lw < nt) {
+      const size_t at = ((size_t)w0 << LG) + tid;
+      E.q = T.adjG[at];
+      E.meta = T.metaG[w0 + lw];
+      if (D == 2) {
+        E.hit[0] = T.hitG[at];
+      } else {
+        const uint4 h4 = reinterpret_cast<const uint4*>(T.hitG)[at];
+        E.hit[0] = h4.x;
+        E.hit[HW - 3 > 0 ? 1 : 0] = h4.y;
+        E.hit[HW - 2 > 0 ? 2 : 0] = h4.z;
+        E.hit[HW - 1 > 0 ? 3 : 0] = h4.w;
+      }
+      if (e < 4) {
+        E.rs_a = iptr[T.L.row(s, e, p0 + lw)];
+        if (lw == nt - 1) E.rs_b = iptr[T.L.row(s, e, p0 + nt)];
+      }
     }
-    if (e < 4) {
-      rstart[e * (TILE + 1) + lw] = iptr[T.L.row(s, e, p0 + lw)];
-      if (lw == nt - 1) rstart[e * (TILE + 1) + nt] = iptr[T.L.row(s, e, p0 + nt)];
+  };
+  // neighbour (s, q) of tile t -> this lane's entry of the given buffer, asynchronously
+  auto gather = [&](int t, int q, double* buf) {
+    if (q >= 0) {
+      const int s = t >= ntile0 ? 1 : 0;
+      const int n_own_s = T.L.n_own[s];
+      const int nodeoff = s ? T.L.n_loc[0] : 0;
+      double* o = buf + (size_t)tid * NB;
+      const double* __restrict__ xs = T.node_x + (size_t)(nodeoff + q) * D;
+      const double* __restrict__ uc = q < n_own_s ? u + T.L.rowbase[s] + q : u + T.L.n_rows + T.L.gbase[s] + (q - n_own_s);
+      const size_t fstride = q < n_own_s ? n_own_s : T.L.n_gh[s];
+      if (D == 2) {
+        cp_async16(o, xs);
+      } else {
+        cp_async8(o, xs);
+        cp_async8(o + 1, xs + 1);
+        cp_async8(o + 2, xs + 2);
+      }
+      cp_async8(o + D, uc);
+      cp_async8(o + D + 1, uc + fstride);
+      cp_async8(o + D + 2, uc + 2 * fstride);
     }
-  }
-  const int deg = meta.x & 255, self = (meta.x >> 8) & 255;
-  const int gdeg = MODE == 0 ? (meta.x >> 16) & 255 : 0;
-  const int g = meta.y;
-  const bool has_ent = q >= 0;
-  double xq[3] = {0.0, 0.0, 0.0}, ce[3] = {0.0, 0.0, 0.0};
-  if (has_ent) {
-#pragma unroll
-    for (int i = 0; i < D; ++i) xq[i] = T.node_x[(size_t)(nodeoff + q) * D + i];
-    const double* __restrict__ uc = q < n_own_s ? u + T.L.rowbase[s] + q : u + T.L.n_rows + T.L.gbase[s] + (q - n_own_s);
-    const int fstride = q < n_own_s ? n_own_s : T.L.n_gh[s];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) ce[k] = uc[(size_t)k * fstride];
-    double2* o = reinterpret_cast<double2*>(nbr + (size_t)tid * NB);
-    if (D == 2) {
-      o[0] = make_double2(xq[0], xq[1]);
-      o[1] = make_double2(ce[0], ce[1]);
-      o[2] = make_double2(ce[2], 0.0);
-    } else {
-      o[0] = make_double2(xq[0], xq[1]);
-      o[1] = make_double2(xq[2], ce[0]);
-      o[2] = make_double2(ce[1], ce[2]);
-    }
-  }
-  __syncthreads();
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
 
-  // ---- phase 2: the lane's five sums over the cells around its edge, ascending cell order ----
-  double a_m = 0.0, a_kk = 0.0, X[3] = {0.0, 0.0, 0.0}, kphi_m[3] = {0.0, 0.0, 0.0}, pp_m = 0.0;
-  double bmem[4] = {0.0, 0.0, 0.0, 0.0};
-  double ga[3] = {0.0, 0.0, 0.0}, g1 = 0.0;
-  const bool is_self = has_ent && e == self;
-  const bool has_gam = MODE == 0 && node_ok && e < gdeg;
-  const uint32_t rep = (uint32_t)e * 0x01010101u;
-  const double* grp = nbr + (size_t)(lw << LG) * NB;              // the dof's neighbour block
-  if (has_ent && !is_self) {
-    const double2* pn = reinterpret_cast<const double2*>(grp + (size_t)self * NB);
-    if (D == 2) {
-      const double2 xp = pn[0], c01 = pn[1];
-      const double c2 = pn[2].x;
-      const double s0 = c01.x + ce[0], s1 = c01.y + ce[1], s2 = c2 + ce[2];
+  int t = blockIdx.x * (ROWS_THREADS / 32) + wid;
+  EdgeTables<D> cur, nxt;
+  load_tables(t, cur);
+  gather(t, cur.q, nbr2);
+  load_tables(t + stride, nxt);
+
+  for (int it = 0; t < ntiles; t += stride, ++it) {
+    double* nbr = nbr2 + (size_t)(it & 1) * 32 * NB;
+    const int s = t >= ntile0 ? 1 : 0;
+    const int p0 = (t - (s ? ntile0 : 0)) * TILE;
+    const int nt = min(TILE, T.L.n_own[s] - p0);
+    const bool node_ok = lw < nt;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");                 // this lane's neighbour entry of the tile has landed
+    if (tid < 4 && it > 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the staging strip is free again
+    __syncwarp();
+    // ---- prefetch: neighbour data of the next mini-tile, tables of the one after it ----
+    gather(t + stride, nxt.q, nbr2 + (size_t)((it + 1) & 1) * 32 * NB);
+    EdgeTables<D> nn;
+    load_tables(t + 2 * stride, nn);
+
+    const int deg = cur.meta.x & 255, self = (cur.meta.x >> 8) & 255;
+    const int gdeg = MODE == 0 ? (cur.meta.x >> 16) & 255 : 0;
+    const int g = cur.meta.y;
+    const bool has_ent = cur.q >= 0;
+
+    // ---- phase 2: the lane's five sums over the cells around its edge, ascending cell order ----
+    double a_m = 0.0, a_kk = 0.0, X[3] = {0.0, 0.0, 0.0}, kphi_m[3] = {0.0, 0.0, 0.0}, pp_m = 0.0;
+    double bmem[4] = {0.0, 0.0, 0.0, 0.0};
+    double ga[3] = {0.0, 0.0, 0.0}, g1 = 0.0;
+    double ce[3] = {0.0, 0.0, 0.0};
+    const bool is_self = has_ent && e == self;
+    const bool has_gam = MODE == 0 && node_ok && e < gdeg;
+    const uint32_t rep = (uint32_t)e * 0x01010101u;
+    const double* grp = nbr + (size_t)(lw << LG) * NB;              // the dof's neighbour block
+    if (has_ent) {
+      const double2* qn = reinterpret_cast<const double2*>(nbr + (size_t)tid * NB);
+      const double2* pn = reinterpret_cast<const double2*>(grp + (size_t)self * NB);
+      if (D == 2) {
+        const double2 xq = qn[0], q01 = qn[1];
+        ce[0] = q01.x;
+        ce[1] = q01.y;
+        ce[2] = qn[2].x;
+        if (!is_self) {
+          const double2 xp = pn[0], c01 = pn[1];
+          const double s0 = c01.x + ce[0], s1 = c01.y + ce[1], s2 = pn[2].x + ce[2];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const uint32_t sl = (hit[0] >> (8 * h)) & 255u;
-        if (sl != 255u) {
-          const double2* rn = reinterpret_cast<const double2*>(grp + (size_t)sl * NB);
-          const double2 xr = rn[0], r01 = rn[1];
-          const double r2 = rn[2].x;
-          const double e1x = xp.x - xr.x, e1y = xp.y - xr.y, e2x = xq[0] - xr.x, e2y = xq[1] - xr.y;
-          const double cr = fabs(e1x * e2y - e1y * e2x);
-          const double dt = e1x * e2x + e1y * e2y;
-          const double kab = -0.5 * dt * (1.0 / cr);
-          a_m += cr * (1.0 / 24.0);
-          a_kk += kab;
-          X[0] += ((s0 + r01.x) * (1.0 / 3.0)) * kab;
-          X[1] += ((s1 + r01.y) * (1.0 / 3.0)) * kab;
-          X[2] += ((s2 + r2) * (1.0 / 3.0)) * kab;
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t sl = (cur.hit[0] >> (8 * h)) & 255u;
+            if (sl != 255u) {
+              const double2* rn = reinterpret_cast<const double2*>(grp + (size_t)sl * NB);
+              const double2 xr = rn[0], r01 = rn[1];
+              const double r2 = rn[2].x;
+              const double e1x = xp.x - xr.x, e1y = xp.y - xr.y, e2x = xq.x - xr.x, e2y = xq.y - xr.y;
+              const double cr = fabs(e1x * e2y - e1y * e2x);
+              const double dt = e1x * e2x + e1y * e2y;
+              const double kab = -0.5 * dt * (1.0 / cr);
+              a_m += cr * (1.0 / 24.0);
+              a_kk += kab;
+              X[0] += ((s0 + r01.x) * (1.0 / 3.0)) * kab;
+              X[1] += ((s1 + r01.y) * (1.0 / 3.0)) * kab;
+              X[2] += ((s2 + r2) * (1.0 / 3.0)) * kab;
+            }
+          }
+        }
+      } else {
+        const double2 q01 = qn[0], q23 = qn[1], q45 = qn[2];          // {x, y} {z, c0} {c1, c2}
+        ce[0] = q23.y;
+        ce[1] = q45.x;
+        ce[2] = q45.y;
+        if (!is_self) {
+          const double2 p01 = pn[0], p23 = pn[1], p45 = pn[2];
+          const double ax = q01.x - p01.x, ay = q01.y - p01.y, az = q23.x - p23.x;
+          const double s0 = p23.y + ce[0], s1 = p45.x + ce[1], s2 = p45.y + ce[2];
+#pragma unroll 2
+          for (int h = 0; h < 8; ++h) {
+            const uint32_t wv = (h >> 1) == 0 ? cur.hit[0] : (h >> 1) == 1 ? cur.hit[HW - 3 > 0 ? 1 : 0]
+                              : (h >> 1) == 2 ? cur.hit[HW - 2 > 0 ? 2 : 0] : cur.hit[HW - 1 > 0 ? 3 : 0];
+            const uint32_t code = (wv >> (16 * (h & 1))) & 0xFFFFu;
+            if (code == 0xFFFFu) break;
+            const double2* rn = reinterpret_cast<const double2*>(grp + (size_t)(code & 255u) * NB);
+            const double2* sn = reinterpret_cast<const double2*>(grp + (size_t)(code >> 8) * NB);
+            const double2 r01 = rn[0], r23 = rn[1], r45 = rn[2];
+            const double2 t01 = sn[0], t23 = sn[1], t45 = sn[2];
+            const double bx = r01.x - p01.x, by = r01.y - p01.y, bz = r23.x - p23.x;
+            const double cx = t01.x - p01.x, cy = t01.y - p01.y, cz = t23.x - p23.x;
+            const double nqx = by * cz - bz * cy, nqy = bz * cx - bx * cz, nqz = bx * cy - by * cx;      // (r - p) x (s - p)
+            const double J = fabs(ax * nqx + ay * nqy + az * nqz);
+            const double ux = bx - ax, uy = by - ay, uz = bz - az, vx = cx - ax, vy = cy - ay, vz = cz - az;
+            const double npx = uy * vz - uz * vy, npy = uz * vx - ux * vz, npz = ux * vy - uy * vx;      // (r - q) x (s - q)
+            const double kab = -(npx * nqx + npy * nqy + npz * nqz) * (1.0 / (6.0 * J));
+            a_m += J * (1.0 / 120.0);
+            a_kk += kab;
+            X[0] += ((s0 + r23.y + t23.y) * 0.25) * kab;
+            X[1] += ((s1 + r45.x + t45.x) * 0.25) * kab;
+            X[2] += ((s2 + r45.y + t45.y) * 0.25) * kab;
+          }
         }
       }
-    } else {
-      const double2 p01 = pn[0], p23 = pn[1], p45 = pn[2];       // {x, y} {z, c0} {c1, c2}
-      const double ax = xq[0] - p01.x, ay = xq[1] - p01.y, az = xq[2] - p23.x;
-      const double s0 = p23.y + ce[0], s1 = p45.x + ce[1], s2 = p45.y + ce[2];
-#pragma unroll 2
-      for (int h = 0; h < 8; ++h) {
-        const uint32_t wv = (h >> 1) == 0 ? hit[0] : (h >> 1) == 1 ? hit[D == 2 ? 0 : 1] : (h >> 1) == 2 ? hit[D == 2 ? 0 : 2] : hit[D == 2 ? 0 : 3];
-        const uint32_t code = (wv >> (16 * (h & 1))) & 0xFFFFu;
-        if (code == 0xFFFFu) break;
-        const double2* rn = reinterpret_cast<const double2*>(grp + (size_t)(code & 255u) * NB);
-        const double2* sn = reinterpret_cast<const double2*>(grp + (size_t)(code >> 8) * NB);
-        const double2 r01 = rn[0], r23 = rn[1], r45 = rn[2];
-        const double2 t01 = sn[0], t23 = sn[1], t45 = sn[2];
-        const double bx = r01.x - p01.x, by = r01.y - p01.y, bz = r23.x - p23.x;
-        const double cx = t01.x - p01.x, cy = t01.y - p01.y, cz = t23.x - p23.x;
-        const double nqx = by * cz - bz * cy, nqy = bz * cx - bx * cz, nqz = bx * cy - by * cx;      // (r - p) x (s - p)
-        const double J = fabs(ax * nqx + ay * nqy + az * nqz);
-        const double ux = bx - ax, uy = by - ay, uz = bz - az, vx = cx - ax, vy = cy - ay, vz = cz - az;
-        const double npx = uy * vz - uz * vy, npy = uz * vx - ux * vz, npz = ux * vy - uy * vx;      // (r - q) x (s - q)
-        const double kab = -(npx * nqx + npy * nqy + npz * nqz) * (1.0 / (6.0 * J));
-        a_m += J * (1.0 / 120.0);
-        a_kk += kab;
-        X[0] += ((s0 + r23.y + t23.y) * 0.25) * kab;
-        X[1] += ((s1 + r45.x + t45.x) * 0.25) * kab;
-        X[2] += ((s2 + r45.y + t45.y) * 0.25) * kab;
+    }
+    {
+      // self slot: K_pp = -sum_q K_pq, (cbar K)_pp = -sum_q (cbar K)_pq, and 2 sum_c |c|/((d+1)(d+2)) = (2/d) sum_q M_pq
+      double ts[5] = {a_m, a_kk, X[0], X[1], X[2]};
+#pragma unroll
+      for (int off = G >> 1; off > 0; off >>= 1) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) ts[i] += __shfl_xor_sync(0xffffffffu, ts[i], off);
+      }
+      if (is_self) {
+        a_m = ts[0] * (2.0 / D);
+        a_kk = -ts[1];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) X[k] = -ts[2 + k];
       }
     }
-  }
-  {
-    // self slot: K_pp = -sum_q K_pq, (cbar K)_pp = -sum_q (cbar K)_pq, and 2 sum_c |c|/((d+1)(d+2)) = (2/d) sum_q M_pq
-    double t[5] = {a_m, a_kk, X[0], X[1], X[2]};
+    // membrane (dS) terms: KNPEMIx_problem.py:599,604,609-610,637-638,641-642 (P: :737-738); lane e serves adjacency
+    // slot e and gamma slot e (couplings to the potential on the other side of the membrane)
+    if (g >= 0 && (has_ent || has_gam)) {
+      const size_t nf = (size_t)T.n_mf;
+      const double sgn = s == 0 ? 1.0 : -1.0;
+      const int m1 = T.minc_ptr[g + 1];
+      for (int mi = T.minc_ptr[g]; mi < m1; ++mi) {
+        const uint4 rec = reinterpret_cast<const uint4*>(T.minc)[mi];
+        const int f = (int)rec.x;
+        const int a = rec.y & 255u;
+        const uint32_t ss = s == 0 ? (rec.y >> 8) : rec.z;
+        const uint32_t ms = has_ent ? (__vcmpeq4(ss, rep) & FMASK) : 0u;
+        const uint32_t mg = has_gam ? (__vcmpeq4(rec.w, rep) & FMASK) : 0u;
+        if (ms) {
+          const int b = (__ffs(ms) - 1) >> 3;
+          const double G1 = T.mf_area[f] * ((a == b) ? 2.0 : 1.0) * (1.0 / (D * (D + 1)));
+          if (MODE == 0) {
+            const int ab = a <= b ? symidx(a, b, D) : symidx(b, a, D);
 #pragma unroll
-    for (int off = G >> 1; off > 0; off >>= 1) {
-#pragma unroll
-      for (int i = 0; i < 5; ++i) t[i] += __shfl_xor_sync(0xffffffffu, t[i], off);
-    }
-    if (is_self) {
-      a_m = t[0] * (2.0 / D);
-      a_kk = -t[1];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) X[k] = -t[2 + k];
-    }
-  }
-  // membrane (dS) terms: KNPEMIx_problem.py:599,604,609-610,637-638,641-642 (P: :737-738); lane e serves adjacency
-  // slot e and gamma slot e (couplings to the potential on the other side of the membrane)
-  if (g >= 0 && (has_ent || has_gam)) {
-    const size_t nf = (size_t)T.n_mf;
-    const double sgn = s == 0 ? 1.0 : -1.0;
-    const int m1 = T.minc_ptr[g + 1];
-    for (int mi = T.minc_ptr[g]; mi < m1; ++mi) {
-      const uint4 rec = reinterpret_cast<const uint4*>(T.minc)[mi];
-      const int f = (int)rec.x;
-      const int a = rec.y & 255u;
-      const uint32_t ss = s == 0 ? (rec.y >> 8) : rec.z;
-      const uint32_t ms = has_ent ? (__vcmpeq4(ss, rep) & FMASK) : 0u;
-      const uint32_t mg = has_gam ? (__vcmpeq4(rec.w, rep) & FMASK) : 0u;
-      if (ms) {
-        const int b = (__ffs(ms) - 1) >> 3;
-        const double G1 = T.mf_area[f] * ((a == b) ? 2.0 : 1.0) * (1.0 / (D * (D + 1)));
-        if (MODE == 0) {
+            for (int k = 0; k < 3; ++k) kphi_m[k] += C.cmz[k] * fe[(size_t)((s * 3 + k) * NS + ab) * nf + f];
+            pp_m += C.cf * G1;
+          } else {
+            pp_m -= C.cf * G1;
+          }
+        }
+        if (MODE == 0 && mg) {
+          const int b = (__ffs(mg) - 1) >> 3;
           const int ab = a <= b ? symidx(a, b, D) : symidx(b, a, D);
 #pragma unroll
-          for (int k = 0; k < 3; ++k) kphi_m[k] += C.cmz[k] * fe[(size_t)((s * 3 + k) * NS + ab) * nf + f];
-          pp_m += C.cf * G1;
-        } else {
-          pp_m -= C.cf * G1;
+          for (int k = 0; k < 3; ++k) ga[k] += C.cmz[k] * fe[(size_t)((s * 3 + k) * NS + ab) * nf + f];
+          g1 += C.cf * (T.mf_area[f] * ((a == b) ? 2.0 : 1.0) * (1.0 / (D * (D + 1))));
+        }
+        if (MODE == 0 && is_self) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) bmem[k] -= sgn * fe[(size_t)(6 * NS + (s * 3 + k) * D + a) * nf + f];
+          bmem[3] -= sgn * fe[(size_t)(6 * NS + 6 * D + a) * nf + f];
         }
       }
-      if (MODE == 0 && mg) {
-        const int b = (__ffs(mg) - 1) >> 3;
-        const int ab = a <= b ? symidx(a, b, D) : symidx(b, a, D);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) ga[k] += C.cmz[k] * fe[(size_t)((s * 3 + k) * NS + ab) * nf + f];
-        g1 += C.cf * (T.mf_area[f] * ((a == b) ? 2.0 : 1.0) * (1.0 / (D * (D + 1))));
-      }
-      if (MODE == 0 && is_self) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) bmem[k] -= sgn * fe[(size_t)(6 * NS + (s * 3 + k) * D + a) * nf + f];
-        bmem[3] -= sgn * fe[(size_t)(6 * NS + 6 * D + a) * nf + f];
-      }
     }
-  }
-  __syncthreads();          // the neighbour block is dead: the staging strip may overwrite it
 
-  // ---- phase 3: form the ten block rows at their CSR-relative offsets of the staging strip ----
-  int so[4], base[4], total[4];
-  {
-    int acc = 0;
+    // ---- phase 3: form the ten block rows at their CSR-relative offsets of the staging strip ----
+    // CSR row starts of the mini-tile's rows travel by shuffle from the lanes that loaded them (lane (dof, field))
+    int so[4], base[4], total[4], rsf4[4];
+    {
+      int acc = 0;
 #pragma unroll
-    for (int f = 0; f < 4; ++f) {
-      base[f] = rstart[f * (TILE + 1)];
-      total[f] = rstart[f * (TILE + 1) + nt] - base[f];
-      so[f] = acc;                                   // even: 16-byte aligned start of the field's strip
-      acc += (total[f] + 3) & ~1;                    // room for the phase shift (base & 1), rounded to even
+      for (int f = 0; f < 4; ++f) {
+        base[f] = __shfl_sync(0xffffffffu, cur.rs_a, f);
+        total[f] = __shfl_sync(0xffffffffu, cur.rs_b, ((nt - 1) << LG) + f) - base[f];
+        rsf4[f] = __shfl_sync(0xffffffffu, cur.rs_a, (lw << LG) + f) - base[f];
+        so[f] = acc;                                   // even: 16-byte aligned start of the field's strip
+        acc += (total[f] + 3) & ~1;                    // room for the phase shift (base & 1), rounded to even
+      }
     }
-  }
-  if (node_ok) {
-    const int goff = s == 1 ? gdeg : 0;
+    if (node_ok) {
+      const int goff = s == 1 ? gdeg : 0;
 #pragma unroll
-    for (int f = 0; f < 4; ++f) {
-      const int rsf = rstart[f * (TILE + 1) + lw] - base[f];
-      double* o = stg + so[f] + (base[f] & 1) + rsf;
-      if (has_ent) {
-        double* oe = o + goff + e;
-        if (MODE == 0) {
-          if (f < 3) {
-            oe[0] = a_m + C.dtD[f] * a_kk;
-            oe[deg] = C.cphi[f] * X[f] + kphi_m[f];
-          } else {
-            double pp = pp_m;
+      for (int f = 0; f < 4; ++f) {
+        const int rsf = rsf4[f];
+        double* o = stg + so[f] + (base[f] & 1) + rsf;
+        if (has_ent) {
+          double* oe = o + goff + e;
+          if (MODE == 0) {
+            if (f < 3) {
+              oe[0] = a_m + C.dtD[f] * a_kk;
+              oe[deg] = C.cphi[f] * X[f] + kphi_m[f];
+            } else {
+              double pp = pp_m;
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-              oe[k * deg] = C.ck[k] * a_kk;
-              pp += C.cpp[k] * X[k];
+              for (int k = 0; k < 3; ++k) {
+                oe[k * deg] = C.ck[k] * a_kk;
+                pp += C.cpp[k] * X[k];
+              }
+              oe[3 * deg] = pp;
             }
-            oe[3 * deg] = pp;
-          }
-        } else {
-          if (f < 3) {
-            oe[0] = a_m + C.dtD[f] * a_kk;
           } else {
-            double pp = pp_m;
+            if (f < 3) {
+              oe[0] = a_m + C.dtD[f] * a_kk;
+            } else {
+              double pp = pp_m;
 #pragma unroll
-            for (int k = 0; k < 3; ++k) pp += C.cpp[k] * X[k];
-            oe[0] = pp;
+              for (int k = 0; k < 3; ++k) pp += C.cpp[k] * X[k];
+              oe[0] = pp;
+            }
           }
         }
+        if (has_gam) o[(s == 1 ? 0 : (f < 3 ? 2 : 4) * deg) + e] = f < 3 ? -ga[f] : -g1;
       }
-      if (has_gam) o[(s == 1 ? 0 : (f < 3 ? 2 : 4) * deg) + e] = f < 3 ? -ga[f] : -g1;
     }
-  }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staging writes -> visible to the TMA (async proxy)
-  __syncthreads();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staging writes -> visible to the TMA (async proxy)
+    __syncwarp();
 
-  // ---- copy-out: one TMA bulk store per field for the 16-byte aligned body, scalar head/tail ----
-  if (tid < 4) {
-    const int f = tid;
-    const int bf = rstart[f * (TILE + 1)], tf = rstart[f * (TILE + 1) + nt] - bf;
-    int sof = 0;
-    for (int ff = 0; ff < f; ++ff) sof += ((rstart[ff * (TILE + 1) + nt] - rstart[ff * (TILE + 1)]) + 3) & ~1;
-    const int sh = bf & 1;
-    const int nbody = (tf - sh) & ~1;
-    if (nbody > 0) bulk_store(vals + (size_t)bf + sh, stg + sof + 2 * sh, (uint32_t)nbody * 8u);
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    if (sh && tf > 0) vals[(size_t)bf] = stg[sof + 1];
-    if ((tf - sh) & 1) vals[(size_t)bf + tf - 1] = stg[sof + sh + tf - 1];
-  }
-  // right-hand side: b_k = sum_e m_e c_k(e) (KNPEMIx_problem.py:613-614,641-642): segmented warp-shuffle reduction over
-  // the dof's lane group (fixed butterfly order -> reproducible)
-  if (MODE == 0) {
-    double bk[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) bk[k] = has_ent ? a_m * ce[k] : 0.0;
-#pragma unroll
-    for (int off = G >> 1; off > 0; off >>= 1) {
-#pragma unroll
-      for (int k = 0; k < 3; ++k) bk[k] += __shfl_xor_sync(0xffffffffu, bk[k], off);
+    // ---- copy-out: one TMA bulk store per field (threads 0..3) for the 16-byte aligned body, scalar head/tail ----
+    if (tid < 4) {
+      const int bf = tid == 0 ? base[0] : tid == 1 ? base[1] : tid == 2 ? base[2] : base[3];
+      const int tf = tid == 0 ? total[0] : tid == 1 ? total[1] : tid == 2 ? total[2] : total[3];
+      const int sof = tid == 0 ? so[0] : tid == 1 ? so[1] : tid == 2 ? so[2] : so[3];
+      const int sh = bf & 1;
+      const int nbody = (tf - sh) & ~1;
+      if (nbody > 0) bulk_store(vals + (size_t)bf + sh, stg + sof + 2 * sh, (uint32_t)nbody * 8u);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      if (sh && tf > 0) vals[(size_t)bf] = stg[sof + 1];
+      if ((tf - sh) & 1) vals[(size_t)bf + tf - 1] = stg[sof + sh + tf - 1];
     }
-    if (is_self) {
+    // right-hand side: b_k = sum_e m_e c_k(e) (KNPEMIx_problem.py:613-614,641-642): segmented warp-shuffle reduction over
+    // the dof's lane group (fixed butterfly order -> reproducible)
+    if (MODE == 0) {
+      double bk[3];
 #pragma unroll
-      for (int k = 0; k < 3; ++k) bvec[T.L.row(s, k, p0 + lw)] = bk[k] + bmem[k];
-      bvec[T.L.row(s, 3, p0 + lw)] = bmem[3];
+      for (int k = 0; k < 3; ++k) bk[k] = has_ent ? a_m * ce[k] : 0.0;
+#pragma unroll
+      for (int off = G >> 1; off > 0; off >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) bk[k] += __shfl_xor_sync(0xffffffffu, bk[k], off);
+      }
+      if (is_self) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) bvec[T.L.row(s, k, p0 + lw)] = bk[k] + bmem[k];
+        bvec[T.L.row(s, 3, p0 + lw)] = bmem[3];
+      }
     }
+    cur = nxt;
+    nxt = nn;
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   if (tid < 4) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
@@ -1166,22 +1230,31 @@ static int launch_rows_t(const DevTopo& T, const KParams& P, const double* u, co
 template <int D, int MODE, int LG>
 static int launch_rows_edge_t(const DevTopo& T, const KParams& P, const double* u, const double* fe, double* vals,
                               double* b, int max_deg, int max_gdeg, cudaStream_t st) {
-  constexpr int TILE = ROWS_THREADS >> LG;
-  const size_t nbr = (size_t)ROWS_THREADS * EDGE_NB * 8;
-  const size_t stage = ((size_t)TILE * (MODE == 0 ? 10 * max_deg + 4 * max_gdeg : 4 * max_deg) + 16) * 8;
-  const int off_rs = (int)((std::max(nbr, stage) + 15) & ~(size_t)15);
-  const int total = off_rs + 4 * (TILE + 1) * 4;
+  constexpr int TILE = 32 >> LG;                                                  // dofs per warp
+  constexpr int WARPS = ROWS_THREADS / 32;
+  // per warp: double-buffered neighbour block + staging strip of the mini-tile's rows (16-byte units)
+  const int stg_doubles = (TILE * (MODE == 0 ? 10 * max_deg + 4 * max_gdeg : 4 * max_deg) + 16 + 1) & ~1;
+  const int total = WARPS * (2 * 32 * EDGE_NB + stg_doubles) * 8;
   if (total > 227 * 1024) {
     set_error("vertex degree %d too large for the row kernel (%d bytes of shared memory)", max_deg, total);
     return KNP_E_UNSUPPORTED;
   }
-  static int configured = 0;
-  if (total > 48 * 1024 && total > configured) {
+  static int configured = -1, per_sm = 0;
+  if (total > configured) {
     KNP_CUDA(cudaFuncSetAttribute(rows_edge_kernel<D, MODE, LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, total));
+    KNP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rows_edge_kernel<D, MODE, LG>, ROWS_THREADS, total));
     configured = total;
   }
   const int nt0 = (T.L.n_own[0] + TILE - 1) / TILE, nt1 = (T.L.n_own[1] + TILE - 1) / TILE;
-  rows_edge_kernel<D, MODE, LG><<<nt0 + nt1, ROWS_THREADS, total, st>>>(T, make_coef(P), u, fe, vals, b, nt0, off_rs);
+  static const int sms = [] {
+    int dev = 0, n = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+  }();
+  // persistent grid: every resident CTA slot of the device; the warps deal the mini-tiles round-robin
+  const int grid = std::min((nt0 + nt1 + WARPS - 1) / WARPS, sms * std::max(per_sm, 1));
+  rows_edge_kernel<D, MODE, LG><<<grid, ROWS_THREADS, total, st>>>(T, make_coef(P), u, fe, vals, b, nt0, nt0 + nt1, stg_doubles);
   KNP_LAUNCHED();
   return KNP_OK;
 }

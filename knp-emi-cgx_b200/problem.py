@@ -32,7 +32,8 @@ class Constant:
     """Stand-in for dolfinx.fem.Constant: a mutable scalar with a ``.value``."""
 
     def __init__(self, value):
-        self.value = value
+        # PyYAML reads `1e-9` (no dot) as a string; dolfinx.fem.Constant converts through numpy, and so do we
+        self.value = float(value) if isinstance(value, str) else value
 
     def __float__(self):
         return float(self.value)
@@ -483,8 +484,12 @@ class ProblemKNPEMI:
     def set_initial_conditions(self):
         """KNPEMIx_problem.py:220-452 (config-provided initial conditions, :326-353 and :386-447)."""
         if self.find_initial_conditions:
-            raise NotImplementedError("steady-state initial-condition ODE solve is outside the B200 hot path "
-                                      "(SURVEY.md 8f-4); provide initial_conditions in the config")
+            self._find_steady_state_initial_conditions()
+            nv = self.mesh.x.shape[0]
+            self.phi_m_prev = Function(self, nv, "phi_m")
+            self._fill_initial_fields()
+            self._print("Initial conditions set.")
+            return
         self._print("Setting initial conditions from input file ...")
         ic = self.initial_conditions
         pick = lambda a, b: ic[a] if a in ic else ic[b]
@@ -504,6 +509,60 @@ class ProblemKNPEMI:
         self.phi_m_prev = Function(self, nv, "phi_m")
         self._fill_initial_fields()
         self._print("Initial conditions set.")
+
+    def calculate_compartment_volumes_and_surface_areas(self):
+        """utils/mixed_dim_problem.py:813-849: volumes [m^3] of the neuronal / glial intracellular space and of the ECS,
+        membrane areas [m^2] of neurons / glia (host sums over the owned cells / facets, all-reduced)."""
+        m = self.mesh
+        vol = self._cell_volumes(m.cells)
+        if m.cell_owned is not None:
+            vol = vol * (np.asarray(m.cell_owned) != 0)
+        xf = m.x[m.mf_verts]
+        if m.gdim == 2:
+            area = np.linalg.norm(xf[:, 1] - xf[:, 0], axis=1)
+        else:
+            area = 0.5 * np.linalg.norm(np.cross(xf[:, 1] - xf[:, 0], xf[:, 2] - xf[:, 0]), axis=1)
+        if m.mf_owned is not None:
+            area = area * (np.asarray(m.mf_owned) != 0)
+        tot = lambda v: self.comm.allreduce(float(v), op=MPI.SUM)
+        self.vol_i_n = tot(vol[np.isin(m.cell_tags, np.asarray(self.neuron_tags))].sum())
+        self.area_g_n = tot(area[np.isin(m.mf_tags, np.asarray(self.neuron_tags))].sum())
+        self.vol_e = tot(vol[m.cell_tags == self.extra_tag[0]].sum())
+        if self.glia_flag:
+            self.vol_i_g = tot(vol[np.isin(m.cell_tags, np.asarray(self.glia_tags))].sum())
+            self.area_g_g = tot(area[np.isin(m.mf_tags, np.asarray(self.glia_tags))].sum())
+
+    def _find_steady_state_initial_conditions(self):
+        """KNPEMIx_problem.py:224-325: no initial_conditions in the config -> integrate the well-mixed membrane ODE system to
+        rest on rank 0 (steady_state.py, mirror of utils/membrane_ODE_systems.py), broadcast, overwrite the constants."""
+        from .steady_state import MembraneSteadyState
+        self._print("Solving ODE system to find steady-state initial conditions ...")
+        self.calculate_compartment_volumes_and_surface_areas()
+        v = lambda c: float(c.value)
+        consts = dict(R=v(self.R), F=v(self.F), T=v(self.T), C_M=v(self.C_M), g_Na_bar=v(self.g_Na_bar), g_K_bar=v(self.g_K_bar),
+                      g_leak=(v(self.g_Na_leak), v(self.g_K_leak), v(self.g_Cl_leak)),
+                      g_leak_g=(v(self.g_Na_leak_g), v(self.g_K_leak_g), v(self.g_Cl_leak_g)), phi_rest=v(self.phi_rest),
+                      phi_m=v(self.phi_m_init), c_i=(v(self.Na_i_init), v(self.K_i_init), v(self.Cl_i_init)),
+                      c_e=(v(self.Na_e_init), v(self.K_e_init), v(self.Cl_e_init)), phi_m_g=v(self.phi_m_g_init),
+                      c_i_g=(v(self.Na_i_g_init), v(self.K_i_g_init), v(self.Cl_i_g_init)))
+        geom = dict(vol_i_n=self.vol_i_n, vol_e=self.vol_e, area_n=self.area_g_n)
+        if self.glia_flag:
+            geom.update(vol_i_g=self.vol_i_g, area_g=self.area_g_g)
+        x = None
+        if self.comm.rank == 0:
+            x, t_end, reached = MembraneSteadyState(consts, geom, glia=self.glia_flag).solve()
+            self._print("Steady state reached. Derivatives zero to within tolerance." if reached
+                        else "Max time exceeded without finding steady state. Exiting.")
+            x = [float(val) for val in x]
+        x = self.comm.bcast(x, root=0)
+        self.steady_state = x
+        if not self.glia_flag:
+            (self.phi_m_init.value, self.Na_i_init.value, self.Na_e_init.value, self.K_i_init.value, self.K_e_init.value,
+             self.Cl_i_init.value, self.Cl_e_init.value, self.n_init.value, self.m_init.value, self.h_init.value) = x
+        else:
+            (self.phi_m_n_init.value, self.Na_i_n_init.value, self.Na_e_init.value, self.K_i_n_init.value, self.K_e_init.value,
+             self.Cl_i_n_init.value, self.Cl_e_init.value, self.phi_m_g_init.value, self.Na_i_g_init.value,
+             self.K_i_g_init.value, self.Cl_i_g_init.value, self.n_init.value, self.m_init.value, self.h_init.value) = x
 
     def _fill_initial_fields(self):
         """Write the initial conditions into wh / phi_m_prev (also used by the iterative solver's

@@ -300,3 +300,54 @@ def test_point_evaluation_and_multiple_stimulus_directions_parse(kb, tmp_path):
     assert p.point_evaluation and np.allclose(p.ics_points, [[0.5e-6, 0.5e-6]]) and np.allclose(p.gamma_points, [[0.25e-6, 0.5e-6]])
     assert p.multiple_stimulus_directions and p.stimulus_region_directions == [0, 1]
     assert np.allclose(p.stimulus_region_range, np.array([[0.0, 0.5], [0.2, 0.6]]) * 1e-6)
+
+
+def test_steady_state_initial_conditions_from_config(kb, tmp_path):
+    """No `initial_conditions` block -> the membrane ODE system is integrated to rest (KNPEMIx_problem.py:224-325) with the
+    compartment sizes of the mesh (utils/mixed_dim_problem.py:813-849); the constants and the fields take the result."""
+    # membrane tags = cell tags as in the production configs (the membrane area is taken over dS(neuron_tags))
+    txt = BASE.replace("ics_tags: [1]", "ics_tags: !range [2, 6]").replace("ecs_tags: [2]", "ecs_tags: [1]") \
+              .replace("membrane_tags: [4]", "membrane_tags: !range [2, 6]")
+    txt = drop(drop(drop(txt, "cell_tag_file"), "facet_tag_file"), "initial_conditions") + \
+        "\nsynthetic_mesh: {kind: cell_array, dim: 2, N: 16, cells_per_dim: 2, first_tag: 2, extra_tag: 1}\n"
+    p = kb.ProblemKNPEMI(write(tmp_path, txt), verbose=False)
+    assert p.find_initial_conditions
+    p.set_initial_conditions()
+    # 2 x 2 square cells of side 0.25 in the unit square x 1e-6
+    assert abs(p.vol_i_n - 0.25e-12) < 1e-24 and abs(p.vol_e - 0.75e-12) < 1e-24 and abs(p.area_g_n - 4e-6) < 1e-18
+    x = np.array(p.steady_state)
+    assert x.shape == (10,) and np.all(np.isfinite(x))
+    assert -0.09 < x[0] < -0.05 and np.all(x[1:7] > 0) and np.all((x[7:] > 0) & (x[7:] < 1))
+    assert p.phi_m_init.value == x[0] and p.K_e_init.value == x[4] and p.h_init.value == x[9]
+    assert np.all(p.wh[0][3].x.array == x[0]) and np.all(p.wh[1][1].x.array == x[4]) and np.all(p.wh[0][0].x.array == x[1])
+    # electroneutral exchange: what leaves the cells arrives in the ECS (the ODE conserves the ion amounts)
+    for k, (ci0, ce0) in enumerate([(10.0, 145.0), (130.0, 3.0), (5.0, 134.0)]):
+        before = ci0 * p.vol_i_n + ce0 * p.vol_e
+        after = x[1 + 2 * k] * p.vol_i_n + x[2 + 2 * k] * p.vol_e
+        assert abs(after - before) < 1e-5 * before
+
+
+def test_steady_state_matches_reference_ode_classes(kb):
+    """steady_state.py against tests/golden/steady_state.json, written by scripts/make_golden_steady_state.py from the
+    reference's own TwoCompartment / ThreeCompartmentMembraneODESystem (utils/membrane_ODE_systems.py) on the same
+    constants and compartment sizes.  Both sides integrate with rtol 1e-6 / atol 1e-8, hence the 1e-5 comparison."""
+    import importlib
+    import json
+    ss = importlib.import_module("knp-emi-cgx_b200.steady_state")
+    path = os.path.join(os.path.dirname(__file__), "golden", "steady_state.json")
+    gold = json.load(open(path))
+    for name, case in gold.items():
+        c, g = case["constants"], case["geometry"]
+        consts = dict(R=c["R"], F=c["F"], T=c["T"], C_M=c["C_M"], g_Na_bar=c["g_Na_bar"], g_K_bar=c["g_K_bar"],
+                      g_leak=(c["g_Na_leak"], c["g_K_leak"], c["g_Cl_leak"]),
+                      g_leak_g=(c["g_Na_leak_g"], c["g_K_leak_g"], c["g_Cl_leak_g"]), phi_rest=c["phi_rest"],
+                      phi_m=c["phi_m_init"], c_i=(c["Na_i_init"], c["K_i_init"], c["Cl_i_init"]),
+                      c_e=(c["Na_e_init"], c["K_e_init"], c["Cl_e_init"]), phi_m_g=c["phi_m_g_init"],
+                      c_i_g=(c["Na_i_g_init"], c["K_i_g_init"], c["Cl_i_g_init"]))
+        geom = dict(vol_i_n=g["vol_i_n"], vol_e=g["vol_e"], area_n=g["area_g_n"])
+        if case["glia"]:
+            geom.update(vol_i_g=g["vol_i_g"], area_g=g["area_g_g"])
+        x, t_end, reached = ss.MembraneSteadyState(consts, geom, glia=case["glia"]).solve()
+        ref = np.array(case["steady_state"])
+        assert reached and x.shape == ref.shape
+        assert np.abs(x - ref).max() / np.abs(ref).max() < 1e-5 and np.all(np.abs(x - ref) <= 1e-4 * np.abs(ref) + 1e-9), name
