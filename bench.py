@@ -384,8 +384,9 @@ def run_ours(args):
     if os.path.exists(tpath) and world == 1:
         traffic = json.load(open(tpath))
     kernels = {
-        "assembly (facet_kernel + rows_kernel)": {"ms": t_asm, "algorithmic_bytes": B_asm, "GB/s": B_asm / t_asm / 1e6,
-                                                  "frac": B_asm / t_asm / 1e6 / peak, "share_of_step": t_asm / step_local},
+        "assembly (facet_kernel + rows_edge_kernel)": {"ms": t_asm, "algorithmic_bytes": B_asm, "GB/s": B_asm / t_asm / 1e6,
+                                                       "frac": B_asm / t_asm / 1e6 / peak, "share_of_step": t_asm / step_local,
+                                                       "traffic": traffic.get(f"assembly@{wl}:N={n}")},
         "spmv A (spmv_stream_kernel<EPI_SET>, plain CSR, TMA-staged)": {
             "ms": t_spmv, "algorithmic_bytes": B_spmv, "GB/s": B_spmv / t_spmv / 1e6, "frac": B_spmv / t_spmv / 1e6 / peak,
             "share_of_step": (mean_its + 1) * t_spmv / step_local, "traffic": traffic.get(f"spmv_stream_kernel<0>@{wl}:N={n}")},

@@ -823,6 +823,9 @@ int launch_facets(const DevTopo& T, const KParams& P, const uint32_t* tag_models
 #ifndef EDGE_MIN_CTAS_3D
 #define EDGE_MIN_CTAS_3D 2      // the 3D cell formulas plus the prefetched tables need ~100 registers
 #endif
+#ifndef EDGE_THREADS
+#define EDGE_THREADS 256
+#endif
 constexpr int EDGE_NB = 6;      // doubles per staged neighbour: 2D {x, y, c0, c1, c2, -}, 3D {x, y, z, c0, c1, c2} (16-byte units)
 
 // The kernel is PERSISTENT, software-pipelined and WARP-AUTONOMOUS.  A lane group never spans warps (G <= 32), so a warp
@@ -849,7 +852,7 @@ struct EdgeTables {      // what one lane holds of a tile before the tile is com
 };
 
 template <int D, int MODE, int LG>
-__global__ void __launch_bounds__(ROWS_THREADS, D == 3 ? EDGE_MIN_CTAS_3D : EDGE_MIN_CTAS) rows_edge_kernel(DevTopo T, RowCoef C, const double* __restrict__ u,
+__global__ void __launch_bounds__(EDGE_THREADS, D == 3 ? EDGE_MIN_CTAS_3D : EDGE_MIN_CTAS) rows_edge_kernel(DevTopo T, RowCoef C, const double* __restrict__ u,
                                                                                 const double* __restrict__ fe,
                                                                                 double* __restrict__ vals, double* __restrict__ bvec,
                                                                                 int ntile0, int ntiles, int stg_doubles) {
@@ -860,11 +863,13 @@ __global__ void __launch_bounds__(ROWS_THREADS, D == 3 ? EDGE_MIN_CTAS_3D : EDGE
   constexpr uint32_t FMASK = D == 3 ? 0x00FFFFFFu : 0x0000FFFFu;
   extern __shared__ __align__(16) unsigned char smraw[];
   const int wid = threadIdx.x >> 5, tid = threadIdx.x & 31;                      // warp in the CTA, lane
-  double* nbr2 = reinterpret_cast<double*>(smraw) + (size_t)wid * (2 * 32 * NB + stg_doubles);   // [2][32][NB] of this warp
-  double* stg = nbr2 + 2 * 32 * NB;                                              // staging strip of the warp's rows
+  // neighbour buffers of all warps first (compile-time stride: the compiler re-derives these addresses instead of holding
+  // them in registers), then the staging strips
+  double* nbr2 = reinterpret_cast<double*>(smraw) + wid * (2 * 32 * NB);         // [2][32][NB] of this warp
+  double* stg = reinterpret_cast<double*>(smraw) + (EDGE_THREADS / 32) * (2 * 32 * NB) + (size_t)wid * stg_doubles;
   const int lw = tid >> LG, e = tid & (G - 1);
   const int* __restrict__ iptr = MODE == 0 ? T.indptr : T.indptr_P;
-  const int stride = gridDim.x * (ROWS_THREADS / 32);                            // warps in the grid
+  const int stride = gridDim.x * (EDGE_THREADS / 32);                            // warps in the grid
 
   auto load_tables = [&](int t, EdgeTables<D>& E) {
     E.q = -1;
@@ -920,7 +925,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, D == 3 ? EDGE_MIN_CTAS_3D : EDGE
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
-  int t = blockIdx.x * (ROWS_THREADS / 32) + wid;
+  int t = blockIdx.x * (EDGE_THREADS / 32) + wid;
   EdgeTables<D> cur, nxt;
   load_tables(t, cur);
   gather(t, cur.q, nbr2);
@@ -1231,7 +1236,7 @@ template <int D, int MODE, int LG>
 static int launch_rows_edge_t(const DevTopo& T, const KParams& P, const double* u, const double* fe, double* vals,
                               double* b, int max_deg, int max_gdeg, cudaStream_t st) {
   constexpr int TILE = 32 >> LG;                                                  // dofs per warp
-  constexpr int WARPS = ROWS_THREADS / 32;
+  constexpr int WARPS = EDGE_THREADS / 32;
   // per warp: double-buffered neighbour block + staging strip of the mini-tile's rows (16-byte units)
   const int stg_doubles = (TILE * (MODE == 0 ? 10 * max_deg + 4 * max_gdeg : 4 * max_deg) + 16 + 1) & ~1;
   const int total = WARPS * (2 * 32 * EDGE_NB + stg_doubles) * 8;
@@ -1242,7 +1247,7 @@ static int launch_rows_edge_t(const DevTopo& T, const KParams& P, const double* 
   static int configured = -1, per_sm = 0;
   if (total > configured) {
     KNP_CUDA(cudaFuncSetAttribute(rows_edge_kernel<D, MODE, LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, total));
-    KNP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rows_edge_kernel<D, MODE, LG>, ROWS_THREADS, total));
+    KNP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rows_edge_kernel<D, MODE, LG>, EDGE_THREADS, total));
     configured = total;
   }
   const int nt0 = (T.L.n_own[0] + TILE - 1) / TILE, nt1 = (T.L.n_own[1] + TILE - 1) / TILE;
@@ -1254,7 +1259,7 @@ static int launch_rows_edge_t(const DevTopo& T, const KParams& P, const double* 
   }();
   // persistent grid: every resident CTA slot of the device; the warps deal the mini-tiles round-robin
   const int grid = std::min((nt0 + nt1 + WARPS - 1) / WARPS, sms * std::max(per_sm, 1));
-  rows_edge_kernel<D, MODE, LG><<<grid, ROWS_THREADS, total, st>>>(T, make_coef(P), u, fe, vals, b, nt0, nt0 + nt1, stg_doubles);
+  rows_edge_kernel<D, MODE, LG><<<grid, EDGE_THREADS, total, st>>>(T, make_coef(P), u, fe, vals, b, nt0, nt0 + nt1, stg_doubles);
   KNP_LAUNCHED();
   return KNP_OK;
 }

@@ -25,5 +25,8 @@ def run(cfgname, repl, models):
 which = sys.argv[1] if len(sys.argv) > 1 else "both"
 if which in ("2d", "both"):
     run("c3_square2048_cells64.yaml", [], lambda p: [kb.NeuronalCotransporters(p), kb.HodgkinHuxley(p), kb.ATPPump(p)])
+if which == "c5":      # BASELINE C5 per-GPU size: N = 128 (1/8 of the N = 256 mesh), plate-stack cells, HH + ATP + KCC2 with stimulus
+    n = sys.argv[2] if len(sys.argv) > 2 else "128"
+    run("c5_cube256_tissue512_hh.yaml", [("N: 256", f"N: {n}")], lambda p: [kb.NeuronalCotransporters(p), kb.HodgkinHuxley(p), kb.ATPPump(p)])
 if which in ("3d", "both"):
     run("c4_cube120_cells64_passive.yaml", [], lambda p: [kb.PassiveModel(p)])
