@@ -166,6 +166,8 @@ struct CsrDev {
   int64_t nnz = 0;
   DevBuf<int32_t> indptr, indices, rowblk;
   DevBuf<double> vals;
+  DevBuf<float> vals32;   // hierarchy operators are STORED in single precision (solver.cu::to_f32): the products are still
+                          // accumulated in double, so the cycle stays a fixed linear operator; vals is freed after conversion
   int nblk = 0;   // row blocks of the streaming SpMV (0: use the CSR-vector kernel)
 };
 
@@ -185,6 +187,7 @@ struct AmgLevelDev {
 struct Amg {
   std::vector<AmgLevelDev*> levels;   // levels[0].A is not owned (views the context's P) when external
   DevBuf<double> coarse_inv;          // dense n_c x n_c (row-major)
+  DevBuf<float> coarse_inv32;         // the same in single-precision storage (used by the cycle when present)
   DevBuf<double> cb, cx;
   int n_coarse = 0;
   int gamma = 1;                      // cycle index on levels 1..gamma_last (1: V-cycle, 2: W-cycle below the finest level)

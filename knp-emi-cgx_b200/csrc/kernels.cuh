@@ -51,6 +51,7 @@ struct CsrView {
   const double* vals;
   const int32_t* rowblk;
   int nblk;
+  const float* vals32 = nullptr;   // non-null: the values are stored in single precision (vals is ignored)
 };
 // out = epilogue(M x): streaming TMA kernel when row blocks exist and the arrays are 16-byte aligned, else CSR-vector
 int spmv(const CsrView& M, const double* x, double* out, int epi, const double* b, const double* dinv, double w,
@@ -59,6 +60,8 @@ int launch_scale_dinv(int n, double w, const double* dinv, const double* b, doub
 int launch_extract_dinv(int n_rows, const int32_t* indptr, const int32_t* indices, const double* vals, double* dinv,
                         cudaStream_t st);
 int launch_dense_gemv(int n, const double* Minv, const double* b, double* x, cudaStream_t st);
+int launch_dense_gemv(int n, const float* Minv, const double* b, double* x, cudaStream_t st);
+int launch_to_f32(int64_t n, const double* src, float* dst, cudaStream_t st);
 // one operation of the fused cycle tail (linalg.cu::amg_tail_kernel)
 enum TailType { TAIL_SPMV = 0, TAIL_DENSE = 1, TAIL_SCALE = 2 };
 struct TailOp {

@@ -17,6 +17,11 @@ __device__ __forceinline__ double ld_stream(const double* p) {
   asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
   return v;
 }
+__device__ __forceinline__ double ld_stream(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return (double)v;
+}
 __device__ __forceinline__ int ld_stream(const int* p) {
   int v;
   asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
@@ -29,10 +34,10 @@ static int grid_for(int n) {
   return grid < 1 ? 1 : grid;
 }
 
-template <int LANES, int EPI>
+template <int LANES, int EPI, typename VT>
 __global__ void __launch_bounds__(256) spmv_kernel(int n_rows, const int32_t* __restrict__ indptr,
                                                    const int32_t* __restrict__ indices,
-                                                   const double* __restrict__ vals, const double* __restrict__ x,
+                                                   const VT* __restrict__ vals, const double* __restrict__ x,
                                                    double* __restrict__ out, const double* __restrict__ b,
                                                    const double* __restrict__ dinv, double w) {
   const int lane = threadIdx.x & (LANES - 1);
@@ -78,8 +83,9 @@ constexpr int SPMV_THREADS = 256;
 constexpr int SPMV_PAD = 8;
 constexpr int SPMV_ROWS = 256;          // max rows per block (multiple of 4: the row-pointer slice is TMA-loaded too)
 
+template <typename VT>
 struct SpmvStage {
-  double v[SPMV_CAP + SPMV_PAD];
+  VT v[SPMV_CAP + SPMV_PAD];
   int c[SPMV_CAP + SPMV_PAD];
   int rp[SPMV_ROWS + 8];
 };
@@ -111,17 +117,17 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
 }
 
 // blkinfo[blk] = {first row r0 (multiple of 4), number of rows, a4 = 4-aligned first non-zero, staged element count}
-template <int EPI, int LANES>
+template <int EPI, int LANES, typename VT>
 __global__ void __launch_bounds__(SPMV_THREADS) spmv_stream_kernel(int nblk, const int4* __restrict__ blkinfo,
                                                                     const int32_t* __restrict__ indptr,
                                                                     const int32_t* __restrict__ indices,
-                                                                    const double* __restrict__ vals,
+                                                                    const VT* __restrict__ vals,
                                                                     const double* __restrict__ x, double* __restrict__ out,
                                                                     const double* __restrict__ b,
                                                                     const double* __restrict__ dinv, double w) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  SpmvStage* st = reinterpret_cast<SpmvStage*>(smem_raw);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + 2 * sizeof(SpmvStage));
+  SpmvStage<VT>* st = reinterpret_cast<SpmvStage<VT>*>(smem_raw);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + 2 * sizeof(SpmvStage<VT>));
   __shared__ double rsum[SPMV_ROWS];
   const int tid = threadIdx.x;
   if (tid == 0) {
@@ -135,10 +141,10 @@ __global__ void __launch_bounds__(SPMV_THREADS) spmv_stream_kernel(int nblk, con
     const int ntma = bi.w & ~3;
     const int nrp = (bi.y + 1 + 3) & ~3;     // row pointers r0 .. r0+nrows, rounded up to 16 bytes (arrays are padded)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    mbar_expect_tx(&bar[s], (uint32_t)ntma * 12u + (uint32_t)nrp * 4u);
+    mbar_expect_tx(&bar[s], (uint32_t)ntma * (uint32_t)(sizeof(VT) + 4) + (uint32_t)nrp * 4u);
     tma_load_1d(st[s].rp, indptr + bi.x, (uint32_t)nrp * 4u, &bar[s]);
     if (ntma > 0) {
-      tma_load_1d(st[s].v, vals + bi.z, (uint32_t)ntma * 8u, &bar[s]);
+      tma_load_1d(st[s].v, vals + bi.z, (uint32_t)ntma * (uint32_t)sizeof(VT), &bar[s]);
       tma_load_1d(st[s].c, indices + bi.z, (uint32_t)ntma * 4u, &bar[s]);
     }
   };
@@ -156,7 +162,7 @@ __global__ void __launch_bounds__(SPMV_THREADS) spmv_stream_kernel(int nblk, con
     if (tid == 0 && blk + stride < nblk) issue(nx1, s ^ 1);
     const int r0 = cur.x, nrows = cur.y, a4 = cur.z, n = cur.w;
     const int ntma = n & ~3;
-    double* sv = st[s].v;
+    VT* sv = st[s].v;
     int* sc = st[s].c;
     const int* rp = st[s].rp;
     // epilogue operands of "my" row (thread t <-> row r0 + t): coalesced, issued long before they are needed
@@ -241,62 +247,70 @@ int build_rowblocks(const int32_t* indptr, int n_rows, std::vector<int32_t>& inf
   return (int)(info.size() / 4);
 }
 
-template <int LANES>
+template <int LANES, typename VT>
 static int launch_spmv_stream_l(int nblk, const int32_t* blkinfo, const int32_t* indptr, const int32_t* indices,
-                                const double* vals, const double* x, double* out, int epi, const double* b,
+                                const VT* vals, const double* x, double* out, int epi, const double* b,
                                 const double* dinv, double w, cudaStream_t st) {
-  const size_t smem = 2 * sizeof(SpmvStage) + 2 * sizeof(uint64_t);
+  const size_t smem = 2 * sizeof(SpmvStage<VT>) + 2 * sizeof(uint64_t);
   static bool configured = false;
   if (!configured) {
-    KNP_CUDA(cudaFuncSetAttribute(spmv_stream_kernel<EPI_SET, LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    KNP_CUDA(cudaFuncSetAttribute(spmv_stream_kernel<EPI_RESID, LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    KNP_CUDA(cudaFuncSetAttribute(spmv_stream_kernel<EPI_JACOBI, LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    KNP_CUDA(cudaFuncSetAttribute(spmv_stream_kernel<EPI_ADD, LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    KNP_CUDA(cudaFuncSetAttribute(spmv_stream_kernel<EPI_SET, LANES, VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    KNP_CUDA(cudaFuncSetAttribute(spmv_stream_kernel<EPI_RESID, LANES, VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    KNP_CUDA(cudaFuncSetAttribute(spmv_stream_kernel<EPI_JACOBI, LANES, VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    KNP_CUDA(cudaFuncSetAttribute(spmv_stream_kernel<EPI_ADD, LANES, VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   const int grid = nblk < 148 * KNP_SPMV_CTAS ? nblk : 148 * KNP_SPMV_CTAS;   // persistent CTAs
   const int4* bi = reinterpret_cast<const int4*>(blkinfo);
   switch (epi) {
-    case EPI_SET: spmv_stream_kernel<EPI_SET, LANES><<<grid, SPMV_THREADS, smem, st>>>(nblk, bi, indptr, indices, vals, x, out, b, dinv, w); break;
-    case EPI_RESID: spmv_stream_kernel<EPI_RESID, LANES><<<grid, SPMV_THREADS, smem, st>>>(nblk, bi, indptr, indices, vals, x, out, b, dinv, w); break;
-    case EPI_JACOBI: spmv_stream_kernel<EPI_JACOBI, LANES><<<grid, SPMV_THREADS, smem, st>>>(nblk, bi, indptr, indices, vals, x, out, b, dinv, w); break;
-    default: spmv_stream_kernel<EPI_ADD, LANES><<<grid, SPMV_THREADS, smem, st>>>(nblk, bi, indptr, indices, vals, x, out, b, dinv, w); break;
+    case EPI_SET: spmv_stream_kernel<EPI_SET, LANES, VT><<<grid, SPMV_THREADS, smem, st>>>(nblk, bi, indptr, indices, vals, x, out, b, dinv, w); break;
+    case EPI_RESID: spmv_stream_kernel<EPI_RESID, LANES, VT><<<grid, SPMV_THREADS, smem, st>>>(nblk, bi, indptr, indices, vals, x, out, b, dinv, w); break;
+    case EPI_JACOBI: spmv_stream_kernel<EPI_JACOBI, LANES, VT><<<grid, SPMV_THREADS, smem, st>>>(nblk, bi, indptr, indices, vals, x, out, b, dinv, w); break;
+    default: spmv_stream_kernel<EPI_ADD, LANES, VT><<<grid, SPMV_THREADS, smem, st>>>(nblk, bi, indptr, indices, vals, x, out, b, dinv, w); break;
   }
   KNP_LAUNCHED();
   return KNP_OK;
+}
+
+template <typename VT>
+static int launch_spmv_stream_t(int nblk, const int32_t* blkinfo, const int32_t* indptr, const int32_t* indices, const VT* vals,
+                                const double* x, double* out, int epi, const double* b, const double* dinv, double w,
+                                cudaStream_t st, double avg_row) {
+  if (nblk == 0) return KNP_OK;
+  static const int force = getenv("KNP_SPMV_LANES") ? atoi(getenv("KNP_SPMV_LANES")) : 0;
+  const int lanes = force ? force : (avg_row <= 10.0 ? 1 : avg_row <= 24.0 ? 2 : 4);
+  switch (lanes) {
+    case 1: return launch_spmv_stream_l<1, VT>(nblk, blkinfo, indptr, indices, vals, x, out, epi, b, dinv, w, st);
+    case 2: return launch_spmv_stream_l<2, VT>(nblk, blkinfo, indptr, indices, vals, x, out, epi, b, dinv, w, st);
+    case 4: return launch_spmv_stream_l<4, VT>(nblk, blkinfo, indptr, indices, vals, x, out, epi, b, dinv, w, st);
+    default: return launch_spmv_stream_l<8, VT>(nblk, blkinfo, indptr, indices, vals, x, out, epi, b, dinv, w, st);
+  }
 }
 
 int launch_spmv_stream(int nblk, const int32_t* blkinfo, const int32_t* indptr, const int32_t* indices, const double* vals,
                        const double* x, double* out, int epi, const double* b, const double* dinv, double w, cudaStream_t st,
                        double avg_row) {
-  if (nblk == 0) return KNP_OK;
-  static const int force = getenv("KNP_SPMV_LANES") ? atoi(getenv("KNP_SPMV_LANES")) : 0;
-  const int lanes = force ? force : (avg_row <= 10.0 ? 1 : avg_row <= 24.0 ? 2 : 4);
-  switch (lanes) {
-    case 1: return launch_spmv_stream_l<1>(nblk, blkinfo, indptr, indices, vals, x, out, epi, b, dinv, w, st);
-    case 2: return launch_spmv_stream_l<2>(nblk, blkinfo, indptr, indices, vals, x, out, epi, b, dinv, w, st);
-    case 4: return launch_spmv_stream_l<4>(nblk, blkinfo, indptr, indices, vals, x, out, epi, b, dinv, w, st);
-    default: return launch_spmv_stream_l<8>(nblk, blkinfo, indptr, indices, vals, x, out, epi, b, dinv, w, st);
-  }
+  return launch_spmv_stream_t<double>(nblk, blkinfo, indptr, indices, vals, x, out, epi, b, dinv, w, st, avg_row);
 }
 
-template <int LANES>
-static int launch_spmv_l(int grid, int n_rows, const int32_t* indptr, const int32_t* indices, const double* vals,
+template <int LANES, typename VT>
+static int launch_spmv_l(int grid, int n_rows, const int32_t* indptr, const int32_t* indices, const VT* vals,
                          const double* x, double* out, int epi, const double* b, const double* dinv, double w,
                          cudaStream_t st) {
   switch (epi) {
-    case EPI_SET: spmv_kernel<LANES, EPI_SET><<<grid, 256, 0, st>>>(n_rows, indptr, indices, vals, x, out, b, dinv, w); break;
-    case EPI_RESID: spmv_kernel<LANES, EPI_RESID><<<grid, 256, 0, st>>>(n_rows, indptr, indices, vals, x, out, b, dinv, w); break;
-    case EPI_JACOBI: spmv_kernel<LANES, EPI_JACOBI><<<grid, 256, 0, st>>>(n_rows, indptr, indices, vals, x, out, b, dinv, w); break;
-    default: spmv_kernel<LANES, EPI_ADD><<<grid, 256, 0, st>>>(n_rows, indptr, indices, vals, x, out, b, dinv, w); break;
+    case EPI_SET: spmv_kernel<LANES, EPI_SET, VT><<<grid, 256, 0, st>>>(n_rows, indptr, indices, vals, x, out, b, dinv, w); break;
+    case EPI_RESID: spmv_kernel<LANES, EPI_RESID, VT><<<grid, 256, 0, st>>>(n_rows, indptr, indices, vals, x, out, b, dinv, w); break;
+    case EPI_JACOBI: spmv_kernel<LANES, EPI_JACOBI, VT><<<grid, 256, 0, st>>>(n_rows, indptr, indices, vals, x, out, b, dinv, w); break;
+    default: spmv_kernel<LANES, EPI_ADD, VT><<<grid, 256, 0, st>>>(n_rows, indptr, indices, vals, x, out, b, dinv, w); break;
   }
   KNP_LAUNCHED();
   return KNP_OK;
 }
 
-int launch_spmv(int n_rows, int64_t nnz, const int32_t* indptr, const int32_t* indices, const double* vals,
-                const double* x, double* out, int epi, const double* b, const double* dinv, double w,
-                cudaStream_t st) {
+template <typename VT>
+static int launch_spmv_t(int n_rows, int64_t nnz, const int32_t* indptr, const int32_t* indices, const VT* vals,
+                         const double* x, double* out, int epi, const double* b, const double* dinv, double w,
+                         cudaStream_t st) {
   if (n_rows == 0) return KNP_OK;
   const double avg = (double)nnz / n_rows;
   int lanes = avg <= 3 ? 2 : avg <= 6 ? 4 : avg <= 12 ? 8 : avg <= 40 ? 16 : 32;
@@ -304,24 +318,46 @@ int launch_spmv(int n_rows, int64_t nnz, const int32_t* indptr, const int32_t* i
   const int64_t want = ((int64_t)n_rows + rows_per_block - 1) / rows_per_block;
   const int grid = (int)(want < (int64_t)148 * 64 ? want : (int64_t)148 * 64);
   switch (lanes) {
-    case 2: return launch_spmv_l<2>(grid, n_rows, indptr, indices, vals, x, out, epi, b, dinv, w, st);
-    case 4: return launch_spmv_l<4>(grid, n_rows, indptr, indices, vals, x, out, epi, b, dinv, w, st);
-    case 8: return launch_spmv_l<8>(grid, n_rows, indptr, indices, vals, x, out, epi, b, dinv, w, st);
-    case 16: return launch_spmv_l<16>(grid, n_rows, indptr, indices, vals, x, out, epi, b, dinv, w, st);
-    default: return launch_spmv_l<32>(grid, n_rows, indptr, indices, vals, x, out, epi, b, dinv, w, st);
+    case 2: return launch_spmv_l<2, VT>(grid, n_rows, indptr, indices, vals, x, out, epi, b, dinv, w, st);
+    case 4: return launch_spmv_l<4, VT>(grid, n_rows, indptr, indices, vals, x, out, epi, b, dinv, w, st);
+    case 8: return launch_spmv_l<8, VT>(grid, n_rows, indptr, indices, vals, x, out, epi, b, dinv, w, st);
+    case 16: return launch_spmv_l<16, VT>(grid, n_rows, indptr, indices, vals, x, out, epi, b, dinv, w, st);
+    default: return launch_spmv_l<32, VT>(grid, n_rows, indptr, indices, vals, x, out, epi, b, dinv, w, st);
   }
+}
+
+int launch_spmv(int n_rows, int64_t nnz, const int32_t* indptr, const int32_t* indices, const double* vals,
+                const double* x, double* out, int epi, const double* b, const double* dinv, double w,
+                cudaStream_t st) {
+  return launch_spmv_t<double>(n_rows, nnz, indptr, indices, vals, x, out, epi, b, dinv, w, st);
 }
 
 int spmv(const CsrView& M, const double* x, double* out, int epi, const double* b, const double* dinv, double w,
          cudaStream_t st) {
-  const bool aligned = (((uintptr_t)M.vals | (uintptr_t)M.indices) & 15u) == 0;
+  const void* vp = M.vals32 ? (const void*)M.vals32 : (const void*)M.vals;
+  const bool aligned = (((uintptr_t)vp | (uintptr_t)M.indices) & 15u) == 0;
   // the TMA-staged kernel pays off on long-enough rows and enough blocks to fill the persistent grid
   static const double min_avg = getenv("KNP_SPMV_STREAM_MIN_AVG") ? atof(getenv("KNP_SPMV_STREAM_MIN_AVG")) : 0.0;
   static const int min_blk = getenv("KNP_SPMV_STREAM_MIN_BLK") ? atoi(getenv("KNP_SPMV_STREAM_MIN_BLK")) : 1;
   const double avg = M.n_rows > 0 ? (double)M.nnz / M.n_rows : 0.0;
-  if (M.nblk >= min_blk && M.rowblk && aligned && avg >= min_avg)
-    return launch_spmv_stream(M.nblk, M.rowblk, M.indptr, M.indices, M.vals, x, out, epi, b, dinv, w, st, avg);
+  const bool stream = M.nblk >= min_blk && M.rowblk && aligned && avg >= min_avg;
+  if (M.vals32) {
+    if (stream) return launch_spmv_stream_t<float>(M.nblk, M.rowblk, M.indptr, M.indices, M.vals32, x, out, epi, b, dinv, w, st, avg);
+    return launch_spmv_t<float>(M.n_rows, M.nnz, M.indptr, M.indices, M.vals32, x, out, epi, b, dinv, w, st);
+  }
+  if (stream) return launch_spmv_stream(M.nblk, M.rowblk, M.indptr, M.indices, M.vals, x, out, epi, b, dinv, w, st, avg);
   return launch_spmv(M.n_rows, M.nnz, M.indptr, M.indices, M.vals, x, out, epi, b, dinv, w, st);
+}
+
+__global__ void to_f32_kernel(int64_t n, const double* __restrict__ src, float* __restrict__ dst) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = (float)src[i];
+}
+int launch_to_f32(int64_t n, const double* src, float* dst, cudaStream_t st) {
+  if (n == 0) return KNP_OK;
+  const int64_t want = (n + 255) / 256;
+  to_f32_kernel<<<(int)(want < 148 * 16 ? want : 148 * 16), 256, 0, st>>>(n, src, dst);
+  KNP_LAUNCHED();
+  return KNP_OK;
 }
 
 __global__ void scale_dinv_kernel(int n, double w, const double* __restrict__ dinv, const double* __restrict__ b,
@@ -354,8 +390,9 @@ int launch_extract_dinv(int n_rows, const int32_t* indptr, const int32_t* indice
   return KNP_OK;
 }
 
-// x = Minv b, Minv dense row-major n x n; one warp per row
-__global__ void dense_gemv_kernel(int n, const double* __restrict__ M, const double* __restrict__ b,
+// x = Minv b, Minv dense row-major n x n (double or single-precision storage); one warp per row
+template <typename VT>
+__global__ void dense_gemv_kernel(int n, const VT* __restrict__ M, const double* __restrict__ b,
                                   double* __restrict__ x) {
   const int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
   const int lane = threadIdx.x & 31;
@@ -368,7 +405,13 @@ __global__ void dense_gemv_kernel(int n, const double* __restrict__ M, const dou
 }
 int launch_dense_gemv(int n, const double* Minv, const double* b, double* x, cudaStream_t st) {
   if (n == 0) return KNP_OK;
-  dense_gemv_kernel<<<(n + 7) / 8, 256, 0, st>>>(n, Minv, b, x);
+  dense_gemv_kernel<double><<<(n + 7) / 8, 256, 0, st>>>(n, Minv, b, x);
+  KNP_LAUNCHED();
+  return KNP_OK;
+}
+int launch_dense_gemv(int n, const float* Minv, const double* b, double* x, cudaStream_t st) {
+  if (n == 0) return KNP_OK;
+  dense_gemv_kernel<float><<<(n + 7) / 8, 256, 0, st>>>(n, Minv, b, x);
   KNP_LAUNCHED();
   return KNP_OK;
 }

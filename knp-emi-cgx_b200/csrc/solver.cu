@@ -53,6 +53,26 @@ static int upload_csr(const CsrHost& h, CsrDev& d) {
 
 static int vcycle(Amg& M, int l, const double* bl, double* xout, cudaStream_t st);
 
+// Single-precision STORAGE of the hierarchy operators (level matrices, prolongators, restrictions, dense coarsest inverse).
+// One preconditioner application streams every operator of both hierarchies once or more (W-cycle) and is bound by that
+// traffic; rounding the stored entries to float (relative perturbation 6e-8 of a preconditioner that is an approximation
+// anyway) takes a third off the bytes per non-zero (12 -> 8).  All products are accumulated in double on double vectors, so
+// the cycle remains a fixed linear operator and GMRES needs no flexible variant; the system matrix A and everything the
+// solution is measured with stay in double.  KNP_AMG_F32=0 keeps double storage; the opt-in fused tail reads double too.
+static bool amg_f32() {
+  static const bool on = !(getenv("KNP_AMG_F32") && atoi(getenv("KNP_AMG_F32")) == 0) &&
+                         !(getenv("KNP_FUSE_NNZ") && atoll(getenv("KNP_FUSE_NNZ")) > 0);
+  return on;
+}
+static int to_f32(CsrDev& M, cudaStream_t st) {
+  if (!amg_f32() || M.nnz == 0 || !M.vals.p) return KNP_OK;
+  KNP_TRY(M.vals32.alloc((size_t)M.nnz));
+  KNP_TRY(launch_to_f32(M.nnz, M.vals.p, M.vals32.p, st));
+  KNP_CUDA(cudaStreamSynchronize(st));
+  M.vals.free();
+  return KNP_OK;
+}
+
 // In-place Gauss-Jordan inversion of a dense SPD matrix on the device (no pivoting needed for SPD operators): the
 // coarsest Galerkin operators of the Schur hierarchies have a few thousand unknowns, which removes the deepest,
 // launch-bound levels from the cycle; the host inversion (with pivoting) stays for the indefinite blocks of P.
@@ -109,10 +129,20 @@ static int build_amg(knp_ctx* c, const CsrHost& A0, std::unique_ptr<Amg>& out, i
     KNP_TRY(lv->b.alloc(nr));
     KNP_TRY(lv->r.alloc(nr));
     KNP_TRY(launch_extract_dinv(nr, lv->A.indptr.p, lv->A.indices.p, lv->A.vals.p, lv->dinv.p, c->stream));
+    KNP_TRY(to_f32(lv->A, c->stream));
+    KNP_TRY(to_f32(lv->P, c->stream));
+    KNP_TRY(to_f32(lv->R, c->stream));
   }
   amg->n_coarse = As.back().n_rows;
   KNP_TRY(amg->coarse_inv.upload(cinv));
   if (spd) KNP_TRY(dense_inverse_device(amg->n_coarse, amg->coarse_inv.p, c->stream));
+  if (amg_f32() && amg->n_coarse > 0) {
+    const int64_t nn = (int64_t)amg->n_coarse * amg->n_coarse;
+    KNP_TRY(amg->coarse_inv32.alloc((size_t)nn));
+    KNP_TRY(launch_to_f32(nn, amg->coarse_inv.p, amg->coarse_inv32.p, c->stream));
+    KNP_CUDA(cudaStreamSynchronize(c->stream));
+    amg->coarse_inv.free();
+  }
   KNP_TRY(amg->cb.alloc(amg->n_coarse));
   KNP_TRY(amg->cx.alloc(amg->n_coarse));
   amg->hostA = std::move(As);
@@ -259,6 +289,9 @@ static int build_dist_amg(knp_ctx* c, CsrHost&& A0, HaloHost&& halo0, std::vecto
     KNP_TRY(lv->b.alloc(h.n_own));
     KNP_TRY(lv->r.alloc(h.n_own));
     KNP_TRY(launch_extract_dinv(h.n_own, lv->A.indptr.p, lv->A.indices.p, lv->A.vals.p, lv->dinv.p, c->stream));
+    KNP_TRY(to_f32(lv->A, c->stream));
+    KNP_TRY(to_f32(lv->P, c->stream));
+    KNP_TRY(to_f32(lv->R, c->stream));
     {
       // direct NVLink exchange of this level: the neighbours store into the ghost tail of lv->x
       const int np = (int)h.halo.peers.size();
@@ -665,14 +698,16 @@ int pc_setup(knp_ctx* c, const knp_solve_opts* o) {
 
 // z = V-cycle(r); level-l right-hand side in bl, result written to xout (distinct from bl)
 static CsrView view(const CsrDev& M) {
-  return CsrView{M.n_rows, M.nnz, M.indptr.p, M.indices.p, M.vals.p, M.rowblk.p, M.nblk};
+  return CsrView{M.n_rows, M.nnz, M.indptr.p, M.indices.p, M.vals.p, M.rowblk.p, M.nblk, M.vals32.p};
 }
 
 static int vcycle(Amg& M, int l, const double* bl, double* xout, cudaStream_t st) {
   const int nl = (int)M.levels.size();
   if (l == M.fuse_from && M.tail_nops > 0 && bl == M.tail_in && xout == M.tail_out)
     return launch_amg_tail(reinterpret_cast<const TailOp*>(M.tail_ops.p), M.tail_nops, M.tail_bar.p, st);
-  if (l == nl) return launch_dense_gemv(M.n_coarse, M.coarse_inv.p, bl, xout, st);
+  if (l == nl)
+    return M.coarse_inv32.p ? launch_dense_gemv(M.n_coarse, M.coarse_inv32.p, bl, xout, st)
+                            : launch_dense_gemv(M.n_coarse, M.coarse_inv.p, bl, xout, st);
   AmgLevelDev& L = *M.levels[l];
   const int n = L.A.n_rows;
   const double w = (4.0 / 3.0) / L.rho;
@@ -791,7 +826,8 @@ static int schur_apply_graphed(knp_ctx* c, const double* r, double* z, cudaStrea
 // iterate); the dense coarsest solve reads the inverse once per visit; the Schur glue kernels read / write each of their
 // vectors once.  Visits follow the cycle index (W on levels 1..gamma_last).
 static double spmv_bytes(const CsrDev& M, int extra_vectors) {
-  return 12.0 * (double)M.nnz + 4.0 * M.n_rows + 8.0 * M.n_cols + 8.0 * M.n_rows + 8.0 * (double)extra_vectors * M.n_rows;
+  const double per_nnz = M.vals32.p ? 8.0 : 12.0;      // value (single- or double-precision storage) + column index
+  return per_nnz * (double)M.nnz + 4.0 * M.n_rows + 8.0 * M.n_cols + 8.0 * M.n_rows + 8.0 * (double)extra_vectors * M.n_rows;
 }
 static double level_bytes(const CsrDev& A, const CsrDev& P, const CsrDev& R, int reps, double child) {
   double b = 24.0 * A.n_rows;                                                     // x = w D^-1 b
@@ -800,7 +836,7 @@ static double level_bytes(const CsrDev& A, const CsrDev& P, const CsrDev& R, int
 }
 static double amg_bytes(const Amg& M, int l) {
   const int nl = (int)M.levels.size();
-  if (l == nl) return 8.0 * (double)M.n_coarse * M.n_coarse + 16.0 * M.n_coarse;
+  if (l == nl) return (M.coarse_inv32.p ? 4.0 : 8.0) * (double)M.n_coarse * M.n_coarse + 16.0 * M.n_coarse;
   const AmgLevelDev& L = *M.levels[l];
   const int lg = l + M.level0;
   const int reps = (lg >= 1 && lg <= M.gamma_last) ? M.gamma : 1;

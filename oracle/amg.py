@@ -120,8 +120,12 @@ class SAAMG:
     """V(1,1)-cycle with weighted Jacobi (or Chebyshev) smoothing; dense inverse on the coarsest level."""
 
     def __init__(self, A, theta=0.08, max_levels=12, coarse_size=600, smoother="jacobi", cheb_deg=2, filtered=None,
-                 theta_decay=1.0, gamma=1, gamma_last=1 << 20):
+                 theta_decay=1.0, gamma=1, gamma_last=1 << 20, storage="float64"):
+        """storage="float32": the cycle applies the level operators, transfers and the coarsest inverse rounded to single
+        precision (products still accumulated in double) -- how the product stores its hierarchies on the device
+        (csrc/solver.cu::to_f32); the setup and lv["A"] / Ac stay exact for the level-by-level comparisons."""
         self.levels = []
+        self.storage = storage
         self.smoother, self.cheb_deg = smoother, cheb_deg
         self.gamma, self.gamma_last = gamma, gamma_last   # cycle index on levels 1..gamma_last (2: W-cycle)
         A = A.tocsr()
@@ -133,9 +137,19 @@ class SAAMG:
             A = Ac
         self.Ac = A
         self.Ac_inv = np.linalg.inv(A.toarray())
+        rnd = (lambda M: M) if storage == "float64" else self._rounded
+        for lv in self.levels:
+            lv["Aop"], lv["Pop"], lv["Rop"] = rnd(lv["A"]), rnd(lv["P"]), rnd(lv["R"])
+        self.Ac_inv_op = self.Ac_inv if storage == "float64" else self.Ac_inv.astype(np.float32).astype(np.float64)
+
+    @staticmethod
+    def _rounded(M):
+        M = M.copy()
+        M.data = M.data.astype(np.float32).astype(np.float64)
+        return M
 
     def _smooth(self, lv, x, b):
-        A, dinv, rho = lv["A"], lv["dinv"], lv["rho"]
+        A, dinv, rho = lv["Aop"], lv["dinv"], lv["rho"]
         if self.smoother == "jacobi":
             w = (4.0 / 3.0) / rho
             return x + w * dinv * (b - A @ x)
@@ -157,12 +171,12 @@ class SAAMG:
 
     def vcycle(self, b, lvl=0):
         if lvl == len(self.levels):
-            return self.Ac_inv @ b
+            return self.Ac_inv_op @ b
         lv = self.levels[lvl]
         x = self._smooth(lv, np.zeros_like(b), b)
         for _ in range(self.gamma if 1 <= lvl <= self.gamma_last else 1):
-            rc = lv["R"] @ (b - lv["A"] @ x)
-            x = x + lv["P"] @ self.vcycle(rc, lvl + 1)
+            rc = lv["Rop"] @ (b - lv["Aop"] @ x)
+            x = x + lv["Pop"] @ self.vcycle(rc, lvl + 1)
         return self._smooth(lv, x, b)
 
     def __call__(self, b):

@@ -274,7 +274,7 @@ def test_amg_hierarchy_matches_oracle_level_by_level(kb):
     ctx.assemble_P()
     opts = kb.lib.SolveOpts(rtol=1e-9, max_it=100, restart=30, pc=2, project_nullspace=1, zero_mean_solution=0, refine=0)
     ctx.pc_setup(opts)
-    amg = SAAMG(o.assemble_P())
+    amg = SAAMG(o.assemble_P(), storage="float32")      # the device stores the hierarchy operators in single precision
     levels = ctx.amg_levels()
     ref = [lv["A"] for lv in amg.levels] + [amg.Ac]
     assert [a.shape[0] for a in levels] == [a.shape[0] for a in ref]
@@ -339,7 +339,7 @@ def test_c2_iterative_solver_matches_oracle_per_timestep(kb, cfgdir, form):
     s.amg_form = form
     s.time_steps = 1
     o = KNPEMIOracle(unit_square(32), OracleParams(), MODELS_TEST)
-    pc = SchurPC(o) if form == "schur" else SAAMG(o.assemble_P())
+    pc = SchurPC(o, storage="float32") if form == "schur" else SAAMG(o.assemble_P(), storage="float32")
     x = o.pack()
     s.setup_solver(); p.setup_preconditioner(True); s.ctx.pc_setup(s.opts); s.ctx.set_time(0.0, 0)
     assert s.opts.pc == (3 if form == "schur" else 2)
@@ -370,7 +370,7 @@ def test_schur_preconditioner_matches_oracle(kb, name):
     push_oracle_state(ctx, o)
     opts = kb.lib.SolveOpts(rtol=1e-9, max_it=100, restart=30, pc=3, project_nullspace=1, zero_mean_solution=0, refine=0)
     ctx.pc_setup(opts)
-    pc = SchurPC(o)
+    pc = SchurPC(o, storage="float32")                  # the device stores the hierarchy operators in single precision
     for part, amg in ((0, pc.amg_c), (1, pc.amg_p)):
         levels = ctx.amg_levels(part)
         ref = [lv["A"] for lv in amg.levels] + [amg.Ac]
@@ -522,7 +522,7 @@ def test_point_probes_match_oracle_fields(kb, cfgdir):
     s.solve()
     om = unit_square(32)
     o = KNPEMIOracle(om, OracleParams(), MODELS_TEST)
-    pc = SchurPC(o)
+    pc = SchurPC(o, storage="float32")
     x = o.pack()
 
     def interp(field, pt, tag):
@@ -564,7 +564,7 @@ def test_3d_passive_time_loop_matches_oracle(kb):
     opts = kb.lib.SolveOpts(rtol=1e-11, max_it=500, restart=30, pc=2, project_nullspace=1, zero_mean_solution=0, refine=0)
     ctx.pc_setup(opts)
     ctx.set_time(0.0, 0)
-    amg = SAAMG(o.assemble_P())
+    amg = SAAMG(o.assemble_P(), storage="float32")
     x = o.pack()
     for i in range(3):
         info = ctx.step(opts)
