@@ -218,10 +218,12 @@ class SchurPC:
             self.amg_c, self.amg_p = spla.splu(Acc.tocsc()).solve, spla.splu(App.tocsc()).solve
         else:
             amg_kw.setdefault("gamma", 2)
-            amg_kw.setdefault("gamma_last", 3)
             amg_kw.setdefault("coarse_size", 2500)      # dense coarsest solve (inverted on the device in the product)
             self.amg_c = SAAMG(Acc, theta=theta, smoother=smoother, **amg_kw)
             self.amg_p = SAAMG(App, theta=theta, smoother=smoother, **amg_kw)
+            if "gamma_last" not in amg_kw:              # W-cycle on all levels but the finest and the coarsest sparse one
+                for a in (self.amg_c, self.amg_p):
+                    a.gamma_last = max(1, len(a.levels) - 2)
         self.z = np.asarray(p.z, float)
 
     def __call__(self, r):

@@ -649,6 +649,9 @@ int schur_setup(Ctx& c) {
     c.err = knp::last_error();
     return -1;
   }
+  // W-cycle on all levels but the finest and the coarsest sparse one (oracle/amg.py::SchurPC)
+  c.amg_c.gamma_last = std::max(1, (int)c.amg_c.lv.size() - 2);
+  c.amg_p.gamma_last = std::max(1, (int)c.amg_p.lv.size() - 2);
   c.vc.resize(3 * (size_t)(n0 + n1));
   c.zc.resize(3 * (size_t)(n0 + n1));
   c.tt.resize((size_t)n0 + n1);

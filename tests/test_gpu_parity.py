@@ -290,7 +290,10 @@ def test_amg_hierarchy_matches_oracle_level_by_level(kb):
     ctx.to_host(zd.data_ptr(), 1)
     z = zd.cpu().numpy()
     zr = amg(r)
-    assert np.abs(z - zr).max() <= 1e-8 * np.abs(zr).max()
+    # single-precision STORAGE on both sides, but the dense coarsest inverse is computed by different algorithms (device
+    # Gauss-Jordan vs LAPACK) before it is rounded: entries near a rounding boundary land on neighbouring floats (6e-8)
+    assert np.abs(z - zr).max() <= 2e-6 * np.abs(zr).max()
+    assert np.abs(z - SAAMG(o.assemble_P())(r)).max() <= 2e-6 * np.abs(zr).max()      # and against the double-precision cycle
     ctx.close()
 
 
@@ -387,7 +390,8 @@ def test_schur_preconditioner_matches_oracle(kb, name):
     for s in range(2):
         for f in range(4):
             sl = slice(o.base[s] + f * o.ns[s], o.base[s] + (f + 1) * o.ns[s])
-            assert np.abs(z[sl] - zr[sl]).max() <= 1e-8 * np.abs(zr[sl]).max(), (s, f)
+            # single-precision storage of the operators on both sides; see test_amg_hierarchy_matches_oracle_level_by_level
+            assert np.abs(z[sl] - zr[sl]).max() <= 2e-6 * np.abs(zr[sl]).max(), (s, f)
     ctx.close()
 
 
