@@ -17,7 +17,7 @@ struct KParams {
 };
 
 int launch_gate(const DevTopo& T, const KParams& P, const double* u, double* gates, cudaStream_t st);
-int facet_ncomp(int gdim);
+int facet_rec(int gdim);     // doubles per (facet, local vertex) record of the facet staging buffer
 int launch_facets(const DevTopo& T, const KParams& P, const uint32_t* tag_models, const int32_t* tag_stim,
                   const double* u, const double* gates, double stim_fac, double* fe, cudaStream_t st);
 int launch_rows(const DevTopo& T, const KParams& P, int mode, const double* u, const double* fe, double* vals,
@@ -82,6 +82,9 @@ int launch_multi_dot(int n, int m, const double* V, size_t ldv, const double* w,
                      cudaStream_t st);
 // w -= sum_j h[j] V_j   (h on device)
 int launch_multi_axpy(int n, int m, const double* V, size_t ldv, const double* h, double* w, cudaStream_t st);
+// the same, and vnext = w_new * inv_norm in the same pass (Gram-Schmidt projection + normalisation fused)
+int launch_multi_axpy_normalize(int n, int m, const double* V, size_t ldv, const double* h, double* w, double* vnext,
+                                double inv_norm, cudaStream_t st);
 int launch_axpby(int n, double a, const double* x, double b, double* y, cudaStream_t st);              // y = a x + b y
 int launch_scale_copy(int n, const double* alpha_dev, int invert, const double* x, double* y, cudaStream_t st);   // y = x*alpha or x/alpha
 int launch_update_x(int n, int m, const double* V, size_t ldv, const double* y_dev, double* x, const double* scale,

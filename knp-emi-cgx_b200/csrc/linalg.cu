@@ -638,28 +638,40 @@ int launch_multi_dot(int n, int m, const double* V, size_t ldv, const double* w,
   return KNP_OK;
 }
 
+// w += sign * (scale .*) sum_j h[j] V_j ; with vnext: vnext = w_new * inv_norm as well (the next Krylov basis vector in the
+// same pass, when the norm after the projection is already known from ||w||^2 - sum h^2)
 __global__ void __launch_bounds__(256) multi_axpy_kernel(int n, int m, const double* __restrict__ V, size_t ldv,
                                                          const double* __restrict__ h, double sign,
-                                                         const double* __restrict__ scale, double* __restrict__ w) {
+                                                         const double* __restrict__ scale, double* __restrict__ w,
+                                                         double* __restrict__ vnext, double inv_norm) {
   __shared__ double hs[64];
   if (threadIdx.x < m) hs[threadIdx.x] = h[threadIdx.x];
   __syncthreads();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     double acc = 0.0;
     for (int j = 0; j < m; ++j) acc += hs[j] * V[(size_t)j * ldv + i];
-    w[i] += sign * (scale ? scale[i] * acc : acc);
+    const double wi = w[i] + sign * (scale ? scale[i] * acc : acc);
+    w[i] = wi;
+    if (vnext) vnext[i] = wi * inv_norm;
   }
 }
 int launch_multi_axpy(int n, int m, const double* V, size_t ldv, const double* h, double* w, cudaStream_t st) {
   if (n == 0 || m == 0) return KNP_OK;
-  multi_axpy_kernel<<<grid_for(n), 256, 0, st>>>(n, m, V, ldv, h, -1.0, nullptr, w);
+  multi_axpy_kernel<<<grid_for(n), 256, 0, st>>>(n, m, V, ldv, h, -1.0, nullptr, w, nullptr, 0.0);
+  KNP_LAUNCHED();
+  return KNP_OK;
+}
+int launch_multi_axpy_normalize(int n, int m, const double* V, size_t ldv, const double* h, double* w, double* vnext,
+                                double inv_norm, cudaStream_t st) {
+  if (n == 0 || m == 0) return KNP_OK;
+  multi_axpy_kernel<<<grid_for(n), 256, 0, st>>>(n, m, V, ldv, h, -1.0, nullptr, w, vnext, inv_norm);
   KNP_LAUNCHED();
   return KNP_OK;
 }
 int launch_update_x(int n, int m, const double* V, size_t ldv, const double* y_dev, double* x, const double* scale,
                     cudaStream_t st) {
   if (n == 0 || m == 0) return KNP_OK;
-  multi_axpy_kernel<<<grid_for(n), 256, 0, st>>>(n, m, V, ldv, y_dev, 1.0, scale, x);
+  multi_axpy_kernel<<<grid_for(n), 256, 0, st>>>(n, m, V, ldv, y_dev, 1.0, scale, x, nullptr, 0.0);
   KNP_LAUNCHED();
   return KNP_OK;
 }

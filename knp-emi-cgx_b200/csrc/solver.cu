@@ -1023,9 +1023,16 @@ int gmres_solve(knp_ctx* c, const double* A_vals, const double* b, double* x, co
         hsq += hp[i] * hp[i];
       }
       const double before = hp[j + 1];
-      KNP_TRY(launch_multi_axpy(n, j + 1, c->V.p, c->ldv, c->hdev.p, w, st));
       double nrm2 = before - hsq;
-      if (!(nrm2 > 0.5 * before)) {
+      double* vnext = c->V.p + (size_t)(j + 1) * c->ldv;
+      bool normalized = false;
+      if (nrm2 > 0.5 * before) {
+        // no refinement needed (the usual case): the norm after the projection is known from the Pythagorean identity, so
+        // the projection and the normalisation of the next basis vector are ONE pass over w and V
+        KNP_TRY(launch_multi_axpy_normalize(n, j + 1, c->V.p, c->ldv, c->hdev.p, w, vnext, 1.0 / std::sqrt(nrm2), st));
+        normalized = true;
+      } else {
+        KNP_TRY(launch_multi_axpy(n, j + 1, c->V.p, c->ldv, c->hdev.p, w, st));
         KNP_TRY(dots_to_host(c, j + 1, w, hp, st));
         double h2sq = 0.0;
         for (int i = 0; i <= j; ++i) {
@@ -1038,7 +1045,7 @@ int gmres_solve(knp_ctx* c, const double* A_vals, const double* b, double* x, co
       if (nrm2 < 0.0) nrm2 = 0.0;
       const double hn = std::sqrt(nrm2);
       Hat(j + 1, j) = hn;
-      if (hn > 0.0) KNP_TRY(launch_axpby(n, 1.0 / hn, w, 0.0, c->V.p + (size_t)(j + 1) * c->ldv, st));
+      if (hn > 0.0 && !normalized) KNP_TRY(launch_axpby(n, 1.0 / hn, w, 0.0, vnext, st));
       for (int i = 0; i < j; ++i) {
         const double t = cs[i] * Hat(i, j) + sn[i] * Hat(i + 1, j);
         Hat(i + 1, j) = -sn[i] * Hat(i, j) + cs[i] * Hat(i + 1, j);

@@ -7,6 +7,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
+#include <chrono>
+#include <cstdlib>
 #include <numeric>
 #include "common.cuh"
 
@@ -32,6 +34,15 @@ int build_topology(const knp_mesh_desc* m, HostTopo& T) {
   KNP_CHECK(NV < (int64_t)1 << 31 && NC < (int64_t)1 << 31, "local mesh too large for int32 indices");
   KNP_CHECK(m->n_quad > 0 && m->n_quad <= 64 && m->quad_bary && m->quad_w, "facet quadrature rule missing (1..64 points)");
   T.gdim = d;
+  // optional phase timing on stderr (KNP_TOPO_TIMING=1)
+  static const bool timing = getenv("KNP_TOPO_TIMING") && atoi(getenv("KNP_TOPO_TIMING"));
+  auto t_prev = std::chrono::steady_clock::now();
+  auto phase = [&](const char* name) {
+    if (!timing) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "build_topology: %-28s %.3f s\n", name, std::chrono::duration<double>(now - t_prev).count());
+    t_prev = now;
+  };
 
   std::vector<int32_t> itags(m->intra_tags, m->intra_tags + m->n_intra_tags);
   std::sort(itags.begin(), itags.end());
@@ -103,6 +114,7 @@ int build_topology(const knp_mesh_desc* m, HostTopo& T) {
     T.cell_owned[s].push_back(m->cell_owned ? m->cell_owned[c] : 1);
   }
 
+  phase("dof sets, cell tables");
   // ---- node -> cell incidence for owned nodes (cells in ascending order => fixed summation order) ----
   const int W = T.n_work;
   T.inc_ptr.assign(W + 1, 0);
@@ -133,6 +145,7 @@ int build_topology(const knp_mesh_desc* m, HostTopo& T) {
     T.max_inc = std::max(T.max_inc, T.inc_ptr[w + 1] - T.inc_ptr[w]);
   }
 
+  phase("incidence");
   // ---- adjacency (sorted unique subdomain-local node ids, includes the node itself) ----
   T.adj_ptr.assign(W + 1, 0);
   std::vector<int32_t> deg(W);
@@ -183,6 +196,7 @@ int build_topology(const knp_mesh_desc* m, HostTopo& T) {
     }
   }
 
+  phase("adjacency, packed slots");
   // ---- membrane ----
   T.n_mf = (int)NF;
   std::vector<int32_t> mvid(NV, -1);
@@ -247,6 +261,10 @@ int build_topology(const knp_mesh_desc* m, HostTopo& T) {
         ++fill[g];
       }
   }
+  // (facet, local vertex) -> incidence index: the facet kernel stores its tensors incidence-major, i.e. in the order in
+  // which the row kernel walks them (membrane vertex by membrane vertex)
+  T.mf_minc.assign((size_t)NF * d, 0);
+  for (int k = 0; k < T.minc_ptr[T.n_mv]; ++k) T.mf_minc[(size_t)minc_f[k] * d + minc_a[k]] = k;
   T.gam_ptr.assign(T.n_mv + 1, 0);
   std::vector<std::vector<int32_t>> gam(T.n_mv);
   int maxg = 0;
@@ -303,6 +321,7 @@ int build_topology(const knp_mesh_desc* m, HostTopo& T) {
     }
   }
 
+  phase("membrane tables");
   // ---- CSR row pointers of A and P ----
   T.gpre.assign(W + 1, 0);
   for (int w = 0; w < W; ++w) {
@@ -331,6 +350,7 @@ int build_topology(const knp_mesh_desc* m, HostTopo& T) {
   T.nnz = pos;
   T.nnz_P = posP;
 
+  phase("row pointers");
   // ---- lane-group tables of the edge-lane row kernel (assembly.cu::rows_edge_kernel) ----
   // A dof is served by G = 2^lgG lanes, lane e = adjacency slot e.  Per (dof, slot), at index (w << lgG) + e:
   //   adjG   the neighbour (subdomain-local node id), -1 beyond the degree
@@ -392,6 +412,7 @@ int build_topology(const knp_mesh_desc* m, HostTopo& T) {
       }
     }
   }
+  phase("lane-group tables");
   return KNP_OK;
 }
 
