@@ -80,7 +80,6 @@ int knp_create(knp_ctx** out, const knp_mesh_desc* mesh, int device) {
   KNP_TRY(c->d_gam_ptr.upload(H.gam_ptr));
   KNP_TRY(c->d_gam_mv.upload(H.gam_mv));
   KNP_TRY(c->d_minc_ptr.upload(H.minc_ptr));
-  KNP_TRY(c->d_mf_minc.upload(H.mf_minc));
   KNP_TRY(c->d_minc.upload(H.minc));
   {
     std::vector<int32_t> ip(H.indptr), ipP(H.indptr_P);
@@ -130,7 +129,6 @@ int knp_create(knp_ctx** out, const knp_mesh_desc* mesh, int device) {
   T.gam_ptr = c->d_gam_ptr.p;
   T.gam_mv = c->d_gam_mv.p;
   T.minc_ptr = c->d_minc_ptr.p;
-  T.mf_minc = c->d_mf_minc.p;
   T.minc = c->d_minc.p;
   T.indptr = c->d_indptr.p;
   T.indptr_P = c->d_indptr_P.p;
@@ -153,7 +151,7 @@ int knp_create(knp_ctx** out, const knp_mesh_desc* mesh, int device) {
   KNP_TRY(c->A_vals.alloc(H.nnz));
   KNP_TRY(c->P_vals.alloc(H.nnz_P));
   KNP_TRY(c->b.alloc(T.L.n_rows));
-  KNP_TRY(c->fe.alloc((size_t)facet_rec(H.gdim) * H.gdim * (T.n_mf > 0 ? T.n_mf : 1)));   // one record per (facet, vertex)
+  KNP_TRY(c->fe.alloc((size_t)facet_ncomp(H.gdim) * (T.n_mf > 0 ? T.n_mf : 1)));
   KNP_CUDA(cudaMemsetAsync(c->u.p, 0, (size_t)T.L.n_cols * sizeof(double), c->stream));
   KNP_TRY(c->fpartial.alloc(1024));
   KNP_TRY(c->fout.alloc(8));

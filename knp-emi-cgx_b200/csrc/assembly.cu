@@ -59,17 +59,10 @@ __global__ void gate_kernel(DevTopo T, KParams P, const double* __restrict__ u, 
 }
 
 // ------------------------------------------------------------------------------------------------ facets
-// Staging layout: INCIDENCE-MAJOR records, one per (facet f, local vertex a), stored at the position at which the row kernel
-// meets the incidence when it walks the facets of a membrane vertex (T.mf_minc[f * D + a]), so that the lane group of a
-// membrane dof reads a few contiguous lines instead of one strided double per component:
-//   rec[(s*3+k)*D + b]   = GA[s][k][a][b]      6*D      row a of the alpha_k-weighted facet mass matrices (both sides)
-//   rec[6*D + s*3+k]     = bc[s][k][a]         6        already divided by F z_k
-//   rec[6*D + 6]         = bphi[a]             1        already divided by F
-// FACET_REC = 6*D + 7 rounded up to even (16-byte records).
-template <int D>
-struct FacetRec {
-  static constexpr int value = (6 * D + 7 + 1) & ~1;
-};
+// Staging layout (component-major, facet fastest):
+//   GA  : ((s*3+k)*NS + ab)            6*NS      NS = D(D+1)/2
+//   bc  : 6*NS + (s*3+k)*D + a         6*D       already divided by F z_k
+//   bphi: 6*NS + 6*D + a               D         already divided by F
 template <int D>
 __global__ void __launch_bounds__(128) facet_kernel(DevTopo T, KParams P, const uint32_t* __restrict__ tag_models,
                                                     const int32_t* __restrict__ tag_stim,
@@ -230,20 +223,19 @@ __global__ void __launch_bounds__(128) facet_kernel(DevTopo T, KParams P, const 
 #pragma unroll
     for (int a = 0; a < D; ++a) bphi[a] += rp * lam[a];
   }
-  constexpr int REC = FacetRec<D>::value;
+  const size_t nf = (size_t)T.n_mf;
 #pragma unroll
-  for (int a = 0; a < D; ++a) {
-    double* rec = fe + (size_t)T.mf_minc[(size_t)f * D + a] * REC;
+  for (int s = 0; s < 2; ++s)
 #pragma unroll
-    for (int s = 0; s < 2; ++s)
+    for (int k = 0; k < 3; ++k) {
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
+      for (int i = 0; i < NS; ++i) fe[(size_t)((s * 3 + k) * NS + i) * nf + f] = GA[s][k][i];
+      const double inv = 1.0 / (P.F * P.z[k]);
 #pragma unroll
-        for (int b = 0; b < D; ++b) rec[(s * 3 + k) * D + b] = GA[s][k][a <= b ? symidx(a, b, D) : symidx(b, a, D)];
-        rec[6 * D + s * 3 + k] = bc[s][k][a] * (1.0 / (P.F * P.z[k]));
-      }
-    rec[6 * D + 6] = bphi[a] / P.F;
-  }
+      for (int a = 0; a < D; ++a) fe[(size_t)(6 * NS + (s * 3 + k) * D + a) * nf + f] = bc[s][k][a] * inv;
+    }
+#pragma unroll
+  for (int a = 0; a < D; ++a) fe[(size_t)(6 * NS + 6 * D + a) * nf + f] = bphi[a] / P.F;
 }
 
 // ------------------------------------------------------------------------------------------------ rows
@@ -349,6 +341,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, ROWS_MIN_CTAS) rows_kernel(DevTo
                                                                double* __restrict__ vals, double* __restrict__ bvec,
                                                                RowsSmem S, int ntile0) {
   constexpr int NV = D + 1;
+  constexpr int NS = D * (D + 1) / 2;
   constexpr int NB = D + 3;                 // doubles per staged neighbour: coordinates + 3 concentrations
   constexpr int NR = NV + 4;                // doubles per (node, cell) result: stiffness row, mass weight, cbar[3]
   constexpr uint32_t VMASK = NV == 4 ? 0xFFFFFFFFu : 0x00FFFFFFu;
@@ -479,6 +472,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, ROWS_MIN_CTAS) rows_kernel(DevTo
   // membrane (dS) terms: KNPEMIx_problem.py:599,604,609-610,637-638,641-642 (P: :737-738); lane e serves adjacency
   // slot e and gamma slot e (couplings to the potential on the other side of the membrane)
   if (g >= 0 && (has_ent || has_gam)) {
+    const size_t nf = (size_t)T.n_mf;
     const double sgn = s == 0 ? 1.0 : -1.0;
     const int m1 = T.minc_ptr[g + 1];
     for (int mi = T.minc_ptr[g]; mi < m1; ++mi) {
@@ -488,13 +482,13 @@ __global__ void __launch_bounds__(ROWS_THREADS, ROWS_MIN_CTAS) rows_kernel(DevTo
       const uint32_t ss = s == 0 ? (rec.y >> 8) : rec.z;
       const uint32_t ms = has_ent ? (__vcmpeq4(ss, rep) & FMASK) : 0u;
       const uint32_t mg = has_gam ? (__vcmpeq4(rec.w, rep) & FMASK) : 0u;
-      const double* __restrict__ frec = fe + (size_t)mi * FacetRec<D>::value;      // this incidence's record
       if (ms) {
         const int b = (__ffs(ms) - 1) >> 3;
         const double G1 = T.mf_area[f] * ((a == b) ? 2.0 : 1.0) * (1.0 / (D * (D + 1)));
         if (MODE == 0) {
+          const int ab = a <= b ? symidx(a, b, D) : symidx(b, a, D);
 #pragma unroll
-          for (int k = 0; k < 3; ++k) kphi_m[k] += C.cmz[k] * frec[(s * 3 + k) * D + b];
+          for (int k = 0; k < 3; ++k) kphi_m[k] += C.cmz[k] * fe[(size_t)((s * 3 + k) * NS + ab) * nf + f];
           pp_m += C.cf * G1;
         } else {
           pp_m -= C.cf * G1;
@@ -502,14 +496,15 @@ __global__ void __launch_bounds__(ROWS_THREADS, ROWS_MIN_CTAS) rows_kernel(DevTo
       }
       if (MODE == 0 && mg) {
         const int b = (__ffs(mg) - 1) >> 3;
+        const int ab = a <= b ? symidx(a, b, D) : symidx(b, a, D);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) ga[k] += C.cmz[k] * frec[(s * 3 + k) * D + b];
+        for (int k = 0; k < 3; ++k) ga[k] += C.cmz[k] * fe[(size_t)((s * 3 + k) * NS + ab) * nf + f];
         g1 += C.cf * (T.mf_area[f] * ((a == b) ? 2.0 : 1.0) * (1.0 / (D * (D + 1))));
       }
       if (MODE == 0 && is_self) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) bmem[k] -= sgn * frec[6 * D + s * 3 + k];
-        bmem[3] -= sgn * frec[6 * D + 6];
+        for (int k = 0; k < 3; ++k) bmem[k] -= sgn * fe[(size_t)(6 * NS + (s * 3 + k) * D + a) * nf + f];
+        bmem[3] -= sgn * fe[(size_t)(6 * NS + 6 * D + a) * nf + f];
       }
     }
   }
@@ -790,7 +785,7 @@ int launch_gate(const DevTopo& T, const KParams& P, const double* u, double* gat
   return KNP_OK;
 }
 
-int facet_rec(int gdim) { return gdim == 2 ? FacetRec<2>::value : FacetRec<3>::value; }
+int facet_ncomp(int gdim) { return 6 * (gdim * (gdim + 1) / 2) + 7 * gdim; }
 
 int launch_facets(const DevTopo& T, const KParams& P, const uint32_t* tag_models, const int32_t* tag_stim,
                   const double* u, const double* gates, double stim_fac, double* fe, cudaStream_t st) {
@@ -862,6 +857,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, D == 3 ? EDGE_MIN_CTAS_3D : EDGE
                                                                                 double* __restrict__ vals, double* __restrict__ bvec,
                                                                                 int ntile0, int ntiles, int stg_doubles) {
   constexpr int G = 1 << LG, TILE = 32 / G;                                      // dofs per warp (mini-tile)
+  constexpr int NS = D * (D + 1) / 2;
   constexpr int NB = EDGE_NB;
   constexpr int HW = D == 2 ? 1 : 4;
   constexpr uint32_t FMASK = D == 3 ? 0x00FFFFFFu : 0x0000FFFFu;
@@ -1046,6 +1042,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, D == 3 ? EDGE_MIN_CTAS_3D : EDGE
     // membrane (dS) terms: KNPEMIx_problem.py:599,604,609-610,637-638,641-642 (P: :737-738); lane e serves adjacency
     // slot e and gamma slot e (couplings to the potential on the other side of the membrane)
     if (g >= 0 && (has_ent || has_gam)) {
+      const size_t nf = (size_t)T.n_mf;
       const double sgn = s == 0 ? 1.0 : -1.0;
       const int m1 = T.minc_ptr[g + 1];
       for (int mi = T.minc_ptr[g]; mi < m1; ++mi) {
@@ -1055,13 +1052,13 @@ __global__ void __launch_bounds__(EDGE_THREADS, D == 3 ? EDGE_MIN_CTAS_3D : EDGE
         const uint32_t ss = s == 0 ? (rec.y >> 8) : rec.z;
         const uint32_t ms = has_ent ? (__vcmpeq4(ss, rep) & FMASK) : 0u;
         const uint32_t mg = has_gam ? (__vcmpeq4(rec.w, rep) & FMASK) : 0u;
-        const double* __restrict__ frec = fe + (size_t)mi * FacetRec<D>::value;      // this incidence's record
         if (ms) {
           const int b = (__ffs(ms) - 1) >> 3;
           const double G1 = T.mf_area[f] * ((a == b) ? 2.0 : 1.0) * (1.0 / (D * (D + 1)));
           if (MODE == 0) {
+            const int ab = a <= b ? symidx(a, b, D) : symidx(b, a, D);
 #pragma unroll
-            for (int k = 0; k < 3; ++k) kphi_m[k] += C.cmz[k] * frec[(s * 3 + k) * D + b];
+            for (int k = 0; k < 3; ++k) kphi_m[k] += C.cmz[k] * fe[(size_t)((s * 3 + k) * NS + ab) * nf + f];
             pp_m += C.cf * G1;
           } else {
             pp_m -= C.cf * G1;
@@ -1069,14 +1066,15 @@ __global__ void __launch_bounds__(EDGE_THREADS, D == 3 ? EDGE_MIN_CTAS_3D : EDGE
         }
         if (MODE == 0 && mg) {
           const int b = (__ffs(mg) - 1) >> 3;
+          const int ab = a <= b ? symidx(a, b, D) : symidx(b, a, D);
 #pragma unroll
-          for (int k = 0; k < 3; ++k) ga[k] += C.cmz[k] * frec[(s * 3 + k) * D + b];
+          for (int k = 0; k < 3; ++k) ga[k] += C.cmz[k] * fe[(size_t)((s * 3 + k) * NS + ab) * nf + f];
           g1 += C.cf * (T.mf_area[f] * ((a == b) ? 2.0 : 1.0) * (1.0 / (D * (D + 1))));
         }
         if (MODE == 0 && is_self) {
 #pragma unroll
-          for (int k = 0; k < 3; ++k) bmem[k] -= sgn * frec[6 * D + s * 3 + k];
-          bmem[3] -= sgn * frec[6 * D + 6];
+          for (int k = 0; k < 3; ++k) bmem[k] -= sgn * fe[(size_t)(6 * NS + (s * 3 + k) * D + a) * nf + f];
+          bmem[3] -= sgn * fe[(size_t)(6 * NS + 6 * D + a) * nf + f];
         }
       }
     }

@@ -112,7 +112,6 @@ struct HostTopo {
   std::vector<int32_t> mtags;                 // sorted unique membrane tags
   std::vector<int32_t> gam_ptr, gam_mv;       // per membrane vertex: sorted neighbouring membrane vertices (incl. self)
   std::vector<int32_t> minc_ptr;              // per membrane vertex: incident facets
-  std::vector<int32_t> mf_minc;               // [n_mf][gdim]: incidence index of (facet, local vertex)
   std::vector<uint32_t> minc;                 // 4 words per incidence: facet, a|slots_i<<8, slots_e, slots_gam
   // cells per subdomain (for functionals)
   std::vector<int32_t> cell_nodes[2];         // [(gdim+1) per cell] subdomain-local node ids
@@ -137,7 +136,7 @@ struct DevTopo {
   const double* node_x;
   const int32_t *adj_ptr, *adj_idx, *inc_ptr, *self_slot, *mv_of_node;
   const uint32_t* inc_slots;
-  const int32_t *mv_node0, *mv_node1, *mf_mv, *mf_tagidx, *gam_ptr, *gam_mv, *minc_ptr, *mf_minc;
+  const int32_t *mv_node0, *mv_node1, *mf_mv, *mf_tagidx, *gam_ptr, *gam_mv, *minc_ptr;
   const double* mf_area;
   const uint32_t* minc;
   const int32_t *indptr, *indptr_P;

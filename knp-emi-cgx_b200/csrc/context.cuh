@@ -69,7 +69,7 @@ struct knp_ctx {
   knp::DevBuf<int32_t> d_adj_ptr, d_adj_idx, d_inc_ptr, d_self_slot, d_mv_of_node, d_gpre;
   knp::DevBuf<uint32_t> d_inc_slots, d_minc, d_hitG;
   knp::DevBuf<int32_t> d_adjG, d_metaG;
-  knp::DevBuf<int32_t> d_mv_node0, d_mv_node1, d_mf_mv, d_mf_tagidx, d_gam_ptr, d_gam_mv, d_minc_ptr, d_mf_minc;
+  knp::DevBuf<int32_t> d_mv_node0, d_mv_node1, d_mf_mv, d_mf_tagidx, d_gam_ptr, d_gam_mv, d_minc_ptr;
   knp::DevBuf<int32_t> d_indptr, d_indices, d_indptr_P, d_indices_P, d_rowblk_A;
   int nblk_A = 0;
   knp::DevBuf<int32_t> d_cell_nodes[2], d_cell_tag[2], d_cell_owned[2];

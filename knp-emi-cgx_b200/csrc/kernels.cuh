@@ -17,7 +17,7 @@ struct KParams {
 };
 
 int launch_gate(const DevTopo& T, const KParams& P, const double* u, double* gates, cudaStream_t st);
-int facet_rec(int gdim);     // doubles per (facet, local vertex) record of the facet staging buffer
+int facet_ncomp(int gdim);
 int launch_facets(const DevTopo& T, const KParams& P, const uint32_t* tag_models, const int32_t* tag_stim,
                   const double* u, const double* gates, double stim_fac, double* fe, cudaStream_t st);
 int launch_rows(const DevTopo& T, const KParams& P, int mode, const double* u, const double* fe, double* vals,

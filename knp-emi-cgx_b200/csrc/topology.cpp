@@ -261,10 +261,6 @@ int build_topology(const knp_mesh_desc* m, HostTopo& T) {
         ++fill[g];
       }
   }
-  // (facet, local vertex) -> incidence index: the facet kernel stores its tensors incidence-major, i.e. in the order in
-  // which the row kernel walks them (membrane vertex by membrane vertex)
-  T.mf_minc.assign((size_t)NF * d, 0);
-  for (int k = 0; k < T.minc_ptr[T.n_mv]; ++k) T.mf_minc[(size_t)minc_f[k] * d + minc_a[k]] = k;
   T.gam_ptr.assign(T.n_mv + 1, 0);
   std::vector<std::vector<int32_t>> gam(T.n_mv);
   int maxg = 0;
