@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(128) facet_kernel(DevTopo T, KParams P, const 
       mq += lam[a] * gm[a];
       hq += lam[a] * gh[a];
     }
-    // alpha_{k,s} (KNPEMIx_problem.py:512-513,582-583)
+    // alpha_{k,s} (KNPEMIx_problem.py:512-513,582-583); one reciprocal per side instead of three divisions
     double al[2][3];
     {
       double di = 0.0, de = 0.0;
@@ -139,19 +139,25 @@ __global__ void __launch_bounds__(128) facet_kernel(DevTopo T, KParams P, const 
         di += P.D[k] * P.z[k] * P.z[k] * ciq[k];
         de += P.D[k] * P.z[k] * P.z[k] * ceq[k];
       }
+      const double idi = 1.0 / di, ide = 1.0 / de;
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        al[0][k] = P.D[k] * P.z[k] * P.z[k] * ciq[k] / di;
-        al[1][k] = P.D[k] * P.z[k] * P.z[k] * ceq[k] / de;
+        al[0][k] = (P.D[k] * P.z[k] * P.z[k] * ciq[k]) * idi;
+        al[1][k] = (P.D[k] * P.z[k] * P.z[k] * ceq[k]) * ide;
       }
     }
-    // Nernst potentials (KNPEMIx_problem.py:516)
-    double E[3];
+    // Nernst potentials (KNPEMIx_problem.py:516): lg[k] = log(c_e / c_i) is shared with the cotransporter currents, whose
+    // argument (K_i Cl_i) / (K_e Cl_e) is exp(-(lg[1] + lg[2]))
+    double E[3], lg[3], ici[3];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) E[k] = (psi / P.z[k]) * log(ceq[k] / ciq[k]);
+    for (int k = 0; k < 3; ++k) {
+      ici[k] = 1.0 / ciq[k];
+      lg[k] = log(ceq[k] * ici[k]);
+      E[k] = (psi / P.z[k]) * lg[k];
+    }
     double I[3] = {0.0, 0.0, 0.0};
     if (models & KNP_MODEL_NEURONAL_CT) {      // KNPEMIx_ionic_model.py:342-369 (f_NKCC1 == 0, :50-75)
-      const double I_KCC2 = 0.0068 * log((ciq[1] * ciq[2]) / (ceq[1] * ceq[2]));
+      const double I_KCC2 = -0.0068 * (lg[1] + lg[2]);
       I[1] += I_KCC2;
       I[2] += -I_KCC2;
     }
@@ -176,20 +182,20 @@ __global__ void __launch_bounds__(128) facet_kernel(DevTopo T, KParams P, const 
     }
     if (models & KNP_MODEL_ATP) {              // :385-422
       const double p1 = 1.0 + 1.5 / ceq[1];
-      const double p2 = 1.0 + 10.0 / ciq[0];
+      const double p2 = 1.0 + 10.0 * ici[0];
       const double I_ATP = 0.25 / ((p1 * p1) * (p2 * p2 * p2));
       I[0] += 3.0 * I_ATP;
       I[1] += -2.0 * I_ATP;
     }
     if (models & KNP_MODEL_GLIAL_CT) {         // :239-298 (f_NKCC1 == 0)
-      const double I_KCC1 = (7e-2 * psi) * log((ciq[1] * ciq[2]) / (ceq[1] * ceq[2]));
+      const double I_KCC1 = -(7e-2 * psi) * (lg[1] + lg[2]);
       I[1] += I_KCC1;
       I[2] += -I_KCC1;
     }
     if (models & KNP_MODEL_KIRNA) {            // :117-222
       const double E_K_init = psi * log(P.K_e_init / P.K_i_g_init);
       const double rho = 1.1 * 1.12e-6;
-      const double r = 10.0 / ciq[0];
+      const double r = 10.0 * ici[0];
       const double pump = (1.0 / (1.0 + r * sqrt(r))) * (1.0 / (1.0 + 1.5 / ceq[1])) * rho;
       const double A_ = 1.0 + exp(0.433);
       const double B_ = 1.0 + exp(-(0.1186 + E_K_init) / 0.0441);

@@ -78,13 +78,14 @@ int launch_amg_tail(const TailOp* ops_dev, int nops, unsigned* bar, cudaStream_t
 // Gram-Schmidt building blocks (deterministic two-stage reductions; no atomics)
 constexpr int RED_BLOCKS = 1184;   // 8 x 148 SMs: full occupancy for the streaming reductions
 // out[j] = sum_i V[j*ldv + i] * w[i], j < m ; out[m] = sum_i w[i]^2 ; partial is (m+1) x RED_BLOCKS scratch
+// jsub >= 0: w is replaced on the fly by d = w - V[jsub]
 int launch_multi_dot(int n, int m, const double* V, size_t ldv, const double* w, double* partial, double* out,
-                     cudaStream_t st);
+                     cudaStream_t st, int jsub = -1);
 // w -= sum_j h[j] V_j   (h on device)
-int launch_multi_axpy(int n, int m, const double* V, size_t ldv, const double* h, double* w, cudaStream_t st);
+int launch_multi_axpy(int n, int m, const double* V, size_t ldv, const double* h, double* w, cudaStream_t st, int jsub = -1);
 // the same, and vnext = w_new * inv_norm in the same pass (Gram-Schmidt projection + normalisation fused)
 int launch_multi_axpy_normalize(int n, int m, const double* V, size_t ldv, const double* h, double* w, double* vnext,
-                                double inv_norm, cudaStream_t st);
+                                double inv_norm, cudaStream_t st, int jsub = -1);
 int launch_axpby(int n, double a, const double* x, double b, double* y, cudaStream_t st);              // y = a x + b y
 int launch_scale_copy(int n, const double* alpha_dev, int invert, const double* x, double* y, cudaStream_t st);   // y = x*alpha or x/alpha
 int launch_update_x(int n, int m, const double* V, size_t ldv, const double* y_dev, double* x, const double* scale,

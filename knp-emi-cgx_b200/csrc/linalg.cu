@@ -575,22 +575,24 @@ __device__ __forceinline__ double block_reduce_256(double v, double* red) {
   return r;
 }
 
-constexpr int MD_CHUNK = 8;   // basis vectors handled per pass over w
+constexpr int MD_CHUNK = 16;   // basis vectors handled per pass over w
 
-// partial[(j)*RED_BLOCKS + blk] ; j in [j0, j0+cnt) for V rows, and slot m for ||w||^2 when with_norm
+// partial[(j)*RED_BLOCKS + blk] ; j in [j0, j0+cnt) for V rows, and slot m for ||w||^2 when with_norm.
+// jsub >= 0: the dots are taken with d = w - V[jsub] formed on the fly (gmres_solve orthogonalises (B A - I) v_j, see there).
 __global__ void __launch_bounds__(256) multi_dot_kernel(int n, int j0, int cnt, int m, int with_norm,
                                                         const double* __restrict__ V, size_t ldv,
-                                                        const double* __restrict__ w, double* __restrict__ partial) {
+                                                        const double* __restrict__ w, double* __restrict__ partial, int jsub) {
   __shared__ double red[8];
   double acc[MD_CHUNK + 1];
 #pragma unroll
   for (int j = 0; j <= MD_CHUNK; ++j) acc[j] = 0.0;
-  // contiguous slab per block => fixed summation order independent of the launch schedule
-  const int per = (n + gridDim.x - 1) / gridDim.x;
-  const int lo = blockIdx.x * per;
-  const int hi = min(n, lo + per);
-  for (int i = lo + threadIdx.x; i < hi; i += 256) {
-    const double wi = w[i];
+  // Block b takes the 256-element chunks b, b + G, b + 2G, ... (G = gridDim.x, a compile-time constant of the launch): the
+  // summation order is fixed whatever the launch schedule, and at any moment the grid works on ONE window of every row,
+  // i.e. ~18 sequential DRAM streams instead of 18 per block (the former slab-per-block split kept 2e4 streams open and
+  // reached 2.6 TB/s)
+  const double* __restrict__ vsub = jsub >= 0 ? V + (size_t)jsub * ldv : nullptr;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+    const double wi = vsub ? w[i] - vsub[i] : w[i];
 #pragma unroll
     for (int j = 0; j < MD_CHUNK; ++j)
       if (j < cnt) acc[j] += V[(size_t)(j0 + j) * ldv + i] * wi;
@@ -623,14 +625,14 @@ __global__ void reduce_rows_kernel(int rows, int n_partial, const double* __rest
 }
 
 int launch_multi_dot(int n, int m, const double* V, size_t ldv, const double* w, double* partial, double* out,
-                     cudaStream_t st) {
+                     cudaStream_t st, int jsub) {
   if (m == 0) {
-    multi_dot_kernel<<<RED_BLOCKS, 256, 0, st>>>(n, 0, 0, 0, 1, V, ldv, w, partial);
+    multi_dot_kernel<<<RED_BLOCKS, 256, 0, st>>>(n, 0, 0, 0, 1, V, ldv, w, partial, jsub);
     KNP_LAUNCHED();
   }
   for (int j0 = 0; j0 < m; j0 += MD_CHUNK) {
     const int cnt = m - j0 < MD_CHUNK ? m - j0 : MD_CHUNK;
-    multi_dot_kernel<<<RED_BLOCKS, 256, 0, st>>>(n, j0, cnt, m, j0 == 0 ? 1 : 0, V, ldv, w, partial);
+    multi_dot_kernel<<<RED_BLOCKS, 256, 0, st>>>(n, j0, cnt, m, j0 == 0 ? 1 : 0, V, ldv, w, partial, jsub);
     KNP_LAUNCHED();
   }
   reduce_rows_kernel<<<(m + 1 + 7) / 8, 256, 0, st>>>(m + 1, RED_BLOCKS, partial, out);
@@ -643,35 +645,39 @@ int launch_multi_dot(int n, int m, const double* V, size_t ldv, const double* w,
 __global__ void __launch_bounds__(256) multi_axpy_kernel(int n, int m, const double* __restrict__ V, size_t ldv,
                                                          const double* __restrict__ h, double sign,
                                                          const double* __restrict__ scale, double* __restrict__ w,
-                                                         double* __restrict__ vnext, double inv_norm) {
+                                                         double* __restrict__ vnext, double inv_norm, int jsub) {
   __shared__ double hs[64];
   if (threadIdx.x < m) hs[threadIdx.x] = h[threadIdx.x];
   __syncthreads();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    double acc = 0.0;
-    for (int j = 0; j < m; ++j) acc += hs[j] * V[(size_t)j * ldv + i];
-    const double wi = w[i] + sign * (scale ? scale[i] * acc : acc);
+    double acc = 0.0, sub = 0.0;
+    for (int j = 0; j < m; ++j) {
+      const double vj = V[(size_t)j * ldv + i];
+      acc += hs[j] * vj;
+      if (j == jsub) sub = vj;                    // jsub >= 0: the projected vector is d = w - V[jsub]
+    }
+    const double wi = (w[i] - sub) + sign * (scale ? scale[i] * acc : acc);
     w[i] = wi;
     if (vnext) vnext[i] = wi * inv_norm;
   }
 }
-int launch_multi_axpy(int n, int m, const double* V, size_t ldv, const double* h, double* w, cudaStream_t st) {
+int launch_multi_axpy(int n, int m, const double* V, size_t ldv, const double* h, double* w, cudaStream_t st, int jsub) {
   if (n == 0 || m == 0) return KNP_OK;
-  multi_axpy_kernel<<<grid_for(n), 256, 0, st>>>(n, m, V, ldv, h, -1.0, nullptr, w, nullptr, 0.0);
+  multi_axpy_kernel<<<grid_for(n), 256, 0, st>>>(n, m, V, ldv, h, -1.0, nullptr, w, nullptr, 0.0, jsub);
   KNP_LAUNCHED();
   return KNP_OK;
 }
 int launch_multi_axpy_normalize(int n, int m, const double* V, size_t ldv, const double* h, double* w, double* vnext,
-                                double inv_norm, cudaStream_t st) {
+                                double inv_norm, cudaStream_t st, int jsub) {
   if (n == 0 || m == 0) return KNP_OK;
-  multi_axpy_kernel<<<grid_for(n), 256, 0, st>>>(n, m, V, ldv, h, -1.0, nullptr, w, vnext, inv_norm);
+  multi_axpy_kernel<<<grid_for(n), 256, 0, st>>>(n, m, V, ldv, h, -1.0, nullptr, w, vnext, inv_norm, jsub);
   KNP_LAUNCHED();
   return KNP_OK;
 }
 int launch_update_x(int n, int m, const double* V, size_t ldv, const double* y_dev, double* x, const double* scale,
                     cudaStream_t st) {
   if (n == 0 || m == 0) return KNP_OK;
-  multi_axpy_kernel<<<grid_for(n), 256, 0, st>>>(n, m, V, ldv, y_dev, 1.0, scale, x, nullptr, 0.0);
+  multi_axpy_kernel<<<grid_for(n), 256, 0, st>>>(n, m, V, ldv, y_dev, 1.0, scale, x, nullptr, 0.0, -1);
   KNP_LAUNCHED();
   return KNP_OK;
 }
@@ -716,10 +722,8 @@ __global__ void __launch_bounds__(256) range_sum_kernel(const double* __restrict
                                                         int hi1, double* __restrict__ partial) {
   __shared__ double red[8];
   const int n0 = hi0 - lo0, n = n0 + (hi1 - lo1);
-  const int per = (n + gridDim.x - 1) / gridDim.x;
-  const int lo = blockIdx.x * per, hi = min(n, lo + per);
   double acc = 0.0;
-  for (int i = lo + threadIdx.x; i < hi; i += 256) acc += x[i < n0 ? lo0 + i : lo1 + (i - n0)];
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) acc += x[i < n0 ? lo0 + i : lo1 + (i - n0)];
   const double r = block_reduce_256(acc, red);
   if (threadIdx.x == 0) partial[blockIdx.x] = r;
 }

@@ -754,6 +754,12 @@ int gmres(Ctx& c, double rtol, int maxit, int* iterations) {
       apply_B(c, r.data(), w);
       tB += omp_get_wtime() - tq;
       tq = omp_get_wtime();
+      // Gram-Schmidt on d = (B A - I) v_j (oracle/knpemi.py::solve_gmres): H(:, j) = e_j + V^T d
+      {
+        const double* vj = V + (size_t)j * n;
+#pragma omp parallel for schedule(static)
+        for (int i = 0; i < n; ++i) w[i] -= vj[i];
+      }
       double before = 0.0;
       std::fill(h.begin(), h.end(), 0.0);
 #pragma omp parallel
@@ -780,7 +786,7 @@ int gmres(Ctx& c, double rtol, int maxit, int* iterations) {
       double hh = 0.0;
       for (int k = 0; k <= j; ++k) hh += h[k] * h[k];
       double nrm2 = before - hh;
-      if (!(nrm2 > 0.5 * before)) {              // DGKS refinement only if needed (PETSc default)
+      if (!(nrm2 > 0.01 * before)) {             // second pass only after a cancellation by more than 10 (oracle/knpemi.py)
         double w2 = 0.0;
         std::fill(h2.begin(), h2.end(), 0.0);
         for (int k = 0; k <= j; ++k) h2[k] = dot(V + (size_t)k * n, w, n);
@@ -798,7 +804,7 @@ int gmres(Ctx& c, double rtol, int maxit, int* iterations) {
         }
         nrm2 = w2 - hh2;
       }
-      for (int k = 0; k <= j; ++k) Hat(k, j) = h[k];
+      for (int k = 0; k <= j; ++k) Hat(k, j) = h[k] + (k == j ? 1.0 : 0.0);
       const double hn = std::sqrt(std::max(nrm2, 0.0));
       Hat(j + 1, j) = hn;
       if (hn > 0.0) {

@@ -506,18 +506,22 @@ class KNPEMIOracle:
             cs, sn = np.zeros(restart), np.zeros(restart)
             j_done = 0
             for j in range(restart):
-                w = B(A @ V[j])
+                # Gram-Schmidt on d = (B A - I) v_j instead of w = B A v_j: same Krylov space, H(:, j) = e_j + V^T d, same
+                # new direction, but no cancellation when B A is close to the identity (the product does the same,
+                # csrc/solver.cu::gmres_solve)
+                w = B(A @ V[j]) - V[j]
                 h = V[: j + 1] @ w
                 before = w @ w
                 w = w - V[: j + 1].T @ h
                 nrm2 = before - h @ h
-                if not (nrm2 > 0.5 * before):          # DGKS refinement only if needed (PETSc default)
+                if not (nrm2 > 0.01 * before):         # second pass only after a cancellation by more than 10 (see the product)
                     h2 = V[: j + 1] @ w
                     w2 = w @ w
                     w = w - V[: j + 1].T @ h2
                     h = h + h2
                     nrm2 = w2 - h2 @ h2
                 H[: j + 1, j] = h
+                H[j, j] += 1.0
                 H[j + 1, j] = np.sqrt(max(nrm2, 0.0))
                 if H[j + 1, j] > 0:
                     V[j + 1] = w / H[j + 1, j]
