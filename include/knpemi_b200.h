@@ -165,6 +165,14 @@ int knp_assemble_P(knp_ctx* ctx, double* P_vals_dev, void* stream);
  * (rows unique, owned).  Carries the ion-injection terms dt * (f_e, v)_{dx_e} of KNP-EMI (KNPEMI/KNPEMIx_problem.py:200-218,
  * 613-614), whose mass-matrix products the host forms once; n = 0 clears. */
 int knp_set_source(knp_ctx* ctx, int32_t n, const int32_t* rows_host, const double* vals_host);
+/* Essential boundary conditions, bcs = p.bcs of assemble_matrix_block / assemble_vector_block (KNPEMI/KNPEMIx_solver.py:113-116,
+ * 123-126) for the conditions ProblemKNPEMI.setup_boundary_conditions builds (KNPEMI/KNPEMIx_problem.py:96-198: every field on
+ * the exterior boundary, or phi_e pinned at one vertex): cols = the constrained dofs in the column layout -- owned AND ghost
+ * columns of this rank -- and their values.  From then on knp_assemble / knp_step zero the rows and columns of these dofs
+ * (diagonal 1) and lift the right-hand side (b_i -= sum_j A_ij g_j, b = g on constrained rows), knp_solve / knp_step start
+ * from an initial guess that carries g, and knp_assemble_P and the preconditioner setups treat their matrices the same way.  The caller switches the nullspace
+ * handling off (project_nullspace = zero_mean_solution = 0), as the reference does (:380,415).  n = 0 clears. */
+int knp_set_dirichlet(knp_ctx* ctx, int32_t n, const int32_t* cols_host, const double* vals_host);
 int knp_values_dev(knp_ctx* ctx, double** A_vals, double** b, double** P_vals, double** x);
 /* y = A x with the context's CSR pattern (PETSc MatMult inside ksp.solve, :435). x in column layout. */
 int knp_spmv(knp_ctx* ctx, const double* A_vals_dev, const double* x_dev, double* y_dev, void* stream);

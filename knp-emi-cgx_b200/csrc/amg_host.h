@@ -14,6 +14,7 @@ struct Graph {
 
 void strength_graph(const CsrHost& A, double theta, Graph& S);
 int mis2_aggregate(const Graph& S, std::vector<int32_t>& agg);
+int drop_dirichlet_aggregates(const CsrHost& A, std::vector<int32_t>& agg, int nagg);
 void spgemm(const CsrHost& A, const CsrHost& B, CsrHost& C);
 void transpose(const CsrHost& A, CsrHost& At);
 int dense_inverse(int n, std::vector<double>& M, std::vector<double>& inv);

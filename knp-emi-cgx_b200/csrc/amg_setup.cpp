@@ -200,6 +200,32 @@ int mis2_aggregate(const Graph& S, std::vector<int32_t>& agg) {
   return nagg;
 }
 
+// Dirichlet rows -- rows without a non-zero off-diagonal entry, as the boundary conditions leave them (knp_set_dirichlet) --
+// are taken out of the coarse space: agg = -1, an empty row of the prolongator.  The level's Jacobi sweeps solve them, and
+// their singleton aggregates would otherwise survive on every level (coarsening stalls at the number of boundary dofs).
+// Identical decisions to oracle/amg.py::drop_dirichlet_aggregates; a no-op for matrices without such rows.
+int drop_dirichlet_aggregates(const CsrHost& A, std::vector<int32_t>& agg, int nagg) {
+  const int n = A.n_rows;
+  std::vector<uint8_t> dir(n, 0);
+  bool any = false;
+#pragma omp parallel for schedule(static) reduction(|| : any)
+  for (int i = 0; i < n; ++i) {
+    bool off = false;
+    for (int j = A.indptr[i]; j < A.indptr[i + 1] && !off; ++j) off = A.indices[j] != i && A.vals[j] != 0.0;
+    dir[i] = !off;
+    any = any || !off;
+  }
+  if (!any) return nagg;
+  std::vector<int32_t> remap(nagg, -1);
+  for (int i = 0; i < n; ++i)
+    if (!dir[i]) remap[agg[i]] = 0;
+  int k = 0;
+  for (int a = 0; a < nagg; ++a)
+    if (remap[a] == 0) remap[a] = k++;
+  for (int i = 0; i < n; ++i) agg[i] = dir[i] ? -1 : remap[agg[i]];
+  return k;
+}
+
 // C = A * B (CSR, sorted columns out): two passes over the rows (count, then fill) with a dense marker / accumulator
 // per thread -- no per-row allocations
 void spgemm(const CsrHost& A, const CsrHost& B, CsrHost& C) {
@@ -365,11 +391,15 @@ void prolongator_build(const CsrHost& A, int n_own_cols, const Graph& S, const s
     for (int i = 0; i < n; ++i) {
       int sp = S.ptr[i], k = 1;
       const int se = S.ptr[i + 1];
+      if (agg[i] < 0) {                  // Dirichlet row: not interpolated
+        plen[i] = 0;
+        continue;
+      }
       mark[agg[i]] = i;
       for (int j = A.indptr[i]; j < A.indptr[i + 1]; ++j) {
         const int c = A.indices[j];
         while (sp < se && S.idx[sp] < c) ++sp;
-        const bool strong = c < n_own_cols && (!filtered || (sp < se && S.idx[sp] == c));
+        const bool strong = c < n_own_cols && agg[c] >= 0 && (!filtered || (sp < se && S.idx[sp] == c));
         if (c != i && strong && mark[agg[c]] != i) {
           mark[agg[c]] = i;
           ++k;
@@ -390,6 +420,7 @@ void prolongator_build(const CsrHost& A, int n_own_cols, const Graph& S, const s
       int32_t* list = P.indices.data() + P.indptr[i];
       int sp = S.ptr[i], k = 0;
       const int se = S.ptr[i + 1];
+      if (agg[i] < 0) continue;
       mark[agg[i]] = i;
       acc[agg[i]] = 0.0;
       list[k++] = agg[i];
@@ -398,7 +429,7 @@ void prolongator_build(const CsrHost& A, int n_own_cols, const Graph& S, const s
         const int c = A.indices[j];
         const double v = A.vals[j];
         while (sp < se && S.idx[sp] < c) ++sp;
-        const bool strong = c < n_own_cols && (!filtered || (sp < se && S.idx[sp] == c));
+        const bool strong = c < n_own_cols && agg[c] >= 0 && (!filtered || (sp < se && S.idx[sp] == c));
         if (c == i || !strong) {
           diagF += v;
         } else {
@@ -446,7 +477,7 @@ int amg_setup_host(const CsrHost& A0, double theta, int coarse_size, int max_lev
     }
     tm.lap("strength", (int)As.size() - 1, n);
     std::vector<int32_t> agg;
-    const int nagg = mis2_aggregate(S, agg);
+    const int nagg = drop_dirichlet_aggregates(A, agg, mis2_aggregate(S, agg));
     tm.lap("mis2", (int)As.size() - 1, n);
     if (nagg >= 0.8 * n) break;
     // Gershgorin bounds, D^-1 and the smoothed prolongator (prolongator_bounds / prolongator_build below).  The filter is

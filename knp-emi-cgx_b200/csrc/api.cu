@@ -399,6 +399,60 @@ int knp_assemble(knp_ctx* c, double t, double* A_vals, double* b, void* stream) 
   KNP_CUDA(cudaEventRecord(c->ev[2], st));
   KNP_TRY(launch_rows(c->T, c->kp, 0, c->u.p, c->fe.p, A_vals ? A_vals : c->A_vals.p, b ? b : c->b.p, c->H.max_deg, c->H.max_gdeg, st));
   if (c->n_src > 0) KNP_TRY(launch_add_sparse(c->n_src, c->src_rows.p, c->src_vals.p, b ? b : c->b.p, st));   // :613-614
+  if (c->n_bc > 0)      // bcs = p.bcs of assemble_matrix_block / assemble_vector_block (:113-116)
+    KNP_TRY(launch_bc_apply(c->n_bc_rows_A, c->bc_rows_A.p, c->d_indptr.p, c->d_indices.p, A_vals ? A_vals : c->A_vals.p,
+                            b ? b : c->b.p, c->n_bc, c->bc_cols.p, c->bc_vals.p, 1.0, st));
+  return KNP_OK;
+}
+
+static int bc_touched_rows(knp_ctx* c, const int32_t* indptr, const int32_t* indices, const uint8_t* flag,
+                           knp::DevBuf<int32_t>& out, int& n_out) {
+  const int n = c->T.L.n_rows;
+  knp::DevBuf<uint8_t> touched;
+  KNP_TRY(touched.alloc(n));
+  KNP_TRY(launch_bc_touch(n, indptr, indices, flag, touched.p, c->stream));
+  std::vector<uint8_t> h(n);
+  KNP_CUDA(cudaStreamSynchronize(c->stream));
+  if (n) KNP_CUDA(cudaMemcpy(h.data(), touched.p, n, cudaMemcpyDeviceToHost));
+  std::vector<int32_t> list;
+  for (int i = 0; i < n; ++i)
+    if (h[i]) list.push_back(i);
+  n_out = (int)list.size();
+  return out.upload(list);
+}
+
+int knp_set_dirichlet(knp_ctx* c, int32_t n, const int32_t* cols, const double* vals) {
+  CTX_GUARD(c);
+  KNP_CHECK(n >= 0 && (n == 0 || (cols && vals)), "knp_set_dirichlet: invalid arguments");
+  const Layout& L = c->T.L;
+  std::vector<std::pair<int32_t, double>> bc(n);
+  for (int i = 0; i < n; ++i) {
+    KNP_CHECK(cols[i] >= 0 && cols[i] < L.n_cols, "knp_set_dirichlet: column out of range");
+    bc[i] = {cols[i], vals[i]};
+  }
+  std::sort(bc.begin(), bc.end());
+  for (int i = 1; i < n; ++i) KNP_CHECK(bc[i].first != bc[i - 1].first, "knp_set_dirichlet: duplicate column");
+  KNP_CUDA(cudaStreamSynchronize(c->stream));
+  c->n_bc = c->n_bc_rows_A = c->n_bc_rows_P = 0;
+  c->h_bc_rows.clear();
+  if (n == 0) return KNP_OK;
+  std::vector<int32_t> hc(n);
+  std::vector<double> hv(n);
+  for (int i = 0; i < n; ++i) {
+    hc[i] = bc[i].first;
+    hv[i] = bc[i].second;
+    if (hc[i] < L.n_rows) c->h_bc_rows.push_back(hc[i]);
+  }
+  KNP_TRY(c->bc_cols.upload(hc));
+  KNP_TRY(c->bc_vals.upload(hv));
+  knp::DevBuf<uint8_t> flag;
+  KNP_TRY(flag.alloc(L.n_cols));
+  KNP_CUDA(cudaMemsetAsync(flag.p, 0, L.n_cols, c->stream));
+  KNP_TRY(launch_bc_flags(n, c->bc_cols.p, flag.p, c->stream));
+  KNP_TRY(bc_touched_rows(c, c->d_indptr.p, c->d_indices.p, flag.p, c->bc_rows_A, c->n_bc_rows_A));
+  KNP_TRY(bc_touched_rows(c, c->d_indptr_P.p, c->d_indices_P.p, flag.p, c->bc_rows_P, c->n_bc_rows_P));
+  c->n_bc = n;
+  c->P_assembled = false;          // a preconditioner matrix assembled before carries no boundary rows
   return KNP_OK;
 }
 
@@ -420,6 +474,9 @@ int knp_assemble_P(knp_ctx* c, double* P_vals, void* stream) {
   CTX_GUARD(c);
   KNP_CHECK(c->params_set, "knp_set_params must be called first");
   KNP_TRY(launch_rows(c->T, c->kp, 1, c->u.p, c->fe.p, P_vals ? P_vals : c->P_vals.p, nullptr, c->H.max_deg, c->H.max_gdeg, pick(c, stream)));
+  if (c->n_bc > 0)                 // assemble_matrix_block(p.P, bcs = p.bcs) (KNPEMIx_solver.py:125-126)
+    KNP_TRY(launch_bc_apply(c->n_bc_rows_P, c->bc_rows_P.p, c->d_indptr_P.p, c->d_indices_P.p, P_vals ? P_vals : c->P_vals.p,
+                            nullptr, c->n_bc, c->bc_cols.p, c->bc_vals.p, 1.0, pick(c, stream)));
   if (!P_vals) c->P_assembled = true;
   return KNP_OK;
 }

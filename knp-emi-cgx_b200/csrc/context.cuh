@@ -86,6 +86,12 @@ struct knp_ctx {
   knp::DevBuf<int32_t> src_rows;
   knp::DevBuf<double> src_vals;
   int n_src = 0;
+  // Dirichlet conditions (knp_set_dirichlet): constrained columns (ascending) with their values, owned rows of A / of P that
+  // hold a constrained entry
+  knp::DevBuf<int32_t> bc_cols, bc_rows_A, bc_rows_P;
+  knp::DevBuf<double> bc_vals;
+  int n_bc = 0, n_bc_rows_A = 0, n_bc_rows_P = 0;
+  std::vector<int32_t> h_bc_rows;     // constrained OWNED rows (host copy, for the Schur preconditioner setup)
   double t = 0.0;
   int step_index = 0;
   // Krylov workspace

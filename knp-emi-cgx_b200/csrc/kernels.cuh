@@ -97,6 +97,14 @@ int launch_range_shift(double* x, int lo0, int hi0, int lo1, int hi1, const doub
                        cudaStream_t st);
 int launch_reduce_partials(const double* partial, int n_partial, double* out, cudaStream_t st);
 int launch_add_sparse(int n, const int32_t* rows, const double* vals, double* y, cudaStream_t st);   // y[rows[i]] += vals[i]
+// Dirichlet conditions (knp_set_dirichlet): flags of the constrained columns, rows with a constrained entry, and the
+// zero-rows-and-columns / lifting pass over those rows
+int launch_bc_flags(int n_bc, const int32_t* bc_cols, uint8_t* flag, cudaStream_t st);
+int launch_bc_touch(int n_rows, const int32_t* indptr, const int32_t* indices, const uint8_t* flag, uint8_t* touched,
+                    cudaStream_t st);
+int launch_bc_apply(int n_list, const int32_t* rows, const int32_t* indptr, const int32_t* indices, double* vals, double* b,
+                    int n_bc, const int32_t* bc_cols, const double* bc_vals, double diag, cudaStream_t st);
+int launch_bc_set(int n_bc, const int32_t* bc_cols, const double* bc_vals, int n_rows, double* x, cudaStream_t st);   // x[bc] = g (owned)
 // preconditioned CG with device-resident scalars (solver.cu::cg_solve)
 int launch_cg_scalar(int phase, int it, const double* dots, double* S, double* hist, cudaStream_t st);
 int launch_cg_xr(int n, const double* S, const double* p, const double* q, double* x, double* r, cudaStream_t st);

@@ -768,6 +768,89 @@ int launch_add_sparse(int n, const int32_t* rows, const double* vals, double* y,
   return KNP_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ Dirichlet conditions
+// Essential boundary conditions the way assemble_matrix_block / assemble_vector_block apply them (KNPEMIx_solver.py:113-116
+// with bcs = p.bcs, KNPEMIx_problem.py:96-198): rows and columns of constrained dofs are zeroed, their diagonal set to `diag`,
+// the right-hand side lifted, b_i -= sum_j A_ij g_j, and b = g on the constrained rows.  bc_cols (ascending, column layout:
+// owned and ghost columns) / bc_vals hold the constrained dofs and their values; `rows` lists the owned rows with at least one
+// constrained entry (found once by bc_touch_kernel), so the pass costs O(boundary), not O(nnz).  One thread per listed row
+// walks it in ascending order: fixed summation order, every entry written by one thread.
+__device__ __forceinline__ int bc_find(const int32_t* __restrict__ cols, int n, int c) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (cols[mid] < c) lo = mid + 1;
+    else hi = mid;
+  }
+  return (lo < n && cols[lo] == c) ? lo : -1;
+}
+__global__ void bc_touch_kernel(int n_rows, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                const uint8_t* __restrict__ flag, uint8_t* __restrict__ touched) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  uint8_t t = flag[r];
+  for (int k = indptr[r]; k < indptr[r + 1] && !t; ++k) t = flag[indices[k]];
+  touched[r] = t;
+}
+__global__ void bc_flag_kernel(int n, const int32_t* __restrict__ cols, uint8_t* __restrict__ flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flag[cols[i]] = 1;
+}
+__global__ void bc_apply_kernel(int n_list, const int32_t* __restrict__ rows, const int32_t* __restrict__ indptr,
+                                const int32_t* __restrict__ indices, double* __restrict__ vals, double* __restrict__ b,
+                                int n_bc, const int32_t* __restrict__ bc_cols, const double* __restrict__ bc_vals,
+                                double diag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_list) return;
+  const int r = rows[i];
+  const int self = bc_find(bc_cols, n_bc, r);
+  double lift = 0.0;
+  for (int k = indptr[r]; k < indptr[r + 1]; ++k) {
+    const int c = indices[k];
+    if (self >= 0) {
+      vals[k] = c == r ? diag : 0.0;
+    } else {
+      const int j = bc_find(bc_cols, n_bc, c);
+      if (j >= 0) {
+        lift += vals[k] * bc_vals[j];
+        vals[k] = 0.0;
+      }
+    }
+  }
+  if (b) b[r] = self >= 0 ? bc_vals[self] : b[r] - lift;
+}
+__global__ void bc_set_kernel(int n, const int32_t* __restrict__ cols, const double* __restrict__ vals, int n_rows,
+                              double* __restrict__ x) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && cols[i] < n_rows) x[cols[i]] = vals[i];
+}
+int launch_bc_set(int n_bc, const int32_t* bc_cols, const double* bc_vals, int n_rows, double* x, cudaStream_t st) {
+  if (n_bc == 0) return KNP_OK;
+  bc_set_kernel<<<(n_bc + 255) / 256, 256, 0, st>>>(n_bc, bc_cols, bc_vals, n_rows, x);
+  KNP_LAUNCHED();
+  return KNP_OK;
+}
+int launch_bc_flags(int n_bc, const int32_t* bc_cols, uint8_t* flag, cudaStream_t st) {
+  if (n_bc == 0) return KNP_OK;
+  bc_flag_kernel<<<(n_bc + 255) / 256, 256, 0, st>>>(n_bc, bc_cols, flag);
+  KNP_LAUNCHED();
+  return KNP_OK;
+}
+int launch_bc_touch(int n_rows, const int32_t* indptr, const int32_t* indices, const uint8_t* flag, uint8_t* touched,
+                    cudaStream_t st) {
+  if (n_rows == 0) return KNP_OK;
+  bc_touch_kernel<<<(n_rows + 255) / 256, 256, 0, st>>>(n_rows, indptr, indices, flag, touched);
+  KNP_LAUNCHED();
+  return KNP_OK;
+}
+int launch_bc_apply(int n_list, const int32_t* rows, const int32_t* indptr, const int32_t* indices, double* vals, double* b,
+                    int n_bc, const int32_t* bc_cols, const double* bc_vals, double diag, cudaStream_t st) {
+  if (n_list == 0) return KNP_OK;
+  bc_apply_kernel<<<(n_list + 127) / 128, 128, 0, st>>>(n_list, rows, indptr, indices, vals, b, n_bc, bc_cols, bc_vals, diag);
+  KNP_LAUNCHED();
+  return KNP_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ conjugate gradients
 // Device-resident scalars of the preconditioned CG loop (solver.cu::cg_solve): S[0] = (r, z), S[1] = alpha, S[2] = beta,
 // S[3] = state (0 running, 1 converged, 2 breakdown: (p, A p) <= 0 or non-finite), S[4] = tol^2, S[5] = iteration at which the

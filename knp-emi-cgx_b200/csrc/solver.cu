@@ -498,6 +498,14 @@ static int schur_setup(knp_ctx* c) {
   for (int k = 0; k < 3; ++k) kp.D[k] = 0.0;
   KNP_TRY(c->M_vals.alloc(c->H.nnz_P));
   KNP_TRY(launch_rows(c->T, kp, 1, c->u.p, c->fe.p, c->M_vals.p, nullptr, c->H.max_deg, c->H.max_gdeg, st));
+  if (c->n_bc > 0) {
+    // Dirichlet dofs are cut out of every operator of the preconditioner (identity rows in the blocks, empty rows and
+    // columns in the mass matrices): with the boundary values in the initial guess their residual is zero throughout
+    KNP_TRY(launch_bc_apply(c->n_bc_rows_P, c->bc_rows_P.p, c->d_indptr_P.p, c->d_indices_P.p, c->P_vals.p, nullptr,
+                            c->n_bc, c->bc_cols.p, c->bc_vals.p, 1.0, st));
+    KNP_TRY(launch_bc_apply(c->n_bc_rows_P, c->bc_rows_P.p, c->d_indptr_P.p, c->d_indices_P.p, c->M_vals.p, nullptr,
+                            c->n_bc, c->bc_cols.p, c->bc_vals.p, 0.0, st));
+  }
   KNP_CUDA(cudaStreamSynchronize(st));
   std::vector<int32_t> idx(c->H.nnz_P);
   std::vector<double> val(c->H.nnz_P), mval(c->H.nnz_P), u(L.n_cols);
@@ -591,7 +599,7 @@ static int schur_setup(knp_ctx* c) {
       for (int j = ip[row]; j < ip[row + 1]; ++j) ms += mval[j];
       double sig = 0.0;
       for (int k = 0; k < 3; ++k) sig += z[k] * z[k] / c->kp.psi * u[L.col(s, k, p)];
-      msig_inv[(size_t)(s ? n0 : 0) + p] = 1.0 / (sig * ms);
+      msig_inv[(size_t)(s ? n0 : 0) + p] = ms != 0.0 ? 1.0 / (sig * ms) : 0.0;     // empty row: Dirichlet dof
     }
   KNP_TRY(c->msig_inv.upload(msig_inv));
   // row blocks of the two mass-matrix row ranges (rows (s, 0, .) of the P pattern): TMA-staged SpMV on sub-ranges
@@ -1269,12 +1277,19 @@ int cg_solve(knp_ctx* c, const double* A_vals, const double* b, double* x, const
 // ksp.solve dispatch on the Krylov type
 int krylov_solve(knp_ctx* c, const double* A_vals, const double* b, double* x, const knp_solve_opts* o, knp_solve_info* info,
                  cudaStream_t st) {
-  if (o->ksp_type == 1) return cg_solve(c, A_vals, b, x, o, info, st);
-  if (o->ksp_type != 0) {
+  // essential boundary conditions: the initial guess takes the boundary values, so the residual of the constrained rows
+  // (identity rows, b = g) is zero from the first Krylov vector on and the solution carries them exactly
+  if (c->n_bc > 0) KNP_TRY(launch_bc_set(c->n_bc, c->bc_cols.p, c->bc_vals.p, c->T.L.n_rows, x, st));
+  if (o->ksp_type != 0 && o->ksp_type != 1) {
     set_error("unknown ksp_type %d (0 = gmres, 1 = cg)", o->ksp_type);
     return KNP_E_INVALID;
   }
-  return gmres_solve(c, A_vals, b, x, o, info, st);
+  const int rc = o->ksp_type == 1 ? cg_solve(c, A_vals, b, x, o, info, st) : gmres_solve(c, A_vals, b, x, o, info, st);
+  // a pinned potential shares its vertex with unconstrained ion rows, whose residuals reach it through the row operation of
+  // the Schur preconditioner: the iterate carries g only to solver tolerance there.  The other unknowns do not depend on it
+  // (its column is zero), so the exact value is simply restored.
+  if (c->n_bc > 0 && rc == KNP_OK) KNP_TRY(launch_bc_set(c->n_bc, c->bc_cols.p, c->bc_vals.p, c->T.L.n_rows, x, st));
+  return rc;
 }
 
 }  // namespace knp

@@ -64,7 +64,7 @@ SYMBOLS = [
     "knp_last_error", "knp_version", "knp_launch_count", "knp_create", "knp_destroy", "knp_get_sizes", "knp_csr_dev", "knp_csr_host",
     "knp_csr_P_host", "knp_dofmap_host", "knp_mverts_host", "knp_set_params", "knp_stimulus_area_local",
     "knp_set_state", "knp_get_state", "knp_state_dev", "knp_phi_m_host", "knp_gate_step", "knp_assemble",
-    "knp_assemble_P", "knp_set_source", "knp_values_dev", "knp_spmv", "knp_pc_setup", "knp_pc_apply", "knp_pc_bytes", "knp_solve", "knp_step",
+    "knp_assemble_P", "knp_set_source", "knp_set_dirichlet", "knp_values_dev", "knp_spmv", "knp_pc_setup", "knp_pc_apply", "knp_pc_bytes", "knp_solve", "knp_step",
     "knp_step_host", "knp_set_time", "knp_get_time", "knp_l2_norm_sq", "knp_integral", "knp_membrane_area", "knp_probe_setup", "knp_probe_eval", "knp_stimulus_current", "knp_last_timings", "knp_amg_num_levels", "knp_amg_part_levels", "knp_amg_setup_host", "knp_amg_host_level", "knp_pattern_host", "knp_edge_tables_host", "knp_rowblocks_host",
     "knp_amg_dist_sim_host", "knp_amg_dist_sim_level", "knp_amg_dist_sim_perm",
     "knp_copy", "knp_amg_level_sizes", "knp_amg_level_host", "knp_nccl_unique_id", "knp_dist_init", "knp_halo_exchange", "knp_peer_direct",
@@ -109,6 +109,7 @@ def load():
     lib.knp_assemble.argtypes = [vp, C.c_double, vp, vp, vp]
     lib.knp_assemble_P.argtypes = [vp, vp, vp]
     lib.knp_set_source.argtypes = [vp, C.c_int32, vp, vp]
+    lib.knp_set_dirichlet.argtypes = [vp, C.c_int32, vp, vp]
     lib.knp_values_dev.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     lib.knp_spmv.argtypes = [vp, vp, vp, vp, vp]
     lib.knp_pc_setup.argtypes = [vp, C.POINTER(SolveOpts)]
@@ -341,6 +342,13 @@ class Context:
         vals = np.ascontiguousarray(vals, np.float64)
         assert rows.shape == vals.shape and np.unique(rows).size == rows.size
         check(self._lib.knp_set_source(self.h, int(rows.size), _ptr(rows), _ptr(vals)))
+
+    def set_dirichlet(self, cols, vals):
+        """Constrained dofs (column layout, owned and ghost) and their values; empty arrays clear (knp_set_dirichlet)."""
+        cols = np.ascontiguousarray(cols, np.int32)
+        vals = np.ascontiguousarray(vals, np.float64)
+        assert cols.shape == vals.shape
+        check(self._lib.knp_set_dirichlet(self.h, int(cols.size), _ptr(cols), _ptr(vals)))
 
     def spmv(self, x_ptr, y_ptr, A_ptr=None, stream=None):
         check(self._lib.knp_spmv(self.h, A_ptr, x_ptr, y_ptr, stream))

@@ -27,6 +27,7 @@ class Mesh:
     cell_owned: np.ndarray = None
     mf_owned: np.ndarray = None
     vert_global: np.ndarray = None
+    bc_verts: np.ndarray = None     # ingested meshes: local vertices on facets tagged with the config's boundary_tags
 
 
 # ------------------------------------------------------------------------------------------ quadrature
@@ -311,6 +312,63 @@ def cell_array_mesh_local(gdim, n, m, rank, size, scale=1e-6, fill=0.5, first_ta
     local = Mesh(gdim, x, lcells, tags, intra, extra_tag, fv.astype(np.int32).reshape(-1, gdim), ft.astype(np.int32),
                  grid=(n,) * gdim, n_owned=n_owned, cell_owned=cell_owned, mf_owned=mf_owned, vert_global=l2g)
     return local, dict(owner_of=own, l2g=l2g, rank=rank, size=size)
+
+
+def boundary_vertices(m: Mesh):
+    """Vertices of the exterior boundary (the facets mark_boundaries_square / _cube tag PARTIAL_OMEGA, misc.py:139-186):
+    by structured index on the generated fixtures (works on a rank's slab through its global vertex ids), otherwise the
+    vertices of the facets that belong to exactly one cell of a GLOBAL mesh."""
+    if m.grid is not None:
+        n = m.grid[0]
+        gid = np.arange(m.x.shape[0], dtype=np.int64) if m.vert_global is None else np.asarray(m.vert_global, np.int64)
+        on = np.zeros(gid.shape, bool)
+        rest = gid
+        for _ in range(m.gdim):
+            i = rest % (n + 1)
+            rest = rest // (n + 1)
+            on |= (i == 0) | (i == n)
+        return np.flatnonzero(on).astype(np.int32)
+    if m.vert_global is not None:
+        raise RuntimeError("exterior facets of a partitioned unstructured mesh must be found before the partition")
+    from .xdmf import _entity_keys
+    nvc = m.cells.shape[1]
+    fac = np.concatenate([m.cells[:, [j for j in range(nvc) if j != i]] for i in range(nvc)], 0)
+    key, srt, exact = _entity_keys(fac, m.x.shape[0])
+    uk, first, cnt = np.unique(key, return_index=True, return_counts=True)
+    return np.unique(srt[first[cnt == 1]].astype(np.int64).ravel()).astype(np.int32)
+
+
+def from_xdmf(mesh_file, facet_file, ct_name, ft_name, intra_tags, extra_tag, boundary_tags, scale):
+    """Mesh ingest (utils/mixed_dim_problem.py:634-681 + the coordinate scaling of :681): cells and cell tags from
+    `mesh_file`, facet tags from `facet_file`.  Membrane facets are the facets between an intracellular and an extracellular
+    cell (sorted by their vertex tuples, like the generated fixtures) and carry the tag the facet file gives them (-1 when
+    it gives none: such facets are in no dS(gamma_tags) integral); `bc_verts` are the vertices of the facets tagged with
+    one of `boundary_tags`."""
+    from .xdmf import read_xdmf_mesh, match_entities
+    d = read_xdmf_mesh(mesh_file, facet_file, ct_name, ft_name)
+    cells, tags, nv = d["cells"], d["cell_tags"], d["x"].shape[0]
+    fv, _own = membrane_facets(cells, tags, intra_tags, extra_tag)
+    ft = match_entities(d["facets"], d["facet_tags"], fv, nv, -1) if fv.size else np.zeros(0, np.int32)
+    on_b = np.isin(d["facet_tags"], np.asarray(boundary_tags, np.int32)) if len(boundary_tags) else np.zeros(0, bool)
+    bc = np.unique(d["facets"][on_b].ravel()).astype(np.int32) if on_b.any() else np.zeros(0, np.int32)
+    return Mesh(d["gdim"], d["x"] * scale, cells, tags, tuple(intra_tags), extra_tag, fv.reshape(-1, d["gdim"]), ft, bc_verts=bc)
+
+
+def export_xdmf(m: Mesh, mesh_path, facet_path, scale=1.0, boundary_tag=3, default_tag=None, fmt="HDF"):
+    """Write a generated mesh the way utils/generate_square_mesh.py:37-42 writes its fixture: `mesh_path` holds the mesh and
+    the cell tags (grid "ct"), `facet_path` the mesh and the facet tags (grid "ft": exterior facets `boundary_tag`,
+    membrane facets their tag).  Coordinates are divided by `scale` (the file is in mesh units)."""
+    from .xdmf import write_xdmf_mesh, _entity_keys
+    nvc = m.cells.shape[1]
+    fac = np.concatenate([m.cells[:, [j for j in range(nvc) if j != i]] for i in range(nvc)], 0)
+    key, srt, _e = _entity_keys(fac, m.x.shape[0])
+    _u, first, cnt = np.unique(key, return_index=True, return_counts=True)
+    ext = srt[first[cnt == 1]].astype(np.int64)
+    ent = np.concatenate([ext, np.asarray(m.mf_verts, np.int64)], 0)
+    val = np.concatenate([np.full(ext.shape[0], boundary_tag, np.int32), np.asarray(m.mf_tags, np.int32)])
+    x = m.x / scale
+    write_xdmf_mesh(mesh_path, x, m.cells, {"ct": (m.cells, m.cell_tags)}, fmt)
+    write_xdmf_mesh(facet_path, x, m.cells, {"ft": (ent, val)}, fmt)
 
 
 def from_descriptor(desc, scale):

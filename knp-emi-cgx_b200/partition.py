@@ -65,6 +65,9 @@ def partition_mesh(m: Mesh, rank: int, size: int, owner=None):
     local = Mesh(m.gdim, m.x[l2g], lcells, ltags.astype(np.int32), m.intra_tags, m.extra_tag, lfv,
                  m.mf_tags[f_has].astype(np.int32), grid=m.grid, n_owned=int(owned_ids.size), cell_owned=cell_owned,
                  mf_owned=mf_owned, vert_global=l2g)
+    if m.bc_verts is not None:
+        lb = g2l[np.asarray(m.bc_verts, np.int64)]
+        local.bc_verts = lb[lb >= 0].astype(np.int32)
     info = dict(owner_of=lambda gid, _o=owner: _o[gid], l2g=l2g, rank=rank, size=size)
     return local, info
 

@@ -303,9 +303,9 @@ class ProblemKNPEMI:
 
     # ------------------------------------------------------------------ domain
     def setup_domain(self):
-        """Mesh ingest (utils/mixed_dim_problem.py:634-733).  There is no HDF5/XDMF reader in this image:
-        the fixture is generated in memory from ``synthetic_mesh`` or from the file name
-        (``square{N}.xdmf`` / ``cube{N}.xdmf``, as written by utils/generate_square_mesh.py)."""
+        """Mesh ingest (utils/mixed_dim_problem.py:634-733): an existing XDMF file is read (xdmf.py / hdf5_min.py); otherwise
+        the fixture is generated in memory from ``synthetic_mesh`` or from the file name (``square{N}.xdmf`` /
+        ``cube{N}.xdmf``, as written by utils/generate_square_mesh.py)."""
         local_info = None
         sm = self.synthetic_mesh
         if sm is not None and self.comm.size > 1 and sm.get("kind") == "cell_array" and self.gamma_tags == self.intra_tags:
@@ -321,13 +321,15 @@ class ProblemKNPEMI:
             base = os.path.basename(self.input_files["mesh_file"])
             mt = re.match(r"(square|cube)(\d+)\.xdmf$", base)
             if os.path.exists(self.input_files["mesh_file"]):
-                # a real mesh must never be replaced by a same-named synthetic fixture behind the user's back
-                raise RuntimeError(f"{self.input_files['mesh_file']} exists, but no XDMF/HDF5 reader is available in this environment "
-                                   "(h5py / meshio absent): the B200 path cannot ingest mesh files yet.  Describe the mesh with a "
-                                   "synthetic_mesh block, or remove the file to use the generated square{N} / cube{N} fixture.")
-            if not mt:
-                raise RuntimeError(f"Cannot read {self.input_files['mesh_file']}: no XDMF/HDF5 reader is available; "
-                                   "use a square{N}.xdmf / cube{N}.xdmf fixture name or a synthetic_mesh block.")
+                # a mesh file that exists is read (never replaced by a same-named synthetic fixture)
+                self._print("Reading mesh from XDMF file...")
+                m = _mesh.from_xdmf(self.input_files["mesh_file"], self.input_files["facet_file"], self.ct_name, self.ft_name,
+                                    self.intra_tags, self.extra_tag[0], self.boundary_tags, self.mesh_conversion_factor)
+                mt = None
+            elif not mt:
+                raise RuntimeError(f"Cannot read {self.input_files['mesh_file']}: the file does not exist (generated fixtures are "
+                                   "available under the names square{N}.xdmf / cube{N}.xdmf or through a synthetic_mesh block).")
+        if sm is None and mt:
             n = int(mt.group(2))
             m = (_mesh.unit_square_fixture if mt.group(1) == "square" else _mesh.unit_cube_fixture)(
                 n, self.mesh_conversion_factor)
@@ -412,10 +414,65 @@ class ProblemKNPEMI:
         pass
 
     def setup_boundary_conditions(self):
-        """KNPEMIx_problem.py:96-198: every shipped config uses pure Neumann conditions (bcs = [])."""
-        if self.dirichlet_bcs or self.pin_ecs_potential:
-            raise NotImplementedError("Dirichlet conditions / ECS pinning are outside the B200 hot path (SURVEY.md 8f-3)")
+        """KNPEMIx_problem.py:96-198.  ``dirichlet_bcs``: every field keeps its initial value (k_init; phi_m_init inside, 0
+        outside) on the vertices of the facets tagged ``boundary_tags`` (:139-161).  ``pin_ecs_potential`` (class switch,
+        :997): phi_e = 0 at one extracellular vertex off the membrane (:163-194; the reference takes geometry point 0 or a
+        random one, here the lowest-numbered admissible vertex).  The constrained dofs go to the device once the dof maps
+        exist (_upload_bcs -> knp_set_dirichlet); the device applies them in every assembly.  Shipped configs use neither
+        (bcs = [])."""
+        self._print("Setting up boundary conditions ...")
         self.bcs = []
+        self._bc_verts = None
+        if self.dirichlet_bcs:
+            m = self.mesh
+            if m.bc_verts is not None:                       # ingested mesh: facets tagged boundary_tags
+                self._bc_verts = np.asarray(m.bc_verts, np.int32)
+            else:                                            # generated fixtures: the exterior boundary carries ONE tag
+                sm = self.synthetic_mesh or {}           # square / cube: PARTIAL_OMEGA = 3 (utils/misc.py:139); tissue blocks: 1
+                btag = int(sm.get("boundary_tag", 3 if sm.get("kind", "square") in ("square", "cube") else 1))
+                self._bc_verts = _mesh.boundary_vertices(m) if btag in self.boundary_tags else np.zeros(0, np.int32)
+            self.bcs = ["dirichlet: %d boundary vertices" % self._bc_verts.size]
+        elif self.pin_ecs_potential:
+            self.bcs = ["phi_e pinned at one vertex"]
+
+    def _upload_bcs(self):
+        """Constrained dofs in the column layout (owned and ghost columns of this rank) with their values."""
+        if not self.bcs:
+            return
+        from .partition import Layout
+        m, ctx = self.mesh, self._ctx
+        n_owned = m.x.shape[0] if m.n_owned is None else m.n_owned
+        lay = Layout(self._node_vert, n_owned)
+        inv = []
+        for s in range(2):
+            a = np.full(m.x.shape[0], -1, np.int64)
+            a[self._node_vert[s]] = np.arange(self._node_vert[s].size)
+            inv.append(a)
+        cols, vals = [], []
+        if self.dirichlet_bcs:
+            for s, suffix in ((0, "i"), (1, "e")):
+                q = inv[s][self._bc_verts]
+                q = q[q >= 0]
+                for k, ion in enumerate(self.ion_list):
+                    cols.append(lay.col(s, k, q))
+                    vals.append(np.full(q.size, ion[f"k{suffix}_init"].value))
+                cols.append(lay.col(s, self.N_ions, q))
+                vals.append(np.full(q.size, self.phi_m_init.value if s == 0 else 0.0))
+        else:
+            gid = np.arange(m.x.shape[0], dtype=np.int64) if m.vert_global is None else np.asarray(m.vert_global, np.int64)
+            ok = inv[1] >= 0
+            ok[self._mverts] = False
+            ok[n_owned:] = False
+            mine = int(gid[ok].min()) if ok.any() else np.iinfo(np.int64).max
+            pin = int(self.comm.allreduce(float(mine), op=MPI.MIN))
+            self.pinned_vertex = pin
+            loc = np.flatnonzero(gid == pin)                  # the owner constrains the row, neighbours the ghost column
+            q = inv[1][loc]
+            q = q[q >= 0]
+            cols.append(lay.col(1, self.N_ions, q))
+            vals.append(np.zeros(q.size))
+            self._print("Phi_e pinned at (vertex, point):", pin, m.x[loc[0]] if loc.size else "")
+        ctx.set_dirichlet(np.concatenate(cols), np.concatenate(vals))
 
     injection_current = 5e-9      # [A], KNPEMIx_problem.py:211
 
@@ -666,6 +723,7 @@ class ProblemKNPEMI:
         self._push_state()
         if self.source_terms == "ion_injection":
             self._upload_source()
+        self._upload_bcs()
         if self.point_evaluation:
             self._setup_probes()
         self.a = self.L = "device-resident forms (csrc/assembly.cu)"

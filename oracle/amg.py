@@ -84,6 +84,22 @@ def mis2_aggregate(S):
     return agg, roots.size + left.size
 
 
+def drop_dirichlet_aggregates(A, agg, nagg):
+    """Rows without a non-zero off-diagonal entry (what essential boundary conditions leave behind) leave the coarse space:
+    agg = -1; the remaining aggregates keep their order.  (csrc/amg_setup.cpp::drop_dirichlet_aggregates)"""
+    A = A.tocsr()
+    n = A.shape[0]
+    rows = np.repeat(np.arange(n), np.diff(A.indptr))
+    off = np.zeros(n, bool)
+    off[rows[(A.indices != rows) & (A.data != 0.0)]] = True
+    if off.all():
+        return agg, nagg
+    used = np.zeros(nagg, bool)
+    used[agg[off]] = True
+    remap = np.cumsum(used) - 1
+    return np.where(off, remap[agg], -1), int(used.sum())
+
+
 def sa_level(A, theta=0.08, omega=4.0 / 3.0, filtered=None, level=0):
     """One smoothed-aggregation coarsening: returns (P, R, A_c, rho) with constant near-nullspace.
     The prolongator is smoothed with the filtered matrix (strong off-diagonals, weak ones lumped into the diagonal)."""
@@ -93,9 +109,10 @@ def sa_level(A, theta=0.08, omega=4.0 / 3.0, filtered=None, level=0):
         S = strength_graph(A, theta * 0.5 ** attempt)
         if S.nnz >= 3.0 * n:
             break
-    agg, nagg = mis2_aggregate(S)
+    agg, nagg = drop_dirichlet_aggregates(A, *mis2_aggregate(S))
     # unnormalised tentative prolongator: the constant stays the near-nullspace vector on every level
-    T = sp.csr_matrix((np.ones(n), (np.arange(n), agg)), shape=(n, nagg))
+    inn = np.flatnonzero(agg >= 0)
+    T = sp.csr_matrix((np.ones(inn.size), (inn, agg[inn])), shape=(n, nagg))
     dinv = 1.0 / A.diagonal()
     rho = float(np.max(np.abs(dinv) * np.asarray(np.abs(A).sum(axis=1)).ravel()))   # Gershgorin bound on rho(D^-1 A)
     keep = (S + sp.identity(n, dtype=np.int8, format="csr")).astype(float)
@@ -205,12 +222,13 @@ class SchurPC:
         self.ic = np.concatenate([np.arange(o.base[s], o.base[s] + 3 * ns[s]) for s in range(2)])
         self.ip = np.concatenate([np.arange(o.base[s] + 3 * ns[s], o.base[s] + 4 * ns[s]) for s in range(2)])
         Pt = o.assemble_P(membrane_sign=+1.0).tocsr()
-        Mm = o.assemble_P(membrane_sign=0.0, D_scale=0.0).tocsr()
+        Mm = o.assemble_P(membrane_sign=0.0, D_scale=0.0, bc_diag=0.0).tocsr()    # Dirichlet dofs: empty rows and columns
         self.M = [Mm[o.base[s]: o.base[s] + ns[s]][:, o.base[s]: o.base[s] + ns[s]].tocsr() for s in range(2)]
         self.msig = []
         for s in range(2):
             sigma = sum(p.z[k] ** 2 / p.psi * o.c[s][k][o.S[s]] for k in range(3))
-            self.msig.append(sigma * np.asarray(self.M[s].sum(axis=1)).ravel())
+            ms = np.asarray(self.M[s].sum(axis=1)).ravel()
+            self.msig.append(np.where(ms != 0.0, sigma * ms, np.inf))
         Acc = Pt[self.ic][:, self.ic].tocsr()
         App = Pt[self.ip][:, self.ip].tocsr()
         if exact:

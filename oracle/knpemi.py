@@ -71,6 +71,11 @@ class OracleParams:
     # "ion_injection": K+ / Cl- source in the extracellular space around the mesh centre (KNPEMIx_problem.py:200-218)
     source_terms: str = None
     injection_current: float = 5e-9
+    # essential boundary conditions (KNPEMIx_problem.py:96-198): dirichlet_bcs = every field at its initial value on the
+    # vertices of the facets tagged boundary_tags (given here as the vertex list); pin_vertex = phi_e = 0 at one vertex
+    dirichlet_bcs: bool = False
+    boundary_verts: tuple = ()
+    pin_vertex: int = None
 
     @property
     def psi(self):
@@ -131,6 +136,53 @@ class KNPEMIOracle:
     # ------------------------------------------------------------------ setup
     def row(self, s, f, verts):
         return self.base[s] + f * self.ns[s] + self.r[s][verts]
+
+    def bc_dofs(self):
+        """ProblemKNPEMI.setup_boundary_conditions (KNPEMIx_problem.py:96-198), non-MMS branches: with dirichlet_bcs every
+        field takes its initial value (k_init, phi_m_init inside, 0 outside) on the boundary dofs of its restriction
+        (:139-161); otherwise pin_ecs_potential pins phi_e = 0 at one vertex off the membrane (:163-194).
+        Returns (unknown indices ascending, values)."""
+        p = self.p
+        idx, val = [], []
+        if p.dirichlet_bcs:
+            bv = np.unique(np.asarray(p.boundary_verts, np.int64))
+            for s in range(2):
+                v = bv[self.r[s][bv] >= 0]
+                init = p.c_i_init if s == 0 else p.c_e_init
+                for k in range(3):
+                    idx.append(self.row(s, k, v))
+                    val.append(np.full(v.size, init[k]))
+                idx.append(self.row(s, 3, v))
+                val.append(np.full(v.size, p.phi_m_init if s == 0 else 0.0))
+        elif p.pin_vertex is not None:
+            assert self.r[1][p.pin_vertex] >= 0 and p.pin_vertex not in self.mverts
+            idx.append(np.array([self.row(1, 3, p.pin_vertex)]))
+            val.append(np.zeros(1))
+        if not idx:
+            return np.zeros(0, np.int64), np.zeros(0)
+        idx, val = np.concatenate(idx), np.concatenate(val)
+        o = np.argsort(idx)
+        return idx[o], val[o]
+
+    def apply_bcs(self, A, b=None, diag=1.0):
+        """assemble_matrix_block(A, a, bcs) + assemble_vector_block(b, L, a, bcs) (KNPEMIx_solver.py:113-116): rows and columns
+        of the constrained dofs are zeroed (the entries stay in the pattern), the diagonal is set to `diag`; the right-hand
+        side is lifted with the unconstrained columns, b -= A[:, bc] g, and set to g on the constrained rows."""
+        idx, g = self.bc_dofs()
+        if idx.size == 0:
+            return A, b
+        A = A.tocsr().copy()
+        isbc = np.zeros(self.n, bool)
+        isbc[idx] = True
+        if b is not None:
+            gf = np.zeros(self.n)
+            gf[idx] = g
+            b = b - A @ gf
+            b[idx] = g
+        rows = np.repeat(np.arange(self.n), np.diff(A.indptr))
+        A.data[isbc[rows] | isbc[A.indices]] = 0.0
+        A.data[isbc[rows] & (rows == A.indices)] = diag
+        return A, b
 
     def _cell_geometry(self, cells):
         x = self.mesh.x[cells]                                  # (nc, d+1, gdim)
@@ -396,9 +448,9 @@ class KNPEMIOracle:
                           shape=(self.n, self.n)).tocsr()
         A.sum_duplicates()
         A.sort_indices()
-        return A, b
+        return self.apply_bcs(A, b)
 
-    def assemble_P(self, membrane_sign=-1.0, D_scale=1.0):
+    def assemble_P(self, membrane_sign=-1.0, D_scale=1.0, bc_diag=1.0):
         """Block-Jacobi preconditioner form (KNPEMIx_problem.py:717-738), from the current fields.
         membrane_sign=+1 / D_scale=0 give the two auxiliary matrices of the product's own Schur preconditioner
         (oracle/amg.py::SchurPC): the phi blocks with the sign the membrane term has in `a`, and the mass matrices."""
@@ -432,12 +484,14 @@ class KNPEMIOracle:
                           shape=(self.n, self.n)).tocsr()
         P.sum_duplicates()
         P.sort_indices()
-        return P
+        return self.apply_bcs(P, None, bc_diag)[0]      # assemble_matrix_block(p.P, bcs=p.bcs) (KNPEMIx_solver.py:125-126)
 
     # ------------------------------------------------------------------- vectors
     def nullspace(self):
         """create_and_set_nullspace (KNPEMIx_solver.py:297-335): normalised indicator of phi rows."""
         ns = np.zeros(self.n)
+        if self.p.dirichlet_bcs or self.p.pin_vertex is not None:
+            return ns                       # no nullspace is attached with essential conditions (KNPEMIx_solver.py:380,415)
         ns[self.base[0] + 3 * self.ns[0]: self.base[0] + 4 * self.ns[0]] = 1.0
         ns[self.base[1] + 3 * self.ns[1]: self.base[1] + 4 * self.ns[1]] = 1.0
         return ns / np.linalg.norm(ns)
@@ -471,6 +525,12 @@ class KNPEMIOracle:
         """Bordered sparse LU [[A, ns],[ns^T, 0]] -> the solution with ns^T x = 0, which is what
         PREONLY+MUMPS(ICNTL24) followed by KSP's nullspace removal returns."""
         As, s = self.equilibrate(A)
+        if not ns.any():                    # essential conditions: the matrix is regular, plain LU
+            lu = spla.splu(As.tocsc())
+            y = lu.solve(s * b)
+            for _ in range(refine):
+                y = y + lu.solve(s * b - As @ y)
+            return s * y
         nss = ns / s
         nss = nss / np.linalg.norm(nss)
         n = self.n
@@ -583,7 +643,11 @@ class KNPEMIOracle:
         if solver == "direct":
             x, its = self.solve_direct(A, b, ns), 0
         else:
-            x, its = self.solve_gmres(A, b, x_prev, ns, Pinv, rtol)
+            idx, g = self.bc_dofs()
+            x0 = x_prev.copy()
+            x0[idx] = g                                                 # the initial guess carries the boundary values
+            x, its = self.solve_gmres(A, b, x0, ns, Pinv, rtol)
+            x[idx] = g                                                  # ... and so does the solution, exactly
         self.unpack(x)
         return A, b, x, its
 

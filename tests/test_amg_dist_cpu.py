@@ -116,3 +116,30 @@ def test_distributed_levels_are_galerkin_and_precondition_like_serial(kb, gdim, 
         its_serial = _cg_iterations(A, serial)
         its_dist = _cg_iterations(As[0], Cycle(As, Ps, rhos))
         assert its_dist <= its_serial + 3, (part, nranks, its_serial, its_dist)
+
+
+@pytest.mark.parametrize("nranks", [1, 4])
+def test_dirichlet_rows_leave_the_coarse_space_on_every_rank(kb, nranks):
+    """Blocks with essential boundary rows (knp_set_dirichlet: identity rows): those dofs get an empty prolongator row on
+    every rank, the coarse operators stay exact Galerkin products, and the first coarse level has no trace of them."""
+    mesh = kb.mesh.cell_array_mesh(2, 48, 2)
+    om = from_arrays(2, mesh.x, mesh.cells, mesh.cell_tags, mesh.intra_tags)
+    it = tuple(mesh.intra_tags)
+    o = KNPEMIOracle(om, OracleParams(intra_tags=it, extra_tag=1, membrane_tags=it, stimulus_tags=it, dirichlet_bcs=True,
+                                      boundary_verts=tuple(kb.mesh.boundary_vertices(mesh))), [("Passive", None)])
+    Pt = o.assemble_P(membrane_sign=+1.0).tocsr()
+    ip = np.concatenate([np.arange(o.base[s] + 3 * o.ns[s], o.base[s] + 4 * o.ns[s]) for s in range(2)])
+    A = Pt[ip][:, ip].tocsr()
+    x = np.concatenate([om.x[o.S[s]] for s in range(2)])
+    is_bc = np.asarray(abs(A - sp.diags(A.diagonal())).sum(axis=1)).ravel() == 0.0
+    assert is_bc.sum() == 4 * 48
+    owner = _owners(kb, x, nranks) if nranks > 1 else np.zeros(A.shape[0], np.int32)
+    As, Ps, rhos, perm = kb.lib.amg_dist_sim_host(A, owner, nranks, repl_threshold=200)
+    assert len(Ps) >= 1
+    P0 = Ps[0].tocsr()
+    assert np.array_equal(np.diff(P0.indptr) == 0, is_bc[perm])
+    G = (P0.T @ As[0] @ P0).tocsr()
+    assert abs(G - As[1]).max() <= 1e-13 * abs(G).max()
+    serial = SAAMG(A, coarse_size=60)
+    assert As[1].shape[0] <= serial.levels[1]["A"].shape[0] * (1.6 if nranks > 1 else 1.0)
+    assert _cg_iterations(As[0], Cycle(As, Ps, rhos)) <= _cg_iterations(A, serial) + 3

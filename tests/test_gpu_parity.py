@@ -802,3 +802,143 @@ def test_ion_injection_source_matches_oracle(kb, cfgdir, d3):
             ref, got = o.l2_norm(o.c[1][f], [1]), p.l2_norm(p.wh[1][f], [1])
             assert abs(got - ref) <= 1e-8 * ref, (i, f, got, ref)
     s.ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------- essential boundary conditions
+def _bc_params(kb, om, p, mode):
+    import dataclasses
+    if mode == "dirichlet":
+        mm = kb.mesh.Mesh(om.gdim, om.x, om.cells, om.cell_tags, p.intra_tags, p.extra_tag, om.mf_verts, om.mf_tags)
+        return dataclasses.replace(p, dirichlet_bcs=True, boundary_verts=tuple(kb.mesh.boundary_vertices(mm)))
+    free = np.setdiff1d(np.unique(om.cells[om.cell_tags == p.extra_tag]), np.unique(om.mf_verts))
+    return dataclasses.replace(p, pin_vertex=int(free[0]))
+
+
+@pytest.mark.parametrize("mode", ["dirichlet", "pinned"])
+@pytest.mark.parametrize("name", ["square32", "cube6", "cells2d", "cells3d"])
+def test_dirichlet_conditions_assembled_system(kb, name, mode):
+    """knp_set_dirichlet against the oracle's restatement of assemble_matrix_block / assemble_vector_block with bcs
+    (KNPEMIx_solver.py:113-116, KNPEMIx_problem.py:96-198): rows and columns of the constrained dofs zeroed with a unit
+    diagonal (entries stay in the pattern), lifted right-hand side, boundary values in the state -- entries to 1e-12 -- and
+    the same for the preconditioner matrix; clearing the conditions restores the unconstrained system bit for bit."""
+    om, p0 = MESHES[name](kb)
+    p = _bc_params(kb, om, p0, mode)
+    o = perturbed_oracle(om, p, MODELS_TEST, seed=2)
+    idx, g = o.bc_dofs()
+    assert idx.size > 0 and (mode == "dirichlet" or idx.size == 1)
+    ctx = make_ctx(kb, om, p, MODELS_TEST)
+    push_oracle_state(ctx, o)
+    t = 2 * p.dt
+    ctx.assemble(t)
+    A_free, b_free, _ = (a.copy() for a in ctx.values_host())
+    ctx.set_dirichlet(idx[::-1], g[::-1])                 # any order
+    A, b = o.assemble(t)
+    ctx.assemble(t)
+    Av, bv, _ = ctx.values_host()
+    assert rel_rows(A, Av) < 1e-12
+    assert np.all(Av[A.data == 0.0] == 0.0)               # zeroed entries are exact zeros, the diagonal exact ones
+    assert np.abs(bv - b).max() <= 1e-12 * np.abs(b).max()
+    for s in range(2):
+        for f in range(4):
+            sl = slice(o.base[s] + f * o.ns[s], o.base[s] + (f + 1) * o.ns[s])
+            assert np.abs(bv[sl] - b[sl]).max() <= 1e-12 * np.abs(b[sl]).max()
+    assert np.array_equal(bv[idx], g)
+    P = o.assemble_P()
+    ctx.assemble_P()
+    _, _, Pv = ctx.values_host()
+    assert rel_rows(P, Pv) < 1e-12 and np.all(Pv[P.data == 0.0] == 0.0)
+    ctx.set_dirichlet(np.zeros(0, np.int32), np.zeros(0))
+    push_oracle_state(ctx, o)
+    ctx.assemble(t)
+    A2, b2, _ = ctx.values_host()
+    assert np.array_equal(A2, A_free) and np.array_equal(b2, b_free)
+    ctx.close()
+
+
+def _bc_problem(kb, cfgdir, tmp_path, mode, d3, direct):
+    src = "c4_cube120_cells64_passive.yaml" if d3 else "c3_square2048_cells64.yaml"
+    txt = open(os.path.join(cfgdir, src)).read().replace("N: 120" if d3 else "N: 2048", "N: 10" if d3 else "N: 40")
+    txt = txt.replace("cells_per_dim: 4" if d3 else "cells_per_dim: 8", "cells_per_dim: 2")
+    txt = txt.replace("!range [2, 66]", "!range [2, 10]" if d3 else "!range [2, 6]")
+    txt = txt.replace("ksp_rtol: 1.0e-9", "ksp_rtol: 1.0e-12")
+    if direct:
+        txt = txt.replace("direct: False", "direct: True")
+    if mode == "dirichlet":
+        txt += "\ndirichlet_bcs: True\nboundary_tags: [1]\n"
+    f = tmp_path / "bc.yaml"
+    f.write_text(txt)
+    cls = kb.ProblemKNPEMI
+    if mode == "pinned":
+        cls = type("PinnedProblem", (kb.ProblemKNPEMI,), {"pin_ecs_potential": True})      # class switch, KNPEMIx_problem.py:997
+    return cls(str(f), verbose=False)
+
+
+@pytest.mark.parametrize("direct", [False, True], ids=["gmres", "direct"])
+@pytest.mark.parametrize("d3", [False, True], ids=["2d", "3d"])
+@pytest.mark.parametrize("mode", ["dirichlet", "pinned"])
+def test_dirichlet_conditions_time_loop_matches_oracle(kb, cfgdir, tmp_path, mode, d3, direct):
+    """``dirichlet_bcs: True`` / ``pin_ecs_potential`` through the reference-facing classes: three timesteps of all eight
+    field norms against the oracle (1e-8), no nullspace handling (KNPEMIx_solver.py:380,415), boundary values exact, and --
+    for the iterative solver -- the iteration counts of the oracle's GMRES with the same Schur preconditioner."""
+    p = _bc_problem(kb, cfgdir, tmp_path, mode, d3, direct)
+    p.set_initial_conditions()
+    models = [("Passive", None)] if d3 else MODELS_TEST
+    p.init_ionic_models([kb.PassiveModel(p)] if d3 else [kb.NeuronalCotransporters(p), kb.HodgkinHuxley(p), kb.ATPPump(p)])
+    p.setup_variational_form()
+    m = p.mesh
+    om = from_arrays(m.gdim, m.x, m.cells, m.cell_tags, m.intra_tags)
+    it = tuple(m.intra_tags)
+    bc = dict(dirichlet_bcs=True, boundary_verts=tuple(kb.mesh.boundary_vertices(m))) if mode == "dirichlet" \
+        else dict(pin_vertex=p.pinned_vertex)
+    op = OracleParams(intra_tags=it, extra_tag=1, membrane_tags=it, stimulus_tags=(2,) if not d3 else it, **bc)
+    o = KNPEMIOracle(om, op, models)
+    if not d3:                                       # configs/c3_*.yaml initial_perturbation
+        X = om.x / 1e-6
+        fac = 1 + 0.01 * np.sin(2 * np.pi * X[:, 0]) * np.sin(2 * np.pi * X[:, 1])
+        for sd in range(2):
+            o.c[sd] *= fac[None, :]
+        dphi = 0.005 * np.cos(2 * np.pi * X[:, 0])
+        o.phi_m += dphi
+        o.phi[0] += dphi
+    idx, g = o.bc_dofs()
+    p.solver_config["view_ksp"] = False
+    s = kb.SolverKNPEMI(p, solver_config=p.solver_config)
+    s.setup_solver(); p.setup_preconditioner(True); s.ctx.pc_setup(s.opts); s.ctx.set_time(0.0, 0)
+    assert s.opts.project_nullspace == 0 and s.opts.zero_mean_solution == 0
+    pc = None if direct else SchurPC(o, storage="float32")
+    x = o.pack()
+    its_gpu, its_cpu = [], []
+    for i in range(3):
+        info = s.ctx.step(s.opts); p._mark_device_newer()
+        _, _, x, its = o.step("direct" if direct else "gmres", pc, 1e-12, x, first=(i == 0))
+        its_gpu.append(info.iterations); its_cpu.append(its)
+        u, _ = s.ctx.get_state()
+        assert np.array_equal(u[idx], g)             # boundary values are imposed exactly
+        for sd in range(2):
+            for f in range(4):
+                ref = o.l2_norm(o.c[sd][f] if f < 3 else o.phi[sd], it if sd == 0 else [1])
+                got = p.l2_norm(p.wh[sd][f], list(it) if sd == 0 else [1])
+                scale = ref if f < 3 else max(ref, o.l2_norm(o.phi[0], it))
+                assert abs(got - ref) <= 1e-8 * scale, (i, sd, f, got, ref)
+    if not direct:
+        assert max(abs(a - b) for a, b in zip(its_gpu, its_cpu)) <= 1, (its_gpu, its_cpu)
+    s.ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------- mesh ingest
+def test_c1_from_an_xdmf_file_reaches_the_golden_norms(kb, cfgdir, tmp_path):
+    """BASELINE C1 with the mesh READ from square32.xdmf / square32_facets.xdmf + .h5 (the layout
+    utils/generate_square_mesh.py:37-42 writes; utils/mixed_dim_problem.py:634-681 reads) instead of generated in memory:
+    same structure as the committed golden, the reference's golden norms to 1e-8."""
+    geo = tmp_path / "geometries"
+    geo.mkdir()
+    kb.mesh.export_xdmf(kb.mesh.unit_square_fixture(32, 1.0), str(geo / "square32.xdmf"), str(geo / "square32_facets.xdmf"))
+    txt = open(os.path.join(cfgdir, "c1_square32_direct.yaml")).read().replace("./input/geometries/", "geometries/")
+    (tmp_path / "c1.yaml").write_text(txt + f'\ninput_dir: "{tmp_path}/"\n')
+    p, s, li, le = run_problem(kb, str(tmp_path), "c1.yaml")
+    assert p.mesh.grid is None and p.mesh.bc_verts is not None and p.mesh.bc_verts.size == 4 * 32     # read, not generated
+    g = np.load(os.path.join(GOLD, "c1_square32.npz"))
+    ip, ix = p._ctx.csr()
+    assert np.array_equal(ip, g["indptr"]) and np.array_equal(ix, g["indices"])
+    assert abs(li - GOLD_DIRECT[0]) / GOLD_DIRECT[0] < 1e-8
+    assert abs(le - GOLD_DIRECT[1]) / GOLD_DIRECT[1] < 1e-8

@@ -136,19 +136,28 @@ def test_no_cpu_fallback(kb, tmp_path):
         p.setup_variational_form()
 
 
-@pytest.mark.parametrize("case", ["schur_ion_2d", "schur_phi_2d", "schur_ion_3d", "jacobi_P_2d"])
+def sp_diag(A):
+    import scipy.sparse as sp
+    return sp.diags(A.diagonal())
+
+
+@pytest.mark.parametrize("case", ["schur_ion_2d", "schur_phi_2d", "schur_ion_3d", "jacobi_P_2d", "schur_ion_2d_dirichlet",
+                                  "schur_phi_2d_dirichlet", "schur_phi_3d_dirichlet"])
 def test_native_amg_setup_matches_oracle_level_by_level(kb, case):
     """amg_setup.cpp (host code of libknpemi_b200.so, no GPU needed) against oracle/amg.py: same MIS(2) aggregates,
-    filtered prolongator smoothing, adaptive strength threshold and Galerkin products -> the level operators agree."""
+    filtered prolongator smoothing, adaptive strength threshold and Galerkin products -> the level operators agree.
+    *_dirichlet: blocks with essential boundary rows (identity rows); those dofs leave the coarse space on both sides, so
+    the first coarse level is as small as that of the interior problem."""
     from oracle.amg import SAAMG, SchurPC
     from oracle.fixtures import from_arrays
     from oracle.knpemi import KNPEMIOracle, OracleParams
     from conftest import MODELS_TEST
-    d = 3 if case.endswith("3d") else 2
+    d = 3 if "3d" in case else 2
     mm = kb.mesh.cell_array_mesh(d, 24 if d == 2 else 12, 3 if d == 2 else 2)
     it = tuple(mm.intra_tags)
+    bc = dict(dirichlet_bcs=True, boundary_verts=tuple(kb.mesh.boundary_vertices(mm))) if "dirichlet" in case else {}
     o = KNPEMIOracle(from_arrays(d, mm.x, mm.cells, mm.cell_tags, mm.intra_tags),
-                     OracleParams(intra_tags=it, extra_tag=1, membrane_tags=it, stimulus_tags=(2,)), MODELS_TEST)
+                     OracleParams(intra_tags=it, extra_tag=1, membrane_tags=it, stimulus_tags=(2,), **bc), MODELS_TEST)
     rng = np.random.default_rng(4)
     for s in range(2):
         o.c[s] *= 1 + 0.05 * rng.random(o.c[s].shape)
@@ -164,6 +173,9 @@ def test_native_amg_setup_matches_oracle_level_by_level(kb, case):
     ref_ops = [lv["A"] for lv in ref.levels] + [ref.Ac]
     assert [a.shape[0] for a in levels] == [a.shape[0] for a in ref_ops]
     assert len(levels) >= 2
+    if bc:
+        nb = int((np.diff(A.indptr) > 0).sum() - (abs(A - sp_diag(A)).sum(axis=1) > 0).sum())      # identity rows
+        assert nb > 0 and levels[1].shape[0] < (A.shape[0] - nb) / 2
     for a, r in zip(levels, ref_ops):
         dd = (a - r).tocoo()
         assert dd.nnz == 0 or np.abs(dd.data).max() <= 1e-10 * np.abs(r.data).max()

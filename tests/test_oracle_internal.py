@@ -226,3 +226,42 @@ def test_pcg_restatement_solves_spd_system():
         x, its = KNPEMIOracle.solve_pcg(A, b, np.zeros(n), Binv, 1e-12)
         assert 0 < its < n
         assert np.abs(x - x_exact).max() <= 1e-10 * np.abs(x_exact).max()
+
+
+@pytest.mark.parametrize("mode", ["dirichlet", "pinned"])
+def test_essential_conditions_equal_the_reduced_system(mode):
+    """oracle.apply_bcs restates assemble_matrix_block / assemble_vector_block with bcs (KNPEMIx_solver.py:113-116: rows and
+    columns zeroed, unit diagonal, lifted right-hand side).  Independent guard: the solution equals the one of the system
+    with the constrained unknowns eliminated by hand, the constrained values come out exactly, the matrix is regular (no
+    nullspace is attached, :380,415), and GMRES with the Schur preconditioner -- Dirichlet dofs cut out of its hierarchies --
+    reaches the direct solution."""
+    import scipy.sparse.linalg as spla
+    from oracle.amg import SchurPC
+    om = unit_square(16)
+    x, y = om.x[:, 0] / om.x[:, 0].max(), om.x[:, 1] / om.x[:, 1].max()
+    bv = np.flatnonzero((x == 0) | (x == 1) | (y == 0) | (y == 1))
+    kw = dict(dirichlet_bcs=True, boundary_verts=tuple(bv)) if mode == "dirichlet" else dict(pin_vertex=0)
+    models = [("NeuronalCT", None), ("HH", None), ("ATP", None)]
+    o, free_o = KNPEMIOracle(om, OracleParams(**kw), models), KNPEMIOracle(om, OracleParams(), models)
+    idx, g = o.bc_dofs()
+    assert idx.size == (8 * 0 + 4 * bv.size if mode == "dirichlet" else 1)      # boundary vertices are extracellular only
+    A, b = o.assemble(o.p.dt)
+    A0, b0 = free_o.assemble(o.p.dt)
+    assert np.array_equal(A.indptr, A0.indptr) and np.array_equal(A.indices, A0.indices)      # entries stay in the pattern
+    assert not o.nullspace().any()
+    free = np.setdiff1d(np.arange(o.n), idx)
+    ref = np.zeros(o.n)
+    ref[idx] = g
+    ref[free] = spla.splu(A0[free][:, free].tocsc()).solve(b0[free] - A0[free][:, idx] @ g)
+    sol = o.solve_direct(A, b, o.nullspace())
+    assert np.array_equal(sol[idx], g)
+    assert np.abs(sol - ref).max() <= 1e-10 * np.abs(ref).max()
+    oa, ob = KNPEMIOracle(om, OracleParams(**kw), models), KNPEMIOracle(om, OracleParams(**kw), models)
+    pc = SchurPC(ob)
+    xb = ob.pack()
+    for i in range(2):
+        _, _, xa, _ = oa.step("direct")
+        _, _, xb, its = ob.step("gmres", pc, 1e-12, xb, first=(i == 0))
+        assert its <= (12 if mode == "dirichlet" else 22)
+        assert np.array_equal(xb[idx], g)
+        assert np.abs(xa - xb).max() <= 1e-9 * np.abs(xa).max()
