@@ -920,8 +920,12 @@ def test_dirichlet_conditions_time_loop_matches_oracle(kb, cfgdir, tmp_path, mod
                 got = p.l2_norm(p.wh[sd][f], list(it) if sd == 0 else [1])
                 scale = ref if f < 3 else max(ref, o.l2_norm(o.phi[0], it))
                 assert abs(got - ref) <= 1e-8 * scale, (i, sd, f, got, ref)
-    if not direct:
+    if not direct and mode == "dirichlet":
         assert max(abs(a - b) for a, b in zip(its_gpu, its_cpu)) <= 1, (its_gpu, its_cpu)
+    elif not direct:
+        # one pinned dof leaves the constant potential mode as a near-singular direction (no projection any more): 40-50
+        # iterations across a GMRES(30) restart, where rounding differences move the count by several iterations
+        assert all(abs(a - b) <= 0.4 * max(a, b) for a, b in zip(its_gpu, its_cpu)), (its_gpu, its_cpu)
     s.ctx.close()
 
 
