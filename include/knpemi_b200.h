@@ -251,6 +251,14 @@ int knp_rowblocks_host(int32_t n_rows, const int32_t* indptr, int32_t max_blocks
 int knp_amg_setup_host(int32_t n, const int32_t* indptr, const int32_t* indices, const double* vals, double theta,
                        int32_t coarse_size, int32_t* n_levels);
 int knp_amg_host_level(int32_t level, int64_t* n, int64_t* nnz, int32_t* indptr, int32_t* indices, double* vals);
+/* The same hierarchy built ON THE DEVICE (amg_device.cu) -- what knp_pc_setup runs on a single GPU, so that reassemble_P
+   (KNPEMIx_solver.py:137-150,405-406) costs a fraction of a second; the level operators are kept for knp_amg_host_level and
+   agree with knp_amg_setup_host bit for bit.  Needs a GPU (no CPU fallback); fails on matrices the device form hands to the
+   host setup (Dirichlet rows, unsymmetric patterns). */
+int knp_amg_setup_device(int32_t n, const int32_t* indptr, const int32_t* indices, const double* vals, double theta,
+                         int32_t coarse_size, int32_t device, int32_t* n_levels);
+/* 1 when the hierarchy of the last knp_pc_setup was built on the device, 0 when the host setup built it */
+int knp_amg_setup_was_on_device(const knp_ctx* ctx);
 /* Host-only (no GPU): the ROW-DISTRIBUTED hierarchy setup of multi-GPU runs (amg_dist.cpp; our counterpart of hypre running
    across the MPI ranks, KNPEMIx_solver.py:269-273) on `nranks` SIMULATED ranks: the matrix is split by owner[] (rows with
    owner == r belong to rank r), every rank runs the collective setup in its own thread, and the per-rank pieces are

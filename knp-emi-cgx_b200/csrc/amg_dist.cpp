@@ -99,7 +99,8 @@ int amg_dist_setup(AmgComm& comm, CsrHost&& A0, HaloHost&& halo0, std::vector<in
       if ((double)e >= 3.0 * (double)n_glob) break;
     }
     std::vector<int32_t> agg;
-    const int nagg = n > 0 ? drop_dirichlet_aggregates(cur.A, agg, mis2_aggregate(S, agg)) : 0;
+    int nagg = n > 0 ? mis2_aggregate(S, agg) : 0;
+    if (n > 0 && out.levels.empty()) nagg = drop_dirichlet_aggregates(cur.A, agg, nagg);   // finest level only (amg_setup.cpp)
     int64_t nagg_glob = nagg;
     KNP_TRY(sum_i64(comm, &nagg_glob, 1));
     if ((double)nagg_glob >= 0.8 * (double)n_glob) break;      // coarsening stalled: replicate this level

@@ -203,6 +203,8 @@ int mis2_aggregate(const Graph& S, std::vector<int32_t>& agg) {
 // Dirichlet rows -- rows without a non-zero off-diagonal entry, as the boundary conditions leave them (knp_set_dirichlet) --
 // are taken out of the coarse space: agg = -1, an empty row of the prolongator.  The level's Jacobi sweeps solve them, and
 // their singleton aggregates would otherwise survive on every level (coarsening stalls at the number of boundary dofs).
+// Applied on the finest level only: a coarse row that has lost its couplings is a whole connected component (the ion
+// block of one biological cell, say) and keeps its singleton aggregate, so that the coarsest solve treats it exactly.
 // Identical decisions to oracle/amg.py::drop_dirichlet_aggregates; a no-op for matrices without such rows.
 int drop_dirichlet_aggregates(const CsrHost& A, std::vector<int32_t>& agg, int nagg) {
   const int n = A.n_rows;
@@ -477,7 +479,8 @@ int amg_setup_host(const CsrHost& A0, double theta, int coarse_size, int max_lev
     }
     tm.lap("strength", (int)As.size() - 1, n);
     std::vector<int32_t> agg;
-    const int nagg = drop_dirichlet_aggregates(A, agg, mis2_aggregate(S, agg));
+    int nagg = mis2_aggregate(S, agg);
+    if (As.size() == 1) nagg = drop_dirichlet_aggregates(A, agg, nagg);      // boundary rows exist on the finest level only
     tm.lap("mis2", (int)As.size() - 1, n);
     if (nagg >= 0.8 * n) break;
     // Gershgorin bounds, D^-1 and the smoothed prolongator (prolongator_bounds / prolongator_build below).  The filter is

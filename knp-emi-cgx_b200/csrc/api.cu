@@ -803,6 +803,34 @@ int knp_amg_setup_host(int32_t n, const int32_t* indptr, const int32_t* indices,
   return KNP_OK;
 }
 
+int knp_amg_setup_was_on_device(const knp_ctx* c) {
+  return c ? c->amg_setup_on_device : 0;
+}
+
+int knp_amg_setup_device(int32_t n, const int32_t* indptr, const int32_t* indices, const double* vals, double theta,
+                         int32_t coarse_size, int32_t device, int32_t* n_levels) {
+  KNP_CHECK(n > 0 && indptr && indices && vals && n_levels, "bad arguments");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device || device < 0) {
+    set_error("knp_amg_setup_device: no CUDA device %d available (this entry point has no CPU fallback; knp_amg_setup_host is the host form)", device);
+    return KNP_E_CUDA;
+  }
+  KNP_CUDA(cudaSetDevice(device));
+  CsrHost A0;
+  A0.n_rows = A0.n_cols = n;
+  A0.indptr.assign(indptr, indptr + n + 1);
+  A0.indices.assign(indices, indices + indptr[n]);
+  A0.vals.assign(vals, vals + indptr[n]);
+  std::vector<CsrHost> Ps, Rs;
+  std::vector<double> rhos, cinv;
+  g_host_levels.clear();
+  int used = 0;
+  KNP_TRY(amg_setup_device(A0, theta, coarse_size, 16, g_host_levels, Ps, Rs, rhos, cinv, nullptr, &used));
+  KNP_CHECK(used, "knp_amg_setup_device: the matrix needs the host setup (Dirichlet rows or an unsymmetric pattern)");
+  *n_levels = (int32_t)g_host_levels.size();
+  return KNP_OK;
+}
+
 int knp_amg_host_level(int32_t level, int64_t* n, int64_t* nnz, int32_t* indptr, int32_t* indices, double* vals) {
   KNP_CHECK(level >= 0 && level < (int)g_host_levels.size(), "no such level");
   const CsrHost& A = g_host_levels[level];

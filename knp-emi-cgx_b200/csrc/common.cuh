@@ -209,5 +209,10 @@ struct Amg {
 int amg_setup_host(const CsrHost& A0, double theta, int coarse_size, int max_levels,
                    std::vector<CsrHost>& As, std::vector<CsrHost>& Ps, std::vector<CsrHost>& Rs,
                    std::vector<double>& rhos, std::vector<double>& coarse_inv, bool invert = true);
+// the same setup on the device (amg_device.cu); coarse_dense = the dense coarsest OPERATOR (the caller inverts it);
+// *used_device = 0: the matrix needs the host setup, outputs untouched
+int amg_setup_device(const CsrHost& A0, double theta, int coarse_size, int max_levels, std::vector<CsrHost>& As,
+                     std::vector<CsrHost>& Ps, std::vector<CsrHost>& Rs, std::vector<double>& rhos,
+                     std::vector<double>& coarse_dense, cudaStream_t st, int* used_device);
 
 }  // namespace knp

@@ -102,6 +102,7 @@ struct knp_ctx {
   knp::DevBuf<double> cg_scal, cg_hist;   // device-resident scalars and norm history of the CG loop
   // preconditioner
   int pc_kind = -1;
+  int amg_setup_on_device = 0;          // the last hierarchy was built by amg_device.cu (1) or by the host setup (0)
   std::unique_ptr<knp::Amg> amg;
   // charge-conservation Schur preconditioner (pc kind 3): hierarchies of the ion and of the potential blocks
   std::unique_ptr<knp::Amg> amg_c, amg_p;

@@ -7,6 +7,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <chrono>
+#include <cstring>
 #include "context.cuh"
 
 namespace knp {
@@ -32,6 +34,19 @@ int ensure_workspace(knp_ctx* c, int restart) {
   c->ws_restart = restart;
   return KNP_OK;
 }
+
+// KNP_AMG_TIMING=1: wall-clock phases of the preconditioner setup on stderr
+struct SetupTimer {
+  bool on = getenv("KNP_AMG_TIMING") && atoi(getenv("KNP_AMG_TIMING"));
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  void lap(const char* what) {
+    if (!on) return;
+    cudaDeviceSynchronize();
+    const auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "pc setup: %-44s %.3f s\n", what, std::chrono::duration<double>(t1 - t0).count());
+    t0 = t1;
+  }
+};
 
 static int upload_csr(const CsrHost& h, CsrDev& d) {
   d.n_rows = h.n_rows;
@@ -113,7 +128,21 @@ static int build_amg(knp_ctx* c, const CsrHost& A0, std::unique_ptr<Amg>& out, i
                      int level0 = 0) {
   std::vector<CsrHost> As, Ps, Rs;
   std::vector<double> rhos, cinv;
-  KNP_TRY(amg_setup_host(A0, 0.08, coarse_size, 16, As, Ps, Rs, rhos, cinv, !spd));
+  // single-GPU runs build the hierarchy on the device (amg_device.cu: same decisions, bit-identical operators);
+  // KNP_AMG_SETUP=host|device overrides, matrices the device form does not take (Dirichlet rows) fall back to the host
+  static const char* where = getenv("KNP_AMG_SETUP");
+  const bool on_device = where ? !strcmp(where, "device") : c->nranks == 1;
+  int used_device = 0;
+  SetupTimer tm;
+  if (on_device) KNP_TRY(amg_setup_device(A0, 0.08, coarse_size, 16, As, Ps, Rs, rhos, cinv, c->stream, &used_device));
+  if (used_device && !spd) {
+    std::vector<double> dense;
+    dense.swap(cinv);
+    KNP_TRY(dense_inverse(As.back().n_rows, dense, cinv));
+  }
+  if (!used_device) KNP_TRY(amg_setup_host(A0, 0.08, coarse_size, 16, As, Ps, Rs, rhos, cinv, !spd));
+  c->amg_setup_on_device = used_device;
+  tm.lap(used_device ? "hierarchy (device setup)" : "hierarchy (host setup)");
   auto amg = std::make_unique<Amg>();
   const int nl = (int)Ps.size();
   for (int l = 0; l < nl; ++l) {
@@ -133,6 +162,7 @@ static int build_amg(knp_ctx* c, const CsrHost& A0, std::unique_ptr<Amg>& out, i
     KNP_TRY(to_f32(lv->P, c->stream));
     KNP_TRY(to_f32(lv->R, c->stream));
   }
+  tm.lap("upload of the levels, row blocks, float32");
   amg->n_coarse = As.back().n_rows;
   KNP_TRY(amg->coarse_inv.upload(cinv));
   if (spd) KNP_TRY(dense_inverse_device(amg->n_coarse, amg->coarse_inv.p, c->stream));
@@ -148,6 +178,7 @@ static int build_amg(knp_ctx* c, const CsrHost& A0, std::unique_ptr<Amg>& out, i
   amg->hostA = std::move(As);
   amg->level0 = level0;
   KNP_CUDA(cudaStreamSynchronize(c->stream));
+  tm.lap("coarsest inverse");
   out = std::move(amg);
   return KNP_OK;
 }
@@ -489,6 +520,7 @@ static int schur_setup(knp_ctx* c) {
   const int n = L.n_rows, n0 = L.n_own[0], n1 = L.n_own[1];
   KNP_CHECK(L.rowbase[0] == 0 && L.rowbase[1] == 4 * n0, "unexpected row layout");
   cudaStream_t st = c->stream;
+  SetupTimer tm;
   // P~: ion blocks M + dt D_k K, phi blocks K_phi + (C_M/F) M_Gamma (the sign the membrane term has in `a`)
   KParams kp = c->kp;
   kp.C_M = -c->kp.C_M;
@@ -514,6 +546,7 @@ static int schur_setup(knp_ctx* c) {
   KNP_CUDA(cudaMemcpy(mval.data(), c->M_vals.p, mval.size() * sizeof(double), cudaMemcpyDeviceToHost));
   KNP_CUDA(cudaMemcpy(u.data(), c->u.p, u.size() * sizeof(double), cudaMemcpyDeviceToHost));
   const std::vector<int32_t>& ip = c->H.indptr_P;
+  tm.lap("P~ and M assembly, copies to the host");
   // compact numbering: c part [s=0: 3 n0 | s=1: 3 n1], phi part [n0 | n1]; ghost columns are dropped (processor-local)
   auto cmap = [&](int i) -> int {   // full row/col -> compact index in its part, or -1 if it belongs to the other part
     if (i < 3 * n0) return i;
@@ -545,6 +578,7 @@ static int schur_setup(knp_ctx* c) {
     M.indptr.push_back((int32_t)M.indices.size());
   }
   // rows were visited in the order c(s=0), phi(s=0), c(s=1), phi(s=1) = ascending compact order in both parts
+  tm.lap("ion / potential blocks extracted");
   if (c->nranks > 1) {
     std::vector<double> oidx;
     KNP_TRY(exchange_owner_index(c, [&](int i) { return cmap(i) >= 0 ? cmap(i) : pmap(i); }, oidx));
@@ -579,6 +613,7 @@ static int schur_setup(knp_ctx* c) {
       a->tail->gamma = 2;
       a->tail->gamma_last = a->gamma_last;
     }
+  tm.lap("both hierarchies");
   // the P buffer now holds the sign-flipped Schur form, not the reference's block-Jacobi P: pc kinds 1 / 2 must re-assemble
   c->P_assembled = false;
   KNP_TRY(c->sch_vc.alloc((size_t)3 * (n0 + n1)));
@@ -616,6 +651,7 @@ static int schur_setup(knp_ctx* c) {
   KNP_TRY(c->sch_q.alloc(L.n_cols));
   KNP_TRY(c->sch_rhs.alloc(L.n_rows));
   KNP_CUDA(cudaMemset(c->sch_q.p, 0, (size_t)L.n_cols * sizeof(double)));
+  tm.lap("lumped mass, row blocks of M, work vectors");
   return KNP_OK;
 }
 

@@ -65,7 +65,7 @@ SYMBOLS = [
     "knp_csr_P_host", "knp_dofmap_host", "knp_mverts_host", "knp_set_params", "knp_stimulus_area_local",
     "knp_set_state", "knp_get_state", "knp_state_dev", "knp_phi_m_host", "knp_gate_step", "knp_assemble",
     "knp_assemble_P", "knp_set_source", "knp_set_dirichlet", "knp_values_dev", "knp_spmv", "knp_pc_setup", "knp_pc_apply", "knp_pc_bytes", "knp_solve", "knp_step",
-    "knp_step_host", "knp_set_time", "knp_get_time", "knp_l2_norm_sq", "knp_integral", "knp_membrane_area", "knp_probe_setup", "knp_probe_eval", "knp_stimulus_current", "knp_last_timings", "knp_amg_num_levels", "knp_amg_part_levels", "knp_amg_setup_host", "knp_amg_host_level", "knp_pattern_host", "knp_edge_tables_host", "knp_rowblocks_host",
+    "knp_step_host", "knp_set_time", "knp_get_time", "knp_l2_norm_sq", "knp_integral", "knp_membrane_area", "knp_probe_setup", "knp_probe_eval", "knp_stimulus_current", "knp_last_timings", "knp_amg_num_levels", "knp_amg_part_levels", "knp_amg_setup_host", "knp_amg_host_level", "knp_amg_setup_device", "knp_amg_setup_was_on_device", "knp_pattern_host", "knp_edge_tables_host", "knp_rowblocks_host",
     "knp_amg_dist_sim_host", "knp_amg_dist_sim_level", "knp_amg_dist_sim_perm",
     "knp_copy", "knp_amg_level_sizes", "knp_amg_level_host", "knp_nccl_unique_id", "knp_dist_init", "knp_halo_exchange", "knp_peer_direct",
     "knp_allreduce_sum",
@@ -134,6 +134,8 @@ def load():
     lib.knp_pattern_host.argtypes = [vp, c_i64p, c_i64p, vp, vp, vp, vp, vp]
     lib.knp_edge_tables_host.argtypes = [vp, c_i32p, c_i64p, c_i32p, vp, vp, vp, vp]
     lib.knp_amg_setup_host.argtypes = [C.c_int32, vp, vp, vp, C.c_double, C.c_int32, vp]
+    lib.knp_amg_setup_device.argtypes = [C.c_int32, vp, vp, vp, C.c_double, C.c_int32, C.c_int32, vp]
+    lib.knp_amg_setup_was_on_device.argtypes = [vp]
     lib.knp_amg_host_level.argtypes = [C.c_int32, c_i64p, c_i64p, vp, vp, vp]
     lib.knp_amg_level_sizes.argtypes = [vp, C.c_int32, c_i64p, c_i64p]
     lib.knp_amg_dist_sim_host.argtypes = [C.c_int32, C.c_int32, vp, vp, vp, vp, C.c_double, C.c_int64, vp]
@@ -490,8 +492,9 @@ def nccl_unique_id():
     return buf.raw
 
 
-def amg_setup_host(A, theta=0.08, coarse_size=600):
-    """Level operators (scipy CSR) of the library's smoothed-aggregation setup for a scipy CSR matrix; host only."""
+def amg_setup_host(A, theta=0.08, coarse_size=600, device=None):
+    """Level operators (scipy CSR) of the library's smoothed-aggregation setup for a scipy CSR matrix: the host form
+    (amg_setup.cpp, no GPU needed) or, with device = a CUDA device index, the device form (amg_device.cu)."""
     import scipy.sparse as sp
     lib = load()
     A = sp.csr_matrix(A)
@@ -500,7 +503,10 @@ def amg_setup_host(A, theta=0.08, coarse_size=600):
     ix = np.ascontiguousarray(A.indices, np.int32)
     va = np.ascontiguousarray(A.data, np.float64)
     nl = C.c_int32()
-    check(lib.knp_amg_setup_host(A.shape[0], _ptr(ip), _ptr(ix), _ptr(va), theta, coarse_size, C.byref(nl)))
+    if device is None:
+        check(lib.knp_amg_setup_host(A.shape[0], _ptr(ip), _ptr(ix), _ptr(va), theta, coarse_size, C.byref(nl)))
+    else:
+        check(lib.knp_amg_setup_device(A.shape[0], _ptr(ip), _ptr(ix), _ptr(va), theta, coarse_size, int(device), C.byref(nl)))
     out = []
     for l in range(nl.value):
         n, nnz = C.c_int64(), C.c_int64()

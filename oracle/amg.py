@@ -109,7 +109,9 @@ def sa_level(A, theta=0.08, omega=4.0 / 3.0, filtered=None, level=0):
         S = strength_graph(A, theta * 0.5 ** attempt)
         if S.nnz >= 3.0 * n:
             break
-    agg, nagg = drop_dirichlet_aggregates(A, *mis2_aggregate(S))
+    agg, nagg = mis2_aggregate(S)
+    if level == 0:                           # boundary rows exist on the finest level only
+        agg, nagg = drop_dirichlet_aggregates(A, agg, nagg)
     # unnormalised tentative prolongator: the constant stays the near-nullspace vector on every level
     inn = np.flatnonzero(agg >= 0)
     T = sp.csr_matrix((np.ones(inn.size), (inn, agg[inn])), shape=(n, nagg))

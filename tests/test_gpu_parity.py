@@ -946,3 +946,59 @@ def test_c1_from_an_xdmf_file_reaches_the_golden_norms(kb, cfgdir, tmp_path):
     assert np.array_equal(ip, g["indptr"]) and np.array_equal(ix, g["indices"])
     assert abs(li - GOLD_DIRECT[0]) / GOLD_DIRECT[0] < 1e-8
     assert abs(le - GOLD_DIRECT[1]) / GOLD_DIRECT[1] < 1e-8
+
+
+# ---------------------------------------------------------------------------------------------- AMG setup on the device
+@pytest.mark.parametrize("case", ["schur_ion_2d", "schur_phi_2d", "schur_ion_3d", "schur_phi_3d", "jacobi_P_2d"])
+def test_device_amg_setup_equals_host_setup(kb, case):
+    """amg_device.cu (what knp_pc_setup runs on a single GPU) against amg_setup.cpp (the host form, itself compared with
+    oracle/amg.py level by level in the CPU tier): same strength graphs, MIS(2) aggregates, prolongators and Galerkin
+    products -- every level operator agrees BIT FOR BIT (one thread per row accumulates in the host's order, without FMA
+    contraction)."""
+    d = 3 if "3d" in case else 2
+    mm = kb.mesh.cell_array_mesh(d, 96 if d == 2 else 20, 3 if d == 2 else 2)
+    it = tuple(mm.intra_tags)
+    o = KNPEMIOracle(from_arrays(d, mm.x, mm.cells, mm.cell_tags, mm.intra_tags),
+                     OracleParams(intra_tags=it, extra_tag=1, membrane_tags=it, stimulus_tags=(2,)), MODELS_TEST)
+    rng = np.random.default_rng(4)
+    for s in range(2):
+        o.c[s] *= 1 + 0.05 * rng.random(o.c[s].shape)
+    if case == "jacobi_P_2d":
+        A = o.assemble_P().tocsr()
+    else:
+        pc = SchurPC(o, exact=True)
+        Pt = o.assemble_P(membrane_sign=+1.0).tocsr()
+        idx = pc.ic if "ion" in case else pc.ip
+        A = Pt[idx][:, idx].tocsr()
+    host = kb.lib.amg_setup_host(A, theta=0.08, coarse_size=100)
+    dev = kb.lib.amg_setup_host(A, theta=0.08, coarse_size=100, device=0)
+    assert len(dev) == len(host) and len(host) >= 3
+    for a, b in zip(dev, host):
+        assert a.shape == b.shape and np.array_equal(a.indptr, b.indptr) and np.array_equal(a.indices, b.indices)
+        assert np.array_equal(a.data, b.data)
+
+
+def test_pc_setup_builds_its_hierarchies_on_the_device(kb):
+    """knp_pc_setup on one GPU uses the device setup (KNP_AMG_SETUP=host switches back) unless the blocks carry Dirichlet
+    rows, and the resulting hierarchy is the host's (level sizes and operators of the Schur ion block)."""
+    om, p = _cells(2, 72, 3)(kb)
+    o = perturbed_oracle(om, p, MODELS_TEST, seed=1)
+    ctx = make_ctx(kb, om, p, MODELS_TEST)
+    push_oracle_state(ctx, o)
+    opts = kb.lib.SolveOpts()
+    opts.pc, opts.rtol, opts.max_it, opts.restart = 3, 1e-9, 100, 30
+    ctx.pc_setup(opts)
+    assert ctx._lib.knp_amg_setup_was_on_device(ctx.h) == 1
+    lv = ctx.amg_levels(part=0)
+    assert len(lv) >= 2
+    pc = SchurPC(o, exact=True)
+    Pt = o.assemble_P(membrane_sign=+1.0).tocsr()
+    host = kb.lib.amg_setup_host(Pt[pc.ic][:, pc.ic].tocsr(), theta=0.08, coarse_size=2500)
+    assert [a.shape[0] for a in lv] == [a.shape[0] for a in host]
+    for a, b in zip(lv[1:], host[1:]):
+        assert abs(a - b).max() <= 1e-12 * abs(b).max()
+    idx, g = KNPEMIOracle(om, _bc_params(kb, om, p, "dirichlet"), MODELS_TEST).bc_dofs()
+    ctx.set_dirichlet(idx, g)
+    ctx.pc_setup(opts)
+    assert ctx._lib.knp_amg_setup_was_on_device(ctx.h) == 0
+    ctx.close()
