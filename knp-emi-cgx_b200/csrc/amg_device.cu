@@ -95,12 +95,6 @@ static int exclusive_scan(const Tin* in, int64_t* out, int64_t n, int64_t* total
 }
 
 // ------------------------------------------------------------------------------------------------ small helpers
-struct DCsr {            // device CSR with 32-bit row pointers (what the cycle and the host form use)
-  int n_rows = 0, n_cols = 0;
-  int64_t nnz = 0;
-  DevBuf<int32_t> indptr, indices;
-  DevBuf<double> vals;
-};
 __global__ void narrow_ptr_kernel(int64_t n1, const int64_t* __restrict__ in, int32_t* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n1) out[i] = (int32_t)in[i];
@@ -490,7 +484,7 @@ static int transpose_device(const DCsr& A, DCsr& T, cudaStream_t st) {
   return KNP_OK;
 }
 
-static int download(const DCsr& D, CsrHost& H) {
+int dcsr_download(const DCsr& D, CsrHost& H) {
   H.n_rows = D.n_rows;
   H.n_cols = D.n_cols;
   H.indptr.resize((size_t)D.n_rows + 1);
@@ -584,7 +578,7 @@ static int mis2_device(int n, const DevBuf<int64_t>& sp, const DevBuf<int32_t>& 
   return KNP_OK;
 }
 
-static int upload_dcsr(const CsrHost& H, DCsr& D) {
+int dcsr_upload(const CsrHost& H, DCsr& D) {
   D.n_rows = H.n_rows;
   D.n_cols = H.n_cols;
   D.nnz = H.nnz();
@@ -594,11 +588,8 @@ static int upload_dcsr(const CsrHost& H, DCsr& D) {
   return KNP_OK;
 }
 
-// Same contract as amg_setup_host (amg_setup.cpp).  *used_device = 0 when the matrix needs the host path (Dirichlet rows,
-// unsymmetric pattern): the outputs are untouched then.
-int amg_setup_device(const CsrHost& A0, double theta, int coarse_size, int max_levels, std::vector<CsrHost>& As,
-                     std::vector<CsrHost>& Ps, std::vector<CsrHost>& Rs, std::vector<double>& rhos,
-                     std::vector<double>& coarse_dense, cudaStream_t st, int* used_device) {
+int amg_setup_device_core(std::unique_ptr<DCsr>& A0, double theta, int coarse_size, int max_levels, DevHierarchy& out,
+                          cudaStream_t st, int* used_device) {
   *used_device = 0;
   const bool timing = getenv("KNP_AMG_TIMING") && atoi(getenv("KNP_AMG_TIMING"));
   auto t0 = std::chrono::steady_clock::now();
@@ -609,14 +600,11 @@ int amg_setup_device(const CsrHost& A0, double theta, int coarse_size, int max_l
     fprintf(stderr, "amg device setup level %d (n = %d): %-12s %.3f s\n", level, n, what, std::chrono::duration<double>(t1 - t0).count());
     t0 = t1;
   };
-  std::vector<CsrHost> As_, Ps_, Rs_;
-  std::vector<double> rhos_;
-  As_.push_back(A0);
-  auto cur = std::make_unique<DCsr>();
-  KNP_TRY(upload_dcsr(A0, *cur));
-  lap("copy + upload", 0, A0.n_rows);
+  DevHierarchy H;
+  const DCsr* cur = A0.get();
   const double omega = 4.0 / 3.0;
-  while (cur->n_rows > coarse_size && (int)As_.size() < max_levels) {
+  int nlev = 1;
+  while (cur->n_rows > coarse_size && nlev < max_levels) {
     const DCsr& A = *cur;
     const int n = A.n_rows;
     DevBuf<int64_t> sp;
@@ -626,16 +614,16 @@ int amg_setup_device(const CsrHost& A0, double theta, int coarse_size, int max_l
     int hflags[2] = {0, 0};
     for (int attempt = 0; attempt < 4; ++attempt, theta_l *= 0.5) {
       KNP_TRY(strength_device(A, theta_l, sp, sidx, &edges, hflags, st));
-      if ((hflags[0] && As_.size() == 1) || hflags[1]) return KNP_OK;      // host setup (Dirichlet rows live on level 0)
+      if ((hflags[0] && nlev == 1) || hflags[1]) return KNP_OK;      // host setup (Dirichlet rows live on level 0)
       if ((double)edges >= 3.0 * n) break;
     }
-    lap("strength", (int)As_.size() - 1, n);
+    lap("strength", nlev - 1, n);
     DevBuf<int32_t> agg;
     int nagg = 0;
     KNP_TRY(mis2_device(n, sp, sidx, agg, &nagg, st));
-    lap("mis2", (int)As_.size() - 1, n);
+    lap("mis2", nlev - 1, n);
     if (nagg >= 0.8 * n) break;
-    const bool filtered = As_.size() == 1 || (double)A.nnz > 32.0 * n;
+    const bool filtered = nlev == 1 || (double)A.nnz > 32.0 * n;
     DevBuf<double> dinv, rho2;
     KNP_TRY(dinv.alloc(n));
     KNP_TRY(rho2.alloc(2));
@@ -645,7 +633,7 @@ int amg_setup_device(const CsrHost& A0, double theta, int coarse_size, int max_l
     KNP_CUDA(cudaMemcpyAsync(hrho, rho2.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
     KNP_CUDA(cudaStreamSynchronize(st));
     // prolongator: scratch segments = the rows of A
-    DCsr P;
+    auto P = std::make_unique<DCsr>();
     {
       DevBuf<int32_t> pcol, plen;
       DevBuf<double> pval;
@@ -658,51 +646,77 @@ int amg_setup_device(const CsrHost& A0, double theta, int coarse_size, int max_l
                  omega / hrho[1], pcol.p, pval.p, plen.p);
       int64_t pnnz = 0;
       KNP_TRY(exclusive_scan<int32_t>(plen.p, pptr.p, n, &pnnz, st));
-      P.n_rows = n;
-      P.n_cols = nagg;
-      P.nnz = pnnz;
-      KNP_TRY(P.indices.alloc((size_t)pnnz));
-      KNP_TRY(P.vals.alloc((size_t)pnnz));
-      DEV_LAUNCH(compact_rows_kernel, n, n, A.indptr.p, nullptr, pcol.p, pval.p, pptr.p, P.indices.p, P.vals.p);
-      KNP_TRY(narrow_ptr(pptr.p, (int64_t)n + 1, P.indptr, st));
+      P->n_rows = n;
+      P->n_cols = nagg;
+      P->nnz = pnnz;
+      KNP_TRY(P->indices.alloc((size_t)pnnz));
+      KNP_TRY(P->vals.alloc((size_t)pnnz));
+      DEV_LAUNCH(compact_rows_kernel, n, n, A.indptr.p, nullptr, pcol.p, pval.p, pptr.p, P->indices.p, P->vals.p);
+      KNP_TRY(narrow_ptr(pptr.p, (int64_t)n + 1, P->indptr, st));
       KNP_CUDA(cudaStreamSynchronize(st));
     }
     sp.free();
     sidx.free();
     agg.free();
-    lap("prolongator", (int)As_.size() - 1, n);
-    DCsr R, AP;
+    lap("prolongator", nlev - 1, n);
+    auto R = std::make_unique<DCsr>();
     auto Ac = std::make_unique<DCsr>();
-    KNP_TRY(transpose_device(P, R, st));
-    lap("transpose", (int)As_.size() - 1, n);
-    KNP_TRY(spgemm_device(A, P, AP, st));
-    lap("A*P", (int)As_.size() - 1, n);
-    KNP_TRY(spgemm_device(R, AP, *Ac, st));
-    lap("R*(AP)", (int)As_.size() - 1, n);
-    rhos_.push_back(hrho[0]);
-    Ps_.emplace_back();
-    Rs_.emplace_back();
-    As_.emplace_back();
-    KNP_TRY(download(P, Ps_.back()));
-    KNP_TRY(download(R, Rs_.back()));
-    KNP_TRY(download(*Ac, As_.back()));
-    lap("download", (int)As_.size() - 2, n);
-    cur = std::move(Ac);
+    DCsr AP;
+    KNP_TRY(transpose_device(*P, *R, st));
+    lap("transpose", nlev - 1, n);
+    KNP_TRY(spgemm_device(A, *P, AP, st));
+    lap("A*P", nlev - 1, n);
+    KNP_TRY(spgemm_device(*R, AP, *Ac, st));
+    lap("R*(AP)", nlev - 1, n);
+    H.rhos.push_back(hrho[0]);
+    H.P.push_back(std::move(P));
+    H.R.push_back(std::move(R));
+    H.A.push_back(std::move(Ac));               // H.A holds the levels 1.. until the setup is known to succeed
+    cur = H.A.back().get();
+    ++nlev;
   }
-  const CsrHost& Ac = As_.back();
-  const int nc = Ac.n_rows;
+  const int nc = cur->n_rows;
   if ((int64_t)nc * nc > (int64_t)64 * 1000 * 1000) {
     set_error("AMG coarsening stalled at %d unknowns; coarsest level too large for a dense solve", nc);
     return KNP_E_UNSUPPORTED;
   }
-  coarse_dense.assign((size_t)nc * nc, 0.0);
-  for (int i = 0; i < nc; ++i)
-    for (int j = Ac.indptr[i]; j < Ac.indptr[i + 1]; ++j) coarse_dense[(size_t)i * nc + Ac.indices[j]] += Ac.vals[j];
-  As.swap(As_);
-  Ps.swap(Ps_);
-  Rs.swap(Rs_);
-  rhos.swap(rhos_);
+  out.A.clear();
+  out.A.push_back(std::move(A0));
+  for (auto& a : H.A) out.A.push_back(std::move(a));
+  out.P = std::move(H.P);
+  out.R = std::move(H.R);
+  out.rhos = std::move(H.rhos);
   *used_device = 1;
+  return KNP_OK;
+}
+
+// dense form of a (small) CSR operator
+static void dense_of(const CsrHost& Ac, std::vector<double>& M) {
+  const int nc = Ac.n_rows;
+  M.assign((size_t)nc * nc, 0.0);
+  for (int i = 0; i < nc; ++i)
+    for (int j = Ac.indptr[i]; j < Ac.indptr[i + 1]; ++j) M[(size_t)i * nc + Ac.indices[j]] += Ac.vals[j];
+}
+
+int amg_setup_device(const CsrHost& A0, double theta, int coarse_size, int max_levels, std::vector<CsrHost>& As,
+                     std::vector<CsrHost>& Ps, std::vector<CsrHost>& Rs, std::vector<double>& rhos,
+                     std::vector<double>& coarse_dense, cudaStream_t st, int* used_device) {
+  auto d0 = std::make_unique<DCsr>();
+  KNP_TRY(dcsr_upload(A0, *d0));
+  DevHierarchy H;
+  KNP_TRY(amg_setup_device_core(d0, theta, coarse_size, max_levels, H, st, used_device));
+  if (!*used_device) return KNP_OK;
+  As.assign(H.A.size(), CsrHost());
+  Ps.assign(H.P.size(), CsrHost());
+  Rs.assign(H.R.size(), CsrHost());
+  As[0] = A0;
+  for (size_t l = 1; l < H.A.size(); ++l) KNP_TRY(dcsr_download(*H.A[l], As[l]));
+  for (size_t l = 0; l < H.P.size(); ++l) {
+    KNP_TRY(dcsr_download(*H.P[l], Ps[l]));
+    KNP_TRY(dcsr_download(*H.R[l], Rs[l]));
+  }
+  rhos = H.rhos;
+  dense_of(As.back(), coarse_dense);
   return KNP_OK;
 }
 

@@ -702,13 +702,16 @@ int knp_amg_level_sizes(const knp_ctx* c, int32_t level, int64_t* n, int64_t* nn
   const CsrHost* A = amg_level(c, level);
   KNP_CHECK(A, "no such AMG level");
   if (n) *n = A->n_rows;
-  if (nnz) *nnz = A->nnz();
+  if (nnz) *nnz = A->indptr.empty() ? 0 : (int64_t)A->indptr.back();
   return KNP_OK;
 }
 
 int knp_amg_level_host(const knp_ctx* c, int32_t level, int32_t* indptr, int32_t* indices, double* vals) {
   const CsrHost* A = amg_level(c, level);
   KNP_CHECK(A, "no such AMG level");
+  KNP_CHECK(!(indices || vals) || A->indptr.empty() || (int64_t)A->indices.size() == (int64_t)A->indptr.back(),
+            "the finest level of a hierarchy built on the device is kept on the host only up to 4 M rows "
+            "(KNP_AMG_KEEP_HOST=1 keeps it)");
   if (indptr) memcpy(indptr, A->indptr.data(), A->indptr.size() * sizeof(int32_t));
   if (indices) memcpy(indices, A->indices.data(), A->indices.size() * sizeof(int32_t));
   if (vals) memcpy(vals, A->vals.data(), A->vals.size() * sizeof(double));

@@ -1,6 +1,7 @@
 // Internal definitions shared by the translation units of libknpemi_b200.so.
 #pragma once
 #include <cuda_runtime.h>
+#include <memory>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -209,8 +210,25 @@ struct Amg {
 int amg_setup_host(const CsrHost& A0, double theta, int coarse_size, int max_levels,
                    std::vector<CsrHost>& As, std::vector<CsrHost>& Ps, std::vector<CsrHost>& Rs,
                    std::vector<double>& rhos, std::vector<double>& coarse_inv, bool invert = true);
-// the same setup on the device (amg_device.cu); coarse_dense = the dense coarsest OPERATOR (the caller inverts it);
-// *used_device = 0: the matrix needs the host setup, outputs untouched
+// ---- the same setup on the device (amg_device.cu) ----
+struct DCsr {            // device CSR, 32-bit row pointers, double values
+  int n_rows = 0, n_cols = 0;
+  int64_t nnz = 0;
+  DevBuf<int32_t> indptr, indices;
+  DevBuf<double> vals;
+};
+struct DevHierarchy {    // A[l] (l = 0 .. L), P[l], R[l], rho[l] (l < L), all device resident
+  std::vector<std::unique_ptr<DCsr>> A, P, R;
+  std::vector<double> rhos;
+};
+int dcsr_upload(const CsrHost& H, DCsr& D);
+int dcsr_download(const DCsr& D, CsrHost& H);
+// Device-resident form: A0 is consumed (it becomes out.A[0]) only when *used_device = 1; *used_device = 0 means the matrix
+// needs the host setup (Dirichlet rows on the finest level, unsymmetric pattern) and A0 / out are untouched.
+int amg_setup_device_core(std::unique_ptr<DCsr>& A0, double theta, int coarse_size, int max_levels, DevHierarchy& out,
+                          cudaStream_t st, int* used_device);
+// Host-in / host-out form with the contract of amg_setup_host; coarse_dense = the dense coarsest OPERATOR (the caller
+// inverts it); *used_device = 0: outputs untouched
 int amg_setup_device(const CsrHost& A0, double theta, int coarse_size, int max_levels, std::vector<CsrHost>& As,
                      std::vector<CsrHost>& Ps, std::vector<CsrHost>& Rs, std::vector<double>& rhos,
                      std::vector<double>& coarse_dense, cudaStream_t st, int* used_device);

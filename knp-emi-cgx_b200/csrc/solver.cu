@@ -122,37 +122,22 @@ static int dense_inverse_device(int n, double* A, cudaStream_t st) {
   return KNP_OK;
 }
 
-// builds the hierarchy of A0 on the host and uploads it; spd: coarsest operator (<= coarse_size unknowns) inverted on
-// the device
-static int build_amg(knp_ctx* c, const CsrHost& A0, std::unique_ptr<Amg>& out, int coarse_size = 600, bool spd = false,
-                     int level0 = 0) {
-  std::vector<CsrHost> As, Ps, Rs;
-  std::vector<double> rhos, cinv;
+static bool amg_setup_device_default(const knp_ctx* c) {
   // single-GPU runs build the hierarchy on the device (amg_device.cu: same decisions, bit-identical operators);
   // KNP_AMG_SETUP=host|device overrides, matrices the device form does not take (Dirichlet rows) fall back to the host
   static const char* where = getenv("KNP_AMG_SETUP");
-  const bool on_device = where ? !strcmp(where, "device") : c->nranks == 1;
-  int used_device = 0;
+  return where ? !strcmp(where, "device") : c->nranks == 1;
+}
+
+// per-level work vectors, D^-1, single-precision storage; coarsest inverse (dense operator in cinv when spd, its inverse
+// otherwise)
+static int finish_amg(knp_ctx* c, std::unique_ptr<Amg>& amg, std::vector<double>& rhos, std::vector<double>& cinv, int n_coarse,
+                      bool spd, int level0, std::unique_ptr<Amg>& out) {
   SetupTimer tm;
-  if (on_device) KNP_TRY(amg_setup_device(A0, 0.08, coarse_size, 16, As, Ps, Rs, rhos, cinv, c->stream, &used_device));
-  if (used_device && !spd) {
-    std::vector<double> dense;
-    dense.swap(cinv);
-    KNP_TRY(dense_inverse(As.back().n_rows, dense, cinv));
-  }
-  if (!used_device) KNP_TRY(amg_setup_host(A0, 0.08, coarse_size, 16, As, Ps, Rs, rhos, cinv, !spd));
-  c->amg_setup_on_device = used_device;
-  tm.lap(used_device ? "hierarchy (device setup)" : "hierarchy (host setup)");
-  auto amg = std::make_unique<Amg>();
-  const int nl = (int)Ps.size();
-  for (int l = 0; l < nl; ++l) {
-    auto* lv = new AmgLevelDev();
-    amg->levels.push_back(lv);
-    KNP_TRY(upload_csr(As[l], lv->A));
-    KNP_TRY(upload_csr(Ps[l], lv->P));
-    KNP_TRY(upload_csr(Rs[l], lv->R));
+  for (size_t l = 0; l < amg->levels.size(); ++l) {
+    AmgLevelDev* lv = amg->levels[l];
     lv->rho = rhos[l];
-    const int nr = As[l].n_rows;
+    const int nr = lv->A.n_rows;
     KNP_TRY(lv->dinv.alloc(nr));
     KNP_TRY(lv->x.alloc(nr));
     KNP_TRY(lv->b.alloc(nr));
@@ -162,8 +147,8 @@ static int build_amg(knp_ctx* c, const CsrHost& A0, std::unique_ptr<Amg>& out, i
     KNP_TRY(to_f32(lv->P, c->stream));
     KNP_TRY(to_f32(lv->R, c->stream));
   }
-  tm.lap("upload of the levels, row blocks, float32");
-  amg->n_coarse = As.back().n_rows;
+  tm.lap("level vectors, D^-1, float32 storage");
+  amg->n_coarse = n_coarse;
   KNP_TRY(amg->coarse_inv.upload(cinv));
   if (spd) KNP_TRY(dense_inverse_device(amg->n_coarse, amg->coarse_inv.p, c->stream));
   if (amg_f32() && amg->n_coarse > 0) {
@@ -175,12 +160,124 @@ static int build_amg(knp_ctx* c, const CsrHost& A0, std::unique_ptr<Amg>& out, i
   }
   KNP_TRY(amg->cb.alloc(amg->n_coarse));
   KNP_TRY(amg->cx.alloc(amg->n_coarse));
-  amg->hostA = std::move(As);
   amg->level0 = level0;
   KNP_CUDA(cudaStreamSynchronize(c->stream));
   tm.lap("coarsest inverse");
   out = std::move(amg);
   return KNP_OK;
+}
+
+// builds the hierarchy of A0 (host copy) and uploads it; spd: coarsest operator (<= coarse_size unknowns) inverted on
+// the device
+static int build_amg(knp_ctx* c, const CsrHost& A0, std::unique_ptr<Amg>& out, int coarse_size = 600, bool spd = false,
+                     int level0 = 0, bool allow_device = true) {
+  std::vector<CsrHost> As, Ps, Rs;
+  std::vector<double> rhos, cinv;
+  int used_device = 0;
+  SetupTimer tm;
+  if (allow_device && amg_setup_device_default(c))
+    KNP_TRY(amg_setup_device(A0, 0.08, coarse_size, 16, As, Ps, Rs, rhos, cinv, c->stream, &used_device));
+  if (used_device && !spd) {
+    std::vector<double> dense;
+    dense.swap(cinv);
+    KNP_TRY(dense_inverse(As.back().n_rows, dense, cinv));
+  }
+  if (!used_device) KNP_TRY(amg_setup_host(A0, 0.08, coarse_size, 16, As, Ps, Rs, rhos, cinv, !spd));
+  c->amg_setup_on_device = used_device;
+  tm.lap(used_device ? "hierarchy (device setup, host in / out)" : "hierarchy (host setup)");
+  auto amg = std::make_unique<Amg>();
+  const int nl = (int)Ps.size();
+  for (int l = 0; l < nl; ++l) {
+    auto* lv = new AmgLevelDev();
+    amg->levels.push_back(lv);
+    KNP_TRY(upload_csr(As[l], lv->A));
+    KNP_TRY(upload_csr(Ps[l], lv->P));
+    KNP_TRY(upload_csr(Rs[l], lv->R));
+  }
+  tm.lap("upload of the levels, row blocks");
+  const int n_coarse = As.back().n_rows;
+  amg->hostA = std::move(As);
+  return finish_amg(c, amg, rhos, cinv, n_coarse, spd, level0, out);
+}
+
+template <class T>
+static void swap_buf(DevBuf<T>& a, DevBuf<T>& b) {
+  std::swap(a.p, b.p);
+  std::swap(a.n, b.n);
+}
+
+// device CSR of the setup -> operator of the cycle: padded row pointers, row blocks of the streaming SpMV; the arrays move.
+// host_keep != nullptr receives the row pointers and -- when `full` -- the whole operator (inspection, knp_amg_level_host)
+static int adopt_csr(DCsr& d, CsrDev& out, CsrHost* host_keep, bool full) {
+  out.n_rows = d.n_rows;
+  out.n_cols = d.n_cols;
+  out.nnz = d.nnz;
+  std::vector<int32_t> ip((size_t)d.n_rows + 1);
+  KNP_CUDA(cudaMemcpy(ip.data(), d.indptr.p, ip.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  if (host_keep) {
+    host_keep->n_rows = d.n_rows;
+    host_keep->n_cols = d.n_cols;
+    if (full) KNP_TRY(dcsr_download(d, *host_keep));
+    else host_keep->indptr = ip;
+  }
+  std::vector<int32_t> blk;
+  out.nblk = build_rowblocks(ip.data(), d.n_rows, blk);
+  if (out.nblk > 0) KNP_TRY(out.rowblk.upload(blk));
+  else out.nblk = 0;
+  for (int k = 0; k < 4; ++k) ip.push_back(ip.back());           // padding for the 16-byte TMA slices
+  KNP_TRY(out.indptr.upload(ip));
+  swap_buf(out.indices, d.indices);
+  swap_buf(out.vals, d.vals);
+  return KNP_OK;
+}
+
+// The same for a matrix that already lives on the device: the hierarchy is built there and stays there (no host round trip
+// of the operators; only row pointers and the small levels are copied for the row blocks / for inspection).  Falls back to the
+// host setup when the device form does not take the matrix.
+static int build_amg_dev(knp_ctx* c, std::unique_ptr<DCsr>& A0, std::unique_ptr<Amg>& out, int coarse_size, bool spd,
+                         int level0 = 0) {
+  DevHierarchy H;
+  int used_device = 0;
+  SetupTimer tm;
+  KNP_TRY(amg_setup_device_core(A0, 0.08, coarse_size, 16, H, c->stream, &used_device));
+  if (!used_device) {
+    CsrHost h;
+    KNP_TRY(dcsr_download(*A0, h));
+    A0.reset();
+    return build_amg(c, h, out, coarse_size, spd, level0, false);
+  }
+  c->amg_setup_on_device = 1;
+  tm.lap("hierarchy (device setup, device resident)");
+  auto amg = std::make_unique<Amg>();
+  const int nl = (int)H.P.size();
+  // host copies for inspection: every level but a large finest one (its row pointers only; KNP_AMG_KEEP_HOST=1 keeps all)
+  static const bool keep_all = getenv("KNP_AMG_KEEP_HOST") && atoi(getenv("KNP_AMG_KEEP_HOST"));
+  amg->hostA.assign(H.A.size(), CsrHost());
+  KNP_TRY(dcsr_download(*H.A.back(), amg->hostA.back()));
+  std::vector<double> cinv;
+  {
+    const CsrHost& Ac = amg->hostA.back();
+    const int nc = Ac.n_rows;
+    cinv.assign((size_t)nc * nc, 0.0);
+    for (int i = 0; i < nc; ++i)
+      for (int j = Ac.indptr[i]; j < Ac.indptr[i + 1]; ++j) cinv[(size_t)i * nc + Ac.indices[j]] += Ac.vals[j];
+    if (!spd) {
+      std::vector<double> dense;
+      dense.swap(cinv);
+      KNP_TRY(dense_inverse(nc, dense, cinv));
+    }
+  }
+  const int n_coarse = H.A.back()->n_rows;
+  for (int l = 0; l < nl; ++l) {
+    auto* lv = new AmgLevelDev();
+    amg->levels.push_back(lv);
+    const bool full = keep_all || l > 0 || H.A[l]->n_rows <= 4000000;
+    KNP_TRY(adopt_csr(*H.A[l], lv->A, &amg->hostA[l], full));
+    KNP_TRY(adopt_csr(*H.P[l], lv->P, nullptr, false));
+    KNP_TRY(adopt_csr(*H.R[l], lv->R, nullptr, false));
+  }
+  tm.lap("row blocks, host copies of the small levels");
+  return finish_amg(c, amg, H.rhos, cinv, n_coarse, spd, level0, out);
 }
 
 // ---- fused cycle tail ------------------------------------------------------------------------------------------------
@@ -515,6 +612,116 @@ static int exchange_owner_index(knp_ctx* c, IndexFn index, std::vector<double>& 
   return KNP_OK;
 }
 
+// ---- single GPU: the ion / potential blocks of P~ and the lumped M_sigma are formed on the device ----
+// compact numbering of a part: ion part [s=0: 3 n0 | s=1: 3 n1], potential part [n0 | n1]; -1: the row / column belongs to
+// the other part
+__device__ __forceinline__ int part_map(int i, int n0, int n1, int part) {
+  if (part == 0) {
+    if (i < 3 * n0) return i;
+    if (i < 4 * n0) return -1;
+    if (i < 4 * n0 + 3 * n1) return i - n0;
+    return -1;
+  }
+  if (i < 3 * n0) return -1;
+  if (i < 4 * n0) return i - 3 * n0;
+  if (i < 4 * n0 + 3 * n1) return -1;
+  return i - 3 * n0 - 3 * n1;
+}
+__global__ void part_count_kernel(int n, int n0, int n1, int part, const int32_t* __restrict__ ip, const int32_t* __restrict__ ix,
+                                  int32_t* __restrict__ cnt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int m = part_map(i, n0, n1, part);
+  if (m < 0) return;
+  int k = 0;
+  for (int j = ip[i]; j < ip[i + 1]; ++j) k += ix[j] < n && part_map(ix[j], n0, n1, part) >= 0;
+  cnt[m] = k;
+}
+__global__ void part_ptr_kernel(int m, const int32_t* __restrict__ cnt, int32_t* __restrict__ ptr) {
+  // exclusive scan by one block (setup time, a few milliseconds): 1024 threads, each over a contiguous chunk
+  __shared__ long long tot[1024];
+  const int t = threadIdx.x;
+  const long long chunk = ((long long)m + 1023) / 1024;
+  const long long b = t * chunk, e = min((long long)m, b + chunk);
+  long long s = 0;
+  for (long long i = b; i < e; ++i) s += cnt[i];
+  tot[t] = s;
+  __syncthreads();
+  if (t == 0) {
+    long long run = 0;
+    for (int k = 0; k < 1024; ++k) {
+      const long long v = tot[k];
+      tot[k] = run;
+      run += v;
+    }
+    ptr[m] = (int32_t)run;
+  }
+  __syncthreads();
+  long long run = tot[t];
+  for (long long i = b; i < e; ++i) {
+    ptr[i] = (int32_t)run;
+    run += cnt[i];
+  }
+}
+__global__ void part_fill_kernel(int n, int n0, int n1, int part, const int32_t* __restrict__ ip, const int32_t* __restrict__ ix,
+                                 const double* __restrict__ val, const int32_t* __restrict__ optr, int32_t* __restrict__ oix,
+                                 double* __restrict__ ov) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int m = part_map(i, n0, n1, part);
+  if (m < 0) return;
+  int pos = optr[m];
+  for (int j = ip[i]; j < ip[i + 1]; ++j) {
+    if (ix[j] >= n) continue;
+    const int cc = part_map(ix[j], n0, n1, part);
+    if (cc < 0) continue;
+    oix[pos] = cc;
+    ov[pos++] = val[j];
+  }
+}
+// 1 / (M_sigma): (sum_k z_k^2 c_k / psi) at the node times the row sum of the mass matrix, in the host's operation order
+__global__ void msig_kernel(Layout L, const int32_t* __restrict__ ipP, const double* __restrict__ mval,
+                            const double* __restrict__ u, double z0, double z1, double z2, double psi, double* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n0 = L.n_own[0], n1 = L.n_own[1];
+  if (t >= n0 + n1) return;
+  const int s = t < n0 ? 0 : 1, p = s ? t - n0 : t;
+  const int row = L.row(s, 0, p);
+  double ms = 0.0;
+  for (int j = ipP[row]; j < ipP[row + 1]; ++j) ms = __dadd_rn(ms, mval[j]);
+  const double z[3] = {z0, z1, z2};
+  double sig = 0.0;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) sig = __dadd_rn(sig, __dmul_rn(__ddiv_rn(__dmul_rn(z[k], z[k]), psi), u[L.col(s, k, p)]));
+  out[t] = ms != 0.0 ? __ddiv_rn(1.0, __dmul_rn(sig, ms)) : 0.0;
+}
+static int extract_part(knp_ctx* c, int part, std::unique_ptr<DCsr>& out) {
+  const Layout& L = c->T.L;
+  const int n = L.n_rows, n0 = L.n_own[0], n1 = L.n_own[1];
+  const int m = part == 0 ? 3 * (n0 + n1) : n0 + n1;
+  cudaStream_t st = c->stream;
+  out = std::make_unique<DCsr>();
+  out->n_rows = out->n_cols = m;
+  DevBuf<int32_t> cnt;
+  KNP_TRY(cnt.alloc((size_t)std::max(m, 1)));
+  KNP_TRY(out->indptr.alloc((size_t)m + 1));
+  part_count_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, n0, n1, part, c->d_indptr_P.p, c->d_indices_P.p, cnt.p);
+  KNP_LAUNCHED();
+  part_ptr_kernel<<<1, 1024, 0, st>>>(m, cnt.p, out->indptr.p);
+  KNP_LAUNCHED();
+  int32_t nnz = 0;
+  KNP_CUDA(cudaMemcpyAsync(&nnz, out->indptr.p + m, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  KNP_CUDA(cudaStreamSynchronize(st));
+  out->nnz = nnz;
+  KNP_TRY(out->indices.alloc((size_t)std::max(nnz, 1)));
+  KNP_TRY(out->vals.alloc((size_t)std::max(nnz, 1)));
+  part_fill_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, n0, n1, part, c->d_indptr_P.p, c->d_indices_P.p, c->P_vals.p,
+                                                    out->indptr.p, out->indices.p, out->vals.p);
+  KNP_LAUNCHED();
+  KNP_CUDA(cudaStreamSynchronize(st));
+  return KNP_OK;
+}
+
 static int schur_setup(knp_ctx* c) {
   const Layout& L = c->T.L;
   const int n = L.n_rows, n0 = L.n_own[0], n1 = L.n_own[1];
@@ -539,12 +746,16 @@ static int schur_setup(knp_ctx* c) {
                             c->n_bc, c->bc_cols.p, c->bc_vals.p, 0.0, st));
   }
   KNP_CUDA(cudaStreamSynchronize(st));
-  std::vector<int32_t> idx(c->H.nnz_P);
-  std::vector<double> val(c->H.nnz_P), mval(c->H.nnz_P), u(L.n_cols);
-  KNP_CUDA(cudaMemcpy(idx.data(), c->d_indices_P.p, idx.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
-  KNP_CUDA(cudaMemcpy(val.data(), c->P_vals.p, val.size() * sizeof(double), cudaMemcpyDeviceToHost));
-  KNP_CUDA(cudaMemcpy(mval.data(), c->M_vals.p, mval.size() * sizeof(double), cudaMemcpyDeviceToHost));
-  KNP_CUDA(cudaMemcpy(u.data(), c->u.p, u.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  // one GPU: blocks, hierarchies and M_sigma are formed on the device; the operators never visit the host
+  const bool dev_path = c->nranks == 1 && amg_setup_device_default(c);
+  std::vector<int32_t> idx(dev_path ? 0 : c->H.nnz_P);
+  std::vector<double> val(idx.size()), mval(idx.size()), u(dev_path ? 0 : L.n_cols);
+  if (!dev_path) {
+    KNP_CUDA(cudaMemcpy(idx.data(), c->d_indices_P.p, idx.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    KNP_CUDA(cudaMemcpy(val.data(), c->P_vals.p, val.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    KNP_CUDA(cudaMemcpy(mval.data(), c->M_vals.p, mval.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    KNP_CUDA(cudaMemcpy(u.data(), c->u.p, u.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  }
   const std::vector<int32_t>& ip = c->H.indptr_P;
   tm.lap("P~ and M assembly, copies to the host");
   // compact numbering: c part [s=0: 3 n0 | s=1: 3 n1], phi part [n0 | n1]; ghost columns are dropped (processor-local)
@@ -565,7 +776,7 @@ static int schur_setup(knp_ctx* c) {
   App.n_rows = App.n_cols = n0 + n1;
   Acc.indptr.assign(1, 0);
   App.indptr.assign(1, 0);
-  for (int i = 0; i < n && c->nranks == 1; ++i) {     // multi-GPU runs keep the ghost columns (dist_part below)
+  for (int i = 0; i < n && c->nranks == 1 && !dev_path; ++i) {     // multi-GPU runs keep the ghost columns (dist_part below)
     const bool isc = cmap(i) >= 0;
     CsrHost& M = isc ? Acc : App;
     for (int j = ip[i]; j < ip[i + 1]; ++j) {
@@ -588,6 +799,15 @@ static int schur_setup(knp_ctx* c) {
     KNP_TRY(dist_part(c, ip, idx, val, oidx, pmap, [](int, int f) { return f == 3; }, n0 + n1, App, hp, gop, gip));
     KNP_TRY(build_dist_amg(c, std::move(Acc), std::move(hc), std::move(goc), std::move(gic), c->damg_c, 2500, true));
     KNP_TRY(build_dist_amg(c, std::move(App), std::move(hp), std::move(gop), std::move(gip), c->damg_p, 2500, true));
+  } else if (dev_path) {
+    std::unique_ptr<DCsr> dcc, dpp;
+    KNP_TRY(extract_part(c, 0, dcc));
+    KNP_TRY(extract_part(c, 1, dpp));
+    tm.lap("ion / potential blocks extracted (device)");
+    KNP_TRY(build_amg_dev(c, dcc, c->amg_c, 2500, true));
+    int on_dev = c->amg_setup_on_device;
+    KNP_TRY(build_amg_dev(c, dpp, c->amg_p, 2500, true));
+    c->amg_setup_on_device = on_dev && c->amg_setup_on_device;
   } else {
     KNP_TRY(build_amg(c, Acc, c->amg_c, 2500, true));
     KNP_TRY(build_amg(c, App, c->amg_p, 2500, true));
@@ -625,9 +845,17 @@ static int schur_setup(knp_ctx* c) {
   for (DistAmg* a : {c->damg_c.get(), c->damg_p.get()})
     if (a) KNP_TRY(prepare_tail(*a->tail, a->gb, a->gx.p));
   // lumped M_sigma = (sum_k z_k^2 c_k / psi) at the node  x  row sum of the mass matrix
-  std::vector<double> msig_inv((size_t)n0 + n1);
+  std::vector<double> msig_inv(dev_path ? 0 : (size_t)n0 + n1);
   const double* z = c->kp.z;
-  for (int s = 0; s < 2; ++s)
+  if (dev_path) {
+    KNP_TRY(c->msig_inv.alloc((size_t)n0 + n1));
+    if (n0 + n1 > 0) {
+      msig_kernel<<<(n0 + n1 + 255) / 256, 256, 0, st>>>(L, c->d_indptr_P.p, c->M_vals.p, c->u.p, z[0], z[1], z[2], c->kp.psi,
+                                                         c->msig_inv.p);
+      KNP_LAUNCHED();
+    }
+  }
+  for (int s = 0; s < 2 && !dev_path; ++s)
     for (int p = 0; p < L.n_own[s]; ++p) {
       const int row = L.row(s, 0, p);
       double ms = 0.0;
@@ -636,7 +864,7 @@ static int schur_setup(knp_ctx* c) {
       for (int k = 0; k < 3; ++k) sig += z[k] * z[k] / c->kp.psi * u[L.col(s, k, p)];
       msig_inv[(size_t)(s ? n0 : 0) + p] = ms != 0.0 ? 1.0 / (sig * ms) : 0.0;     // empty row: Dirichlet dof
     }
-  KNP_TRY(c->msig_inv.upload(msig_inv));
+  if (!dev_path) KNP_TRY(c->msig_inv.upload(msig_inv));
   // row blocks of the two mass-matrix row ranges (rows (s, 0, .) of the P pattern): TMA-staged SpMV on sub-ranges
   for (int s = 0; s < 2; ++s) {
     c->sch_nmblk[s] = 0;
