@@ -48,7 +48,7 @@ typedef struct knp_ctx knp_ctx;
  * by this rank, the rest are ghosts; cells = every cell touching an owned vertex.  Replaces the
  * XDMF read + dS entity ordering of utils/mixed_dim_problem.py:634-733 as *input* to the path. */
 typedef struct {
-  int32_t gdim;                 /* 2 (triangles) or 3 (tetrahedra); P1 elements */
+  int32_t gdim;                 /* 2 (triangles) or 3 (tetrahedra) */
   int64_t n_vertices;
   int64_t n_owned_vertices;
   const double* coords;         /* host, n_vertices x gdim, already scaled (mesh_conversion_factor) */
@@ -66,6 +66,13 @@ typedef struct {
   int32_t n_quad;               /* facet quadrature rule (degree 10 in the reference, :732-733) */
   const double* quad_bary;      /* host, n_quad x gdim barycentric points on the facet */
   const double* quad_w;         /* host, n_quad weights summing to 1 */
+  int32_t degree;               /* element order, fem_order of utils/mixed_dim_problem.py:207-208: 0 or 1 = P1 (everything above
+                                   as stated); 2 = P2 on ONE GPU: "vertices" are then the nodes of the P2 space -- the mesh
+                                   vertices first, then one node per edge with the coordinates of its midpoint --, cell_verts
+                                   lists per cell its gdim+1 vertices followed by its edge nodes in the order (0,1),(0,2),
+                                   [(0,3),](1,2),[(1,3),(2,3)] of the local vertices (6 / 10 per cell), mfacet_verts per facet
+                                   its gdim vertices followed by its edge nodes in the same order (3 / 6 per facet); the
+                                   quadrature rule stays barycentric on the facet's gdim vertices */
 } knp_mesh_desc;
 
 typedef struct {
@@ -233,6 +240,13 @@ int knp_amg_level_host(const knp_ctx* ctx, int32_t level, int32_t* indptr, int32
    counts of the two subdomains), then with arrays of n_rows + 1, nnz, n_loc[0], n_loc[1] entries. */
 int knp_pattern_host(const knp_mesh_desc* mesh, int64_t* n_rows, int64_t* nnz, int32_t* n_own_loc4, int32_t* indptr,
                      int32_t* indices, int32_t* dof_vert_i, int32_t* dof_vert_e);
+/* Host-only (no GPU), TEST INFRASTRUCTURE: one assembly of the P2 element path (mesh->degree == 2) on the CPU with the very
+   functions its kernels run per thread (csrc/p2.cuh), so that the test tier without a GPU checks the P2 tables and element
+   math against the oracle.  mode 0: A values (nnz) and b (n_rows) at time t from (u, gates) as knp_assemble lays them out;
+   mode 1: the preconditioner matrix P (nnz_P values; b, gates unused).  With scale_stimulus the stimulus area is taken
+   from p->stim_area.  No product call reaches this function: knp_create / knp_assemble need a GPU. */
+int knp_p2_emulate_host(const knp_mesh_desc* mesh, const knp_params* p, int32_t n_tags, const knp_tag_models* tags, double t,
+                        int32_t mode, const double* u, const double* gates, double* vals, double* b);
 /* Host-only (no GPU): the lane-group tables the edge-lane row kernel reads (csrc/topology.cpp): per (owned dof w, slot e)
    at (w << lgG) + e the neighbour node id (adjG, -1 beyond the degree) and the cells around the edge (w, neighbour) written
    as the adjacency slots of their other vertices (hitG: 1 word per entry in 2D, 4 words in 3D, unused bytes 0xFF); per dof

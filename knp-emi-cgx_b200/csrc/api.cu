@@ -28,6 +28,127 @@ static cudaStream_t pick(knp_ctx* c, void* stream) { return stream ? (cudaStream
     }                                             \
   } while (0)
 
+// knp_create for P2 elements (knp_mesh_desc::degree == 2, one GPU): the tables of topology_p2.cpp instead of the P1 ones;
+// everything behind the assembly (CSR products, Krylov loop, preconditioners, boundary conditions) is element-agnostic.
+static int create_p2(std::unique_ptr<knp_ctx>& c, const knp_mesh_desc* mesh, knp_ctx** out) {
+  KNP_TRY(build_topology_p2(mesh, c->H));
+  HostTopo& H = c->H;
+  P2Host& Q = H.p2;
+  KNP_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  for (auto& ev : c->ev) KNP_CUDA(cudaEventCreate(&ev));
+  auto& D = c->p2d;
+  KNP_TRY(c->d_node_x.upload(H.node_x));
+  KNP_TRY(D.adj_ptr.upload(Q.adj_ptr));
+  KNP_TRY(D.gam_ptr.upload(Q.gam_ptr));
+  KNP_TRY(D.inc_ptr.upload(Q.inc_ptr));
+  KNP_TRY(D.inc_cell.upload(Q.inc_cell));
+  KNP_TRY(D.inc_loc.upload(Q.inc_loc));
+  KNP_TRY(D.inc_slots.upload(Q.inc_slots));
+  KNP_TRY(D.minc_ptr.upload(Q.minc_ptr));
+  KNP_TRY(D.minc_facet.upload(Q.minc_facet));
+  KNP_TRY(D.minc_loc.upload(Q.minc_loc));
+  KNP_TRY(D.minc_own.upload(Q.minc_own));
+  KNP_TRY(D.minc_gam.upload(Q.minc_gam));
+  KNP_TRY(D.cq_w.upload(Q.cq_w));
+  KNP_TRY(D.cq_N.upload(Q.cq_N));
+  KNP_TRY(D.cq_dN.upload(Q.cq_dN));
+  KNP_TRY(D.fq_N.upload(Q.fq_N));
+  KNP_TRY(D.fq_M.upload(Q.fq_M));
+  KNP_TRY(c->d_qb.upload(Q.fq_b));
+  KNP_TRY(c->d_qw.upload(Q.fq_w));
+  KNP_TRY(c->d_mv_node0.upload(H.mv_node[0]));
+  KNP_TRY(c->d_mv_node1.upload(H.mv_node[1]));
+  KNP_TRY(c->d_mf_mv.upload(H.mf_mv));
+  KNP_TRY(c->d_mf_tagidx.upload(H.mf_tagidx));
+  KNP_TRY(c->d_mf_area.upload(H.mf_area));
+  KNP_TRY(c->d_mf_owned.upload(H.mf_owned));
+  {
+    std::vector<int32_t> ip(H.indptr), ipP(H.indptr_P);
+    for (int k = 0; k < 4; ++k) {   // padding for the 16-byte TMA slices of the streaming SpMV
+      ip.push_back(H.indptr.back());
+      ipP.push_back(H.indptr_P.back());
+    }
+    KNP_TRY(c->d_indptr.upload(ip));
+    KNP_TRY(c->d_indptr_P.upload(ipP));
+  }
+  KNP_TRY(c->d_indices.upload(Q.indices));
+  KNP_TRY(c->d_indices_P.upload(Q.indices_P));
+  {
+    std::vector<int32_t> blk;
+    c->nblk_A = build_rowblocks(H.indptr.data(), H.L.n_rows, blk);
+    if (c->nblk_A > 0) KNP_TRY(c->d_rowblk_A.upload(blk));
+    else c->nblk_A = 0;
+  }
+  for (int s = 0; s < 2; ++s) {
+    KNP_TRY(c->d_cell_nodes[s].upload(H.cell_nodes[s]));
+    KNP_TRY(c->d_cell_tag[s].upload(H.cell_tag[s]));
+    KNP_TRY(c->d_cell_owned[s].upload(H.cell_owned[s]));
+  }
+  P2View& V = c->p2v;
+  V = p2_host_view(H);               // sizes and layout; every pointer is replaced by its device copy
+  V.node_x = c->d_node_x.p;
+  V.cell_nodes[0] = c->d_cell_nodes[0].p;
+  V.cell_nodes[1] = c->d_cell_nodes[1].p;
+  V.adj_ptr = D.adj_ptr.p;
+  V.gam_ptr = D.gam_ptr.p;
+  V.inc_ptr = D.inc_ptr.p;
+  V.inc_cell = D.inc_cell.p;
+  V.inc_loc = D.inc_loc.p;
+  V.inc_slots = D.inc_slots.p;
+  V.minc_ptr = D.minc_ptr.p;
+  V.minc_facet = D.minc_facet.p;
+  V.minc_loc = D.minc_loc.p;
+  V.minc_own = D.minc_own.p;
+  V.minc_gam = D.minc_gam.p;
+  V.indptr = c->d_indptr.p;
+  V.indptr_P = c->d_indptr_P.p;
+  V.cq_w = D.cq_w.p;
+  V.cq_N = D.cq_N.p;
+  V.cq_dN = D.cq_dN.p;
+  V.fq_b = c->d_qb.p;
+  V.fq_w = c->d_qw.p;
+  V.fq_N = D.fq_N.p;
+  V.fq_M = D.fq_M.p;
+  V.mv_node0 = c->d_mv_node0.p;
+  V.mv_node1 = c->d_mv_node1.p;
+  V.mf_mv = c->d_mf_mv.p;
+  V.mf_tagidx = c->d_mf_tagidx.p;
+  V.mf_area = c->d_mf_area.p;
+  DevTopo& T = c->T;                 // the element-agnostic part of the P1 view (gate kernel, layout, patterns)
+  T.gdim = H.gdim;
+  T.L = H.L;
+  T.n_work = H.n_work;
+  T.n_mv = H.n_mv;
+  T.n_mf = H.n_mf;
+  T.nq = mesh->n_quad;
+  T.node_x = c->d_node_x.p;
+  T.mv_node0 = c->d_mv_node0.p;
+  T.mv_node1 = c->d_mv_node1.p;
+  T.mf_mv = c->d_mf_mv.p;
+  T.mf_tagidx = c->d_mf_tagidx.p;
+  T.mf_area = c->d_mf_area.p;
+  T.indptr = c->d_indptr.p;
+  T.indptr_P = c->d_indptr_P.p;
+  T.qb = c->d_qb.p;
+  T.qw = c->d_qw.p;
+  T.max_inc = H.max_inc;
+  T.p2 = &c->p2v;
+  KNP_TRY(c->u.alloc(T.L.n_cols));
+  KNP_TRY(c->gates.alloc((size_t)3 * T.n_mv));
+  KNP_TRY(c->A_vals.alloc(H.nnz));
+  KNP_TRY(c->P_vals.alloc(H.nnz_P));
+  KNP_TRY(c->b.alloc(T.L.n_rows));
+  KNP_TRY(c->fe.alloc((size_t)p2_facet_ncomp(H.gdim) * (T.n_mf > 0 ? T.n_mf : 1)));
+  KNP_CUDA(cudaMemsetAsync(c->u.p, 0, (size_t)T.L.n_cols * sizeof(double), c->stream));
+  KNP_TRY(c->fpartial.alloc(1024));
+  KNP_TRY(c->fout.alloc(8));
+  KNP_TRY(c->ftags.alloc(4096));
+  c->n_phi_global = T.L.n_own[0] + T.L.n_own[1];
+  KNP_CUDA(cudaStreamSynchronize(c->stream));
+  *out = c.release();
+  return KNP_OK;
+}
+
 extern "C" {
 
 const char* knp_last_error(void) { return knp::last_error(); }
@@ -50,6 +171,8 @@ int knp_create(knp_ctx** out, const knp_mesh_desc* mesh, int device) {
   KNP_CUDA(cudaSetDevice(device));
   std::unique_ptr<knp_ctx> c(new knp_ctx());
   c->device = device;
+  if (mesh && mesh->degree == 2) return create_p2(c, mesh, out);
+  KNP_CHECK(!mesh || mesh->degree == 0 || mesh->degree == 1, "element degree %d is not supported (1 or 2)", mesh->degree);
   KNP_TRY(build_topology(mesh, c->H));
   HostTopo& H = c->H;
   KNP_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -250,6 +373,7 @@ int knp_stimulus_area_local(knp_ctx* c, double* out) {
   // setup-time integral of the stimulus mask over owned stimulated facets (host, fixed order)
   const HostTopo& H = c->H;
   const int d = H.gdim;
+  const int fstride = H.degree == 2 ? H.p2.nt : d;          // nodes per membrane facet (its d vertices come first)
   std::vector<double> qb(c->d_qb.n), qw(c->d_qw.n);
   KNP_CUDA(cudaSetDevice(c->device));
   KNP_CUDA(cudaMemcpy(qb.data(), c->d_qb.p, qb.size() * sizeof(double), cudaMemcpyDeviceToHost));
@@ -263,7 +387,7 @@ int knp_stimulus_area_local(knp_ctx* c, double* out) {
       for (int i = 0; i < 3 && p.stim_dir[i] >= 0; ++i) {
         double xq = 0.0;
         for (int a = 0; a < d; ++a) {
-          const int node = H.mv_node[0][H.mf_mv[(size_t)f * d + a]];
+          const int node = H.mv_node[0][H.mf_mv[(size_t)f * fstride + a]];
           xq += qb[q * d + a] * H.node_x[(size_t)node * d + p.stim_dir[i]];
         }
         mask *= (xq > p.stim_lo[i] && xq < p.stim_hi[i]) ? 1.0 : 0.0;
@@ -595,9 +719,13 @@ static int cell_functional(knp_ctx* c, int32_t s, int32_t field, int32_t power, 
   cudaStream_t st = c->stream;
   KNP_CUDA(cudaMemcpyAsync(c->ftags.p, tags, n_tags * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   const int nb = 592;
-  KNP_TRY(launch_l2_cells(c->T.gdim, c->T.L, s, field, power, nc, c->d_cell_nodes[s].p, c->d_cell_tag[s].p,
-                          c->d_cell_owned[s].p, c->d_node_x.p, s ? c->T.L.n_loc[0] : 0, c->ftags.p, n_tags, c->u.p,
-                          c->fpartial.p, nb, st));
+  if (c->H.degree == 2)
+    KNP_TRY(launch_l2_cells_p2(c->p2v, s, field, power, nc, c->d_cell_tag[s].p, c->d_cell_owned[s].p, c->ftags.p, n_tags,
+                               c->u.p, c->fpartial.p, nb, st));
+  else
+    KNP_TRY(launch_l2_cells(c->T.gdim, c->T.L, s, field, power, nc, c->d_cell_nodes[s].p, c->d_cell_tag[s].p,
+                            c->d_cell_owned[s].p, c->d_node_x.p, s ? c->T.L.n_loc[0] : 0, c->ftags.p, n_tags, c->u.p,
+                            c->fpartial.p, nb, st));
   KNP_TRY(launch_reduce_partials(c->fpartial.p, nb, c->fout.p, st));
   KNP_CUDA(cudaMemcpyAsync(out, c->fout.p, sizeof(double), cudaMemcpyDeviceToHost, st));
   KNP_CUDA(cudaStreamSynchronize(st));
@@ -624,7 +752,10 @@ int knp_stimulus_current(knp_ctx* c, double t, double* out) {
   if (p.scale_stimulus) stim_fac *= 1.0 / c->params.stim_area;
   cudaStream_t st = c->stream;
   const int nb = 592;
-  KNP_TRY(launch_stim_current(c->T, c->kp, c->d_tag_stim.p, c->d_mf_owned.p, c->u.p, stim_fac, c->fpartial.p, nb, st));
+  if (c->H.degree == 2)
+    KNP_TRY(launch_stim_current_p2(c->p2v, c->kp, c->d_tag_stim.p, c->d_mf_owned.p, c->u.p, stim_fac, c->fpartial.p, nb, st));
+  else
+    KNP_TRY(launch_stim_current(c->T, c->kp, c->d_tag_stim.p, c->d_mf_owned.p, c->u.p, stim_fac, c->fpartial.p, nb, st));
   KNP_TRY(launch_reduce_partials(c->fpartial.p, nb, c->fout.p, st));
   KNP_CUDA(cudaMemcpyAsync(out, c->fout.p, sizeof(double), cudaMemcpyDeviceToHost, st));
   KNP_CUDA(cudaStreamSynchronize(st));
@@ -723,7 +854,8 @@ int knp_amg_level_host(const knp_ctx* c, int32_t level, int32_t* indptr, int32_t
 int knp_pattern_host(const knp_mesh_desc* mesh, int64_t* n_rows, int64_t* nnz, int32_t* n_own_loc4, int32_t* indptr,
                      int32_t* indices, int32_t* dof_vert_i, int32_t* dof_vert_e) {
   HostTopo H;
-  KNP_TRY(build_topology(mesh, H));
+  const bool p2 = mesh && mesh->degree == 2;
+  KNP_TRY(p2 ? build_topology_p2(mesh, H) : build_topology(mesh, H));
   const Layout& L = H.L;
   if (n_rows) *n_rows = L.n_rows;
   if (nnz) *nnz = H.nnz;
@@ -736,7 +868,9 @@ int knp_pattern_host(const knp_mesh_desc* mesh, int64_t* n_rows, int64_t* nnz, i
   if (indptr) memcpy(indptr, H.indptr.data(), H.indptr.size() * sizeof(int32_t));
   if (dof_vert_i) memcpy(dof_vert_i, H.node_vert[0].data(), H.node_vert[0].size() * sizeof(int32_t));
   if (dof_vert_e) memcpy(dof_vert_e, H.node_vert[1].data(), H.node_vert[1].size() * sizeof(int32_t));
-  if (indices) {
+  if (indices && p2) {
+    memcpy(indices, H.p2.indices.data(), H.p2.indices.size() * sizeof(int32_t));
+  } else if (indices) {
     for (int w = 0; w < H.n_work; ++w) {
       const int s = w >= L.n_own[0] ? 1 : 0, p = w - (s ? L.n_own[0] : 0), o = 1 - s;
       const int a0 = H.adj_ptr[w], deg = H.adj_ptr[w + 1] - a0;
@@ -757,11 +891,57 @@ int knp_pattern_host(const knp_mesh_desc* mesh, int64_t* n_rows, int64_t* nnz, i
   return KNP_OK;
 }
 
+// One assembly of the P2 element path ON THE CPU with the bodies the kernels run (p2.cuh): TEST INFRASTRUCTURE for the tier
+// without a GPU (tables, slot maps and element math against the oracle); no product call reaches it.
+int knp_p2_emulate_host(const knp_mesh_desc* mesh, const knp_params* p, int32_t n_tags, const knp_tag_models* tags, double t,
+                        int32_t mode, const double* u, const double* gates, double* vals, double* b) {
+  KNP_CHECK(mesh && mesh->degree == 2 && p && u && vals && (mode == 1 || (b && gates)), "knp_p2_emulate_host: bad arguments");
+  HostTopo H;
+  KNP_TRY(build_topology_p2(mesh, H));
+  KParams K{};
+  K.dt = p->dt;
+  K.F = p->F;
+  K.C_M = p->C_M;
+  K.psi = p->R * p->T / p->F;
+  K.phi_rest = p->phi_rest;
+  for (int k = 0; k < 3; ++k) {
+    K.z[k] = p->z[k];
+    K.D[k] = p->D[k];
+    K.g_leak[k] = p->g_leak[k];
+    K.g_leak_g[k] = p->g_leak_g[k];
+    K.stim_dir[k] = p->stim_dir[k];
+    K.stim_lo[k] = p->stim_lo[k];
+    K.stim_hi[k] = p->stim_hi[k];
+  }
+  K.g_Na_bar = p->g_Na_bar;
+  K.g_K_bar = p->g_K_bar;
+  K.K_e_init = p->K_e_init;
+  K.K_i_g_init = p->K_i_g_init;
+  K.ode_substeps = p->ode_substeps;
+  K.rush_larsen = p->rush_larsen;
+  std::vector<uint32_t> tm(H.mtags.size() + 1, 0u);
+  std::vector<int32_t> ts(H.mtags.size() + 1, 0);
+  for (size_t i = 0; i < H.mtags.size(); ++i)
+    for (int j = 0; j < n_tags; ++j)
+      if (tags[j].tag == H.mtags[i]) {
+        tm[i] = tags[j].models;
+        ts[i] = tags[j].stimulated ? 1 : 0;
+      }
+  const double t_mod = std::fmod(t + 1e-12, p->T_stim);
+  double stim_fac = p->g_syn_bar * std::exp(-t_mod / p->a_syn);
+  if (p->scale_stimulus) {
+    KNP_CHECK(p->stim_area > 0.0, "knp_p2_emulate_host: pass the stimulus area in knp_params::stim_area");
+    stim_fac *= 1.0 / p->stim_area;
+  }
+  return p2_emulate_host(H, K, tm.data(), ts.data(), stim_fac, mode, u, gates, vals, b);
+}
+
 // lane-group tables of the edge-lane row kernel, host only (CPU test tier: the tables and the closed-form cell entries are
 // checked against the oracle's matrix without a GPU)
 int knp_edge_tables_host(const knp_mesh_desc* mesh, int32_t* lgG, int64_t* n_work, int32_t* edge_ok, int32_t* adjG,
                          uint32_t* hitG, int32_t* metaG, double* node_x) {
   HostTopo H;
+  KNP_CHECK(mesh && mesh->degree != 2, "the lane-group tables belong to the P1 row kernel");
   KNP_TRY(build_topology(mesh, H));
   if (lgG) *lgG = H.lgG;
   if (n_work) *n_work = H.n_work;

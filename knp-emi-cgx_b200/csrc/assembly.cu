@@ -20,6 +20,7 @@
 #include <string>
 #include "common.cuh"
 #include "kernels.cuh"
+#include "p2.cuh"
 
 namespace knp {
 
@@ -795,6 +796,7 @@ int facet_ncomp(int gdim) { return 6 * (gdim * (gdim + 1) / 2) + 7 * gdim; }
 
 int launch_facets(const DevTopo& T, const KParams& P, const uint32_t* tag_models, const int32_t* tag_stim,
                   const double* u, const double* gates, double stim_fac, double* fe, cudaStream_t st) {
+  if (T.p2) return launch_facets_p2(*T.p2, P, tag_models, tag_stim, u, gates, stim_fac, fe, st);
   if (T.n_mf == 0) return KNP_OK;
   const int grid = (T.n_mf + 127) / 128;
   if (T.gdim == 2)
@@ -1285,6 +1287,7 @@ static int launch_rows_edge(const DevTopo& T, const KParams& P, const double* u,
 
 int launch_rows(const DevTopo& T, const KParams& P, int mode, const double* u, const double* fe, double* vals,
                 double* b, int max_deg, int max_gdeg, cudaStream_t st) {
+  if (T.p2) return launch_rows_p2(*T.p2, P, mode, u, fe, vals, b, st);
   if (T.n_work == 0) return KNP_OK;
   if (T.adjG) {      // edge-lane kernel (tables exist: every edge ring fits, lane group <= one warp)
     if (T.gdim == 2) return mode == 0 ? launch_rows_edge<2, 0>(T, P, u, fe, vals, b, max_deg, max_gdeg, st)

@@ -87,9 +87,29 @@ struct Layout {
   }
 };
 
+// Host-side tables of the P2 element path (topology_p2.cpp; p2.cuh describes their use)
+struct P2Host {
+  int nloc = 0, nt = 0, nqc = 0;
+  std::vector<int32_t> adj_ptr, adj_idx;      // per owned node: sorted subdomain-local node ids it shares a cell with (incl. itself)
+  std::vector<int32_t> gam_ptr, gam_idx;      // per owned node: local node ids ACROSS the membrane it shares a facet with (sorted)
+  std::vector<int32_t> inc_ptr, inc_cell;     // per owned node: incident cells, ascending (subdomain-local cell ids)
+  std::vector<uint8_t> inc_loc;               // local index of the node in that cell
+  std::vector<uint16_t> inc_slots;            // nloc per incidence: adjacency slot of every node of the cell
+  std::vector<int32_t> minc_ptr, minc_facet;  // per owned node: incident membrane facets, ascending
+  std::vector<uint8_t> minc_loc;              // local index of the node in that facet
+  std::vector<uint16_t> minc_own, minc_gam;   // nt per incidence: adjacency slot (own side) / gamma slot (other side) of the facet's nodes
+  std::vector<int32_t> indices, indices_P;    // CSR column indices of A and P
+  std::vector<double> cq_w, cq_N, cq_dN;      // cell rule: weights, basis values [q][nloc], d/d lambda_m [q][nloc][gdim + 1]
+  std::vector<double> fq_b, fq_w;             // the facet rule of the mesh descriptor: barycentrics [q][gdim], weights
+  std::vector<double> fq_N, fq_M;             // trace basis at the facet rule's points [q][nt]; reference facet mass [nt][nt]
+};
+struct P2View;
+
 // Host-built topology (topology.cpp)
 struct HostTopo {
   int gdim = 0;
+  int degree = 1;                         // 2: P2 elements -- "vertices" are nodes (vertices + edge nodes), tables in p2
+  P2Host p2;
   Layout L{};
   int n_work = 0;                         // owned nodes (intra then extra)
   std::vector<double> node_x;             // [n_loc0+n_loc1][gdim], intra local nodes first
@@ -149,6 +169,7 @@ struct DevTopo {
   const int32_t* adjG;       // neighbour node or -1
   const uint32_t* hitG;      // cells on the edge as slots of their other vertices (1 word in 2D, 4 words in 3D)
   const int2* metaG;         // {deg | self << 8 | gamma degree << 16, membrane vertex or -1}
+  const P2View* p2;          // HOST pointer, non-null on a P2 context: the launchers hand the work to assembly_p2.cu
 };
 
 struct Params {

@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "kernels.cuh"
 #include "amg_host.h"
+#include "p2.cuh"
 
 struct ncclComm;
 
@@ -75,6 +76,14 @@ struct knp_ctx {
   knp::DevBuf<int32_t> d_cell_nodes[2], d_cell_tag[2], d_cell_owned[2];
   knp::DevBuf<uint32_t> d_tag_models;
   knp::DevBuf<int32_t> d_tag_stim, d_mf_owned;
+  // P2 element path (HostTopo::degree == 2): device copies of HostTopo::p2 and the view its kernels read (T.p2 points at it)
+  struct P2Dev {
+    knp::DevBuf<int32_t> adj_ptr, gam_ptr, inc_ptr, inc_cell, minc_ptr, minc_facet;
+    knp::DevBuf<uint8_t> inc_loc, minc_loc;
+    knp::DevBuf<uint16_t> inc_slots, minc_own, minc_gam;
+    knp::DevBuf<double> cq_w, cq_N, cq_dN, fq_N, fq_M;
+  } p2d;
+  knp::P2View p2v{};
   // parameters
   knp::Params params{};
   knp::KParams kp{};

@@ -24,7 +24,7 @@ class MeshDesc(C.Structure):
                 ("n_intra_tags", C.c_int32), ("intra_tags", c_i32p), ("extra_tag", C.c_int32),
                 ("n_mfacets", C.c_int64), ("mfacet_verts", c_i32p), ("mfacet_tags", c_i32p),
                 ("cell_owned", c_u8p), ("mfacet_owned", c_u8p),
-                ("n_quad", C.c_int32), ("quad_bary", c_f64p), ("quad_w", c_f64p)]
+                ("n_quad", C.c_int32), ("quad_bary", c_f64p), ("quad_w", c_f64p), ("degree", C.c_int32)]
 
 
 class Sizes(C.Structure):
@@ -133,6 +133,8 @@ def load():
     lib.knp_rowblocks_host.argtypes = [C.c_int32, vp, C.c_int32, vp, vp]
     lib.knp_pattern_host.argtypes = [vp, c_i64p, c_i64p, vp, vp, vp, vp, vp]
     lib.knp_edge_tables_host.argtypes = [vp, c_i32p, c_i64p, c_i32p, vp, vp, vp, vp]
+    lib.knp_p2_emulate_host.argtypes = [vp, C.POINTER(Params), C.c_int32, C.POINTER(TagModels), C.c_double, C.c_int32,
+                                        vp, vp, vp, vp]
     lib.knp_amg_setup_host.argtypes = [C.c_int32, vp, vp, vp, C.c_double, C.c_int32, vp]
     lib.knp_amg_setup_device.argtypes = [C.c_int32, vp, vp, vp, C.c_double, C.c_int32, C.c_int32, vp]
     lib.knp_amg_setup_was_on_device.argtypes = [vp]
@@ -164,14 +166,18 @@ def _ptr(a):
 
 
 def mesh_desc(gdim, coords, cells, cell_tags, intra_tags, extra_tag, mf_verts, mf_tags, quad_bary, quad_w,
-              n_owned_vertices=None, cell_owned=None, mfacet_owned=None):
-    """knp_mesh_desc for numpy arrays; returns (descriptor, dict of the arrays that must stay alive)."""
+              n_owned_vertices=None, cell_owned=None, mfacet_owned=None, degree=1):
+    """knp_mesh_desc for numpy arrays; returns (descriptor, dict of the arrays that must stay alive).  degree = 2: the
+    arrays describe the P2 node mesh (mesh.py::p2_node_mesh): nodes for vertices, 6 / 10 nodes per cell, 3 / 6 per facet."""
+    nt = gdim if degree != 2 else gdim * (gdim + 1) // 2
+    if degree == 2 and np.asarray(cells).shape[1] != (gdim + 1) * (gdim + 2) // 2:
+        raise KnpError("degree = 2 expects the P2 node mesh (mesh.p2_node_mesh)")
     k = dict(
         coords=np.ascontiguousarray(coords, np.float64),
         cells=np.ascontiguousarray(cells, np.int32),
         cell_tags=np.ascontiguousarray(cell_tags, np.int32),
         intra=np.ascontiguousarray(intra_tags, np.int32),
-        mfv=np.ascontiguousarray(mf_verts, np.int32).reshape(-1, gdim),
+        mfv=np.ascontiguousarray(mf_verts, np.int32).reshape(-1, nt),
         mft=np.ascontiguousarray(mf_tags, np.int32),
         qb=np.ascontiguousarray(quad_bary, np.float64),
         qw=np.ascontiguousarray(quad_w, np.float64),
@@ -197,6 +203,7 @@ def mesh_desc(gdim, coords, cells, cell_tags, intra_tags, extra_tag, mf_verts, m
     d.n_quad = k["qw"].size
     d.quad_bary = k["qb"].ctypes.data_as(c_f64p)
     d.quad_w = k["qw"].ctypes.data_as(c_f64p)
+    d.degree = int(degree)
     return d, k
 
 
@@ -232,15 +239,39 @@ def edge_tables_host(gdim, coords, cells, cell_tags, intra_tags, extra_tag, mf_v
     return dict(lgG=lg.value, adjG=adjG, hitG=hitG, meta=meta, node_x=x, n_own_loc=tuple(own))
 
 
+def p2_emulate_host(params: Params, tag_models, t, mode, u, gates, gdim, coords, cells, cell_tags, intra_tags, extra_tag,
+                    mf_verts, mf_tags, quad_bary, quad_w, **kw):
+    """TEST INFRASTRUCTURE (no GPU): one P2 assembly on the CPU with the functions the P2 kernels run per thread
+    (knp_p2_emulate_host).  Returns (indptr, indices, values, b) for mode 0 and the values of P for mode 1."""
+    lib = load()
+    d, keep = mesh_desc(gdim, coords, cells, cell_tags, intra_tags, extra_tag, mf_verts, mf_tags, quad_bary, quad_w, degree=2, **kw)
+    n, nnz = C.c_int64(), C.c_int64()
+    check(lib.knp_pattern_host(C.byref(d), C.byref(n), C.byref(nnz), None, None, None, None, None))
+    arr = (TagModels * max(1, len(tag_models)))(*tag_models)
+    u = np.ascontiguousarray(u, np.float64)
+    gates = None if gates is None else np.ascontiguousarray(gates, np.float64)
+    if mode == 0:
+        indptr, indices = np.empty(n.value + 1, np.int32), np.empty(nnz.value, np.int32)
+        check(lib.knp_pattern_host(C.byref(d), None, None, None, _ptr(indptr), _ptr(indices), None, None))
+        vals, b = np.full(nnz.value, np.nan), np.full(n.value, np.nan)
+        check(lib.knp_p2_emulate_host(C.byref(d), C.byref(params), len(tag_models), arr, float(t), 0, _ptr(u), _ptr(gates),
+                                      _ptr(vals), _ptr(b)))
+        return indptr, indices, vals, b
+    vals = np.full(nnz.value, np.nan)           # nnz_P <= nnz
+    check(lib.knp_p2_emulate_host(C.byref(d), C.byref(params), len(tag_models), arr, float(t), 1, _ptr(u), None, _ptr(vals), None))
+    return vals
+
+
 class Context:
     """Thin object wrapper around a knp_ctx*; numpy in, numpy out; device pointers as ints."""
 
     def __init__(self, gdim, coords, cells, cell_tags, intra_tags, extra_tag, mf_verts, mf_tags, quad_bary, quad_w,
-                 n_owned_vertices=None, cell_owned=None, mfacet_owned=None, device=0):
+                 n_owned_vertices=None, cell_owned=None, mfacet_owned=None, device=0, degree=1):
         lib = load()
         self._lib = lib
         d, k = mesh_desc(gdim, coords, cells, cell_tags, intra_tags, extra_tag, mf_verts, mf_tags, quad_bary, quad_w,
-                         n_owned_vertices, cell_owned, mfacet_owned)
+                         n_owned_vertices, cell_owned, mfacet_owned, degree)
+        self.degree = degree
         h = C.c_void_p()
         check(lib.knp_create(C.byref(h), C.byref(d), device))
         self.h = h

@@ -28,6 +28,50 @@ class Mesh:
     mf_owned: np.ndarray = None
     vert_global: np.ndarray = None
     bc_verts: np.ndarray = None     # ingested meshes: local vertices on facets tagged with the config's boundary_tags
+    # P2 node mesh (p2_node_mesh): degree 2, x / cells / mf_verts list NODES (vertices, then edge midpoints)
+    degree: int = 1
+    n_vertices: int = None          # number of mesh vertices = first node id of an edge
+    edges: np.ndarray = None        # (Ne, 2) vertex pairs (lower, higher) of the edge nodes, sorted lexicographically
+
+
+# ------------------------------------------------------------------------------------------ P2 node mesh
+def _local_edges(nv):
+    return [(i, j) for i in range(nv) for j in range(i + 1, nv)]
+
+
+def p2_node_mesh(m: "Mesh") -> "Mesh":
+    """The nodes of the ("Lagrange", 2) space (fem_order = 2, utils/mixed_dim_problem.py:207-208, KNPEMIx_problem.py:38-42) as
+    a mesh the rest of the host code can treat like the P1 one (dof = node): the mesh vertices keep their ids, every edge adds
+    one node at its midpoint (edges sorted by (lower vertex, higher vertex)); a cell lists its gdim+1 vertices and then its
+    edge nodes in the order (0,1),(0,2),[(0,3),](1,2),[(1,3),(2,3)] of its local vertices, a membrane facet its gdim vertices
+    and then its edge nodes in the same order (knp_mesh_desc::degree = 2 expects exactly this).  Single GPU only."""
+    import dataclasses
+    if m.degree == 2:
+        return m
+    if m.n_owned is not None and m.n_owned != m.x.shape[0]:
+        raise NotImplementedError("fem_order = 2 runs on one GPU (no partitioned P2 meshes)")
+    d, nv = m.gdim, m.x.shape[0]
+    cells = np.asarray(m.cells, np.int64)
+    nc = cells.shape[0]
+    pairs = _local_edges(d + 1)
+    keys = np.concatenate([np.minimum(cells[:, i], cells[:, j]) * nv + np.maximum(cells[:, i], cells[:, j]) for i, j in pairs])
+    uk, inv = np.unique(keys, return_inverse=True)
+    edges = np.stack([uk // nv, uk % nv], 1)
+    cell_nodes = np.concatenate([cells] + [nv + inv[k * nc:(k + 1) * nc, None] for k in range(len(pairs))], axis=1)
+    fv = np.asarray(m.mf_verts, np.int64).reshape(-1, d)
+    fcols = [fv]
+    for i, j in _local_edges(d):
+        k = np.minimum(fv[:, i], fv[:, j]) * nv + np.maximum(fv[:, i], fv[:, j])
+        pos = np.searchsorted(uk, k)
+        if pos.size and not np.array_equal(uk[np.minimum(pos, uk.size - 1)], k):
+            raise RuntimeError("a membrane facet has an edge that is not an edge of the mesh")
+        fcols.append(nv + pos[:, None])
+    x = np.concatenate([m.x, 0.5 * (m.x[edges[:, 0]] + m.x[edges[:, 1]])], axis=0)
+    bc = None
+    if m.bc_verts is not None:          # boundary nodes: the tagged vertices and the edges between two of them that lie on a
+        raise NotImplementedError("dirichlet_bcs on ingested meshes with fem_order = 2")
+    return dataclasses.replace(m, x=x, cells=cell_nodes.astype(np.int32), mf_verts=np.concatenate(fcols, axis=1).astype(np.int32),
+                               degree=2, n_vertices=nv, edges=edges.astype(np.int32), bc_verts=bc, grid=None)
 
 
 # ------------------------------------------------------------------------------------------ quadrature

@@ -229,7 +229,7 @@ class SchurPC:
         self.msig = []
         for s in range(2):
             sigma = sum(p.z[k] ** 2 / p.psi * o.c[s][k][o.S[s]] for k in range(3))
-            ms = np.asarray(self.M[s].sum(axis=1)).ravel()
+            ms = o.lumped_mass(self.M[s])
             self.msig.append(np.where(ms != 0.0, sigma * ms, np.inf))
         Acc = Pt[self.ic][:, self.ic].tocsr()
         App = Pt[self.ip][:, self.ip].tocsr()

@@ -120,6 +120,7 @@ class KNPEMIOracle:
         else:
             self.farea = 0.5 * np.linalg.norm(np.cross(xf[:, 1] - xf[:, 0], xf[:, 2] - xf[:, 0]), axis=1)
         self.qb, self.qw = facet_rule(d)
+        self.qN = self._trace_basis(self.qb)                   # trace basis at the facet quadrature points (P1: the barycentrics)
         self.mverts = np.unique(fv.ravel())
         # fields on the whole mesh, like the reference's wh / phi_m_prev / n,m,h
         self.c = [np.zeros((3, nv)), np.zeros((3, nv))]
@@ -184,9 +185,23 @@ class KNPEMIOracle:
         A.data[isbc[rows] & (rows == A.indices)] = diag
         return A, b
 
+    def _trace_basis(self, qb):
+        """Basis functions of the facet's dofs at barycentric points qb (nq, d): P1 -> the barycentric coordinates."""
+        return qb
+
+    def lumped_mass(self, M):
+        """Diagonal stand-in for a mass matrix (M_sigma of the Schur preconditioner): P1 -> row sums."""
+        return np.asarray(M.sum(axis=1)).ravel()
+
+    def _cK(self, s, k, coef):
+        """Element matrices coef * int c_k grad N_a . grad N_b dx of subdomain s (the c_k-weighted stiffness terms of
+        KNPEMIx_problem.py:599-610): for P1 the cell mean of c_k times the stiffness matrix, exactly."""
+        cbar = self.c[s][k][self.cells_s[s]].mean(axis=1)
+        return coef * cbar[:, None, None] * self.geo[s]["K"]
+
     def _cell_geometry(self, cells):
-        x = self.mesh.x[cells]                                  # (nc, d+1, gdim)
         d = self.mesh.gdim
+        x = self.mesh.x[cells[:, :d + 1]]                       # (nc, d+1, gdim): the cell's vertices come first
         J = np.transpose(x[:, 1:] - x[:, :1], (0, 2, 1))        # columns = edge vectors
         det = np.linalg.det(J)
         vol = np.abs(det) / (2.0 if d == 2 else 6.0)
@@ -194,7 +209,7 @@ class KNPEMIOracle:
         g = np.concatenate([-Jinv.sum(1, keepdims=True), Jinv], 1)   # (nc, d+1, gdim)
         K = vol[:, None, None] * np.einsum("cai,cbi->cab", g, g)
         M = vol[:, None, None] / ((d + 1) * (d + 2)) * (1.0 + np.eye(d + 1))[None]
-        return dict(vol=vol, K=K, M=M)
+        return dict(vol=vol, K=K, M=M, g=g)
 
     def set_initial_conditions(self):
         """ProblemKNPEMI.set_initial_conditions (KNPEMIx_problem.py:326-353,386-447) and
@@ -274,7 +289,7 @@ class KNPEMIOracle:
         """p.stimulus_area = assemble(mask * dS(stimulus_tags)) (KNPEMIx_ionic_model.py:591-601)."""
         m = self.mesh
         sel = np.isin(m.mf_tags, np.asarray(self.p.stimulus_tags))
-        xq = np.einsum("qa,fai->fqi", self.qb, m.x[m.mf_verts[sel]])
+        xq = np.einsum("qa,fai->fqi", self.qb, m.x[m.mf_verts[sel][:, :m.gdim]])
         return float(np.sum(self.farea[sel, None] * self.qw[None, :] * self.stimulus_mask(xq)))
 
     def channel_currents(self, tag, ci, ce, phim, gq, xq, t_mod):
@@ -343,12 +358,12 @@ class KNPEMIOracle:
     def _facet_quadrature_fields(self):
         m = self.mesh
         fv = m.mf_verts
-        qb = self.qb
+        qb = self.qN
         ci = [np.einsum("qa,fa->fq", qb, self.c[0][k][fv]) for k in range(3)]
         ce = [np.einsum("qa,fa->fq", qb, self.c[1][k][fv]) for k in range(3)]
         phim = np.einsum("qa,fa->fq", qb, self.phi_m[fv])
         gq = [np.einsum("qa,fa->fq", qb, self.gates[j][fv]) for j in range(3)]
-        xq = np.einsum("qa,fai->fqi", qb, m.x[fv])
+        xq = np.einsum("qa,fai->fqi", self.qb, m.x[fv[:, :m.gdim]])
         return ci, ce, phim, gq, xq
 
     def facet_tensors(self, t_mod):
@@ -359,7 +374,7 @@ class KNPEMIOracle:
         nf = m.mf_verts.shape[0]
         ci, ce, phim, gq, xq = self._facet_quadrature_fields()
         wq = self.farea[:, None] * self.qw[None, :]                      # (nf, nq)
-        NN = np.einsum("qa,qb->qab", self.qb, self.qb)
+        NN = np.einsum("qa,qb->qab", self.qN, self.qN)
         cs = [ci, ce]
         alpha = []
         for s in range(2):
@@ -375,9 +390,9 @@ class KNPEMIOracle:
         Itot = (I[0] + I[1]) + I[2]
         GA = [[np.einsum("fq,fq,qab->fab", wq, alpha[s][k], NN) for k in range(3)] for s in range(2)]
         G1 = np.einsum("fq,qab->fab", wq, NN)
-        bc = [[np.einsum("fq,fq,qa->fa", wq, (p.dt * I[k] - alpha[s][k] * p.C_M * phim), self.qb) / (p.F * p.z[k])
+        bc = [[np.einsum("fq,fq,qa->fa", wq, (p.dt * I[k] - alpha[s][k] * p.C_M * phim), self.qN) / (p.F * p.z[k])
                for k in range(3)] for s in range(2)]
-        bphi = np.einsum("fq,fq,qa->fa", wq, (p.dt * Itot - p.C_M * phim), self.qb) / p.F
+        bphi = np.einsum("fq,fq,qa->fa", wq, (p.dt * Itot - p.C_M * phim), self.qN) / p.F
         return GA, G1, bc, bphi
 
     def setup_ion_injection(self):
@@ -414,16 +429,15 @@ class KNPEMIOracle:
         for s in range(2):
             cells = self.cells_s[s]
             K, M = self.geo[s]["K"], self.geo[s]["M"]
-            cv = [self.c[s][k][cells] for k in range(3)]                  # (nc, d+1)
-            cbar = [cvk.mean(axis=1) for cvk in cv]
+            cv = [self.c[s][k][cells] for k in range(3)]                  # (nc, dofs per cell)
             Rphi = self.row(s, 3, cells)
             Kphi = np.zeros_like(K)
             for k in range(3):
                 Rk = self.row(s, k, cells)
                 add(Rk[:, :, None], Rk[:, None, :], M + p.dt * p.D[k] * K)
-                add(Rk[:, :, None], Rphi[:, None, :], (p.dt * p.D[k] * p.z[k] / psi) * cbar[k][:, None, None] * K)
+                add(Rk[:, :, None], Rphi[:, None, :], self._cK(s, k, p.dt * p.D[k] * p.z[k] / psi))
                 add(Rphi[:, :, None], Rk[:, None, :], (p.dt * p.z[k] * p.D[k]) * K)
-                Kphi = Kphi + (p.dt * p.D[k] * p.z[k] ** 2 / psi) * cbar[k][:, None, None] * K
+                Kphi = Kphi + self._cK(s, k, p.dt * p.D[k] * p.z[k] ** 2 / psi)
                 np.add.at(b, Rk.ravel(), np.einsum("cab,cb->ca", M, cv[k]).ravel())
                 if s == 1 and self.f_e[k].any():                          # L += dt f_e v dx_e  (KNPEMIx_problem.py:614)
                     np.add.at(b, Rk.ravel(), p.dt * np.einsum("cab,cb->ca", M, self.f_e[k][cells]).ravel())
@@ -466,15 +480,14 @@ class KNPEMIOracle:
         for s in range(2):
             cells = self.cells_s[s]
             K, M = self.geo[s]["K"], self.geo[s]["M"]
-            cbar = [self.c[s][k][cells].mean(axis=1) for k in range(3)]
             Rphi = self.row(s, 3, cells)
             Kphi = np.zeros_like(K)
             for k in range(3):
                 Rk = self.row(s, k, cells)
                 add(Rk[:, :, None], Rk[:, None, :], M + (D_scale * p.dt * p.D[k]) * K)
-                Kphi = Kphi + (D_scale * p.dt * p.D[k] * p.z[k] ** 2 / psi) * cbar[k][:, None, None] * K
+                Kphi = Kphi + self._cK(s, k, D_scale * p.dt * p.D[k] * p.z[k] ** 2 / psi)
             add(Rphi[:, :, None], Rphi[:, None, :], Kphi)
-        NN = np.einsum("qa,qb->qab", self.qb, self.qb)
+        NN = np.einsum("qa,qb->qab", self.qN, self.qN)
         G1 = np.einsum("fq,qab->fab", self.farea[:, None] * self.qw[None, :], NN)
         fv = m.mf_verts
         for s in range(2):

@@ -1,0 +1,68 @@
+"""P2 element path (fem_order = 2) without a GPU: the product's node mesh, dof maps and CSR pattern against the oracle's
+(bit-exact), and one assembly by knp_p2_emulate_host -- the functions the P2 kernels run per thread, called in a loop on the
+CPU -- against the oracle's matrices and vectors (1e-12 relative to the row's largest entry)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle.fixtures import unit_square, unit_cube, from_arrays
+from oracle.knpemi import OracleParams
+from oracle.p2 import KNPEMIOracleP2, p2_mesh
+from conftest import MODELS_TEST, params_struct, perturb
+
+
+def _mesh(kb, name):
+    if name == "square8":
+        return unit_square(8), OracleParams(stimulus_region=(0, 0.2e-6, 0.6e-6))
+    if name == "cube4":
+        return unit_cube(4), OracleParams(stimulus_region=((0, 0.2e-6, 0.8e-6), (2, 0.0, 0.6e-6)))
+    d, n, m = (2, 12, 3) if name == "cells2d" else (3, 6, 2)
+    mm = kb.mesh.cell_array_mesh(d, n, m)
+    it = tuple(mm.intra_tags)
+    return (from_arrays(d, mm.x, mm.cells, mm.cell_tags, mm.intra_tags),
+            OracleParams(intra_tags=it, extra_tag=1, membrane_tags=it, stimulus_tags=(2,)))
+
+
+def _product_node_mesh(kb, om, p):
+    m = kb.mesh.Mesh(om.gdim, om.x, om.cells.astype(np.int32), om.cell_tags.astype(np.int32), tuple(p.intra_tags), p.extra_tag,
+                     om.mf_verts.astype(np.int32), om.mf_tags.astype(np.int32))
+    return kb.mesh.p2_node_mesh(m)
+
+
+def rel_rows(A_ref, vals):
+    scale = np.maximum.reduceat(np.abs(A_ref.data), A_ref.indptr[:-1])
+    return (np.abs(vals - A_ref.data) / np.repeat(scale, np.diff(A_ref.indptr))).max()
+
+
+@pytest.mark.parametrize("name", ["square8", "cube4", "cells2d", "cells3d"])
+def test_p2_node_mesh_pattern_and_emulated_assembly(kb, name):
+    om, p = _mesh(kb, name)
+    m2 = _product_node_mesh(kb, om, p)
+    o2m = p2_mesh(om)
+    assert np.array_equal(m2.x, o2m.x) and np.array_equal(m2.cells, o2m.cells) and np.array_equal(m2.mf_verts, o2m.mf_verts)
+    models = MODELS_TEST
+    o = perturb(KNPEMIOracleP2(o2m, p, models), seed=3)
+    t = 3 * p.dt
+    A, b = o.assemble(t)
+    P = o.assemble_P()
+    qb, qw = kb.mesh.facet_quadrature(om.gdim)
+    args = (om.gdim, m2.x, m2.cells, m2.cell_tags, p.intra_tags, p.extra_tag, m2.mf_verts, m2.mf_tags, qb, qw)
+    ip, ix, vi, ve = kb.lib.pattern_host(*args, degree=2)
+    assert np.array_equal(ip, A.indptr) and np.array_equal(ix, A.indices)
+    assert np.array_equal(vi, o.S[0]) and np.array_equal(ve, o.S[1])
+    Pm, table = params_struct(kb, p, models, stim_area=o.stimulus_area())
+    tm = [kb.lib.TagModels(tg, fl, int(st)) for tg, fl, st in table]
+    ip2, ix2, vals, bv = kb.lib.p2_emulate_host(Pm, tm, t, 0, o.pack(), o.gates[:, o.mverts], *args)
+    assert np.array_equal(ip2, A.indptr) and np.array_equal(ix2, A.indices)
+    assert rel_rows(A, vals) < 1e-12
+    for s in range(2):
+        for f in range(4):
+            sl = slice(o.base[s] + f * o.ns[s], o.base[s] + (f + 1) * o.ns[s])
+            assert np.abs(bv[sl] - b[sl]).max() <= 1e-12 * np.abs(b[sl]).max()
+    pv = kb.lib.p2_emulate_host(Pm, tm, t, 1, o.pack(), None, *args)[:P.nnz]
+    assert rel_rows(P, pv) < 1e-12
+    # the two auxiliary matrices of the Schur preconditioner come from the same rows with modified constants
+    Pm2, _ = params_struct(kb, p, models, stim_area=1.0)
+    Pm2.C_M = -p.C_M
+    pv2 = kb.lib.p2_emulate_host(Pm2, tm, t, 1, o.pack(), None, *args)[:P.nnz]
+    assert rel_rows(o.assemble_P(membrane_sign=+1.0), pv2) < 1e-12
