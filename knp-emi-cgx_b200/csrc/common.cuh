@@ -90,6 +90,7 @@ struct Layout {
 // Host-side tables of the P2 element path (topology_p2.cpp; p2.cuh describes their use)
 struct P2Host {
   int nloc = 0, nt = 0, nqc = 0;
+  double hrz = 0.0;                           // 1 / trace of the reference mass matrix: HRZ lumping factor (Schur preconditioner)
   std::vector<int32_t> adj_ptr, adj_idx;      // per owned node: sorted subdomain-local node ids it shares a cell with (incl. itself)
   std::vector<int32_t> gam_ptr, gam_idx;      // per owned node: local node ids ACROSS the membrane it shares a facet with (sorted)
   std::vector<int32_t> inc_ptr, inc_cell;     // per owned node: incident cells, ascending (subdomain-local cell ids)

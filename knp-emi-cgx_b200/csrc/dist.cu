@@ -513,6 +513,7 @@ int knp_dist_init(knp_ctx* c, int32_t rank, int32_t nranks, const char* unique_i
   c->nranks = nranks;
   c->n_phi_global = n_phi_global;
   if (nranks == 1) return KNP_OK;
+  KNP_CHECK(c->H.degree != 2, "P2 elements run on one GPU");
   KNP_CHECK(unique_id128 && n_peers >= 0 && send_ptr && recv_ptr && (n_peers == 0 || peers), "NULL argument");
   NcclApi* api = nccl_api();
   if (!api) return KNP_E_NCCL;

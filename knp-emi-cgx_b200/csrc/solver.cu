@@ -126,6 +126,7 @@ static bool amg_setup_device_default(const knp_ctx* c) {
   // single-GPU runs build the hierarchy on the device (amg_device.cu: same decisions, bit-identical operators);
   // KNP_AMG_SETUP=host|device overrides, matrices the device form does not take (Dirichlet rows) fall back to the host
   static const char* where = getenv("KNP_AMG_SETUP");
+  if (c->H.degree == 2) return false;       // P2 blocks: host setup (the device form has only been verified on P1 operators)
   return where ? !strcmp(where, "device") : c->nranks == 1;
 }
 
@@ -679,8 +680,11 @@ __global__ void part_fill_kernel(int n, int n0, int n1, int part, const int32_t*
     ov[pos++] = val[j];
   }
 }
-// 1 / (M_sigma): (sum_k z_k^2 c_k / psi) at the node times the row sum of the mass matrix, in the host's operation order
-__global__ void msig_kernel(Layout L, const int32_t* __restrict__ ipP, const double* __restrict__ mval,
+// 1 / (M_sigma): (sum_k z_k^2 c_k / psi) at the node times the lumped mass of the node, in the host's operation order.
+// Lumped mass: the row sum of the mass matrix (P1), or hrz x its diagonal entry (hrz > 0: P2, whose row sums vanish at the
+// vertices in 2D and are negative in 3D -- HRZ lumping keeps the total mass with positive weights)
+__global__ void msig_kernel(Layout L, const int32_t* __restrict__ ipP, const int32_t* __restrict__ ixP,
+                            const double* __restrict__ mval, double hrz,
                             const double* __restrict__ u, double z0, double z1, double z2, double psi, double* __restrict__ out) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int n0 = L.n_own[0], n1 = L.n_own[1];
@@ -688,7 +692,12 @@ __global__ void msig_kernel(Layout L, const int32_t* __restrict__ ipP, const dou
   const int s = t < n0 ? 0 : 1, p = s ? t - n0 : t;
   const int row = L.row(s, 0, p);
   double ms = 0.0;
-  for (int j = ipP[row]; j < ipP[row + 1]; ++j) ms = __dadd_rn(ms, mval[j]);
+  if (hrz > 0.0) {
+    for (int j = ipP[row]; j < ipP[row + 1]; ++j)
+      if (ixP[j] == row) ms = __dmul_rn(hrz, mval[j]);
+  } else {
+    for (int j = ipP[row]; j < ipP[row + 1]; ++j) ms = __dadd_rn(ms, mval[j]);
+  }
   const double z[3] = {z0, z1, z2};
   double sig = 0.0;
 #pragma unroll
@@ -847,11 +856,12 @@ static int schur_setup(knp_ctx* c) {
   // lumped M_sigma = (sum_k z_k^2 c_k / psi) at the node  x  row sum of the mass matrix
   std::vector<double> msig_inv(dev_path ? 0 : (size_t)n0 + n1);
   const double* z = c->kp.z;
+  const double hrz = c->H.degree == 2 ? c->H.p2.hrz : 0.0;        // P2: HRZ lumping (see msig_kernel)
   if (dev_path) {
     KNP_TRY(c->msig_inv.alloc((size_t)n0 + n1));
     if (n0 + n1 > 0) {
-      msig_kernel<<<(n0 + n1 + 255) / 256, 256, 0, st>>>(L, c->d_indptr_P.p, c->M_vals.p, c->u.p, z[0], z[1], z[2], c->kp.psi,
-                                                         c->msig_inv.p);
+      msig_kernel<<<(n0 + n1 + 255) / 256, 256, 0, st>>>(L, c->d_indptr_P.p, c->d_indices_P.p, c->M_vals.p, hrz, c->u.p, z[0],
+                                                         z[1], z[2], c->kp.psi, c->msig_inv.p);
       KNP_LAUNCHED();
     }
   }
@@ -859,7 +869,10 @@ static int schur_setup(knp_ctx* c) {
     for (int p = 0; p < L.n_own[s]; ++p) {
       const int row = L.row(s, 0, p);
       double ms = 0.0;
-      for (int j = ip[row]; j < ip[row + 1]; ++j) ms += mval[j];
+      for (int j = ip[row]; j < ip[row + 1]; ++j) {
+        if (hrz > 0.0) ms = idx[j] == row ? hrz * mval[j] : ms;
+        else ms += mval[j];
+      }
       double sig = 0.0;
       for (int k = 0; k < 3; ++k) sig += z[k] * z[k] / c->kp.psi * u[L.col(s, k, p)];
       msig_inv[(size_t)(s ? n0 : 0) + p] = ms != 0.0 ? 1.0 / (sig * ms) : 0.0;     // empty row: Dirichlet dof

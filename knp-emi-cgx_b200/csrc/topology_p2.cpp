@@ -325,6 +325,12 @@ int build_topology_p2(const knp_mesh_desc* m, HostTopo& T) {
     Q.cq_w[q] = row[nv];
     p2_basis(nv, row, &Q.cq_N[(size_t)q * NL], &Q.cq_dN[(size_t)q * NL * nv]);
   }
+  {
+    double tr = 0.0;
+    for (int q = 0; q < nqc; ++q)
+      for (int a = 0; a < NL; ++a) tr += Q.cq_w[q] * Q.cq_N[(size_t)q * NL + a] * Q.cq_N[(size_t)q * NL + a];
+    Q.hrz = 1.0 / tr;
+  }
   const int nqf = m->n_quad;
   Q.fq_b.assign(m->quad_bary, m->quad_bary + (size_t)nqf * d);
   Q.fq_w.assign(m->quad_w, m->quad_w + nqf);

@@ -61,7 +61,7 @@ class SolveInfo(C.Structure):
 
 # every symbol declared in include/knpemi_b200.h (tests check that the library exports all of them)
 SYMBOLS = [
-    "knp_last_error", "knp_version", "knp_launch_count", "knp_create", "knp_destroy", "knp_get_sizes", "knp_csr_dev", "knp_csr_host",
+    "knp_p2_emulate_host", "knp_last_error", "knp_version", "knp_launch_count", "knp_create", "knp_destroy", "knp_get_sizes", "knp_csr_dev", "knp_csr_host",
     "knp_csr_P_host", "knp_dofmap_host", "knp_mverts_host", "knp_set_params", "knp_stimulus_area_local",
     "knp_set_state", "knp_get_state", "knp_state_dev", "knp_phi_m_host", "knp_gate_step", "knp_assemble",
     "knp_assemble_P", "knp_set_source", "knp_set_dirichlet", "knp_values_dev", "knp_spmv", "knp_pc_setup", "knp_pc_apply", "knp_pc_bytes", "knp_solve", "knp_step",

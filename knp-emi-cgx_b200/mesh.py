@@ -39,6 +39,39 @@ def _local_edges(nv):
     return [(i, j) for i in range(nv) for j in range(i + 1, nv)]
 
 
+def p2_shape(bary):
+    """P2 Lagrange basis on a simplex at barycentric points bary (..., nv): vertex functions lam_a (2 lam_a - 1), then
+    4 lam_i lam_j per edge in the order of _local_edges."""
+    bary = np.asarray(bary, float)
+    nv = bary.shape[-1]
+    return np.concatenate([bary * (2.0 * bary - 1.0)] + [4.0 * bary[..., i:i + 1] * bary[..., j:j + 1] for i, j in _local_edges(nv)],
+                          axis=-1)
+
+
+def reference_mass(d, degree):
+    """int N_a N_b over a d-simplex divided by its measure, exactly (monomial formula int prod lam_i^a_i = d! prod a_i! /
+    (sum a_i + d)!); P1: (1 + delta_ab) / ((d + 1)(d + 2))."""
+    from math import factorial
+    nv = d + 1
+    if degree == 1:
+        return (1.0 + np.eye(nv)) / ((d + 1) * (d + 2))
+    unit = lambda i: tuple(1 if k == i else 0 for k in range(nv))
+    add = lambda a, b: tuple(x + y for x, y in zip(a, b))
+    polys = [{add(unit(a), unit(a)): 2.0, unit(a): -1.0} for a in range(nv)]
+    polys += [{add(unit(i), unit(j)): 4.0} for i, j in _local_edges(nv)]
+
+    def integ(e):
+        num = factorial(d)
+        for a in e:
+            num *= factorial(a)
+        return num / factorial(sum(e) + d)
+    M = np.zeros((len(polys), len(polys)))
+    for a, pa in enumerate(polys):
+        for b, pb in enumerate(polys):
+            M[a, b] = sum(ca * cb * integ(add(ea, eb)) for ea, ca in pa.items() for eb, cb in pb.items())
+    return M
+
+
 def p2_node_mesh(m: "Mesh") -> "Mesh":
     """The nodes of the ("Lagrange", 2) space (fem_order = 2, utils/mixed_dim_problem.py:207-208, KNPEMIx_problem.py:38-42) as
     a mesh the rest of the host code can treat like the P1 one (dof = node): the mesh vertices keep their ids, every edge adds
@@ -68,7 +101,7 @@ def p2_node_mesh(m: "Mesh") -> "Mesh":
         fcols.append(nv + pos[:, None])
     x = np.concatenate([m.x, 0.5 * (m.x[edges[:, 0]] + m.x[edges[:, 1]])], axis=0)
     bc = None
-    if m.bc_verts is not None:          # boundary nodes: the tagged vertices and the edges between two of them that lie on a
+    if m.bc_verts is not None:          # the tagged facets themselves are not kept by the ingest, only their vertices
         raise NotImplementedError("dirichlet_bcs on ingested meshes with fem_order = 2")
     return dataclasses.replace(m, x=x, cells=cell_nodes.astype(np.int32), mf_verts=np.concatenate(fcols, axis=1).astype(np.int32),
                                degree=2, n_vertices=nv, edges=edges.astype(np.int32), bc_verts=bc, grid=None)
@@ -362,6 +395,21 @@ def boundary_vertices(m: Mesh):
     """Vertices of the exterior boundary (the facets mark_boundaries_square / _cube tag PARTIAL_OMEGA, misc.py:139-186):
     by structured index on the generated fixtures (works on a rank's slab through its global vertex ids), otherwise the
     vertices of the facets that belong to exactly one cell of a GLOBAL mesh."""
+    if m.degree == 2:
+        # nodes of the P2 space on the exterior boundary: the vertices AND the edge nodes of the facets that belong to one cell
+        # (an edge between two boundary vertices can cross the interior, so the facets decide)
+        from .xdmf import _entity_keys
+        d, nv = m.gdim, m.n_vertices
+        cv = m.cells[:, :d + 1]
+        fac = np.concatenate([cv[:, [j for j in range(d + 1) if j != i]] for i in range(d + 1)], 0)
+        key, srt, exact = _entity_keys(fac, nv)
+        uk, first, cnt = np.unique(key, return_index=True, return_counts=True)
+        bf = srt[first[cnt == 1]].astype(np.int64)                       # boundary facets (sorted vertex ids)
+        ek = m.edges[:, 0].astype(np.int64) * nv + m.edges[:, 1]
+        nodes = [bf.ravel()]
+        for i, j in _local_edges(d):
+            nodes.append(nv + np.searchsorted(ek, np.minimum(bf[:, i], bf[:, j]) * nv + np.maximum(bf[:, i], bf[:, j])))
+        return np.unique(np.concatenate(nodes)).astype(np.int32)
     if m.grid is not None:
         n = m.grid[0]
         gid = np.arange(m.x.shape[0], dtype=np.int64) if m.vert_global is None else np.asarray(m.vert_global, np.int64)

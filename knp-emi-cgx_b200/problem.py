@@ -333,6 +333,11 @@ class ProblemKNPEMI:
             n = int(mt.group(2))
             m = (_mesh.unit_square_fixture if mt.group(1) == "square" else _mesh.unit_cube_fixture)(
                 n, self.mesh_conversion_factor)
+        if self.fem_order == 2:
+            # ("Lagrange", 2) spaces (KNPEMIx_problem.py:38-42): the host code below works on the nodes of the P2 space
+            if self.comm.size > 1:
+                raise NotImplementedError("fem_order = 2 runs on one GPU")
+            m = _mesh.p2_node_mesh(m)
         if not (all(t < self.extra_tag[0] for t in self.intra_tags) or all(t > self.extra_tag[0] for t in self.intra_tags)):
             raise RuntimeError("Intracellular tags must be all smaller or all larger than extracellular tag.")
         # keep only membrane facets whose tag is listed, check the listed tags exist
@@ -384,10 +389,11 @@ class ProblemKNPEMI:
         self.N_ions = len(self.ion_list)
 
     def setup_spaces(self):
-        """KNPEMIx_problem.py:28-94: P1 space on the whole mesh, 8 fields, restrictions to the vertices of the
-        intracellular / extracellular cells (membrane vertices belong to both)."""
-        if self.fem_order != 1:
-            raise NotImplementedError("fem_order = 2 is not implemented on the B200 path yet (no shipped config uses it)")
+        """KNPEMIx_problem.py:28-94: ("Lagrange", fem_order) space on the whole mesh, 8 fields, restrictions to the dofs of the
+        intracellular / extracellular cells (membrane dofs belong to both).  fem_order = 2: the mesh is the P2 node mesh
+        (mesh.p2_node_mesh; dof = node = vertex or edge midpoint), everything below is written per node."""
+        if self.fem_order not in (1, 2):
+            raise NotImplementedError(f"fem_order = {self.fem_order}: P1 and P2 elements are implemented")
         self._print("Setting up function spaces ...")
         m = self.mesh
         self.num_variables = self.N_ions + 1
@@ -477,8 +483,8 @@ class ProblemKNPEMI:
     injection_current = 5e-9      # [A], KNPEMIx_problem.py:211
 
     def _cell_volumes(self, cells):
-        x = self.mesh.x[cells]
         d = self.mesh.gdim
+        x = self.mesh.x[cells[:, :d + 1]]                  # the vertices come first (P2 node mesh)
         det = np.linalg.det(x[:, 1:] - x[:, :1])
         return np.abs(det) / (2.0 if d == 2 else 6.0)
 
@@ -521,14 +527,15 @@ class ProblemKNPEMI:
         node_of = np.full(m.x.shape[0], -1, np.int64)
         node_of[self._node_vert[1]] = np.arange(self._node_vert[1].size)
         cells = m.cells[m.cell_tags == self.extra_tag[0]]
-        w = self._cell_volumes(cells) / ((d + 1) * (d + 2))
+        vol = self._cell_volumes(cells)
+        Mref = _mesh.reference_mass(d, m.degree)                             # int N_a N_b / |cell|
         rows, vals = [], []
         for k, ion in enumerate(self.ion_list):
             f = ion["f_e"]
             if not isinstance(f, Function) or not f._data.any():
                 continue
-            fc = f._data[cells]                                              # (nc, d+1)
-            contrib = w[:, None] * (fc + fc.sum(axis=1, keepdims=True))     # M_c f = vol/((d+1)(d+2)) (f_p + sum_q f_q)
+            fc = f._data[cells]                                              # (nc, dofs per cell)
+            contrib = vol[:, None] * (fc @ Mref)                            # M_c f  (P1: vol/((d+1)(d+2)) (f_p + sum_q f_q))
             sv = np.bincount(cells.ravel(), weights=contrib.ravel(), minlength=m.x.shape[0]) * float(self.dt.value)
             nodes = node_of[np.flatnonzero(sv)]
             nodes = nodes[(nodes >= 0) & (nodes < lay.n_own[1])]
@@ -712,7 +719,7 @@ class ProblemKNPEMI:
             self.device = int(os.environ.get("LOCAL_RANK", "0"))
         self._ctx = _lib.Context(m.gdim, m.x, m.cells, m.cell_tags, self.intra_tags, self.extra_tag[0], m.mf_verts,
                                  m.mf_tags, qb, qw, n_owned_vertices=m.n_owned, cell_owned=m.cell_owned,
-                                 mfacet_owned=m.mf_owned, device=self.device)
+                                 mfacet_owned=m.mf_owned, device=self.device, degree=m.degree)
         ctx = self._ctx
         self._node_vert = ctx.dofmaps()
         self._mverts = ctx.mverts()
@@ -733,7 +740,7 @@ class ProblemKNPEMI:
         """Index into `cells` of the first cell containing `point` and its barycentric coordinates, or (None, None)."""
         m = self.mesh
         d = m.gdim
-        xc = m.x[cells]                                                    # (nc, d+1, d)
+        xc = m.x[cells[:, :d + 1]]                                         # (nc, d+1, d): the vertices come first
         tol = 1e-9 * float(np.abs(m.x).max())
         cand = np.flatnonzero(np.all(xc.min(1) <= point + tol, axis=1) & np.all(xc.max(1) >= point - tol, axis=1))
         if cand.size == 0:
@@ -781,7 +788,7 @@ class ProblemKNPEMI:
                     if take:
                         nodes = inv[s][m.cells[idx[c]]]
                         cols += [int(v) for v in lay.col(s, f, nodes)]
-                        wts += [float(b) for b in bary]
+                        wts += [float(b) for b in (bary if m.degree == 1 else _mesh.p2_shape(bary))]
                     ptr.append(len(cols))
         if self.gamma_points is not None:
             fowned = np.ones(m.mf_verts.shape[0], bool) if m.mf_owned is None else m.mf_owned.astype(bool)
@@ -789,7 +796,7 @@ class ProblemKNPEMI:
             for pt in self.gamma_points:
                 best, bw = None, None
                 if fidx.size:
-                    xf = m.x[m.mf_verts[fidx]]                             # (nf, d, d): closest point by facet barycentrics
+                    xf = m.x[m.mf_verts[fidx][:, :d]]                      # (nf, d, d): closest point by facet barycentrics
                     E = np.transpose(xf[:, 1:] - xf[:, :1], (0, 2, 1))     # (nf, d, d-1)
                     rhs = (pt[:d] - xf[:, 0])[:, :, None]
                     G = np.transpose(E, (0, 2, 1)) @ E
@@ -806,6 +813,8 @@ class ProblemKNPEMI:
                 found.append(self.comm.allreduce(float(best is not None), op=MPI.MAX) > 0)
                 if take:
                     verts = m.mf_verts[fidx[best]]
+                    if m.degree == 2:
+                        bw = _mesh.p2_shape(bw)                             # trace basis on the facet's 3 / 6 nodes
                     cols += [int(v) for v in lay.col(0, 3, inv[0][verts])] + [int(v) for v in lay.col(1, 3, inv[1][verts])]
                     wts += [float(b) for b in bw] + [-float(b) for b in bw]
                 ptr.append(len(cols))
@@ -949,11 +958,8 @@ class ProblemKNPEMI:
         if m.cell_owned is not None:
             sel &= m.cell_owned.astype(bool)
         cells = m.cells[sel]
-        xx = m.x[cells]
-        d = m.gdim
-        vol = np.abs(np.linalg.det(xx[:, 1:] - xx[:, :1])) / (2.0 if d == 2 else 6.0)
         uc = function._data[cells]
-        return float((vol / ((d + 1) * (d + 2)) * ((uc ** 2).sum(1) + uc.sum(1) ** 2)).sum())
+        return float((self._cell_volumes(cells) * np.einsum("ca,ab,cb->c", uc, _mesh.reference_mass(m.gdim, m.degree), uc)).sum())
 
     def l2_norm(self, function, tags):
         return float(np.sqrt(self.comm.allreduce(self.l2_norm_squared(function, tags), op=MPI.SUM)))

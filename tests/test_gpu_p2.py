@@ -1,0 +1,181 @@
+"""GPU parity tests of the P2 element path (fem_order = 2; run on the B200 box with -m gpu): the CUDA kernels through the C ABI
+against oracle/p2.py on the same inputs.  Tolerances as for P1: CSR structure / dof maps bit-exact, matrix and vector entries
+1e-12 relative to the row's largest entry, norms per timestep 1e-8 relative."""
+import os
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle.fixtures import unit_square, unit_cube, from_arrays
+from oracle.knpemi import OracleParams
+from oracle.p2 import KNPEMIOracleP2, p2_mesh
+from oracle.amg import SchurPC
+from conftest import MODELS_TEST, params_struct, perturb
+
+pytestmark = pytest.mark.gpu
+
+
+def _mesh(kb, name):
+    if name == "square8":
+        return unit_square(8), OracleParams(stimulus_region=(0, 0.2e-6, 0.6e-6))
+    if name == "cube4":
+        return unit_cube(4), OracleParams(stimulus_region=((0, 0.2e-6, 0.8e-6), (2, 0.0, 0.6e-6)))
+    d, n, m = (2, 12, 3) if name == "cells2d" else (3, 6, 2)
+    mm = kb.mesh.cell_array_mesh(d, n, m)
+    it = tuple(mm.intra_tags)
+    return (from_arrays(d, mm.x, mm.cells, mm.cell_tags, mm.intra_tags),
+            OracleParams(intra_tags=it, extra_tag=1, membrane_tags=it, stimulus_tags=(2,)))
+
+
+def make_ctx_p2(kb, o2m, p, models):
+    qb, qw = kb.mesh.facet_quadrature(o2m.gdim)
+    ctx = kb.lib.Context(o2m.gdim, o2m.x, o2m.cells, o2m.cell_tags, p.intra_tags, p.extra_tag, o2m.mf_verts, o2m.mf_tags,
+                         qb, qw, degree=2)
+    P, table = params_struct(kb, p, models)
+    ctx.set_params(P, table)
+    return ctx
+
+
+def rel_rows(A_ref, vals):
+    scale = np.maximum.reduceat(np.abs(A_ref.data), A_ref.indptr[:-1])
+    return (np.abs(vals - A_ref.data) / np.repeat(scale, np.diff(A_ref.indptr))).max()
+
+
+@pytest.mark.parametrize("name", ["square8", "cube4", "cells2d", "cells3d"])
+def test_p2_structure_assembly_and_functionals(kb, name):
+    om, p = _mesh(kb, name)
+    o2m = p2_mesh(om)
+    o = perturb(KNPEMIOracleP2(o2m, p, MODELS_TEST), seed=5)
+    ctx = make_ctx_p2(kb, o2m, p, MODELS_TEST)
+    t = 3 * p.dt
+    A, b = o.assemble(t)
+    P = o.assemble_P()
+    # structure: bit-exact
+    ip, ix = ctx.csr()
+    assert ctx.n_rows == o.n and ctx.nnz == A.nnz
+    assert np.array_equal(ip, A.indptr) and np.array_equal(ix, A.indices)
+    vi, ve = ctx.dofmaps()
+    assert np.array_equal(vi, o.S[0]) and np.array_equal(ve, o.S[1])
+    assert np.array_equal(ctx.mverts(), o.mverts)
+    ipP, ixP = ctx.csr_P()
+    assert np.array_equal(ipP, P.indptr) and np.array_equal(ixP, P.indices)
+    assert abs(ctx.stimulus_area_local() - o.stimulus_area()) <= 1e-13 * o.stimulus_area()
+    # values
+    ctx.set_state(o.pack(), o.gates[:, o.mverts])
+    ctx.assemble(t)
+    ctx.assemble_P()
+    Av, bv, Pv = ctx.values_host()
+    assert rel_rows(A, Av) < 1e-12
+    for s in range(2):
+        for f in range(4):
+            sl = slice(o.base[s] + f * o.ns[s], o.base[s] + (f + 1) * o.ns[s])
+            assert np.abs(bv[sl] - b[sl]).max() <= 1e-12 * np.abs(b[sl]).max()
+    assert rel_rows(P, Pv) < 1e-12
+    # bitwise repeatable (one owner per entry, fixed order)
+    ctx.assemble(t)
+    Av2, bv2, _ = ctx.values_host()
+    assert np.array_equal(Av, Av2) and np.array_equal(bv, bv2)
+    # y = A x with the streaming SpMV on the P2 pattern
+    import torch
+    x = torch.from_numpy(np.random.default_rng(0).standard_normal(o.n)).cuda()
+    y = torch.empty_like(x)
+    ctx.spmv(x.data_ptr(), y.data_ptr())
+    torch.cuda.synchronize()
+    ref = A @ x.cpu().numpy()
+    assert np.abs(y.cpu().numpy() - ref).max() <= 1e-12 * np.abs(ref).max()
+    # functionals
+    itag, etag = list(p.intra_tags), [p.extra_tag]
+    for s, tags in ((0, itag), (1, etag)):
+        for f in range(4):
+            u = o.c[s][f] if f < 3 else o.phi[s]
+            for power in (0, 1, 2):
+                ref = o.integral(u, tags, power)
+                assert abs(ctx.integral(s, f, tags, power) - ref) <= 1e-12 * abs(ref)
+    o._stim_area = o.stimulus_area()
+    ref = o.stimulus_current(t)
+    assert abs(ctx.stimulus_current(t) - ref) <= 1e-11 * abs(ref)
+    ctx.close()
+
+
+P2_CONFIG = """
+problem_type: "KNP-EMI"
+dt: 2.5e-5
+time_steps: 4
+fem_order: 2
+physical_constants: {{T: 300, F: 96485, R: 8.314}}
+C_M: 0.02
+mesh_file: "./input/geometries/{mesh}.xdmf"
+cell_tag_file: "./input/geometries/{mesh}.xdmf"
+facet_tag_file: "./input/geometries/{mesh}_facets.xdmf"
+ics_tags: [1]
+ecs_tags: [2]
+boundary_tags: [3]
+membrane_tags: [4]
+mesh_conversion_factor: 1e-6
+initial_conditions:
+  {{phi_m: -0.070, Na_i: 12, Na_e: 140, K_i: 130, K_e: 4, Cl_i: 5, Cl_e: 125, n: 0.276, m: 0.0379, h: 0.688}}
+stimulus:
+  conductance: {{g_syn_bar: 1.0e-9}}
+  a_syn: 5.0e-4
+  T_stim: 1.0
+  scale: True
+solver:
+  direct: {direct}
+  ksp_settings: {{ksp_rtol: 1.0e-9, ksp_type: gmres, pc_type: hypre, norm_type: preconditioned, non_zero_init_guess: True}}
+  output: {{save_xdmf: False, save_cpoints: False, save_pngs: False, save_dat: False}}
+"""
+
+
+def _problem(kb, tmp_path, mesh, direct):
+    cfg = tmp_path / f"p2_{mesh}_{direct}.yaml"
+    cfg.write_text(P2_CONFIG.format(mesh=mesh, direct=direct))
+    p = kb.ProblemKNPEMI(str(cfg), verbose=False)
+    HH, ATP, NCT = kb.HodgkinHuxley(p), kb.ATPPump(p), kb.NeuronalCotransporters(p)
+    p.set_initial_conditions()
+    p.init_ionic_models([NCT, HH, ATP])
+    p.setup_variational_form()
+    p.solver_config["view_ksp"] = False
+    return p, kb.SolverKNPEMI(p, solver_config=p.solver_config)
+
+
+def _norms_oracle(o):
+    return [o.l2_norm(o.c[sd][f] if f < 3 else o.phi[sd], 1 if sd == 0 else 2) for sd in range(2) for f in range(4)]
+
+
+def _norms_gpu(p):
+    return [p.l2_norm(p.wh[sd][f], 1 if sd == 0 else 2) for sd in range(2) for f in range(4)]
+
+
+@pytest.mark.parametrize("mesh,fixture", [("square16", lambda: unit_square(16)), ("cube4", lambda: unit_cube(4))])
+def test_p2_time_loop_direct_matches_oracle(kb, tmp_path, mesh, fixture):
+    """fem_order: 2 through the reference's class surface, direct-solver mode, against the oracle's sparse LU."""
+    p, s = _problem(kb, tmp_path, mesh, True)
+    assert p.mesh.degree == 2
+    s.solve()
+    o = KNPEMIOracleP2(fixture(), OracleParams(), MODELS_TEST)
+    assert p._ctx.n_rows == o.n
+    o.run(4, "direct")
+    ref, got = _norms_oracle(o), _norms_gpu(p)
+    pot = ref[3]
+    for i, (g, r) in enumerate(zip(got, ref)):
+        scale = r if i % 4 < 3 else max(r, pot)
+        assert abs(g - r) <= 1e-8 * scale, (i, g, r)
+
+
+def test_p2_time_loop_gmres_schur_matches_oracle(kb, tmp_path):
+    """GMRES(30) + charge-conservation Schur preconditioner (HRZ-lumped M_sigma for P2) step by step against the oracle."""
+    p, s = _problem(kb, tmp_path, "square16", False)
+    o = KNPEMIOracleP2(unit_square(16), OracleParams(), MODELS_TEST)
+    pc = SchurPC(o, storage="float32")
+    x = o.pack()
+    s.setup_solver(); p.setup_preconditioner(True); s.ctx.pc_setup(s.opts); s.ctx.set_time(0.0, 0)
+    assert s.opts.pc == 3
+    pot = None
+    for i in range(4):
+        info = s.ctx.step(s.opts); p._mark_device_newer()
+        _, _, x, its = o.step("gmres", pc, 1e-9, x, first=(i == 0))
+        assert abs(info.iterations - its) <= 2, (i, info.iterations, its)
+        ref, got = _norms_oracle(o), _norms_gpu(p)
+        for j, (g, r) in enumerate(zip(got, ref)):
+            scale = r if j % 4 < 3 else max(r, ref[3])
+            assert abs(g - r) <= 1e-8 * scale, (i, j, g, r)

@@ -66,3 +66,50 @@ def test_p2_node_mesh_pattern_and_emulated_assembly(kb, name):
     Pm2.C_M = -p.C_M
     pv2 = kb.lib.p2_emulate_host(Pm2, tm, t, 1, o.pack(), None, *args)[:P.nnz]
     assert rel_rows(o.assemble_P(membrane_sign=+1.0), pv2) < 1e-12
+
+
+def test_p2_boundary_nodes_shape_functions_and_reference_mass(kb):
+    """Boundary nodes of the P2 space (vertices and edge nodes of the exterior facets) and P2 point evaluation."""
+    om = unit_square(8)
+    m = kb.mesh.Mesh(2, om.x, om.cells.astype(np.int32), om.cell_tags.astype(np.int32), (1,), 2, om.mf_verts.astype(np.int32),
+                     om.mf_tags.astype(np.int32))
+    m2 = kb.mesh.p2_node_mesh(m)
+    bn = kb.mesh.boundary_vertices(m2)
+    x = m2.x / 1e-6
+    on = (np.abs(x[:, 0]) < 1e-12) | (np.abs(x[:, 0] - 1) < 1e-12) | (np.abs(x[:, 1]) < 1e-12) | (np.abs(x[:, 1] - 1) < 1e-12)
+    assert np.array_equal(bn, np.flatnonzero(on))
+    # a quadratic field is reproduced exactly by the P2 shape functions at an arbitrary point of a cell
+    c = m2.cells[37]
+    bary = np.array([0.2, 0.5, 0.3])
+    pt = bary @ m2.x[c[:3]]
+    f = lambda y: 1.0 + y[..., 0] * 3e6 + (y[..., 0] * 1e6) ** 2 - 2.0 * (y[..., 0] * 1e6) * (y[..., 1] * 1e6)
+    assert abs(kb.mesh.p2_shape(bary) @ f(m2.x[c]) - f(pt)) < 1e-12
+    # reference mass matrices (exact monomial integrals) against the oracle's quadrature
+    for d in (2, 3):
+        o = KNPEMIOracleP2(unit_square(2) if d == 2 else unit_cube(2), OracleParams(), [("Passive", None)])
+        assert np.abs(kb.mesh.reference_mass(d, 2) - o.Mref).max() < 1e-15
+
+
+
+@pytest.mark.parametrize("case", ["ion_2d", "potential_2d", "ion_3d", "potential_3d"])
+def test_host_amg_setup_on_p2_blocks_matches_oracle(kb, case):
+    """The hierarchy setup the P2 contexts use (amg_setup.cpp on the host) on the ion / potential blocks of the P2 Schur
+    preconditioner against oracle/amg.py level by level (P2 stiffness matrices have positive off-diagonal entries)."""
+    from oracle.amg import SAAMG, SchurPC
+    om, p = (unit_square(16), OracleParams()) if "2d" in case else (unit_cube(6), OracleParams())
+    o = perturb(KNPEMIOracleP2(om, p, MODELS_TEST), seed=4)
+    pc = SchurPC(o, exact=True)
+    Pt = o.assemble_P(membrane_sign=+1.0).tocsr()
+    idx = pc.ic if "ion" in case else pc.ip
+    A = Pt[idx][:, idx].tocsr()
+    ref = SAAMG(A, coarse_size=100)
+    levels = kb.lib.amg_setup_host(A, theta=0.08, coarse_size=100)
+    ref_ops = [lv["A"] for lv in ref.levels] + [ref.Ac]
+    assert [a.shape[0] for a in levels] == [a.shape[0] for a in ref_ops]
+    assert len(levels) >= 2
+    for a, r in zip(levels, ref_ops):
+        dd = (a - r).tocoo()
+        assert dd.nnz == 0 or np.abs(dd.data).max() <= 1e-10 * np.abs(r.data).max()
+    # HRZ-lumped M_sigma is positive on every dof (row sums are not)
+    for s in range(2):
+        assert (pc.msig[s] > 0).all()
