@@ -3,7 +3,12 @@
 //   p2_rows_kernel    one thread per restricted dof: its four matrix rows and right-hand side entries
 //   p2_l2_kernel      int u^power over tagged cells (L2 norms, ion amounts, measures)
 //   p2_stim_kernel    total stimulus current
+#include <cstdlib>
 #include "p2.cuh"
+
+#ifndef P2_DEFAULT_MINB
+#define P2_DEFAULT_MINB 4
+#endif
 
 namespace knp {
 
@@ -16,9 +21,12 @@ __global__ void __launch_bounds__(64) p2_facet_kernel(P2View V, KParams P, const
   if (f < V.n_mf) p2_facet_body<D>(V, P, tag_models, tag_stim, u, gates, stim_fac, fe, f);
 }
 
-template <int D, int MODE>
-__global__ void __launch_bounds__(64) p2_rows_kernel(P2View V, P2Coef C, const double* __restrict__ u,
-                                                     const double* __restrict__ fe, double* vals, double* bvec) {
+// MINB = resident CTAs per SM the register allocation is capped for: 4 leaves 255 registers (the 80 accumulators of a 3D row
+// stay in registers, 8 warps per SM), 6 caps at 168 (12 warps per SM, part of the accumulators in L1-backed local memory);
+// KNP_P2_MINB selects, the default is the faster one measured on B200 (profiles/r02p_p2.md)
+template <int D, int MODE, int MINB>
+__global__ void __launch_bounds__(64, MINB) p2_rows_kernel(P2View V, P2Coef C, const double* __restrict__ u,
+                                                           const double* __restrict__ fe, double* vals, double* bvec) {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w < V.n_work) p2_row_body<D, MODE>(V, C, u, fe, vals, bvec, w);
 }
@@ -81,12 +89,23 @@ int launch_rows_p2(const P2View& V, const KParams& P, int mode, const double* u,
   if (V.n_work == 0) return KNP_OK;
   const P2Coef C = p2_coef(P);
   const int grid = (V.n_work + 63) / 64;
-  if (V.gdim == 2) {
-    if (mode == 0) p2_rows_kernel<2, 0><<<grid, 64, 0, st>>>(V, C, u, fe, vals, b);
-    else p2_rows_kernel<2, 1><<<grid, 64, 0, st>>>(V, C, u, fe, vals, b);
+  static const int minb = getenv("KNP_P2_MINB") ? atoi(getenv("KNP_P2_MINB")) : P2_DEFAULT_MINB;
+  if (minb >= 6) {
+    if (V.gdim == 2) {
+      if (mode == 0) p2_rows_kernel<2, 0, 6><<<grid, 64, 0, st>>>(V, C, u, fe, vals, b);
+      else p2_rows_kernel<2, 1, 6><<<grid, 64, 0, st>>>(V, C, u, fe, vals, b);
+    } else {
+      if (mode == 0) p2_rows_kernel<3, 0, 6><<<grid, 64, 0, st>>>(V, C, u, fe, vals, b);
+      else p2_rows_kernel<3, 1, 6><<<grid, 64, 0, st>>>(V, C, u, fe, vals, b);
+    }
   } else {
-    if (mode == 0) p2_rows_kernel<3, 0><<<grid, 64, 0, st>>>(V, C, u, fe, vals, b);
-    else p2_rows_kernel<3, 1><<<grid, 64, 0, st>>>(V, C, u, fe, vals, b);
+    if (V.gdim == 2) {
+      if (mode == 0) p2_rows_kernel<2, 0, 4><<<grid, 64, 0, st>>>(V, C, u, fe, vals, b);
+      else p2_rows_kernel<2, 1, 4><<<grid, 64, 0, st>>>(V, C, u, fe, vals, b);
+    } else {
+      if (mode == 0) p2_rows_kernel<3, 0, 4><<<grid, 64, 0, st>>>(V, C, u, fe, vals, b);
+      else p2_rows_kernel<3, 1, 4><<<grid, 64, 0, st>>>(V, C, u, fe, vals, b);
+    }
   }
   KNP_LAUNCHED();
   return KNP_OK;

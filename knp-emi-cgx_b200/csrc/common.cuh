@@ -57,7 +57,14 @@ struct DevBuf {
   }
   int upload(const std::vector<T>& h) {
     KNP_TRY(alloc(h.size()));
-    if (!h.empty()) KNP_CUDA(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    if (!h.empty()) {
+      // A synchronous copy from PAGEABLE host memory returns once the data sits in the driver's staging buffer; the DMA into
+      // device memory is ordered on the legacy stream only, and the contexts' streams are non-blocking (no implicit ordering
+      // with it).  Without the second call a kernel launched right after an upload can read the tail of the buffer before it
+      // has landed (seen as a run-to-run varying coarse inverse / float32 operator copy in the host hierarchy setup).
+      KNP_CUDA(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+      KNP_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
+    }
     return KNP_OK;
   }
   void free() {

@@ -340,18 +340,31 @@ KNP_HD void p2_row_body(const P2View& V, const P2Coef& C, const double* u, const
       }
     }
     for (int b = 0; b < NL; ++b) {
+      // the ten entries of column slot[b] are read together before the first one is written back: the loads are independent,
+      // a load after a store to the same array would have to wait for it
       const int sl = slot[b];
+      double* const vcc[3] = {vals + rs[0] + goff + sl, vals + rs[1] + goff + sl, vals + rs[2] + goff + sl};
+      double* const vpp = vals + rs[3] + goff + (MODE == 0 ? 3 * deg : 0) + sl;
+      double occ[3], ocp[3] = {0.0, 0.0, 0.0}, opc[3] = {0.0, 0.0, 0.0};
+      for (int k = 0; k < 3; ++k) {
+        occ[k] = *vcc[k];
+        if (MODE == 0) {
+          ocp[k] = vcc[k][deg];
+          opc[k] = vals[rs[3] + goff + k * deg + sl];
+        }
+      }
+      const double opp = *vpp;
       double pp = 0.0;
       for (int k = 0; k < 3; ++k) {
-        vals[rs[k] + goff + sl] += rM[b] + C.dtD[k] * rK[b];
+        *vcc[k] = occ[k] + (rM[b] + C.dtD[k] * rK[b]);
         pp += C.cpp[k] * rW[k][b];
         if (MODE == 0) {
-          vals[rs[k] + goff + deg + sl] += C.cphi[k] * rW[k][b];
-          vals[rs[3] + goff + k * deg + sl] += C.ck[k] * rK[b];
+          vcc[k][deg] = ocp[k] + C.cphi[k] * rW[k][b];
+          vals[rs[3] + goff + k * deg + sl] = opc[k] + C.ck[k] * rK[b];
           bk[k] += rM[b] * ck[k][b];
         }
       }
-      vals[rs[3] + goff + (MODE == 0 ? 3 * deg : 0) + sl] += pp;
+      *vpp = opp + pp;
     }
   }
   // membrane (dS) terms: KNPEMIx_problem.py:599,604,609-610,637-638,641-642 (P: :737-738)
@@ -367,13 +380,19 @@ KNP_HD void p2_row_body(const P2View& V, const P2Coef& C, const double* u, const
       const double G1 = C.cf * (area * V.fq_M[a * NT + b]);
       if (MODE == 0) {
         const int ab = p2_sym(a, b, NT);
-        for (int k = 0; k < 3; ++k) {
-          const double ga = C.cmz[k] * fe[(size_t)((s * 3 + k) * NSF + ab) * nf + f];
-          vals[rs[k] + goff + deg + so[b]] += ga;
-          vals[rs[k] + gam_ion + sg[b]] -= ga;
+        double ga[3], oo[3], og[3];
+        for (int k = 0; k < 3; ++k) {          // reads first, then the writes (see above)
+          ga[k] = C.cmz[k] * fe[(size_t)((s * 3 + k) * NSF + ab) * nf + f];
+          oo[k] = vals[rs[k] + goff + deg + so[b]];
+          og[k] = vals[rs[k] + gam_ion + sg[b]];
         }
-        vals[rs[3] + goff + 3 * deg + so[b]] += G1;
-        vals[rs[3] + gam_phi + sg[b]] -= G1;
+        const double po = vals[rs[3] + goff + 3 * deg + so[b]], pg = vals[rs[3] + gam_phi + sg[b]];
+        for (int k = 0; k < 3; ++k) {
+          vals[rs[k] + goff + deg + so[b]] = oo[k] + ga[k];
+          vals[rs[k] + gam_ion + sg[b]] = og[k] - ga[k];
+        }
+        vals[rs[3] + goff + 3 * deg + so[b]] = po + G1;
+        vals[rs[3] + gam_phi + sg[b]] = pg - G1;
       } else {
         vals[rs[3] + so[b]] -= G1;
       }

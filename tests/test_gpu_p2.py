@@ -181,3 +181,96 @@ def test_p2_time_loop_gmres_schur_matches_oracle(kb, tmp_path):
         for j, (g, r) in enumerate(zip(got, ref)):
             scale = r if j % 4 < 3 else max(r, ref[3])
             assert abs(g - r) <= 1e-8 * scale, (i, j, g, r)
+
+
+def test_p2_kernels_equal_their_host_emulation_at_scale(kb):
+    """A 3D tissue block with 1.2 M unknowns / 82 M non-zeros (the rows no longer fit the caches, 4 300 CTAs): the kernels against the same
+    per-thread functions run in a loop on the CPU (knp_p2_emulate_host, itself checked against the oracle on the small meshes
+    of tests/test_p2_host.py).  Identical arithmetic up to fused multiply-adds: 1e-13 relative to the row's largest entry."""
+    mm = kb.mesh.cell_array_mesh(3, 32, 4)
+    m2 = kb.mesh.p2_node_mesh(mm)
+    it = tuple(mm.intra_tags)
+    p = OracleParams(intra_tags=it, extra_tag=1, membrane_tags=it, stimulus_tags=(2,), stimulus_region=(0, 0.0, 0.5e-6))
+    qb, qw = kb.mesh.facet_quadrature(3)
+    args = (3, m2.x, m2.cells, m2.cell_tags, it, 1, m2.mf_verts, m2.mf_tags, qb, qw)
+    ctx = kb.lib.Context(*args, degree=2)
+    P, table = params_struct(kb, p, MODELS_TEST)
+    ctx.set_params(P, table)
+    vi, ve = ctx.dofmaps()
+    rng = np.random.default_rng(11)
+    ci, ce = p.c_i_init, p.c_e_init
+    u = np.concatenate([np.full(vi.size, ci[0]), np.full(vi.size, ci[1]), np.full(vi.size, ci[2]), np.full(vi.size, -0.07),
+                        np.full(ve.size, ce[0]), np.full(ve.size, ce[1]), np.full(ve.size, ce[2]), np.zeros(ve.size)])
+    u *= 1 + 0.05 * rng.random(u.size)
+    u[-ve.size:] = 0.002 * rng.standard_normal(ve.size)
+    gates = np.array([[p.n_init], [p.m_init], [p.h_init]]) * (1 + 0.1 * rng.random((3, ctx.n_mverts)))
+    ctx.set_state(u, gates)
+    t = 2 * p.dt
+    ctx.assemble(t)
+    ctx.assemble_P()
+    Av, bv, Pv = ctx.values_host()
+    Pe, tab = params_struct(kb, p, MODELS_TEST, stim_area=ctx.stimulus_area_local())
+    tm = [kb.lib.TagModels(tg, fl, int(st)) for tg, fl, st in tab]
+    ip, ix, vals, b = kb.lib.p2_emulate_host(Pe, tm, t, 0, u, gates, *args)
+    assert ctx.n_rows > 1000000
+    cip, cix = ctx.csr()
+    assert np.array_equal(ip, cip) and np.array_equal(ix, cix)
+    A = sp.csr_matrix((vals, ix, ip), shape=(ctx.n_rows, ctx.n_rows))
+    assert rel_rows(A, Av) < 1e-13
+    assert np.abs(bv - b).max() <= 1e-12 * np.abs(b).max()
+    pv = kb.lib.p2_emulate_host(Pe, tm, t, 1, u, None, *args)[:ctx.nnz_P]
+    ipP, ixP = ctx.csr_P()
+    assert rel_rows(sp.csr_matrix((pv, ixP, ipP), shape=(ctx.n_rows, ctx.n_rows)), Pv) < 1e-13
+    ctx.close()
+
+
+def test_p2_3d_tissue_block_gmres_schur_matches_oracle(kb, tmp_path):
+    """C4 in miniature with P2 elements (3D tissue block, passive membrane, 66 k unknowns: the hierarchies have sparse
+    coarse levels): per-step norms 1e-8 and GMRES iteration counts against the oracle running the same algorithm."""
+    cfg = tmp_path / "p2_c4_mini.yaml"
+    cfg.write_text('''
+problem_type: "KNP-EMI"
+fem_order: 2
+dt: 2.5e-5
+time_steps: 2
+physical_constants: {T: 300, F: 96485, R: 8.314}
+C_M: 0.02
+synthetic_mesh: {kind: cell_array, dim: 3, N: 12, cells_per_dim: 2, fill: 0.5, first_tag: 2, extra_tag: 1}
+ics_tags: !range [2, 10]
+ecs_tags: [1]
+membrane_tags: !range [2, 10]
+mesh_conversion_factor: 1e-6
+initial_conditions:
+  {phi_m: -0.070, Na_i: 12, Na_e: 140, K_i: 130, K_e: 4, Cl_i: 5, Cl_e: 125, n: 0.276, m: 0.0379, h: 0.688}
+solver:
+  direct: False
+  ksp_settings: {ksp_rtol: 1.0e-9, ksp_type: gmres, pc_type: hypre, norm_type: preconditioned, non_zero_init_guess: True}
+  output: {save_xdmf: False, save_cpoints: False, save_pngs: False, save_dat: False}
+''')
+    p = kb.ProblemKNPEMI(str(cfg), verbose=False)
+    p.set_initial_conditions()
+    p.init_ionic_models([kb.PassiveModel(p)])
+    p.setup_variational_form()
+    p.solver_config["view_ksp"] = False
+    s = kb.SolverKNPEMI(p, solver_config=p.solver_config)
+    mm = kb.mesh.cell_array_mesh(3, 12, 2)
+    it = tuple(mm.intra_tags)
+    o = KNPEMIOracleP2(from_arrays(3, mm.x, mm.cells, mm.cell_tags, mm.intra_tags),
+                       OracleParams(intra_tags=it, extra_tag=1, membrane_tags=it, stimulus_tags=(2,)), [("Passive", None)])
+    assert p._ctx.n_rows == o.n
+    pc = SchurPC(o, storage="float32")
+    x = o.pack()
+    s.setup_solver(); p.setup_preconditioner(True); s.ctx.pc_setup(s.opts); s.ctx.set_time(0.0, 0)
+    itags = list(it)
+    for i in range(2):
+        info = s.ctx.step(s.opts); p._mark_device_newer()
+        _, _, x, its = o.step("gmres", pc, 1e-9, x, first=(i == 0))
+        assert abs(info.iterations - its) <= 2, (i, info.iterations, its)
+        for sd in range(2):
+            tags = itags if sd == 0 else [1]
+            pot = o.l2_norm(o.phi[0], itags)
+            for f in range(4):
+                ref = o.l2_norm(o.c[sd][f] if f < 3 else o.phi[sd], tags)
+                got = p.l2_norm(p.wh[sd][f], tags)
+                scale = ref if f < 3 else max(ref, pot)
+                assert abs(got - ref) <= 1e-8 * scale, (i, sd, f, got, ref)
