@@ -516,16 +516,17 @@ class ProblemKNPEMI:
             f._data[verts] = src_term
             ion["f_e"] = f
 
-    def _upload_source(self):
-        """Entries dt * sum_{c in ECS} (M_c f_e)|_p of the right-hand side for the owned extracellular dofs (the local mesh
-        holds every cell that touches an owned vertex)."""
+    def _source_entries(self, node_vert):
+        """(rows, values) of the entries dt * sum_{c in ECS} (M_c f_e)|_p of the right-hand side for the owned extracellular
+        dofs (the local mesh holds every cell that touches an owned vertex); node_vert = the restricted dof maps
+        (knp_dofmap_host).  P1 and P2: M_c = |c| x the reference mass matrix of the element."""
         from .partition import Layout
-        m, ctx = self.mesh, self._ctx
+        m = self.mesh
         d = m.gdim
         n_owned = m.x.shape[0] if m.n_owned is None else m.n_owned
-        lay = Layout(self._node_vert, n_owned)
+        lay = Layout(node_vert, n_owned)
         node_of = np.full(m.x.shape[0], -1, np.int64)
-        node_of[self._node_vert[1]] = np.arange(self._node_vert[1].size)
+        node_of[node_vert[1]] = np.arange(node_vert[1].size)
         cells = m.cells[m.cell_tags == self.extra_tag[0]]
         vol = self._cell_volumes(cells)
         Mref = _mesh.reference_mass(d, m.degree)                             # int N_a N_b / |cell|
@@ -540,9 +541,15 @@ class ProblemKNPEMI:
             nodes = node_of[np.flatnonzero(sv)]
             nodes = nodes[(nodes >= 0) & (nodes < lay.n_own[1])]
             rows.append(lay.col(1, k, nodes))
-            vals.append(sv[self._node_vert[1][nodes]])
-        if rows:
-            ctx.set_source(np.concatenate(rows), np.concatenate(vals))
+            vals.append(sv[node_vert[1][nodes]])
+        if not rows:
+            return np.zeros(0, np.int64), np.zeros(0)
+        return np.concatenate(rows), np.concatenate(vals)
+
+    def _upload_source(self):
+        rows, vals = self._source_entries(self._node_vert)
+        if rows.size:
+            self._ctx.set_source(rows, vals)
 
     # ------------------------------------------------------------------ initial conditions
     def set_initial_conditions(self):

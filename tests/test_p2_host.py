@@ -113,3 +113,62 @@ def test_host_amg_setup_on_p2_blocks_matches_oracle(kb, case):
     # HRZ-lumped M_sigma is positive on every dof (row sums are not)
     for s in range(2):
         assert (pc.msig[s] > 0).all()
+
+
+P2_YAML = """
+problem_type: "KNP-EMI"
+dt: 2.5e-5
+time_steps: 2
+fem_order: 2
+physical_constants: {T: 300, F: 96485, R: 8.314}
+C_M: 0.02
+mesh_file: "./input/geometries/%s.xdmf"
+cell_tag_file: "./input/geometries/%s.xdmf"
+facet_tag_file: "./input/geometries/%s_facets.xdmf"
+ics_tags: [1]
+ecs_tags: [2]
+boundary_tags: [3]
+membrane_tags: [4]
+mesh_conversion_factor: 1e-6
+source_terms: "ion_injection"
+initial_conditions:
+  {phi_m: -0.070, Na_i: 12, Na_e: 140, K_i: 130, K_e: 4, Cl_i: 5, Cl_e: 125, n: 0.276, m: 0.0379, h: 0.688}
+solver:
+  direct: False
+  ksp_settings: {ksp_rtol: 1.0e-9, ksp_type: gmres, pc_type: hypre, norm_type: preconditioned, non_zero_init_guess: True}
+  output: {save_xdmf: False, save_cpoints: False, save_pngs: False, save_dat: False}
+"""
+
+
+@pytest.mark.parametrize("mesh,fixture", [("square16", lambda: unit_square(16)), ("cube10", lambda: unit_cube(10))])
+def test_fem_order_2_host_path_and_ion_injection_source(kb, tmp_path, mesh, fixture):
+    """fem_order: 2 through ProblemKNPEMI on the CPU: node mesh, restrictions and the ion-injection entries of the right-hand
+    side against the oracle; creating the device context without a GPU fails loudly (no CPU fallback)."""
+    cfg = tmp_path / "p2.yaml"
+    cfg.write_text(P2_YAML % (mesh, mesh, mesh))
+    p = kb.ProblemKNPEMI(str(cfg), verbose=False)
+    om = fixture()
+    prm = OracleParams(source_terms="ion_injection", c_i_init=(12.0, 130.0, 5.0), c_e_init=(140.0, 4.0, 125.0))
+    o = KNPEMIOracleP2(om, prm, MODELS_TEST)
+    assert p.mesh.degree == 2 and np.array_equal(p.mesh.cells, o.mesh.cells) and np.array_equal(p.mesh.mf_verts, o.mesh.mf_verts)
+    assert np.array_equal(p.dofs_intra, o.S[0]) and np.array_equal(p.dofs_extra, o.S[1])
+    assert abs(p.injection_volume - o.injection_volume) <= 1e-14 * o.injection_volume
+    # source entries: b with the source minus b without it
+    rows, vals = p._source_entries([o.S[0].astype(np.int32), o.S[1].astype(np.int32)])
+    _, b1 = o.assemble(prm.dt)
+    o0 = KNPEMIOracleP2(om, OracleParams(c_i_init=prm.c_i_init, c_e_init=prm.c_e_init), MODELS_TEST)
+    _, b0 = o0.assemble(prm.dt)
+    ref = b1 - b0
+    got = np.zeros(o.n)
+    got[rows] = vals
+    assert np.abs(got - ref).max() <= 1e-10 * np.abs(ref).max()
+    try:
+        import torch
+        gpu = torch.cuda.is_available()
+    except Exception:
+        gpu = False
+    if not gpu:
+        p.set_initial_conditions()
+        p.init_ionic_models([kb.NeuronalCotransporters(p), kb.HodgkinHuxley(p), kb.ATPPump(p)])
+        with pytest.raises(kb.lib.KnpError):
+            p.setup_variational_form()
