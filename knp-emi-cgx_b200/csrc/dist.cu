@@ -251,6 +251,7 @@ int peer_link_create(knp_ctx* c, const std::vector<int32_t>& peers, const std::v
     KNP_TRY(out.peers.upload(pp));
     KNP_TRY(out.epoch.alloc(np));
     KNP_CUDA(cudaMemset(out.epoch.p, 0, np * sizeof(unsigned long long)));
+    KNP_CUDA(cudaStreamSynchronize(cudaStreamLegacy));    // legacy-stream memset vs the context's non-blocking stream
   }
   out.np = np;
   out.ready = true;
@@ -267,7 +268,8 @@ static int peer_direct_init(knp_ctx* c) {
   // every rank exports its flag arena; a rank that cannot (or does not want to) sends an empty handle
   std::vector<char> mine;
   if (want && c->flag_arena.alloc(2 * (size_t)FLAG_SLOTS) == KNP_OK &&
-      cudaMemset(c->flag_arena.p, 0, 2 * (size_t)FLAG_SLOTS * sizeof(unsigned long long)) == cudaSuccess) {
+      cudaMemset(c->flag_arena.p, 0, 2 * (size_t)FLAG_SLOTS * sizeof(unsigned long long)) == cudaSuccess &&
+      cudaStreamSynchronize(cudaStreamLegacy) == cudaSuccess) {      // the peers write flags as soon as they hold the handle
     cudaIpcMemHandle_t h;
     if (cudaIpcGetMemHandle(&h, c->flag_arena.p) == cudaSuccess) mine.assign((const char*)&h, (const char*)&h + 64);
   }
@@ -317,6 +319,7 @@ static int peer_direct_init(knp_ctx* c) {
   {
     KNP_TRY(c->red_slots.alloc((size_t)R * RED_MAX));
     KNP_CUDA(cudaMemset(c->red_slots.p, 0, (size_t)R * RED_MAX * sizeof(double)));
+    KNP_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
     std::vector<int32_t> peers;
     std::vector<int64_t> sb, sc, off;
     for (int r = 0; r < R; ++r)

@@ -26,6 +26,8 @@ int ensure_workspace(knp_ctx* c, int restart) {
   KNP_CUDA(cudaMemset(c->tmp2.p, 0, c->ldv * sizeof(double)));
   KNP_CUDA(cudaMemset(c->w.p, 0, c->ldv * sizeof(double)));
   KNP_CUDA(cudaMemset(c->tmp.p, 0, c->ldv * sizeof(double)));
+  // device memsets run on the legacy stream, asynchronously to the host and unordered with the context's non-blocking stream
+  KNP_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
   KNP_TRY(c->partial.alloc((size_t)(restart + 2) * RED_BLOCKS));
   KNP_TRY(c->hdev.alloc(restart + 2));
   KNP_TRY(c->ydev.alloc(restart + 2));
@@ -366,6 +368,7 @@ static int prepare_tail(Amg& M, const double* in0, double* out0) {
   if (!M.tail_bar.p) {
     KNP_TRY(M.tail_bar.alloc(2));
     KNP_CUDA(cudaMemset(M.tail_bar.p, 0, 2 * sizeof(unsigned)));
+    KNP_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
   }
   M.tail_nops = (int)ops.size();
   M.fuse_from = from;
@@ -892,6 +895,7 @@ static int schur_setup(knp_ctx* c) {
   KNP_TRY(c->sch_q.alloc(L.n_cols));
   KNP_TRY(c->sch_rhs.alloc(L.n_rows));
   KNP_CUDA(cudaMemset(c->sch_q.p, 0, (size_t)L.n_cols * sizeof(double)));
+  KNP_CUDA(cudaStreamSynchronize(cudaStreamLegacy));      // legacy-stream memset vs the context's non-blocking stream
   tm.lap("lumped mass, row blocks of M, work vectors");
   return KNP_OK;
 }
