@@ -26,4 +26,8 @@ golden matrices / vectors / CSR patterns in the reference, so entry-level parity
 with respect to the real DOLFINx numbering and per-entry values it is PARITY UNPINNED
 (DESIGN.md section 3).  ``oracle/amg.py`` restates the product's OWN preconditioners
 (SA-AMG cycle, charge-conservation Schur form); hypre is not restated.
+
+``oracle/p2.py`` (``fem_order: 2``): PARITY UNPINNED against the reference -- no config, test or golden vector of the
+reference uses order 2.  It is pinned against the pinned P1 restatement instead: the P2 forms must equal the P1 forms on
+the P1 subspace (tests/test_oracle_p2.py), plus exact integrals of the P2 basis and convergence towards a fine P1 solution.
 """
