@@ -441,18 +441,17 @@ class ProblemKNPEMI:
         elif self.pin_ecs_potential:
             self.bcs = ["phi_e pinned at one vertex"]
 
-    def _upload_bcs(self):
-        """Constrained dofs in the column layout (owned and ghost columns of this rank) with their values."""
-        if not self.bcs:
-            return
+    def _bc_entries(self, node_vert, mverts):
+        """Constrained dofs in the column layout (owned and ghost columns of this rank) with their values; node_vert = the
+        restricted dof maps (knp_dofmap_host), mverts = the membrane dofs (knp_mverts_host)."""
         from .partition import Layout
-        m, ctx = self.mesh, self._ctx
+        m = self.mesh
         n_owned = m.x.shape[0] if m.n_owned is None else m.n_owned
-        lay = Layout(self._node_vert, n_owned)
+        lay = Layout(node_vert, n_owned)
         inv = []
         for s in range(2):
             a = np.full(m.x.shape[0], -1, np.int64)
-            a[self._node_vert[s]] = np.arange(self._node_vert[s].size)
+            a[node_vert[s]] = np.arange(node_vert[s].size)
             inv.append(a)
         cols, vals = [], []
         if self.dirichlet_bcs:
@@ -467,7 +466,7 @@ class ProblemKNPEMI:
         else:
             gid = np.arange(m.x.shape[0], dtype=np.int64) if m.vert_global is None else np.asarray(m.vert_global, np.int64)
             ok = inv[1] >= 0
-            ok[self._mverts] = False
+            ok[mverts] = False
             ok[n_owned:] = False
             mine = int(gid[ok].min()) if ok.any() else np.iinfo(np.int64).max
             pin = int(self.comm.allreduce(float(mine), op=MPI.MIN))
@@ -478,7 +477,12 @@ class ProblemKNPEMI:
             cols.append(lay.col(1, self.N_ions, q))
             vals.append(np.zeros(q.size))
             self._print("Phi_e pinned at (vertex, point):", pin, m.x[loc[0]] if loc.size else "")
-        ctx.set_dirichlet(np.concatenate(cols), np.concatenate(vals))
+        return np.concatenate(cols), np.concatenate(vals)
+
+    def _upload_bcs(self):
+        if not self.bcs:
+            return
+        self._ctx.set_dirichlet(*self._bc_entries(self._node_vert, self._mverts))
 
     injection_current = 5e-9      # [A], KNPEMIx_problem.py:211
 

@@ -172,3 +172,27 @@ def test_fem_order_2_host_path_and_ion_injection_source(kb, tmp_path, mesh, fixt
         p.init_ionic_models([kb.NeuronalCotransporters(p), kb.HodgkinHuxley(p), kb.ATPPump(p)])
         with pytest.raises(kb.lib.KnpError):
             p.setup_variational_form()
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_dirichlet_entries_match_the_oracle(kb, tmp_path, order):
+    """dirichlet_bcs through ProblemKNPEMI on the CPU: the constrained columns and values handed to knp_set_dirichlet against
+    the oracle's bc_dofs (P1: boundary vertices; P2: vertices and edge nodes of the exterior facets)."""
+    cfg = tmp_path / "bc.yaml"
+    txt = (P2_YAML % ("square16", "square16", "square16")).replace('source_terms: "ion_injection"', "dirichlet_bcs: True")
+    cfg.write_text(txt.replace("fem_order: 2", f"fem_order: {order}"))
+    p = kb.ProblemKNPEMI(str(cfg), verbose=False)
+    p.set_initial_conditions()            # the boundary values are the initial values of the config
+    om = unit_square(16)
+    mesh = p2_mesh(om) if order == 2 else om
+    bn = kb.mesh.boundary_vertices(p.mesh)
+    from oracle.knpemi import KNPEMIOracle
+    cls = KNPEMIOracleP2 if order == 2 else KNPEMIOracle
+    prm = OracleParams(dirichlet_bcs=True, boundary_verts=tuple(int(v) for v in bn), c_i_init=(12.0, 130.0, 5.0),
+                       c_e_init=(140.0, 4.0, 125.0))
+    o = cls(mesh, prm, MODELS_TEST)
+    idx, g = o.bc_dofs()
+    cols, vals = p._bc_entries([o.S[0].astype(np.int32), o.S[1].astype(np.int32)], o.mverts)
+    order_ = np.argsort(cols)
+    assert np.array_equal(cols[order_], idx) and np.array_equal(vals[order_], g)
+    assert idx.size == 4 * bn.size          # the exterior boundary belongs to the extracellular space only
