@@ -765,18 +765,23 @@ class ProblemKNPEMI:
         return int(cand[ok[0]]), bary[ok[0]]
 
     def _setup_probes(self):
-        """Containing cells and barycentric weights of the probe points (scifem.evaluate_function, KNPEMIx_solver.py:612-643),
+        ptr, cols, wts = self._probe_tables(self._node_vert)
+        self._ctx.probe_setup(ptr, cols if cols else [0], wts if wts else [0.0])
+
+    def _probe_tables(self, node_vert):
+        """Containing cells and shape-function weights of the probe points (scifem.evaluate_function, KNPEMIx_solver.py:612-643),
         found once on the host; the device evaluates the resulting sparse functionals of the state every step.  Output order:
-        [ics point p, variable j] , [ecs point p, variable j] , [gamma point p] (phi_m = phi_i - phi_e on the membrane)."""
+        [ics point p, variable j] , [ecs point p, variable j] , [gamma point p] (phi_m = phi_i - phi_e on the membrane).
+        Returns (ptr, columns in the column layout, weights); node_vert = the restricted dof maps (knp_dofmap_host)."""
         from .partition import Layout
-        m, ctx = self.mesh, self._ctx
+        m = self.mesh
         d = m.gdim
         n_owned = m.x.shape[0] if m.n_owned is None else m.n_owned
-        lay = Layout(self._node_vert, n_owned)
+        lay = Layout(node_vert, n_owned)
         inv = []
         for s in range(2):
             a = np.full(m.x.shape[0], -1, np.int64)
-            a[self._node_vert[s]] = np.arange(self._node_vert[s].size)
+            a[node_vert[s]] = np.arange(node_vert[s].size)
             inv.append(a)
         owned = np.ones(m.cells.shape[0], bool) if m.cell_owned is None else m.cell_owned.astype(bool)
         is_in = np.isin(m.cell_tags, np.asarray(self.intra_tags)) & owned
@@ -832,7 +837,7 @@ class ProblemKNPEMI:
         if not all(found):
             raise RuntimeError("point_evaluation: a probe point lies outside its subdomain (ics_points must be inside "
                                "intracellular cells, ecs_points inside extracellular cells, gamma_points on the membrane)")
-        ctx.probe_setup(ptr, cols if cols else [0], wts if wts else [0.0])
+        return ptr, cols, wts
 
     def evaluate_probes(self):
         """(ics values [variable, point], ecs values [variable, point], gamma values [point]) from the device state."""

@@ -196,3 +196,29 @@ def test_dirichlet_entries_match_the_oracle(kb, tmp_path, order):
     order_ = np.argsort(cols)
     assert np.array_equal(cols[order_], idx) and np.array_equal(vals[order_], g)
     assert idx.size == 4 * bn.size          # the exterior boundary belongs to the extracellular space only
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_probe_tables_reproduce_polynomial_fields(kb, tmp_path, order):
+    """point_evaluation through ProblemKNPEMI on the CPU: the sparse functionals handed to knp_probe_setup evaluate a field of
+    the space exactly (linear for P1, quadratic for P2) at points inside cells and on the membrane."""
+    cfg = tmp_path / "probe.yaml"
+    txt = (P2_YAML % ("square16", "square16", "square16")).replace('source_terms: "ion_injection"', """point_evaluation:
+  ics_points: [[0.43, 0.52], [0.3, 0.7]]
+  ecs_points: [[0.11, 0.93], [0.8, 0.13]]
+  gamma_points: [[0.25, 0.4], [0.6, 0.75]]""")
+    cfg.write_text(txt.replace("fem_order: 2", f"fem_order: {order}"))
+    p = kb.ProblemKNPEMI(str(cfg), verbose=False)
+    om = unit_square(16)
+    o = (KNPEMIOracleP2 if order == 2 else __import__("oracle.knpemi", fromlist=["KNPEMIOracle"]).KNPEMIOracle)(
+        om, OracleParams(), MODELS_TEST)
+    nv = [o.S[0].astype(np.int32), o.S[1].astype(np.int32)]
+    ptr, cols, wts = p._probe_tables(nv)
+    x = p.mesh.x / 1e-6
+    f = (lambda y: 2.0 - y[:, 0] + 3.0 * y[:, 1] + (y[:, 0] ** 2 - 0.5 * y[:, 0] * y[:, 1] if order == 2 else 0.0))
+    # state vector in the column layout: every field carries f (phi_e carries 2 f so that phi_m = phi_i - phi_e = -f)
+    u = np.concatenate([f(x[nv[0]])] * 4 + [f(x[nv[1]])] * 3 + [2.0 * f(x[nv[1]])])
+    vals = np.array([np.dot(wts[ptr[i]:ptr[i + 1]], u[cols[ptr[i]:ptr[i + 1]]]) for i in range(len(ptr) - 1)])
+    pts = np.array([[0.43, 0.52], [0.3, 0.7]]), np.array([[0.11, 0.93], [0.8, 0.13]]), np.array([[0.25, 0.4], [0.6, 0.75]])
+    ref = np.concatenate([np.repeat(f(pts[0]), 4), np.repeat(f(pts[1]), 4) * np.tile([1, 1, 1, 2.0], 2), -f(pts[2])])
+    assert np.abs(vals - ref).max() < 1e-12
