@@ -16,8 +16,12 @@ def _mesh(kb, name):
         return unit_square(8), OracleParams(stimulus_region=(0, 0.2e-6, 0.6e-6))
     if name == "cube4":
         return unit_cube(4), OracleParams(stimulus_region=((0, 0.2e-6, 0.8e-6), (2, 0.0, 0.6e-6)))
-    d, n, m = (2, 12, 3) if name == "cells2d" else (3, 6, 2)
-    mm = kb.mesh.cell_array_mesh(d, n, m)
+    if name == "plates3d":      # BASELINE C5 in miniature: plate-stack cells, every intracellular vertex on the membrane
+        mm = kb.mesh.cell_array_mesh(3, 8, 2, fill=0.75, shape={"plates": True, "thickness": 1, "pitch": 2, "spine": 1})
+    else:
+        d, n, m = (2, 12, 3) if name == "cells2d" else (3, 6, 2)
+        mm = kb.mesh.cell_array_mesh(d, n, m)
+    d = mm.gdim
     it = tuple(mm.intra_tags)
     return (from_arrays(d, mm.x, mm.cells, mm.cell_tags, mm.intra_tags),
             OracleParams(intra_tags=it, extra_tag=1, membrane_tags=it, stimulus_tags=(2,)))
@@ -34,13 +38,16 @@ def rel_rows(A_ref, vals):
     return (np.abs(vals - A_ref.data) / np.repeat(scale, np.diff(A_ref.indptr))).max()
 
 
-@pytest.mark.parametrize("name", ["square8", "cube4", "cells2d", "cells3d"])
-def test_p2_node_mesh_pattern_and_emulated_assembly(kb, name):
+GLIA = [("KirNa", None), ("GlialCT", None), ("Passive", None)]
+
+
+@pytest.mark.parametrize("name,models", [("square8", MODELS_TEST), ("cube4", MODELS_TEST), ("cells2d", MODELS_TEST),
+                                         ("cells3d", MODELS_TEST), ("plates3d", MODELS_TEST), ("square8", GLIA), ("cube4", GLIA)])
+def test_p2_node_mesh_pattern_and_emulated_assembly(kb, name, models):
     om, p = _mesh(kb, name)
     m2 = _product_node_mesh(kb, om, p)
     o2m = p2_mesh(om)
     assert np.array_equal(m2.x, o2m.x) and np.array_equal(m2.cells, o2m.cells) and np.array_equal(m2.mf_verts, o2m.mf_verts)
-    models = MODELS_TEST
     o = perturb(KNPEMIOracleP2(o2m, p, models), seed=3)
     t = 3 * p.dt
     A, b = o.assemble(t)
