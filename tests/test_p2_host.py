@@ -147,28 +147,58 @@ solver:
 """
 
 
-@pytest.mark.parametrize("mesh,fixture", [("square16", lambda: unit_square(16)), ("cube10", lambda: unit_cube(10))])
-def test_fem_order_2_host_path_and_ion_injection_source(kb, tmp_path, mesh, fixture):
-    """fem_order: 2 through ProblemKNPEMI on the CPU: node mesh, restrictions and the ion-injection entries of the right-hand
-    side against the oracle; creating the device context without a GPU fails loudly (no CPU fallback)."""
-    cfg = tmp_path / "p2.yaml"
-    cfg.write_text(P2_YAML % (mesh, mesh, mesh))
+TISSUE_YAML = """
+problem_type: "KNP-EMI"
+dt: 2.5e-5
+time_steps: 2
+fem_order: %d
+physical_constants: {T: 300, F: 96485, R: 8.314}
+C_M: 0.02
+synthetic_mesh: {kind: cell_array, dim: %d, N: %d, cells_per_dim: 2, fill: 0.5, first_tag: 2, extra_tag: 1}
+ics_tags: !range [2, %d]
+ecs_tags: [1]
+membrane_tags: !range [2, %d]
+mesh_conversion_factor: 1e-6
+source_terms: "ion_injection"
+initial_conditions:
+  {phi_m: -0.070, Na_i: 12, Na_e: 140, K_i: 130, K_e: 4, Cl_i: 5, Cl_e: 125, n: 0.276, m: 0.0379, h: 0.688}
+solver:
+  direct: False
+  ksp_settings: {ksp_rtol: 1.0e-9, ksp_type: gmres, pc_type: hypre, norm_type: preconditioned, non_zero_init_guess: True}
+  output: {save_xdmf: False, save_cpoints: False, save_pngs: False, save_dat: False}
+"""
+
+
+@pytest.mark.parametrize("order", [1, 2])
+@pytest.mark.parametrize("dim,n", [(2, 20), (3, 10)])
+def test_host_path_and_ion_injection_source(kb, tmp_path, order, dim, n):
+    """fem_order 1 / 2 through ProblemKNPEMI on the CPU for a tissue block whose centre (the injection site) lies in the
+    extracellular space: node mesh, restrictions and the ion-injection entries of the right-hand side against the oracle;
+    creating the device context without a GPU fails loudly (no CPU fallback)."""
+    ncell = 2 ** dim
+    cfg = tmp_path / "tissue.yaml"
+    cfg.write_text(TISSUE_YAML % (order, dim, n, 2 + ncell, 2 + ncell))
     p = kb.ProblemKNPEMI(str(cfg), verbose=False)
-    om = fixture()
-    prm = OracleParams(source_terms="ion_injection", c_i_init=(12.0, 130.0, 5.0), c_e_init=(140.0, 4.0, 125.0))
-    o = KNPEMIOracleP2(om, prm, MODELS_TEST)
-    assert p.mesh.degree == 2 and np.array_equal(p.mesh.cells, o.mesh.cells) and np.array_equal(p.mesh.mf_verts, o.mesh.mf_verts)
+    mm = kb.mesh.cell_array_mesh(dim, n, 2)
+    it = tuple(mm.intra_tags)
+    om = from_arrays(dim, mm.x, mm.cells, mm.cell_tags, mm.intra_tags)
+    from oracle.knpemi import KNPEMIOracle
+    cls = KNPEMIOracleP2 if order == 2 else KNPEMIOracle
+    kw = dict(intra_tags=it, extra_tag=1, membrane_tags=it, stimulus_tags=(2,), c_i_init=(12.0, 130.0, 5.0), c_e_init=(140.0, 4.0, 125.0))
+    o = cls(om, OracleParams(source_terms="ion_injection", **kw), MODELS_TEST)
+    assert p.mesh.degree == order and np.array_equal(p.mesh.cells, o.mesh.cells) and np.array_equal(p.mesh.mf_verts, o.mesh.mf_verts)
     assert np.array_equal(p.dofs_intra, o.S[0]) and np.array_equal(p.dofs_extra, o.S[1])
     assert abs(p.injection_volume - o.injection_volume) <= 1e-14 * o.injection_volume
     # source entries: b with the source minus b without it
     rows, vals = p._source_entries([o.S[0].astype(np.int32), o.S[1].astype(np.int32)])
-    _, b1 = o.assemble(prm.dt)
-    o0 = KNPEMIOracleP2(om, OracleParams(c_i_init=prm.c_i_init, c_e_init=prm.c_e_init), MODELS_TEST)
-    _, b0 = o0.assemble(prm.dt)
+    _, b1 = o.assemble(2.5e-5)
+    _, b0 = cls(om, OracleParams(**kw), MODELS_TEST).assemble(2.5e-5)
     ref = b1 - b0
+    assert np.abs(ref).max() > 0.0 and rows.size > 0
     got = np.zeros(o.n)
     got[rows] = vals
-    assert np.abs(got - ref).max() <= 1e-10 * np.abs(ref).max()
+    # ref is a difference of right-hand sides that are 1e6 times larger than the source: cancellation limits it to ~1e-9
+    assert np.abs(got - ref).max() <= min(1e-6 * np.abs(ref).max(), 1e-14 * np.abs(b1).max())
     try:
         import torch
         gpu = torch.cuda.is_available()
@@ -229,3 +259,41 @@ def test_probe_tables_reproduce_polynomial_fields(kb, tmp_path, order):
     pts = np.array([[0.43, 0.52], [0.3, 0.7]]), np.array([[0.11, 0.93], [0.8, 0.13]]), np.array([[0.25, 0.4], [0.6, 0.75]])
     ref = np.concatenate([np.repeat(f(pts[0]), 4), np.repeat(f(pts[1]), 4) * np.tile([1, 1, 1, 2.0], 2), -f(pts[2])])
     assert np.abs(vals - ref).max() < 1e-12
+
+
+def test_upload_wrappers_hand_the_tables_to_the_context(kb, tmp_path):
+    """_upload_source / _upload_bcs / _setup_probes with a recording stand-in for the device context (the pure table builders
+    are checked above; this guards the glue that the GPU tests exercise)."""
+    class Recorder:
+        def __init__(self):
+            self.calls = {}
+
+        def __getattr__(self, name):
+            return lambda *a: self.calls.__setitem__(name, a)
+
+    txt = (TISSUE_YAML % (1, 2, 20, 6, 6)) + """
+dirichlet_bcs: True
+boundary_tags: [1]
+point_evaluation:
+  ics_points: [[0.25, 0.26]]
+  ecs_points: [[0.51, 0.52]]
+"""
+    cfg = tmp_path / "glue.yaml"
+    cfg.write_text(txt)
+    p = kb.ProblemKNPEMI(str(cfg), verbose=False)
+    p.set_initial_conditions()
+    from oracle.knpemi import KNPEMIOracle
+    mm = kb.mesh.cell_array_mesh(2, 20, 2)
+    it = tuple(mm.intra_tags)
+    o = KNPEMIOracle(from_arrays(2, mm.x, mm.cells, mm.cell_tags, mm.intra_tags),
+                     OracleParams(intra_tags=it, extra_tag=1, membrane_tags=it, stimulus_tags=(2,)), MODELS_TEST)
+    p._ctx, p._node_vert, p._mverts = Recorder(), [o.S[0].astype(np.int32), o.S[1].astype(np.int32)], o.mverts
+    p._upload_source()
+    p._upload_bcs()
+    p._setup_probes()
+    rows, vals = p._ctx.calls["set_source"]
+    assert rows.size == vals.size > 0
+    cols, g = p._ctx.calls["set_dirichlet"]
+    assert cols.size == g.size == 4 * kb.mesh.boundary_vertices(p.mesh).size
+    ptr, pc, pw = p._ctx.calls["probe_setup"]
+    assert len(ptr) == 1 + 8 and len(pc) == len(pw) == 8 * 3
