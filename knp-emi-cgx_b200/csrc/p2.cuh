@@ -7,7 +7,9 @@
 // ions and the potential), walks the node's incident cells and membrane facets in ascending order and adds each element row
 // at precomputed slots (2 bytes per (node, cell, local dof): the position in the node's sorted adjacency).  Every entry is
 // touched by one thread in a fixed order: no atomics, bitwise reproducible.  This is the plain owner-computes form, not a
-// tuned one -- no shipped configuration of the reference uses order 2 and BASELINE.json benchmarks none.
+// tuned one -- no shipped configuration of the reference uses order 2 and BASELINE.json benchmarks none.  Measured on B200
+// (profiles/r02p_p2.md): 2.65 ms for 4.27 M unknowns in 2D, 4.05 ms for 1.20 M unknowns in 3D; the rows of the resident
+// threads exceed the L2, so the kernel is bound by the latency of the read-modify-write of its own rows.
 //
 // The bodies are __host__ __device__: the kernels in assembly_p2.cu call them per thread, and knp_p2_emulate_host (api.cu)
 // calls the same functions in a loop on the CPU so that the test tier without a GPU checks the tables and the element math
